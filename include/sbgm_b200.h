@@ -1,0 +1,189 @@
+/* sbgm_b200.h -- C ABI of the B200-native (sm_100a) kernels behind the SBGM_DANRA hot path.
+ *
+ * The reference (TheaQG/SBGM_DANRA) has no FFI of its own: its hot path is three Python files
+ * whose arithmetic is library calls (cuDNN / cuBLAS / ATen).  Every entry point below replaces
+ * one of those call sites; the reference location is cited per function as file:line relative
+ * to the reference root.  The host side (sbgm_danra_b200/*.py) mirrors the reference's Python
+ * API and reaches these symbols through ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; `stream` is a cudaStream_t
+ *   - all functions are asynchronous on `stream` and return 0 on success, non-zero on failure
+ *     (sbgm_last_error() gives the message); nothing here falls back to the CPU
+ *   - activations are NHWC ("pixels x channels"), C % 8 == 0, in one of three storage formats:
+ *       SBGM_FMT_F32     float32
+ *       SBGM_FMT_BF16    bfloat16
+ *       SBGM_FMT_BF16X2  two bfloat16 planes hi|lo with x ~= hi + lo (16 significant bits);
+ *                        the lo plane starts `plane` elements after the hi plane.  Tensor-core
+ *                        products use hi*hi + lo*hi + hi*lo, i.e. fp32-class accuracy at
+ *                        bf16 tensor throughput / 3.
+ *   - `plane` arguments are the hi->lo plane distance in elements (ignored unless BF16X2)
+ */
+#ifndef SBGM_B200_H_
+#define SBGM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SBGM_FMT_F32 = 0, SBGM_FMT_BF16 = 1, SBGM_FMT_BF16X2 = 2 };
+enum { SBGM_ACT_NONE = 0, SBGM_ACT_RELU = 1, SBGM_ACT_SILU = 2, SBGM_ACT_GELU = 3 };
+
+const char* sbgm_last_error(void);
+int sbgm_version(void);
+/* 1 if the current device is compute capability 10.x (tcgen05 / TMEM / TMA present). */
+int sbgm_device_is_sm100(void);
+
+/* ---- layout / format ------------------------------------------------------------------- */
+/* NCHW fp32 (the reference's tensor layout, score_unet.py:247-364) -> NHWC `fmt`, and back.  */
+int sbgm_nchw_to_nhwc(const float* src, void* dst, size_t dst_plane, int fmt, int n, int c, int h, int w, void* stream);
+int sbgm_nhwc_to_nchw(const void* src, size_t src_plane, int fmt, float* dst, int n, int c, int h, int w, void* stream);
+/* fp32 <-> fmt on a flat buffer of `count` elements (count % 8 == 0); used to pack weights.   */
+int sbgm_convert(const void* src, size_t src_plane, int src_fmt, void* dst, size_t dst_plane, int dst_fmt,
+                 size_t count, void* stream);
+
+/* ---- time embedding + projections -------------------------------------------------------
+ * SinusoidalEmbedding.forward (score_unet.py:41-45), label embedding add (:307-308) and the nine
+ * SiLU->Linear time projections (Encoder :373-383 used at :314-357; DecoderBlock :501-504,:609).
+ *   t                            time of row r = t[r * t_row_stride + step * t_step_stride], where
+ *                                step = *step_counter (0 if step_counter is NULL).  A sampler passes its
+ *                                step table with t_row_stride = 0, t_step_stride = SBGM_STEP_COLS.
+ *   y[rows] or NULL              class label per row (int64), added to embedding set 0 only
+ *   fourier_w[n_sets][te/2]      the Gaussian-Fourier W buffers (set 0 = encoder, 1.. = decoder blocks)
+ *   label_emb[n_cls+1][te]       or NULL
+ *   proj_w[c_total][te], proj_b[c_total], proj_set[c_total] (which W set feeds output channel c)
+ *   out[rows][c_total]           fp32
+ */
+int sbgm_time_embed_project(const float* t, int t_row_stride, int t_step_stride, const int32_t* step_counter,
+                            const int64_t* y, const float* fourier_w, int n_sets, int te,
+                            const float* label_emb, const float* proj_w, const float* proj_b,
+                            const int32_t* proj_set, int c_total, float* out, int rows, void* stream);
+
+/* SinusoidalEmbedding.forward alone (score_unet.py:41-45): out[rows][2*half] = cat(sin, cos)(2 pi t W). */
+int sbgm_fourier_embed(const float* t, const float* fourier_w, int half, float* out, int rows, void* stream);
+
+/* ---- stem convolution (Encoder.conv1, score_unet.py:206-211,:312-315) ---------------------
+ * 8x8 stride-2 pad-3 convolution over the virtual channel concat  x || planes  (:273-291) for
+ * the input-channel range [c_begin, c_end), CUDA cores (K is tiny and the op is bandwidth bound).
+ *   x[n][h][w]              channel 0 (the noisy HR field), may be NULL if c_begin > 0
+ *   planes[np][cc][h][w]    NCHW conditioning channels 1..cc; np == 1 broadcasts over the batch
+ *   w_packed[cin][64 taps][64]  fp32, tap-major (see pack_stem_weight in engine.py)
+ *   addend[na][h/2][w/2][64] fp32 NHWC partial sums or NULL (na == 1 broadcasts)
+ *   tproj[n][tproj_stride]  fp32 time projection added per (n, channel) or NULL
+ *   out                     NHWC `fmt` [n][h/2][w/2][64]
+ */
+int sbgm_stem_conv(const float* x, const float* planes, int np, int cc, int c_begin, int c_end,
+                   const float* w_packed, const float* addend, int na, const float* tproj, int tproj_stride,
+                   void* out, size_t out_plane, int fmt, int n, int h, int w, void* stream);
+
+/* ---- convolution as implicit GEMM -------------------------------------------------------
+ * Replaces nn.Conv2d at every 3x3 / 1x1 / 8x8 site of the UNet (encoder BasicBlocks via
+ * torchvision resnet.py:89-103, Encoder.conv2 score_unet.py:214-219, DecoderBlock.conv_up/conv
+ * :472-489) and nn.Linear inside ImageSelfAttention (:112-148; a Linear is a 1x1 convolution
+ * over tokens).  Epilogue order:  v = acc + bias[co];  v += residual[pix][co];  v = act(v);
+ * v += tproj[n][co].
+ *   in  [n][h][w][cin]   NHWC `fmt`;   out [n][ho][wo][cout] NHWC `fmt`
+ *   weight: packed [planes][cout][kh*kw*cin] (K-major, k = (r*kw + s)*cin + ci), same fmt as `in`
+ *           for the tensor-core path; fp32 [kh*kw*cin][cout] for the SIMT path.
+ * sbgm_conv2d_tc   tcgen05.mma + TMEM accumulators + TMA (BF16 / BF16X2; cin % 64 == 0, cout % 64 == 0)
+ * sbgm_conv2d_simt fp32 CUDA-core implicit GEMM (F32; exact-arithmetic mode and debugging aid)
+ */
+int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                   const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
+                   void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
+                   int kh, int kw, int stride, int pad, int act, void* stream);
+int sbgm_conv2d_simt(const float* in, const float* weight, const float* bias, const float* residual,
+                     const float* tproj, int tproj_stride, float* out, int n, int h, int w, int cin, int cout,
+                     int kh, int kw, int stride, int pad, int act, void* stream);
+
+/* ---- normalisation ------------------------------------------------------------------------
+ * GroupNorm / InstanceNorm of the decoder (score_unet.py:483-487, :582-590) fused with the
+ * skip add, time-projection add and activation that follow norm2 (:593-613):
+ *   y = act( (x - mean_g) * rstd_g * gamma[c] + beta[c] + skip[pix][c] + tproj[n][c] )
+ * gamma/beta NULL = no affine (InstanceNorm2d); groups == c gives instance norm.
+ * `partials` is scratch of sbgm_groupnorm_scratch_floats(n, c, h*w) floats.
+ */
+size_t sbgm_groupnorm_scratch_floats(int n, int c, int hw);
+int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const float* beta, int groups, float eps,
+                   const void* skip, size_t skip_plane, const float* tproj, int tproj_stride, int act,
+                   void* y, size_t y_plane, int fmt, int n, int hw, int c, float* partials, void* stream);
+/* LayerNorm over the channel axis of [rows][c] tokens (ImageSelfAttention.ln1/ln2, :127-128). */
+int sbgm_layernorm(const void* x, size_t x_plane, const float* gamma, const float* beta, float eps,
+                   void* y, size_t y_plane, int fmt, int rows, int c, void* stream);
+
+/* ---- bilinear x2 upsample (nn.Upsample(scale_factor=2, bilinear, align_corners=False),
+ *      score_unet.py:467, :583) --------------------------------------------------------------- */
+int sbgm_upsample2x(const void* x, size_t x_plane, void* y, size_t y_plane, int fmt, int n, int h, int w, int c,
+                    void* stream);
+
+/* ---- multi-head self-attention core (nn.MultiheadAttention inside ImageSelfAttention,
+ *      score_unet.py:124,:141): out = softmax(Q K^T / sqrt(d)) V per head, from the packed
+ *      in_proj output qkv[b][s][3c] (q | k | v), d = c / heads.  out[b][s][c]. ---------------- */
+int sbgm_attention(const void* qkv, size_t qkv_plane, void* out, size_t out_plane, int fmt,
+                   int b, int s, int c, int heads, void* stream);
+
+/* ---- final convolution (Decoder.final_layer.conv, score_unet.py:713-730) fused with the
+ *      division by the marginal std (ScoreNet.forward :876-877):
+ *      out[n][co][h][w] = (conv3x3(in)[co] + bias[co]) * s_n             (NCHW fp32, cout <= 4)
+ *      s_n = inv_std[n * inv_std_stride + step * inv_std_step_stride], step = *step_counter (0 if NULL);
+ *      inv_std NULL = no scaling.  weight fp32 [cout][9][cin]. --------------------------------- */
+int sbgm_final_conv(const void* in, size_t in_plane, int fmt, const float* weight, const float* bias,
+                    const float* inv_std, int inv_std_stride, int inv_std_step_stride, const int32_t* step_counter,
+                    float* out, int n, int h, int w, int cin, int cout, void* stream);
+
+/* ---- counter-based noise + fused sampler updates -------------------------------------------
+ * Noise stream: Philox4x32-10, key = seed, counter = (elem/4, draw); see oracle/philox_ref.py
+ * for the exact definition (the oracle restates it in numpy).  `first_elem` is the index of
+ * out[0] in the *global* [members][1][h][w] ensemble, so sharded ensembles are reproducible.
+ */
+int sbgm_philox_normal(float* out, size_t count, uint64_t seed, uint32_t draw, uint64_t first_elem, void* stream);
+int sbgm_philox_uniform(float* out, size_t count, uint64_t seed, uint32_t draw, uint64_t first_elem, void* stream);
+
+/* Per-step scalar table, one row of SBGM_STEP_COLS floats per sampler step (built on the host
+ * with the reference's own arithmetic, score_sampling.py:96-103,169-176):
+ *   [0] t   [1] g = sigma^t   [2] dt   [3] 1/std(t)   [4] g*g*dt   [5] noise scale
+ *   (EM: sqrt(dt)*g, :125; PC predictor: sqrt(g*g*dt), :227)   [6..7] reserved
+ * `step_counter` points at TWO device int32, zero-initialised by the caller: [0] is the current
+ * step, [1] is scratch (block-arrival count).  Kernels read row step_counter[0]; the predictor /
+ * EM update increments it when its last block retires, which is what lets the whole step loop
+ * replay as one CUDA graph with frozen kernel arguments.
+ */
+#define SBGM_STEP_COLS 8
+/* x0 = z * std(1)  (score_sampling.py:93-95 / :167-168) */
+int sbgm_sampler_init(float* x, size_t count, float std1, uint64_t seed, uint64_t first_elem, void* stream);
+/* Euler-Maruyama / PC predictor update (score_sampling.py:124-125, :224-227):
+ *   mean = x + (g*g*dt) * score ;  x = mean + noise_scale * z ;  ++*step_counter
+ * draw id = draw_base + draw_stride * step.  `mean_out` receives `mean` (always written). */
+int sbgm_sampler_predictor(float* x, const float* score, float* mean_out, size_t count, const float* step_table,
+                           int32_t* step_counter, uint64_t seed, uint32_t draw_base, uint32_t draw_stride,
+                           uint64_t first_elem, void* stream);
+/* per-member sum of squares of `score` -> sumsq[members] (PC corrector, score_sampling.py:201) */
+int sbgm_sampler_sumsq(const float* score, float* sumsq, int members, int per_member, void* stream);
+/* Langevin corrector (score_sampling.py:198-204):  grad_norm = mean_b sqrt(sumsq[b]) over
+ * `members_total` members (sumsq already holds every member of the global ensemble);
+ *   eps = 2 (snr sqrt(per_member) / grad_norm)^2 ;  x += eps * score + sqrt(2 eps) * z          */
+int sbgm_sampler_corrector(float* x, const float* score, const float* sumsq, int members_total, int per_member,
+                           float snr, size_t count, const int32_t* step_counter, uint64_t seed,
+                           uint32_t draw_base, uint32_t draw_stride, uint64_t first_elem, void* stream);
+/* classifier-free guidance combine (guided_score_fn, score_sampling.py:54): out = (1+scale) s_c - scale s_u */
+int sbgm_cfg_combine(const float* s_cond, const float* s_uncond, float scale, float* out, size_t count, void* stream);
+/* copy row *step_counter of table[steps][cols] to out[cols] (time projections of the step) */
+int sbgm_select_step_row(const float* table, int cols, const int32_t* step_counter, float* out, void* stream);
+
+/* ---- DSM loss (loss_fn, score_unet.py:936-985) -------------------------------------------
+ * perturb: x_t = x + std[n] * z, z from the Philox stream (draw id `draw`), also stores z.
+ * loss:    loss = 1/n * sum_{n,pix} w * (score * std[n] + z)^2, w = 0.5 sigmoid(sdf) + 0.5 or 1;
+ *          two-stage deterministic reduction; `partials` has sbgm_dsm_scratch_floats(count) floats. */
+int sbgm_dsm_perturb(const float* x, const float* std, float* xt, float* z, int n, int per_member, uint64_t seed,
+                     uint32_t draw, uint64_t first_elem, void* stream);
+size_t sbgm_dsm_scratch_floats(size_t count);
+int sbgm_dsm_loss(const float* score, const float* std, const float* z, const float* sdf, int n, int per_member,
+                  float* partials, float* loss_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBGM_B200_H_ */

@@ -1,0 +1,474 @@
+"""Kernel-level execution engine for the score-UNet: weight packing + the launch sequence.
+
+The engine owns *derived* copies of the module parameters (NHWC / K-major, BatchNorm folded,
+bf16 or split-bf16) and sequences the C-ABI kernels of `include/sbgm_b200.h` for one forward pass
+(reference: Encoder.forward sbgm/score_unet.py:247-364, DecoderBlock.forward :559-627,
+Decoder.forward :733-758, ScoreNet.forward :829-879).  torch is used for device memory and
+streams only; every FLOP on the path runs in this repo's kernels.
+
+Precisions
+    "fp32"    exact fp32 arithmetic on CUDA cores (debug / strict-parity mode)
+    "bf16x3"  tensor cores, split-bf16 operands (hi*hi + lo*hi + hi*lo), fp32 accumulate:
+              fp32-class accuracy; this is the "fp32/TF32 mode" of the north star (plain TF32
+              sits on the 1e-3 parity gate)
+    "bf16"    tensor cores, bf16 operands, fp32 accumulate
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, FMT_BF16, FMT_BF16X2, FMT_F32, call
+
+PRECISIONS = {"fp32": FMT_F32, "bf16x3": FMT_BF16X2, "bf16": FMT_BF16}
+ACTS = {"relu": ACT_RELU, "silu": ACT_SILU, "gelu": ACT_GELU, "identity": ACT_NONE, None: ACT_NONE}
+FMAP_CHANNELS = (64, 64, 128, 256, 512)
+BN_EPS = 1e-5
+GN_EPS = 1e-5
+LN_EPS = 1e-5
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Act:
+    """An NHWC activation tensor in one of the three storage formats."""
+    __slots__ = ("buf", "fmt", "n", "h", "w", "c")
+
+    def __init__(self, fmt: int, n: int, h: int, w: int, c: int, device) -> None:
+        self.fmt, self.n, self.h, self.w, self.c = fmt, n, h, w, c
+        if fmt == FMT_F32:
+            self.buf = torch.empty((n, h, w, c), dtype=torch.float32, device=device)
+        elif fmt == FMT_BF16:
+            self.buf = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+        else:
+            self.buf = torch.empty((2, n, h, w, c), dtype=torch.bfloat16, device=device)
+
+    @property
+    def plane(self) -> int:
+        return self.n * self.h * self.w * self.c
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def tokens(self) -> "Act":
+        """View [n, h, w, c] as a token matrix [1, 1, n*h*w, c] (no copy)."""
+        v = Act.__new__(Act)
+        v.buf, v.fmt, v.n, v.h, v.w, v.c = self.buf, self.fmt, 1, 1, self.n * self.h * self.w, self.c
+        return v
+
+    def like(self, c: Optional[int] = None, h: Optional[int] = None, w: Optional[int] = None) -> "Act":
+        return Act(self.fmt, self.n, h or self.h, w or self.w, c or self.c, self.buf.device)
+
+    def to_nchw(self) -> torch.Tensor:
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
+        call("sbgm_nhwc_to_nchw", self.ptr, self.plane, self.fmt, out.data_ptr(), self.n, self.c, self.h, self.w, _stream())
+        return out
+
+    @staticmethod
+    def from_nchw(x: torch.Tensor, fmt: int) -> "Act":
+        x = x.contiguous().float()
+        n, c, h, w = x.shape
+        a = Act(fmt, n, h, w, c, x.device)
+        call("sbgm_nchw_to_nhwc", x.data_ptr(), a.ptr, a.plane, fmt, n, c, h, w, _stream())
+        return a
+
+
+@dataclass
+class ConvW:
+    """A packed convolution / linear weight (+ folded bias)."""
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]
+    cin: int
+    cout: int
+    kh: int
+    kw: int
+
+    @property
+    def plane(self) -> int:
+        return self.cout * self.kh * self.kw * self.cin
+
+
+def _split_bf16(x: torch.Tensor) -> torch.Tensor:
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+class _Packer:
+    def __init__(self, sd: Dict[str, torch.Tensor], fmt: int, device) -> None:
+        self.sd, self.fmt, self.device = sd, fmt, device
+
+    def get(self, key: str) -> torch.Tensor:
+        return self.sd[key].detach().to(device=self.device, dtype=torch.float32)
+
+    def vec(self, key: str) -> torch.Tensor:
+        return self.get(key).contiguous()
+
+    def conv(self, wkey: str, bias_key: Optional[str] = None, bn: Optional[str] = None) -> ConvW:
+        w = self.get(wkey)
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        cout, cin, kh, kw = w.shape
+        bias = self.get(bias_key) if bias_key is not None else None
+        if bn is not None:   # eval-mode BatchNorm folded into the convolution
+            scale = self.get(f"{bn}.weight") / torch.sqrt(self.get(f"{bn}.running_var") + BN_EPS)
+            shift = self.get(f"{bn}.bias") - self.get(f"{bn}.running_mean") * scale
+            w = w * scale[:, None, None, None]
+            bias = shift if bias is None else bias * scale + shift
+        if self.fmt == FMT_F32:
+            packed = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()      # [K][cout]
+        else:
+            km = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).contiguous()           # [cout][K]
+            packed = km.to(torch.bfloat16) if self.fmt == FMT_BF16 else _split_bf16(km)
+        return ConvW(packed, None if bias is None else bias.contiguous(), cin, cout, kh, kw)
+
+
+class Kernels:
+    """Thin typed wrappers over the C ABI operating on `Act` tensors."""
+
+    def __init__(self, fmt: int, device) -> None:
+        self.fmt, self.device = fmt, device
+        self._gn_scratch: Optional[torch.Tensor] = None
+
+    def conv(self, x: Act, cw: ConvW, stride: int = 1, pad: int = 0, act: int = ACT_NONE,
+             residual: Optional[Act] = None, tproj: Optional[torch.Tensor] = None) -> Act:
+        assert x.c == cw.cin, f"conv: input has {x.c} channels, weight expects {cw.cin}"
+        ho = (x.h + 2 * pad - cw.kh) // stride + 1
+        wo = (x.w + 2 * pad - cw.kw) // stride + 1
+        out = Act(self.fmt, x.n, ho, wo, cw.cout, self.device)
+        tp_ptr = _ptr(tproj)
+        tp_stride = tproj.stride(0) if tproj is not None else 0
+        if self.fmt == FMT_F32:
+            call("sbgm_conv2d_simt", x.ptr, cw.w.data_ptr(), _ptr(cw.bias), None if residual is None else residual.ptr,
+                 tp_ptr, tp_stride, out.ptr, x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw, stride, pad, act, _stream())
+        else:
+            call("sbgm_conv2d_tc", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias),
+                 None if residual is None else residual.ptr, 0 if residual is None else residual.plane,
+                 tp_ptr, tp_stride, out.ptr, out.plane, self.fmt, x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw,
+                 stride, pad, act, _stream())
+        return out
+
+    def linear(self, x: Act, cw: ConvW, act: int = ACT_NONE, residual: Optional[Act] = None) -> Act:
+        return self.conv(x, cw, 1, 0, act, residual)
+
+    def groupnorm(self, x: Act, gamma, beta, groups: int, act: int = ACT_NONE, skip: Optional[Act] = None,
+                  tproj: Optional[torch.Tensor] = None) -> Act:
+        need = _lib.query("sbgm_groupnorm_scratch_floats", x.n, x.c, x.h * x.w)
+        if self._gn_scratch is None or self._gn_scratch.numel() < need:
+            self._gn_scratch = torch.empty(need, dtype=torch.float32, device=self.device)
+        out = x.like()
+        call("sbgm_groupnorm", x.ptr, x.plane, _ptr(gamma), _ptr(beta), groups, GN_EPS,
+             None if skip is None else skip.ptr, 0 if skip is None else skip.plane,
+             _ptr(tproj), tproj.stride(0) if tproj is not None else 0, act, out.ptr, out.plane, self.fmt,
+             x.n, x.h * x.w, x.c, self._gn_scratch.data_ptr(), _stream())
+        return out
+
+    def layernorm(self, x: Act, gamma, beta) -> Act:
+        out = x.like()
+        rows = x.n * x.h * x.w
+        call("sbgm_layernorm", x.ptr, x.plane, gamma.data_ptr(), beta.data_ptr(), LN_EPS, out.ptr, out.plane, self.fmt,
+             rows, x.c, _stream())
+        return out
+
+    def upsample2x(self, x: Act) -> Act:
+        out = x.like(h=2 * x.h, w=2 * x.w)
+        call("sbgm_upsample2x", x.ptr, x.plane, out.ptr, out.plane, self.fmt, x.n, x.h, x.w, x.c, _stream())
+        return out
+
+    def attention_core(self, qkv: Act, b: int, s: int, c: int, heads: int) -> Act:
+        out = Act(self.fmt, 1, 1, b * s, c, self.device)
+        call("sbgm_attention", qkv.ptr, qkv.plane, out.ptr, out.plane, self.fmt, b, s, c, heads, _stream())
+        return out
+
+
+class AttentionW:
+    def __init__(self, pk: _Packer, prefix: str, heads: int) -> None:
+        self.heads = heads
+        self.ln1 = (pk.vec(f"{prefix}.ln1.weight"), pk.vec(f"{prefix}.ln1.bias"))
+        self.ln2 = (pk.vec(f"{prefix}.ln2.weight"), pk.vec(f"{prefix}.ln2.bias"))
+        self.in_proj = pk.conv(f"{prefix}.mha.in_proj_weight", f"{prefix}.mha.in_proj_bias")
+        self.out_proj = pk.conv(f"{prefix}.mha.out_proj.weight", f"{prefix}.mha.out_proj.bias")
+        self.ff0 = pk.conv(f"{prefix}.ff.0.weight", f"{prefix}.ff.0.bias")
+        self.ff2 = pk.conv(f"{prefix}.ff.2.weight", f"{prefix}.ff.2.bias")
+
+
+def attention_block(k: Kernels, aw: AttentionW, x: Act) -> Act:
+    """ImageSelfAttention.forward (score_unet.py:136-148) on NHWC tokens (the flatten is free)."""
+    tok = x.tokens()
+    b, s, c = x.n, x.h * x.w, x.c
+    h1 = k.layernorm(tok, *aw.ln1)
+    qkv = k.linear(h1, aw.in_proj)
+    att = k.attention_core(qkv, b, s, c, aw.heads)
+    h = k.linear(att, aw.out_proj, residual=tok)
+    g = k.layernorm(h, *aw.ln2)
+    g = k.linear(g, aw.ff0, act=ACT_GELU)
+    y = k.linear(g, aw.ff2, residual=h)
+    out = Act.__new__(Act)
+    out.buf, out.fmt, out.n, out.h, out.w, out.c = y.buf, y.fmt, x.n, x.h, x.w, x.c
+    return out
+
+
+class TimeProjector:
+    """All Gaussian-Fourier embeddings and SiLU->Linear projections in one launch.
+
+    Heads are addressed by name; `cols(name)` gives the column slice of the [rows, c_total] output.
+    """
+
+    def __init__(self, device, te: int) -> None:
+        self.device, self.te = device, te
+        self.sets: List[torch.Tensor] = []
+        self.w: List[torch.Tensor] = []
+        self.b: List[torch.Tensor] = []
+        self.set_of: List[torch.Tensor] = []
+        self.slices: Dict[str, Tuple[int, int]] = {}
+        self.label_emb: Optional[torch.Tensor] = None
+        self.c_total = 0
+        self._packed = None
+
+    def add_set(self, W: torch.Tensor) -> int:
+        self.sets.append(W.reshape(-1))
+        return len(self.sets) - 1
+
+    def add_head(self, name: str, set_idx: int, w: torch.Tensor, b: torch.Tensor) -> None:
+        c = w.shape[0]
+        self.slices[name] = (self.c_total, self.c_total + c)
+        self.c_total += c
+        self.w.append(w)
+        self.b.append(b)
+        self.set_of.append(torch.full((c,), set_idx, dtype=torch.int32, device=self.device))
+
+    def finalize(self) -> None:
+        self._packed = (torch.stack(self.sets).contiguous(), torch.cat(self.w).contiguous(),
+                        torch.cat(self.b).contiguous(), torch.cat(self.set_of).contiguous())
+
+    def __call__(self, t: torch.Tensor, y: Optional[torch.Tensor], *, rows: Optional[int] = None,
+                 t_row_stride: int = 1, t_step_stride: int = 0, step_counter: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Projection table [rows, c_total].  Default: one row per element of `t`.  A sampler passes its
+        step table as `t` with t_row_stride=0, t_step_stride=STEP_COLS and the device step counter."""
+        fw, pw, pb, ps = self._packed
+        if rows is None:
+            rows = t.numel()
+            t = t.reshape(-1).to(device=self.device, dtype=torch.float32).contiguous()
+        yy = None if y is None else y.reshape(-1).to(device=self.device, dtype=torch.int64).contiguous()
+        if yy is not None and yy.numel() != rows:
+            raise ValueError(f"Batch mismatch: x= {rows}, y={yy.numel()}.")
+        if out is None:
+            out = torch.empty((rows, self.c_total), dtype=torch.float32, device=self.device)
+        call("sbgm_time_embed_project", t.data_ptr(), t_row_stride, t_step_stride, _ptr(step_counter), _ptr(yy),
+             fw.data_ptr(), fw.shape[0], self.te, _ptr(self.label_emb) if yy is not None else None, pw.data_ptr(),
+             pb.data_ptr(), ps.data_ptr(), self.c_total, out.data_ptr(), rows, _stream())
+        return out
+
+    def cols(self, table: torch.Tensor, name: str) -> torch.Tensor:
+        a, b = self.slices[name]
+        return table[:, a:b]
+
+
+class EncoderEngine:
+    def __init__(self, sd, prefix: str, *, block_layers: Sequence[int], n_heads: int, te: int, has_labels: bool,
+                 fmt: int, device, tp: TimeProjector) -> None:
+        pk = _Packer(sd, fmt, device)
+        self.k = Kernels(fmt, device)
+        self.fmt, self.device, self.prefix = fmt, device, prefix
+        p = prefix
+        w1 = pk.get(f"{p}conv1.weight")                                  # [64, cin, 8, 8]
+        self.cin = w1.shape[1]
+        self.stem_w = w1.permute(1, 2, 3, 0).reshape(self.cin, 64, 64).contiguous()   # [cin][tap][co]
+        self.conv2 = pk.conv(f"{p}conv2.weight", bn=f"{p}bn1")
+        self.layers = []
+        for li, nblk in enumerate(block_layers, start=1):
+            blocks = []
+            for b in range(nblk):
+                bp = f"{p}layer{li}.{b}"
+                stride = 2 if (b == 0 and li > 1) else 1
+                down = pk.conv(f"{bp}.downsample.0.weight", bn=f"{bp}.downsample.1") if f"{bp}.downsample.0.weight" in sd else None
+                blocks.append((pk.conv(f"{bp}.conv1.weight", bn=f"{bp}.bn1"), pk.conv(f"{bp}.conv2.weight", bn=f"{bp}.bn2"), down, stride))
+            self.layers.append(blocks)
+        self.attn = {i: AttentionW(pk, f"{p}attention_layers.{i}", n_heads) for i in (3, 4)}
+        set0 = tp.add_set(pk.get(f"{p}sinusoidal_embedding.W"))
+        for i in range(5):
+            tp.add_head(f"enc{i}", set0, pk.get(f"{p}time_projection_layers.{i}.1.weight"), pk.vec(f"{p}time_projection_layers.{i}.1.bias"))
+        if has_labels:
+            tp.label_emb = pk.get(f"{p}label_emb.weight").contiguous()
+        self.tp = tp
+
+    def stem_partial(self, planes: torch.Tensor, h: int, w: int) -> torch.Tensor:
+        """conv1 restricted to the conditioning channels (step-invariant in a sampler): fp32 NHWC."""
+        npl, cc = planes.shape[0], planes.shape[1]
+        out = Act(FMT_F32, npl, h // 2, w // 2, 64, self.device)
+        call("sbgm_stem_conv", None, planes.data_ptr(), npl, cc, 1, cc + 1, self.stem_w.data_ptr(), None, 0, None, 0,
+             out.ptr, out.plane, FMT_F32, npl, h, w, _stream())
+        return out.buf
+
+    def forward(self, x: torch.Tensor, planes: Optional[torch.Tensor], tproj: torch.Tensor,
+                partial: Optional[torch.Tensor] = None) -> List[Act]:
+        """x [n,1,h,w] fp32; planes [n or 1, cin-1, h, w] fp32 (conditioning channels in concat order)
+        or, when `partial` is given, their precomputed stem contribution."""
+        k, tp = self.k, self.tp
+        n, _, h, w = x.shape
+        cc = self.cin - 1
+        f1 = Act(self.fmt, n, h // 2, w // 2, 64, self.device)
+        t0 = tp.cols(tproj, "enc0")
+        if partial is not None:
+            call("sbgm_stem_conv", x.data_ptr(), None, 1, cc, 0, 1, self.stem_w.data_ptr(), partial.data_ptr(),
+                 partial.shape[0], t0.data_ptr(), t0.stride(0), f1.ptr, f1.plane, self.fmt, n, h, w, _stream())
+        else:
+            if cc > 0:
+                assert planes is not None and planes.shape[1] == cc, f"encoder expects {cc} conditioning channels"
+            call("sbgm_stem_conv", x.data_ptr(), _ptr(planes), 1 if planes is None else planes.shape[0], cc, 0, self.cin,
+                 self.stem_w.data_ptr(), None, 0, t0.data_ptr(), t0.stride(0), f1.ptr, f1.plane, self.fmt, n, h, w, _stream())
+        fmaps = [f1]
+        hcur = k.conv(f1, self.conv2, stride=2, pad=3, act=ACT_RELU)
+        for li, blocks in enumerate(self.layers, start=1):
+            for bi, (c1, c2, down, stride) in enumerate(blocks):
+                last = bi == len(blocks) - 1
+                idn = hcur if down is None else k.conv(hcur, down, stride=stride, pad=0)
+                mid = k.conv(hcur, c1, stride=stride, pad=1, act=ACT_RELU)
+                hcur = k.conv(mid, c2, stride=1, pad=1, act=ACT_RELU, residual=idn,
+                              tproj=tp.cols(tproj, f"enc{li}") if last else None)
+            if li in self.attn:
+                hcur = attention_block(k, self.attn[li], hcur)
+            fmaps.append(hcur)
+        return fmaps
+
+
+class DecoderEngine:
+    def __init__(self, sd, prefix: str, *, plan: Sequence[Tuple[int, int, bool]], n_heads: int, norm: str,
+                 gn_groups: int, activation: str, use_resize_conv: bool, out_channels: int, fmt: int, device,
+                 tp: TimeProjector) -> None:
+        if not use_resize_conv:
+            raise NotImplementedError("use_resize_conv=False (ConvTranspose2d decoder) is not on the CUDA path yet")
+        pk = _Packer(sd, fmt, device)
+        self.k = Kernels(fmt, device)
+        self.fmt, self.device = fmt, device
+        self.act = ACTS[activation]
+        self.norm, self.gn_groups = norm, gn_groups
+        self.blocks = []
+        for i, (cin, cout, attn) in enumerate(plan):
+            bp = f"{prefix}residual_layers.{i}"
+            affine = norm == "group"
+            blk = dict(
+                conv_up=pk.conv(f"{bp}.conv_up.weight", f"{bp}.conv_up.bias"),
+                conv=pk.conv(f"{bp}.conv.weight", f"{bp}.conv.bias"),
+                n1=(pk.vec(f"{bp}.norm1.weight"), pk.vec(f"{bp}.norm1.bias")) if affine else (None, None),
+                n2=(pk.vec(f"{bp}.norm2.weight"), pk.vec(f"{bp}.norm2.bias")) if affine else (None, None),
+                g1=max(1, min(gn_groups, cin)) if affine else cin,
+                g2=max(1, min(gn_groups, cout)) if affine else cout,
+                attn=AttentionW(pk, f"{bp}.attention", n_heads) if attn else None,
+                name=f"dec{i}")
+            s = tp.add_set(pk.get(f"{bp}.sinusoidal_embedding.W"))
+            tp.add_head(f"dec{i}", s, pk.get(f"{bp}.time_projection_layer.1.weight"), pk.vec(f"{bp}.time_projection_layer.1.bias"))
+            self.blocks.append(blk)
+        fp = f"{prefix}final_layer"
+        self.final_up = pk.conv(f"{fp}.conv_up.weight", f"{fp}.conv_up.bias")
+        wf = pk.get(f"{fp}.conv.weight")                                   # [cout, cin, 3, 3]
+        self.final_w = wf.permute(0, 2, 3, 1).reshape(wf.shape[0], 9, wf.shape[1]).contiguous()
+        self.final_b = pk.vec(f"{fp}.conv.bias")
+        self.out_channels = out_channels
+        self.tp = tp
+
+    def forward(self, fmaps: List[Act], tproj: torch.Tensor, inv_std: Optional[torch.Tensor], *,
+                inv_std_stride: int = 1, inv_std_step_stride: int = 0, step_counter: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        k, tp = self.k, self.tp
+        rev = list(reversed(fmaps))
+        out = rev[0]
+        for i, blk in enumerate(self.blocks):
+            up = k.upsample2x(out)
+            a = k.conv(up, blk["conv_up"], pad=1)
+            a = k.groupnorm(a, *blk["n1"], groups=blk["g1"])
+            b = k.conv(a, blk["conv"], pad=1)
+            skip = rev[i + 1]
+            if (skip.n, skip.h, skip.w, skip.c) != (b.n, b.h, b.w, b.c):
+                raise AssertionError(f"prev_fmap shape {(skip.n, skip.c, skip.h, skip.w)} must match output shape {(b.n, b.c, b.h, b.w)}")
+            out = k.groupnorm(b, *blk["n2"], groups=blk["g2"], act=self.act, skip=skip, tproj=tp.cols(tproj, blk["name"]))
+            if blk["attn"] is not None:
+                out = attention_block(k, blk["attn"], out)
+        up = k.upsample2x(out)
+        a = k.conv(up, self.final_up, pad=1)
+        res = out if out is not None else torch.empty((a.n, self.out_channels, a.h, a.w), dtype=torch.float32, device=self.device)
+        call("sbgm_final_conv", a.ptr, a.plane, self.fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std),
+             inv_std_stride, inv_std_step_stride, _ptr(step_counter), res.data_ptr(), a.n, a.h, a.w, a.c,
+             self.out_channels, _stream())
+        return res
+
+
+def concat_planes(x_batch: int, lsm, topo, cond, device) -> Optional[torch.Tensor]:
+    """Conditioning channels in the reference's concat order lsm || topo || cond_img (score_unet.py:273-291)."""
+    parts = []
+    for name, c in (("lsm_cond", lsm), ("topo_cond", topo), ("cond_img", cond)):
+        if c is None:
+            continue
+        if name != "cond_img" and c.shape[0] != x_batch:
+            raise ValueError(f"Batch mismatch: x= {x_batch}, {name}={c.shape[0]}.")
+        parts.append(c.to(device=device, dtype=torch.float32))
+    if not parts:
+        return None
+    return torch.cat(parts, dim=1).contiguous()
+
+
+@dataclass
+class UNetSpec:
+    """Architecture knobs recovered from the module tree (they mirror the reference constructors)."""
+    cin_total: int
+    time_embedding: int = 256
+    block_layers: Tuple[int, ...] = (2, 2, 2, 2)
+    n_heads: int = 4
+    has_labels: bool = False
+    plan: Tuple[Tuple[int, int, bool], ...] = ((512, 256, True), (256, 128, True), (128, 64, False), (64, 64, False))
+    out_channels: int = 1
+    use_resize_conv: bool = True
+    norm: str = "group"
+    gn_groups: int = 8
+    activation: str = "silu"
+
+
+class UNetEngine:
+    """Encoder + decoder + time projector packed for one (state-dict, precision, device)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], spec: UNetSpec, precision: str, device) -> None:
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("sbgm_danra_b200 runs on CUDA devices only (no CPU fallback); got device " + str(device))
+        _lib.load_library()
+        self.spec, self.precision, self.device = spec, precision, device
+        self.fmt = PRECISIONS[precision]
+        with torch.cuda.device(device), torch.no_grad():
+            self.tp = TimeProjector(device, spec.time_embedding)
+            self.enc = EncoderEngine(sd, "encoder.", block_layers=spec.block_layers, n_heads=spec.n_heads,
+                                     te=spec.time_embedding, has_labels=spec.has_labels, fmt=self.fmt, device=device, tp=self.tp)
+            self.dec = DecoderEngine(sd, "decoder.", plan=spec.plan, n_heads=spec.n_heads, norm=spec.norm,
+                                     gn_groups=spec.gn_groups, activation=spec.activation,
+                                     use_resize_conv=spec.use_resize_conv, out_channels=spec.out_channels, fmt=self.fmt,
+                                     device=device, tp=self.tp)
+            self.tp.finalize()
+
+    def check_input(self, x: torch.Tensor) -> None:
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError(f"x must be [B, 1, H, W], got {tuple(x.shape)}")
+        if x.shape[2] % 32 != 0 or x.shape[3] % 32 != 0:
+            raise ValueError(f"H and W must be multiples of 32 (five stride-2 stages), got {tuple(x.shape[2:])}")
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, y=None, planes: Optional[torch.Tensor] = None,
+                inv_std: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One UNet evaluation: out[n,co,h,w] = decoder(encoder(x, planes, t, y)) * inv_std[n]."""
+        self.check_input(x)
+        with torch.cuda.device(self.device):
+            x = x.to(device=self.device, dtype=torch.float32).contiguous()
+            tproj = self.tp(t, y)
+            fmaps = self.enc.forward(x, planes, tproj)
+            return self.dec.forward(fmaps, tproj, inv_std)

@@ -1,0 +1,385 @@
+"""Drop-in mirror of the reference's `sbgm/score_sampling.py`: VE-SDE samplers on sm_100a kernels.
+
+`Euler_Maruyama_sampler`, `pc_sampler`, `ode_sampler`, `guided_score_fn` keep the reference's
+signatures (score_sampling.py:63-127, :136-230, :239-300, :10-56).  When `score_model` is this
+package's `ScoreNet` the whole sampler step -- time projections, UNet forward, 1/std scaling,
+drift + diffusion update with in-kernel Philox noise (and the Langevin corrector for PC) -- is
+captured once in a CUDA graph and replayed `num_steps` times; the step index lives on the device.
+
+Differences from the reference, all deliberate:
+  * EM/ODE initial state honours `img_size` (the reference hard-codes 32 and crashes otherwise);
+  * noise comes from a counter-based Philox stream keyed by (seed, global member index, draw), not
+    from torch's global generator: `manual_seed()` below controls it, and an ensemble sharded over
+    several GPUs (`set_ensemble_shard`) reproduces the single-GPU stream member by member;
+  * `ode_sampler` forwards the conditioning tensors to the model (the reference drops them).
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from . import engine as _eng
+from ._lib import STEP_COLS, call
+
+logger = logging.getLogger(__name__)
+
+num_steps = 800
+signal_to_noise_ratio = 0.16
+error_tolerance = 1e-5
+
+
+# ---- noise stream / sharding state ------------------------------------------------------------
+@dataclass
+class _NoiseState:
+    seed: int = 0x5B6D0DA1
+    calls: int = 0
+    first_member: int = 0          # index of this rank's first member in the global ensemble
+    members_total: Optional[int] = None
+    group: object = None           # torch.distributed process group for the PC grad-norm exchange
+
+
+_state = _NoiseState()
+
+
+def manual_seed(seed: int) -> None:
+    """Seed the Philox noise stream; the next sampler / loss call uses exactly `seed`, the one after seed+1, ..."""
+    _state.seed, _state.calls = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+
+
+def set_ensemble_shard(first_member: int = 0, members_total: Optional[int] = None, group=None) -> None:
+    """Declare that this process samples members [first_member, first_member + batch_size) of a
+    `members_total`-member ensemble.  EM needs no communication; PC all-gathers one float per member
+    per step over `group` so the batch-mean gradient norm (score_sampling.py:201) matches the
+    unsharded run exactly."""
+    _state.first_member, _state.members_total, _state.group = int(first_member), members_total, group
+
+
+def noise_state() -> _NoiseState:
+    return _state
+
+
+def _next_seed() -> int:
+    s = (_state.seed + _state.calls) & 0xFFFFFFFFFFFFFFFF
+    _state.calls += 1
+    return s
+
+
+def _is_native(score_model) -> bool:
+    from .score_unet import ScoreNet
+    return isinstance(score_model, ScoreNet)
+
+
+def _cfg_scale(cfg, clamp: bool) -> Optional[float]:
+    """classifier_free_guidance lookup (score_sampling.py:106-110, :180-186)."""
+    cfg = cfg or {}
+    g = cfg.get("classifier_free_guidance", {})
+    if not g.get("enabled", False):
+        return None
+    scale = g.get("guidance_scale", 2.0)
+    if clamp:
+        mx = g.get("guidance_scale_max", None)
+        if mx is not None and scale > mx:
+            scale = mx
+    return float(scale)
+
+
+def _strip_mask(v):
+    if v is None or v.shape[1] != 2:
+        return v
+    v = v.clone()
+    v[:, 1] = 0.0
+    return v
+
+
+def guided_score_fn(score_model, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=None,
+                    null_token: int = 0, scale: float = 2.0):
+    """Classifier-free guidance: (1 + w) s(x|c) - w s(x|null) with null = zero LR image, geo mask
+    channel zeroed, label -> null token (score_sampling.py:10-56)."""
+    s_c = score_model(x, t, y, cond_img, lsm_cond, topo_cond)
+    s_u = score_model(x, t,
+                      torch.full_like(y, null_token) if y is not None else None,
+                      torch.zeros_like(cond_img) if cond_img is not None else None,
+                      _strip_mask(lsm_cond), _strip_mask(topo_cond))
+    if not s_c.is_cuda:
+        raise RuntimeError("guided_score_fn: scores must live on a CUDA device (no CPU path)")
+    s_c, s_u = s_c.contiguous().float(), s_u.contiguous().float()
+    out = torch.empty_like(s_c)
+    with torch.cuda.device(s_c.device):
+        call("sbgm_cfg_combine", s_c.data_ptr(), s_u.data_ptr(), float(scale), out.data_ptr(), out.numel(), _eng._stream())
+    return out
+
+
+# ---- step tables (host arithmetic identical to the reference's) -------------------------------
+def _table_em(marginal_prob_std, diffusion_coeff, n_steps: int, eps: float) -> torch.Tensor:
+    ts = torch.linspace(1.0, eps, n_steps)                       # score_sampling.py:96
+    dt = ts[0] - ts[1] if n_steps > 1 else torch.tensor(0.0)     # :97
+    g = diffusion_coeff(ts).float()                              # :103
+    std = marginal_prob_std(ts).float()
+    tab = torch.zeros(n_steps, STEP_COLS)
+    tab[:, 0], tab[:, 1], tab[:, 2], tab[:, 3] = ts, g, dt, 1.0 / std
+    tab[:, 4] = (g ** 2) * dt                                    # :124
+    tab[:, 5] = torch.sqrt(dt) * g                               # :125
+    return tab
+
+
+def _table_pc(marginal_prob_std, diffusion_coeff, n_steps: int, eps: float) -> torch.Tensor:
+    ts64 = np.linspace(1.0, eps, n_steps)                        # :169 (float64 on the host)
+    dt = ts64[0] - ts64[1] if n_steps > 1 else 0.0               # :170
+    ts = torch.stack([(torch.ones(1) * tk)[0] for tk in ts64])  # ones(B) * time_step -> fp32, :176
+    g = diffusion_coeff(ts).float()                              # :207
+    std = marginal_prob_std(ts).float()
+    tab = torch.zeros(n_steps, STEP_COLS)
+    tab[:, 0], tab[:, 1], tab[:, 2], tab[:, 3] = ts, g, float(dt), 1.0 / std
+    tab[:, 4] = (g ** 2) * dt                                    # :224
+    tab[:, 5] = torch.sqrt(g ** 2 * dt)                          # :227
+    return tab
+
+
+class _NativeStep:
+    """One fused sampler step on the engine, written so it can be captured in a CUDA graph."""
+
+    def __init__(self, model, batch: int, size: int, table: torch.Tensor, y, cond_img, lsm_cond, topo_cond,
+                 cfg_scale: Optional[float]):
+        eng = model.engine()
+        if model.training:
+            raise NotImplementedError("sampling with train-mode BatchNorm is not on the CUDA path yet; call model.eval()")
+        self.eng, self.dev, self.b, self.size = eng, eng.device, batch, size
+        dev = self.dev
+        self.table = table.to(dev).contiguous()
+        self.inv_std = self.table[:, 3]
+        self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.x = torch.zeros((batch, 1, size, size), dtype=torch.float32, device=dev)
+        self.score = torch.empty_like(self.x)
+        self.mean = torch.empty_like(self.x)
+        self.tproj = torch.empty((batch, eng.tp.c_total), dtype=torch.float32, device=dev)
+        self.y = None if y is None else y.to(device=dev, dtype=torch.int64).contiguous()
+        self.cfg_scale = cfg_scale
+        self.partial = self._partial(cond_img, lsm_cond, topo_cond)
+        if cfg_scale is not None:
+            self.partial_u = self._partial(None if cond_img is None else torch.zeros_like(cond_img),
+                                           _strip_mask(lsm_cond), _strip_mask(topo_cond))
+            self.y_u = None if self.y is None else torch.zeros_like(self.y)
+            self.score_c = torch.empty_like(self.x)
+            self.score_u = torch.empty_like(self.x)
+            self.tproj_u = torch.empty_like(self.tproj)
+
+    def _partial(self, cond_img, lsm_cond, topo_cond) -> Optional[torch.Tensor]:
+        planes = _eng.concat_planes(self.b, lsm_cond, topo_cond, cond_img, self.dev)
+        cc = self.eng.enc.cin - 1
+        if planes is None:
+            if cc != 0:
+                raise ValueError(f"model expects {cc} conditioning channels but none were given")
+            return None
+        if planes.shape[1] != cc:
+            raise ValueError(f"model expects {cc} conditioning channels, got {planes.shape[1]}")
+        if planes.shape[0] not in (1, self.b):
+            raise ValueError(f"Batch mismatch: batch_size={self.b}, conditions={planes.shape[0]}.")
+        if planes.shape[0] > 1 and bool((planes == planes[:1]).all()):
+            planes = planes[:1].contiguous()     # every member shares one conditioning sample: broadcast
+        return self.eng.enc.stem_partial(planes, self.size, self.size)
+
+    def _forward(self, partial, y, tproj, out) -> None:
+        eng = self.eng
+        eng.tp(self.table, y, rows=self.b, t_row_stride=0, t_step_stride=STEP_COLS, step_counter=self.counter, out=tproj)
+        if partial is None:
+            fmaps = eng.enc.forward(self.x, None, tproj)
+        else:
+            fmaps = eng.enc.forward(self.x, None, tproj, partial=partial)
+        eng.dec.forward(fmaps, tproj, self.inv_std, inv_std_stride=0, inv_std_step_stride=STEP_COLS,
+                        step_counter=self.counter, out=out)
+
+    def score_into(self) -> torch.Tensor:
+        if self.cfg_scale is None:
+            self._forward(self.partial, self.y, self.tproj, self.score)
+        else:
+            self._forward(self.partial, self.y, self.tproj, self.score_c)
+            self._forward(self.partial_u, self.y_u, self.tproj_u, self.score_u)
+            call("sbgm_cfg_combine", self.score_c.data_ptr(), self.score_u.data_ptr(), self.cfg_scale,
+                 self.score.data_ptr(), self.score.numel(), _eng._stream())
+        return self.score
+
+
+class _GenericStep:
+    """Same update kernels around an arbitrary `score_model` callable (no CUDA graph)."""
+
+    def __init__(self, score_model, batch, size, table, device, y, cond_img, lsm_cond, topo_cond, cfg_scale):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("samplers run on CUDA devices only (no CPU fallback); got device=" + str(device))
+        self.dev, self.b, self.size = dev, batch, size
+        self.model, self.args = score_model, (y, cond_img, lsm_cond, topo_cond)
+        self.table = table.to(dev).contiguous()
+        self.table_host = table
+        self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.x = torch.zeros((batch, 1, size, size), dtype=torch.float32, device=dev)
+        self.mean = torch.empty_like(self.x)
+        self.cfg_scale = cfg_scale
+        self.k = 0
+
+    def score_into(self) -> torch.Tensor:
+        bt = torch.full((self.b,), float(self.table_host[self.k, 0]), dtype=torch.float32, device=self.dev)
+        if self.cfg_scale is None:
+            s = self.model(self.x, bt, *self.args)
+        else:
+            s = guided_score_fn(self.model, self.x, bt, *self.args, scale=self.cfg_scale)
+        self.score = s.contiguous().float()
+        return self.score
+
+
+def _predict(st, seed, draw_base, draw_stride, first_elem) -> None:
+    call("sbgm_sampler_predictor", st.x.data_ptr(), st.score.data_ptr(), st.mean.data_ptr(), st.x.numel(),
+         st.table.data_ptr(), st.counter.data_ptr(), seed, draw_base, draw_stride, first_elem, _eng._stream())
+
+
+def _correct(st, sumsq, sumsq_all, snr, seed, first_elem) -> None:
+    per = st.size * st.size
+    call("sbgm_sampler_sumsq", st.score.data_ptr(), sumsq.data_ptr(), st.b, per, _eng._stream())
+    if sumsq_all is not sumsq:
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(sumsq_all, sumsq, group=_state.group)
+    call("sbgm_sampler_corrector", st.x.data_ptr(), st.score.data_ptr(), sumsq_all.data_ptr(), sumsq_all.numel(), per,
+         float(snr), st.x.numel(), st.counter.data_ptr(), seed, 1, 2, first_elem, _eng._stream())
+
+
+def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_size, n_steps, snr, device, eps, img_size,
+            y, cond_img, lsm_cond, topo_cond, cfg, use_graph: bool = True) -> torch.Tensor:
+    if img_size % 32 != 0:
+        raise ValueError(f"img_size must be a multiple of 32, got {img_size}")
+    seed = _next_seed()
+    table = (_table_em if kind == "em" else _table_pc)(marginal_prob_std, diffusion_coeff, n_steps, eps)
+    scale = _cfg_scale(cfg, clamp=(kind == "pc"))
+    native = _is_native(score_model)
+    dev = score_model.engine().device if native else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("samplers run on CUDA devices only (no CPU fallback); got device=" + str(device))
+    with torch.no_grad(), torch.cuda.device(dev):
+        if native:
+            st = _NativeStep(score_model, batch_size, img_size, table, y, cond_img, lsm_cond, topo_cond, scale)
+        else:
+            st = _GenericStep(score_model, batch_size, img_size, table, dev, y, cond_img, lsm_cond, topo_cond, scale)
+    per = img_size * img_size
+    first_elem = _state.first_member * per
+    std1 = float(marginal_prob_std(torch.ones(1))[0])             # score_sampling.py:93-95 / :167-168
+    sharded = kind == "pc" and _state.members_total is not None and _state.members_total != batch_size
+
+    with torch.no_grad(), torch.cuda.device(dev):
+        sumsq = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+        sumsq_all = torch.zeros(_state.members_total, dtype=torch.float32, device=dev) if sharded else sumsq
+
+        def one_step() -> None:
+            if kind == "pc":
+                st.score_into()
+                _correct(st, sumsq, sumsq_all, snr, seed, first_elem)
+                st.score_into()
+                _predict(st, seed, 2, 2, first_elem)
+            else:
+                st.score_into()
+                _predict(st, seed, 1, 1, first_elem)
+
+        graph = None
+        if native and use_graph and n_steps > 1:
+            # eager warm-up step (lazy kernel attributes, scratch buffers), then capture one step
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                one_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            st.counter.zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                one_step()
+            st.counter.zero_()
+        call("sbgm_sampler_init", st.x.data_ptr(), st.x.numel(), std1, seed, first_elem, _eng._stream())
+        for k in range(n_steps):
+            if graph is not None:
+                graph.replay()
+            else:
+                if not native:
+                    st.k = k
+                one_step()
+        return st.mean.clone()
+
+
+def Euler_Maruyama_sampler(score_model, marginal_prob_std, diffusion_coeff, batch_size=64, num_steps=500,
+                           device="cuda", eps=1e-3, img_size=64, y=None, cond_img=None, lsm_cond=None,
+                           topo_cond=None, cfg=None):
+    """Euler-Maruyama reverse-SDE sampler (score_sampling.py:63-127).  Returns the noise-free mean of the last step."""
+    return _sample("em", score_model, marginal_prob_std, diffusion_coeff, batch_size, num_steps, 0.0, device, eps,
+                   img_size, y, cond_img, lsm_cond, topo_cond, cfg)
+
+
+def pc_sampler(score_model, marginal_prob_std, diffusion_coeff, batch_size=64, num_steps=num_steps,
+               snr=signal_to_noise_ratio, device="cuda", eps=1e-3, img_size=64, y=None, cond_img=None,
+               lsm_cond=None, topo_cond=None, cfg=None):
+    """Predictor-corrector sampler: Langevin corrector + Euler-Maruyama predictor, 2 NFE per step
+    (score_sampling.py:136-230)."""
+    return _sample("pc", score_model, marginal_prob_std, diffusion_coeff, batch_size, num_steps, snr, device, eps,
+                   img_size, y, cond_img, lsm_cond, topo_cond, cfg)
+
+
+def ode_sampler(score_model, marginal_prob_std, diffusion_coeff, num_steps=100, batch_size=64, atol=error_tolerance,
+                rtol=error_tolerance, device="cuda", z=None, eps=1e-3, img_size=64, y=None, cond_img=None,
+                lsm_cond=None, topo_cond=None, cfg=None):
+    """Probability-flow ODE through scipy RK45 (score_sampling.py:239-300): the integrator runs on the host
+    in float64 exactly as in the reference; only the score evaluations run on the GPU."""
+    from scipy import integrate
+    dev = torch.device(device)
+    if z is None:
+        init = torch.empty((batch_size, 1, img_size, img_size), dtype=torch.float32, device=dev)
+        std1 = float(marginal_prob_std(torch.ones(1))[0])
+        with torch.cuda.device(dev):
+            call("sbgm_sampler_init", init.data_ptr(), init.numel(), std1, _next_seed(),
+                 _state.first_member * img_size * img_size, _eng._stream())
+    else:
+        init = z.to(dev)
+    shape = tuple(init.shape)
+
+    def rhs(t, xflat):
+        sample = torch.tensor(xflat, device=dev, dtype=torch.float32).reshape(shape)
+        ts = torch.full((shape[0],), float(t), device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            s = score_model(sample, ts, y, cond_img, lsm_cond, topo_cond)
+        g = float(diffusion_coeff(torch.tensor(t)))
+        return -0.5 * (g ** 2) * s.cpu().numpy().reshape(-1).astype(np.float64)
+
+    res = integrate.solve_ivp(rhs, (1.0, eps), init.reshape(-1).cpu().numpy(), rtol=rtol, atol=atol, method="RK45")
+    logger.info(f"Number of function evaluations: {res.nfev}")
+    return torch.tensor(res.y[:, -1], device=dev).reshape(shape)
+
+
+def edm_sigma_schedule(n_steps, sigma_min=0.002, sigma_max=80, rho=7.0, device="cuda"):
+    """Karras et al. sigma schedule (score_sampling.py:304-306); a host-side helper, unused by the samplers."""
+    i = torch.linspace(0, 1, n_steps, device=device)
+    return (sigma_max ** (1 / rho) + i * (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
+
+
+# ---- DSM loss forward (score_unet.py:936-985) --------------------------------------------------
+def _dsm_loss_forward(model, x, marginal_prob_std, t_eps, y, cond_img, lsm_cond, topo_cond, sdf_cond):
+    from . import _lib
+    if not x.is_cuda:
+        raise RuntimeError("loss_fn: x must live on a CUDA device (no CPU path)")
+    dev = x.device
+    seed = _next_seed()
+    n, per = x.shape[0], x[0].numel()
+    with torch.no_grad(), torch.cuda.device(dev):
+        x = x.contiguous().float()
+        start = _state.first_member // 4 * 4          # Philox counters cover 4 elements: generate from an aligned start
+        off = _state.first_member - start
+        u = torch.empty((off + n + 3) // 4 * 4, dtype=torch.float32, device=dev)
+        call("sbgm_philox_uniform", u.data_ptr(), u.numel(), seed, 0, start, _eng._stream())
+        t = u[off:off + n] * (1.0 - t_eps) + t_eps
+        std = marginal_prob_std(t).float().contiguous()
+        xt, z = torch.empty_like(x), torch.empty_like(x)
+        call("sbgm_dsm_perturb", x.data_ptr(), std.data_ptr(), xt.data_ptr(), z.data_ptr(), n, per, seed, 1,
+             _state.first_member * per, _eng._stream())
+        score = model(xt, t, y=y, cond_img=cond_img, lsm_cond=lsm_cond, topo_cond=topo_cond).contiguous().float()
+        partials = torch.empty(_lib.query("sbgm_dsm_scratch_floats", x.numel()), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        sdf = None if sdf_cond is None else sdf_cond.to(dev).contiguous().float()
+        call("sbgm_dsm_loss", score.data_ptr(), std.data_ptr(), z.data_ptr(), None if sdf is None else sdf.data_ptr(),
+             n, per, partials.data_ptr(), loss.data_ptr(), _eng._stream())
+        return loss

@@ -1,0 +1,220 @@
+"""GPU parity tests of the drop-in modules and samplers against the CPU oracle and the committed
+golden vectors of the real reference (tests/golden/).  Everything goes through the public Python
+API of `sbgm_danra_b200` (which reaches the kernels through the C ABI).
+
+Score parity gate (BASELINE.json north star): rel-L2 <= 1e-3 in the fp32-class modes; bf16 is
+reported with its own tolerance (5e-2)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FORWARD_CASES = {
+    "fwd_c1_64_cin2": (dict(n_lr=1), dict(batch=2, size=64, n_lr=1)),
+    "fwd_c3_64_cin7_seasons": (dict(n_lr=2, geo=True, seasons=True), dict(batch=2, size=64, n_lr=2, geo=True, seasons=True)),
+    "fwd_32_instance_relu_3463": (dict(n_lr=1, norm="instance", activation="relu", block_layers=(3, 4, 6, 3)),
+                                  dict(batch=2, size=32, n_lr=1)),
+    "fwd_128_cin2": (dict(n_lr=1), dict(batch=1, size=128, n_lr=1)),
+}
+SCORE_TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "bf16": 5e-2}
+SEED_NOISE = 2024
+DEV = "cuda:0"
+
+
+def _cuda(v):
+    return None if v is None else v.to(DEV)
+
+
+def _model(ck, precision):
+    from oracle.synth import config_for, synth_state_dict
+    from sbgm_danra_b200._smoke import build_model
+    cfg = config_for(**ck)
+    sd = synth_state_dict(cfg)
+    return build_model(cfg, sd, precision, DEV), cfg, sd
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name", list(FORWARD_CASES))
+def test_score_matches_reference_golden(golden, name, precision):
+    from oracle.synth import synth_batch
+    ck, bk = FORWARD_CASES[name]
+    net, _, _ = _model(ck, precision)
+    b = synth_batch(**bk)
+    out = net(*[_cuda(v) for v in b.model_args()]).cpu()
+    err = rel_l2(out, golden[f"{name}/score"])
+    print(f"{name} [{precision}] rel-L2 = {err:.3e}")
+    assert err < SCORE_TOL[precision], f"rel-L2 {err:.3e}"
+    per_sample = [rel_l2(out[i], golden[f"{name}/score"][i]) for i in range(out.shape[0])]
+    assert max(per_sample) < 2 * SCORE_TOL[precision]
+
+
+def test_state_dict_keys_match_reference_schema():
+    with open(os.path.join(GOLDEN_DIR, "reference_schema.json")) as f:
+        ref = json.load(f)
+    for name, (ck, _) in FORWARD_CASES.items():
+        net, _, _ = _model(ck, "fp32")
+        mine = {k: list(v.shape) for k, v in net.state_dict().items()}
+        assert mine == ref[name], name
+
+
+def test_encoder_decoder_standalone_api():
+    """Encoder.forward -> 5 NCHW fmaps, Decoder.forward(*fmaps, t=t) -> pre-division output."""
+    from oracle import score_ref
+    from oracle.synth import synth_batch
+    ck = dict(n_lr=2, geo=True, seasons=True)
+    net, cfg, sd = _model(ck, "fp32")
+    b = synth_batch(batch=2, size=64, n_lr=2, geo=True, seasons=True)
+    fm = net.encoder(*[_cuda(v) for v in b.model_args()])
+    with torch.no_grad():
+        want = score_ref.encoder_forward(sd, cfg, *b.model_args())
+        want_out = score_ref.decoder_forward(sd, cfg, want, b.t)
+    assert len(fm) == 5
+    for got, w in zip(fm, want):
+        assert got.shape == w.shape and rel_l2(got.cpu(), w) < 1e-4
+    out = net.decoder(*fm, t=b.t.to(DEV))
+    assert rel_l2(out.cpu(), want_out) < 1e-4
+    with pytest.raises(AssertionError):
+        net.decoder(*fm[:4], t=b.t.to(DEV))
+
+
+def test_attention_and_embedding_modules():
+    from oracle import score_ref
+    from sbgm_danra_b200.score_unet import ImageSelfAttention, SinusoidalEmbedding
+    torch.manual_seed(0)
+    att = ImageSelfAttention(128, 4).to(DEV)
+    att.precision = "fp32"
+    x = torch.randn(2, 128, 8, 8)
+    sd = {f"a.{k}": v.cpu() for k, v in att.state_dict().items()}
+    with torch.no_grad():
+        want = score_ref.attention_block(sd, "a", x, 4)
+    assert rel_l2(att(x.to(DEV)).cpu(), want) < 1e-4
+    emb = SinusoidalEmbedding(256).to(DEV)
+    t = torch.rand(7)
+    assert rel_l2(emb(t.to(DEV)).cpu(), score_ref.fourier_embed(emb.W.cpu(), t)) < 1e-5
+    with pytest.raises(ValueError):
+        SinusoidalEmbedding(255)
+    with pytest.raises(ValueError):
+        ImageSelfAttention(100, 3)
+
+
+def test_error_behaviour_matches_reference():
+    from oracle.synth import synth_batch
+    net, _, _ = _model(dict(n_lr=2, geo=True, seasons=True), "fp32")
+    b = synth_batch(batch=2, size=64, n_lr=2, geo=True, seasons=True)
+    with pytest.raises(ValueError):     # batch mismatch on lsm_cond (score_unet.py:274-275)
+        net(b.x.to(DEV), b.t.to(DEV), b.y.to(DEV), b.cond_img.to(DEV), b.lsm_cond[:1].to(DEV), b.topo_cond.to(DEV))
+    cpu_net, _, _ = _model(dict(n_lr=1), "fp32")
+    cpu_net.to("cpu")
+    with pytest.raises(RuntimeError):   # no CPU fallback
+        cpu_net(b.x, b.t, None, b.cond_img[:, :1])
+
+
+def _sampler_inputs(name):
+    from oracle.synth import synth_batch
+    size, ck = {"c1": (64, dict(n_lr=1)), "c3": (32, dict(n_lr=2, geo=True, seasons=True))}[name]
+    b = synth_batch(batch=2, size=size, shared_cond=True, **ck)
+    return size, ck, b
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name", ["c1", "c3"])
+def test_em_sampler_matches_reference_golden(golden, name, precision):
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    size, ck, b = _sampler_inputs(name)
+    net, _, _ = _model(ck, precision)
+    ss.manual_seed(SEED_NOISE)
+    out = ss.Euler_Maruyama_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=2, num_steps=3, device=DEV,
+                                    img_size=size, y=_cuda(b.y), cond_img=_cuda(b.cond_img), lsm_cond=_cuda(b.lsm_cond),
+                                    topo_cond=_cuda(b.topo_cond))
+    err = rel_l2(out.cpu(), golden[f"em_{name}/mean_x"])
+    print(f"EM {name} [{precision}] rel-L2 = {err:.3e}")
+    assert err < 2e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name", ["c1", "c3"])
+def test_pc_sampler_matches_reference_golden(golden, name, precision):
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    size, ck, b = _sampler_inputs(name)
+    net, _, _ = _model(ck, precision)
+    ss.manual_seed(SEED_NOISE)
+    out = ss.pc_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=2, num_steps=3, snr=0.16, device=DEV,
+                        img_size=size, y=_cuda(b.y), cond_img=_cuda(b.cond_img), lsm_cond=_cuda(b.lsm_cond),
+                        topo_cond=_cuda(b.topo_cond))
+    err = rel_l2(out.cpu(), golden[f"pc_{name}/x_mean"])
+    print(f"PC {name} [{precision}] rel-L2 = {err:.3e}")
+    assert err < 2e-3
+
+
+def test_guided_em_matches_reference_golden(golden):
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    size, ck, b = _sampler_inputs("c3")
+    net, _, _ = _model(ck, "bf16x3")
+    ss.manual_seed(SEED_NOISE)
+    cfg = {"classifier_free_guidance": {"enabled": True, "guidance_scale": 1.5}}
+    out = ss.Euler_Maruyama_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=2, num_steps=3, device=DEV,
+                                    img_size=size, y=_cuda(b.y), cond_img=_cuda(b.cond_img), lsm_cond=_cuda(b.lsm_cond),
+                                    topo_cond=_cuda(b.topo_cond), cfg=cfg)
+    assert rel_l2(out.cpu(), golden["em_c3_cfg/mean_x"]) < 2e-3
+
+
+def test_generic_callable_path_equals_graph_path():
+    """A plain callable goes through the un-captured loop; it must reproduce the CUDA-graph path."""
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    size, ck, b = _sampler_inputs("c1")
+    net, _, _ = _model(ck, "bf16x3")
+    kw = dict(batch_size=2, num_steps=6, device=DEV, img_size=size, cond_img=_cuda(b.cond_img))
+    ss.manual_seed(5)
+    a = ss.Euler_Maruyama_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, **kw)
+    ss.manual_seed(5)
+    c = ss.Euler_Maruyama_sampler(lambda *args: net(*args), marginal_prob_std_fn, diffusion_coeff_fn, **kw)
+    assert rel_l2(a.cpu(), c.cpu()) < 1e-5
+    ss.manual_seed(5)
+    p1 = ss.pc_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, **kw)
+    ss.manual_seed(5)
+    p2 = ss.pc_sampler(lambda *args: net(*args), marginal_prob_std_fn, diffusion_coeff_fn, **kw)
+    assert rel_l2(p1.cpu(), p2.cpu()) < 1e-5
+
+
+def test_sharded_em_ensemble_reproduces_unsharded():
+    """Members [2,4) sampled as a shard equal members [2,4) of the 4-member run (global Philox indexing)."""
+    from oracle.synth import synth_batch
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    net, _, _ = _model(dict(n_lr=1), "bf16x3")
+    b = synth_batch(batch=4, size=32, n_lr=1, shared_cond=True)
+    kw = dict(num_steps=4, device=DEV, img_size=32)
+    ss.manual_seed(9)
+    full = ss.Euler_Maruyama_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=4, cond_img=_cuda(b.cond_img), **kw)
+    try:
+        ss.manual_seed(9)
+        ss.set_ensemble_shard(2, 4)
+        part = ss.Euler_Maruyama_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=2,
+                                         cond_img=_cuda(b.cond_img[2:]), **kw)
+    finally:
+        ss.set_ensemble_shard(0, None)
+    assert rel_l2(part.cpu(), full[2:].cpu()) < 1e-5
+
+
+def test_dsm_loss_forward_matches_reference_golden(golden):
+    from oracle.synth import synth_batch
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    net, _, _ = _model(dict(n_lr=2, geo=True, seasons=True), "bf16x3")
+    b = synth_batch(batch=4, size=32, n_lr=2, geo=True, seasons=True)
+    ss.manual_seed(SEED_NOISE)
+    with torch.no_grad():
+        loss = loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, y=_cuda(b.y), cond_img=_cuda(b.cond_img),
+                       lsm_cond=_cuda(b.lsm_cond), topo_cond=_cuda(b.topo_cond), sdf_cond=_cuda(b.sdf_cond))
+    want = float(golden["dsm_eval/loss"])
+    assert abs(loss.item() - want) / want < 1e-3

@@ -1,0 +1,314 @@
+"""GPU parity tests, one per C-ABI kernel: each calls the CUDA path through the C ABI (ctypes) and
+compares with a plain torch fp32 CPU evaluation of the same operator on the same seeded inputs.
+
+Tolerances (relative L2 unless noted): fp32 kernels 1e-5; bf16x3 (split-bf16 tensor-core) 1e-4;
+bf16 2e-2 -- written next to each check."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FMTS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
+TOL = {"fp32": 2e-5, "bf16": 2e-2, "bf16x3": 1e-4}
+ELEM_TOL = {"fp32": 1e-6, "bf16": 6e-3, "bf16x3": 2e-5}   # storage round-trip only
+
+
+@pytest.fixture(scope="module")
+def E():
+    from sbgm_danra_b200 import engine
+    return engine
+
+
+def gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def act_of(E, x, fmt):
+    return E.Act.from_nchw(x.cuda(), fmt)
+
+
+@pytest.mark.parametrize("prec", list(FMTS))
+def test_layout_roundtrip(E, prec):
+    x = gen(3, 72, 5, 7)
+    y = act_of(E, x, FMTS[prec]).to_nchw().cpu()
+    assert rel_l2(y, x) < ELEM_TOL[prec]
+
+
+@pytest.mark.parametrize("rows,labels", [(5, False), (3, True)])
+def test_time_embed_project(E, rows, labels):
+    from oracle import score_ref
+    te = 256
+    tp = E.TimeProjector(torch.device("cuda"), te)
+    W0, W1 = gen(128, seed=1, scale=30.0), gen(128, seed=2, scale=30.0)
+    s0, s1 = tp.add_set(W0.cuda()), tp.add_set(W1.cuda())
+    heads = [("a", s0, 64), ("b", s0, 128), ("c", s1, 256)]
+    ws = {}
+    for i, (name, s, c) in enumerate(heads):
+        ws[name] = (gen(c, te, seed=10 + i, scale=0.06), gen(c, seed=20 + i, scale=0.1))
+        tp.add_head(name, s, ws[name][0].cuda(), ws[name][1].cuda())
+    lab = gen(5, te, seed=30, scale=0.5)
+    tp.label_emb = lab.cuda() if labels else None
+    tp.finalize()
+    t = torch.rand(rows, generator=torch.Generator().manual_seed(3))
+    y = torch.tensor([1, 4, 0][:rows]) if labels else None
+    out = tp(t.cuda(), None if y is None else y.cuda()).cpu()
+    for name, s, c in heads:
+        emb = score_ref.fourier_embed(W0 if s == s0 else W1, t)
+        if labels and s == s0:
+            emb = emb + lab[y]
+        want = F.linear(F.silu(emb), *ws[name])
+        got = tp.cols(out, name)
+        assert rel_l2(got, want) < 2e-5, name
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("cc,bcast", [(1, False), (6, True)])
+def test_stem_conv(E, prec, cc, bcast):
+    from sbgm_danra_b200._lib import call
+    n, h = 3, 64
+    x = gen(n, 1, h, h, seed=1)
+    planes = gen(1 if bcast else n, cc, h, h, seed=2)
+    w = gen(64, cc + 1, 8, 8, seed=3, scale=0.1)
+    tproj = gen(n, 100, seed=4)
+    full = torch.cat([x, planes.expand(n, -1, -1, -1)], 1)
+    want = F.conv2d(full, w, stride=2, padding=3) + tproj[:, 10:74, None, None]
+    wp = w.permute(1, 2, 3, 0).reshape(cc + 1, 64, 64).contiguous().cuda()
+    fmt = FMTS[prec]
+    xd, pd, td = x.cuda(), planes.cuda().contiguous(), tproj.cuda()
+    tview = td[:, 10:74]
+    st = torch.cuda.current_stream().cuda_stream
+    # (a) everything in one launch
+    out = E.Act(fmt, n, h // 2, h // 2, 64, "cuda")
+    call("sbgm_stem_conv", xd.data_ptr(), pd.data_ptr(), pd.shape[0], cc, 0, cc + 1, wp.data_ptr(), None, 0,
+         tview.data_ptr(), tview.stride(0), out.ptr, out.plane, fmt, n, h, h, st)
+    assert rel_l2(out.to_nchw().cpu(), want) < TOL[prec]
+    # (b) step-invariant conditioning partial + per-step x channel (sampler split)
+    part = E.Act(0, pd.shape[0], h // 2, h // 2, 64, "cuda")
+    call("sbgm_stem_conv", None, pd.data_ptr(), pd.shape[0], cc, 1, cc + 1, wp.data_ptr(), None, 0, None, 0,
+         part.ptr, part.plane, 0, pd.shape[0], h, h, st)
+    out2 = E.Act(fmt, n, h // 2, h // 2, 64, "cuda")
+    call("sbgm_stem_conv", xd.data_ptr(), None, 1, cc, 0, 1, wp.data_ptr(), part.ptr, pd.shape[0],
+         tview.data_ptr(), tview.stride(0), out2.ptr, out2.plane, fmt, n, h, h, st)
+    assert rel_l2(out2.to_nchw().cpu(), want) < TOL[prec]
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, epilogue
+    (2, 32, 32, 64, 64, 3, 1, 1, "plain"),
+    (2, 32, 32, 64, 64, 3, 1, 1, "full"),
+    (3, 8, 8, 128, 256, 3, 1, 1, "full"),
+    (2, 16, 16, 64, 128, 3, 2, 1, "relu"),
+    (2, 16, 16, 64, 128, 1, 2, 0, "plain"),
+    (2, 32, 32, 64, 64, 8, 2, 3, "relu"),
+    (3, 4, 4, 256, 512, 3, 1, 1, "full"),
+    (5, 2, 2, 512, 512, 3, 1, 1, "plain"),
+    (3, 1, 1, 512, 512, 3, 1, 1, "plain"),
+    (1, 1, 200, 128, 384, 1, 1, 0, "gelu"),       # Linear over 200 tokens (tail masking)
+    (1, 1, 1024, 512, 1536, 1, 1, 0, "plain"),    # in_proj of the 512-channel attention
+    (1, 64, 64, 64, 64, 3, 1, 1, "full"),
+    (2, 12, 24, 64, 192, 3, 1, 1, "full"),        # non power-of-two spatial, cout = 3 x 64
+]
+
+
+@pytest.mark.parametrize("prec", list(FMTS))
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv2d(E, prec, case):
+    n, h, w, cin, cout, k, stride, pad, epi = case
+    fmt = FMTS[prec]
+    x = gen(n, cin, h, w, seed=1)
+    wt = gen(cout, cin, k, k, seed=2, scale=1.0 / math.sqrt(cin * k * k))
+    bias = gen(cout, seed=3, scale=0.1) if epi != "plain" else None
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = gen(n, cout, ho, wo, seed=4) if epi == "full" else None
+    tproj = gen(n, cout + 7, seed=5) if epi == "full" else None
+    act = {"plain": 0, "full": 1, "relu": 1, "gelu": 3}[epi]
+    want = F.conv2d(x, wt, bias, stride=stride, padding=pad)
+    if res is not None:
+        want = want + res
+    want = {0: lambda v: v, 1: F.relu, 3: F.gelu}[act](want)
+    if tproj is not None:
+        want = want + tproj[:, 3:3 + cout, None, None]
+    kern = E.Kernels(fmt, torch.device("cuda"))
+    sd = {"w": wt}
+    if bias is not None:
+        sd["b"] = bias
+    cw = E._Packer(sd, fmt, torch.device("cuda")).conv("w", "b" if bias is not None else None)
+    tp = tproj.cuda()[:, 3:3 + cout] if tproj is not None else None
+    out = kern.conv(act_of(E, x, fmt), cw, stride=stride, pad=pad, act=act,
+                    residual=None if res is None else act_of(E, res, fmt), tproj=tp)
+    torch.cuda.synchronize()
+    assert (out.h, out.w, out.c) == (ho, wo, cout)
+    err = rel_l2(out.to_nchw().cpu(), want)
+    assert err < TOL[prec], f"rel-L2 {err:.3e}"
+
+
+def test_conv_bn_fold(E):
+    """Eval-mode BatchNorm folded into the packed convolution (engine._Packer.conv)."""
+    x = gen(2, 64, 16, 16, seed=1)
+    sd = {"c.weight": gen(128, 64, 3, 3, seed=2, scale=0.05), "bn.weight": 1 + 0.1 * gen(128, seed=3),
+          "bn.bias": gen(128, seed=4, scale=0.1), "bn.running_mean": gen(128, seed=5, scale=0.1),
+          "bn.running_var": torch.rand(128, generator=torch.Generator().manual_seed(6)) + 0.5}
+    want = F.relu(F.batch_norm(F.conv2d(x, sd["c.weight"], padding=1), sd["bn.running_mean"], sd["bn.running_var"],
+                               sd["bn.weight"], sd["bn.bias"], False, 0.0, 1e-5))
+    for prec in ("fp32", "bf16x3"):
+        fmt = FMTS[prec]
+        cw = E._Packer(sd, fmt, torch.device("cuda")).conv("c.weight", bn="bn")
+        out = E.Kernels(fmt, torch.device("cuda")).conv(act_of(E, x, fmt), cw, pad=1, act=1)
+        assert rel_l2(out.to_nchw().cpu(), want) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", list(FMTS))
+@pytest.mark.parametrize("c,groups,hw,fused", [(64, 8, 32, True), (512, 8, 8, False), (128, 128, 16, True), (256, 8, 4, True)])
+def test_groupnorm(E, prec, c, groups, hw, fused):
+    fmt = FMTS[prec]
+    n = 3
+    x = gen(n, c, hw, hw, seed=1) * 2 + 0.5
+    instance = groups == c
+    gamma = None if instance else 1 + 0.2 * gen(c, seed=2)
+    beta = None if instance else gen(c, seed=3, scale=0.2)
+    skip = gen(n, c, hw, hw, seed=4) if fused else None
+    tproj = gen(n, c, seed=5) if fused else None
+    if prec != "fp32":   # compare against the norm of what the kernel actually reads
+        x = act_of(E, x, fmt).to_nchw().cpu()
+    want = F.instance_norm(x, eps=1e-5) if instance else F.group_norm(x, groups, gamma, beta, 1e-5)
+    if fused:
+        want = F.silu(want + skip + tproj[:, :, None, None])
+    kern = E.Kernels(fmt, torch.device("cuda"))
+    out = kern.groupnorm(act_of(E, x, fmt), None if gamma is None else gamma.cuda(), None if beta is None else beta.cuda(),
+                         groups, act=2 if fused else 0, skip=None if skip is None else act_of(E, skip, fmt),
+                         tproj=None if tproj is None else tproj.cuda())
+    tol = {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3}[prec]
+    assert rel_l2(out.to_nchw().cpu(), want) < tol
+
+
+@pytest.mark.parametrize("prec", list(FMTS))
+@pytest.mark.parametrize("c", [128, 256, 512])
+def test_layernorm(E, prec, c):
+    fmt = FMTS[prec]
+    x = gen(1, c, 1, 77, seed=1) * 3 + 1
+    if prec != "fp32":
+        x = act_of(E, x, fmt).to_nchw().cpu()
+    g, b = 1 + 0.2 * gen(c, seed=2), gen(c, seed=3, scale=0.2)
+    want = F.layer_norm(x[0, :, 0].T, (c,), g, b, 1e-5).T[None, :, None]
+    out = E.Kernels(fmt, torch.device("cuda")).layernorm(act_of(E, x, fmt), g.cuda(), b.cuda())
+    tol = {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3}[prec]
+    assert rel_l2(out.to_nchw().cpu(), want) < tol
+
+
+@pytest.mark.parametrize("prec", list(FMTS))
+def test_upsample2x(E, prec):
+    fmt = FMTS[prec]
+    x = gen(2, 64, 5, 9, seed=1)
+    if prec != "fp32":
+        x = act_of(E, x, fmt).to_nchw().cpu()
+    want = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    out = E.Kernels(fmt, torch.device("cuda")).upsample2x(act_of(E, x, fmt))
+    assert rel_l2(out.to_nchw().cpu(), want) < ELEM_TOL[prec] * 2
+
+
+@pytest.mark.parametrize("prec", list(FMTS))
+@pytest.mark.parametrize("b,s,c,heads", [(2, 64, 256, 4), (3, 16, 512, 4), (2, 256, 128, 4), (1, 100, 128, 16), (2, 40, 256, 1)])
+def test_attention_core(E, prec, b, s, c, heads):
+    fmt = FMTS[prec]
+    qkv = gen(1, 3 * c, 1, b * s, seed=1)
+    if prec != "fp32":
+        qkv = act_of(E, qkv, fmt).to_nchw().cpu()
+    tok = qkv[0, :, 0].T.reshape(b, s, 3 * c)
+    d = c // heads
+    q, k, v = (z.reshape(b, s, heads, d).permute(0, 2, 1, 3) for z in tok.chunk(3, dim=-1))
+    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).permute(0, 2, 1, 3).reshape(b * s, c)
+    out = E.Kernels(fmt, torch.device("cuda")).attention_core(act_of(E, qkv, fmt), b, s, c, heads)
+    got = out.to_nchw().cpu()[0, :, 0].T
+    assert rel_l2(got, want) < {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3}[prec]
+
+
+@pytest.mark.parametrize("prec", list(FMTS))
+def test_final_conv(E, prec):
+    from sbgm_danra_b200._lib import call
+    fmt = FMTS[prec]
+    n, h = 3, 32
+    x = gen(n, 64, h, h, seed=1)
+    if prec != "fp32":
+        x = act_of(E, x, fmt).to_nchw().cpu()
+    w, bias, inv = gen(1, 64, 3, 3, seed=2, scale=0.05), gen(1, seed=3), torch.tensor([0.5, 2.0, 10.0])
+    want = F.conv2d(x, w, bias, padding=1) * inv[:, None, None, None]
+    a = act_of(E, x, fmt)
+    wp = w.permute(0, 2, 3, 1).reshape(1, 9, 64).contiguous().cuda()
+    out = torch.empty(n, 1, h, h, device="cuda")
+    call("sbgm_final_conv", a.ptr, a.plane, fmt, wp.data_ptr(), bias.cuda().data_ptr(), inv.cuda().data_ptr(), 1, 0, None,
+         out.data_ptr(), n, h, h, 64, 1, torch.cuda.current_stream().cuda_stream)
+    assert rel_l2(out.cpu(), want) < 1e-5
+
+
+def test_philox_matches_numpy_restatement():
+    from oracle import philox_ref
+    from sbgm_danra_b200._lib import call
+    st = torch.cuda.current_stream().cuda_stream
+    for count, first in ((4096, 0), (1001, 64)):
+        out = torch.empty(count, device="cuda")
+        call("sbgm_philox_normal", out.data_ptr(), count, 0x1234567890ABCDEF, 5, first, st)
+        want = philox_ref.normal(count, 0x1234567890ABCDEF, 5, first)
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=0, atol=3e-6)
+        call("sbgm_philox_uniform", out.data_ptr(), count, 99, 2, first, st)
+        np.testing.assert_array_equal(out.cpu().numpy(), philox_ref.uniform(count, 99, 2, first))   # bit-exact
+
+
+def test_sampler_update_kernels():
+    from oracle import philox_ref
+    from sbgm_danra_b200._lib import STEP_COLS, call
+    st = torch.cuda.current_stream().cuda_stream
+    b, per, seed = 3, 32 * 32, 77
+    x0, s = gen(b, 1, 32, 32, seed=1), gen(b, 1, 32, 32, seed=2)
+    table = torch.zeros(4, STEP_COLS)
+    table[:, 4] = torch.tensor([0.3, 0.2, 0.1, 0.05])
+    table[:, 5] = torch.tensor([0.9, 0.7, 0.5, 0.3])
+    tab, counter = table.cuda(), torch.tensor([2, 0], dtype=torch.int32, device="cuda")
+    x, mean = x0.cuda().clone(), torch.empty(b, 1, 32, 32, device="cuda")
+    first = 5 * per   # this shard starts at global member 5
+    call("sbgm_sampler_predictor", x.data_ptr(), s.cuda().data_ptr(), mean.data_ptr(), x.numel(), tab.data_ptr(),
+         counter.data_ptr(), seed, 1, 1, first, st)
+    z = torch.from_numpy(philox_ref.normal(b * per, seed, 1 + 2, first)).reshape(x0.shape)
+    want_mean = x0 + 0.1 * s
+    assert rel_l2(mean.cpu(), want_mean) < 1e-6
+    assert rel_l2(x.cpu(), want_mean + 0.5 * z) < 1e-6
+    assert counter.cpu().tolist() == [3, 0]
+    # corrector
+    sumsq = torch.empty(b, device="cuda")
+    call("sbgm_sampler_sumsq", s.cuda().data_ptr(), sumsq.data_ptr(), b, per, st)
+    np.testing.assert_allclose(sumsq.cpu().numpy(), (s.reshape(b, -1) ** 2).sum(1).numpy(), rtol=1e-5)
+    x = x0.cuda().clone()
+    call("sbgm_sampler_corrector", x.data_ptr(), s.cuda().data_ptr(), sumsq.data_ptr(), b, per, 0.16, x.numel(),
+         counter.data_ptr(), seed, 1, 2, first, st)
+    gn = torch.norm(s.reshape(b, -1), dim=-1).mean()
+    eps = 2 * (0.16 * math.sqrt(per) / gn) ** 2
+    z = torch.from_numpy(philox_ref.normal(b * per, seed, 1 + 2 * 3, first)).reshape(x0.shape)
+    assert rel_l2(x.cpu(), x0 + eps * s + torch.sqrt(2 * eps) * z) < 1e-6
+
+
+def test_dsm_kernels():
+    from oracle import philox_ref
+    from sbgm_danra_b200 import _lib
+    from sbgm_danra_b200._lib import call
+    st = torch.cuda.current_stream().cuda_stream
+    n, per, seed = 4, 32 * 32, 11
+    x, std = gen(n, 1, 32, 32, seed=1), torch.tensor([0.1, 1.0, 5.0, 20.0])
+    xt, z = torch.empty(n, 1, 32, 32, device="cuda"), torch.empty(n, 1, 32, 32, device="cuda")
+    call("sbgm_dsm_perturb", x.cuda().data_ptr(), std.cuda().data_ptr(), xt.data_ptr(), z.data_ptr(), n, per, seed, 1, 0, st)
+    zr = torch.from_numpy(philox_ref.normal(n * per, seed, 1)).reshape(x.shape)
+    assert rel_l2(z.cpu(), zr) < 1e-6 and rel_l2(xt.cpu(), x + std[:, None, None, None] * zr) < 1e-6
+    score, sdf = gen(n, 1, 32, 32, seed=3), gen(n, 1, 32, 32, seed=4)
+    partials = torch.empty(_lib.query("sbgm_dsm_scratch_floats", n * per), device="cuda")
+    loss = torch.empty((), device="cuda")
+    for sd_ in (sdf, None):
+        call("sbgm_dsm_loss", score.cuda().data_ptr(), std.cuda().data_ptr(), z.data_ptr(),
+             None if sd_ is None else sd_.cuda().data_ptr(), n, per, partials.data_ptr(), loss.data_ptr(), st)
+        w = torch.sigmoid(sd_) * 0.5 + 0.5 if sd_ is not None else torch.ones_like(x)
+        want = torch.mean(torch.sum(w * (score * std[:, None, None, None] + zr) ** 2, dim=(1, 2, 3)))
+        assert abs(loss.item() - want.item()) / want.item() < 1e-5

@@ -1,0 +1,140 @@
+"""CPU-only tests of the host side: module tree / checkpoint ABI, constructor errors, step tables,
+the `sbgm` import shim, and the no-CPU-fallback rule."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from conftest import GOLDEN_DIR
+from oracle import score_ref
+from oracle.synth import config_for, param_schema, synth_state_dict
+
+
+def _build(cfg, device="cpu"):
+    from sbgm_danra_b200._smoke import build_model
+    return build_model(cfg, synth_state_dict(cfg), "bf16x3", device)
+
+
+@pytest.mark.parametrize("ck", [dict(n_lr=1), dict(n_lr=2, geo=True, seasons=True),
+                                dict(n_lr=1, norm="instance", activation="relu", block_layers=(3, 4, 6, 3)),
+                                dict(n_lr=1, use_resize_conv=False, activation="gelu", n_heads=8)])
+def test_module_tree_has_reference_state_dict_keys(ck):
+    cfg = config_for(**ck)
+    net = _build(cfg)       # load_state_dict(strict=True) inside
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert mine == dict(param_schema(cfg))
+
+
+def test_schema_equals_reference_and_param_count():
+    with open(os.path.join(GOLDEN_DIR, "reference_schema.json")) as f:
+        ref = json.load(f)["fwd_c1_64_cin2"]
+    net = _build(config_for(n_lr=1))
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == ref
+    assert sum(p.numel() for p in net.parameters()) == 19_062_082
+
+
+def test_constructor_errors_match_reference():
+    from sbgm_danra_b200.score_unet import Decoder, DecoderBlock, Encoder, ImageSelfAttention, SinusoidalEmbedding
+    with pytest.raises(ValueError):
+        SinusoidalEmbedding(7)
+    with pytest.raises(ValueError):
+        ImageSelfAttention(64, 5)
+    with pytest.raises(ValueError):          # 64 % 3 != 0 inside make_attention_layers -> Optuna prunes on it
+        Encoder(1, 256, n_heads=3, device="cpu")
+    blk = DecoderBlock(64, 32, 256, device="cpu", norm="group", activation=nn.SiLU)
+    assert isinstance(blk.norm1, nn.GroupNorm) and blk.norm1.num_groups == 8
+    assert isinstance(DecoderBlock(64, 32, 256, device="cpu").norm1, nn.InstanceNorm2d)
+    dec = Decoder(512, 1, 256, device="cpu", norm="group", activation=nn.SiLU)
+    assert [(b.input_channels, b.output_channels, b.compute_attn) for b in dec.residual_layers] == \
+        [(512, 256, True), (256, 128, True), (128, 64, False), (64, 64, False)]
+    assert isinstance(dec.final_layer.norm1, nn.Identity) and isinstance(dec.final_layer.activation, nn.Identity)
+
+
+def test_no_cpu_fallback():
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    net = _build(config_for(n_lr=1))
+    x, t, c = torch.randn(1, 1, 32, 32), torch.rand(1), torch.randn(1, 1, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        net(x, t, None, c)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ss.Euler_Maruyama_sampler(lambda *a: a[0], marginal_prob_std_fn, diffusion_coeff_fn, batch_size=1, num_steps=2,
+                                  device="cpu", img_size=32)
+
+
+def test_sde_scalars_match_reference_golden(golden):
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    t = torch.from_numpy(golden["sde/t"])
+    np.testing.assert_allclose(marginal_prob_std_fn(t).numpy(), golden["sde/std"], rtol=1e-6)
+    np.testing.assert_allclose(diffusion_coeff_fn(t).numpy(), golden["sde/g"], rtol=1e-6)
+
+
+def test_step_tables_follow_reference_arithmetic():
+    from sbgm_danra_b200 import score_sampling as ss
+    n, eps = 7, 1e-3
+    em = ss._table_em(score_ref.marginal_prob_std, score_ref.diffusion_coeff, n, eps)
+    ts = torch.linspace(1.0, eps, n)
+    dt = ts[0] - ts[1]
+    g = score_ref.diffusion_coeff(ts)
+    assert torch.equal(em[:, 0], ts) and torch.equal(em[:, 1], g)
+    assert torch.allclose(em[:, 4], g ** 2 * dt, rtol=1e-7) and torch.allclose(em[:, 5], torch.sqrt(dt) * g, rtol=1e-7)
+    assert torch.allclose(em[:, 3], 1.0 / score_ref.marginal_prob_std(ts), rtol=1e-7)
+    pc = ss._table_pc(score_ref.marginal_prob_std, score_ref.diffusion_coeff, n, eps)
+    ts64 = np.linspace(1.0, eps, n)
+    assert np.array_equal(pc[:, 0].numpy(), ts64.astype(np.float32))
+    gp = score_ref.diffusion_coeff(torch.from_numpy(ts64.astype(np.float32)))
+    assert torch.allclose(pc[:, 5], torch.sqrt(gp ** 2 * (ts64[0] - ts64[1])), rtol=1e-7)
+
+
+def test_cfg_lookup_and_mask_strip():
+    from sbgm_danra_b200 import score_sampling as ss
+    assert ss._cfg_scale(None, False) is None
+    assert ss._cfg_scale({"classifier_free_guidance": {"enabled": True}}, False) == 2.0
+    c = {"classifier_free_guidance": {"enabled": True, "guidance_scale": 5.0, "guidance_scale_max": 3.0}}
+    assert ss._cfg_scale(c, clamp=True) == 3.0 and ss._cfg_scale(c, clamp=False) == 5.0   # only pc_sampler clamps
+    v = torch.ones(2, 2, 4, 4)
+    s = ss._strip_mask(v)
+    assert s[:, 0].eq(1).all() and s[:, 1].eq(0).all() and v.eq(1).all()
+    assert ss._strip_mask(torch.ones(2, 3, 4, 4)).eq(1).all()
+
+
+def test_import_shim_redirects_reference_imports():
+    import sbgm_danra_b200
+    saved = {k: sys.modules.get(k) for k in ("sbgm", "sbgm.score_unet", "sbgm.score_sampling")}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        sbgm_danra_b200.install_as_sbgm()
+        from sbgm.score_sampling import Euler_Maruyama_sampler, guided_score_fn, ode_sampler, pc_sampler  # noqa: F401
+        from sbgm.score_unet import (Decoder, Encoder, ScoreNet, diffusion_coeff_fn, loss_fn,  # noqa: F401
+                                     marginal_prob_std_fn)
+        from sbgm_danra_b200.score_unet import ScoreNet as Mine
+        assert ScoreNet is Mine
+    finally:
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+
+
+def test_bn_fold_algebra_on_cpu():
+    """engine._Packer.conv folds eval-mode BatchNorm exactly (checked with torch on CPU tensors)."""
+    import torch.nn.functional as F
+    from sbgm_danra_b200 import engine
+    g = torch.Generator().manual_seed(0)
+    sd = {"c.weight": torch.randn(16, 8, 3, 3, generator=g), "bn.weight": torch.rand(16, generator=g) + 0.5,
+          "bn.bias": torch.randn(16, generator=g), "bn.running_mean": torch.randn(16, generator=g),
+          "bn.running_var": torch.rand(16, generator=g) + 0.5}
+    cw = engine._Packer(sd, engine.FMT_F32, "cpu").conv("c.weight", bn="bn")
+    x = torch.randn(2, 8, 6, 6, generator=g)
+    w = cw.w.reshape(3, 3, 8, 16).permute(3, 2, 0, 1)
+    got = F.conv2d(x, w, cw.bias, padding=1)
+    want = F.batch_norm(F.conv2d(x, sd["c.weight"], padding=1), sd["bn.running_mean"], sd["bn.running_var"],
+                        sd["bn.weight"], sd["bn.bias"], False, 0.0, 1e-5)
+    assert torch.allclose(got, want, atol=1e-5)
+    hi_lo = engine._split_bf16(x)
+    assert (hi_lo[0].float() + hi_lo[1].float() - x).abs().max() < 2e-5 * x.abs().max()
