@@ -53,6 +53,16 @@ _RESTYPES = {"sbgm_last_error": C.c_char_p, "sbgm_groupnorm_scratch_floats": _sz
 
 _lib: Optional[C.CDLL] = None
 
+# kernel launches issued per entry point (for bench.py's `gpu_launches` claim)
+_LAUNCHES = {"sbgm_groupnorm": 2, "sbgm_dsm_loss": 2}
+
+
+class _Stats:
+    launches = 0          # kernels launched eagerly or recorded into a CUDA graph through call()
+
+
+stats = _Stats()
+
 
 def load_library() -> C.CDLL:
     """dlopen the in-tree library and bind every symbol of include/sbgm_b200.h (no compute is run)."""
@@ -76,6 +86,7 @@ def call(name: str, *args) -> None:
     """Invoke a status-returning entry point; raise RuntimeError with the library's message on failure."""
     lib = load_library()
     status = getattr(lib, name)(*args)
+    stats.launches += _LAUNCHES.get(name, 1)
     if status != 0:
         msg = lib.sbgm_last_error()
         raise RuntimeError(f"{name} failed (status {status}): {msg.decode() if msg else '?'}")

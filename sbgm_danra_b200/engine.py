@@ -381,7 +381,7 @@ class DecoderEngine:
 
     def forward(self, fmaps: List[Act], tproj: torch.Tensor, inv_std: Optional[torch.Tensor], *,
                 inv_std_stride: int = 1, inv_std_step_stride: int = 0, step_counter: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                dst: Optional[torch.Tensor] = None) -> torch.Tensor:
         k, tp = self.k, self.tp
         rev = list(reversed(fmaps))
         out = rev[0]
@@ -398,7 +398,7 @@ class DecoderEngine:
                 out = attention_block(k, blk["attn"], out)
         up = k.upsample2x(out)
         a = k.conv(up, self.final_up, pad=1)
-        res = out if out is not None else torch.empty((a.n, self.out_channels, a.h, a.w), dtype=torch.float32, device=self.device)
+        res = dst if dst is not None else torch.empty((a.n, self.out_channels, a.h, a.w), dtype=torch.float32, device=self.device)
         call("sbgm_final_conv", a.ptr, a.plane, self.fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std),
              inv_std_stride, inv_std_step_stride, _ptr(step_counter), res.data_ptr(), a.n, a.h, a.w, a.c,
              self.out_channels, _stream())

@@ -24,6 +24,7 @@ import torch
 
 from . import engine as _eng
 from ._lib import STEP_COLS, call
+from ._lib import stats as _lib_stats
 
 logger = logging.getLogger(__name__)
 
@@ -190,7 +191,7 @@ class _NativeStep:
         else:
             fmaps = eng.enc.forward(self.x, None, tproj, partial=partial)
         eng.dec.forward(fmaps, tproj, self.inv_std, inv_std_stride=0, inv_std_step_stride=STEP_COLS,
-                        step_counter=self.counter, out=out)
+                        step_counter=self.counter, dst=out)
 
     def score_into(self) -> torch.Tensor:
         if self.cfg_scale is None:
@@ -290,13 +291,17 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
             torch.cuda.current_stream(dev).wait_stream(side)
             st.counter.zero_()
             graph = torch.cuda.CUDAGraph()
+            before = _lib_stats.launches
             with torch.cuda.graph(graph):
                 one_step()
+            per_replay = _lib_stats.launches - before     # kernels recorded in the graph
+            _lib_stats.launches = before
             st.counter.zero_()
         call("sbgm_sampler_init", st.x.data_ptr(), st.x.numel(), std1, seed, first_elem, _eng._stream())
         for k in range(n_steps):
             if graph is not None:
                 graph.replay()
+                _lib_stats.launches += per_replay
             else:
                 if not native:
                     st.k = k

@@ -242,7 +242,8 @@ def test_final_conv(E, prec):
     a = act_of(E, x, fmt)
     wp = w.permute(0, 2, 3, 1).reshape(1, 9, 64).contiguous().cuda()
     out = torch.empty(n, 1, h, h, device="cuda")
-    call("sbgm_final_conv", a.ptr, a.plane, fmt, wp.data_ptr(), bias.cuda().data_ptr(), inv.cuda().data_ptr(), 1, 0, None,
+    bias_d, inv_d = bias.cuda(), inv.cuda()      # keep the device copies alive across the launch
+    call("sbgm_final_conv", a.ptr, a.plane, fmt, wp.data_ptr(), bias_d.data_ptr(), inv_d.data_ptr(), 1, 0, None,
          out.data_ptr(), n, h, h, 64, 1, torch.cuda.current_stream().cuda_stream)
     assert rel_l2(out.cpu(), want) < 1e-5
 
@@ -266,13 +267,14 @@ def test_sampler_update_kernels():
     st = torch.cuda.current_stream().cuda_stream
     b, per, seed = 3, 32 * 32, 77
     x0, s = gen(b, 1, 32, 32, seed=1), gen(b, 1, 32, 32, seed=2)
+    s_d = s.cuda()
     table = torch.zeros(4, STEP_COLS)
     table[:, 4] = torch.tensor([0.3, 0.2, 0.1, 0.05])
     table[:, 5] = torch.tensor([0.9, 0.7, 0.5, 0.3])
     tab, counter = table.cuda(), torch.tensor([2, 0], dtype=torch.int32, device="cuda")
     x, mean = x0.cuda().clone(), torch.empty(b, 1, 32, 32, device="cuda")
     first = 5 * per   # this shard starts at global member 5
-    call("sbgm_sampler_predictor", x.data_ptr(), s.cuda().data_ptr(), mean.data_ptr(), x.numel(), tab.data_ptr(),
+    call("sbgm_sampler_predictor", x.data_ptr(), s_d.data_ptr(), mean.data_ptr(), x.numel(), tab.data_ptr(),
          counter.data_ptr(), seed, 1, 1, first, st)
     z = torch.from_numpy(philox_ref.normal(b * per, seed, 1 + 2, first)).reshape(x0.shape)
     want_mean = x0 + 0.1 * s
@@ -281,10 +283,10 @@ def test_sampler_update_kernels():
     assert counter.cpu().tolist() == [3, 0]
     # corrector
     sumsq = torch.empty(b, device="cuda")
-    call("sbgm_sampler_sumsq", s.cuda().data_ptr(), sumsq.data_ptr(), b, per, st)
+    call("sbgm_sampler_sumsq", s_d.data_ptr(), sumsq.data_ptr(), b, per, st)
     np.testing.assert_allclose(sumsq.cpu().numpy(), (s.reshape(b, -1) ** 2).sum(1).numpy(), rtol=1e-5)
     x = x0.cuda().clone()
-    call("sbgm_sampler_corrector", x.data_ptr(), s.cuda().data_ptr(), sumsq.data_ptr(), b, per, 0.16, x.numel(),
+    call("sbgm_sampler_corrector", x.data_ptr(), s_d.data_ptr(), sumsq.data_ptr(), b, per, 0.16, x.numel(),
          counter.data_ptr(), seed, 1, 2, first, st)
     gn = torch.norm(s.reshape(b, -1), dim=-1).mean()
     eps = 2 * (0.16 * math.sqrt(per) / gn) ** 2
@@ -300,15 +302,17 @@ def test_dsm_kernels():
     n, per, seed = 4, 32 * 32, 11
     x, std = gen(n, 1, 32, 32, seed=1), torch.tensor([0.1, 1.0, 5.0, 20.0])
     xt, z = torch.empty(n, 1, 32, 32, device="cuda"), torch.empty(n, 1, 32, 32, device="cuda")
-    call("sbgm_dsm_perturb", x.cuda().data_ptr(), std.cuda().data_ptr(), xt.data_ptr(), z.data_ptr(), n, per, seed, 1, 0, st)
+    x_d, std_d = x.cuda(), std.cuda()
+    call("sbgm_dsm_perturb", x_d.data_ptr(), std_d.data_ptr(), xt.data_ptr(), z.data_ptr(), n, per, seed, 1, 0, st)
     zr = torch.from_numpy(philox_ref.normal(n * per, seed, 1)).reshape(x.shape)
     assert rel_l2(z.cpu(), zr) < 1e-6 and rel_l2(xt.cpu(), x + std[:, None, None, None] * zr) < 1e-6
     score, sdf = gen(n, 1, 32, 32, seed=3), gen(n, 1, 32, 32, seed=4)
     partials = torch.empty(_lib.query("sbgm_dsm_scratch_floats", n * per), device="cuda")
     loss = torch.empty((), device="cuda")
+    score_d, sdf_d = score.cuda(), sdf.cuda()
     for sd_ in (sdf, None):
-        call("sbgm_dsm_loss", score.cuda().data_ptr(), std.cuda().data_ptr(), z.data_ptr(),
-             None if sd_ is None else sd_.cuda().data_ptr(), n, per, partials.data_ptr(), loss.data_ptr(), st)
+        call("sbgm_dsm_loss", score_d.data_ptr(), std_d.data_ptr(), z.data_ptr(),
+             None if sd_ is None else sdf_d.data_ptr(), n, per, partials.data_ptr(), loss.data_ptr(), st)
         w = torch.sigmoid(sd_) * 0.5 + 0.5 if sd_ is not None else torch.ones_like(x)
         want = torch.mean(torch.sum(w * (score * std[:, None, None, None] + zr) ** 2, dim=(1, 2, 3)))
         assert abs(loss.item() - want.item()) / want.item() < 1e-5
