@@ -94,7 +94,29 @@ int sbgm_stem_conv(const float* x, const float* planes, int np, int cc, int c_be
 int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
                    const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
                    void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
-                   int kh, int kw, int stride, int pad, int act, void* stream);
+                   int kh, int kw, int stride, int pad, int act,
+                   const float* proj_w, int n_proj, float* proj_out, void* stream);
+/* The same operator specialised for the 64 -> 64 channel 3x3 stride-1 convolutions that carry 45% of
+ * the network's FLOPs (encoder layer1, decoder blocks 3 and final conv_up): a persistent kernel (one
+ * CTA per SM) keeps the whole 9 x 64 x 64 weight tensor resident in shared memory, fetches each
+ * input tile as three (rows+2)-high halo slabs that serve all nine taps (2.4x less L2->SM traffic
+ * than per-tap boxes) and double-buffers the TMEM accumulator so the epilogue of one tile overlaps
+ * the MMAs of the next.  Requires h % 8 == 0 and w % 16 == 0.  Extra outputs:
+ *   proj_w / proj_out : as above
+ *   gn_partials       : if non-NULL, per-(image, 32-pixel strip) GroupNorm partial sums of the stored
+ *                       values, layout [n][chunks][groups][2] with chunks = (h/8)*(w/16)*4 and
+ *                       groups = 64 / gn_cpg, consumed by sbgm_groupnorm_apply (saves the statistics
+ *                       pass over the activations).
+ */
+int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                     const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
+                     void* out, size_t out_plane, int fmt, int n, int h, int w, int act,
+                     const float* proj_w, int n_proj, float* proj_out, float* gn_partials, int gn_cpg, void* stream);
+/* Projection epilogue (proj_w != NULL, cout == 64 only): instead of storing the 64 output channels the
+ * kernel stores proj_out[pix][SBGM_PROJ_STRIDE] = sum_c v[c] * proj_w[q][c] for q < n_proj (fp32) -- the
+ * nine per-tap partial products of the final 64 -> 1 convolution, so its input never touches HBM.
+ * bias, tproj rows and proj_w must be 16-byte aligned. */
+#define SBGM_PROJ_STRIDE 12
 int sbgm_conv2d_simt(const float* in, const float* weight, const float* bias, const float* residual,
                      const float* tproj, int tproj_stride, float* out, int n, int h, int w, int cin, int cout,
                      int kh, int kw, int stride, int pad, int act, void* stream);
@@ -110,6 +132,11 @@ size_t sbgm_groupnorm_scratch_floats(int n, int c, int hw);
 int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const float* beta, int groups, float eps,
                    const void* skip, size_t skip_plane, const float* tproj, int tproj_stride, int act,
                    void* y, size_t y_plane, int fmt, int n, int hw, int c, float* partials, void* stream);
+/* The apply half alone, from partial sums [n][chunks][groups][2] produced by a convolution epilogue. */
+int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, int chunks, const float* gamma,
+                         const float* beta, int groups, float eps, const void* skip, size_t skip_plane,
+                         const float* tproj, int tproj_stride, int act, void* y, size_t y_plane, int fmt,
+                         int n, int hw, int c, void* stream);
 /* LayerNorm over the channel axis of [rows][c] tokens (ImageSelfAttention.ln1/ln2, :127-128). */
 int sbgm_layernorm(const void* x, size_t x_plane, const float* gamma, const float* beta, float eps,
                    void* y, size_t y_plane, int fmt, int rows, int c, void* stream);
@@ -133,6 +160,12 @@ int sbgm_attention(const void* qkv, size_t qkv_plane, void* out, size_t out_plan
 int sbgm_final_conv(const void* in, size_t in_plane, int fmt, const float* weight, const float* bias,
                     const float* inv_std, int inv_std_stride, int inv_std_step_stride, const int32_t* step_counter,
                     float* out, int n, int h, int w, int cin, int cout, void* stream);
+/* Second half of the fused final convolution: gathers the per-tap partial products written by the
+ * projection epilogue, out[n][0][y][x] = (sum_{r,s} proj[n][y+r-1][x+s-1][3r+s] + bias) * s_n
+ * (zero outside the image = the convolution's zero padding). */
+int sbgm_final_gather(const float* proj, const float* bias, const float* inv_std, int inv_std_stride,
+                      int inv_std_step_stride, const int32_t* step_counter, float* out, int n, int h, int w,
+                      void* stream);
 
 /* ---- counter-based noise + fused sampler updates -------------------------------------------
  * Noise stream: Philox4x32-10, key = seed, counter = (elem/4, draw); see oracle/philox_ref.py

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsbgm_b200.so")
 FMT_F32, FMT_BF16, FMT_BF16X2 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
 STEP_COLS = 8
+PROJ_STRIDE = 12
 
 _p, _sz, _i, _f, _u64, _u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
@@ -27,7 +28,10 @@ PROTOTYPES = {
     "sbgm_fourier_embed": [_p, _p, _i, _p, _i, _p],
     "sbgm_cfg_combine": [_p, _p, _f, _p, _sz, _p],
     "sbgm_stem_conv": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _sz, _i, _i, _i, _i, _p],
-    "sbgm_conv2d_tc": [_p, _sz, _p, _sz, _p, _p, _sz, _p, _i, _p, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sbgm_conv2d_tc": [_p, _sz, _p, _sz, _p, _p, _sz, _p, _i, _p, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p],
+    "sbgm_conv3x3_c64": [_p, _sz, _p, _sz, _p, _p, _sz, _p, _i, _p, _sz, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p],
+    "sbgm_groupnorm_apply": [_p, _sz, _p, _i, _p, _p, _i, _f, _p, _sz, _p, _i, _i, _p, _sz, _i, _i, _i, _i, _p],
+    "sbgm_final_gather": [_p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _p],
     "sbgm_conv2d_simt": [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sbgm_groupnorm": [_p, _sz, _p, _p, _i, _f, _p, _sz, _p, _i, _i, _p, _sz, _i, _i, _i, _i, _p, _p],
     "sbgm_layernorm": [_p, _sz, _p, _p, _f, _p, _sz, _i, _i, _i, _p],

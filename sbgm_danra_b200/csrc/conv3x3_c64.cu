@@ -1,0 +1,245 @@
+// conv3x3_c64.cu -- persistent tcgen05 kernel for the 64 -> 64 channel 3x3 stride-1 convolutions
+// (encoder layer1, decoder block 3 and the final conv_up: 45% of the network's FLOPs, all with a
+// K loop of only nine 64-wide blocks, SURVEY.md section 7 "hard parts").
+//
+// The generic kernel (conv_tc.cu) re-fetches a 16 KB activation box and an 8 KB weight box for every
+// tap: 24 KB per 128 MMA-cycles, 4x more than the L2->SM path sustains.  Here
+//   * one CTA per SM stays resident and walks tiles blockIdx.x, +gridDim.x, ...;
+//   * the 9 x 64 x 64 weights (72 KB bf16, 144 KB split-bf16) are loaded ONCE per CTA and stay in smem;
+//   * a tile is 8 rows x 16 columns of one image; its input arrives as three halo slabs
+//     (one per horizontal tap offset s): box = 64 ch x 16 w x 10 h at (w0+s-1, h0-1), zero-filled outside
+//     the image.  Tap (r, s) reads slab s at byte offset r * 16 * 128 -- 1024-aligned, so the UMMA
+//     descriptor needs no base offset -- i.e. 3 x 20 KB serve nine taps;
+//   * two TMEM accumulators (2 x 64 columns) ping-pong between MMA issue and the epilogue warps.
+// Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..5 = epilogue.
+#include "tc_common.cuh"
+
+namespace sbgm {
+
+constexpr int kTH = 8, kTW = 16;                       // output tile (rows x cols) = 128 pixels
+constexpr uint32_t kSlabBytes = (kTH + 2) * kTW * 128;  // 20480 per plane
+constexpr uint32_t kWTapBytes = 64 * 128;               // 8192 per (tap, plane)
+
+struct C64Params {
+  int n, h, w;
+  int tiles_w, tiles_h, total_tiles;
+  EpilogueParams ep;
+  float* gn_partials;   // [n][chunks][8][2] or nullptr (groups of 8 channels)
+};
+
+template <int FMT, int kStages>
+struct C64Cfg {
+  static constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
+  static constexpr uint32_t kWeightBytes = 9 * kSplit * kWTapBytes;
+  static constexpr uint32_t kStageBytes = kSplit * kSlabBytes;
+  static constexpr uint32_t kBarOffset = kWeightBytes + kStages * kStageBytes;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 128 + 1024;
+};
+
+template <int FMT, int kStages>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const C64Params p) {
+  using Cfg = C64Cfg<FMT, kStages>;
+  constexpr int kSplit = Cfg::kSplit;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base;                              // [tap][plane][64 x 128 B]
+  const uint32_t slab_base = smem_base + Cfg::kWeightBytes;       // [stage][plane][10 x 16 x 128 B]
+  const uint32_t bar_base = smem_base + Cfg::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kStages);
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * kStages + 1 + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * kStages + 3 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 5);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 4);     // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights: 9 taps x planes boxes of 64 rows x 64 k
+      mbar_expect_tx(w_bar, Cfg::kWeightBytes);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int pl = 0; pl < kSplit; ++pl)
+          tma_load_3d(w_base + (tap * kSplit + pl) * kWTapBytes, &tmap_b, w_bar, tap * 64, 0, pl);
+      uint32_t sidx = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+        for (int s = 0; s < 3; ++s, ++sidx) {
+          const int stage = sidx % kStages;
+          const uint32_t phase = (sidx / kStages) & 1u;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          for (int pl = 0; pl < kSplit; ++pl)
+            tma_load_5d(slab_base + stage * Cfg::kStageBytes + pl * kSlabBytes, &tmap_a, full_bar(stage), 0,
+                        tw * kTW + s - 1, th * kTH - 1, n, pl);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(64);
+      mbar_wait(w_bar, 0);
+      uint32_t sidx = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, use = it >> 1;
+        mbar_wait(acc_empty(acc), (use & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 64u;
+        for (int s = 0; s < 3; ++s, ++sidx) {
+          const int stage = sidx % kStages;
+          const uint32_t phase = (sidx / kStages) & 1u;
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_slab = slab_base + stage * Cfg::kStageBytes;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const uint32_t a0 = a_slab + r * (kTW * 128);
+            const uint32_t b0 = w_base + ((r * 3 + s) * kSplit) * kWTapBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a_hi = make_smem_desc(a0 + k * 32), b_hi = make_smem_desc(b0 + k * 32);
+              umma_bf16(tmem_d, a_hi, b_hi, idesc, (s | r | k) != 0);
+              if (kSplit == 2) {
+                const uint64_t a_lo = make_smem_desc(a0 + kSlabBytes + k * 32), b_lo = make_smem_desc(b0 + kWTapBytes + k * 32);
+                umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+                umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+              }
+            }
+          }
+          umma_commit(empty_bar(stage));
+        }
+        umma_commit(acc_full(acc));
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int w_l = row % kTW, h_l = row / kTW;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+      const int oy = th * kTH + h_l, ox = tw * kTW + w_l;
+      const size_t pix = (static_cast<size_t>(n) * p.h + oy) * p.w + ox;
+      const uint32_t acc = it & 1u, use = it >> 1;
+      float proj_acc[kProjMax];
+#pragma unroll
+      for (int q = 0; q < kProjMax; ++q) proj_acc[q] = 0.0f;
+      mbar_wait(acc_full(acc), use & 1u);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 64u;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 32, r1);
+      // the accumulator is in registers: hand the TMEM buffer back before the (long) epilogue math
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(acc));
+      if (p.gn_partials) {
+        // GroupNorm partial sums (groups of 8 channels) of the values as stored, reduced over this warp's 32 pixels
+        float gs[8], gq[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float s = 0.0f, q = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]);
+            if (p.ep.bias) v += __ldg(p.ep.bias + g * 8 + j);
+            if (FMT == SBGM_FMT_BF16) v = bf16_round(v);
+            s += v;
+            q = fmaf(v, v, q);
+          }
+          gs[g] = warp_sum(s);
+          gq[g] = warp_sum(q);
+        }
+        if (lane == 0) {
+          const int chunks = p.tiles_w * p.tiles_h * 4;
+          const int chunk = (th * p.tiles_w + tw) * 4 + quarter;
+          float* dst = p.gn_partials + (static_cast<size_t>(n) * chunks + chunk) * 16;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            dst[2 * g] = gs[g];
+            dst[2 * g + 1] = gq[g];
+          }
+        }
+      }
+      epilogue_chunk<FMT>(p.ep, r0, 0, n, pix, proj_acc, 0);
+      epilogue_chunk<FMT>(p.ep, r1, 32, n, pix, proj_acc, 32);
+      if (p.ep.proj_w) epilogue_store_proj(p.ep, pix, proj_acc);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+template <int FMT, int kStages>
+static int launch_c64(const CUtensorMap& ta, const CUtensorMap& tb, const C64Params& p, cudaStream_t st) {
+  using Cfg = C64Cfg<FMT, kStages>;
+  auto kern = conv3x3_c64_kernel<FMT, kStages>;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
+      set_error("conv3x3_c64: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
+      return 1;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  return check_launch("conv3x3_c64");
+}
+
+}  // namespace sbgm
+
+using namespace sbgm;
+
+extern "C" int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                                const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
+                                void* out, size_t out_plane, int fmt, int n, int h, int w, int act,
+                                const float* proj_w, int n_proj, float* proj_out, float* gn_partials, int gn_cpg,
+                                void* stream) {
+  SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv3x3_c64: format %d is not a tensor-core format", fmt);
+  SBGM_REQUIRE(h % kTH == 0 && w % kTW == 0, "conv3x3_c64: h=%d must be a multiple of %d and w=%d of %d", h, kTH, w, kTW);
+  SBGM_REQUIRE(proj_w == nullptr || (n_proj >= 1 && n_proj <= kProjMax && proj_out != nullptr), "conv3x3_c64: bad projection arguments");
+  SBGM_REQUIRE(gn_partials == nullptr || (gn_cpg == 8 && residual == nullptr && tproj == nullptr && act == SBGM_ACT_NONE),
+               "conv3x3_c64: fused GroupNorm statistics need 8 channels per group and a bias-only epilogue");
+  const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;
+  C64Params p;
+  p.n = n; p.h = h; p.w = w;
+  p.tiles_w = w / kTW; p.tiles_h = h / kTH; p.total_tiles = p.tiles_w * p.tiles_h * n;
+  p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
+  p.ep.act = act; p.ep.cout = 64; p.ep.out = out; p.ep.out_plane = out_plane;
+  p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
+  p.gn_partials = gn_partials;
+  CUtensorMap ta, tb;
+  if (encode_act_map(&ta, in, planes, in_plane, n, h, w, 64, kTW, kTH + 2, 1, 1)) return 1;
+  if (encode_weight_map(&tb, weight, planes, w_plane, 64, 9 * 64, 64)) return 1;
+  cudaStream_t st = as_stream(stream);
+  if (fmt == SBGM_FMT_BF16) return launch_c64<SBGM_FMT_BF16, 4>(ta, tb, p, st);
+  return launch_c64<SBGM_FMT_BF16X2, 2>(ta, tb, p, st);
+}

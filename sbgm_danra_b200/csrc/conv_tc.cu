@@ -18,105 +18,18 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (warp w may only touch TMEM lanes 32*(w%4) .. +31).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sbgm {
 
 struct ConvTcParams {
-  int n, ho, wo, cout;
+  int n, ho, wo;
   int kh, kw, stride, pad;
   int w_tile, h_tile, n_tile;
   int tiles_w, tiles_h;
   int cin_blocks;
-  int act;
-  const float* bias;
-  const void* residual;
-  size_t res_plane;
-  const float* tproj;
-  int tproj_stride;
-  void* out;
-  size_t out_plane;
+  EpilogueParams ep;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded wait: a TMA fault or a descriptor bug would otherwise hang the GPU until the watchdog.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && spin > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (see cute/arch/mma_sm100_desc.hpp):
-//   [0,14) start >> 4 | [16,30) LBO >> 4 (unused with swizzle: 1) | [32,46) SBO >> 4 (8 rows x 128 B = 1024)
-//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n.
-__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ---- kernel ---------------------------------------------------------------------------------
 template <int kSplit, int BLOCK_N, int kStages>
@@ -154,10 +67,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BLOCK_N) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -223,55 +133,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int n = n0 + n_l, oy = ho0 + h_l, ox = wo0 + w_l;
     const bool valid = (n < p.n) && (oy < p.ho) && (ox < p.wo);
     const size_t pix = (static_cast<size_t>(n) * p.ho + oy) * p.wo + ox;
+    float proj_acc[kProjMax];
+#pragma unroll
+    for (int q = 0; q < kProjMax; ++q) proj_acc[q] = 0.0f;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, r);
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int co = co0 + c0 + g * 8;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += __ldg(p.bias + co + j);
-          }
-          if (p.residual) {
-            float rv[8];
-            Act<FMT>::load8(p.residual, p.res_plane, pix * p.cout + co, rv);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += rv[j];
-          }
-          if (p.act != SBGM_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          if (p.tproj) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += __ldg(p.tproj + static_cast<size_t>(n) * p.tproj_stride + co + j);
-          }
-          Act<FMT>::store8(p.out, p.out_plane, pix * p.cout + co, v);
-        }
-      }
+      if (valid) epilogue_chunk<FMT>(p.ep, r, co0 + c0, n, pix, proj_acc, c0);
     }
+    if (valid && p.ep.proj_w) epilogue_store_proj(p.ep, pix, proj_acc);
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BLOCK_N) : "memory");
-  }
+  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
   void* ptr = nullptr;
@@ -280,6 +161,36 @@ static EncodeTiledFn get_encode_fn() {
     return nullptr;
   fn = reinterpret_cast<EncodeTiledFn>(ptr);
   return fn;
+}
+
+int encode_act_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int n, int h, int w, int c,
+                   int box_w, int box_h, int box_n, int stride) {
+  EncodeTiledFn encode = get_encode_fn();
+  SBGM_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, (cuuint64_t)planes};
+  const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
+                                 planes == 2 ? (cuuint64_t)plane_elems * 2 : (cuuint64_t)n * h * w * c * 2};
+  const cuuint32_t box[5] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), (cuuint32_t)box_n, 1};
+  const cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SBGM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+  return 0;
+}
+
+int encode_weight_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int cout, int K, int box_rows) {
+  EncodeTiledFn encode = get_encode_fn();
+  SBGM_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)cout, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * 2, planes == 2 ? (cuuint64_t)plane_elems * 2 : (cuuint64_t)K * cout * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SBGM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  return 0;
 }
 
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
@@ -319,7 +230,7 @@ static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Co
     }
     configured = true;
   }
-  dim3 grid(m_tiles, p.cout / BLOCK_N);
+  dim3 grid(m_tiles, p.ep.cout / BLOCK_N);
   kern<<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, p);
   return check_launch("conv2d_tc");
 }
@@ -331,53 +242,35 @@ using namespace sbgm;
 extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
                               const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
                               void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
-                              int kh, int kw, int stride, int pad, int act, void* stream) {
+                              int kh, int kw, int stride, int pad, int act, const float* proj_w, int n_proj,
+                              float* proj_out, void* stream) {
   SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv2d_tc: format %d is not a tensor-core format", fmt);
   SBGM_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv2d_tc: cin=%d and cout=%d must be multiples of 64", cin, cout);
   SBGM_REQUIRE(stride >= 1 && stride <= 8, "conv2d_tc: stride %d unsupported", stride);
+  SBGM_REQUIRE(proj_w == nullptr || (cout == 64 && n_proj >= 1 && n_proj <= kProjMax && proj_out != nullptr),
+               "conv2d_tc: the projection epilogue needs cout == 64 and 1 <= n_proj <= %d", kProjMax);
   const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
   SBGM_REQUIRE(ho > 0 && wo > 0, "conv2d_tc: empty output");
-  EncodeTiledFn encode = get_encode_fn();
-  SBGM_REQUIRE(encode != nullptr, "conv2d_tc: cuTensorMapEncodeTiled unavailable (driver too old?)");
   const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;
 
   ConvTcParams p;
-  p.n = n; p.ho = ho; p.wo = wo; p.cout = cout;
+  p.n = n; p.ho = ho; p.wo = wo;
   p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
   pick_tile(n, ho, wo, &p.w_tile, &p.h_tile, &p.n_tile);
   p.tiles_w = ceil_div(wo, p.w_tile);
   p.tiles_h = ceil_div(ho, p.h_tile);
   const int tiles_n = ceil_div(n, p.n_tile);
   p.cin_blocks = cin / 64;
-  p.act = act;
-  p.bias = bias; p.residual = residual; p.res_plane = res_plane; p.tproj = tproj; p.tproj_stride = tproj_stride;
-  p.out = out; p.out_plane = out_plane;
+  p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
+  p.ep.act = act; p.ep.cout = cout; p.ep.out = out; p.ep.out_plane = out_plane;
+  p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
   SBGM_REQUIRE(p.w_tile * stride <= 256 && p.h_tile * stride <= 256, "conv2d_tc: TMA box too large for stride %d", stride);
 
   CUtensorMap ta, tb;
-  {
-    const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, (cuuint64_t)planes};
-    const cuuint64_t strides[4] = {(cuuint64_t)cin * 2, (cuuint64_t)w * cin * 2, (cuuint64_t)h * w * cin * 2,
-                                   planes == 2 ? (cuuint64_t)in_plane * 2 : (cuuint64_t)n * h * w * cin * 2};
-    const cuuint32_t box[5] = {64, (cuuint32_t)(p.w_tile * stride), (cuuint32_t)(p.h_tile * stride), (cuuint32_t)p.n_tile, 1};
-    const cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
-    CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SBGM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
-  }
+  if (encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
   const int K = kh * kw * cin;
   const int block_n = (cout % 256 == 0 && planes == 1) ? 256 : (cout % 128 == 0 ? 128 : 64);
-  {
-    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)cout, (cuuint64_t)planes};
-    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, planes == 2 ? (cuuint64_t)w_plane * 2 : (cuuint64_t)K * cout * 2};
-    const cuuint32_t box[3] = {64, (cuuint32_t)block_n, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(weight), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SBGM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
-  }
+  if (encode_weight_map(&tb, weight, planes, w_plane, cout, K, block_n)) return 1;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   cudaStream_t st = as_stream(stream);
   if (fmt == SBGM_FMT_BF16) {

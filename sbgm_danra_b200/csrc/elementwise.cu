@@ -82,6 +82,7 @@ __global__ void convert_kernel(const void* __restrict__ src, size_t sp, void* __
 // One block per row (batch member or sampler step).  Phase 1: the n_sets Gaussian-Fourier
 // embeddings (+ label embedding on set 0), SiLU applied, into shared memory.  Phase 2: one warp
 // per output channel does the te-long dot product.
+constexpr int kTimeProjCols = 128;   // output channels per block
 __global__ void time_embed_project_kernel(const float* __restrict__ t, int t_row_stride, int t_step_stride,
                                           const int32_t* __restrict__ step_counter, const int64_t* __restrict__ y,
                                           const float* __restrict__ fw, int n_sets, int te,
@@ -108,7 +109,8 @@ __global__ void time_embed_project_kernel(const float* __restrict__ t, int t_row
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int c = warp; c < c_total; c += nwarp) {
+  const int c_begin = blockIdx.y * kTimeProjCols, c_end = min(c_total, c_begin + kTimeProjCols);
+  for (int c = c_begin + warp; c < c_end; c += nwarp) {
     const float* e = emb + pset[c] * te;
     const float* wrow = pw + static_cast<size_t>(c) * te;
     float acc = 0.0f;
@@ -201,7 +203,7 @@ __global__ void gn_partial_kernel(const void* __restrict__ x, size_t plane, int 
 // Stage 2: finish the reduction per group (double accumulation over the 32 chunks) and apply.
 template <int FMT>
 __global__ void gn_apply_kernel(const void* __restrict__ x, size_t x_plane, const float* __restrict__ partials,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                                int chunks, const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                                 const void* __restrict__ skip, size_t skip_plane, const float* __restrict__ tproj,
                                 int tproj_stride, int act, void* __restrict__ y, size_t y_plane, int hw, int c) {
   extern __shared__ float coef[];  // [c][2]: scale, shift per channel (norm + affine + tproj folded), then [groups][2]
@@ -210,8 +212,8 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, size_t x_plane, cons
   const int cpg = c / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double s = 0.0, q = 0.0;
-    for (int k = 0; k < kGnChunks; ++k) {
-      const float* p = partials + ((static_cast<size_t>(n) * kGnChunks + k) * groups + g) * 2;
+    for (int k = 0; k < chunks; ++k) {
+      const float* p = partials + ((static_cast<size_t>(n) * chunks + k) * groups + g) * 2;
       s += p[0];
       q += p[1];
     }
@@ -377,6 +379,35 @@ __global__ void final_conv_kernel(const void* __restrict__ in, size_t plane, con
   }
 }
 
+// out = (sum of the 9 per-tap partial products of the neighbours + bias) * scale; 4 pixels (one float4) per thread.
+__global__ void final_gather_kernel(const float* __restrict__ proj, const float* __restrict__ bias,
+                                    const float* __restrict__ inv_std, int inv_stride, int inv_step_stride,
+                                    const int32_t* __restrict__ step_counter, float* __restrict__ out, int n, int h, int w) {
+  const size_t total = static_cast<size_t>(n) * h * w;
+  const int step = step_counter ? *step_counter : 0;
+  const float b0 = bias[0];
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    const int y = static_cast<int>((i / w) % h);
+    const int b = static_cast<int>(i / (static_cast<size_t>(w) * h));
+    float acc = b0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y + r - 1;
+      if (yy < 0 || yy >= h) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int xx = x + s - 1;
+        if (xx < 0 || xx >= w) continue;
+        acc += __ldg(proj + ((static_cast<size_t>(b) * h + yy) * w + xx) * SBGM_PROJ_STRIDE + r * 3 + s);
+      }
+    }
+    const float sc = inv_std ? inv_std[static_cast<size_t>(b) * inv_stride + static_cast<size_t>(step) * inv_step_stride] : 1.0f;
+    out[i] = acc * sc;
+  }
+}
+
 static int grid_for(size_t items, int block, int max_blocks = 148 * 16) {
   size_t g = (items + block - 1) / block;
   if (g < 1) g = 1;
@@ -435,7 +466,7 @@ int sbgm_time_embed_project(const float* t, int t_row_stride, int t_step_stride,
   SBGM_REQUIRE(te % 2 == 0 && n_sets >= 1 && rows >= 1, "time_embed_project: bad sizes te=%d sets=%d rows=%d", te, n_sets, rows);
   const size_t smem = static_cast<size_t>(n_sets) * te * sizeof(float);
   SBGM_REQUIRE(smem <= 48 * 1024, "time_embed_project: n_sets*te too large");
-  time_embed_project_kernel<<<rows, 512, smem, as_stream(stream)>>>(t, t_row_stride, t_step_stride, step_counter, y,
+  time_embed_project_kernel<<<dim3(rows, ceil_div(c_total, kTimeProjCols)), 256, smem, as_stream(stream)>>>(t, t_row_stride, t_step_stride, step_counter, y,
                                                                     fourier_w, n_sets, te, label_emb, proj_w, proj_b,
                                                                     proj_set, c_total, out);
   return check_launch("time_embed_project");
@@ -473,10 +504,25 @@ int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const floa
   dim3 g2(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
     gn_partial_kernel<FMT><<<g1, 256, smem1, st>>>(x, x_plane, hw, c, groups, partials);
-    gn_apply_kernel<FMT><<<g2, 256, smem2, st>>>(x, x_plane, partials, gamma, beta, groups, eps, skip, skip_plane,
-                                                  tproj, tproj_stride, act, y, y_plane, hw, c);
+    gn_apply_kernel<FMT><<<g2, 256, smem2, st>>>(x, x_plane, partials, kGnChunks, gamma, beta, groups, eps, skip,
+                                                  skip_plane, tproj, tproj_stride, act, y, y_plane, hw, c);
   });
   return check_launch("groupnorm");
+}
+
+int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, int chunks, const float* gamma,
+                         const float* beta, int groups, float eps, const void* skip, size_t skip_plane,
+                         const float* tproj, int tproj_stride, int act, void* y, size_t y_plane, int fmt,
+                         int n, int hw, int c, void* stream) {
+  SBGM_REQUIRE(c % 8 == 0 && c <= 2048 && groups >= 1 && c % groups == 0 && chunks >= 1, "groupnorm_apply: bad c=%d groups=%d chunks=%d", c, groups, chunks);
+  const int vecs = c / 8;
+  const size_t smem2 = (static_cast<size_t>(c) + groups) * 2 * sizeof(float);
+  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
+  dim3 g2(per_n_blocks, n);
+  SBGM_DISPATCH_FMT(fmt, (gn_apply_kernel<FMT><<<g2, 256, smem2, as_stream(stream)>>>(
+                             x, x_plane, partials, chunks, gamma, beta, groups, eps, skip, skip_plane, tproj,
+                             tproj_stride, act, y, y_plane, hw, c)));
+  return check_launch("groupnorm_apply");
 }
 
 int sbgm_layernorm(const void* x, size_t x_plane, const float* gamma, const float* beta, float eps,
@@ -515,6 +561,15 @@ int sbgm_final_conv(const void* in, size_t in_plane, int fmt, const float* weigh
   }
 #undef SBGM_FC
   return check_launch("final_conv");
+}
+
+int sbgm_final_gather(const float* proj, const float* bias, const float* inv_std, int inv_std_stride,
+                      int inv_std_step_stride, const int32_t* step_counter, float* out, int n, int h, int w,
+                      void* stream) {
+  const size_t total = static_cast<size_t>(n) * h * w;
+  final_gather_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(proj, bias, inv_std, inv_std_stride,
+                                                                           inv_std_step_stride, step_counter, out, n, h, w);
+  return check_launch("final_gather");
 }
 
 }  // extern "C"

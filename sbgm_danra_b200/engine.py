@@ -141,29 +141,64 @@ class Kernels:
         self.fmt, self.device = fmt, device
         self._gn_scratch: Optional[torch.Tensor] = None
 
+    def _c64_ok(self, x: Act, cw: ConvW, stride: int, pad: int) -> bool:
+        return (self.fmt != FMT_F32 and cw.cin == 64 and cw.cout == 64 and cw.kh == 3 and cw.kw == 3 and stride == 1
+                and pad == 1 and x.h % 8 == 0 and x.w % 16 == 0)
+
     def conv(self, x: Act, cw: ConvW, stride: int = 1, pad: int = 0, act: int = ACT_NONE,
-             residual: Optional[Act] = None, tproj: Optional[torch.Tensor] = None) -> Act:
+             residual: Optional[Act] = None, tproj: Optional[torch.Tensor] = None,
+             proj: Optional[torch.Tensor] = None, gn_stats: bool = False):
+        """Convolution + fused epilogue.  Returns the output `Act`; with `proj` ([n_proj, 64] fp32) returns the
+        projected fp32 tensor [n, h, w, PROJ_STRIDE] instead; with `gn_stats=True` returns (Act, stats) where
+        stats = (partials, chunks) if the producing kernel could fuse the GroupNorm statistics, else None."""
         assert x.c == cw.cin, f"conv: input has {x.c} channels, weight expects {cw.cin}"
         ho = (x.h + 2 * pad - cw.kh) // stride + 1
         wo = (x.w + 2 * pad - cw.kw) // stride + 1
-        out = Act(self.fmt, x.n, ho, wo, cw.cout, self.device)
         tp_ptr = _ptr(tproj)
         tp_stride = tproj.stride(0) if tproj is not None else 0
-        if self.fmt == FMT_F32:
-            call("sbgm_conv2d_simt", x.ptr, cw.w.data_ptr(), _ptr(cw.bias), None if residual is None else residual.ptr,
-                 tp_ptr, tp_stride, out.ptr, x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw, stride, pad, act, _stream())
+        res_ptr = None if residual is None else residual.ptr
+        res_plane = 0 if residual is None else residual.plane
+        if proj is not None:
+            assert self.fmt != FMT_F32 and cw.cout == 64
+            out, out_ptr, out_plane = None, None, 0
+            pout = torch.empty((x.n, ho, wo, _lib.PROJ_STRIDE), dtype=torch.float32, device=self.device)
+            pargs = (proj.data_ptr(), proj.shape[0], pout.data_ptr())
         else:
-            call("sbgm_conv2d_tc", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias),
-                 None if residual is None else residual.ptr, 0 if residual is None else residual.plane,
-                 tp_ptr, tp_stride, out.ptr, out.plane, self.fmt, x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw,
-                 stride, pad, act, _stream())
-        return out
+            out = Act(self.fmt, x.n, ho, wo, cw.cout, self.device)
+            out_ptr, out_plane, pout, pargs = out.ptr, out.plane, None, (None, 0, None)
+        stats = None
+        if self.fmt == FMT_F32:
+            call("sbgm_conv2d_simt", x.ptr, cw.w.data_ptr(), _ptr(cw.bias), res_ptr, tp_ptr, tp_stride, out.ptr,
+                 x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw, stride, pad, act, _stream())
+        elif self._c64_ok(x, cw, stride, pad):
+            part = None
+            if gn_stats and residual is None and tproj is None and act == ACT_NONE and proj is None:
+                chunks = (x.h // 8) * (x.w // 16) * 4
+                part = torch.empty((x.n, chunks, 8, 2), dtype=torch.float32, device=self.device)
+                stats = (part, chunks)
+            call("sbgm_conv3x3_c64", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias), res_ptr, res_plane,
+                 tp_ptr, tp_stride, out_ptr, out_plane, self.fmt, x.n, x.h, x.w, act, *pargs, _ptr(part), 8, _stream())
+        else:
+            call("sbgm_conv2d_tc", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias), res_ptr, res_plane,
+                 tp_ptr, tp_stride, out_ptr, out_plane, self.fmt, x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw,
+                 stride, pad, act, *pargs, _stream())
+        if proj is not None:
+            return pout
+        return (out, stats) if gn_stats else out
 
     def linear(self, x: Act, cw: ConvW, act: int = ACT_NONE, residual: Optional[Act] = None) -> Act:
         return self.conv(x, cw, 1, 0, act, residual)
 
     def groupnorm(self, x: Act, gamma, beta, groups: int, act: int = ACT_NONE, skip: Optional[Act] = None,
-                  tproj: Optional[torch.Tensor] = None) -> Act:
+                  tproj: Optional[torch.Tensor] = None, stats=None) -> Act:
+        if stats is not None and groups == 8 and x.c == 64:
+            part, chunks = stats
+            out = x.like()
+            call("sbgm_groupnorm_apply", x.ptr, x.plane, part.data_ptr(), chunks, _ptr(gamma), _ptr(beta), groups, GN_EPS,
+                 None if skip is None else skip.ptr, 0 if skip is None else skip.plane,
+                 _ptr(tproj), tproj.stride(0) if tproj is not None else 0, act, out.ptr, out.plane, self.fmt,
+                 x.n, x.h * x.w, x.c, _stream())
+            return out
         need = _lib.query("sbgm_groupnorm_scratch_floats", x.n, x.c, x.h * x.w)
         if self._gn_scratch is None or self._gn_scratch.numel() < need:
             self._gn_scratch = torch.empty(need, dtype=torch.float32, device=self.device)
@@ -387,18 +422,27 @@ class DecoderEngine:
         out = rev[0]
         for i, blk in enumerate(self.blocks):
             up = k.upsample2x(out)
-            a = k.conv(up, blk["conv_up"], pad=1)
-            a = k.groupnorm(a, *blk["n1"], groups=blk["g1"])
-            b = k.conv(a, blk["conv"], pad=1)
+            a, st1 = k.conv(up, blk["conv_up"], pad=1, gn_stats=True)
+            a = k.groupnorm(a, *blk["n1"], groups=blk["g1"], stats=st1)
+            b, st2 = k.conv(a, blk["conv"], pad=1, gn_stats=True)
             skip = rev[i + 1]
             if (skip.n, skip.h, skip.w, skip.c) != (b.n, b.h, b.w, b.c):
                 raise AssertionError(f"prev_fmap shape {(skip.n, skip.c, skip.h, skip.w)} must match output shape {(b.n, b.c, b.h, b.w)}")
-            out = k.groupnorm(b, *blk["n2"], groups=blk["g2"], act=self.act, skip=skip, tproj=tp.cols(tproj, blk["name"]))
+            out = k.groupnorm(b, *blk["n2"], groups=blk["g2"], act=self.act, skip=skip, tproj=tp.cols(tproj, blk["name"]),
+                              stats=st2)
             if blk["attn"] is not None:
                 out = attention_block(k, blk["attn"], out)
         up = k.upsample2x(out)
+        n, h, w = up.n, up.h, up.w
+        res = dst if dst is not None else torch.empty((n, self.out_channels, h, w), dtype=torch.float32, device=self.device)
+        if self.fmt != FMT_F32 and self.out_channels == 1 and self.final_up.cout == 64:
+            # conv_up's epilogue emits the 9 per-tap partial products of the final 64->1 convolution; its
+            # 64-channel output never reaches HBM (tc_common.cuh: projection epilogue)
+            pr = k.conv(up, self.final_up, pad=1, proj=self.final_w[0])
+            call("sbgm_final_gather", pr.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), inv_std_stride,
+                 inv_std_step_stride, _ptr(step_counter), res.data_ptr(), n, h, w, _stream())
+            return res
         a = k.conv(up, self.final_up, pad=1)
-        res = dst if dst is not None else torch.empty((a.n, self.out_channels, a.h, a.w), dtype=torch.float32, device=self.device)
         call("sbgm_final_conv", a.ptr, a.plane, self.fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std),
              inv_std_stride, inv_std_step_stride, _ptr(step_counter), res.data_ptr(), a.n, a.h, a.w, a.c,
              self.out_channels, _stream())

@@ -113,6 +113,8 @@ CONV_CASES = [
     (1, 1, 200, 128, 384, 1, 1, 0, "gelu"),       # Linear over 200 tokens (tail masking)
     (1, 1, 1024, 512, 1536, 1, 1, 0, "plain"),    # in_proj of the 512-channel attention
     (1, 64, 64, 64, 64, 3, 1, 1, "full"),
+    (3, 8, 16, 64, 64, 3, 1, 1, "full"),          # single tile per image of the persistent 64->64 kernel
+    (70, 16, 32, 64, 64, 3, 1, 1, "relu"),        # 280 tiles: more than one wave of the persistent kernel
     (2, 12, 24, 64, 192, 3, 1, 1, "full"),        # non power-of-two spatial, cout = 3 x 64
 ]
 
@@ -127,20 +129,20 @@ def test_conv2d(E, prec, case):
     bias = gen(cout, seed=3, scale=0.1) if epi != "plain" else None
     ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     res = gen(n, cout, ho, wo, seed=4) if epi == "full" else None
-    tproj = gen(n, cout + 7, seed=5) if epi == "full" else None
+    tproj = gen(n, cout + 16, seed=5) if epi == "full" else None
     act = {"plain": 0, "full": 1, "relu": 1, "gelu": 3}[epi]
     want = F.conv2d(x, wt, bias, stride=stride, padding=pad)
     if res is not None:
         want = want + res
     want = {0: lambda v: v, 1: F.relu, 3: F.gelu}[act](want)
     if tproj is not None:
-        want = want + tproj[:, 3:3 + cout, None, None]
+        want = want + tproj[:, 8:8 + cout, None, None]   # 16-byte aligned column offset (ABI requirement)
     kern = E.Kernels(fmt, torch.device("cuda"))
     sd = {"w": wt}
     if bias is not None:
         sd["b"] = bias
     cw = E._Packer(sd, fmt, torch.device("cuda")).conv("w", "b" if bias is not None else None)
-    tp = tproj.cuda()[:, 3:3 + cout] if tproj is not None else None
+    tp = tproj.cuda()[:, 8:8 + cout] if tproj is not None else None
     out = kern.conv(act_of(E, x, fmt), cw, stride=stride, pad=pad, act=act,
                     residual=None if res is None else act_of(E, res, fmt), tproj=tp)
     torch.cuda.synchronize()
@@ -316,3 +318,43 @@ def test_dsm_kernels():
         w = torch.sigmoid(sd_) * 0.5 + 0.5 if sd_ is not None else torch.ones_like(x)
         want = torch.mean(torch.sum(w * (score * std[:, None, None, None] + zr) ** 2, dim=(1, 2, 3)))
         assert abs(loss.item() - want.item()) / want.item() < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("kernel", ["c64", "generic"])
+def test_projection_epilogue_and_gather(E, prec, kernel):
+    """conv_up (64->64) with the projection epilogue + sbgm_final_gather == conv3x3(64->1)(conv3x3(64->64)(x))."""
+    from sbgm_danra_b200._lib import call
+    fmt = FMTS[prec]
+    n, h, w = (3, 16, 32) if kernel == "c64" else (3, 12, 20)     # 12x20 is not tileable by 8x16 -> generic kernel
+    x = gen(n, 64, h, w, seed=1)
+    w1, b1 = gen(64, 64, 3, 3, seed=2, scale=0.05), gen(64, seed=3, scale=0.1)
+    w2, b2 = gen(1, 64, 3, 3, seed=4, scale=0.05), gen(1, seed=5)
+    inv = torch.tensor([0.5, 2.0, 10.0])
+    want = F.conv2d(F.conv2d(x, w1, b1, padding=1), w2, b2, padding=1) * inv[:, None, None, None]
+    kern = E.Kernels(fmt, torch.device("cuda"))
+    cw = E._Packer({"w": w1, "b": b1}, fmt, torch.device("cuda")).conv("w", "b")
+    pw = w2.permute(0, 2, 3, 1).reshape(9, 64).contiguous().cuda()
+    pr = kern.conv(act_of(E, x, fmt), cw, pad=1, proj=pw)
+    b2_d, inv_d = b2.cuda(), inv.cuda()
+    out = torch.empty(n, 1, h, w, device="cuda")
+    call("sbgm_final_gather", pr.data_ptr(), b2_d.data_ptr(), inv_d.data_ptr(), 1, 0, None, out.data_ptr(), n, h, w,
+         torch.cuda.current_stream().cuda_stream)
+    assert rel_l2(out.cpu(), want) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+def test_conv_fused_groupnorm_statistics(E, prec):
+    """GroupNorm from the statistics emitted by the 64->64 kernel's epilogue == GroupNorm of its output."""
+    fmt = FMTS[prec]
+    n, h, w = 3, 32, 32
+    x = gen(n, 64, h, w, seed=1)
+    w1, b1 = gen(64, 64, 3, 3, seed=2, scale=0.05), gen(64, seed=3, scale=0.5)
+    gamma, beta = 1 + 0.2 * gen(64, seed=4), gen(64, seed=5, scale=0.2)
+    kern = E.Kernels(fmt, torch.device("cuda"))
+    cw = E._Packer({"w": w1, "b": b1}, fmt, torch.device("cuda")).conv("w", "b")
+    y, stats = kern.conv(act_of(E, x, fmt), cw, pad=1, gn_stats=True)
+    assert stats is not None
+    got = kern.groupnorm(y, gamma.cuda(), beta.cuda(), 8, stats=stats).to_nchw().cpu()
+    want = F.group_norm(y.to_nchw().cpu(), 8, gamma, beta, 1e-5)
+    assert rel_l2(got, want) < {"bf16": 8e-3, "bf16x3": 3e-5}[prec]
