@@ -36,7 +36,7 @@ struct C64Cfg {
   static constexpr uint32_t kSmemBytes = kBarOffset + 128 + 1024;
 };
 
-template <int FMT, int kStages>
+template <int FMT, int kStages, int ACT, bool PROJ>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const C64Params p) {
   using Cfg = C64Cfg<FMT, kStages>;
@@ -183,9 +183,9 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
       }
-      epilogue_chunk<FMT>(p.ep, r0, 0, n, pix, proj_acc, 0);
-      epilogue_chunk<FMT>(p.ep, r1, 32, n, pix, proj_acc, 32);
-      if (p.ep.proj_w) epilogue_store_proj(p.ep, pix, proj_acc);
+      epilogue_chunk<FMT, ACT, PROJ, 0>(p.ep, r0, 0, n, pix, proj_acc);
+      epilogue_chunk<FMT, ACT, PROJ, 32>(p.ep, r1, 32, n, pix, proj_acc);
+      if (PROJ) epilogue_store_proj(p.ep, pix, proj_acc);
     }
   }
   tcgen05_fence_before();
@@ -193,10 +193,10 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
 
-template <int FMT, int kStages>
-static int launch_c64(const CUtensorMap& ta, const CUtensorMap& tb, const C64Params& p, cudaStream_t st) {
+template <int FMT, int kStages, int ACT, bool PROJ>
+static int launch_c64_inst(const CUtensorMap& ta, const CUtensorMap& tb, const C64Params& p, cudaStream_t st) {
   using Cfg = C64Cfg<FMT, kStages>;
-  auto kern = conv3x3_c64_kernel<FMT, kStages>;
+  auto kern = conv3x3_c64_kernel<FMT, kStages, ACT, PROJ>;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
@@ -209,9 +209,22 @@ static int launch_c64(const CUtensorMap& ta, const CUtensorMap& tb, const C64Par
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
+  if (PROJ && cudaMemcpyToSymbolAsync(c_proj_w, p.ep.proj_w, sizeof(float) * kProjN * 64, 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    set_error("conv3x3_c64: projection weight upload failed");
+    return 1;
+  }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   kern<<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, p);
   return check_launch("conv3x3_c64");
+}
+
+template <int FMT, int kStages>
+static int launch_c64(const CUtensorMap& ta, const CUtensorMap& tb, const C64Params& p, cudaStream_t st) {
+  if (p.ep.proj_w) return launch_c64_inst<FMT, kStages, SBGM_ACT_NONE, true>(ta, tb, p, st);
+  if (p.ep.act == SBGM_ACT_NONE) return launch_c64_inst<FMT, kStages, SBGM_ACT_NONE, false>(ta, tb, p, st);
+  if (p.ep.act == SBGM_ACT_RELU) return launch_c64_inst<FMT, kStages, SBGM_ACT_RELU, false>(ta, tb, p, st);
+  set_error("conv3x3_c64: activation %d not instantiated (none / relu only)", p.ep.act);
+  return 1;
 }
 
 }  // namespace sbgm
@@ -225,7 +238,9 @@ extern "C" int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* wei
                                 void* stream) {
   SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv3x3_c64: format %d is not a tensor-core format", fmt);
   SBGM_REQUIRE(h % kTH == 0 && w % kTW == 0, "conv3x3_c64: h=%d must be a multiple of %d and w=%d of %d", h, kTH, w, kTW);
-  SBGM_REQUIRE(proj_w == nullptr || (n_proj >= 1 && n_proj <= kProjMax && proj_out != nullptr), "conv3x3_c64: bad projection arguments");
+  SBGM_REQUIRE(proj_w == nullptr || (n_proj == kProjN && proj_out != nullptr && residual == nullptr && tproj == nullptr &&
+                                     act == SBGM_ACT_NONE),
+               "conv3x3_c64: the projection epilogue needs n_proj == %d and a bias-only epilogue", kProjN);
   SBGM_REQUIRE(gn_partials == nullptr || (gn_cpg == 8 && residual == nullptr && tproj == nullptr && act == SBGM_ACT_NONE),
                "conv3x3_c64: fused GroupNorm statistics need 8 channels per group and a bias-only epilogue");
   const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;

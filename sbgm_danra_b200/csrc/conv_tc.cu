@@ -41,7 +41,7 @@ struct ConvTcCfg {
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
-template <int FMT, int BLOCK_N, int kStages>
+template <int FMT, int BLOCK_N, int kStages, int ACT, bool PROJ>
 __global__ void __launch_bounds__(192, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
@@ -138,13 +138,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int q = 0; q < kProjMax; ++q) proj_acc[q] = 0.0f;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    if (PROJ) {       // BLOCK_N == 64: both chunks unrolled so the constant-bank weight offsets are immediates
       uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, r);
-      if (valid) epilogue_chunk<FMT>(p.ep, r, co0 + c0, n, pix, proj_acc, c0);
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16), r);
+      if (valid) epilogue_chunk<FMT, ACT, PROJ, 0>(p.ep, r, co0, n, pix, proj_acc);
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 32, r);
+      if (valid) epilogue_chunk<FMT, ACT, PROJ, 32>(p.ep, r, co0 + 32, n, pix, proj_acc);
+      if (valid) epilogue_store_proj(p.ep, pix, proj_acc);
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, r);
+        if (valid) epilogue_chunk<FMT, ACT, false, 0>(p.ep, r, co0 + c0, n, pix, proj_acc);
+      }
     }
-    if (valid && p.ep.proj_w) epilogue_store_proj(p.ep, pix, proj_acc);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -217,11 +225,11 @@ static void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
   (void)pow2_floor;
 }
 
-template <int FMT, int BLOCK_N, int kStages>
-static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTcParams& p, int m_tiles, cudaStream_t st) {
+template <int FMT, int BLOCK_N, int kStages, int ACT, bool PROJ>
+static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTcParams& p, int m_tiles, cudaStream_t st) {
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   using Cfg = ConvTcCfg<kSplit, BLOCK_N, kStages>;
-  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages>;
+  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -230,9 +238,23 @@ static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Co
     }
     configured = true;
   }
+  if (PROJ && cudaMemcpyToSymbolAsync(c_proj_w, p.ep.proj_w, sizeof(float) * kProjN * 64, 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    set_error("conv2d_tc: projection weight upload failed");
+    return 1;
+  }
   dim3 grid(m_tiles, p.ep.cout / BLOCK_N);
   kern<<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, p);
   return check_launch("conv2d_tc");
+}
+
+template <int FMT, int BLOCK_N, int kStages>
+static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTcParams& p, int m_tiles, cudaStream_t st) {
+  if (p.ep.proj_w) {
+    if (BLOCK_N != 64) { set_error("conv2d_tc: projection epilogue needs a 64-wide tile"); return 1; }
+    return launch_conv_tc_inst<FMT, 64, (FMT == SBGM_FMT_BF16X2 ? 2 : 4), SBGM_ACT_NONE, true>(ta, tb, p, m_tiles, st);
+  }
+  SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kStages, ACT, false>(ta, tb, p, m_tiles, st)));
+  return 0;
 }
 
 }  // namespace sbgm
@@ -247,8 +269,9 @@ extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weigh
   SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv2d_tc: format %d is not a tensor-core format", fmt);
   SBGM_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv2d_tc: cin=%d and cout=%d must be multiples of 64", cin, cout);
   SBGM_REQUIRE(stride >= 1 && stride <= 8, "conv2d_tc: stride %d unsupported", stride);
-  SBGM_REQUIRE(proj_w == nullptr || (cout == 64 && n_proj >= 1 && n_proj <= kProjMax && proj_out != nullptr),
-               "conv2d_tc: the projection epilogue needs cout == 64 and 1 <= n_proj <= %d", kProjMax);
+  SBGM_REQUIRE(proj_w == nullptr || (cout == 64 && n_proj == kProjN && proj_out != nullptr && residual == nullptr &&
+                                     tproj == nullptr && act == SBGM_ACT_NONE),
+               "conv2d_tc: the projection epilogue needs cout == 64, n_proj == %d and a bias-only epilogue", kProjN);
   const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
   SBGM_REQUIRE(ho > 0 && wo > 0, "conv2d_tc: empty output");
   const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;

@@ -97,11 +97,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // ---- epilogue ----------------------------------------------------------------------------------
 // v = acc + bias[co];  v += residual[pix][co];  v = act(v);  v += tproj[n][co];  store (NHWC, fmt)
-// Optional extras for cout == 64 tiles (one thread holds a whole pixel):
-//   proj_w / proj_out : instead of storing the 64 channels, store kProj dot products
-//                       proj_out[pix][kProjPad] = sum_c v[c] * proj_w[p][c]  (the 9 taps of the final
-//                       64->1 convolution, Decoder.final_layer.conv, score_unet.py:713-730)
-//   gn_part            : per-(tile, warp) GroupNorm partial sums of the stored values
+// Projection mode (cout == 64 tiles, one thread holds a whole pixel): instead of storing the 64
+// channels, accumulate kProjN dot products  proj[q] += sum_c v[c] * c_proj_w[q][c]  -- the nine taps of
+// the final 64 -> 1 convolution (Decoder.final_layer.conv, score_unet.py:713-730) -- and store them
+// as proj_out[pix][SBGM_PROJ_STRIDE] fp32.  The 9 x 64 weights live in constant memory so every FFMA
+// takes its weight as a constant-bank operand (no loads, warp-uniform address).
 struct EpilogueParams {
   const float* bias;
   const void* residual;
@@ -112,16 +112,27 @@ struct EpilogueParams {
   int cout;
   void* out;
   size_t out_plane;
-  const float* proj_w;   // [kProj][64] fp32 or nullptr
-  float* proj_out;       // [pix][kProjPad] fp32
+  const float* proj_w;   // [kProjN][64] fp32 (device) or nullptr; copied to c_proj_w before the launch
+  float* proj_out;       // [pix][SBGM_PROJ_STRIDE] fp32
   int n_proj;
 };
-constexpr int kProjMax = 12;   // projection outputs per pixel (padded row), 9 used for cout_final = 1
+constexpr int kProjN = 9;
+constexpr int kProjMax = SBGM_PROJ_STRIDE;
+static __constant__ float c_proj_w[kProjN * 64];
 
-// One 32-column chunk of one accumulator row.
-template <int FMT>
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x) {
+  if (ACT == SBGM_ACT_RELU) return fmaxf(x, 0.0f);
+  if (ACT == SBGM_ACT_SILU) return silu(x);
+  if (ACT == SBGM_ACT_GELU) return gelu_erf(x);
+  return x;
+}
+
+// One 32-column chunk of one accumulator row.  ACT and PROJ are compile-time; COL0 is the chunk's first
+// channel inside a 64-wide tile (only used by the projection).
+template <int FMT, int ACT, bool PROJ, int COL0>
 __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, const uint32_t (&r)[32], int co_base, int n,
-                                               size_t pix, float (&proj_acc)[kProjMax], int chunk_col0) {
+                                               size_t pix, float (&proj_acc)[kProjMax]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int co = co_base + g * 8;
@@ -132,33 +143,24 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, const u
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + co)), b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + co + 4));
       v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
-    if (ep.residual) {
+    if (!PROJ && ep.residual) {
       float rv[8];
       Act<FMT>::load8(ep.residual, ep.res_plane, pix * ep.cout + co, rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += rv[j];
     }
-    if (ep.act != SBGM_ACT_NONE) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
-    }
-    if (ep.tproj) {
+    for (int j = 0; j < 8; ++j) v[j] = act_ct<ACT>(v[j]);
+    if (!PROJ && ep.tproj) {
       const float* tp = ep.tproj + static_cast<size_t>(n) * ep.tproj_stride + co;
       const float4 t0 = __ldg(reinterpret_cast<const float4*>(tp)), t1 = __ldg(reinterpret_cast<const float4*>(tp + 4));
       v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
     }
-    if (ep.proj_w) {
-      const int c = chunk_col0 + g * 8;   // channel index inside the 64-wide tile
+    if (PROJ) {
 #pragma unroll
-      for (int q = 0; q < kProjMax; ++q) {
-        if (q >= ep.n_proj) break;
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(ep.proj_w + q * 64 + c));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(ep.proj_w + q * 64 + c + 4));
-        float a = proj_acc[q];
-        a = fmaf(v[0], w0.x, a); a = fmaf(v[1], w0.y, a); a = fmaf(v[2], w0.z, a); a = fmaf(v[3], w0.w, a);
-        a = fmaf(v[4], w1.x, a); a = fmaf(v[5], w1.y, a); a = fmaf(v[6], w1.z, a); a = fmaf(v[7], w1.w, a);
-        proj_acc[q] = a;
-      }
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int q = 0; q < kProjN; ++q) proj_acc[q] = fmaf(v[j], c_proj_w[q * 64 + COL0 + g * 8 + j], proj_acc[q]);
     } else {
       Act<FMT>::store8(ep.out, ep.out_plane, pix * ep.cout + co, v);
     }
@@ -171,6 +173,16 @@ __device__ __forceinline__ void epilogue_store_proj(const EpilogueParams& ep, si
   dst[1] = make_float4(proj_acc[4], proj_acc[5], proj_acc[6], proj_acc[7]);
   dst[2] = make_float4(proj_acc[8], proj_acc[9], proj_acc[10], proj_acc[11]);
 }
+
+// Runtime activation id -> compile-time template argument.
+#define SBGM_DISPATCH_ACT(act, ...)                                                              \
+  switch (act) {                                                                                  \
+    case SBGM_ACT_NONE: { constexpr int ACT = SBGM_ACT_NONE; __VA_ARGS__; break; }                \
+    case SBGM_ACT_RELU: { constexpr int ACT = SBGM_ACT_RELU; __VA_ARGS__; break; }                \
+    case SBGM_ACT_GELU: { constexpr int ACT = SBGM_ACT_GELU; __VA_ARGS__; break; }                \
+    case SBGM_ACT_SILU: { constexpr int ACT = SBGM_ACT_SILU; __VA_ARGS__; break; }                \
+    default: ::sbgm::set_error("unknown activation %d", act); return 1;                            \
+  }
 
 // ---- host: tensor-map encoding -----------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
