@@ -179,10 +179,11 @@ int sbgm_philox_uniform(float* out, size_t count, uint64_t seed, uint32_t draw, 
  * with the reference's own arithmetic, score_sampling.py:96-103,169-176):
  *   [0] t   [1] g = sigma^t   [2] dt   [3] 1/std(t)   [4] g*g*dt   [5] noise scale
  *   (EM: sqrt(dt)*g, :125; PC predictor: sqrt(g*g*dt), :227)   [6..7] reserved
- * `step_counter` points at TWO device int32, zero-initialised by the caller: [0] is the current
- * step, [1] is scratch (block-arrival count).  Kernels read row step_counter[0]; the predictor /
- * EM update increments it when its last block retires, which is what lets the whole step loop
- * replay as one CUDA graph with frozen kernel arguments.
+ * `step_counter` points at FOUR device int32 (the sampler state): [0] the current step, [1] scratch
+ * (block-arrival count, zero), [2..3] the 64-bit Philox seed (lo, hi).  Kernels read row
+ * step_counter[0]; the predictor / EM update increments it when its last block retires.  Keeping step
+ * and seed on the device is what lets one captured CUDA graph (frozen kernel arguments) replay every
+ * step of every sampler call.
  */
 #define SBGM_STEP_COLS 8
 /* x0 = z * std(1)  (score_sampling.py:93-95 / :167-168) */
@@ -191,7 +192,7 @@ int sbgm_sampler_init(float* x, size_t count, float std1, uint64_t seed, uint64_
  *   mean = x + (g*g*dt) * score ;  x = mean + noise_scale * z ;  ++*step_counter
  * draw id = draw_base + draw_stride * step.  `mean_out` receives `mean` (always written). */
 int sbgm_sampler_predictor(float* x, const float* score, float* mean_out, size_t count, const float* step_table,
-                           int32_t* step_counter, uint64_t seed, uint32_t draw_base, uint32_t draw_stride,
+                           int32_t* step_counter, uint32_t draw_base, uint32_t draw_stride,
                            uint64_t first_elem, void* stream);
 /* per-member sum of squares of `score` -> sumsq[members] (PC corrector, score_sampling.py:201) */
 int sbgm_sampler_sumsq(const float* score, float* sumsq, int members, int per_member, void* stream);
@@ -199,7 +200,7 @@ int sbgm_sampler_sumsq(const float* score, float* sumsq, int members, int per_me
  * `members_total` members (sumsq already holds every member of the global ensemble);
  *   eps = 2 (snr sqrt(per_member) / grad_norm)^2 ;  x += eps * score + sqrt(2 eps) * z          */
 int sbgm_sampler_corrector(float* x, const float* score, const float* sumsq, int members_total, int per_member,
-                           float snr, size_t count, const int32_t* step_counter, uint64_t seed,
+                           float snr, size_t count, const int32_t* step_counter,
                            uint32_t draw_base, uint32_t draw_stride, uint64_t first_elem, void* stream);
 /* classifier-free guidance combine (guided_score_fn, score_sampling.py:54): out = (1+scale) s_c - scale s_u */
 int sbgm_cfg_combine(const float* s_cond, const float* s_uncond, float scale, float* out, size_t count, void* stream);

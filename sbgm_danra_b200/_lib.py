@@ -41,9 +41,9 @@ PROTOTYPES = {
     "sbgm_philox_normal": [_p, _sz, _u64, _u32, _u64, _p],
     "sbgm_philox_uniform": [_p, _sz, _u64, _u32, _u64, _p],
     "sbgm_sampler_init": [_p, _sz, _f, _u64, _u64, _p],
-    "sbgm_sampler_predictor": [_p, _p, _p, _sz, _p, _p, _u64, _u32, _u32, _u64, _p],
+    "sbgm_sampler_predictor": [_p, _p, _p, _sz, _p, _p, _u32, _u32, _u64, _p],
     "sbgm_sampler_sumsq": [_p, _p, _i, _i, _p],
-    "sbgm_sampler_corrector": [_p, _p, _p, _i, _i, _f, _sz, _p, _u64, _u32, _u32, _u64, _p],
+    "sbgm_sampler_corrector": [_p, _p, _p, _i, _i, _f, _sz, _p, _u32, _u32, _u64, _p],
     "sbgm_select_step_row": [_p, _i, _p, _p, _p],
     "sbgm_dsm_perturb": [_p, _p, _p, _p, _i, _i, _u64, _u32, _u64, _p],
     "sbgm_dsm_loss": [_p, _p, _p, _p, _i, _i, _p, _p, _p],

@@ -69,7 +69,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  constexpr uint32_t kAccCols = 64u * kSplit;     // split mode keeps x_hi*w_lo in a second 64-column half
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kAccCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -97,41 +98,44 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(64);
-      mbar_wait(w_bar, 0);
-      uint32_t sidx = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1u, use = it >> 1;
-        mbar_wait(acc_empty(acc), (use & 1u) ^ 1u);
+    // whole warp, uniform control flow; one elected lane issues each tcgen05 instruction
+    constexpr uint32_t idesc = make_idesc(64), idesc2 = make_idesc(128);
+    mbar_wait(w_bar, 0);
+    const uint32_t w_lo = desc_lo(w_base), slab_lo0 = desc_lo(slab_base);
+    uint32_t sidx = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u, use = it >> 1;
+      mbar_wait(acc_empty(acc), (use & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kAccCols;
+#pragma unroll
+      for (int s = 0; s < 3; ++s, ++sidx) {
+        const uint32_t stage = sidx % kStages;
+        const uint32_t phase = (sidx / kStages) & 1u;
+        mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * 64u;
-        for (int s = 0; s < 3; ++s, ++sidx) {
-          const int stage = sidx % kStages;
-          const uint32_t phase = (sidx / kStages) & 1u;
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint32_t a_slab = slab_base + stage * Cfg::kStageBytes;
+        const uint32_t a_slab = slab_lo0 + stage * (Cfg::kStageBytes >> 4);
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const uint32_t a0 = a_slab + r * (kTW * 128);
-            const uint32_t b0 = w_base + ((r * 3 + s) * kSplit) * kWTapBytes;
+        for (int r = 0; r < 3; ++r) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t a_hi = make_smem_desc(a0 + k * 32), b_hi = make_smem_desc(b0 + k * 32);
-              umma_bf16(tmem_d, a_hi, b_hi, idesc, (s | r | k) != 0);
-              if (kSplit == 2) {
-                const uint64_t a_lo = make_smem_desc(a0 + kSlabBytes + k * 32), b_lo = make_smem_desc(b0 + kWTapBytes + k * 32);
-                umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
-                umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
-              }
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t a_hi = a_slab + ((r * (kTW * 128) + k * 32) >> 4);
+            const uint32_t b_hi = w_lo + ((((r * 3 + s) * kSplit) * kWTapBytes + k * 32) >> 4);
+            if (kSplit == 2) {
+              // hi|lo weight planes of a tap are adjacent in smem: one N = 128 MMA gives x_hi*w_hi (cols 0..63)
+              // and x_hi*w_lo (cols 64..127); x_lo*w_hi accumulates into cols 0..63.  The epilogue adds the halves.
+              umma_bf16_elect(tmem_d, a_hi, b_hi, idesc2, (s | r | k) != 0);
+              umma_bf16_elect(tmem_d, a_hi + (kSlabBytes >> 4), b_hi, idesc, 1u);
+            } else {
+              umma_bf16_elect(tmem_d, a_hi, b_hi, idesc, (s | r | k) != 0);
             }
           }
-          umma_commit(empty_bar(stage));
         }
-        umma_commit(acc_full(acc));
+        umma_commit_elect(empty_bar(stage));
       }
+      umma_commit_elect(acc_full(acc));
     }
+    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -147,10 +151,19 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       for (int q = 0; q < kProjMax; ++q) proj_acc[q] = 0.0f;
       mbar_wait(acc_full(acc), use & 1u);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 64u;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
       uint32_t r0[32], r1[32];
       tmem_ld32(taddr, r0);
       tmem_ld32(taddr + 32, r1);
+      if (kSplit == 2) {
+        uint32_t t[32];
+        tmem_ld32(taddr + 64, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(t[j]));
+        tmem_ld32(taddr + 96, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(t[j]));
+      }
       // the accumulator is in registers: hand the TMEM buffer back before the (long) epilogue math
       tcgen05_fence_before();
       __syncwarp();
@@ -183,14 +196,13 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
       }
-      epilogue_chunk<FMT, ACT, PROJ, 0>(p.ep, r0, 0, n, pix, proj_acc);
-      epilogue_chunk<FMT, ACT, PROJ, 32>(p.ep, r1, 32, n, pix, proj_acc);
+      epilogue_block64<FMT, ACT, PROJ>(p.ep, r0, r1, 0, n, pix, true, lane, proj_acc);
       if (PROJ) epilogue_store_proj(p.ep, pix, proj_acc);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 128);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * kAccCols);
 }
 
 template <int FMT, int kStages, int ACT, bool PROJ>

@@ -67,7 +67,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, kSplit * BLOCK_N);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -101,30 +101,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        tcgen05_fence_after();
-        const uint32_t a0 = smem_base + stage * Cfg::kStageBytes;
-        const uint32_t b0 = a0 + kSplit * Cfg::kABytes;
+    // whole warp, uniform control flow; one elected lane issues each tcgen05 instruction
+    constexpr uint32_t idesc = make_idesc(BLOCK_N), idesc2 = make_idesc(kSplit * BLOCK_N);
+    const uint32_t base_lo = desc_lo(smem_base);
+    uint32_t stage = 0, phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(full_bar(stage), phase);
+      tcgen05_fence_after();
+      const uint32_t a0 = base_lo + stage * (Cfg::kStageBytes >> 4);
+      const uint32_t b0 = a0 + ((kSplit * Cfg::kABytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) per 64-element block
-          const uint64_t a_hi = make_smem_desc(a0 + k * 32), b_hi = make_smem_desc(b0 + k * 32);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
-          if (kSplit == 2) {
-            const uint64_t a_lo = make_smem_desc(a0 + Cfg::kABytes + k * 32), b_lo = make_smem_desc(b0 + Cfg::kBBytes + k * 32);
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1u);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-          }
+      for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) per 64-element block
+        if (kSplit == 2) {
+          // the hi|lo weight planes of a stage are adjacent: one N = 2*BLOCK_N MMA yields x_hi*w_hi (first half
+          // of the columns) and x_hi*w_lo (second half); x_lo*w_hi accumulates into the first half.
+          umma_bf16_elect(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2, (kb | k) != 0);
+          umma_bf16_elect(tmem_base, a0 + (Cfg::kABytes >> 4) + 2 * k, b0 + 2 * k, idesc, 1u);
+        } else {
+          umma_bf16_elect(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
+      umma_commit_elect(empty_bar(stage));          // frees the smem slot once these MMAs retire
+      if (kb == num_kb - 1) umma_commit_elect(tmem_full_bar);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
+    __syncwarp();
   } else {
     // ---- epilogue: TMEM -> registers -> bias/residual/act/time -> NHWC global ----
     const int quarter = warp & 3;
@@ -138,25 +139,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int q = 0; q < kProjMax; ++q) proj_acc[q] = 0.0f;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
-    if (PROJ) {       // BLOCK_N == 64: both chunks unrolled so the constant-bank weight offsets are immediates
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16), r);
-      if (valid) epilogue_chunk<FMT, ACT, PROJ, 0>(p.ep, r, co0, n, pix, proj_acc);
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 32, r);
-      if (valid) epilogue_chunk<FMT, ACT, PROJ, 32>(p.ep, r, co0 + 32, n, pix, proj_acc);
-      if (valid) epilogue_store_proj(p.ep, pix, proj_acc);
-    } else {
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, r);
-        if (valid) epilogue_chunk<FMT, ACT, false, 0>(p.ep, r, co0 + c0, n, pix, proj_acc);
+    auto load_acc = [&](int c0, uint32_t (&r)[32]) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
+      tmem_ld32(taddr, r);
+      if (kSplit == 2) {
+        uint32_t t[32];
+        tmem_ld32(taddr + BLOCK_N, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
       }
+    };
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {      // the whole warp walks the tile in 64-channel blocks
+      uint32_t ra[32], rb[32];
+      load_acc(c0, ra);
+      load_acc(c0 + 32, rb);
+      epilogue_block64<FMT, ACT, PROJ>(p.ep, ra, rb, co0 + c0, n, pix, valid, lane, proj_acc);
     }
+    if (PROJ && valid) epilogue_store_proj(p.ep, pix, proj_acc);
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_base, kSplit * BLOCK_N);
 }
 
 // ---- host side ---------------------------------------------------------------------------------

@@ -33,6 +33,11 @@ __global__ void philox_fill_kernel(float* __restrict__ out, size_t count, uint64
   }
 }
 
+// sampler state (device, int32[4]): [0] step, [1] block-arrival scratch, [2..3] Philox seed (lo, hi)
+__device__ __forceinline__ uint64_t state_seed(const int32_t* state) {
+  return static_cast<uint64_t>(static_cast<uint32_t>(state[2])) | (static_cast<uint64_t>(static_cast<uint32_t>(state[3])) << 32);
+}
+
 __global__ void sampler_init_kernel(float* __restrict__ x, size_t nq, float std1, uint64_t seed, uint64_t first_q) {
   for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq;
        q += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -45,9 +50,9 @@ __global__ void sampler_init_kernel(float* __restrict__ x, size_t nq, float std1
 // mean = x + (g^2 dt) score ; x = mean + noise_scale z ; last block to finish bumps the step counter.
 __global__ void predictor_kernel(float* __restrict__ x, const float* __restrict__ score, float* __restrict__ mean_out,
                                  size_t nq, const float* __restrict__ table, int32_t* __restrict__ step_counter,
-                                 uint64_t seed, uint32_t draw_base,
-                                 uint32_t draw_stride, uint64_t first_q) {
+                                 uint32_t draw_base, uint32_t draw_stride, uint64_t first_q) {
   const int step = *step_counter;
+  const uint64_t seed = state_seed(step_counter);
   const float* row = table + static_cast<size_t>(step) * SBGM_STEP_COLS;
   const float drift = row[4], nscale = row[5];
   const uint32_t draw = draw_base + draw_stride * static_cast<uint32_t>(step);
@@ -102,8 +107,9 @@ __global__ void sumsq_kernel(const float* __restrict__ score, float* __restrict_
 
 __global__ void corrector_kernel(float* __restrict__ x, const float* __restrict__ score, const float* __restrict__ sumsq,
                                  int members_total, float noise_norm, float snr, size_t nq,
-                                 const int32_t* __restrict__ step_counter, uint64_t seed, uint32_t draw_base,
+                                 const int32_t* __restrict__ step_counter, uint32_t draw_base,
                                  uint32_t draw_stride, uint64_t first_q) {
+  const uint64_t seed = state_seed(step_counter);
   __shared__ float s_eps;
   if (threadIdx.x == 0) {
     float gn = 0.0f;
@@ -207,11 +213,11 @@ int sbgm_sampler_init(float* x, size_t count, float std1, uint64_t seed, uint64_
 }
 
 int sbgm_sampler_predictor(float* x, const float* score, float* mean_out, size_t count, const float* step_table,
-                           int32_t* step_counter, uint64_t seed, uint32_t draw_base, uint32_t draw_stride,
+                           int32_t* step_counter, uint32_t draw_base, uint32_t draw_stride,
                            uint64_t first_elem, void* stream) {
   SBGM_REQUIRE(count % 4 == 0 && first_elem % 4 == 0, "sampler_predictor: count and first_elem must be multiples of 4");
   predictor_kernel<<<grid_for(count / 4), kBlock, 0, as_stream(stream)>>>(x, score, mean_out, count / 4, step_table,
-                                                                          step_counter, seed, draw_base, draw_stride,
+                                                                          step_counter, draw_base, draw_stride,
                                                                           first_elem / 4);
   return check_launch("sampler_predictor");
 }
@@ -223,11 +229,11 @@ int sbgm_sampler_sumsq(const float* score, float* sumsq, int members, int per_me
 }
 
 int sbgm_sampler_corrector(float* x, const float* score, const float* sumsq, int members_total, int per_member,
-                           float snr, size_t count, const int32_t* step_counter, uint64_t seed,
+                           float snr, size_t count, const int32_t* step_counter,
                            uint32_t draw_base, uint32_t draw_stride, uint64_t first_elem, void* stream) {
   SBGM_REQUIRE(count % 4 == 0 && first_elem % 4 == 0, "sampler_corrector: count and first_elem must be multiples of 4");
   corrector_kernel<<<grid_for(count / 4), kBlock, 0, as_stream(stream)>>>(
-      x, score, sumsq, members_total, sqrtf(static_cast<float>(per_member)), snr, count / 4, step_counter, seed,
+      x, score, sumsq, members_total, sqrtf(static_cast<float>(per_member)), snr, count / 4, step_counter,
       draw_base, draw_stride, first_elem / 4);
   return check_launch("sampler_corrector");
 }

@@ -71,6 +71,31 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-uniform issue path: the WHOLE warp runs the MMA loop (uniform control flow, so descriptor arithmetic
+// stays on the uniform datapath) and one elected lane issues.  `a_lo` / `b_lo` are the low descriptor words
+// ((smem_addr & 0x3FFFF) >> 4 | 1 << 16); the high word is the constant kDescHi (SBO = 1024 B, version 1,
+// SWIZZLE_128B).  Advancing an operand by `bytes` is a plain add of bytes >> 4 to the low word.
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -128,42 +153,102 @@ __device__ __forceinline__ float act_ct(float x) {
   return x;
 }
 
-// One 32-column chunk of one accumulator row.  ACT and PROJ are compile-time; COL0 is the chunk's first
-// channel inside a 64-wide tile (only used by the projection).
-template <int FMT, int ACT, bool PROJ, int COL0>
-__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, const uint32_t (&r)[32], int co_base, int n,
-                                               size_t pix, float (&proj_acc)[kProjMax]) {
+// 8 x 8 transpose of 16-byte items inside each group of 8 lanes: on entry lane j of a group holds the 8
+// channel-chunks of ITS pixel; on exit it holds chunk j of the group's 8 pixels, so that a group writes one
+// full 128-byte line per store instruction (4 lines per warp-instruction instead of 32).
+__device__ __forceinline__ void transpose8_u4(uint4 (&v)[8], int lane) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int co = co_base + g * 8;
-    float v[8];
+  for (int s = 4; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-    if (ep.bias) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + co)), b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + co + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    for (int i = 0; i < 8; ++i) {
+      if (i & s) continue;
+      const uint4 send = up ? v[i] : v[i | s];
+      uint4 recv;
+      recv.x = __shfl_xor_sync(0xffffffffu, send.x, s);
+      recv.y = __shfl_xor_sync(0xffffffffu, send.y, s);
+      recv.z = __shfl_xor_sync(0xffffffffu, send.z, s);
+      recv.w = __shfl_xor_sync(0xffffffffu, send.w, s);
+      if (up) v[i] = recv; else v[i | s] = recv;
     }
-    if (!PROJ && ep.residual) {
+  }
+}
+
+// Store one pixel's 64 consecutive channels (this lane's `v`) for all 32 lanes of the warp, coalesced through
+// the 8-lane transpose.  Must be called by the whole warp; `valid` masks pixels outside the tensor.
+template <int FMT>
+__device__ __forceinline__ void store_block64(void* out, size_t out_plane, int cout, const float (&v)[64], size_t pix,
+                                              bool valid, int co_base, int lane) {
+  const int l8 = lane & 7, gbase = lane & ~7;
+  constexpr int kPlanes = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
+#pragma unroll
+  for (int pl = 0; pl < kPlanes; ++pl) {
+    uint4 c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = v[j * 8 + e];
+        t[e] = (pl == 0) ? x : x - bf16_round(x);
+      }
+      c[j] = pack_bf16x8(t);
+    }
+    transpose8_u4(c, lane);
+    __nv_bfloat16* base = static_cast<__nv_bfloat16*>(out) + pl * out_plane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned long long pk = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(pix), gbase + k);
+      const int vk = __shfl_sync(0xffffffffu, static_cast<int>(valid), gbase + k);
+      if (vk) *reinterpret_cast<uint4*>(base + pk * cout + co_base + l8 * 8) = c[k];
+    }
+  }
+}
+
+// 64 accumulator columns (two 32-column TMEM loads) of one row.  ACT and PROJ are compile-time.
+template <int FMT, int ACT, bool PROJ>
+__device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const uint32_t (&ra)[32], const uint32_t (&rb)[32],
+                                                 int co_base, int n, size_t pix, bool valid, int lane,
+                                                 float (&proj_acc)[kProjMax]) {
+  float v[64];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = __uint_as_float(ra[j]);
+    v[32 + j] = __uint_as_float(rb[j]);
+  }
+  if (ep.bias) {
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + co_base) + g);
+      v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+    }
+  }
+  if (!PROJ && ep.residual && valid) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
       float rv[8];
-      Act<FMT>::load8(ep.residual, ep.res_plane, pix * ep.cout + co, rv);
+      Act<FMT>::load8(ep.residual, ep.res_plane, pix * ep.cout + co_base + g * 8, rv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += rv[j];
+      for (int j = 0; j < 8; ++j) v[g * 8 + j] += rv[j];
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_ct<ACT>(v[j]);
-    if (!PROJ && ep.tproj) {
-      const float* tp = ep.tproj + static_cast<size_t>(n) * ep.tproj_stride + co;
-      const float4 t0 = __ldg(reinterpret_cast<const float4*>(tp)), t1 = __ldg(reinterpret_cast<const float4*>(tp + 4));
-      v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+  for (int j = 0; j < 64; ++j) v[j] = act_ct<ACT>(v[j]);
+  if (!PROJ && ep.tproj && valid) {
+    const float4* tp = reinterpret_cast<const float4*>(ep.tproj + static_cast<size_t>(n) * ep.tproj_stride + co_base);
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      const float4 t = __ldg(tp + g);
+      v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
     }
-    if (PROJ) {
+  }
+  if (PROJ) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 64; ++j)
 #pragma unroll
-        for (int q = 0; q < kProjN; ++q) proj_acc[q] = fmaf(v[j], c_proj_w[q * 64 + COL0 + g * 8 + j], proj_acc[q]);
-    } else {
-      Act<FMT>::store8(ep.out, ep.out_plane, pix * ep.cout + co, v);
-    }
+      for (int q = 0; q < kProjN; ++q) proj_acc[q] = fmaf(v[j], c_proj_w[q * 64 + j], proj_acc[q]);
+  } else {
+    store_block64<FMT>(ep.out, ep.out_plane, ep.cout, v, pix, valid, co_base, lane);
   }
 }
 

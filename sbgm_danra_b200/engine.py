@@ -339,13 +339,15 @@ class EncoderEngine:
             tp.label_emb = pk.get(f"{p}label_emb.weight").contiguous()
         self.tp = tp
 
-    def stem_partial(self, planes: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    def stem_partial(self, planes: torch.Tensor, h: int, w: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """conv1 restricted to the conditioning channels (step-invariant in a sampler): fp32 NHWC."""
         npl, cc = planes.shape[0], planes.shape[1]
-        out = Act(FMT_F32, npl, h // 2, w // 2, 64, self.device)
+        if out is None:
+            out = torch.empty((npl, h // 2, w // 2, 64), dtype=torch.float32, device=self.device)
+        assert tuple(out.shape) == (npl, h // 2, w // 2, 64) and out.is_contiguous()
         call("sbgm_stem_conv", None, planes.data_ptr(), npl, cc, 1, cc + 1, self.stem_w.data_ptr(), None, 0, None, 0,
-             out.ptr, out.plane, FMT_F32, npl, h, w, _stream())
-        return out.buf
+             out.data_ptr(), out.numel(), FMT_F32, npl, h, w, _stream())
+        return out
 
     def forward(self, x: torch.Tensor, planes: Optional[torch.Tensor], tproj: torch.Tensor,
                 partial: Optional[torch.Tensor] = None) -> List[Act]:

@@ -140,48 +140,65 @@ def _table_pc(marginal_prob_std, diffusion_coeff, n_steps: int, eps: float) -> t
     return tab
 
 
-class _NativeStep:
-    """One fused sampler step on the engine, written so it can be captured in a CUDA graph."""
+def _seed_words(seed: int):
+    lo, hi = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    return [0, 0, lo - (1 << 32) if lo >= (1 << 31) else lo, hi - (1 << 32) if hi >= (1 << 31) else hi]
 
-    def __init__(self, model, batch: int, size: int, table: torch.Tensor, y, cond_img, lsm_cond, topo_cond,
-                 cfg_scale: Optional[float]):
+
+class _NativeStep:
+    """One fused sampler step on the engine, written so it can be captured in a CUDA graph.  All buffers have
+    fixed addresses; a new sampler call with the same shapes only rewrites their contents."""
+
+    def __init__(self, model, batch: int, size: int, n_steps: int, has_y: bool, planes_batch: int, cfg_scale: Optional[float]):
         eng = model.engine()
-        if model.training:
-            raise NotImplementedError("sampling with train-mode BatchNorm is not on the CUDA path yet; call model.eval()")
         self.eng, self.dev, self.b, self.size = eng, eng.device, batch, size
         dev = self.dev
-        self.table = table.to(dev).contiguous()
+        self.table = torch.zeros((n_steps, STEP_COLS), dtype=torch.float32, device=dev)
         self.inv_std = self.table[:, 3]
-        self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(4, dtype=torch.int32, device=dev)       # step, scratch, seed lo, seed hi
         self.x = torch.zeros((batch, 1, size, size), dtype=torch.float32, device=dev)
         self.score = torch.empty_like(self.x)
         self.mean = torch.empty_like(self.x)
         self.tproj = torch.empty((batch, eng.tp.c_total), dtype=torch.float32, device=dev)
-        self.y = None if y is None else y.to(device=dev, dtype=torch.int64).contiguous()
+        self.y = torch.zeros(batch, dtype=torch.int64, device=dev) if has_y else None
         self.cfg_scale = cfg_scale
-        self.partial = self._partial(cond_img, lsm_cond, topo_cond)
+        cc = eng.enc.cin - 1
+        self.partial = torch.empty((planes_batch, size // 2, size // 2, 64), dtype=torch.float32, device=dev) if cc > 0 else None
         if cfg_scale is not None:
-            self.partial_u = self._partial(None if cond_img is None else torch.zeros_like(cond_img),
-                                           _strip_mask(lsm_cond), _strip_mask(topo_cond))
+            self.partial_u = None if self.partial is None else torch.empty_like(self.partial)
             self.y_u = None if self.y is None else torch.zeros_like(self.y)
             self.score_c = torch.empty_like(self.x)
             self.score_u = torch.empty_like(self.x)
             self.tproj_u = torch.empty_like(self.tproj)
+        self.graph = None
+        self.per_replay = 0
 
-    def _partial(self, cond_img, lsm_cond, topo_cond) -> Optional[torch.Tensor]:
-        planes = _eng.concat_planes(self.b, lsm_cond, topo_cond, cond_img, self.dev)
-        cc = self.eng.enc.cin - 1
+    @staticmethod
+    def planes_of(eng, batch, cond_img, lsm_cond, topo_cond):
+        planes = _eng.concat_planes(batch, lsm_cond, topo_cond, cond_img, eng.device)
+        cc = eng.enc.cin - 1
         if planes is None:
             if cc != 0:
                 raise ValueError(f"model expects {cc} conditioning channels but none were given")
             return None
         if planes.shape[1] != cc:
             raise ValueError(f"model expects {cc} conditioning channels, got {planes.shape[1]}")
-        if planes.shape[0] not in (1, self.b):
-            raise ValueError(f"Batch mismatch: batch_size={self.b}, conditions={planes.shape[0]}.")
+        if planes.shape[0] not in (1, batch):
+            raise ValueError(f"Batch mismatch: batch_size={batch}, conditions={planes.shape[0]}.")
         if planes.shape[0] > 1 and bool((planes == planes[:1]).all()):
             planes = planes[:1].contiguous()     # every member shares one conditioning sample: broadcast
-        return self.eng.enc.stem_partial(planes, self.size, self.size)
+        return planes
+
+    def load(self, table: torch.Tensor, seed: int, y, planes, planes_u) -> None:
+        """Rewrite the call-specific contents (step table, seed, labels, conditioning partial sums) in place."""
+        self.table.copy_(table)
+        self.counter.copy_(torch.tensor(_seed_words(seed), dtype=torch.int32))
+        if self.y is not None:
+            self.y.copy_(y.to(device=self.dev, dtype=torch.int64).reshape(-1))
+        if self.partial is not None:
+            self.eng.enc.stem_partial(planes, self.size, self.size, out=self.partial)
+            if self.cfg_scale is not None:
+                self.eng.enc.stem_partial(planes_u, self.size, self.size, out=self.partial_u)
 
     def _forward(self, partial, y, tproj, out) -> None:
         eng = self.eng
@@ -215,11 +232,12 @@ class _GenericStep:
         self.model, self.args = score_model, (y, cond_img, lsm_cond, topo_cond)
         self.table = table.to(dev).contiguous()
         self.table_host = table
-        self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
         self.x = torch.zeros((batch, 1, size, size), dtype=torch.float32, device=dev)
         self.mean = torch.empty_like(self.x)
         self.cfg_scale = cfg_scale
         self.k = 0
+        self.graph = None
 
     def score_into(self) -> torch.Tensor:
         bt = torch.full((self.b,), float(self.table_host[self.k, 0]), dtype=torch.float32, device=self.dev)
@@ -231,19 +249,29 @@ class _GenericStep:
         return self.score
 
 
-def _predict(st, seed, draw_base, draw_stride, first_elem) -> None:
+def _predict(st, draw_base, draw_stride, first_elem) -> None:
     call("sbgm_sampler_predictor", st.x.data_ptr(), st.score.data_ptr(), st.mean.data_ptr(), st.x.numel(),
-         st.table.data_ptr(), st.counter.data_ptr(), seed, draw_base, draw_stride, first_elem, _eng._stream())
+         st.table.data_ptr(), st.counter.data_ptr(), draw_base, draw_stride, first_elem, _eng._stream())
 
 
-def _correct(st, sumsq, sumsq_all, snr, seed, first_elem) -> None:
+def _correct(st, sumsq, sumsq_all, snr, first_elem) -> None:
     per = st.size * st.size
     call("sbgm_sampler_sumsq", st.score.data_ptr(), sumsq.data_ptr(), st.b, per, _eng._stream())
     if sumsq_all is not sumsq:
         import torch.distributed as dist
         dist.all_gather_into_tensor(sumsq_all, sumsq, group=_state.group)
     call("sbgm_sampler_corrector", st.x.data_ptr(), st.score.data_ptr(), sumsq_all.data_ptr(), sumsq_all.numel(), per,
-         float(snr), st.x.numel(), st.counter.data_ptr(), seed, 1, 2, first_elem, _eng._stream())
+         float(snr), st.x.numel(), st.counter.data_ptr(), 1, 2, first_elem, _eng._stream())
+
+
+# captured sampler plans (buffers + CUDA graph), most recent first; each holds one forward's activations
+_PLAN_CACHE: list = []
+_PLAN_CACHE_SIZE = 2
+
+
+def clear_sampler_cache() -> None:
+    """Drop the cached CUDA graphs / activation pools of previous sampler calls."""
+    _PLAN_CACHE.clear()
 
 
 def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_size, n_steps, snr, device, eps, img_size,
@@ -254,54 +282,73 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
     table = (_table_em if kind == "em" else _table_pc)(marginal_prob_std, diffusion_coeff, n_steps, eps)
     scale = _cfg_scale(cfg, clamp=(kind == "pc"))
     native = _is_native(score_model)
+    if native and score_model.training:
+        raise NotImplementedError("sampling with train-mode BatchNorm is not on the CUDA path yet; call model.eval()")
     dev = score_model.engine().device if native else torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("samplers run on CUDA devices only (no CPU fallback); got device=" + str(device))
-    with torch.no_grad(), torch.cuda.device(dev):
-        if native:
-            st = _NativeStep(score_model, batch_size, img_size, table, y, cond_img, lsm_cond, topo_cond, scale)
-        else:
-            st = _GenericStep(score_model, batch_size, img_size, table, dev, y, cond_img, lsm_cond, topo_cond, scale)
     per = img_size * img_size
     first_elem = _state.first_member * per
     std1 = float(marginal_prob_std(torch.ones(1))[0])             # score_sampling.py:93-95 / :167-168
     sharded = kind == "pc" and _state.members_total is not None and _state.members_total != batch_size
+    total = _state.members_total if sharded else batch_size
 
     with torch.no_grad(), torch.cuda.device(dev):
-        sumsq = torch.zeros(batch_size, dtype=torch.float32, device=dev)
-        sumsq_all = torch.zeros(_state.members_total, dtype=torch.float32, device=dev) if sharded else sumsq
+        if native:
+            eng = score_model.engine()
+            planes = _NativeStep.planes_of(eng, batch_size, cond_img, lsm_cond, topo_cond)
+            planes_u = None
+            if scale is not None and planes is not None:
+                planes_u = _NativeStep.planes_of(eng, batch_size, None if cond_img is None else torch.zeros_like(cond_img),
+                                                 _strip_mask(lsm_cond), _strip_mask(topo_cond))
+                if planes_u.shape[0] != planes.shape[0]:
+                    planes_u = planes_u.expand(planes.shape[0], -1, -1, -1).contiguous()
+            key = (id(eng), kind, batch_size, img_size, n_steps, scale, float(snr), y is not None,
+                   0 if planes is None else planes.shape[0], first_elem, total, id(_state.group) if sharded else 0, use_graph)
+            st = next((p for k, p in _PLAN_CACHE if k == key), None)
+            if st is None:
+                st = _NativeStep(score_model, batch_size, img_size, n_steps, y is not None,
+                                 0 if planes is None else planes.shape[0], scale)
+                st.sumsq = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+                st.sumsq_all = torch.zeros(total, dtype=torch.float32, device=dev) if sharded else st.sumsq
+                _PLAN_CACHE.insert(0, (key, st))
+                del _PLAN_CACHE[_PLAN_CACHE_SIZE:]
+            st.load(table, seed, y, planes, planes_u)
+        else:
+            st = _GenericStep(score_model, batch_size, img_size, table, dev, y, cond_img, lsm_cond, topo_cond, scale)
+            st.counter.copy_(torch.tensor(_seed_words(seed), dtype=torch.int32))
+            st.sumsq = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+            st.sumsq_all = torch.zeros(total, dtype=torch.float32, device=dev) if sharded else st.sumsq
 
         def one_step() -> None:
             if kind == "pc":
                 st.score_into()
-                _correct(st, sumsq, sumsq_all, snr, seed, first_elem)
+                _correct(st, st.sumsq, st.sumsq_all, snr, first_elem)
                 st.score_into()
-                _predict(st, seed, 2, 2, first_elem)
+                _predict(st, 2, 2, first_elem)
             else:
                 st.score_into()
-                _predict(st, seed, 1, 1, first_elem)
+                _predict(st, 1, 1, first_elem)
 
-        graph = None
-        if native and use_graph and n_steps > 1:
+        if native and use_graph and n_steps > 1 and st.graph is None:
             # eager warm-up step (lazy kernel attributes, scratch buffers), then capture one step
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 one_step()
             torch.cuda.current_stream(dev).wait_stream(side)
-            st.counter.zero_()
-            graph = torch.cuda.CUDAGraph()
+            st.graph = torch.cuda.CUDAGraph()
             before = _lib_stats.launches
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(st.graph):
                 one_step()
-            per_replay = _lib_stats.launches - before     # kernels recorded in the graph
+            st.per_replay = _lib_stats.launches - before     # kernels recorded in the graph
             _lib_stats.launches = before
-            st.counter.zero_()
+        st.counter[:2].zero_()
         call("sbgm_sampler_init", st.x.data_ptr(), st.x.numel(), std1, seed, first_elem, _eng._stream())
         for k in range(n_steps):
-            if graph is not None:
-                graph.replay()
-                _lib_stats.launches += per_replay
+            if st.graph is not None:
+                st.graph.replay()
+                _lib_stats.launches += st.per_replay
             else:
                 if not native:
                     st.k = k

@@ -273,23 +273,23 @@ def test_sampler_update_kernels():
     table = torch.zeros(4, STEP_COLS)
     table[:, 4] = torch.tensor([0.3, 0.2, 0.1, 0.05])
     table[:, 5] = torch.tensor([0.9, 0.7, 0.5, 0.3])
-    tab, counter = table.cuda(), torch.tensor([2, 0], dtype=torch.int32, device="cuda")
+    tab, counter = table.cuda(), torch.tensor([2, 0, seed, 0], dtype=torch.int32, device="cuda")
     x, mean = x0.cuda().clone(), torch.empty(b, 1, 32, 32, device="cuda")
     first = 5 * per   # this shard starts at global member 5
     call("sbgm_sampler_predictor", x.data_ptr(), s_d.data_ptr(), mean.data_ptr(), x.numel(), tab.data_ptr(),
-         counter.data_ptr(), seed, 1, 1, first, st)
+         counter.data_ptr(), 1, 1, first, st)
     z = torch.from_numpy(philox_ref.normal(b * per, seed, 1 + 2, first)).reshape(x0.shape)
     want_mean = x0 + 0.1 * s
     assert rel_l2(mean.cpu(), want_mean) < 1e-6
     assert rel_l2(x.cpu(), want_mean + 0.5 * z) < 1e-6
-    assert counter.cpu().tolist() == [3, 0]
+    assert counter.cpu().tolist() == [3, 0, seed, 0]
     # corrector
     sumsq = torch.empty(b, device="cuda")
     call("sbgm_sampler_sumsq", s_d.data_ptr(), sumsq.data_ptr(), b, per, st)
     np.testing.assert_allclose(sumsq.cpu().numpy(), (s.reshape(b, -1) ** 2).sum(1).numpy(), rtol=1e-5)
     x = x0.cuda().clone()
     call("sbgm_sampler_corrector", x.data_ptr(), s_d.data_ptr(), sumsq.data_ptr(), b, per, 0.16, x.numel(),
-         counter.data_ptr(), seed, 1, 2, first, st)
+         counter.data_ptr(), 1, 2, first, st)
     gn = torch.norm(s.reshape(b, -1), dim=-1).mean()
     eps = 2 * (0.16 * math.sqrt(per) / gn) ** 2
     z = torch.from_numpy(philox_ref.normal(b * per, seed, 1 + 2 * 3, first)).reshape(x0.shape)
