@@ -95,7 +95,16 @@ int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w
                    const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
                    void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
                    int kh, int kw, int stride, int pad, int act,
-                   const float* proj_w, int n_proj, float* proj_out, void* stream);
+                   const float* proj_w, int n_proj, float* proj_out,
+                   void* workspace, size_t workspace_bytes, float* gn_partials, void* stream);
+/* Fused GroupNorm statistics: if gn_partials != NULL (bias-only epilogue) the kernel also writes partial sums of
+ * its output at 8-channel granularity, layout [n][chunks][cout/8][2] (sum, sum of squares), chunks =
+ * sbgm_conv2d_tc_gn_chunks(...) (0 = this shape cannot fuse them).  Consumed by sbgm_groupnorm_apply. */
+int sbgm_conv2d_tc_gn_chunks(int fmt, int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad);
+/* Scratch for deterministic split-K (layers on 4x4 / 8x8 maps, where the output grid would leave most SMs
+ * idle): 0 if the shape does not split.  Passing NULL / too little simply disables split-K. */
+size_t sbgm_conv2d_tc_workspace_bytes(int fmt, int n, int h, int w, int cin, int cout, int kh, int kw,
+                                      int stride, int pad);
 /* The same operator specialised for the 64 -> 64 channel 3x3 stride-1 convolutions that carry 45% of
  * the network's FLOPs (encoder layer1, decoder blocks 3 and final conv_up): a persistent kernel (one
  * CTA per SM) keeps the whole 9 x 64 x 64 weight tensor resident in shared memory, fetches each
@@ -104,9 +113,8 @@ int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w
  * the MMAs of the next.  Requires h % 8 == 0 and w % 16 == 0.  Extra outputs:
  *   proj_w / proj_out : as above
  *   gn_partials       : if non-NULL, per-(image, 32-pixel strip) GroupNorm partial sums of the stored
- *                       values, layout [n][chunks][groups][2] with chunks = (h/8)*(w/16)*4 and
- *                       groups = 64 / gn_cpg, consumed by sbgm_groupnorm_apply (saves the statistics
- *                       pass over the activations).
+ *                       values at 8-channel granularity, layout [n][chunks][8][2] with chunks =
+ *                       (h/8)*(w/16)*4, consumed by sbgm_groupnorm_apply (saves the statistics pass).
  */
 int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
                      const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
@@ -132,8 +140,9 @@ size_t sbgm_groupnorm_scratch_floats(int n, int c, int hw);
 int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const float* beta, int groups, float eps,
                    const void* skip, size_t skip_plane, const float* tproj, int tproj_stride, int act,
                    void* y, size_t y_plane, int fmt, int n, int hw, int c, float* partials, void* stream);
-/* The apply half alone, from partial sums [n][chunks][groups][2] produced by a convolution epilogue. */
-int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, int chunks, const float* gamma,
+/* The apply half alone, from partial sums [n][chunks][pgroups][2] produced by a convolution epilogue;
+ * pgroups (a multiple of groups, c/8 for the fused statistics) consecutive partial groups form one group. */
+int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, int chunks, int pgroups, const float* gamma,
                          const float* beta, int groups, float eps, const void* skip, size_t skip_plane,
                          const float* tproj, int tproj_stride, int act, void* y, size_t y_plane, int fmt,
                          int n, int hw, int c, void* stream);

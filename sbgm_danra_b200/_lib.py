@@ -28,9 +28,11 @@ PROTOTYPES = {
     "sbgm_fourier_embed": [_p, _p, _i, _p, _i, _p],
     "sbgm_cfg_combine": [_p, _p, _f, _p, _sz, _p],
     "sbgm_stem_conv": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _sz, _i, _i, _i, _i, _p],
-    "sbgm_conv2d_tc": [_p, _sz, _p, _sz, _p, _p, _sz, _p, _i, _p, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p],
+    "sbgm_conv2d_tc": [_p, _sz, _p, _sz, _p, _p, _sz, _p, _i, _p, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p, _p],
+    "sbgm_conv2d_tc_gn_chunks": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i],
+    "sbgm_conv2d_tc_workspace_bytes": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i],
     "sbgm_conv3x3_c64": [_p, _sz, _p, _sz, _p, _p, _sz, _p, _i, _p, _sz, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p],
-    "sbgm_groupnorm_apply": [_p, _sz, _p, _i, _p, _p, _i, _f, _p, _sz, _p, _i, _i, _p, _sz, _i, _i, _i, _i, _p],
+    "sbgm_groupnorm_apply": [_p, _sz, _p, _i, _i, _p, _p, _i, _f, _p, _sz, _p, _i, _i, _p, _sz, _i, _i, _i, _i, _p],
     "sbgm_final_gather": [_p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _p],
     "sbgm_conv2d_simt": [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sbgm_groupnorm": [_p, _sz, _p, _p, _i, _f, _p, _sz, _p, _i, _i, _p, _sz, _i, _i, _i, _i, _p, _p],
@@ -53,12 +55,12 @@ PROTOTYPES = {
     "sbgm_version": [],
     "sbgm_device_is_sm100": [],
 }
-_RESTYPES = {"sbgm_last_error": C.c_char_p, "sbgm_groupnorm_scratch_floats": _sz, "sbgm_dsm_scratch_floats": _sz}
+_RESTYPES = {"sbgm_last_error": C.c_char_p, "sbgm_conv2d_tc_workspace_bytes": _sz, "sbgm_groupnorm_scratch_floats": _sz, "sbgm_dsm_scratch_floats": _sz}
 
 _lib: Optional[C.CDLL] = None
 
 # kernel launches issued per entry point (for bench.py's `gpu_launches` claim)
-_LAUNCHES = {"sbgm_groupnorm": 2, "sbgm_dsm_loss": 2}
+_LAUNCHES = {"sbgm_groupnorm": 2, "sbgm_dsm_loss": 2}   # split-K convolutions add one (not counted: conservative)
 
 
 class _Stats:

@@ -10,38 +10,42 @@
 namespace sbgm {
 
 constexpr int kAttnWarps = 8;
-constexpr int kQPerWarp = 4;
 constexpr int kKeyChunk = 32;
 
-template <int FMT, int DPL>  // DPL = ceil(d / 32): output dims per lane
+// QPW queries per warp (8 when the per-lane output slice is small, else 4).  Per 32-key chunk a warp does
+//   scores: lane <-> key, d x (1 LDS k + QPW/4 LDS.128 q-broadcast + QPW FMA)
+//   online softmax per query (warp max / sum)
+//   P V:    probabilities staged in smem, lane <-> output dim, 32 x (QPW/4 LDS.128 p-broadcast + DPL LDS v + QPW*DPL FMA)
+template <int FMT, int DPL, int QPW>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attention_kernel(const void* __restrict__ qkv, size_t plane, void* __restrict__ out, size_t out_plane, int s, int c,
                  int heads, float scale) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int d = c / heads;
-  float* ks = smem;                                  // [32][d + 1]
-  float* vs = ks + kKeyChunk * (d + 1);              // [32][d]
-  float* qs = vs + kKeyChunk * d;                    // [warps][d][4]
+  float* ks = smem;                                              // [32][d + 1]
+  float* vs = ks + kKeyChunk * (d + 1) + ((kKeyChunk * (d + 1)) & 3 ? 4 - ((kKeyChunk * (d + 1)) & 3) : 0);  // [32][d], 16-B aligned
+  float* qs = vs + kKeyChunk * d;                                // [warps][d][QPW]
+  float* ps = qs + kAttnWarps * d * QPW;                         // [warps][32][QPW]
   const int b = blockIdx.z, head = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (kAttnWarps * kQPerWarp) + warp * kQPerWarp;
+  const int q0 = blockIdx.x * (kAttnWarps * QPW) + warp * QPW;
   const size_t row_stride = static_cast<size_t>(3) * c;
   const size_t base = static_cast<size_t>(b) * s * row_stride;
   const int dvec = d >> 3;
 
-  // stage this warp's 4 query vectors (pre-scaled) as qs[warp][i][q]
-  float* myq = qs + static_cast<size_t>(warp) * d * kQPerWarp;
-  for (int item = lane; item < kQPerWarp * dvec; item += 32) {
+  float* myq = qs + static_cast<size_t>(warp) * d * QPW;
+  float* myp = ps + static_cast<size_t>(warp) * kKeyChunk * QPW;
+  for (int item = lane; item < QPW * dvec; item += 32) {
     const int qi = item / dvec, vec = item % dvec;
     float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (q0 + qi < s) Act<FMT>::load8(qkv, plane, base + static_cast<size_t>(q0 + qi) * row_stride + head * d + vec * 8, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) myq[(vec * 8 + j) * kQPerWarp + qi] = v[j] * scale;
+    for (int j = 0; j < 8; ++j) myq[(vec * 8 + j) * QPW + qi] = v[j] * scale;
   }
 
-  float m[kQPerWarp], l[kQPerWarp], acc[kQPerWarp][DPL];
+  float m[QPW], l[QPW], acc[QPW][DPL];
 #pragma unroll
-  for (int qi = 0; qi < kQPerWarp; ++qi) {
+  for (int qi = 0; qi < QPW; ++qi) {
     m[qi] = -INFINITY;
     l[qi] = 0.0f;
 #pragma unroll
@@ -65,54 +69,76 @@ attention_kernel(const void* __restrict__ qkv, size_t plane, void* __restrict__ 
       }
     }
     __syncthreads();
-    // scores: lane <-> key k0 + lane, 4 queries at once
-    float sc[kQPerWarp] = {0.f, 0.f, 0.f, 0.f};
+    float sc[QPW];
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) sc[qi] = 0.0f;
     const float* krow = ks + lane * (d + 1);
     for (int i = 0; i < d; ++i) {
       const float kvv = krow[i];
-      const float4 qv = *reinterpret_cast<const float4*>(myq + i * kQPerWarp);
-      sc[0] = fmaf(kvv, qv.x, sc[0]); sc[1] = fmaf(kvv, qv.y, sc[1]);
-      sc[2] = fmaf(kvv, qv.z, sc[2]); sc[3] = fmaf(kvv, qv.w, sc[3]);
+#pragma unroll
+      for (int g = 0; g < QPW / 4; ++g) {
+        const float4 qv = *reinterpret_cast<const float4*>(myq + i * QPW + 4 * g);
+        sc[4 * g + 0] = fmaf(kvv, qv.x, sc[4 * g + 0]); sc[4 * g + 1] = fmaf(kvv, qv.y, sc[4 * g + 1]);
+        sc[4 * g + 2] = fmaf(kvv, qv.z, sc[4 * g + 2]); sc[4 * g + 3] = fmaf(kvv, qv.w, sc[4 * g + 3]);
+      }
     }
     const bool key_ok = (k0 + lane) < s;
+    float corr[QPW];
 #pragma unroll
-    for (int qi = 0; qi < kQPerWarp; ++qi) {
+    for (int qi = 0; qi < QPW; ++qi) {
       const float sv = key_ok ? sc[qi] : -INFINITY;
       const float mnew = fmaxf(m[qi], warp_max(sv));
-      const float p = key_ok ? expf(sv - mnew) : 0.0f;
-      const float corr = expf(m[qi] - mnew);   // m = -inf on the first chunk -> 0
-      l[qi] = l[qi] * corr + warp_sum(p);
+      const float pv = key_ok ? expf(sv - mnew) : 0.0f;
+      corr[qi] = expf(m[qi] - mnew);          // m = -inf on the first chunk -> 0
+      l[qi] = l[qi] * corr[qi] + warp_sum(pv);
       m[qi] = mnew;
+      sc[qi] = pv;
+    }
+    __syncwarp();
 #pragma unroll
-      for (int dd = 0; dd < DPL; ++dd) acc[qi][dd] *= corr;
-      for (int j = 0; j < kKeyChunk; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, p, j);
+    for (int g = 0; g < QPW / 4; ++g)
+      *reinterpret_cast<float4*>(myp + lane * QPW + 4 * g) = make_float4(sc[4 * g], sc[4 * g + 1], sc[4 * g + 2], sc[4 * g + 3]);
+    __syncwarp();
 #pragma unroll
-        for (int dd = 0; dd < DPL; ++dd) {
-          const int dim = lane + 32 * dd;
-          if (dim < d) acc[qi][dd] = fmaf(pj, vs[j * d + dim], acc[qi][dd]);
+    for (int qi = 0; qi < QPW; ++qi)
+#pragma unroll
+      for (int dd = 0; dd < DPL; ++dd) acc[qi][dd] *= corr[qi];
+    for (int j = 0; j < kKeyChunk; ++j) {
+      float pj[QPW];
+#pragma unroll
+      for (int g = 0; g < QPW / 4; ++g) {
+        const float4 t = *reinterpret_cast<const float4*>(myp + j * QPW + 4 * g);
+        pj[4 * g] = t.x; pj[4 * g + 1] = t.y; pj[4 * g + 2] = t.z; pj[4 * g + 3] = t.w;
+      }
+#pragma unroll
+      for (int dd = 0; dd < DPL; ++dd) {
+        const int dim = lane + 32 * dd;
+        if (dim < d) {
+          const float vv = vs[j * d + dim];
+#pragma unroll
+          for (int qi = 0; qi < QPW; ++qi) acc[qi][dd] = fmaf(pj[qi], vv, acc[qi][dd]);
         }
       }
     }
   }
-  // write: stage through smem (reuse this warp's q slot) so stores are 8-channel vectors
+  // write: stage through smem (this warp's q slot) so stores are 8-channel vectors
   __syncwarp();
 #pragma unroll
-  for (int qi = 0; qi < kQPerWarp; ++qi) {
+  for (int qi = 0; qi < QPW; ++qi) {
     const float inv = 1.0f / l[qi];
 #pragma unroll
     for (int dd = 0; dd < DPL; ++dd) {
       const int dim = lane + 32 * dd;
-      if (dim < d) myq[dim * kQPerWarp + qi] = acc[qi][dd] * inv;
+      if (dim < d) myq[dim * QPW + qi] = acc[qi][dd] * inv;
     }
   }
   __syncwarp();
-  for (int item = lane; item < kQPerWarp * dvec; item += 32) {
+  for (int item = lane; item < QPW * dvec; item += 32) {
     const int qi = item / dvec, vec = item % dvec;
     if (q0 + qi >= s) continue;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = myq[(vec * 8 + j) * kQPerWarp + qi];
+    for (int j = 0; j < 8; ++j) v[j] = myq[(vec * 8 + j) * QPW + qi];
     Act<FMT>::store8(out, out_plane, (static_cast<size_t>(b) * s + q0 + qi) * c + head * d + vec * 8, v);
   }
 }
@@ -120,16 +146,18 @@ attention_kernel(const void* __restrict__ qkv, size_t plane, void* __restrict__ 
 template <int FMT, int DPL>
 static int launch_attention(const void* qkv, size_t plane, void* out, size_t out_plane, int b, int s, int c, int heads,
                             cudaStream_t st) {
+  constexpr int QPW = (DPL <= 4) ? 8 : 4;
   const int d = c / heads;
-  const size_t smem = (static_cast<size_t>(kKeyChunk) * (d + 1) + kKeyChunk * d + kAttnWarps * d * kQPerWarp) * sizeof(float);
-  auto kern = attention_kernel<FMT, DPL>;
+  const size_t ks_floats = (static_cast<size_t>(kKeyChunk) * (d + 1) + 3) & ~static_cast<size_t>(3);
+  const size_t smem = (ks_floats + kKeyChunk * d + kAttnWarps * d * QPW + kAttnWarps * kKeyChunk * QPW) * sizeof(float);
+  auto kern = attention_kernel<FMT, DPL, QPW>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
       set_error("attention: cannot reserve %zu bytes of shared memory", smem);
       return 1;
     }
   }
-  dim3 grid(ceil_div(s, kAttnWarps * kQPerWarp), heads, b);
+  dim3 grid(ceil_div(s, kAttnWarps * QPW), heads, b);
   kern<<<grid, kAttnWarps * 32, smem, st>>>(qkv, plane, out, out_plane, s, c, heads, 1.0f / sqrtf(static_cast<float>(d)));
   return check_launch("attention");
 }

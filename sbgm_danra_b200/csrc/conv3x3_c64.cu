@@ -169,32 +169,9 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(acc));
       if (p.gn_partials) {
-        // GroupNorm partial sums (groups of 8 channels) of the values as stored, reduced over this warp's 32 pixels
-        float gs[8], gq[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float s = 0.0f, q = 0.0f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]);
-            if (p.ep.bias) v += __ldg(p.ep.bias + g * 8 + j);
-            if (FMT == SBGM_FMT_BF16) v = bf16_round(v);
-            s += v;
-            q = fmaf(v, v, q);
-          }
-          gs[g] = warp_sum(s);
-          gq[g] = warp_sum(q);
-        }
-        if (lane == 0) {
-          const int chunks = p.tiles_w * p.tiles_h * 4;
-          const int chunk = (th * p.tiles_w + tw) * 4 + quarter;
-          float* dst = p.gn_partials + (static_cast<size_t>(n) * chunks + chunk) * 16;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            dst[2 * g] = gs[g];
-            dst[2 * g + 1] = gq[g];
-          }
-        }
+        const int chunks = p.tiles_w * p.tiles_h * 4;
+        const int chunk = (th * p.tiles_w + tw) * 4 + quarter;
+        gn_block64_stats<FMT>(r0, r1, p.ep.bias, 0, true, lane, p.gn_partials + (static_cast<size_t>(n) * chunks + chunk) * 16);
       }
       epilogue_block64<FMT, ACT, PROJ>(p.ep, r0, r1, 0, n, pix, true, lane, proj_acc);
       if (PROJ) epilogue_store_proj(p.ep, pix, proj_acc);

@@ -28,6 +28,10 @@ struct ConvTcParams {
   int w_tile, h_tile, n_tile;
   int tiles_w, tiles_h;
   int cin_blocks;
+  int splits;          // split-K factor (gridDim.z); > 1 => raw fp32 partial tiles go to `ws`
+  float* ws;           // [splits][pixels][cout] fp32
+  float* gn_partials;  // [n][gn_chunks][cout/8][2] or nullptr: fused GroupNorm statistics (8-channel granularity)
+  int gn_chunks;
   EpilogueParams ep;
 };
 
@@ -78,13 +82,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
   const int wo0 = tw * p.w_tile, ho0 = th * p.h_tile, n0 = tn * p.n_tile;
   const int co0 = blockIdx.y * BLOCK_N;
-  const int num_kb = p.kh * p.kw * p.cin_blocks;
+  const int total_kb = p.kh * p.kw * p.cin_blocks;
+  const int kb_per = (total_kb + p.splits - 1) / p.splits;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;     // >= 1 by construction of `splits`
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kbi = 0; kbi < num_kb; ++kbi) {
+        const int kb = kb_begin + kbi;
         const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
         const int r = tap / p.kw, s = tap - r * p.kw;
         mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -149,18 +157,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
       }
     };
+    if (!PROJ && p.splits > 1) {                    // split-K: raw fp32 partial tile, finished by splitk_finalize_kernel
+      float* dst = p.ws + (static_cast<size_t>(blockIdx.z) * p.n * p.ho * p.wo + pix) * p.ep.cout + co0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {      // the whole warp walks the tile in 64-channel blocks
-      uint32_t ra[32], rb[32];
-      load_acc(c0, ra);
-      load_acc(c0 + 32, rb);
-      epilogue_block64<FMT, ACT, PROJ>(p.ep, ra, rb, co0 + c0, n, pix, valid, lane, proj_acc);
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t ra[32];
+        load_acc(c0, ra);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(dst + c0)[j] = make_float4(__uint_as_float(ra[4 * j]), __uint_as_float(ra[4 * j + 1]),
+                                                                 __uint_as_float(ra[4 * j + 2]), __uint_as_float(ra[4 * j + 3]));
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {      // the whole warp walks the tile in 64-channel blocks
+        uint32_t ra[32], rb[32];
+        load_acc(c0, ra);
+        load_acc(c0 + 32, rb);
+        if (!PROJ && p.gn_partials) {
+          // this warp's 32 rows lie in one image (host-checked): chunk = which 32-row strip of that image
+          int img, chunk;
+          if (p.n_tile == 1) {
+            img = n0;
+            chunk = (th * p.tiles_w + tw) * 4 + quarter;
+          } else {
+            const int rows_per_img = p.h_tile * p.w_tile;
+            img = n0 + (quarter * 32) / rows_per_img;
+            chunk = ((quarter * 32) % rows_per_img) >> 5;
+          }
+          if (img < p.n)
+            gn_block64_stats<FMT>(ra, rb, p.ep.bias, co0 + c0, valid, lane,
+                                  p.gn_partials + ((static_cast<size_t>(img) * p.gn_chunks + chunk) * (p.ep.cout >> 3) + ((co0 + c0) >> 3)) * 2);
+        }
+        epilogue_block64<FMT, ACT, PROJ>(p.ep, ra, rb, co0 + c0, n, pix, valid, lane, proj_acc);
+      }
     }
     if (PROJ && valid) epilogue_store_proj(p.ep, pix, proj_acc);
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kSplit * BLOCK_N);
+}
+
+// Sum the split-K partial tiles in a fixed order (deterministic) and apply the fused epilogue.
+template <int FMT, int ACT>
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits, size_t pixels, int hw, EpilogueParams ep) {
+  const int vecs = ep.cout >> 3;
+  const size_t total = pixels * vecs;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = i / vecs;
+    const int co = static_cast<int>(i % vecs) * 8;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int z = 0; z < splits; ++z) {
+      const float4* src = reinterpret_cast<const float4*>(ws + (static_cast<size_t>(z) * pixels + pix) * ep.cout + co);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (ep.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(ep.bias + co + j);
+    }
+    if (ep.residual) {
+      float rv[8];
+      Act<FMT>::load8(ep.residual, ep.res_plane, pix * ep.cout + co, rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += rv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_ct<ACT>(v[j]);
+    if (ep.tproj) {
+      const int n = static_cast<int>(pix / hw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(ep.tproj + static_cast<size_t>(n) * ep.tproj_stride + co + j);
+    }
+    Act<FMT>::store8(ep.out, ep.out_plane, pix * ep.cout + co, v);
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -246,8 +320,14 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
     set_error("conv2d_tc: projection weight upload failed");
     return 1;
   }
-  dim3 grid(m_tiles, p.ep.cout / BLOCK_N);
+  dim3 grid(m_tiles, p.ep.cout / BLOCK_N, p.splits);
   kern<<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  if (!PROJ && p.splits > 1) {
+    const size_t pixels = static_cast<size_t>(p.n) * p.ho * p.wo;
+    const size_t items = pixels * (p.ep.cout / 8);
+    const int fgrid = static_cast<int>(items / 256 + 1 < 148 * 8 ? items / 256 + 1 : 148 * 8);
+    splitk_finalize_kernel<FMT, ACT><<<fgrid, 256, 0, st>>>(p.ws, p.splits, pixels, p.ho * p.wo, p.ep);
+  }
   return check_launch("conv2d_tc");
 }
 
@@ -265,11 +345,63 @@ static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Co
 
 using namespace sbgm;
 
+// Split-K factor: layers whose output grid leaves most SMs idle and whose K loop is long (the 4x4 / 8x8 maps)
+// are bound by one SM's operand ingest; slicing K over up to 4 CTAs spreads the same bytes over 4x the SMs.
+static int pick_splits(int ctas, int total_kb) {
+  int splits = 1;
+  while (splits < 4 && ctas * splits * 2 <= 148 && total_kb / (splits * 2) >= 8) splits *= 2;
+  return splits;
+}
+
+static void conv_tc_geometry(int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, int planes,
+                             ConvTcParams* p, int* block_n, int* m_tiles) {
+  p->n = n;
+  p->ho = (h + 2 * pad - kh) / stride + 1;
+  p->wo = (w + 2 * pad - kw) / stride + 1;
+  p->kh = kh; p->kw = kw; p->stride = stride; p->pad = pad;
+  pick_tile(n, p->ho, p->wo, &p->w_tile, &p->h_tile, &p->n_tile);
+  p->tiles_w = ceil_div(p->wo, p->w_tile);
+  p->tiles_h = ceil_div(p->ho, p->h_tile);
+  p->cin_blocks = cin / 64;
+  *m_tiles = p->tiles_w * p->tiles_h * ceil_div(n, p->n_tile);
+  *block_n = (cout % 256 == 0 && planes == 1) ? 256 : (cout % 128 == 0 ? 128 : 64);
+  p->splits = pick_splits(*m_tiles * (cout / *block_n), kh * kw * p->cin_blocks);
+}
+
+// chunks per image of the fused GroupNorm statistics, or 0 if this shape cannot fuse them
+static int gn_chunks_for(const ConvTcParams& p) {
+  if (p.splits > 1) return 0;
+  if (p.n_tile == 1) return p.tiles_w * p.tiles_h * 4;
+  const int hw = p.ho * p.wo;
+  if (p.h_tile == p.ho && p.w_tile == p.wo && hw % 32 == 0) return hw / 32;
+  return 0;
+}
+
+extern "C" int sbgm_conv2d_tc_gn_chunks(int fmt, int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad) {
+  if (cin % 64 != 0 || cout % 64 != 0 || stride < 1) return 0;
+  ConvTcParams p;
+  int block_n = 0, m_tiles = 0;
+  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, fmt == SBGM_FMT_BF16X2 ? 2 : 1, &p, &block_n, &m_tiles);
+  if (p.ho <= 0 || p.wo <= 0) return 0;
+  return gn_chunks_for(p);
+}
+
+extern "C" size_t sbgm_conv2d_tc_workspace_bytes(int fmt, int n, int h, int w, int cin, int cout, int kh, int kw,
+                                                 int stride, int pad) {
+  if (cin % 64 != 0 || cout % 64 != 0 || stride < 1) return 0;
+  ConvTcParams p;
+  int block_n = 0, m_tiles = 0;
+  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, fmt == SBGM_FMT_BF16X2 ? 2 : 1, &p, &block_n, &m_tiles);
+  if (p.ho <= 0 || p.wo <= 0 || p.splits <= 1) return 0;
+  return static_cast<size_t>(p.splits) * n * p.ho * p.wo * cout * sizeof(float);
+}
+
 extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
                               const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
                               void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
                               int kh, int kw, int stride, int pad, int act, const float* proj_w, int n_proj,
-                              float* proj_out, void* stream) {
+                              float* proj_out, void* workspace, size_t workspace_bytes, float* gn_partials,
+                              void* stream) {
   SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv2d_tc: format %d is not a tensor-core format", fmt);
   SBGM_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv2d_tc: cin=%d and cout=%d must be multiples of 64", cin, cout);
   SBGM_REQUIRE(stride >= 1 && stride <= 8, "conv2d_tc: stride %d unsupported", stride);
@@ -281,13 +413,16 @@ extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weigh
   const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;
 
   ConvTcParams p;
-  p.n = n; p.ho = ho; p.wo = wo;
-  p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
-  pick_tile(n, ho, wo, &p.w_tile, &p.h_tile, &p.n_tile);
-  p.tiles_w = ceil_div(wo, p.w_tile);
-  p.tiles_h = ceil_div(ho, p.h_tile);
-  const int tiles_n = ceil_div(n, p.n_tile);
-  p.cin_blocks = cin / 64;
+  int block_n = 0, m_tiles = 0;
+  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, planes, &p, &block_n, &m_tiles);
+  const size_t ws_need = static_cast<size_t>(p.splits) * n * ho * wo * cout * sizeof(float);
+  if (p.splits > 1 && (proj_w != nullptr || workspace == nullptr || workspace_bytes < ws_need)) p.splits = 1;
+  p.ws = static_cast<float*>(workspace);
+  p.gn_partials = gn_partials;
+  p.gn_chunks = gn_chunks_for(p);
+  SBGM_REQUIRE(gn_partials == nullptr || (p.gn_chunks > 0 && residual == nullptr && tproj == nullptr && act == SBGM_ACT_NONE &&
+                                          proj_w == nullptr),
+               "conv2d_tc: this shape / epilogue cannot fuse GroupNorm statistics (query sbgm_conv2d_tc_gn_chunks first)");
   p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
   p.ep.act = act; p.ep.cout = cout; p.ep.out = out; p.ep.out_plane = out_plane;
   p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
@@ -296,9 +431,7 @@ extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weigh
   CUtensorMap ta, tb;
   if (encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
   const int K = kh * kw * cin;
-  const int block_n = (cout % 256 == 0 && planes == 1) ? 256 : (cout % 128 == 0 ? 128 : 64);
   if (encode_weight_map(&tb, weight, planes, w_plane, cout, K, block_n)) return 1;
-  const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   cudaStream_t st = as_stream(stream);
   if (fmt == SBGM_FMT_BF16) {
     if (block_n == 256) return launch_conv_tc<SBGM_FMT_BF16, 256, 4>(ta, tb, p, m_tiles, st);

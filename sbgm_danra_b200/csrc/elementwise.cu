@@ -203,25 +203,38 @@ __global__ void gn_partial_kernel(const void* __restrict__ x, size_t plane, int 
 // Stage 2: finish the reduction per group (double accumulation over the 32 chunks) and apply.
 template <int FMT>
 __global__ void gn_apply_kernel(const void* __restrict__ x, size_t x_plane, const float* __restrict__ partials,
-                                int chunks, const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                                int chunks, int pgroups, const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                                 const void* __restrict__ skip, size_t skip_plane, const float* __restrict__ tproj,
                                 int tproj_stride, int act, void* __restrict__ y, size_t y_plane, int hw, int c) {
   extern __shared__ float coef[];  // [c][2]: scale, shift per channel (norm + affine + tproj folded), then [groups][2]
   float* gstat = coef + 2 * c;
   const int n = blockIdx.y;
   const int cpg = c / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-      const float* p = partials + ((static_cast<size_t>(n) * chunks + k) * groups + g) * 2;
-      s += p[0];
-      q += p[1];
+  // finish the reduction over chunks: one warp per group (lanes stride the chunks, double accumulation, fixed order)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int g = warp; g < groups; g += nwarp) {
+      double s = 0.0, q = 0.0;
+      const int sub = pgroups / groups;      // partial groups per group (1 for the stand-alone statistics kernel)
+      for (int k = lane; k < chunks * sub; k += 32) {
+        const int ck = k / sub, sg = k - ck * sub;
+        const float2 p = __ldg(reinterpret_cast<const float2*>(partials + ((static_cast<size_t>(n) * chunks + ck) * pgroups + g * sub + sg) * 2));
+        s += p.x;
+        q += p.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) {
+        const double cnt = static_cast<double>(hw) * cpg;
+        const double mean = s / cnt;
+        const double var = fmax(q / cnt - mean * mean, 0.0);
+        gstat[2 * g] = static_cast<float>(mean);
+        gstat[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      }
     }
-    const double cnt = static_cast<double>(hw) * cpg;
-    const double mean = s / cnt;
-    const double var = fmax(q / cnt - mean * mean, 0.0);
-    gstat[2 * g] = static_cast<float>(mean);
-    gstat[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
   __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -504,23 +517,24 @@ int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const floa
   dim3 g2(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
     gn_partial_kernel<FMT><<<g1, 256, smem1, st>>>(x, x_plane, hw, c, groups, partials);
-    gn_apply_kernel<FMT><<<g2, 256, smem2, st>>>(x, x_plane, partials, kGnChunks, gamma, beta, groups, eps, skip,
+    gn_apply_kernel<FMT><<<g2, 256, smem2, st>>>(x, x_plane, partials, kGnChunks, groups, gamma, beta, groups, eps, skip,
                                                   skip_plane, tproj, tproj_stride, act, y, y_plane, hw, c);
   });
   return check_launch("groupnorm");
 }
 
-int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, int chunks, const float* gamma,
+int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, int chunks, int pgroups, const float* gamma,
                          const float* beta, int groups, float eps, const void* skip, size_t skip_plane,
                          const float* tproj, int tproj_stride, int act, void* y, size_t y_plane, int fmt,
                          int n, int hw, int c, void* stream) {
-  SBGM_REQUIRE(c % 8 == 0 && c <= 2048 && groups >= 1 && c % groups == 0 && chunks >= 1, "groupnorm_apply: bad c=%d groups=%d chunks=%d", c, groups, chunks);
+  SBGM_REQUIRE(c % 8 == 0 && c <= 2048 && groups >= 1 && c % groups == 0 && chunks >= 1 && pgroups >= groups && pgroups % groups == 0,
+               "groupnorm_apply: bad c=%d groups=%d pgroups=%d chunks=%d", c, groups, pgroups, chunks);
   const int vecs = c / 8;
   const size_t smem2 = (static_cast<size_t>(c) + groups) * 2 * sizeof(float);
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
   dim3 g2(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, (gn_apply_kernel<FMT><<<g2, 256, smem2, as_stream(stream)>>>(
-                             x, x_plane, partials, chunks, gamma, beta, groups, eps, skip, skip_plane, tproj,
+                             x, x_plane, partials, chunks, pgroups, gamma, beta, groups, eps, skip, skip_plane, tproj,
                              tproj_stride, act, y, y_plane, hw, c)));
   return check_launch("groupnorm_apply");
 }

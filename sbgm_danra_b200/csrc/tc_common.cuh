@@ -205,6 +205,33 @@ __device__ __forceinline__ void store_block64(void* out, size_t out_plane, int c
   }
 }
 
+// GroupNorm partial statistics of one 64-channel block, at 8-channel granularity, reduced over the warp's 32
+// rows: dst[sub][2] (sum, sum of squares) for sub = 0..7.  Values are taken as stored (bias added, bf16-rounded
+// in BF16 mode).  Must be called by the whole warp; rows with !valid contribute nothing.
+template <int FMT>
+__device__ __forceinline__ void gn_block64_stats(const uint32_t (&ra)[32], const uint32_t (&rb)[32], const float* bias,
+                                                 int co_base, bool valid, int lane, float* dst) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float s = 0.0f, q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = __uint_as_float(g < 4 ? ra[g * 8 + j] : rb[(g - 4) * 8 + j]);
+      if (bias) v += __ldg(bias + co_base + g * 8 + j);
+      if (FMT == SBGM_FMT_BF16) v = bf16_round(v);
+      if (!valid) v = 0.0f;
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) {
+      dst[2 * g] = s;
+      dst[2 * g + 1] = q;
+    }
+  }
+}
+
 // 64 accumulator columns (two 32-column TMEM loads) of one row.  ACT and PROJ are compile-time.
 template <int FMT, int ACT, bool PROJ>
 __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const uint32_t (&ra)[32], const uint32_t (&rb)[32],

@@ -140,6 +140,7 @@ class Kernels:
     def __init__(self, fmt: int, device) -> None:
         self.fmt, self.device = fmt, device
         self._gn_scratch: Optional[torch.Tensor] = None
+        self._splitk_ws: Optional[torch.Tensor] = None
 
     def _c64_ok(self, x: Act, cw: ConvW, stride: int, pad: int) -> bool:
         return (self.fmt != FMT_F32 and cw.cin == 64 and cw.cout == 64 and cw.kh == 3 and cw.kw == 3 and stride == 1
@@ -179,9 +180,22 @@ class Kernels:
             call("sbgm_conv3x3_c64", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias), res_ptr, res_plane,
                  tp_ptr, tp_stride, out_ptr, out_plane, self.fmt, x.n, x.h, x.w, act, *pargs, _ptr(part), 8, _stream())
         else:
+            ws_bytes = 0 if proj is not None else _lib.query("sbgm_conv2d_tc_workspace_bytes", self.fmt, x.n, x.h, x.w,
+                                                              cw.cin, cw.cout, cw.kh, cw.kw, stride, pad)
+            part = None
+            if gn_stats and residual is None and tproj is None and act == ACT_NONE and proj is None:
+                chunks = _lib.query("sbgm_conv2d_tc_gn_chunks", self.fmt, x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw, stride, pad)
+                if chunks > 0:
+                    part = torch.empty((x.n, chunks, cw.cout // 8, 2), dtype=torch.float32, device=self.device)
+                    stats = (part, chunks)
+            ws = None
+            if ws_bytes:
+                if self._splitk_ws is None or self._splitk_ws.numel() * 4 < ws_bytes:
+                    self._splitk_ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=self.device)
+                ws = self._splitk_ws.data_ptr()
             call("sbgm_conv2d_tc", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias), res_ptr, res_plane,
                  tp_ptr, tp_stride, out_ptr, out_plane, self.fmt, x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw,
-                 stride, pad, act, *pargs, _stream())
+                 stride, pad, act, *pargs, ws, ws_bytes, _ptr(part), _stream())
         if proj is not None:
             return pout
         return (out, stats) if gn_stats else out
@@ -191,10 +205,10 @@ class Kernels:
 
     def groupnorm(self, x: Act, gamma, beta, groups: int, act: int = ACT_NONE, skip: Optional[Act] = None,
                   tproj: Optional[torch.Tensor] = None, stats=None) -> Act:
-        if stats is not None and groups == 8 and x.c == 64:
+        if stats is not None and (x.c // 8) % groups == 0:
             part, chunks = stats
             out = x.like()
-            call("sbgm_groupnorm_apply", x.ptr, x.plane, part.data_ptr(), chunks, _ptr(gamma), _ptr(beta), groups, GN_EPS,
+            call("sbgm_groupnorm_apply", x.ptr, x.plane, part.data_ptr(), chunks, x.c // 8, _ptr(gamma), _ptr(beta), groups, GN_EPS,
                  None if skip is None else skip.ptr, 0 if skip is None else skip.plane,
                  _ptr(tproj), tproj.stride(0) if tproj is not None else 0, act, out.ptr, out.plane, self.fmt,
                  x.n, x.h * x.w, x.c, _stream())

@@ -344,17 +344,22 @@ def test_projection_epilogue_and_gather(E, prec, kernel):
 
 
 @pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
-def test_conv_fused_groupnorm_statistics(E, prec):
-    """GroupNorm from the statistics emitted by the 64->64 kernel's epilogue == GroupNorm of its output."""
+@pytest.mark.parametrize("shape", [(3, 32, 32, 64, 64, True), (40, 16, 16, 128, 128, True), (64, 8, 8, 256, 512, True),
+                                   (3, 16, 16, 128, 128, False),    # small grid -> split-K -> statistics not fused
+                                   (2, 12, 24, 64, 128, False)],    # tile spans several partial images
+                         ids=lambda t: "x".join(map(str, t)))
+def test_conv_fused_groupnorm_statistics(E, prec, shape):
+    """GroupNorm from the statistics emitted by a conv epilogue == GroupNorm of that conv's output
+    (persistent 64->64 kernel; generic kernel with one image per tile and with several images per tile)."""
     fmt = FMTS[prec]
-    n, h, w = 3, 32, 32
-    x = gen(n, 64, h, w, seed=1)
-    w1, b1 = gen(64, 64, 3, 3, seed=2, scale=0.05), gen(64, seed=3, scale=0.5)
-    gamma, beta = 1 + 0.2 * gen(64, seed=4), gen(64, seed=5, scale=0.2)
+    n, h, w, cin, cout, fused = shape
+    x = gen(n, cin, h, w, seed=1)
+    w1, b1 = gen(cout, cin, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * cin)), gen(cout, seed=3, scale=0.5)
+    gamma, beta = 1 + 0.2 * gen(cout, seed=4), gen(cout, seed=5, scale=0.2)
     kern = E.Kernels(fmt, torch.device("cuda"))
     cw = E._Packer({"w": w1, "b": b1}, fmt, torch.device("cuda")).conv("w", "b")
     y, stats = kern.conv(act_of(E, x, fmt), cw, pad=1, gn_stats=True)
-    assert stats is not None
+    assert (stats is not None) == fused
     got = kern.groupnorm(y, gamma.cuda(), beta.cuda(), 8, stats=stats).to_nchw().cpu()
     want = F.group_norm(y.to_nchw().cpu(), 8, gamma, beta, 1e-5)
     assert rel_l2(got, want) < {"bf16": 8e-3, "bf16x3": 3e-5}[prec]
