@@ -9,30 +9,33 @@
 namespace sbgm {
 
 // ---- stem ------------------------------------------------------------------------------------
-constexpr int kStemTile = 16;                    // 16x16 output pixels per block
-constexpr int kStemIn = 2 * kStemTile + 6;       // 38x38 input halo tile
+// Block = 256 threads = 16 rows x 16 column-pairs of output pixels (a 16 x 32 tile); every thread keeps
+// 2 pixels x 64 output channels in registers so each weight vector read from smem feeds two FMAs.
+constexpr int kStemTH = 16, kStemTW = 32;
+constexpr int kStemInH = 2 * kStemTH + 6;        // 38 input rows
+constexpr int kStemInW = 2 * kStemTW + 6;        // 70 input cols
 
 template <int FMT>
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ planes, int np, int cc, int c_begin, int c_end,
                  const float* __restrict__ wp, const float* __restrict__ addend, int na, const float* __restrict__ tproj,
                  int tproj_stride, void* __restrict__ out, size_t out_plane, int h, int w) {
-  __shared__ float s_in[kStemIn][kStemIn + 1];
+  __shared__ float s_in[kStemInH][kStemInW + 1];
   __shared__ __align__(16) float s_w[64][64];    // [tap][co]
   const int n = blockIdx.z, ho = h / 2, wo = w / 2;
-  const int ty = threadIdx.x / kStemTile, tx = threadIdx.x % kStemTile;
-  const int oy = blockIdx.y * kStemTile + ty, ox = blockIdx.x * kStemTile + tx;
-  const int iy0 = blockIdx.y * kStemTile * 2 - 3, ix0 = blockIdx.x * kStemTile * 2 - 3;
-  float acc[64];
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  const int oy = blockIdx.y * kStemTH + ty, ox = blockIdx.x * kStemTW + 2 * tx;
+  const int iy0 = blockIdx.y * kStemTH * 2 - 3, ix0 = blockIdx.x * kStemTW * 2 - 3;
+  float acc0[64], acc1[64];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < 64; ++i) { acc0[i] = 0.0f; acc1[i] = 0.0f; }
 
   for (int c = c_begin; c < c_end; ++c) {
     const float* src = (c == 0) ? x + static_cast<size_t>(n) * h * w
                                 : planes + (static_cast<size_t>(np == 1 ? 0 : n) * cc + (c - 1)) * h * w;
     __syncthreads();
-    for (int i = threadIdx.x; i < kStemIn * kStemIn; i += 256) {
-      const int yy = i / kStemIn, xx = i % kStemIn;
+    for (int i = threadIdx.x; i < kStemInH * kStemInW; i += 256) {
+      const int yy = i / kStemInW, xx = i % kStemInW;
       const int iy = iy0 + yy, ix = ix0 + xx;
       s_in[yy][xx] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(src + static_cast<size_t>(iy) * w + ix) : 0.0f;
     }
@@ -41,36 +44,41 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ planes, 
     __syncthreads();
 #pragma unroll 1
     for (int r = 0; r < 8; ++r) {
-#pragma unroll
+#pragma unroll 2
       for (int s = 0; s < 8; ++s) {
-        const float v = s_in[2 * ty + r][2 * tx + s];
+        const float v0 = s_in[2 * ty + r][4 * tx + s];
+        const float v1 = s_in[2 * ty + r][4 * tx + 2 + s];
         const float4* wrow = reinterpret_cast<const float4*>(&s_w[r * 8 + s][0]);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 wv = wrow[j];
-          acc[4 * j + 0] = fmaf(v, wv.x, acc[4 * j + 0]);
-          acc[4 * j + 1] = fmaf(v, wv.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(v, wv.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(v, wv.w, acc[4 * j + 3]);
+          acc0[4 * j + 0] = fmaf(v0, wv.x, acc0[4 * j + 0]); acc1[4 * j + 0] = fmaf(v1, wv.x, acc1[4 * j + 0]);
+          acc0[4 * j + 1] = fmaf(v0, wv.y, acc0[4 * j + 1]); acc1[4 * j + 1] = fmaf(v1, wv.y, acc1[4 * j + 1]);
+          acc0[4 * j + 2] = fmaf(v0, wv.z, acc0[4 * j + 2]); acc1[4 * j + 2] = fmaf(v1, wv.z, acc1[4 * j + 2]);
+          acc0[4 * j + 3] = fmaf(v0, wv.w, acc0[4 * j + 3]); acc1[4 * j + 3] = fmaf(v1, wv.w, acc1[4 * j + 3]);
         }
       }
     }
   }
-  if (oy >= ho || ox >= wo) return;
-  const size_t pix = (static_cast<size_t>(n) * ho + oy) * wo + ox;
-  const float* ad = addend ? addend + ((static_cast<size_t>(na == 1 ? 0 : n) * ho + oy) * wo + ox) * 64 : nullptr;
+  if (oy >= ho) return;
   const float* tp = tproj ? tproj + static_cast<size_t>(n) * tproj_stride : nullptr;
 #pragma unroll
-  for (int v8 = 0; v8 < 8; ++v8) {
-    float o[8];
+  for (int px = 0; px < 2; ++px) {
+    if (ox + px >= wo) continue;
+    const size_t pix = (static_cast<size_t>(n) * ho + oy) * wo + ox + px;
+    const float* ad = addend ? addend + ((static_cast<size_t>(na == 1 ? 0 : n) * ho + oy) * wo + ox + px) * 64 : nullptr;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = acc[v8 * 8 + j];
-      if (ad) t += __ldg(ad + v8 * 8 + j);
-      if (tp) t += __ldg(tp + v8 * 8 + j);
-      o[j] = t;
+    for (int v8 = 0; v8 < 8; ++v8) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = px == 0 ? acc0[v8 * 8 + j] : acc1[v8 * 8 + j];
+        if (ad) t += __ldg(ad + v8 * 8 + j);
+        if (tp) t += __ldg(tp + v8 * 8 + j);
+        o[j] = t;
+      }
+      Act<FMT>::store8(out, out_plane, pix * 64 + v8 * 8, o);
     }
-    Act<FMT>::store8(out, out_plane, pix * 64 + v8 * 8, o);
   }
 }
 
@@ -167,7 +175,7 @@ int sbgm_stem_conv(const float* x, const float* planes, int np, int cc, int c_be
   SBGM_REQUIRE(h % 2 == 0 && w % 2 == 0, "stem_conv: h=%d w=%d must be even", h, w);
   SBGM_REQUIRE(c_begin >= 0 && c_end <= cc + 1 && c_begin <= c_end, "stem_conv: bad channel range [%d,%d) of %d", c_begin, c_end, cc + 1);
   SBGM_REQUIRE(c_begin > 0 || x != nullptr || c_end == 0, "stem_conv: x is NULL but channel 0 requested");
-  dim3 grid(ceil_div(w / 2, kStemTile), ceil_div(h / 2, kStemTile), n);
+  dim3 grid(ceil_div(w / 2, kStemTW), ceil_div(h / 2, kStemTH), n);
   SBGM_DISPATCH_FMT(fmt, (stem_conv_kernel<FMT><<<grid, 256, 0, as_stream(stream)>>>(
                              x, planes, np, cc, c_begin, c_end, w_packed, addend, na, tproj, tproj_stride, out,
                              out_plane, h, w)));

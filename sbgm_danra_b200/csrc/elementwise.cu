@@ -315,33 +315,50 @@ __global__ void layernorm_kernel(const void* __restrict__ x, size_t x_plane, con
 }
 
 // ---- bilinear x2 upsample, align_corners=False ------------------------------------------------
+// One thread per (input pixel, 8-channel vector): the 3x3 clamped neighbourhood (9 vector loads) yields the
+// 2x2 output block.  ATen's rule src = max(0, (dst + 0.5) / 2 - 0.5) gives, for output row 2i: rows (i-1, i)
+// with weights (0.25, 0.75) [row 0: (0,0) -> in[0]]; for row 2i+1: rows (i, min(i+1, h-1)) with (0.75, 0.25).
 template <int FMT>
 __global__ void upsample2x_kernel(const void* __restrict__ x, size_t x_plane, void* __restrict__ y, size_t y_plane,
                                   int n, int h, int w, int c) {
-  const int vecs = c >> 3, ho = 2 * h, wo = 2 * w;
-  const size_t total = static_cast<size_t>(n) * ho * wo * vecs;
+  const int vecs = c >> 3;
+  const size_t total = static_cast<size_t>(n) * h * w * vecs;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int vec = static_cast<int>(i % vecs);
     size_t r = i / vecs;
-    const int ox = static_cast<int>(r % wo);
-    r /= wo;
-    const int oy = static_cast<int>(r % ho);
-    const int b = static_cast<int>(r / ho);
-    // ATen area_pixel_compute_source_index: src = max(0, (dst + 0.5) * 0.5 - 0.5)
-    const float sy = fmaxf(0.0f, (oy + 0.5f) * 0.5f - 0.5f), sx = fmaxf(0.0f, (ox + 0.5f) * 0.5f - 0.5f);
-    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float ly = sy - y0, lx = sx - x0, hy = 1.0f - ly, hx = 1.0f - lx;
-    float a[8], bq[8], cq[8], d[8], o[8];
+    const int ix = static_cast<int>(r % w);
+    r /= w;
+    const int iy = static_cast<int>(r % h);
+    const int b = static_cast<int>(r / h);
+    const int ys[3] = {max(iy - 1, 0), iy, min(iy + 1, h - 1)};
+    const int xs[3] = {max(ix - 1, 0), ix, min(ix + 1, w - 1)};
+    float v[3][3][8];
     const size_t base = static_cast<size_t>(b) * h * w;
-    Act<FMT>::load8(x, x_plane, ((base + static_cast<size_t>(y0) * w + x0) * c) + vec * 8, a);
-    Act<FMT>::load8(x, x_plane, ((base + static_cast<size_t>(y0) * w + x1) * c) + vec * 8, bq);
-    Act<FMT>::load8(x, x_plane, ((base + static_cast<size_t>(y1) * w + x0) * c) + vec * 8, cq);
-    Act<FMT>::load8(x, x_plane, ((base + static_cast<size_t>(y1) * w + x1) * c) + vec * 8, d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a[j] + lx * bq[j]) + ly * (hx * cq[j] + lx * d[j]);
-    Act<FMT>::store8(y, y_plane, i * 8, o);
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        Act<FMT>::load8(x, x_plane, (base + static_cast<size_t>(ys[a]) * w + xs[e]) * c + vec * 8, v[a][e]);
+    // ATen evaluates  h0 * (w0 * p00 + w1 * p01) + h1 * (w0 * p10 + w1 * p11)  with h1 = lambda, h0 = 1 - lambda
+    const float l0 = (iy == 0) ? 0.0f : 0.75f, m0 = (ix == 0) ? 0.0f : 0.75f;   // lambda of the even output row / col
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      constexpr int kDummy = 0; (void)kDummy;
+      const int ra = py, rb = py + 1;        // static tap rows in v[][] (the clamped loads make borders exact)
+      const float ly = (py == 0) ? l0 : 0.25f, hy = 1.0f - ly;
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int ca = px, cb = px + 1;
+        const float lx = (px == 0) ? m0 : 0.25f, hx = 1.0f - lx;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = hy * (hx * v[ra][ca][j] + lx * v[ra][cb][j]) + ly * (hx * v[rb][ca][j] + lx * v[rb][cb][j]);
+        const size_t opix = (static_cast<size_t>(b) * 2 * h + 2 * iy + py) * 2 * w + 2 * ix + px;
+        Act<FMT>::store8(y, y_plane, opix * c + vec * 8, o);
+      }
+    }
   }
 }
 
@@ -550,7 +567,7 @@ int sbgm_layernorm(const void* x, size_t x_plane, const float* gamma, const floa
 int sbgm_upsample2x(const void* x, size_t x_plane, void* y, size_t y_plane, int fmt, int n, int h, int w, int c,
                     void* stream) {
   SBGM_REQUIRE(c % 8 == 0, "upsample2x: c=%d must be a multiple of 8", c);
-  const size_t total = static_cast<size_t>(n) * 4 * h * w * (c / 8);
+  const size_t total = static_cast<size_t>(n) * h * w * (c / 8);
   SBGM_DISPATCH_FMT(fmt, (upsample2x_kernel<FMT><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
                              x, x_plane, y, y_plane, n, h, w, c)));
   return check_launch("upsample2x");

@@ -344,7 +344,7 @@ def test_projection_epilogue_and_gather(E, prec, kernel):
 
 
 @pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
-@pytest.mark.parametrize("shape", [(3, 32, 32, 64, 64, True), (40, 16, 16, 128, 128, True), (64, 8, 8, 256, 512, True),
+@pytest.mark.parametrize("shape", [(3, 32, 32, 64, 64, True), (40, 16, 16, 128, 128, True), (160, 8, 8, 256, 512, True),
                                    (3, 16, 16, 128, 128, False),    # small grid -> split-K -> statistics not fused
                                    (2, 12, 24, 64, 128, False)],    # tile spans several partial images
                          ids=lambda t: "x".join(map(str, t)))
