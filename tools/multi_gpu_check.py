@@ -56,11 +56,17 @@ def main():
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
-    dist.destroy_process_group()
-    if int(flag.item()) != 1:
-        sys.exit(1)
-    if rank == 0:
-        print("multi-gpu check OK")
+    good = int(flag.item()) == 1
+    if rank == 0 and good:
+        print("multi-gpu check OK", flush=True)
+    # the cached sampler plans hold CUDA graphs with captured NCCL all-gathers: drop them before the
+    # communicator goes away, and skip interpreter teardown (destroying a communicator that graphs still
+    # reference can block)
+    ss.clear_sampler_cache()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0 if good else 1)
 
 
 if __name__ == "__main__":
