@@ -220,3 +220,28 @@ def test_dsm_loss_forward_matches_reference_golden(golden):
                        lsm_cond=_cuda(b.lsm_cond), topo_cond=_cuda(b.topo_cond), sdf_cond=_cuda(b.sdf_cond))
     want = float(golden["dsm_eval/loss"])
     assert abs(loss.item() - want) / want < 1e-3
+
+
+def test_score_256x256_matches_oracle():
+    """C5 shape (256x256 crop, attention over 1024 tokens): one member against the CPU oracle."""
+    from oracle import score_ref
+    from oracle.synth import synth_batch
+    net, cfg, sd = _model(dict(n_lr=1), "bf16x3")
+    b = synth_batch(batch=1, size=256, n_lr=1)
+    with torch.no_grad():
+        want = score_ref.score_forward(sd, cfg, *b.model_args())
+    got = net(*[_cuda(v) for v in b.model_args()]).cpu()
+    assert rel_l2(got, want) < 1e-3
+
+
+def test_non_power_of_two_size_matches_oracle():
+    """96x96 input (feature maps 48/24/12/6/3): tiles with padding rows, odd attention lengths."""
+    from oracle import score_ref
+    from oracle.synth import synth_batch
+    for precision, tol in (("fp32", 1e-4), ("bf16x3", 1e-3)):
+        net, cfg, sd = _model(dict(n_lr=1), precision)
+        b = synth_batch(batch=2, size=96, n_lr=1)
+        with torch.no_grad():
+            want = score_ref.score_forward(sd, cfg, *b.model_args())
+        got = net(*[_cuda(v) for v in b.model_args()]).cpu()
+        assert rel_l2(got, want) < tol, precision
