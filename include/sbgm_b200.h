@@ -226,6 +226,107 @@ size_t sbgm_dsm_scratch_floats(size_t count);
 int sbgm_dsm_loss(const float* score, const float* std, const float* z, const float* sdf, int n, int per_member,
                   float* partials, float* loss_out, void* stream);
 
+/* ==== training (DSM step): forward pieces with batch statistics + every backward =================
+ * The reference obtains all of these from torch autograd (loss.backward(), sbgm/training.py:323-410)
+ * over the modules of sbgm/score_unet.py; cuDNN/ATen supply the arithmetic.  Gradients of activations
+ * use the same NHWC storage formats as the activations; parameter gradients are fp32 in torch's
+ * parameter layouts (conv: OIHW).  All reductions are two-stage with a fixed order (deterministic). */
+
+/* per (n, chunk of 32) partial (sum, sumsq) over `groups` channel groups: partials[n][32][groups][2].
+ * groups == c gives the per-channel partials of train-mode BatchNorm (torchvision resnet.py:89-103). */
+int sbgm_norm_partials(const void* x, size_t x_plane, int fmt, int n, int hw, int c, int groups, float* partials, void* stream);
+/* GroupNorm / InstanceNorm: stats[n][groups][2] = (mean, rstd) from partials[n][chunks][pgroups][2]
+ * (the stand-alone partials above or the fused statistics of the convolution kernels). */
+int sbgm_gn_stats_finalize(const float* partials, int chunks, int pgroups, int groups, int n, int hw, int c, float eps,
+                           float* stats, void* stream);
+/* BatchNorm2d.forward in training mode: stats[c][2] = (batch mean, rstd of the biased variance) and the
+ * running_mean / running_var update (momentum, unbiased variance); either running pointer may be NULL. */
+int sbgm_bn_stats_finalize(const float* partials, int chunks, int n, int hw, int c, float eps, float momentum, float* stats,
+                           float* running_mean, float* running_var, void* stream);
+/* y = act((x - mean) * rstd * gamma + beta + add + [tproj if tproj_pre_act]) + [tproj if !tproj_pre_act]
+ * stats index: per_sample_stats == 1 ? [n][groups] : [groups] (BatchNorm: groups = c, per_sample_stats = 0;
+ * per_sample_stats = 2: per-channel CONSTANT statistics, i.e. eval-mode BatchNorm -- its backward has no
+ * mean / variance terms).
+ * DecoderBlock.forward score_unet.py:559-627 (tproj before the activation); BasicBlock + Encoder.forward
+ * :314-357 (ReLU, then the time projection). */
+int sbgm_norm_apply(const void* x, size_t x_plane, const float* stats, int per_sample_stats, int groups, const float* gamma,
+                    const float* beta, const void* add, size_t add_plane, const float* tproj, int tproj_stride,
+                    int tproj_pre_act, int act, void* y, size_t y_plane, int fmt, int n, int hw, int c, void* stream);
+/* backward of sbgm_norm_apply: dx, dadd (= gradient w.r.t. the pre-activation; NULL to skip), dgamma/dbeta[c]
+ * (NULL for non-affine norms), dtproj[n][dtproj_stride] (NULL to skip).  `scratch`:
+ * sbgm_norm_backward_scratch_floats(n, c) floats. */
+size_t sbgm_norm_backward_scratch_floats(int n, int c);
+int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, const float* stats, int per_sample_stats,
+                       int groups, const float* gamma, const float* beta, const void* add, size_t add_plane,
+                       const float* tproj, int tproj_stride, int tproj_pre_act, int act, void* dx, size_t dx_plane,
+                       void* dadd, size_t dadd_plane, float* dgamma, float* dbeta, float* dtproj, int dtproj_stride,
+                       int fmt, int n, int hw, int c, float* scratch, void* stream);
+/* nn.LayerNorm backward (ImageSelfAttention.ln1 / ln2, score_unet.py:136-148) */
+size_t sbgm_layernorm_backward_scratch_floats(int c);
+int sbgm_layernorm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, const float* gamma, float eps,
+                            void* dx, size_t dx_plane, float* dgamma, float* dbeta, int fmt, int rows, int c, float* scratch,
+                            void* stream);
+/* stand-alone activation (the feed-forward GELU keeps its pre-activation for the backward) */
+int sbgm_act_forward(const void* x, size_t x_plane, void* y, size_t y_plane, int fmt, size_t count, int act, void* stream);
+int sbgm_act_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, void* dx, size_t dx_plane, int fmt,
+                      size_t count, int act, void* stream);
+/* dst += src (gradient accumulation where a tensor has several consumers) */
+int sbgm_add_inplace(void* dst, size_t dst_plane, const void* src, size_t src_plane, int fmt, size_t count, void* stream);
+/* out_per_sample[n][out_stride] (nullable) = sum over the hw pixels; out_total[c] (nullable) = sum over everything
+ * (bias gradients; time-projection gradients of the encoder stages) */
+size_t sbgm_channel_sums_scratch_floats(int n, int c);
+int sbgm_channel_sums(const void* x, size_t x_plane, int fmt, int n, int hw, int c, float* out_per_sample, int out_stride,
+                      float* out_total, float* scratch, void* stream);
+/* adjoint of sbgm_upsample2x: dy [n, 2h, 2w, c] -> dx [n, h, w, c] */
+int sbgm_upsample2x_backward(const void* dy, size_t dy_plane, void* dx, size_t dx_plane, int fmt, int n, int h, int w, int c,
+                             void* stream);
+/* attention core backward: dqkv [b*s][3c] from qkv and dout [b*s][c]; scratch = ..._scratch_floats floats */
+size_t sbgm_attention_backward_scratch_floats(int b, int s, int c, int heads);
+int sbgm_attention_backward(const void* qkv, size_t qkv_plane, const void* dout, size_t dout_plane, void* dqkv, size_t dqkv_plane,
+                            int fmt, int b, int s, int c, int heads, float* scratch, void* stream);
+/* backward of sbgm_time_embed_project (one row per batch member): d_proj_w[c_total][te], d_proj_b[c_total],
+ * d_label_emb[n_classes][te] (NULL when the model has no labels) */
+size_t sbgm_time_embed_backward_scratch_floats(int n_sets, int te, int rows);
+int sbgm_time_embed_backward(const float* dout, const float* t, const int64_t* y, const float* fourier_w, int n_sets, int te,
+                             const float* label_emb, int n_classes, const float* proj_w, const int32_t* proj_set, int c_total,
+                             int rows, float* d_proj_w, float* d_proj_b, float* d_label_emb, float* scratch, void* stream);
+
+/* ---- convolution gradients --------------------------------------------------------------------
+ * data gradient, CUDA cores: weight as fp32 [tap][cout][cin]; `accumulate` adds into dx */
+int sbgm_conv2d_dgrad_simt(const void* dy, size_t dy_plane, const float* weight_tap_co_ci, void* dx, size_t dx_plane, int accumulate,
+                           int fmt, int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, void* stream);
+/* data gradient, tensor cores: the forward implicit-GEMM kernel run over dy with flipped / parity-sliced weights;
+ * separate paddings, explicit logical output size and scattered store out[n][oy*out_step+out_oy][ox*out_step+out_ox]
+ * (`residual`, read at the same positions, accumulates an existing gradient). */
+int sbgm_conv2d_tc_ex(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                      const void* residual, size_t res_plane, void* out, size_t out_plane, int fmt, int n, int h,
+                      int w, int cin, int cout, int kh, int kw, int stride, int pad_h, int pad_w, int ho, int wo,
+                      int out_h, int out_w, int out_step, int out_oy, int out_ox, int act, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* weight gradient -> dweight_oihw[cout][cin][kh][kw] fp32; x is the layer input [n,h,w,cin], dy [n,ho,wo,cout] */
+size_t sbgm_conv2d_wgrad_simt_workspace_floats(int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad);
+int sbgm_conv2d_wgrad_simt(const void* x, size_t x_plane, const void* dy, size_t dy_plane, float* dweight_oihw, int fmt, int n, int h,
+                           int w, int cin, int cout, int kh, int kw, int stride, int pad, float* workspace, void* stream);
+/* tensor cores (tcgen05, MN-major operands straight from the NHWC tensors; cin, cout multiples of 64) */
+size_t sbgm_conv2d_wgrad_tc_workspace_floats(int fmt, int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad);
+int sbgm_conv2d_wgrad_tc(const void* x, size_t x_plane, const void* dy, size_t dy_plane, float* dweight_oihw, int fmt,
+                         int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, float* workspace, void* stream);
+/* sum workspace[splits][cout][taps*cin] over the splits in a fixed order into OIHW */
+int sbgm_wgrad_reduce(const float* workspace, int splits, int cout, int taps, int cin, float* dweight_oihw, void* stream);
+/* Encoder.conv1 (8x8 s2 p3 over NCHW fp32 x || planes, score_unet.py:310): weight gradient from df [n,h/2,w/2,64] */
+size_t sbgm_stem_wgrad_workspace_floats(int cin);
+int sbgm_stem_wgrad(const float* x, const float* planes, int np, int cc, const void* df, size_t df_plane, int fmt, float* dweight_oihw,
+                    int n, int h, int w, float* workspace, void* stream);
+/* Decoder.final_layer.conv (cin -> 1, 3x3) + the 1/std scaling, backward: g = dscore * inv_std[n];
+ * da [n,h,w,cin] (fmt), dweight_oihw[1][cin][3][3], dbias[1]; weight_tap_ci = fp32 [9][cin] */
+size_t sbgm_final_conv_backward_scratch_floats(int cin);
+int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const void* a, size_t a_plane, int fmt,
+                             const float* weight_tap_ci, void* da, size_t da_plane, float* dweight_oihw, float* dbias, int n, int h,
+                             int w, int cin, float* scratch, void* stream);
+/* d loss / d score of sbgm_dsm_loss, times *grad_loss (device scalar; NULL = 1) */
+int sbgm_dsm_loss_backward(const float* score, const float* std, const float* z, const float* sdf, const float* grad_loss, int n,
+                           int per_member, float* dscore, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

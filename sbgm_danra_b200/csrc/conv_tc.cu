@@ -24,7 +24,8 @@ namespace sbgm {
 
 struct ConvTcParams {
   int n, ho, wo;
-  int kh, kw, stride, pad;
+  int kh, kw, stride, pad_h, pad_w;
+  int out_h, out_w, out_step, out_oy, out_ox;   // scatter addressing of the output tensor (dgrad of strided convs)
   int w_tile, h_tile, n_tile;
   int tiles_w, tiles_h;
   int cin_blocks;
@@ -101,8 +102,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t b_dst = a_dst + kSplit * Cfg::kABytes;
 #pragma unroll
         for (int pl = 0; pl < kSplit; ++pl) {
-          tma_load_5d(a_dst + pl * Cfg::kABytes, &tmap_a, full_bar(stage), cb * 64, wo0 * p.stride + s - p.pad,
-                      ho0 * p.stride + r - p.pad, n0, pl);
+          tma_load_5d(a_dst + pl * Cfg::kABytes, &tmap_a, full_bar(stage), cb * 64, wo0 * p.stride + s - p.pad_w,
+                      ho0 * p.stride + r - p.pad_h, n0, pl);
           tma_load_3d(b_dst + pl * Cfg::kBBytes, &tmap_b, full_bar(stage), kb * 64, co0, pl);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -141,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int w_l = row % p.w_tile, h_l = (row / p.w_tile) % p.h_tile, n_l = row / (p.w_tile * p.h_tile);
     const int n = n0 + n_l, oy = ho0 + h_l, ox = wo0 + w_l;
     const bool valid = (n < p.n) && (oy < p.ho) && (ox < p.wo);
-    const size_t pix = (static_cast<size_t>(n) * p.ho + oy) * p.wo + ox;
+    const size_t pix = (static_cast<size_t>(n) * p.out_h + oy * p.out_step + p.out_oy) * p.out_w + ox * p.out_step + p.out_ox;
     float proj_acc[kProjMax];
 #pragma unroll
     for (int q = 0; q < kProjMax; ++q) proj_acc[q] = 0.0f;
@@ -284,7 +285,7 @@ static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 static int pow2_divisor(int v) { return v & (-v); }
 
 // Pick (w_tile, h_tile, n_tile), product 128, powers of two, covering the output with the least padding.
-static void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
+void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
   if (ho == 1 && n == 1) {  // token matrix [M][C] (Linear layers): plain 128-row tiles, tail masked
     *wt = 128; *ht = 1; *nt = 1;
     return;
@@ -354,11 +355,12 @@ static int pick_splits(int ctas, int total_kb) {
 }
 
 static void conv_tc_geometry(int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, int planes,
-                             ConvTcParams* p, int* block_n, int* m_tiles) {
+                             ConvTcParams* p, int* block_n, int* m_tiles, int ho_override = 0, int wo_override = 0) {
   p->n = n;
-  p->ho = (h + 2 * pad - kh) / stride + 1;
-  p->wo = (w + 2 * pad - kw) / stride + 1;
-  p->kh = kh; p->kw = kw; p->stride = stride; p->pad = pad;
+  p->ho = ho_override > 0 ? ho_override : (h + 2 * pad - kh) / stride + 1;
+  p->wo = wo_override > 0 ? wo_override : (w + 2 * pad - kw) / stride + 1;
+  p->kh = kh; p->kw = kw; p->stride = stride; p->pad_h = pad; p->pad_w = pad;
+  p->out_h = p->ho; p->out_w = p->wo; p->out_step = 1; p->out_oy = 0; p->out_ox = 0;
   pick_tile(n, p->ho, p->wo, &p->w_tile, &p->h_tile, &p->n_tile);
   p->tiles_w = ceil_div(p->wo, p->w_tile);
   p->tiles_h = ceil_div(p->ho, p->h_tile);
@@ -396,27 +398,41 @@ extern "C" size_t sbgm_conv2d_tc_workspace_bytes(int fmt, int n, int h, int w, i
   return static_cast<size_t>(p.splits) * n * p.ho * p.wo * cout * sizeof(float);
 }
 
-extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
-                              const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
-                              void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
-                              int kh, int kw, int stride, int pad, int act, const float* proj_w, int n_proj,
-                              float* proj_out, void* workspace, size_t workspace_bytes, float* gn_partials,
-                              void* stream) {
+struct ConvTcEx {      // optional generalisation used by the data-gradient path (all zero = plain convolution)
+  int pad_h, pad_w, ho, wo, out_h, out_w, out_step, out_oy, out_ox;
+  bool on;
+};
+
+static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                          const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
+                          void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
+                          int kh, int kw, int stride, int pad, int act, const float* proj_w, int n_proj,
+                          float* proj_out, void* workspace, size_t workspace_bytes, float* gn_partials,
+                          const ConvTcEx& ex, void* stream) {
   SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv2d_tc: format %d is not a tensor-core format", fmt);
   SBGM_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv2d_tc: cin=%d and cout=%d must be multiples of 64", cin, cout);
   SBGM_REQUIRE(stride >= 1 && stride <= 8, "conv2d_tc: stride %d unsupported", stride);
   SBGM_REQUIRE(proj_w == nullptr || (cout == 64 && n_proj == kProjN && proj_out != nullptr && residual == nullptr &&
                                      tproj == nullptr && act == SBGM_ACT_NONE),
                "conv2d_tc: the projection epilogue needs cout == 64, n_proj == %d and a bias-only epilogue", kProjN);
-  const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
+  const int ho = ex.on ? ex.ho : (h + 2 * pad - kh) / stride + 1, wo = ex.on ? ex.wo : (w + 2 * pad - kw) / stride + 1;
   SBGM_REQUIRE(ho > 0 && wo > 0, "conv2d_tc: empty output");
   const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;
 
   ConvTcParams p;
   int block_n = 0, m_tiles = 0;
-  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, planes, &p, &block_n, &m_tiles);
+  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, planes, &p, &block_n, &m_tiles, ex.on ? ex.ho : 0, ex.on ? ex.wo : 0);
+  bool scatter = false;
+  if (ex.on) {
+    p.pad_h = ex.pad_h; p.pad_w = ex.pad_w;
+    p.out_h = ex.out_h; p.out_w = ex.out_w; p.out_step = ex.out_step; p.out_oy = ex.out_oy; p.out_ox = ex.out_ox;
+    scatter = !(ex.out_step == 1 && ex.out_oy == 0 && ex.out_ox == 0 && ex.out_h == ho && ex.out_w == wo);
+    SBGM_REQUIRE((ho - 1) * ex.out_step + ex.out_oy < ex.out_h && (wo - 1) * ex.out_step + ex.out_ox < ex.out_w,
+                 "conv2d_tc: scattered output exceeds the output tensor");
+    SBGM_REQUIRE(proj_w == nullptr && gn_partials == nullptr, "conv2d_tc: extended addressing excludes the projection / GroupNorm epilogues");
+  }
   const size_t ws_need = static_cast<size_t>(p.splits) * n * ho * wo * cout * sizeof(float);
-  if (p.splits > 1 && (proj_w != nullptr || workspace == nullptr || workspace_bytes < ws_need)) p.splits = 1;
+  if (p.splits > 1 && (scatter || proj_w != nullptr || workspace == nullptr || workspace_bytes < ws_need)) p.splits = 1;
   p.ws = static_cast<float*>(workspace);
   p.gn_partials = gn_partials;
   p.gn_chunks = gn_chunks_for(p);
@@ -440,4 +456,28 @@ extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weigh
   }
   if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16X2, 128, 3>(ta, tb, p, m_tiles, st);
   return launch_conv_tc<SBGM_FMT_BF16X2, 64, 2>(ta, tb, p, m_tiles, st);
+}
+
+extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                              const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
+                              void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
+                              int kh, int kw, int stride, int pad, int act, const float* proj_w, int n_proj,
+                              float* proj_out, void* workspace, size_t workspace_bytes, float* gn_partials,
+                              void* stream) {
+  ConvTcEx ex = {};
+  return conv2d_tc_impl(in, in_plane, weight, w_plane, bias, residual, res_plane, tproj, tproj_stride, out, out_plane, fmt, n, h, w,
+                        cin, cout, kh, kw, stride, pad, act, proj_w, n_proj, proj_out, workspace, workspace_bytes, gn_partials, ex, stream);
+}
+
+// Generalised form used by the data gradients: separate vertical / horizontal padding, an explicit logical output
+// size (ho, wo) and a scattered store  out[n][oy * out_step + out_oy][ox * out_step + out_ox]  into an
+// [n][out_h][out_w][cout] tensor (`residual`, if given, is read at the same scattered positions).
+extern "C" int sbgm_conv2d_tc_ex(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                                 const void* residual, size_t res_plane, void* out, size_t out_plane, int fmt, int n, int h,
+                                 int w, int cin, int cout, int kh, int kw, int stride, int pad_h, int pad_w, int ho, int wo,
+                                 int out_h, int out_w, int out_step, int out_oy, int out_ox, int act, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  ConvTcEx ex = {pad_h, pad_w, ho, wo, out_h, out_w, out_step, out_oy, out_ox, true};
+  return conv2d_tc_impl(in, in_plane, weight, w_plane, bias, residual, res_plane, nullptr, 0, out, out_plane, fmt, n, h, w, cin, cout,
+                        kh, kw, stride, pad_h, act, nullptr, 0, nullptr, workspace, workspace_bytes, nullptr, ex, stream);
 }

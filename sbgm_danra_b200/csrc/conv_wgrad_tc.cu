@@ -1,0 +1,246 @@
+// conv_wgrad_tc.cu -- convolution / linear weight gradients on the 5th-generation tensor cores.
+//
+//   dW^T[(tap, ci)][co]  =  sum over output pixels p of  x[p * stride + tap - pad][ci] * dy[p][co]
+//
+// is a GEMM whose reduction dimension is the PIXEL axis.  With NHWC activations both operands arrive with the
+// reduction index as the row and the channel as the contiguous 128-byte swizzle row -- exactly what the forward's
+// TMA boxes produce -- so the same shared-memory tiles are consumed as MN-major UMMA operands (instruction
+// descriptor a_major = b_major = 1; canonical layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in bf16 elements):
+//   A (M = 128) = two (tap, 64-channel chunk) boxes of x, 16 KB apart (LBO);  rows = 128 pixels
+//   B (N = BN)  = BN/64 boxes of dy, 16 KB apart;  in split-bf16 mode the lo plane follows the hi plane so one
+//                 N = 2 BN instruction yields x_hi*dy_hi | x_hi*dy_lo and a second adds x_lo*dy_hi.
+// One instruction consumes 16 pixels (two 8-row swizzle atoms, SBO = 1024 B): 8 instructions per 128-pixel tile.
+// The pixel axis is split over gridDim.z; every CTA keeps its [128 x BN] fp32 accumulator in TMEM across its whole
+// pixel range and writes one partial [co][K] slab; sbgm_wgrad_reduce sums the slabs in a fixed order
+// (deterministic) into torch's OIHW layout.
+// Warp roles as in conv_tc.cu: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..5 = epilogue.
+#include "tc_common.cuh"
+
+namespace sbgm {
+
+struct WgradParams {
+  int n, ho, wo;
+  int kh, kw, stride, pad;
+  int w_tile, h_tile, n_tile, tiles_w, tiles_h, total_tiles;
+  int cin_blocks, units, tiles_per_split, cout;
+  size_t K;
+  float* ws;     // [splits][cout][K]
+};
+
+constexpr uint32_t kBoxBytes = 128 * 128;   // 128 pixels x 64 bf16
+
+template <int kSplit, int BN, int kStages>
+struct WgradCfg {
+  static constexpr uint32_t kABytes = kSplit * 2 * kBoxBytes;
+  static constexpr uint32_t kBBytes = kSplit * (BN / 64) * kBoxBytes;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;
+};
+
+// MN-major operands: descriptor low word carries LBO = 16 KB (distance between 64-channel blocks)
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | ((kBoxBytes >> 4) << 16); }
+__device__ __forceinline__ constexpr uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
+
+template <int FMT, int BN, int kStages>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const WgradParams p) {
+  constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
+  using Cfg = WgradCfg<kSplit, BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kSplit * BN);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int u0 = blockIdx.x * 2;
+  const bool second = (u0 + 1) < p.units;
+  const int u1 = second ? u0 + 1 : u0;
+  const int co0 = blockIdx.y * BN;
+  const int tile_begin = blockIdx.z * p.tiles_per_split;
+  const int tile_end = min(p.total_tiles, tile_begin + p.tiles_per_split);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int us[2] = {u0, u1};
+      int r_[2], s_[2], cb_[2];
+      for (int i = 0; i < 2; ++i) {
+        const int tap = us[i] / p.cin_blocks;
+        cb_[i] = us[i] - tap * p.cin_blocks;
+        r_[i] = tap / p.kw;
+        s_[i] = tap - r_[i] * p.kw;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
+        const int wo0 = tw * p.w_tile, ho0 = th * p.h_tile, n0 = tn * p.n_tile;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+        const uint32_t b_dst = a_dst + Cfg::kABytes;
+#pragma unroll
+        for (int pl = 0; pl < kSplit; ++pl) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            tma_load_5d(a_dst + (pl * 2 + i) * kBoxBytes, &tmap_x, full_bar(stage), cb_[i] * 64, wo0 * p.stride + s_[i] - p.pad,
+                        ho0 * p.stride + r_[i] - p.pad, n0, pl);
+#pragma unroll
+          for (int ch = 0; ch < BN / 64; ++ch)
+            tma_load_5d(b_dst + (pl * (BN / 64) + ch) * kBoxBytes, &tmap_dy, full_bar(stage), co0 + ch * 64, wo0, ho0, n0, pl);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_mn(BN), idesc2 = make_idesc_mn(kSplit * BN);
+    const uint32_t base_lo = desc_lo_mn(smem_base);
+    uint32_t stage = 0, phase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(full_bar(stage), phase);
+      tcgen05_fence_after();
+      const uint32_t a0 = base_lo + stage * (Cfg::kStageBytes >> 4);
+      const uint32_t b0 = a0 + (Cfg::kABytes >> 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {        // 8 x 16 pixels; 16 rows x 128 B = 2048 B per step
+        const uint32_t acc = (tile != tile_begin || j != 0) ? 1u : 0u;
+        if (kSplit == 2) {
+          umma_bf16_elect(tmem_base, a0 + j * 128, b0 + j * 128, idesc2, acc);
+          umma_bf16_elect(tmem_base, a0 + ((2 * kBoxBytes) >> 4) + j * 128, b0 + j * 128, idesc, 1u);
+        } else {
+          umma_bf16_elect(tmem_base, a0 + j * 128, b0 + j * 128, idesc, acc);
+        }
+      }
+      umma_commit_elect(empty_bar(stage));
+      if (tile == tile_end - 1) umma_commit_elect(tmem_full_bar);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int unit = (row < 64) ? u0 : u1;
+    const bool valid = (row < 64) || second;
+    const size_t kcol = static_cast<size_t>(unit) * 64 + (row & 63);
+    float* dst = p.ws + (static_cast<size_t>(blockIdx.z) * p.cout + co0) * p.K + kcol;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
+      uint32_t r[32];
+      tmem_ld32(taddr, r);
+      if (kSplit == 2) {
+        uint32_t t[32];
+        tmem_ld32(taddr + BN, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(c0 + j) * p.K] = __uint_as_float(r[j]);   // lanes <-> consecutive k: coalesced
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kSplit * BN);
+}
+
+static void wgrad_tc_plan(int n, int ho, int wo, int cin, int cout, int kh, int kw, int fmt, WgradParams* p, int* bn, int* splits) {
+  p->n = n; p->ho = ho; p->wo = wo; p->kh = kh; p->kw = kw;
+  pick_tile(n, ho, wo, &p->w_tile, &p->h_tile, &p->n_tile);
+  p->tiles_w = ceil_div(wo, p->w_tile);
+  p->tiles_h = ceil_div(ho, p->h_tile);
+  p->total_tiles = p->tiles_w * p->tiles_h * ceil_div(n, p->n_tile);
+  p->cin_blocks = cin / 64;
+  p->units = kh * kw * p->cin_blocks;
+  p->cout = cout;
+  p->K = static_cast<size_t>(kh) * kw * cin;
+  *bn = (fmt == SBGM_FMT_BF16 && cout % 128 == 0) ? 128 : 64;
+  const int base = ((p->units + 1) / 2) * (cout / *bn);
+  int s = (148 * 3 + base - 1) / base;
+  if (s > p->total_tiles) s = p->total_tiles;
+  if (s < 1) s = 1;
+  p->tiles_per_split = (p->total_tiles + s - 1) / s;
+  *splits = (p->total_tiles + p->tiles_per_split - 1) / p->tiles_per_split;
+}
+
+template <int FMT, int BN, int kStages>
+static int launch_wgrad_tc(const CUtensorMap& tx, const CUtensorMap& td, const WgradParams& p, int splits, cudaStream_t st) {
+  constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
+  using Cfg = WgradCfg<kSplit, BN, kStages>;
+  auto kern = conv_wgrad_tc_kernel<FMT, BN, kStages>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
+      set_error("conv2d_wgrad_tc: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
+      return 1;
+    }
+    configured = true;
+  }
+  dim3 grid((p.units + 1) / 2, p.cout / BN, splits);
+  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tx, td, p);
+  return check_launch("conv2d_wgrad_tc");
+}
+
+}  // namespace sbgm
+
+using namespace sbgm;
+
+extern "C" size_t sbgm_conv2d_wgrad_tc_workspace_floats(int fmt, int n, int h, int w, int cin, int cout, int kh, int kw, int stride,
+                                                        int pad) {
+  if (cin % 64 != 0 || cout % 64 != 0 || stride < 1) return 0;
+  const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
+  if (ho <= 0 || wo <= 0) return 0;
+  WgradParams p;
+  int bn = 0, splits = 0;
+  wgrad_tc_plan(n, ho, wo, cin, cout, kh, kw, fmt, &p, &bn, &splits);
+  return static_cast<size_t>(splits) * cout * p.K;
+}
+
+extern "C" int sbgm_conv2d_wgrad_tc(const void* x, size_t x_plane, const void* dy, size_t dy_plane, float* dweight_oihw, int fmt,
+                                    int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, float* workspace,
+                                    void* stream) {
+  SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv2d_wgrad_tc: format %d is not a tensor-core format", fmt);
+  SBGM_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv2d_wgrad_tc: cin=%d and cout=%d must be multiples of 64", cin, cout);
+  SBGM_REQUIRE(stride >= 1 && stride <= 8, "conv2d_wgrad_tc: stride %d unsupported", stride);
+  const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
+  SBGM_REQUIRE(ho > 0 && wo > 0, "conv2d_wgrad_tc: empty output");
+  const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;
+  WgradParams p;
+  int bn = 0, splits = 0;
+  wgrad_tc_plan(n, ho, wo, cin, cout, kh, kw, fmt, &p, &bn, &splits);
+  p.stride = stride; p.pad = pad; p.ws = workspace;
+  SBGM_REQUIRE(p.w_tile * stride <= 256 && p.h_tile * stride <= 256, "conv2d_wgrad_tc: TMA box too large for stride %d", stride);
+  CUtensorMap tx, td;
+  if (encode_act_map(&tx, x, planes, x_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
+  if (encode_act_map(&td, dy, planes, dy_plane, n, ho, wo, cout, p.w_tile, p.h_tile, p.n_tile, 1)) return 1;
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (fmt == SBGM_FMT_BF16) rc = (bn == 128) ? launch_wgrad_tc<SBGM_FMT_BF16, 128, 3>(tx, td, p, splits, st)
+                                             : launch_wgrad_tc<SBGM_FMT_BF16, 64, 4>(tx, td, p, splits, st);
+  else rc = launch_wgrad_tc<SBGM_FMT_BF16X2, 64, 2>(tx, td, p, splits, st);
+  if (rc) return rc;
+  return sbgm_wgrad_reduce(workspace, splits, cout, kh * kw, cin, dweight_oihw, stream);
+}

@@ -540,6 +540,19 @@ int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const floa
   return check_launch("groupnorm");
 }
 
+// Stage 1 alone: per (n, chunk) partial sums [n][32][groups][2]; groups == c gives the per-channel partials
+// of train-mode BatchNorm (finished by sbgm_bn_stats_finalize / sbgm_gn_stats_finalize, backward.cu).
+int sbgm_norm_partials(const void* x, size_t x_plane, int fmt, int n, int hw, int c, int groups, float* partials, void* stream) {
+  SBGM_REQUIRE(c % 8 == 0 && c <= 2048 && groups >= 1 && c % groups == 0, "norm_partials: bad c=%d groups=%d", c, groups);
+  const int vecs = c / 8;
+  SBGM_REQUIRE(vecs <= 256, "norm_partials: c too large");
+  const int lanes = 256 / vecs;
+  const size_t smem1 = (static_cast<size_t>(lanes) + 1) * c * 2 * sizeof(float);
+  dim3 g1(kGnChunks, n);
+  SBGM_DISPATCH_FMT(fmt, (gn_partial_kernel<FMT><<<g1, 256, smem1, as_stream(stream)>>>(x, x_plane, hw, c, groups, partials)));
+  return check_launch("norm_partials");
+}
+
 int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, int chunks, int pgroups, const float* gamma,
                          const float* beta, int groups, float eps, const void* skip, size_t skip_plane,
                          const float* tproj, int tproj_stride, int act, void* y, size_t y_plane, int fmt,

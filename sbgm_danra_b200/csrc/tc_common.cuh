@@ -306,5 +306,7 @@ int encode_act_map(CUtensorMap* map, const void* base, int planes, size_t plane_
                    int box_w, int box_h, int box_n, int stride);
 // packed weights [planes][cout][K] bf16 as a 3-D map, box = (64, box_rows, 1)
 int encode_weight_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int cout, int K, int box_rows);
+// (w_tile, h_tile, n_tile), product 128, powers of two, covering an [n][ho][wo] pixel grid with the least padding
+void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt);
 
 }  // namespace sbgm

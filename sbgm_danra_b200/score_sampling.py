@@ -417,21 +417,19 @@ def _dsm_loss_forward(model, x, marginal_prob_std, t_eps, y, cond_img, lsm_cond,
     dev = x.device
     seed = _next_seed()
     n, per = x.shape[0], x[0].numel()
-    with torch.no_grad(), torch.cuda.device(dev):
-        x = x.contiguous().float()
-        start = _state.first_member // 4 * 4          # Philox counters cover 4 elements: generate from an aligned start
-        off = _state.first_member - start
-        u = torch.empty((off + n + 3) // 4 * 4, dtype=torch.float32, device=dev)
-        call("sbgm_philox_uniform", u.data_ptr(), u.numel(), seed, 0, start, _eng._stream())
-        t = u[off:off + n] * (1.0 - t_eps) + t_eps
-        std = marginal_prob_std(t).float().contiguous()
-        xt, z = torch.empty_like(x), torch.empty_like(x)
-        call("sbgm_dsm_perturb", x.data_ptr(), std.data_ptr(), xt.data_ptr(), z.data_ptr(), n, per, seed, 1,
-             _state.first_member * per, _eng._stream())
-        score = model(xt, t, y=y, cond_img=cond_img, lsm_cond=lsm_cond, topo_cond=topo_cond).contiguous().float()
-        partials = torch.empty(_lib.query("sbgm_dsm_scratch_floats", x.numel()), dtype=torch.float32, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        sdf = None if sdf_cond is None else sdf_cond.to(dev).contiguous().float()
-        call("sbgm_dsm_loss", score.data_ptr(), std.data_ptr(), z.data_ptr(), None if sdf is None else sdf.data_ptr(),
-             n, per, partials.data_ptr(), loss.data_ptr(), _eng._stream())
-        return loss
+    with torch.cuda.device(dev):
+        with torch.no_grad():
+            x = x.contiguous().float()
+            start = _state.first_member // 4 * 4          # Philox counters cover 4 elements: generate from an aligned start
+            off = _state.first_member - start
+            u = torch.empty((off + n + 3) // 4 * 4, dtype=torch.float32, device=dev)
+            call("sbgm_philox_uniform", u.data_ptr(), u.numel(), seed, 0, start, _eng._stream())
+            t = u[off:off + n] * (1.0 - t_eps) + t_eps
+            std = marginal_prob_std(t).float().contiguous()
+            xt, z = torch.empty_like(x), torch.empty_like(x)
+            call("sbgm_dsm_perturb", x.data_ptr(), std.data_ptr(), xt.data_ptr(), z.data_ptr(), n, per, seed, 1,
+                 _state.first_member * per, _eng._stream())
+            sdf = None if sdf_cond is None else sdf_cond.to(dev).contiguous().float()
+        score = model(xt, t, y=y, cond_img=cond_img, lsm_cond=lsm_cond, topo_cond=topo_cond)
+        from .score_unet import _DSMLossFn
+        return _DSMLossFn.apply(score, std, z, sdf)

@@ -381,16 +381,36 @@ class ScoreNet(nn.Module):
         _require_cuda(self.encoder.conv1.weight, "ScoreNet")
         return self._cache.get(self, self.precision, lambda dev: _eng.UNetEngine(self.state_dict(), self.spec(), self.precision, dev))
 
+    def _bn_modules(self):
+        return [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+
     def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor] = None,
                 cond_img: Optional[torch.Tensor] = None, lsm_cond: Optional[torch.Tensor] = None,
                 topo_cond: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _require_cuda(self.encoder.conv1.weight, "ScoreNet")
+        dev = self.encoder.conv1.weight.device
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad or self.training:
+            # training graph: unfolded BatchNorm (batch statistics when .training), backward tape (train_engine.py)
+            with torch.cuda.device(dev):
+                x = x.to(dev).float().contiguous()
+                t = t.to(dev).float()
+                planes = _eng.concat_planes(x.shape[0], lsm_cond, topo_cond, cond_img, dev)
+                std = self.marginal_prob_std(t)
+                pre = bool(getattr(self, "debug_pre_sigma_div", True))
+                inv_std = None if pre else (1.0 / std.float()).contiguous()
+                names = [k for k, _ in self.named_parameters()]
+                params = [p_ for _, p_ in self.named_parameters()]
+                out = _ScoreNetFn.apply(self, x, t, y, planes, inv_std, names, *params)
+                if self.training:
+                    torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
+                if pre:
+                    with torch.no_grad():
+                        logger.info(f"[pre-σ-div] mean = {float(out.mean()):.4g}, std = {float(out.std()):.4g}, "
+                                    f"σ ∈ [{std.min():.4g}, {std.max():.4g}]")
+                    return out / std.view(-1, 1, 1, 1)
+                return out
         eng = self.engine()
-        dev = eng.device
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("the DSM training path (backward kernels, train-mode BatchNorm) is not built yet; "
-                                      "wrap inference in torch.no_grad() and call .eval()")
-        if self.training:
-            raise NotImplementedError("train-mode BatchNorm (batch statistics) is not on the CUDA path yet; call .eval()")
         with torch.no_grad(), torch.cuda.device(dev):
             x = x.to(dev)
             t = t.to(dev).float()
@@ -403,6 +423,59 @@ class ScoreNet(nn.Module):
                 return out / std.view(-1, 1, 1, 1)
             inv_std = (1.0 / std.float()).contiguous()
             return eng.forward(x, t, y, planes, inv_std)
+
+
+class _ScoreNetFn(torch.autograd.Function):
+    """The whole score-UNet as one autograd node: forward and backward both run this repo's kernels
+    (train_engine.TrainEngine); replaces torch autograd over sbgm/score_unet.py:829-879."""
+
+    @staticmethod
+    def forward(ctx, model, x, t, y, planes, inv_std, names, *params):
+        from .train_engine import TrainEngine
+        tensors = dict(zip(names, params))
+        tensors.update({k: v for k, v in model.named_buffers()})
+        hook = getattr(model, "_grad_sync", None)
+        eng = TrainEngine(tensors, model.spec(), model.precision, x.device, bn_train=model.training)
+        eng.grad_sync = hook          # parallel.GradSync: bucketed all-reduce of the flat gradient buffer, overlapped
+        out = eng.forward(x, t, y, planes, inv_std)
+        ctx.eng, ctx.names = eng, names
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng = ctx.eng
+        with torch.cuda.device(eng.device):
+            grads = eng.backward(dout)
+        ctx.eng = None
+        return (None,) * 7 + tuple(grads.get(n) for n in ctx.names)
+
+
+class _DSMLossFn(torch.autograd.Function):
+    """loss = mean_n sum_pix w (score std + z)^2 and its gradient w.r.t. score (score_unet.py:936-985)."""
+
+    @staticmethod
+    def forward(ctx, score, std, z, sdf):
+        from . import _lib
+        n, per = score.shape[0], score[0].numel()
+        score = score.contiguous().float()
+        partials = torch.empty(_lib.query("sbgm_dsm_scratch_floats", score.numel()), dtype=torch.float32, device=score.device)
+        loss = torch.empty((), dtype=torch.float32, device=score.device)
+        call("sbgm_dsm_loss", score.data_ptr(), std.data_ptr(), z.data_ptr(), None if sdf is None else sdf.data_ptr(),
+             n, per, partials.data_ptr(), loss.data_ptr(), _eng._stream())
+        ctx.save_for_backward(score, std, z, *(() if sdf is None else (sdf,)))
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        score, std, z, *rest = ctx.saved_tensors
+        sdf = rest[0] if rest else None
+        n, per = score.shape[0], score[0].numel()
+        dscore = torch.empty_like(score)
+        gl = grad_loss.to(device=score.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(score.device):
+            call("sbgm_dsm_loss_backward", score.data_ptr(), std.data_ptr(), z.data_ptr(), None if sdf is None else sdf.data_ptr(),
+                 gl.data_ptr(), n, per, dscore.data_ptr(), _eng._stream())
+        return dscore, None, None, None
 
 
 def marginal_prob_std(t: torch.Tensor, sigma: float, eps: float = 1e-5) -> torch.Tensor:
@@ -425,10 +498,12 @@ diffusion_coeff_fn = functools.partial(diffusion_coeff, sigma=sigma)
 
 def loss_fn(model, x, marginal_prob_std, t_eps=1e-3, device=None, y=None, cond_img=None, lsm_cond=None,
             topo_cond=None, sdf_cond=None):
-    """Denoising score-matching loss (score_unet.py:936-985): forward value on the CUDA path.
+    """Denoising score-matching loss (score_unet.py:936-985).
 
     t ~ U(t_eps, 1), z ~ N(0, I) come from the Philox stream of `sbgm_danra_b200.score_sampling.noise_state()`.
-    The returned scalar carries no autograd graph yet (backward kernels are a later round)."""
+    With grad enabled the returned 0-d tensor carries an autograd graph whose nodes (`_DSMLossFn`, `_ScoreNetFn`)
+    run this repo's backward kernels, so `loss.backward()` fills `param.grad` exactly as in the reference flow
+    (sbgm/training.py:323-410)."""
     from . import score_sampling as _ss
     for name, arr in (("cond_img", cond_img), ("lsm_cond", lsm_cond), ("topo_cond", topo_cond), ("y", y)):
         if arr is not None and arr.shape[0] != x.shape[0]:

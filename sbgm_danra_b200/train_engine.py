@@ -1,0 +1,594 @@
+"""Training-mode execution of the score-UNet: forward with batch statistics + a reverse tape of CUDA kernels.
+
+The reference trains through torch autograd (sbgm/training.py:323-410 calls `loss_fn` -> `loss.backward()`,
+sbgm/score_unet.py:936-985).  Here one `torch.autograd.Function` (score_unet._ScoreNetFn) wraps the whole
+network: its forward runs `TrainEngine.forward`, which sequences the same forward kernels as inference but
+with unfolded BatchNorm (batch statistics, running-stat update) and records, per kernel, a closure that
+launches the matching backward kernels of `include/sbgm_b200.h` (convolution data / weight gradients on the
+tensor cores, normalisation / attention / upsample / time-embedding backward).  `TrainEngine.backward`
+replays the closures in reverse and returns fp32 gradients in torch's parameter layouts, written as views of
+ONE flat buffer so that data-parallel training can all-reduce it in place (parallel.py).
+
+torch supplies memory, streams and the autograd hook; every FLOP runs in this repo's kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, FMT_BF16, FMT_BF16X2, FMT_F32, call
+from .engine import (ACTS, BN_EPS, GN_EPS, LN_EPS, PRECISIONS, Act, ConvW, Kernels, UNetSpec, _Packer, _ptr, _split_bf16,
+                     _stream)
+
+BN_MOMENTUM = 0.1
+NORM_CHUNKS = 32
+
+
+def _pack_oihw(w: torch.Tensor, fmt: int) -> torch.Tensor:
+    """OIHW fp32 -> the forward kernels' packed layout (engine._Packer.conv without BatchNorm folding)."""
+    cout, cin, kh, kw = w.shape
+    if fmt == FMT_F32:
+        return w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
+    km = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).contiguous()
+    return km.to(torch.bfloat16) if fmt == FMT_BF16 else _split_bf16(km)
+
+
+class ConvLayer:
+    """One convolution / linear layer of the training graph: forward pack + what its gradients need."""
+
+    def __init__(self, name: str, w: torch.Tensor, bias: Optional[torch.Tensor], fmt: int, bias_name: Optional[str] = None):
+        self.name, self.bias_name, self.fmt = name, bias_name, fmt
+        w4 = w if w.dim() == 4 else w[:, :, None, None]
+        self.w4, self.shape = w4, tuple(w.shape)
+        self.cout, self.cin, self.kh, self.kw = w4.shape
+        self.fwd = ConvW(_pack_oihw(w4, fmt), None if bias is None else bias.contiguous(), self.cin, self.cout, self.kh, self.kw)
+        self._dgrad: Dict[Tuple, object] = {}
+
+    def dgrad_simt_weight(self) -> torch.Tensor:
+        key = ("simt",)
+        if key not in self._dgrad:
+            self._dgrad[key] = self.w4.permute(2, 3, 0, 1).reshape(self.kh * self.kw, self.cout, self.cin).contiguous()
+        return self._dgrad[key]
+
+    def dgrad_tc_weight(self, stride: int, pad: int, py: int = 0, px: int = 0):
+        """Packed weight of the stride-1 convolution over dy that yields the input gradient of parity class
+        (py, px) (all pixels when stride == 1).  Returns (ConvW, pad_h, pad_w) or None if the class has no taps."""
+        key = ("tc", stride, pad, py, px)
+        if key in self._dgrad:
+            return self._dgrad[key]
+
+        def taps(k: int, par: int):
+            # input index i = stride * j + par receives dy[j + d] * w[r] with r = par + pad - stride * d
+            ds = sorted(d for d in range(-k, k + 1) if 0 <= par + pad - stride * d < k)
+            return ds, [par + pad - stride * d for d in ds]
+
+        dys, rs = taps(self.kh, py)
+        dxs, ss = taps(self.kw, px)
+        if not rs or not ss:
+            self._dgrad[key] = None
+            return None
+        # tap index r' of the sub-kernel reads dy at offset d = r' - pad'  ->  pad' = -d_min; taps must be contiguous in d
+        assert dys == list(range(dys[0], dys[0] + len(dys))) and dxs == list(range(dxs[0], dxs[0] + len(dxs)))
+        sub = self.w4[:, :, rs, :][:, :, :, ss]                       # [co, ci, kh', kw'] in increasing-d order
+        wt = sub.permute(1, 0, 2, 3).contiguous()                     # transposed conv: OIHW with O = ci, I = co
+        cw = ConvW(_pack_oihw(wt, self.fmt), None, self.cout, self.cin, len(rs), len(ss))
+        self._dgrad[key] = (cw, -dys[0], -dxs[0])
+        return self._dgrad[key]
+
+
+class Tape:
+    """Reverse-mode tape over `Act` tensors.  Gradients are keyed by the storage pointer, so views
+    (`Act.tokens()`) share their producer's gradient; the tape keeps every activation alive."""
+
+    def __init__(self, fmt: int, device) -> None:
+        self.fmt, self.device = fmt, device
+        self.steps: List[Callable[[], None]] = []
+        self.grads: Dict[int, Act] = {}
+        self.keep: List[object] = []
+        self.pgrads: Dict[str, torch.Tensor] = {}
+
+    def record(self, fn: Callable[[], None], *keep) -> None:
+        self.steps.append(fn)
+        self.keep.extend(keep)
+
+    def pop(self, a: Act) -> Optional[Act]:
+        return self.grads.pop(a.buf.data_ptr(), None)
+
+    def add(self, a: Act, g: Act) -> None:
+        key = a.buf.data_ptr()
+        cur = self.grads.get(key)
+        if cur is None:
+            self.grads[key] = g
+        else:
+            call("sbgm_add_inplace", cur.ptr, cur.plane, g.ptr, g.plane, self.fmt, cur.plane, _stream())
+
+
+class TrainKernels:
+    """Forward ops that record their backward on a tape."""
+
+    def __init__(self, fmt: int, device, flat_grad: Callable[[str, Tuple[int, ...]], torch.Tensor]) -> None:
+        self.fmt, self.device = fmt, device
+        self.k = Kernels(fmt, device)
+        self.tape: Optional[Tape] = None
+        self.param_grad = flat_grad
+        self._scratch: Dict[str, torch.Tensor] = {}
+
+    # -- scratch management --------------------------------------------------------------------
+    def scratch(self, tag: str, floats: int) -> torch.Tensor:
+        cur = self._scratch.get(tag)
+        if cur is None or cur.numel() < floats:
+            cur = torch.empty(max(int(floats), 1), dtype=torch.float32, device=self.device)
+            self._scratch[tag] = cur
+        return cur
+
+    def grad_like(self, a: Act, zero: bool = False) -> Act:
+        g = Act(self.fmt, a.n, a.h, a.w, a.c, self.device)
+        if zero:
+            g.buf.zero_()
+        return g
+
+    # -- convolution ----------------------------------------------------------------------------
+    def conv(self, x: Act, layer: ConvLayer, stride: int = 1, pad: int = 0, residual: Optional[Act] = None,
+             gn_stats: bool = False, need_dx: bool = True):
+        out = self.k.conv(x, layer.fwd, stride=stride, pad=pad, residual=residual, gn_stats=gn_stats)
+        y, stats = out if gn_stats else (out, None)
+        tape = self.tape
+
+        def backward() -> None:
+            dy = tape.pop(y)
+            if dy is None:
+                return
+            self._conv_backward(x, dy, layer, stride, pad, need_dx)
+            if residual is not None:
+                tape.add(residual, dy)
+
+        tape.record(backward, x, y)
+        return (y, stats) if gn_stats else y
+
+    def _conv_backward(self, x: Act, dy: Act, layer: ConvLayer, stride: int, pad: int, need_dx: bool) -> None:
+        fmt, st = self.fmt, _stream()
+        n, h, w = x.n, x.h, x.w
+        cin, cout, kh, kw = layer.cin, layer.cout, layer.kh, layer.kw
+        if layer.bias_name is not None:
+            db = self.param_grad(layer.bias_name, (cout,))
+            ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, cout))
+            call("sbgm_channel_sums", dy.ptr, dy.plane, fmt, dy.n, dy.h * dy.w, cout, None, 0, db.data_ptr(), ws.data_ptr(), st)
+        dw = self.param_grad(layer.name, layer.shape)
+        tc = fmt != FMT_F32 and cin % 64 == 0 and cout % 64 == 0
+        if tc:
+            ws = self.scratch("wgrad", _lib.query("sbgm_conv2d_wgrad_tc_workspace_floats", fmt, n, h, w, cin, cout, kh, kw, stride, pad))
+            call("sbgm_conv2d_wgrad_tc", x.ptr, x.plane, dy.ptr, dy.plane, dw.data_ptr(), fmt, n, h, w, cin, cout, kh, kw, stride, pad,
+                 ws.data_ptr(), st)
+        else:
+            ws = self.scratch("wgrad", _lib.query("sbgm_conv2d_wgrad_simt_workspace_floats", n, h, w, cin, cout, kh, kw, stride, pad))
+            call("sbgm_conv2d_wgrad_simt", x.ptr, x.plane, dy.ptr, dy.plane, dw.data_ptr(), fmt, n, h, w, cin, cout, kh, kw, stride, pad,
+                 ws.data_ptr(), st)
+        if not need_dx:
+            return
+        tape = self.tape
+        if not tc:
+            dx = self.grad_like(x)
+            call("sbgm_conv2d_dgrad_simt", dy.ptr, dy.plane, layer.dgrad_simt_weight().data_ptr(), dx.ptr, dx.plane, 0, fmt,
+                 n, h, w, cin, cout, kh, kw, stride, pad, st)
+            tape.add(x, dx)
+            return
+        if stride == 1:
+            cw, ph, pw = layer.dgrad_tc_weight(1, pad)
+            assert ph == pw
+            dx = self.k.conv(dy, cw, stride=1, pad=ph)
+            assert (dx.h, dx.w) == (h, w)
+            tape.add(x, dx)
+            return
+        # strided convolution: one stride-1 convolution over dy per input-parity class, scattered into dx
+        dx = self.grad_like(x, zero=True)
+        for py in range(stride):
+            for px in range(stride):
+                ent = layer.dgrad_tc_weight(stride, pad, py, px)
+                if ent is None:
+                    continue
+                cw, ph, pw = ent
+                ho, wo = (h - py + stride - 1) // stride, (w - px + stride - 1) // stride
+                call("sbgm_conv2d_tc_ex", dy.ptr, dy.plane, cw.w.data_ptr(), cw.plane, None, None, 0, dx.ptr, dx.plane, fmt,
+                     dy.n, dy.h, dy.w, cout, cin, cw.kh, cw.kw, 1, ph, pw, ho, wo, h, w, stride, py, px, ACT_NONE, None, 0, st)
+        tape.add(x, dx)
+
+    # -- normalisation ------------------------------------------------------------------------------
+    def _norm(self, x: Act, stats: torch.Tensor, mode: int, groups: int, gamma, beta, gamma_name, beta_name, add: Optional[Act],
+              tproj: Optional[torch.Tensor], dtproj: Optional[torch.Tensor], tproj_pre: int, act: int) -> Act:
+        fmt = self.fmt
+        y = x.like()
+        hw = x.h * x.w
+        call("sbgm_norm_apply", x.ptr, x.plane, stats.data_ptr(), mode, groups, _ptr(gamma), _ptr(beta),
+             None if add is None else add.ptr, 0 if add is None else add.plane, _ptr(tproj),
+             tproj.stride(0) if tproj is not None else 0, tproj_pre, act, y.ptr, y.plane, fmt, x.n, hw, x.c, _stream())
+        tape = self.tape
+
+        def backward() -> None:
+            dy = tape.pop(y)
+            if dy is None:
+                return
+            dx = self.grad_like(x)
+            dadd = self.grad_like(x) if add is not None else None
+            dg = self.param_grad(gamma_name, (x.c,)) if gamma_name else None
+            db = self.param_grad(beta_name, (x.c,)) if beta_name else None
+            ws = self.scratch("norm_bwd", _lib.query("sbgm_norm_backward_scratch_floats", x.n, x.c))
+            call("sbgm_norm_backward", dy.ptr, dy.plane, x.ptr, x.plane, stats.data_ptr(), mode, groups, _ptr(gamma), _ptr(beta),
+                 None if add is None else add.ptr, 0 if add is None else add.plane, _ptr(tproj),
+                 tproj.stride(0) if tproj is not None else 0, tproj_pre, act, dx.ptr, dx.plane,
+                 None if dadd is None else dadd.ptr, 0 if dadd is None else dadd.plane, _ptr(dg), _ptr(db),
+                 _ptr(dtproj), dtproj.stride(0) if dtproj is not None else 0, fmt, x.n, hw, x.c, ws.data_ptr(), _stream())
+            tape.add(x, dx)
+            if add is not None:
+                tape.add(add, dadd)
+
+        tape.record(backward, x, y, stats)
+        return y
+
+    def batchnorm(self, x: Act, bn: dict, train: bool, act: int = ACT_NONE, residual: Optional[Act] = None,
+                  tproj: Optional[torch.Tensor] = None, dtproj: Optional[torch.Tensor] = None) -> Act:
+        """nn.BatchNorm2d (+residual, ReLU, then the time projection).  train=True: batch statistics and
+        running-stat update (torchvision resnet.py:89-103 in .train()); else the running statistics as constants."""
+        c, hw = x.c, x.h * x.w
+        stats = torch.empty((c, 2), dtype=torch.float32, device=self.device)
+        if train:
+            part = torch.empty((x.n, NORM_CHUNKS, c, 2), dtype=torch.float32, device=self.device)
+            call("sbgm_norm_partials", x.ptr, x.plane, self.fmt, x.n, hw, c, c, part.data_ptr(), _stream())
+            call("sbgm_bn_stats_finalize", part.data_ptr(), NORM_CHUNKS, x.n, hw, c, BN_EPS, BN_MOMENTUM, stats.data_ptr(),
+                 bn["running_mean"].data_ptr(), bn["running_var"].data_ptr(), _stream())
+            mode = 0
+        else:
+            stats[:, 0] = bn["running_mean"]
+            stats[:, 1] = torch.rsqrt(bn["running_var"] + BN_EPS)
+            mode = 2
+        return self._norm(x, stats, mode, c, bn["weight"], bn["bias"], bn["weight_name"], bn["bias_name"], residual, tproj, dtproj, 0, act)
+
+    def groupnorm(self, x: Act, gamma, beta, gamma_name, beta_name, groups: int, act: int = ACT_NONE, skip: Optional[Act] = None,
+                  tproj: Optional[torch.Tensor] = None, dtproj: Optional[torch.Tensor] = None, fused=None) -> Act:
+        hw = x.h * x.w
+        stats = torch.empty((x.n, groups, 2), dtype=torch.float32, device=self.device)
+        if fused is not None and (x.c // 8) % groups == 0:
+            part, chunks = fused
+            pgroups = x.c // 8
+        else:
+            part = torch.empty((x.n, NORM_CHUNKS, groups, 2), dtype=torch.float32, device=self.device)
+            call("sbgm_norm_partials", x.ptr, x.plane, self.fmt, x.n, hw, x.c, groups, part.data_ptr(), _stream())
+            chunks, pgroups = NORM_CHUNKS, groups
+        call("sbgm_gn_stats_finalize", part.data_ptr(), chunks, pgroups, groups, x.n, hw, x.c, GN_EPS, stats.data_ptr(), _stream())
+        return self._norm(x, stats, 1, groups, gamma, beta, gamma_name, beta_name, skip, tproj, dtproj, 1, act)
+
+    def layernorm(self, x: Act, gamma, beta, gamma_name, beta_name) -> Act:
+        y = self.k.layernorm(x, gamma, beta)
+        tape = self.tape
+
+        def backward() -> None:
+            dy = tape.pop(y)
+            if dy is None:
+                return
+            dx = self.grad_like(x)
+            rows = x.n * x.h * x.w
+            ws = self.scratch("ln_bwd", _lib.query("sbgm_layernorm_backward_scratch_floats", x.c))
+            call("sbgm_layernorm_backward", dy.ptr, dy.plane, x.ptr, x.plane, gamma.data_ptr(), LN_EPS, dx.ptr, dx.plane,
+                 self.param_grad(gamma_name, (x.c,)).data_ptr(), self.param_grad(beta_name, (x.c,)).data_ptr(), self.fmt, rows, x.c,
+                 ws.data_ptr(), _stream())
+            tape.add(x, dx)
+
+        tape.record(backward, x, y)
+        return y
+
+    def activation(self, x: Act, act: int) -> Act:
+        y = x.like()
+        call("sbgm_act_forward", x.ptr, x.plane, y.ptr, y.plane, self.fmt, x.plane, act, _stream())
+        tape = self.tape
+
+        def backward() -> None:
+            dy = tape.pop(y)
+            if dy is None:
+                return
+            dx = self.grad_like(x)
+            call("sbgm_act_backward", dy.ptr, dy.plane, x.ptr, x.plane, dx.ptr, dx.plane, self.fmt, x.plane, act, _stream())
+            tape.add(x, dx)
+
+        tape.record(backward, x, y)
+        return y
+
+    def upsample2x(self, x: Act) -> Act:
+        y = self.k.upsample2x(x)
+        tape = self.tape
+
+        def backward() -> None:
+            dy = tape.pop(y)
+            if dy is None:
+                return
+            dx = self.grad_like(x)
+            call("sbgm_upsample2x_backward", dy.ptr, dy.plane, dx.ptr, dx.plane, self.fmt, x.n, x.h, x.w, x.c, _stream())
+            tape.add(x, dx)
+
+        tape.record(backward, x, y)
+        return y
+
+    def attention_core(self, qkv: Act, b: int, s: int, c: int, heads: int) -> Act:
+        y = self.k.attention_core(qkv, b, s, c, heads)
+        tape = self.tape
+
+        def backward() -> None:
+            dy = tape.pop(y)
+            if dy is None:
+                return
+            dqkv = self.grad_like(qkv)
+            ws = self.scratch("attn_bwd", _lib.query("sbgm_attention_backward_scratch_floats", b, s, c, heads))
+            call("sbgm_attention_backward", qkv.ptr, qkv.plane, dy.ptr, dy.plane, dqkv.ptr, dqkv.plane, self.fmt, b, s, c, heads,
+                 ws.data_ptr(), _stream())
+            tape.add(qkv, dqkv)
+
+        tape.record(backward, qkv, y)
+        return y
+
+
+class _AttnLayers:
+    def __init__(self, sd, prefix: str, heads: int, fmt: int) -> None:
+        g = lambda k: sd[f"{prefix}.{k}"]
+        self.heads, self.prefix = heads, prefix
+        self.ln1 = (g("ln1.weight"), g("ln1.bias"))
+        self.ln2 = (g("ln2.weight"), g("ln2.bias"))
+        self.in_proj = ConvLayer(f"{prefix}.mha.in_proj_weight", g("mha.in_proj_weight"), g("mha.in_proj_bias"), fmt, f"{prefix}.mha.in_proj_bias")
+        self.out_proj = ConvLayer(f"{prefix}.mha.out_proj.weight", g("mha.out_proj.weight"), g("mha.out_proj.bias"), fmt, f"{prefix}.mha.out_proj.bias")
+        self.ff0 = ConvLayer(f"{prefix}.ff.0.weight", g("ff.0.weight"), g("ff.0.bias"), fmt, f"{prefix}.ff.0.bias")
+        self.ff2 = ConvLayer(f"{prefix}.ff.2.weight", g("ff.2.weight"), g("ff.2.bias"), fmt, f"{prefix}.ff.2.bias")
+
+
+def _attention_block(tk: TrainKernels, aw: _AttnLayers, x: Act) -> Act:
+    """ImageSelfAttention.forward (score_unet.py:136-148) with its backward recorded."""
+    tok = x.tokens()
+    b, s, c = x.n, x.h * x.w, x.c
+    p = aw.prefix
+    h1 = tk.layernorm(tok, *aw.ln1, f"{p}.ln1.weight", f"{p}.ln1.bias")
+    qkv = tk.conv(h1, aw.in_proj)
+    att = tk.attention_core(qkv, b, s, c, aw.heads)
+    h = tk.conv(att, aw.out_proj, residual=tok)
+    g = tk.layernorm(h, *aw.ln2, f"{p}.ln2.weight", f"{p}.ln2.bias")
+    g1 = tk.conv(g, aw.ff0)
+    g2 = tk.activation(g1, ACT_GELU)
+    y = tk.conv(g2, aw.ff2, residual=h)
+    out = Act.__new__(Act)
+    out.buf, out.fmt, out.n, out.h, out.w, out.c = y.buf, y.fmt, x.n, x.h, x.w, x.c
+    return out
+
+
+class TrainEngine:
+    """One forward + backward of the score-UNet for the DSM training step.
+
+    `params` maps state-dict names to the live parameter / buffer tensors (fp32, CUDA).  BatchNorm running
+    statistics are updated in place when `bn_train` is set."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], spec: UNetSpec, precision: str, device, bn_train: bool) -> None:
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("sbgm_danra_b200 runs on CUDA devices only (no CPU fallback); got device " + str(device))
+        if not spec.use_resize_conv:
+            raise NotImplementedError("use_resize_conv=False (ConvTranspose2d decoder) has no training path yet")
+        _lib.load_library()
+        self.spec, self.device, self.fmt, self.bn_train = spec, device, PRECISIONS[precision], bn_train
+        self.sd = {k: v.detach() for k, v in params.items()}
+        for k, v in self.sd.items():
+            if v.is_floating_point() and (v.dtype != torch.float32 or not v.is_cuda):
+                raise RuntimeError(f"parameter {k} must be fp32 on CUDA for the training path, got {v.dtype} on {v.device}")
+        # flat gradient buffer: parameters in state-dict order, each gradient a view (parallel.py all-reduces it in place)
+        names = [k for k, v in params.items() if isinstance(v, torch.nn.Parameter) or v.requires_grad]
+        is_tail = lambda k: "time_projection_layer" in k or k.endswith("label_emb.weight")   # produced last by backward
+        self.grad_names = [k for k in names if not is_tail(k)] + [k for k in names if is_tail(k)]
+        self.offsets: Dict[str, Tuple[int, int]] = {}
+        off = 0
+        for k in self.grad_names:
+            self.offsets[k] = (off, self.sd[k].numel())
+            off += (self.sd[k].numel() + 63) // 64 * 64
+        self.flat_numel = off
+        self.flat: Optional[torch.Tensor] = None
+        self.touched: Dict[str, torch.Tensor] = {}
+        self.tk = TrainKernels(self.fmt, device, self._param_grad)
+        self.grad_sync = None      # parallel.GradSync or None
+        with torch.cuda.device(device), torch.no_grad():
+            self._pack()
+
+    # -- parameters -------------------------------------------------------------------------------
+    def _param_grad(self, name: str, shape: Tuple[int, ...]) -> torch.Tensor:
+        off, numel = self.offsets[name]
+        g = self.flat[off:off + numel].view(shape)
+        self.touched[name] = g
+        return g
+
+    def _bn(self, prefix: str) -> dict:
+        return dict(weight=self.sd[f"{prefix}.weight"], bias=self.sd[f"{prefix}.bias"], running_mean=self.sd[f"{prefix}.running_mean"],
+                    running_var=self.sd[f"{prefix}.running_var"], weight_name=f"{prefix}.weight", bias_name=f"{prefix}.bias")
+
+    def _conv(self, wname: str, bname: Optional[str] = None) -> ConvLayer:
+        return ConvLayer(wname, self.sd[wname], None if bname is None else self.sd[bname], self.fmt, bname)
+
+    def _pack(self) -> None:
+        sd, spec, fmt = self.sd, self.spec, self.fmt
+        p = "encoder."
+        w1 = sd[f"{p}conv1.weight"]
+        self.cin = w1.shape[1]
+        self.stem_w = w1.permute(1, 2, 3, 0).reshape(self.cin, 64, 64).contiguous()
+        self.conv2 = self._conv(f"{p}conv2.weight")
+        self.bn1 = self._bn(f"{p}bn1")
+        self.layers = []
+        for li, nblk in enumerate(spec.block_layers, start=1):
+            blocks = []
+            for b in range(nblk):
+                bp = f"{p}layer{li}.{b}"
+                stride = 2 if (b == 0 and li > 1) else 1
+                down = None
+                if f"{bp}.downsample.0.weight" in sd:
+                    down = (self._conv(f"{bp}.downsample.0.weight"), self._bn(f"{bp}.downsample.1"))
+                blocks.append(dict(c1=self._conv(f"{bp}.conv1.weight"), b1=self._bn(f"{bp}.bn1"), c2=self._conv(f"{bp}.conv2.weight"),
+                                   b2=self._bn(f"{bp}.bn2"), down=down, stride=stride))
+            self.layers.append(blocks)
+        self.enc_attn = {i: _AttnLayers(sd, f"{p}attention_layers.{i}", spec.n_heads, fmt) for i in (3, 4)}
+        # time projector: same packing as inference (engine.TimeProjector) plus the names for the gradients
+        from .engine import TimeProjector
+        self.tp = TimeProjector(self.device, spec.time_embedding)
+        self.tp_names: List[Tuple[str, str, int]] = []      # (weight name, bias name, channels) in head order
+        set0 = self.tp.add_set(sd[f"{p}sinusoidal_embedding.W"])
+        for i in range(5):
+            wn, bn = f"{p}time_projection_layers.{i}.1.weight", f"{p}time_projection_layers.{i}.1.bias"
+            self.tp.add_head(f"enc{i}", set0, sd[wn], sd[bn])
+            self.tp_names.append((wn, bn, sd[wn].shape[0]))
+        self.label_name = f"{p}label_emb.weight" if spec.has_labels else None
+        if spec.has_labels:
+            self.tp.label_emb = sd[self.label_name].contiguous()
+        d = "decoder."
+        affine = spec.norm == "group"
+        self.dec_blocks = []
+        for i, (cin, cout, attn) in enumerate(spec.plan):
+            bp = f"{d}residual_layers.{i}"
+            blk = dict(conv_up=self._conv(f"{bp}.conv_up.weight", f"{bp}.conv_up.bias"), conv=self._conv(f"{bp}.conv.weight", f"{bp}.conv.bias"),
+                       n1=(sd[f"{bp}.norm1.weight"], sd[f"{bp}.norm1.bias"], f"{bp}.norm1.weight", f"{bp}.norm1.bias") if affine else (None, None, None, None),
+                       n2=(sd[f"{bp}.norm2.weight"], sd[f"{bp}.norm2.bias"], f"{bp}.norm2.weight", f"{bp}.norm2.bias") if affine else (None, None, None, None),
+                       g1=max(1, min(spec.gn_groups, cin)) if affine else cin, g2=max(1, min(spec.gn_groups, cout)) if affine else cout,
+                       attn=_AttnLayers(sd, f"{bp}.attention", spec.n_heads, fmt) if attn else None, name=f"dec{i}")
+            s = self.tp.add_set(sd[f"{bp}.sinusoidal_embedding.W"])
+            wn, bn = f"{bp}.time_projection_layer.1.weight", f"{bp}.time_projection_layer.1.bias"
+            self.tp.add_head(f"dec{i}", s, sd[wn], sd[bn])
+            self.tp_names.append((wn, bn, sd[wn].shape[0]))
+            self.dec_blocks.append(blk)
+        self.tp.finalize()
+        fp = f"{d}final_layer"
+        self.final_up = self._conv(f"{fp}.conv_up.weight", f"{fp}.conv_up.bias")
+        wf = sd[f"{fp}.conv.weight"]
+        if wf.shape[0] != 1:
+            raise NotImplementedError("the training path supports output_channels == 1 (the reference's only configuration)")
+        self.final_w = wf.permute(0, 2, 3, 1).reshape(wf.shape[0], 9, wf.shape[1]).contiguous()
+        self.final_b = sd[f"{fp}.conv.bias"].contiguous()
+        self.final_names = (f"{fp}.conv.weight", f"{fp}.conv.bias")
+        self.act = ACTS[spec.activation]
+
+    # -- forward ----------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor], planes: Optional[torch.Tensor],
+                inv_std: Optional[torch.Tensor]) -> torch.Tensor:
+        tk, fmt, dev = self.tk, self.fmt, self.device
+        tape = Tape(fmt, dev)
+        tk.tape = tape
+        self.tape = tape
+        self.flat = torch.zeros(self.flat_numel, dtype=torch.float32, device=dev)
+        self.touched = {}
+        n, _, h, w = x.shape
+        cc = self.cin - 1
+        if cc > 0 and (planes is None or planes.shape[1] != cc):
+            raise AssertionError(f"encoder expects {cc} conditioning channels")
+        t = t.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+        yy = None if y is None else y.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+        tproj = self.tp(t, yy)
+        dtproj = torch.zeros_like(tproj)
+        tape.keep += [tproj, t, yy, x, planes]
+        col = lambda table, name: self.tp.cols(table, name)
+
+        # Encoder.conv1 + time projection 0 (score_unet.py:310-314)
+        f1 = Act(fmt, n, h // 2, w // 2, 64, dev)
+        t0 = col(tproj, "enc0")
+        call("sbgm_stem_conv", x.data_ptr(), _ptr(planes), 1 if planes is None else planes.shape[0], cc, 0, self.cin,
+             self.stem_w.data_ptr(), None, 0, t0.data_ptr(), t0.stride(0), f1.ptr, f1.plane, fmt, n, h, w, _stream())
+
+        def stem_backward() -> None:
+            df = tape.pop(f1)
+            if df is None:
+                return
+            d0 = col(dtproj, "enc0")
+            ws = tk.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", n, 64))
+            call("sbgm_channel_sums", df.ptr, df.plane, fmt, n, f1.h * f1.w, 64, d0.data_ptr(), d0.stride(0), None, ws.data_ptr(), _stream())
+            dw = self._param_grad("encoder.conv1.weight", (64, self.cin, 8, 8))
+            ws2 = tk.scratch("stem", _lib.query("sbgm_stem_wgrad_workspace_floats", self.cin))
+            call("sbgm_stem_wgrad", x.data_ptr(), _ptr(planes), 1 if planes is None else planes.shape[0], cc, df.ptr, df.plane, fmt,
+                 dw.data_ptr(), n, h, w, ws2.data_ptr(), _stream())
+
+        tape.record(stem_backward, f1)
+        fmaps = [f1]
+        hcur = tk.batchnorm(tk.conv(f1, self.conv2, stride=2, pad=3), self.bn1, self.bn_train, act=ACT_RELU)
+        for li, blocks in enumerate(self.layers, start=1):
+            for bi, blk in enumerate(blocks):
+                last = bi == len(blocks) - 1
+                if blk["down"] is not None:
+                    idn = tk.batchnorm(tk.conv(hcur, blk["down"][0], stride=blk["stride"], pad=0), blk["down"][1], self.bn_train)
+                else:
+                    idn = hcur
+                mid = tk.batchnorm(tk.conv(hcur, blk["c1"], stride=blk["stride"], pad=1), blk["b1"], self.bn_train, act=ACT_RELU)
+                hcur = tk.batchnorm(tk.conv(mid, blk["c2"], stride=1, pad=1), blk["b2"], self.bn_train, act=ACT_RELU, residual=idn,
+                                    tproj=col(tproj, f"enc{li}") if last else None, dtproj=col(dtproj, f"enc{li}") if last else None)
+            if li in self.enc_attn:
+                hcur = _attention_block(tk, self.enc_attn[li], hcur)
+            fmaps.append(hcur)
+
+        # Decoder (score_unet.py:733-758)
+        rev = list(reversed(fmaps))
+        out = rev[0]
+        for i, blk in enumerate(self.dec_blocks):
+            up = tk.upsample2x(out)
+            a, st1 = tk.conv(up, blk["conv_up"], pad=1, gn_stats=True)
+            a = tk.groupnorm(a, *blk["n1"], groups=blk["g1"], fused=st1)
+            b, st2 = tk.conv(a, blk["conv"], pad=1, gn_stats=True)
+            skip = rev[i + 1]
+            if (skip.n, skip.h, skip.w, skip.c) != (b.n, b.h, b.w, b.c):
+                raise AssertionError(f"prev_fmap shape {(skip.n, skip.c, skip.h, skip.w)} must match output shape {(b.n, b.c, b.h, b.w)}")
+            out = tk.groupnorm(b, *blk["n2"], groups=blk["g2"], act=self.act, skip=skip, tproj=col(tproj, blk["name"]),
+                               dtproj=col(dtproj, blk["name"]), fused=st2)
+            if blk["attn"] is not None:
+                out = _attention_block(tk, blk["attn"], out)
+        up = tk.upsample2x(out)
+        a = tk.conv(up, self.final_up, pad=1)
+        res = torch.empty((n, 1, 2 * out.h, 2 * out.w), dtype=torch.float32, device=dev)
+        call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None,
+             res.data_ptr(), a.n, a.h, a.w, a.c, 1, _stream())
+        self._final = (a, inv_std)
+        self._time = (t, yy, dtproj)
+        return res
+
+    # -- backward ----------------------------------------------------------------------------------------
+    def backward(self, dscore: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """dscore: gradient of the loss w.r.t. the network output [n, 1, h, w] (fp32).  Returns {name: grad}."""
+        tk, tape, fmt = self.tk, self.tape, self.fmt
+        a, inv_std = self._final
+        t, yy, dtproj = self._time
+        dscore = dscore.to(device=self.device, dtype=torch.float32).contiguous()
+        da = tk.grad_like(a)
+        dwf = self._param_grad(self.final_names[0], (1, a.c, 3, 3))
+        dbf = self._param_grad(self.final_names[1], (1,))
+        ws = tk.scratch("final", _lib.query("sbgm_final_conv_backward_scratch_floats", a.c))
+        call("sbgm_final_conv_backward", dscore.data_ptr(), _ptr(inv_std), a.ptr, a.plane, fmt, self.final_w.data_ptr(), da.ptr, da.plane,
+             dwf.data_ptr(), dbf.data_ptr(), a.n, a.h, a.w, a.c, ws.data_ptr(), _stream())
+        tape.add(a, da)
+        sync = self.grad_sync
+        if sync is not None:
+            sync.begin(self.flat, [(k, *self.offsets[k]) for k in self.grad_names])
+        reported = 0
+        for fn in reversed(tape.steps):
+            fn()
+            if sync is not None and len(self.touched) > reported:
+                new = list(self.touched)[reported:]
+                reported = len(self.touched)
+                sync.progress(new)
+        # time embedding: one launch set for all nine projections (+ label embedding)
+        fw, pw, pb, ps = self.tp._packed
+        rows = t.numel()
+        dpw = torch.empty_like(pw)
+        dpb = torch.empty_like(pb)
+        dlab = self._param_grad(self.label_name, tuple(self.sd[self.label_name].shape)) if (self.label_name and yy is not None) else None
+        ws = tk.scratch("time", _lib.query("sbgm_time_embed_backward_scratch_floats", fw.shape[0], self.tp.te, rows))
+        call("sbgm_time_embed_backward", dtproj.data_ptr(), t.data_ptr(), _ptr(yy), fw.data_ptr(), fw.shape[0], self.tp.te,
+             _ptr(self.tp.label_emb) if yy is not None else None, 0 if dlab is None else dlab.shape[0], pw.data_ptr(), ps.data_ptr(),
+             self.tp.c_total, rows, dpw.data_ptr(), dpb.data_ptr(), _ptr(dlab), ws.data_ptr(), _stream())
+        off = 0
+        for wn, bn, c in self.tp_names:
+            self._param_grad(wn, (c, self.tp.te)).copy_(dpw[off:off + c])
+            self._param_grad(bn, (c,)).copy_(dpb[off:off + c])
+            off += c
+        if sync is not None:
+            sync.progress(list(self.touched)[reported:])
+            sync.finish()
+        grads = dict(self.touched)
+        self.tape = None
+        tk.tape = None
+        self._final = self._time = None
+        return grads

@@ -1,0 +1,414 @@
+"""GPU parity tests of the DSM training path: every backward kernel against torch autograd on the same
+operator (plain fp32 torch), then the whole loss + gradients against the CPU oracle's autograd and the
+committed reference goldens (tests/golden/, generated from the real reference by make_golden.py).
+
+Tolerances are relative L2: fp32 kernels 2e-5; bf16x3 (split-bf16 tensor cores, fp32-class) 2e-4 per op and
+2e-3 for whole-network gradients; bf16 5e-2 per op (reported, bf16 gradients are bf16-rounded)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN_DIR, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FMTS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
+TOL = {"fp32": 2e-5, "bf16": 5e-2, "bf16x3": 2e-4}
+DEV = "cuda:0"
+ACT = {"none": 0, "relu": 1, "silu": 2, "gelu": 3}
+ACT_F = {"none": lambda v: v, "relu": F.relu, "silu": F.silu, "gelu": F.gelu}
+
+
+def gen(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+@pytest.fixture(scope="module")
+def E():
+    from sbgm_danra_b200 import engine
+    return engine
+
+
+@pytest.fixture(scope="module")
+def T():
+    from sbgm_danra_b200 import train_engine
+    return train_engine
+
+
+def act_of(E, x, fmt):
+    return E.Act.from_nchw(x.to(DEV), fmt)
+
+
+def stored(E, x, fmt):
+    """x after a round trip through the activation storage format (what the kernels actually see)."""
+    return act_of(E, x, fmt).to_nchw().cpu()
+
+
+def make_tk(T, fmt):
+    grads = {}
+
+    def flat(name, shape):
+        grads[name] = torch.zeros(shape, dtype=torch.float32, device=DEV)
+        return grads[name]
+
+    tk = T.TrainKernels(fmt, torch.device(DEV), flat)
+    tk.tape = T.Tape(fmt, torch.device(DEV))
+    return tk, grads
+
+
+def run_tape(tk):
+    for fn in reversed(tk.tape.steps):
+        fn()
+
+
+# ---- normalisation ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("case", ["bn_train_relu_res_tproj", "bn_eval", "gn_silu_skip_tproj", "gn_plain", "instance_relu"])
+def test_norm_forward_backward(E, T, prec, case):
+    fmt = FMTS[prec]
+    n, c, h = 3, 64, 8
+    x0, add0, dy0 = gen(n, c, h, h, seed=1), gen(n, c, h, h, seed=2), gen(n, c, h, h, seed=3)
+    gamma, beta = 1 + 0.2 * gen(c, seed=4), 0.1 * gen(c, seed=5)
+    tproj = gen(n, 2 * c, seed=6)[:, c:]           # a column slice (stride 2c), like the real projection table
+    x, add, dy = (stored(E, v, fmt).requires_grad_(v is not dy0) for v in (x0, add0, dy0))
+    g, b = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    tp = tproj.clone().requires_grad_()
+    tk, grads = make_tk(T, fmt)
+    xa, adda = act_of(E, x.detach(), fmt), act_of(E, add.detach(), fmt)
+    tpc = tproj.to(DEV)
+    tpj = torch.zeros(n, 2 * c, device=DEV)
+    tpj[:, c:] = tpc
+    tp_dev = tpj[:, c:]
+    dtp = torch.zeros(n, 2 * c, device=DEV)
+    rm, rv = gen(c, seed=7) * 0.1, torch.rand(c, generator=torch.Generator().manual_seed(8)) + 0.5
+    if case == "bn_train_relu_res_tproj":
+        bn = dict(weight=gamma.to(DEV), bias=beta.to(DEV), running_mean=rm.to(DEV), running_var=rv.to(DEV), weight_name="g", bias_name="b")
+        ya = tk.batchnorm(xa, bn, True, act=ACT["relu"], residual=adda, tproj=tp_dev, dtproj=dtp[:, c:])
+        rm_ref, rv_ref = rm.clone(), rv.clone()
+        want = F.relu(F.batch_norm(x, rm_ref, rv_ref, g, b, training=True, momentum=0.1, eps=1e-5) + add) + tp[:, :, None, None]
+        assert rel_l2(bn["running_mean"].cpu(), rm_ref) < 1e-5 and rel_l2(bn["running_var"].cpu(), rv_ref) < 1e-5
+    elif case == "bn_eval":
+        bn = dict(weight=gamma.to(DEV), bias=beta.to(DEV), running_mean=rm.to(DEV), running_var=rv.to(DEV), weight_name="g", bias_name="b")
+        ya = tk.batchnorm(xa, bn, False, act=ACT["relu"])
+        want = F.relu(F.batch_norm(x, rm, rv, g, b, training=False, eps=1e-5))
+    elif case == "gn_silu_skip_tproj":
+        ya = tk.groupnorm(xa, gamma.to(DEV), beta.to(DEV), "g", "b", 8, act=ACT["silu"], skip=adda, tproj=tp_dev, dtproj=dtp[:, c:])
+        want = F.silu(F.group_norm(x, 8, g, b, eps=1e-5) + add + tp[:, :, None, None])
+    elif case == "gn_plain":
+        ya = tk.groupnorm(xa, gamma.to(DEV), beta.to(DEV), "g", "b", 8)
+        want = F.group_norm(x, 8, g, b, eps=1e-5)
+    else:
+        ya = tk.groupnorm(xa, None, None, None, None, c, act=ACT["relu"], skip=adda)
+        want = F.relu(F.instance_norm(x, eps=1e-5) + add)
+    assert rel_l2(ya.to_nchw().cpu(), want.detach()) < max(TOL[prec], 1e-4 if prec != "fp32" else 0)
+    want.backward(dy)
+    tk.tape.add(ya, act_of(E, dy, fmt))
+    run_tape(tk)
+    tol = TOL[prec] * 5
+    assert rel_l2(tk.tape.grads[xa.buf.data_ptr()].to_nchw().cpu(), x.grad) < tol
+    if add.grad is not None:
+        assert rel_l2(tk.tape.grads[adda.buf.data_ptr()].to_nchw().cpu(), add.grad) < tol
+    if g.grad is not None:
+        assert rel_l2(grads["g"].cpu(), g.grad) < tol and rel_l2(grads["b"].cpu(), b.grad) < tol
+    if tp.grad is not None:
+        assert rel_l2(dtp[:, c:].cpu(), tp.grad) < tol
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_layernorm_act_upsample_backward(E, T, prec):
+    fmt = FMTS[prec]
+    tk, grads = make_tk(T, fmt)
+    # LayerNorm over tokens [1, 1, rows, c]
+    rows, c = 200, 256
+    x = stored(E, gen(1, c, 1, rows, seed=1), fmt).requires_grad_()
+    dy = stored(E, gen(1, c, 1, rows, seed=2), fmt)
+    gamma, beta = (1 + 0.2 * gen(c, seed=3)).requires_grad_(), (0.1 * gen(c, seed=4)).requires_grad_()
+    xa = act_of(E, x.detach(), fmt)
+    ya = tk.layernorm(xa, gamma.detach().to(DEV), beta.detach().to(DEV), "g", "b")
+    want = F.layer_norm(x.permute(0, 2, 3, 1), (c,), gamma, beta, eps=1e-5).permute(0, 3, 1, 2)
+    want.backward(dy)
+    tk.tape.add(ya, act_of(E, dy, fmt))
+    run_tape(tk)
+    assert rel_l2(tk.tape.grads[xa.buf.data_ptr()].to_nchw().cpu(), x.grad) < TOL[prec] * 5
+    assert rel_l2(grads["g"].cpu(), gamma.grad) < TOL[prec] * 5 and rel_l2(grads["b"].cpu(), beta.grad) < TOL[prec] * 5
+    # activations
+    for name in ("relu", "silu", "gelu"):
+        tk, _ = make_tk(T, fmt)
+        x = stored(E, gen(2, 64, 5, 7, seed=5), fmt).requires_grad_()
+        dy = stored(E, gen(2, 64, 5, 7, seed=6), fmt)
+        xa = act_of(E, x.detach(), fmt)
+        ya = tk.activation(xa, ACT[name])
+        want = ACT_F[name](x)
+        assert rel_l2(ya.to_nchw().cpu(), want.detach()) < max(TOL[prec], 1e-5)
+        want.backward(dy)
+        tk.tape.add(ya, act_of(E, dy, fmt))
+        run_tape(tk)
+        assert rel_l2(tk.tape.grads[xa.buf.data_ptr()].to_nchw().cpu(), x.grad) < TOL[prec] * 2, name
+    # bilinear x2 upsample
+    for shape in ((2, 64, 4, 4), (1, 72, 5, 9)):
+        tk, _ = make_tk(T, fmt)
+        x = stored(E, gen(*shape, seed=7), fmt).requires_grad_()
+        dy = stored(E, gen(shape[0], shape[1], 2 * shape[2], 2 * shape[3], seed=8), fmt)
+        xa = act_of(E, x.detach(), fmt)
+        ya = tk.upsample2x(xa)
+        want = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        want.backward(dy)
+        tk.tape.add(ya, act_of(E, dy, fmt))
+        run_tape(tk)
+        assert rel_l2(tk.tape.grads[xa.buf.data_ptr()].to_nchw().cpu(), x.grad) < TOL[prec] * 2, shape
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("b,s,c,heads", [(2, 16, 128, 4), (3, 64, 256, 4), (1, 100, 64, 8)])
+def test_attention_backward(E, T, prec, b, s, c, heads):
+    fmt = FMTS[prec]
+    tk, _ = make_tk(T, fmt)
+    qkv = stored(E, gen(1, 3 * c, 1, b * s, seed=1), fmt).requires_grad_()
+    dy = stored(E, gen(1, c, 1, b * s, seed=2), fmt)
+    qa = act_of(E, qkv.detach(), fmt)
+    ya = tk.attention_core(qa, b, s, c, heads)
+    tok = qkv[0, :, 0, :].t().reshape(b, s, 3 * c)
+    q, k, v = (z.reshape(b, s, heads, c // heads).permute(0, 2, 1, 3) for z in tok.chunk(3, dim=-1))
+    att = torch.softmax(q @ k.transpose(-1, -2) / (c // heads) ** 0.5, dim=-1) @ v
+    want = att.permute(0, 2, 1, 3).reshape(b * s, c).t()[None, :, None, :]
+    assert rel_l2(ya.to_nchw().cpu(), want.detach()) < max(TOL[prec], 2e-5)
+    want.backward(dy)
+    tk.tape.add(ya, act_of(E, dy, fmt))
+    run_tape(tk)
+    assert rel_l2(tk.tape.grads[qa.buf.data_ptr()].to_nchw().cpu(), qkv.grad) < TOL[prec] * 5
+
+
+# ---- convolution gradients ----------------------------------------------------------------------------
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, bias
+    (2, 16, 16, 64, 64, 3, 1, 1, True),        # c64 kernel path (dgrad) + wgrad
+    (2, 8, 8, 128, 256, 3, 1, 1, True),
+    (2, 16, 16, 64, 128, 3, 2, 1, False),      # strided 3x3: parity-sliced dgrad
+    (2, 16, 16, 128, 256, 1, 2, 0, False),     # downsample 1x1 stride 2
+    (2, 32, 32, 64, 64, 8, 2, 3, False),       # Encoder.conv2
+    (3, 4, 4, 512, 512, 3, 1, 1, True),        # tiny maps, tile covers several images
+    (1, 1, 300, 256, 768, 1, 1, 0, True),      # Linear (token matrix, ragged tail)
+]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_backward(E, T, prec, case):
+    fmt = FMTS[prec]
+    n, h, w, cin, cout, k, stride, pad, bias = case
+    wt = gen(cout, cin, k, k, seed=1, scale=(cin * k * k) ** -0.5)
+    bt = gen(cout, seed=2, scale=0.1) if bias else None
+    x = stored(E, gen(n, cin, h, w, seed=3), fmt).requires_grad_()
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    dy = stored(E, gen(n, cout, ho, wo, seed=4), fmt)
+    wr = wt.clone().requires_grad_()
+    br = bt.clone().requires_grad_() if bias else None
+    want = F.conv2d(x, wr, br, stride=stride, padding=pad)
+    want.backward(dy)
+    tk, grads = make_tk(T, fmt)
+    layer = T.ConvLayer("w", wt.to(DEV), None if bt is None else bt.to(DEV), fmt, "b" if bias else None)
+    xa = act_of(E, x.detach(), fmt)
+    ya = tk.conv(xa, layer, stride=stride, pad=pad)
+    ftol = {"fp32": 2e-5, "bf16x3": 1e-4, "bf16": 2e-2}[prec]
+    assert rel_l2(ya.to_nchw().cpu(), want.detach()) < ftol
+    tk.tape.add(ya, act_of(E, dy, fmt))
+    run_tape(tk)
+    e_dx = rel_l2(tk.tape.grads[xa.buf.data_ptr()].to_nchw().cpu(), x.grad)
+    e_dw = rel_l2(grads["w"].cpu(), wr.grad)
+    print(f"{case} [{prec}] dx {e_dx:.2e} dW {e_dw:.2e}")
+    assert e_dx < ftol and e_dw < ftol
+    if bias:
+        assert rel_l2(grads["b"].cpu(), br.grad) < ftol
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_wgrad_tc_matches_simt(E, prec):
+    """The tensor-core weight gradient against the CUDA-core one on identical stored operands."""
+    from sbgm_danra_b200 import _lib
+    from sbgm_danra_b200._lib import call
+    fmt = FMTS[prec]
+    n, h, w, cin, cout, k, stride, pad = 4, 32, 32, 64, 64, 3, 1, 1
+    xa, da = act_of(E, gen(n, cin, h, w, seed=1), fmt), act_of(E, gen(n, cout, h, w, seed=2), fmt)
+    st = torch.cuda.current_stream().cuda_stream
+    out = []
+    for name in ("tc", "simt"):
+        args = (n, h, w, cin, cout, k, k, stride, pad)
+        nws = _lib.query(f"sbgm_conv2d_wgrad_{name}_workspace_floats", *(((fmt,) + args) if name == "tc" else args))
+        ws = torch.empty(nws, device=DEV)
+        dw = torch.zeros(cout, cin, k, k, device=DEV)
+        call(f"sbgm_conv2d_wgrad_{name}", xa.ptr, xa.plane, da.ptr, da.plane, dw.data_ptr(), fmt, *args, ws.data_ptr(), st)
+        out.append(dw.cpu())
+    assert rel_l2(out[0], out[1]) < (5e-5 if prec == "bf16x3" else 1e-5)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("cc,bcast", [(1, False), (6, True)])
+def test_stem_wgrad(E, prec, cc, bcast):
+    from sbgm_danra_b200 import _lib
+    from sbgm_danra_b200._lib import call
+    fmt = FMTS[prec]
+    n, h = 3, 32
+    x = gen(n, 1, h, h, seed=1)
+    planes = gen(1 if bcast else n, cc, h, h, seed=2)
+    w = gen(64, cc + 1, 8, 8, seed=3, scale=0.1).requires_grad_()
+    full = torch.cat([x, planes.expand(n, -1, -1, -1)], 1)
+    df = stored(E, gen(n, 64, h // 2, h // 2, seed=4), fmt)
+    F.conv2d(full, w, None, stride=2, padding=3).backward(df)
+    dfa = act_of(E, df, fmt)
+    dw = torch.zeros(64, cc + 1, 8, 8, device=DEV)
+    ws = torch.empty(_lib.query("sbgm_stem_wgrad_workspace_floats", cc + 1), device=DEV)
+    xd, pd = x.to(DEV).contiguous(), planes.to(DEV).contiguous()
+    call("sbgm_stem_wgrad", xd.data_ptr(), pd.data_ptr(), pd.shape[0], cc, dfa.ptr, dfa.plane, fmt, dw.data_ptr(), n, h, h,
+         ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rel_l2(dw.cpu(), w.grad) < 2e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_final_conv_backward(E, prec):
+    from sbgm_danra_b200 import _lib
+    from sbgm_danra_b200._lib import call
+    fmt = FMTS[prec]
+    n, h, w, c = 3, 16, 24, 64
+    a = stored(E, gen(n, c, h, w, seed=1), fmt).requires_grad_()
+    wt = gen(1, c, 3, 3, seed=2, scale=0.05).requires_grad_()
+    bt = gen(1, seed=3).requires_grad_()
+    inv = torch.rand(n, generator=torch.Generator().manual_seed(4)) + 0.5
+    ds = gen(n, 1, h, w, seed=5)
+    (F.conv2d(a, wt, bt, padding=1) * inv[:, None, None, None]).backward(ds)
+    aa = act_of(E, a.detach(), fmt)
+    da = E.Act(fmt, n, h, w, c, torch.device(DEV))
+    dw, db = torch.zeros(1, c, 3, 3, device=DEV), torch.zeros(1, device=DEV)
+    wp = wt.detach().permute(0, 2, 3, 1).reshape(9, c).contiguous().to(DEV)
+    ws = torch.empty(_lib.query("sbgm_final_conv_backward_scratch_floats", c), device=DEV)
+    dsd, invd = ds.to(DEV), inv.to(DEV)
+    call("sbgm_final_conv_backward", dsd.data_ptr(), invd.data_ptr(), aa.ptr, aa.plane, fmt, wp.data_ptr(), da.ptr, da.plane,
+         dw.data_ptr(), db.data_ptr(), n, h, w, c, ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rel_l2(da.to_nchw().cpu(), a.grad) < TOL[prec]
+    assert rel_l2(dw.cpu(), wt.grad) < 2e-5 and rel_l2(db.cpu(), bt.grad) < 2e-5
+
+
+def test_time_embed_backward(E):
+    from oracle import score_ref
+    from sbgm_danra_b200 import _lib
+    from sbgm_danra_b200._lib import call
+    te, rows = 256, 5
+    tp = E.TimeProjector(torch.device(DEV), te)
+    W0, W1 = gen(128, seed=1, scale=30.0), gen(128, seed=2, scale=30.0)
+    s0, s1 = tp.add_set(W0.to(DEV)), tp.add_set(W1.to(DEV))
+    heads = [("a", s0, 64), ("b", s1, 128), ("c", s0, 256)]
+    ws = {}
+    for i, (name, s, c) in enumerate(heads):
+        ws[name] = (gen(c, te, seed=10 + i, scale=0.06).requires_grad_(), gen(c, seed=20 + i, scale=0.1).requires_grad_())
+        tp.add_head(name, s, ws[name][0].detach().to(DEV), ws[name][1].detach().to(DEV))
+    lab = gen(5, te, seed=30, scale=0.5).requires_grad_()
+    tp.label_emb = lab.detach().to(DEV)
+    tp.finalize()
+    t = torch.rand(rows, generator=torch.Generator().manual_seed(3))
+    y = torch.tensor([1, 4, 0, 1, 2])
+    dout = gen(rows, tp.c_total, seed=40)
+    outs = []
+    for name, s, c in heads:
+        emb = score_ref.fourier_embed(W0 if s == s0 else W1, t)
+        if s == s0:
+            emb = emb + lab[y]
+        outs.append(F.linear(F.silu(emb), *ws[name]))
+    torch.cat(outs, 1).backward(dout)
+    fw, pw, pb, ps = tp._packed
+    dpw, dpb, dlab = torch.empty_like(pw), torch.empty_like(pb), torch.zeros(5, te, device=DEV)
+    scratch = torch.empty(_lib.query("sbgm_time_embed_backward_scratch_floats", 2, te, rows), device=DEV)
+    td, yd, dd = t.to(DEV), y.to(DEV), dout.to(DEV)
+    call("sbgm_time_embed_backward", dd.data_ptr(), td.data_ptr(), yd.data_ptr(), fw.data_ptr(), 2, te, tp.label_emb.data_ptr(), 5,
+         pw.data_ptr(), ps.data_ptr(), tp.c_total, rows, dpw.data_ptr(), dpb.data_ptr(), dlab.data_ptr(), scratch.data_ptr(),
+         torch.cuda.current_stream().cuda_stream)
+    assert rel_l2(dpw.cpu(), torch.cat([ws[n][0].grad for n, _, _ in heads])) < 2e-5
+    assert rel_l2(dpb.cpu(), torch.cat([ws[n][1].grad for n, _, _ in heads])) < 2e-5
+    assert rel_l2(dlab.cpu(), lab.grad) < 2e-5
+
+
+# ---- whole network: loss + gradients ----------------------------------------------------------------------
+def _dsm_case(precision, mode, size=32, batch=4):
+    from oracle import philox_ref, score_ref
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=2, geo=True, seasons=True)
+    sd = synth_state_dict(cfg)
+    b = synth_batch(batch=batch, size=size, n_lr=2, geo=True, seasons=True)
+    net = build_model(cfg, sd, precision, DEV)
+    net.train(mode == "train")
+    score_sampling.manual_seed(2024)
+    c = lambda v: None if v is None else v.to(DEV)
+    loss = loss_fn(net, c(b.x), marginal_prob_std_fn, y=c(b.y), cond_img=c(b.cond_img), lsm_cond=c(b.lsm_cond),
+                   topo_cond=c(b.topo_cond), sdf_cond=c(b.sdf_cond))
+    loss.backward()
+    # oracle with the same Philox draws
+    sdo = {k: (v.clone().requires_grad_() if v.is_floating_point() and not k.endswith(("running_mean", "running_var", ".W")) else v.clone())
+           for k, v in sd.items()}
+    u = torch.from_numpy(philox_ref.uniform(batch, 2024, philox_ref.DRAW_DSM_T))
+    z = torch.from_numpy(philox_ref.normal(b.x.numel(), 2024, philox_ref.DRAW_DSM_Z)).reshape(b.x.shape)
+    rt = u * (1.0 - 1e-3) + 1e-3
+    lo = score_ref.dsm_loss(sdo, cfg, b.x, rt, z, b.y, b.cond_img, b.lsm_cond, b.topo_cond, b.sdf_cond, bn_train=(mode == "train"))
+    lo.backward()
+    return net, loss, sdo, lo
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_dsm_loss_and_gradients_match_oracle(golden, precision, mode):
+    net, loss, sdo, lo = _dsm_case(precision, mode)
+    ltol = {"fp32": 1e-4, "bf16x3": 1e-3, "bf16": 5e-2}[precision]
+    gtol = {"fp32": 1e-3, "bf16x3": 2e-3, "bf16": 1.5e-1}[precision]
+    assert abs(loss.item() - lo.item()) / abs(lo.item()) < ltol
+    assert abs(loss.item() - float(golden[f"dsm_{mode}/loss"])) / abs(float(golden[f"dsm_{mode}/loss"])) < ltol
+    worst = ("", 0.0)
+    params = dict(net.named_parameters())
+    unused = []
+    for k, v in sdo.items():
+        if not (torch.is_tensor(v) and v.requires_grad):
+            continue
+        if v.grad is None:
+            unused.append(k)
+            assert params[k].grad is None, f"{k} unused by the oracle but has a gradient here"
+            continue
+        assert params[k].grad is not None, f"{k} has no gradient"
+        e = rel_l2(params[k].grad.cpu(), v.grad)
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < gtol, f"{k}: rel-L2 {e:.3e}"
+    print(f"[{precision}/{mode}] loss {loss.item():.6f} vs oracle {lo.item():.6f}; worst grad {worst[0]} {worst[1]:.2e}; unused {len(unused)}")
+    with open(os.path.join(GOLDEN_DIR, "dsm_grad_keys.json")) as f:
+        gkeys = json.load(f)
+    got = np.array([params[k].grad.norm().item() for k in gkeys])
+    assert np.allclose(got, golden[f"dsm_{mode}/grad_norms"], rtol=gtol)
+    assert rel_l2(params["decoder.final_layer.conv.weight"].grad.cpu(), golden[f"dsm_{mode}/grad_final_conv"]) < gtol
+
+
+def test_bn_running_stats_and_training_steps_reduce_loss():
+    """Three Adam steps on a fixed batch: the running statistics move as torch's would and the loss falls."""
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16x3", DEV).train()
+    b = synth_batch(batch=4, size=32, n_lr=1)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    nbt0 = int(net.encoder.bn1.num_batches_tracked)
+    rm0 = net.encoder.bn1.running_mean.clone()
+    losses = []
+    for _ in range(4):
+        score_sampling.manual_seed(11)                 # same (t, z): a deterministic objective
+        opt.zero_grad()
+        loss = loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, cond_img=b.cond_img.to(DEV), sdf_cond=b.sdf_cond.to(DEV))
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert int(net.encoder.bn1.num_batches_tracked) == nbt0 + 4
+    assert not torch.equal(net.encoder.bn1.running_mean, rm0)
+    assert losses[-1] < losses[0], losses
+    assert all(np.isfinite(losses))
