@@ -65,6 +65,11 @@ int sbgm_time_embed_project(const float* t, int t_row_stride, int t_step_stride,
 /* SinusoidalEmbedding.forward alone (score_unet.py:41-45): out[rows][2*half] = cat(sin, cos)(2 pi t W). */
 int sbgm_fourier_embed(const float* t, const float* fourier_w, int half, float* out, int rows, void* stream);
 
+/* im2col of the stem's 8x8 stride-2 pad-3 window: out[n][oy][ox][(c - c_begin) * 64 + r * 8 + s] = in[n][c][2oy+r-3][2ox+s-3]
+ * (0 outside), in = x || planes (channel 0 = x), out NHWC `fmt` with (c_end - c_begin) * 64 channels.  The stem then is a
+ * 1x1 tensor-core convolution over this tensor (sbgm_conv2d_tc / _ex) and its weight gradient sbgm_conv2d_wgrad_tc. */
+int sbgm_stem_im2col(const float* x, const float* planes, int np, int cc, int c_begin, int c_end, void* out, size_t out_plane,
+                     int fmt, int n, int h, int w, void* stream);
 /* ---- stem convolution (Encoder.conv1, score_unet.py:206-211,:312-315) ---------------------
  * 8x8 stride-2 pad-3 convolution over the virtual channel concat  x || planes  (:273-291) for
  * the input-channel range [c_begin, c_end), CUDA cores (K is tiny and the op is bandwidth bound).
@@ -295,11 +300,13 @@ int sbgm_time_embed_backward(const float* dout, const float* t, const int64_t* y
  * data gradient, CUDA cores: weight as fp32 [tap][cout][cin]; `accumulate` adds into dx */
 int sbgm_conv2d_dgrad_simt(const void* dy, size_t dy_plane, const float* weight_tap_co_ci, void* dx, size_t dx_plane, int accumulate,
                            int fmt, int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, void* stream);
-/* data gradient, tensor cores: the forward implicit-GEMM kernel run over dy with flipped / parity-sliced weights;
- * separate paddings, explicit logical output size and scattered store out[n][oy*out_step+out_oy][ox*out_step+out_ox]
- * (`residual`, read at the same positions, accumulates an existing gradient). */
+/* generalised tensor-core convolution (data gradients = the forward implicit-GEMM kernel run over dy with flipped /
+ * parity-sliced weights; ConvTranspose2d decoder; im2col stem): separate paddings, explicit logical output size and
+ * scattered store out[n][oy*out_step+out_oy][ox*out_step+out_ox]; `residual` is read at the same positions
+ * (accumulates an existing gradient) or, with res_pix_mod > 0, broadcast over the batch by pix % res_pix_mod. */
 int sbgm_conv2d_tc_ex(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
-                      const void* residual, size_t res_plane, void* out, size_t out_plane, int fmt, int n, int h,
+                      const void* residual, size_t res_plane, int res_pix_mod, const float* tproj, int tproj_stride,
+                      void* out, size_t out_plane, int fmt, int n, int h,
                       int w, int cin, int cout, int kh, int kw, int stride, int pad_h, int pad_w, int ho, int wo,
                       int out_h, int out_w, int out_step, int out_oy, int out_ox, int act, void* workspace,
                       size_t workspace_bytes, void* stream);
@@ -323,6 +330,12 @@ size_t sbgm_final_conv_backward_scratch_floats(int cin);
 int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const void* a, size_t a_plane, int fmt,
                              const float* weight_tap_ci, void* da, size_t da_plane, float* dweight_oihw, float* dbias, int n, int h,
                              int w, int cin, float* scratch, void* stream);
+/* Pack a torch OIHW fp32 weight for the tensor-core kernels in one launch: out[o][t][i] = w[co][ci][taps_host[t]]
+ * with (o, i) = (co, ci), or (ci, co) when `transpose` (the flipped / parity-sliced data-gradient weights);
+ * K-major bf16 or split-bf16 (planes `out_plane` elements apart).  taps_host is a HOST array of ntaps <= 64
+ * flat tap indices r * kw + s.  A training step re-packs every parameter after each optimizer update. */
+int sbgm_pack_weight(const float* w_oihw, int cout, int cin, int khw, const int* taps_host, int ntaps, int transpose,
+                     void* out, size_t out_plane, int fmt, void* stream);
 /* d loss / d score of sbgm_dsm_loss, times *grad_loss (device scalar; NULL = 1) */
 int sbgm_dsm_loss_backward(const float* score, const float* std, const float* z, const float* sdf, const float* grad_loss, int n,
                            int per_member, float* dscore, void* stream);

@@ -20,6 +20,7 @@ template <int FMT, int DPL, int QPW>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attention_kernel(const void* __restrict__ qkv, size_t plane, void* __restrict__ out, size_t out_plane, int s, int c,
                  int heads, float scale) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) float smem[];
   const int d = c / heads;
   float* ks = smem;                                              // [32][d + 1]
@@ -158,7 +159,7 @@ static int launch_attention(const void* qkv, size_t plane, void* out, size_t out
     }
   }
   dim3 grid(ceil_div(s, kAttnWarps * QPW), heads, b);
-  kern<<<grid, kAttnWarps * 32, smem, st>>>(qkv, plane, out, out_plane, s, c, heads, 1.0f / sqrtf(static_cast<float>(d)));
+  launch_k((kern), grid, kAttnWarps * 32, smem, st, qkv, plane, out, out_plane, s, c, heads, 1.0f / sqrtf(static_cast<float>(d)));
   return check_launch("attention");
 }
 

@@ -14,6 +14,7 @@ template <int FMT>
 __global__ void attn_unpack_kernel(const void* __restrict__ qkv, size_t qkv_plane, const void* __restrict__ dout, size_t dout_plane,
                                    float* __restrict__ q, float* __restrict__ k, float* __restrict__ v, float* __restrict__ go,
                                    int b, int s, int c, int heads) {
+  pdl_grid_sync();
   const int d = c / heads, dvec = d >> 3, cvec = c >> 3;
   const size_t total = static_cast<size_t>(b) * s * cvec;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -41,6 +42,7 @@ __global__ void attn_unpack_kernel(const void* __restrict__ qkv, size_t qkv_plan
 template <int FMT>
 __global__ void attn_pack_kernel(const float* __restrict__ dq, const float* __restrict__ dk, const float* __restrict__ dv,
                                  void* __restrict__ dqkv, size_t plane, int b, int s, int c, int heads) {
+  pdl_grid_sync();
   const int d = c / heads, dvec = d >> 3, cvec = c >> 3;
   const size_t total = static_cast<size_t>(b) * s * cvec;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -67,6 +69,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 bgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, float alpha,
              size_t strideA, size_t strideB, size_t strideC) {
+  pdl_grid_sync();
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const float* a = A + blockIdx.z * strideA;
@@ -118,6 +121,7 @@ bgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
 
 // One warp per row: p <- softmax(p);  ds <- p o (ds - sum(p o ds))   (ds holds dP on entry)
 __global__ void attn_softmax_bwd_kernel(float* __restrict__ p, float* __restrict__ ds, size_t rows, int s) {
+  pdl_grid_sync();
   const size_t row = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -148,7 +152,7 @@ template <bool TA, bool TB>
 static void launch_bgemm(const float* A, const float* B, float* C, int M, int N, int K, float alpha, size_t sA, size_t sB, size_t sC,
                          int batch, cudaStream_t st) {
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
-  bgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, C, M, N, K, alpha, sA, sB, sC);
+  launch_k((bgemm_kernel<TA, TB>), grid, 256, 0, st, A, B, C, M, N, K, alpha, sA, sB, sC);
 }
 
 }  // namespace sbgm
@@ -180,16 +184,16 @@ int sbgm_attention_backward(const void* qkv, size_t qkv_plane, const void* dout,
   const float scale = 1.0f / sqrtf(static_cast<float>(d));
   const size_t items = static_cast<size_t>(b) * s * (c / 8);
   const int g = static_cast<int>(items / 256 + 1 < 148 * 8 ? items / 256 + 1 : 148 * 8);
-  SBGM_DISPATCH_FMT(fmt, (attn_unpack_kernel<FMT><<<g, 256, 0, st>>>(qkv, qkv_plane, dout, dout_plane, q, k, v, go, b, s, c, heads)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((attn_unpack_kernel<FMT>), g, 256, 0, st, qkv, qkv_plane, dout, dout_plane, q, k, v, go, b, s, c, heads)));
   const size_t sd = static_cast<size_t>(s) * d, ss = static_cast<size_t>(s) * s;
   launch_bgemm<false, true>(q, k, p, s, s, d, scale, sd, sd, ss, bh, st);        // S = scale Q K^T
   launch_bgemm<false, true>(go, v, ds, s, s, d, 1.0f, sd, sd, ss, bh, st);       // dP = dO V^T
   const size_t rows = static_cast<size_t>(bh) * s;
-  attn_softmax_bwd_kernel<<<ceil_div(static_cast<long long>(rows) * 32, 256), 256, 0, st>>>(p, ds, rows, s);
+  launch_k((attn_softmax_bwd_kernel), ceil_div(static_cast<long long>(rows) * 32, 256), 256, 0, st, p, ds, rows, s);
   launch_bgemm<true, false>(p, go, dv, s, d, s, 1.0f, ss, sd, sd, bh, st);       // dV = P^T dO
   launch_bgemm<false, false>(ds, k, dq, s, d, s, scale, ss, sd, sd, bh, st);     // dQ = scale dS K
   launch_bgemm<true, false>(ds, q, dk, s, d, s, scale, ss, sd, sd, bh, st);      // dK = scale dS^T Q
-  SBGM_DISPATCH_FMT(fmt, (attn_pack_kernel<FMT><<<g, 256, 0, st>>>(dq, dk, dv, dqkv, dqkv_plane, b, s, c, heads)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((attn_pack_kernel<FMT>), g, 256, 0, st, dq, dk, dv, dqkv, dqkv_plane, b, s, c, heads)));
   return check_launch("attention_backward");
 }
 

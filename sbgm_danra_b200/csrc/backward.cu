@@ -42,6 +42,7 @@ constexpr int kNormChunks = 32;   // must equal kGnChunks of elementwise.cu (the
 // GroupNorm: finish [n][chunks][pgroups][2] partial (sum, sumsq) into stats[n][groups][2] = (mean, rstd).
 __global__ void gn_stats_finalize_kernel(const float* __restrict__ partials, int chunks, int pgroups, int groups, double cnt,
                                          float eps, float* __restrict__ stats) {
+  pdl_grid_sync();
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int sub = pgroups / groups;
@@ -72,6 +73,7 @@ __global__ void gn_stats_finalize_kernel(const float* __restrict__ partials, int
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int n, int chunks, int c, double cnt, float eps,
                                          float momentum, float* __restrict__ stats, float* __restrict__ running_mean,
                                          float* __restrict__ running_var) {
+  pdl_grid_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= c) return;
   double s = 0.0, q = 0.0;
@@ -127,6 +129,7 @@ __device__ __forceinline__ void norm_coefs(const NormArgs& a, int n, int ch0, fl
 
 template <int FMT>
 __global__ void norm_apply_kernel(const NormArgs a, void* __restrict__ y, size_t y_plane) {
+  pdl_grid_sync();
   const int n = blockIdx.y;
   const int vecs = a.c >> 3;
   const size_t total = static_cast<size_t>(a.hw) * vecs;
@@ -158,12 +161,13 @@ __global__ void norm_apply_kernel(const NormArgs a, void* __restrict__ y, size_t
 // ---- normalisation backward ---------------------------------------------------------------------
 // Stage 1: per (n, chunk) per-channel sums of  dY,  dU = dY * act'(u),  dU * xhat.
 template <int FMT>
-__global__ void norm_bwd_partial_kernel(const NormArgs a, const void* __restrict__ dy, size_t dy_plane, float* __restrict__ partials) {
+__global__ void norm_bwd_partial_kernel(const NormArgs a, const void* __restrict__ dy, size_t dy_plane, float* __restrict__ partials, int chunks) {
+  pdl_grid_sync();
   extern __shared__ float red[];  // [lanes][c][3]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int c = a.c, vecs = c >> 3, lanes = blockDim.x / vecs;
   const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
-  const int per_chunk = (a.hw + kNormChunks - 1) / kNormChunks;
+  const int per_chunk = (a.hw + chunks - 1) / chunks;
   const int p_begin = chunk * per_chunk, p_end = min(a.hw, p_begin + per_chunk);
   float s0[8], s1[8], s2[8];
 #pragma unroll
@@ -198,23 +202,21 @@ __global__ void norm_bwd_partial_kernel(const NormArgs a, const void* __restrict
   for (int i = threadIdx.x; i < c * 3; i += blockDim.x) {
     float acc = 0.0f;
     for (int l = 0; l < lanes; ++l) acc += red[static_cast<size_t>(l) * c * 3 + i];
-    partials[(static_cast<size_t>(n) * kNormChunks + chunk) * c * 3 + i] = acc;
+    partials[(static_cast<size_t>(n) * chunks + chunk) * c * 3 + i] = acc;
   }
 }
 
 // Stage 2a: sums[n][c][3] over the chunks; dtproj[n][c].
-__global__ void norm_bwd_reduce_kernel(const float* __restrict__ partials, int c, int tproj_pre, float* __restrict__ sums,
+__global__ void norm_bwd_reduce_kernel(const float* __restrict__ partials, int c, int chunks, int tproj_pre, float* __restrict__ sums,
                                        float* __restrict__ dtproj, int dtproj_stride) {
+  pdl_grid_sync();
   const int n = blockIdx.x;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
-    for (int k = 0; k < kNormChunks; ++k) {
-      const float* p = partials + ((static_cast<size_t>(n) * kNormChunks + k) * c + ch) * 3;
-      s0 += p[0]; s1 += p[1]; s2 += p[2];
-    }
-    float* o = sums + (static_cast<size_t>(n) * c + ch) * 3;
-    o[0] = s0; o[1] = s1; o[2] = s2;
-    if (dtproj) dtproj[static_cast<size_t>(n) * dtproj_stride + ch] = tproj_pre ? s1 : s0;
+  for (int i = threadIdx.x; i < c * 3; i += blockDim.x) {
+    float s = 0.0f;
+    for (int k = 0; k < chunks; ++k) s += partials[(static_cast<size_t>(n) * chunks + k) * c * 3 + i];
+    sums[static_cast<size_t>(n) * c * 3 + i] = s;
+    const int ch = i / 3, which = i - ch * 3;
+    if (dtproj && which == (tproj_pre ? 1 : 0)) dtproj[static_cast<size_t>(n) * dtproj_stride + ch] = s;
   }
 }
 
@@ -223,6 +225,7 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ partials, int c
 __global__ void norm_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ gamma, int n, int c, int n_stride,
                                      int cpg, float inv_cnt, int fixed_stats, float* __restrict__ coef, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c && dgamma) {
     float a = 0.0f, b = 0.0f;
@@ -267,6 +270,7 @@ __global__ void norm_bwd_coef_kernel(const float* __restrict__ sums, const float
 template <int FMT>
 __global__ void norm_bwd_apply_kernel(const NormArgs a, const void* __restrict__ dy, size_t dy_plane, const float* __restrict__ coef,
                                       void* __restrict__ dx, size_t dx_plane, void* __restrict__ dadd, size_t dadd_plane) {
+  pdl_grid_sync();
   const int n = blockIdx.y;
   const int vecs = a.c >> 3;
   const size_t total = static_cast<size_t>(a.hw) * vecs;
@@ -307,6 +311,7 @@ template <int FMT>
 __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, size_t dy_plane, const void* __restrict__ x, size_t x_plane,
                                      const float* __restrict__ gamma, float eps, void* __restrict__ dx, size_t dx_plane,
                                      int rows, int c, float* __restrict__ partials) {
+  pdl_grid_sync();
   extern __shared__ float red[];   // [warps][c][2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int vecs = c >> 3;
@@ -391,20 +396,26 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, size_t dy_plan
 }
 __global__ void layernorm_bwd_finish_kernel(const float* __restrict__ partials, int blocks, int c, float* __restrict__ dgamma,
                                             float* __restrict__ dbeta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_grid_sync();
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (ch >= c) return;
   float a = 0.0f, b = 0.0f;
-  for (int k = 0; k < blocks; ++k) {
+  for (int k = lane; k < blocks; k += 32) {
     a += partials[(static_cast<size_t>(k) * c + ch) * 2];
     b += partials[(static_cast<size_t>(k) * c + ch) * 2 + 1];
   }
-  dgamma[ch] = a;
-  dbeta[ch] = b;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    dgamma[ch] = a;
+    dbeta[ch] = b;
+  }
 }
 
 // ---- elementwise --------------------------------------------------------------------------------
 template <int FMT>
 __global__ void act_fwd_kernel(const void* __restrict__ x, size_t xp, void* __restrict__ y, size_t yp, size_t nvec, int act) {
+  pdl_grid_sync();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float v[8];
     Act<FMT>::load8(x, xp, i * 8, v);
@@ -416,6 +427,7 @@ __global__ void act_fwd_kernel(const void* __restrict__ x, size_t xp, void* __re
 template <int FMT>
 __global__ void act_bwd_kernel(const void* __restrict__ dy, size_t dyp, const void* __restrict__ x, size_t xp, void* __restrict__ dx,
                                size_t dxp, size_t nvec, int act) {
+  pdl_grid_sync();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float v[8], g[8];
     Act<FMT>::load8(x, xp, i * 8, v);
@@ -427,6 +439,7 @@ __global__ void act_bwd_kernel(const void* __restrict__ dy, size_t dyp, const vo
 }
 template <int FMT>
 __global__ void add_inplace_kernel(void* __restrict__ dst, size_t dp, const void* __restrict__ src, size_t sp, size_t nvec) {
+  pdl_grid_sync();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float a[8], b[8];
     Act<FMT>::load8(dst, dp, i * 8, a);
@@ -440,6 +453,7 @@ __global__ void add_inplace_kernel(void* __restrict__ dst, size_t dp, const void
 // per-sample channel sums: out[n][c] = sum over the hw pixels of sample n (two-stage via [n][chunks][c] partials)
 template <int FMT>
 __global__ void chansum_partial_kernel(const void* __restrict__ x, size_t plane, int hw, int c, float* __restrict__ partials) {
+  pdl_grid_sync();
   extern __shared__ float red[];  // [lanes][c]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int vecs = c >> 3, lanes = blockDim.x / vecs;
@@ -464,19 +478,24 @@ __global__ void chansum_partial_kernel(const void* __restrict__ x, size_t plane,
     partials[(static_cast<size_t>(n) * kNormChunks + chunk) * c + i] = acc;
   }
 }
-// out_n[n][c] (nullable) and out_total[c] (nullable)
+// out_n[n][c] (nullable) and out_total[c] (nullable).  One warp per channel: lane <-> chunk (kNormChunks == 32).
 __global__ void chansum_finish_kernel(const float* __restrict__ partials, int n, int c, float* __restrict__ out_n, int out_n_stride,
                                       float* __restrict__ out_total) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_grid_sync();
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (ch >= c) return;
   float tot = 0.0f;
-  for (int k = 0; k < n; ++k) {
-    float s = 0.0f;
-    for (int j = 0; j < kNormChunks; ++j) s += partials[(static_cast<size_t>(k) * kNormChunks + j) * c + ch];
-    if (out_n) out_n[static_cast<size_t>(k) * out_n_stride + ch] = s;
-    tot += s;
+  if (out_n) {
+    for (int k = 0; k < n; ++k) {
+      const float s = warp_sum(partials[(static_cast<size_t>(k) * kNormChunks + lane) * c + ch]);
+      if (lane == 0) out_n[static_cast<size_t>(k) * out_n_stride + ch] = s;
+      tot += s;
+    }
+  } else {
+    for (int k = lane; k < n * kNormChunks; k += 32) tot += partials[static_cast<size_t>(k) * c + ch];
+    tot = warp_sum(tot);
   }
-  if (out_total) out_total[ch] = tot;
+  if (out_total && lane == 0) out_total[ch] = tot;
 }
 
 // ---- bilinear x2 upsample backward (adjoint of upsample2x_kernel) ----------------------------------
@@ -485,6 +504,7 @@ __global__ void chansum_finish_kernel(const float* __restrict__ partials, int n,
 template <int FMT>
 __global__ void upsample2x_bwd_kernel(const void* __restrict__ dy, size_t dy_plane, void* __restrict__ dx, size_t dx_plane,
                                       int n, int h, int w, int c) {
+  pdl_grid_sync();
   const int vecs = c >> 3;
   const size_t total = static_cast<size_t>(n) * h * w * vecs;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -522,6 +542,7 @@ __global__ void upsample2x_bwd_kernel(const void* __restrict__ dy, size_t dy_pla
 // (1) e -> workspace;  (2) dW, db per column;  (3) d(label_emb) through set 0.
 __global__ void time_embed_bwd_embed_kernel(const float* __restrict__ t, const int64_t* __restrict__ y, const float* __restrict__ fw,
                                             int n_sets, int te, const float* __restrict__ label_emb, float* __restrict__ e_ws) {
+  pdl_grid_sync();
   const int row = blockIdx.x, half = te / 2, rows = gridDim.x;
   const float tv = t[row];
   const int64_t lab = y ? y[row] : -1;
@@ -541,6 +562,7 @@ __global__ void time_embed_bwd_embed_kernel(const float* __restrict__ t, const i
 // one block per output column; threads over k
 __global__ void time_embed_bwd_weight_kernel(const float* __restrict__ dout, int c_total, const float* __restrict__ e_ws, int rows, int te,
                                              const int32_t* __restrict__ pset, float* __restrict__ dW, float* __restrict__ db) {
+  pdl_grid_sync();
   const int col = blockIdx.x;
   const float* e = e_ws + static_cast<size_t>(pset[col]) * rows * te;
   for (int k = threadIdx.x; k < te; k += blockDim.x) {
@@ -557,6 +579,7 @@ __global__ void time_embed_bwd_weight_kernel(const float* __restrict__ dout, int
 // de0[row][k] = silu'(e0[row][k]) * sum_{col in set 0} dout[row][col] * W[col][k]
 __global__ void time_embed_bwd_input_kernel(const float* __restrict__ dout, int c_total, const float* __restrict__ e_ws, int te,
                                             const int32_t* __restrict__ pset, const float* __restrict__ pw, float* __restrict__ de0) {
+  pdl_grid_sync();
   const int row = blockIdx.x;
   for (int k = threadIdx.x; k < te; k += blockDim.x) {
     float acc = 0.0f;
@@ -567,6 +590,7 @@ __global__ void time_embed_bwd_input_kernel(const float* __restrict__ dout, int 
 }
 __global__ void label_emb_bwd_kernel(const float* __restrict__ de0, const int64_t* __restrict__ y, int rows, int te,
                                      float* __restrict__ dlabel) {
+  pdl_grid_sync();
   const int cls = blockIdx.x;
   for (int k = threadIdx.x; k < te; k += blockDim.x) {
     float acc = 0.0f;
@@ -580,6 +604,7 @@ __global__ void label_emb_bwd_kernel(const float* __restrict__ de0, const int64_
 __global__ void dsm_loss_bwd_kernel(const float* __restrict__ score, const float* __restrict__ std, const float* __restrict__ z,
                                     const float* __restrict__ sdf, const float* __restrict__ grad_loss, size_t nq, int per_member_q,
                                     float inv_n, float* __restrict__ dscore) {
+  pdl_grid_sync();
   const float gl = grad_loss ? *grad_loss : 1.0f;
   for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq; q += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float sd = std[q / per_member_q];
@@ -616,13 +641,13 @@ extern "C" {
 int sbgm_gn_stats_finalize(const float* partials, int chunks, int pgroups, int groups, int n, int hw, int c, float eps,
                            float* stats, void* stream) {
   SBGM_REQUIRE(groups >= 1 && pgroups >= groups && pgroups % groups == 0 && c % groups == 0, "gn_stats_finalize: bad groups=%d pgroups=%d c=%d", groups, pgroups, c);
-  gn_stats_finalize_kernel<<<n, 256, 0, as_stream(stream)>>>(partials, chunks, pgroups, groups, static_cast<double>(hw) * (c / groups), eps, stats);
+  launch_k((gn_stats_finalize_kernel), n, 256, 0, as_stream(stream), partials, chunks, pgroups, groups, static_cast<double>(hw) * (c / groups), eps, stats);
   return check_launch("gn_stats_finalize");
 }
 
 int sbgm_bn_stats_finalize(const float* partials, int chunks, int n, int hw, int c, float eps, float momentum, float* stats,
                            float* running_mean, float* running_var, void* stream) {
-  bn_stats_finalize_kernel<<<ceil_div(static_cast<long long>(c) * 32, 256), 256, 0, as_stream(stream)>>>(
+  launch_k((bn_stats_finalize_kernel), ceil_div(static_cast<long long>(c) * 32, 256), 256, 0, as_stream(stream), 
       partials, n, chunks, c, static_cast<double>(n) * hw, eps, momentum, stats, running_mean, running_var);
   return check_launch("bn_stats_finalize");
 }
@@ -637,7 +662,7 @@ int sbgm_norm_apply(const void* x, size_t x_plane, const float* stats, int per_s
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
   SBGM_REQUIRE(vecs <= 256, "norm_apply: c too large");
   dim3 grid(per_n_blocks, n);
-  SBGM_DISPATCH_FMT(fmt, (norm_apply_kernel<FMT><<<grid, 256, 0, as_stream(stream)>>>(a, y, y_plane)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((norm_apply_kernel<FMT>), grid, 256, 0, as_stream(stream), a, y, y_plane)));
   return check_launch("norm_apply");
 }
 
@@ -664,13 +689,15 @@ int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_
   const int n_groups_total = per_sample_stats == 1 ? n * groups : c;
   const double cnt = per_sample_stats == 1 ? static_cast<double>(hw) * (c / groups) : static_cast<double>(n) * hw;
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
-  dim3 g1(kNormChunks, n), g3(per_n_blocks, n);
+  // enough pixels per thread to amortise the per-block prologue: ~8 per lane
+  const int chunks = max(1, min(kNormChunks, hw / (lanes * 8)));
+  dim3 g1(chunks, n), g3(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
-    norm_bwd_partial_kernel<FMT><<<g1, 256, smem1, st>>>(a, dy, dy_plane, partials);
-    norm_bwd_reduce_kernel<<<n, 256, 0, st>>>(partials, c, tproj_pre_act, sums, dtproj, dtproj_stride);
-    norm_bwd_coef_kernel<<<ceil_div(max(c, n_groups_total), 256), 256, 0, st>>>(sums, gamma, n, c, a.n_stride, a.cpg,
+    launch_k((norm_bwd_partial_kernel<FMT>), g1, 256, smem1, st, a, dy, dy_plane, partials, chunks);
+    launch_k((norm_bwd_reduce_kernel), n, 256, 0, st, partials, c, chunks, tproj_pre_act, sums, dtproj, dtproj_stride);
+    launch_k((norm_bwd_coef_kernel), ceil_div(max(c, n_groups_total), 256), 256, 0, st, sums, gamma, n, c, a.n_stride, a.cpg,
                                                                                 static_cast<float>(1.0 / cnt), per_sample_stats == 2, coef, dgamma, dbeta);
-    norm_bwd_apply_kernel<FMT><<<g3, 256, 0, st>>>(a, dy, dy_plane, coef, dx, dx_plane, dadd, dadd_plane);
+    launch_k((norm_bwd_apply_kernel<FMT>), g3, 256, 0, st, a, dy, dy_plane, coef, dx, dx_plane, dadd, dadd_plane);
   });
   return check_launch("norm_backward");
 }
@@ -684,26 +711,26 @@ int sbgm_layernorm_backward(const void* dy, size_t dy_plane, const void* x, size
   cudaStream_t st = as_stream(stream);
   const int blocks = min(kLnBwdBlocks, ceil_div(rows, 8));
   const size_t smem = static_cast<size_t>(8) * c * 2 * sizeof(float);
-  SBGM_DISPATCH_FMT(fmt, (layernorm_bwd_kernel<FMT><<<blocks, 256, smem, st>>>(dy, dy_plane, x, x_plane, gamma, eps, dx, dx_plane,
+  SBGM_DISPATCH_FMT(fmt, (launch_k((layernorm_bwd_kernel<FMT>), blocks, 256, smem, st, dy, dy_plane, x, x_plane, gamma, eps, dx, dx_plane,
                                                                                 rows, c, scratch)));
-  layernorm_bwd_finish_kernel<<<ceil_div(c, 128), 128, 0, st>>>(scratch, blocks, c, dgamma, dbeta);
+  launch_k((layernorm_bwd_finish_kernel), ceil_div(c, 8), 256, 0, st, scratch, blocks, c, dgamma, dbeta);
   return check_launch("layernorm_backward");
 }
 
 int sbgm_act_forward(const void* x, size_t x_plane, void* y, size_t y_plane, int fmt, size_t count, int act, void* stream) {
   SBGM_REQUIRE(count % 8 == 0, "act_forward: count must be a multiple of 8");
-  SBGM_DISPATCH_FMT(fmt, (act_fwd_kernel<FMT><<<bgrid_for(count / 8, 256), 256, 0, as_stream(stream)>>>(x, x_plane, y, y_plane, count / 8, act)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((act_fwd_kernel<FMT>), bgrid_for(count / 8, 256), 256, 0, as_stream(stream), x, x_plane, y, y_plane, count / 8, act)));
   return check_launch("act_forward");
 }
 int sbgm_act_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, void* dx, size_t dx_plane, int fmt,
                       size_t count, int act, void* stream) {
   SBGM_REQUIRE(count % 8 == 0, "act_backward: count must be a multiple of 8");
-  SBGM_DISPATCH_FMT(fmt, (act_bwd_kernel<FMT><<<bgrid_for(count / 8, 256), 256, 0, as_stream(stream)>>>(dy, dy_plane, x, x_plane, dx, dx_plane, count / 8, act)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((act_bwd_kernel<FMT>), bgrid_for(count / 8, 256), 256, 0, as_stream(stream), dy, dy_plane, x, x_plane, dx, dx_plane, count / 8, act)));
   return check_launch("act_backward");
 }
 int sbgm_add_inplace(void* dst, size_t dst_plane, const void* src, size_t src_plane, int fmt, size_t count, void* stream) {
   SBGM_REQUIRE(count % 8 == 0, "add_inplace: count must be a multiple of 8");
-  SBGM_DISPATCH_FMT(fmt, (add_inplace_kernel<FMT><<<bgrid_for(count / 8, 256), 256, 0, as_stream(stream)>>>(dst, dst_plane, src, src_plane, count / 8)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((add_inplace_kernel<FMT>), bgrid_for(count / 8, 256), 256, 0, as_stream(stream), dst, dst_plane, src, src_plane, count / 8)));
   return check_launch("add_inplace");
 }
 
@@ -715,8 +742,8 @@ int sbgm_channel_sums(const void* x, size_t x_plane, int fmt, int n, int hw, int
   const int vecs = c / 8, lanes = 256 / vecs;
   cudaStream_t st = as_stream(stream);
   dim3 g1(kNormChunks, n);
-  SBGM_DISPATCH_FMT(fmt, (chansum_partial_kernel<FMT><<<g1, 256, static_cast<size_t>(lanes) * c * sizeof(float), st>>>(x, x_plane, hw, c, scratch)));
-  chansum_finish_kernel<<<ceil_div(c, 128), 128, 0, st>>>(scratch, n, c, out_per_sample, out_stride, out_total);
+  SBGM_DISPATCH_FMT(fmt, (launch_k((chansum_partial_kernel<FMT>), g1, 256, static_cast<size_t>(lanes) * c * sizeof(float), st, x, x_plane, hw, c, scratch)));
+  launch_k((chansum_finish_kernel), ceil_div(c, 8), 256, 0, st, scratch, n, c, out_per_sample, out_stride, out_total);
   return check_launch("channel_sums");
 }
 
@@ -724,7 +751,7 @@ int sbgm_upsample2x_backward(const void* dy, size_t dy_plane, void* dx, size_t d
                              void* stream) {
   SBGM_REQUIRE(c % 8 == 0, "upsample2x_backward: c=%d must be a multiple of 8", c);
   const size_t total = static_cast<size_t>(n) * h * w * (c / 8);
-  SBGM_DISPATCH_FMT(fmt, (upsample2x_bwd_kernel<FMT><<<bgrid_for(total, 256), 256, 0, as_stream(stream)>>>(dy, dy_plane, dx, dx_plane, n, h, w, c)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((upsample2x_bwd_kernel<FMT>), bgrid_for(total, 256), 256, 0, as_stream(stream), dy, dy_plane, dx, dx_plane, n, h, w, c)));
   return check_launch("upsample2x_backward");
 }
 
@@ -739,11 +766,11 @@ int sbgm_time_embed_backward(const float* dout, const float* t, const int64_t* y
   cudaStream_t st = as_stream(stream);
   float* e_ws = scratch;
   float* de0 = scratch + static_cast<size_t>(n_sets) * rows * te;
-  time_embed_bwd_embed_kernel<<<rows, 256, 0, st>>>(t, y, fourier_w, n_sets, te, label_emb, e_ws);
-  time_embed_bwd_weight_kernel<<<c_total, 256, 0, st>>>(dout, c_total, e_ws, rows, te, proj_set, d_proj_w, d_proj_b);
+  launch_k((time_embed_bwd_embed_kernel), rows, 256, 0, st, t, y, fourier_w, n_sets, te, label_emb, e_ws);
+  launch_k((time_embed_bwd_weight_kernel), c_total, 256, 0, st, dout, c_total, e_ws, rows, te, proj_set, d_proj_w, d_proj_b);
   if (d_label_emb != nullptr && y != nullptr) {
-    time_embed_bwd_input_kernel<<<rows, 256, 0, st>>>(dout, c_total, e_ws, te, proj_set, proj_w, de0);
-    label_emb_bwd_kernel<<<n_classes, 256, 0, st>>>(de0, y, rows, te, d_label_emb);
+    launch_k((time_embed_bwd_input_kernel), rows, 256, 0, st, dout, c_total, e_ws, te, proj_set, proj_w, de0);
+    launch_k((label_emb_bwd_kernel), n_classes, 256, 0, st, de0, y, rows, te, d_label_emb);
   }
   return check_launch("time_embed_backward");
 }
@@ -752,7 +779,7 @@ int sbgm_dsm_loss_backward(const float* score, const float* std, const float* z,
                            int per_member, float* dscore, void* stream) {
   SBGM_REQUIRE(per_member % 4 == 0, "dsm_loss_backward: per_member must be a multiple of 4");
   const size_t nq = static_cast<size_t>(n) * per_member / 4;
-  dsm_loss_bwd_kernel<<<bgrid_for(nq, 256), 256, 0, as_stream(stream)>>>(score, std, z, sdf, grad_loss, nq, per_member / 4,
+  launch_k((dsm_loss_bwd_kernel), bgrid_for(nq, 256), 256, 0, as_stream(stream), score, std, z, sdf, grad_loss, nq, per_member / 4,
                                                                          1.0f / static_cast<float>(n), dscore);
   return check_launch("dsm_loss_backward");
 }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/sbgm_b200.h"
 
@@ -22,6 +23,39 @@ int check_launch(const char* what);   // cudaGetLastError -> status
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- launches: programmatic dependent launch (PDL) ------------------------------------------------------
+// A sampler step is ~150 and a training step ~1 500 short kernels back to back on one stream (replayed from a
+// CUDA graph).  Every kernel is launched with programmatic stream serialization and starts with pdl_grid_sync():
+// it releases its own dependents at once and then waits for its predecessor to complete and flush, so the next
+// kernel's blocks are scheduled (and its launch latency paid) while the previous grid drains.  Semantics are those
+// of an ordinary in-order stream because no kernel touches global memory before the wait.
+// SBGM_B200_PDL=0 disables the attribute (the device-side instructions are then no-ops).
+void note_launch_error(cudaError_t e);
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) note_launch_error(e);
+}
+#endif
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 // ---- activation formats ---------------------------------------------------------------------

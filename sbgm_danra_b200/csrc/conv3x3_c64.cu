@@ -36,9 +36,10 @@ struct C64Cfg {
   static constexpr uint32_t kSmemBytes = kBarOffset + 128 + 1024;
 };
 
-template <int FMT, int kStages, int ACT, bool PROJ>
+template <int FMT, int kStages, int ACT, int PROJ>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const C64Params p) {
+  pdl_grid_sync();
   using Cfg = C64Cfg<FMT, kStages>;
   constexpr int kSplit = Cfg::kSplit;
   extern __shared__ uint8_t smem_raw[];
@@ -182,7 +183,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 2 * kAccCols);
 }
 
-template <int FMT, int kStages, int ACT, bool PROJ>
+template <int FMT, int kStages, int ACT, int PROJ>
 static int launch_c64_inst(const CUtensorMap& ta, const CUtensorMap& tb, const C64Params& p, cudaStream_t st) {
   using Cfg = C64Cfg<FMT, kStages>;
   auto kern = conv3x3_c64_kernel<FMT, kStages, ACT, PROJ>;
@@ -203,13 +204,14 @@ static int launch_c64_inst(const CUtensorMap& ta, const CUtensorMap& tb, const C
     return 1;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  launch_k((kern), grid, 192, Cfg::kSmemBytes, st, ta, tb, p);
   return check_launch("conv3x3_c64");
 }
 
 template <int FMT, int kStages>
 static int launch_c64(const CUtensorMap& ta, const CUtensorMap& tb, const C64Params& p, cudaStream_t st) {
-  if (p.ep.proj_w) return launch_c64_inst<FMT, kStages, SBGM_ACT_NONE, true>(ta, tb, p, st);
+  if (p.ep.proj_w) return p.ep.out ? launch_c64_inst<FMT, kStages, SBGM_ACT_NONE, 2>(ta, tb, p, st)
+                                   : launch_c64_inst<FMT, kStages, SBGM_ACT_NONE, 1>(ta, tb, p, st);
   if (p.ep.act == SBGM_ACT_NONE) return launch_c64_inst<FMT, kStages, SBGM_ACT_NONE, false>(ta, tb, p, st);
   if (p.ep.act == SBGM_ACT_RELU) return launch_c64_inst<FMT, kStages, SBGM_ACT_RELU, false>(ta, tb, p, st);
   set_error("conv3x3_c64: activation %d not instantiated (none / relu only)", p.ep.act);
@@ -236,7 +238,7 @@ extern "C" int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* wei
   C64Params p;
   p.n = n; p.h = h; p.w = w;
   p.tiles_w = w / kTW; p.tiles_h = h / kTH; p.total_tiles = p.tiles_w * p.tiles_h * n;
-  p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
+  p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.res_pix_mod = 0; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
   p.ep.act = act; p.ep.cout = 64; p.ep.out = out; p.ep.out_plane = out_plane;
   p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
   p.gn_partials = gn_partials;

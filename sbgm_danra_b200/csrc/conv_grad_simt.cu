@@ -14,6 +14,7 @@ template <int FMT>
 __global__ void dgrad_simt_kernel(const void* __restrict__ dy, size_t dy_plane, const float* __restrict__ wgt, void* __restrict__ dx,
                                   size_t dx_plane, int accumulate, int n, int h, int w, int cin, int cout, int kh, int kw,
                                   int stride, int pad, int ho, int wo) {
+  pdl_grid_sync();
   const int vecs = cin >> 3;
   const size_t total = static_cast<size_t>(n) * h * w * vecs;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256)
 wgrad_simt_kernel(const void* __restrict__ x, size_t x_plane, const void* __restrict__ dy, size_t dy_plane, float* __restrict__ ws,
                   int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, int ho, int wo, int ci_blocks,
                   int pix_per_split) {
+  pdl_grid_sync();
   __shared__ float xs[16][64];
   __shared__ float ds[16][64];
   const int cib = blockIdx.x % ci_blocks, cob = blockIdx.x / ci_blocks;
@@ -126,6 +128,7 @@ wgrad_simt_kernel(const void* __restrict__ x, size_t x_plane, const void* __rest
 
 // Sum the split partials in a fixed order and emit torch's OIHW layout: out[co][ci][tap].
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int taps, int cin, float* __restrict__ out) {
+  pdl_grid_sync();
   const size_t K = static_cast<size_t>(taps) * cin;
   const size_t total = static_cast<size_t>(cout) * K;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -145,6 +148,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ planes, int np, int cc, const void* __restrict__ df, size_t df_plane,
                   float* __restrict__ ws, int n, int h, int w) {
+  pdl_grid_sync();
   __shared__ float patch[8][64];
   __shared__ float g[8][64];
   const int chunk = blockIdx.x, ci = blockIdx.y;
@@ -201,6 +205,7 @@ stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ planes,
     for (int j = 0; j < 4; ++j) dst[(ty * 4 + i) * 64 + tx * 4 + j] = acc[i][j];
 }
 __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ ws, int cin, float* __restrict__ out) {
+  pdl_grid_sync();
   const int total = cin * 64 * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i & 63, tap = (i >> 6) & 63, ci = i >> 12;
@@ -215,6 +220,7 @@ __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ ws, int cin, 
 template <int FMT>
 __global__ void final_conv_bwd_input_kernel(const float* __restrict__ dscore, const float* __restrict__ inv_std, const float* __restrict__ wgt,
                                             void* __restrict__ da, size_t da_plane, int n, int h, int w, int cin) {
+  pdl_grid_sync();
   extern __shared__ float wsm[];  // [9][cin]
   for (int i = threadIdx.x; i < 9 * cin; i += blockDim.x) wsm[i] = wgt[i];
   __syncthreads();
@@ -252,6 +258,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 final_conv_bwd_weight_kernel(const float* __restrict__ dscore, const float* __restrict__ inv_std, const void* __restrict__ a, size_t a_plane,
                              float* __restrict__ partials, int n, int h, int w, int cin) {
+  pdl_grid_sync();
   extern __shared__ float red[];   // [lanes][9 * cin + 1]
   const int vecs = cin >> 3, lanes = blockDim.x / vecs;
   const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
@@ -299,6 +306,7 @@ final_conv_bwd_weight_kernel(const float* __restrict__ dscore, const float* __re
   }
 }
 __global__ void final_conv_bwd_finish_kernel(const float* __restrict__ partials, int blocks, int cin, float* __restrict__ dW, float* __restrict__ db) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > 9 * cin) return;
   float s = 0.0f;
@@ -342,7 +350,7 @@ int sbgm_conv2d_dgrad_simt(const void* dy, size_t dy_plane, const float* weight_
   const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
   SBGM_REQUIRE(ho > 0 && wo > 0, "conv2d_dgrad_simt: empty output");
   const size_t total = static_cast<size_t>(n) * h * w * (cin / 8);
-  SBGM_DISPATCH_FMT(fmt, (dgrad_simt_kernel<FMT><<<cgrid_for(total, 128, 148 * 32), 128, 0, as_stream(stream)>>>(
+  SBGM_DISPATCH_FMT(fmt, (launch_k((dgrad_simt_kernel<FMT>), cgrid_for(total, 128, 148 * 32), 128, 0, as_stream(stream), 
                              dy, dy_plane, weight_tap_co_ci, dx, dx_plane, accumulate, n, h, w, cin, cout, kh, kw, stride, pad, ho, wo)));
   return check_launch("conv2d_dgrad_simt");
 }
@@ -363,16 +371,16 @@ int sbgm_conv2d_wgrad_simt(const void* x, size_t x_plane, const void* dy, size_t
   wgrad_simt_plan(n, ho, wo, cin, cout, kh * kw, &cib, &cob, &splits, &per);
   cudaStream_t st = as_stream(stream);
   dim3 grid(cib * cob, kh * kw, splits);
-  SBGM_DISPATCH_FMT(fmt, (wgrad_simt_kernel<FMT><<<grid, 256, 0, st>>>(x, x_plane, dy, dy_plane, workspace, n, h, w, cin, cout, kh, kw,
+  SBGM_DISPATCH_FMT(fmt, (launch_k((wgrad_simt_kernel<FMT>), grid, 256, 0, st, x, x_plane, dy, dy_plane, workspace, n, h, w, cin, cout, kh, kw,
                                                                         stride, pad, ho, wo, cib, per)));
   const size_t total = static_cast<size_t>(cout) * kh * kw * cin;
-  wgrad_reduce_kernel<<<cgrid_for(total, 256), 256, 0, st>>>(workspace, splits, cout, kh * kw, cin, dweight_oihw);
+  launch_k((wgrad_reduce_kernel), cgrid_for(total, 256), 256, 0, st, workspace, splits, cout, kh * kw, cin, dweight_oihw);
   return check_launch("conv2d_wgrad_simt");
 }
 
 int sbgm_wgrad_reduce(const float* workspace, int splits, int cout, int taps, int cin, float* dweight_oihw, void* stream) {
   const size_t total = static_cast<size_t>(cout) * taps * cin;
-  wgrad_reduce_kernel<<<cgrid_for(total, 256), 256, 0, as_stream(stream)>>>(workspace, splits, cout, taps, cin, dweight_oihw);
+  launch_k((wgrad_reduce_kernel), cgrid_for(total, 256), 256, 0, as_stream(stream), workspace, splits, cout, taps, cin, dweight_oihw);
   return check_launch("wgrad_reduce");
 }
 
@@ -386,8 +394,8 @@ int sbgm_stem_wgrad(const float* x, const float* planes, int np, int cc, const v
   cudaStream_t st = as_stream(stream);
   const int cin = cc + 1;
   dim3 grid(kStemChunks, cin);
-  SBGM_DISPATCH_FMT(fmt, (stem_wgrad_kernel<FMT><<<grid, 256, 0, st>>>(x, planes, np, cc, df, df_plane, workspace, n, h, w)));
-  stem_wgrad_reduce_kernel<<<cgrid_for(static_cast<size_t>(cin) * 4096, 256), 256, 0, st>>>(workspace, cin, dweight_oihw);
+  SBGM_DISPATCH_FMT(fmt, (launch_k((stem_wgrad_kernel<FMT>), grid, 256, 0, st, x, planes, np, cc, df, df_plane, workspace, n, h, w)));
+  launch_k((stem_wgrad_reduce_kernel), cgrid_for(static_cast<size_t>(cin) * 4096, 256), 256, 0, st, workspace, cin, dweight_oihw);
   return check_launch("stem_wgrad");
 }
 
@@ -407,10 +415,10 @@ int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const vo
       set_error("final_conv_backward: cannot reserve %zu bytes of shared memory", smem_w);
       return 1;
     }
-    final_conv_bwd_input_kernel<FMT><<<cgrid_for(total, 256), 256, 9 * cin * sizeof(float), st>>>(dscore, inv_std, weight_tap_ci, da, da_plane, n, h, w, cin);
-    kw_<<<kFinalBwdBlocks, 256, smem_w, st>>>(dscore, inv_std, a, a_plane, scratch, n, h, w, cin);
+    launch_k((final_conv_bwd_input_kernel<FMT>), cgrid_for(total, 256), 256, 9 * cin * sizeof(float), st, dscore, inv_std, weight_tap_ci, da, da_plane, n, h, w, cin);
+    launch_k((kw_), kFinalBwdBlocks, 256, smem_w, st, dscore, inv_std, a, a_plane, scratch, n, h, w, cin);
   });
-  final_conv_bwd_finish_kernel<<<ceil_div(9 * cin + 1, 128), 128, 0, st>>>(scratch, kFinalBwdBlocks, cin, dweight_oihw, dbias);
+  launch_k((final_conv_bwd_finish_kernel), ceil_div(9 * cin + 1, 128), 128, 0, st, scratch, kFinalBwdBlocks, cin, dweight_oihw, dbias);
   return check_launch("final_conv_backward");
 }
 

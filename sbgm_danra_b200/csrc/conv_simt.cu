@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ planes, int np, int cc, int c_begin, int c_end,
                  const float* __restrict__ wp, const float* __restrict__ addend, int na, const float* __restrict__ tproj,
                  int tproj_stride, void* __restrict__ out, size_t out_plane, int h, int w) {
+  pdl_grid_sync();
   __shared__ float s_in[kStemInH][kStemInW + 1];
   __shared__ __align__(16) float s_w[64][64];    // [tap][co]
   const int n = blockIdx.z, ho = h / 2, wo = w / 2;
@@ -90,6 +91,7 @@ conv_simt_kernel(const float* __restrict__ in, const float* __restrict__ wgt, co
                  const float* __restrict__ residual, const float* __restrict__ tproj, int tproj_stride,
                  float* __restrict__ out, int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad,
                  int ho, int wo, int act) {
+  pdl_grid_sync();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN];
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -176,7 +178,7 @@ int sbgm_stem_conv(const float* x, const float* planes, int np, int cc, int c_be
   SBGM_REQUIRE(c_begin >= 0 && c_end <= cc + 1 && c_begin <= c_end, "stem_conv: bad channel range [%d,%d) of %d", c_begin, c_end, cc + 1);
   SBGM_REQUIRE(c_begin > 0 || x != nullptr || c_end == 0, "stem_conv: x is NULL but channel 0 requested");
   dim3 grid(ceil_div(w / 2, kStemTW), ceil_div(h / 2, kStemTH), n);
-  SBGM_DISPATCH_FMT(fmt, (stem_conv_kernel<FMT><<<grid, 256, 0, as_stream(stream)>>>(
+  SBGM_DISPATCH_FMT(fmt, (launch_k((stem_conv_kernel<FMT>), grid, 256, 0, as_stream(stream), 
                              x, planes, np, cc, c_begin, c_end, w_packed, addend, na, tproj, tproj_stride, out,
                              out_plane, h, w)));
   return check_launch("stem_conv");
@@ -189,7 +191,7 @@ int sbgm_conv2d_simt(const float* in, const float* weight, const float* bias, co
   const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
   SBGM_REQUIRE(ho > 0 && wo > 0, "conv2d_simt: empty output");
   dim3 grid(ceil_div(static_cast<long long>(n) * ho * wo, BM), cout / BN);
-  conv_simt_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, weight, bias, residual, tproj, tproj_stride, out, n, h, w,
+  launch_k((conv_simt_kernel), grid, 256, 0, as_stream(stream), in, weight, bias, residual, tproj, tproj_stride, out, n, h, w,
                                                         cin, cout, kh, kw, stride, pad, ho, wo, act);
   return check_launch("conv2d_simt");
 }

@@ -46,9 +46,10 @@ struct ConvTcCfg {
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, bool PROJ>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ>
 __global__ void __launch_bounds__(192, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
+  pdl_grid_sync();
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   using Cfg = ConvTcCfg<kSplit, BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
@@ -205,6 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // Sum the split-K partial tiles in a fixed order (deterministic) and apply the fused epilogue.
 template <int FMT, int ACT>
 __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits, size_t pixels, int hw, EpilogueParams ep) {
+  pdl_grid_sync();
   const int vecs = ep.cout >> 3;
   const size_t total = pixels * vecs;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -223,7 +225,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits,
     }
     if (ep.residual) {
       float rv[8];
-      Act<FMT>::load8(ep.residual, ep.res_plane, pix * ep.cout + co, rv);
+      Act<FMT>::load8(ep.residual, ep.res_plane, (ep.res_pix_mod ? pix % ep.res_pix_mod : pix) * ep.cout + co, rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += rv[j];
     }
@@ -304,7 +306,7 @@ void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
   (void)pow2_floor;
 }
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, bool PROJ>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ>
 static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTcParams& p, int m_tiles, cudaStream_t st) {
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   using Cfg = ConvTcCfg<kSplit, BLOCK_N, kStages>;
@@ -322,12 +324,12 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
     return 1;
   }
   dim3 grid(m_tiles, p.ep.cout / BLOCK_N, p.splits);
-  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  launch_k((kern), grid, 192, Cfg::kSmemBytes, st, ta, tb, p);
   if (!PROJ && p.splits > 1) {
     const size_t pixels = static_cast<size_t>(p.n) * p.ho * p.wo;
     const size_t items = pixels * (p.ep.cout / 8);
     const int fgrid = static_cast<int>(items / 256 + 1 < 148 * 8 ? items / 256 + 1 : 148 * 8);
-    splitk_finalize_kernel<FMT, ACT><<<fgrid, 256, 0, st>>>(p.ws, p.splits, pixels, p.ho * p.wo, p.ep);
+    launch_k((splitk_finalize_kernel<FMT, ACT>), fgrid, 256, 0, st, p.ws, p.splits, pixels, p.ho * p.wo, p.ep);
   }
   return check_launch("conv2d_tc");
 }
@@ -399,7 +401,7 @@ extern "C" size_t sbgm_conv2d_tc_workspace_bytes(int fmt, int n, int h, int w, i
 }
 
 struct ConvTcEx {      // optional generalisation used by the data-gradient path (all zero = plain convolution)
-  int pad_h, pad_w, ho, wo, out_h, out_w, out_step, out_oy, out_ox;
+  int pad_h, pad_w, ho, wo, out_h, out_w, out_step, out_oy, out_ox, res_pix_mod;
   bool on;
 };
 
@@ -439,7 +441,7 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
   SBGM_REQUIRE(gn_partials == nullptr || (p.gn_chunks > 0 && residual == nullptr && tproj == nullptr && act == SBGM_ACT_NONE &&
                                           proj_w == nullptr),
                "conv2d_tc: this shape / epilogue cannot fuse GroupNorm statistics (query sbgm_conv2d_tc_gn_chunks first)");
-  p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
+  p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.res_pix_mod = ex.on ? ex.res_pix_mod : 0; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
   p.ep.act = act; p.ep.cout = cout; p.ep.out = out; p.ep.out_plane = out_plane;
   p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
   SBGM_REQUIRE(p.w_tile * stride <= 256 && p.h_tile * stride <= 256, "conv2d_tc: TMA box too large for stride %d", stride);
@@ -469,15 +471,17 @@ extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weigh
                         cin, cout, kh, kw, stride, pad, act, proj_w, n_proj, proj_out, workspace, workspace_bytes, gn_partials, ex, stream);
 }
 
-// Generalised form used by the data gradients: separate vertical / horizontal padding, an explicit logical output
-// size (ho, wo) and a scattered store  out[n][oy * out_step + out_oy][ox * out_step + out_ox]  into an
-// [n][out_h][out_w][cout] tensor (`residual`, if given, is read at the same scattered positions).
+// Generalised form used by the data gradients, the transposed-convolution decoder and the im2col stem: separate
+// vertical / horizontal padding, an explicit logical output size (ho, wo), a scattered store
+// out[n][oy * out_step + out_oy][ox * out_step + out_ox] into an [n][out_h][out_w][cout] tensor (`residual`, if given,
+// is read at the same positions; res_pix_mod > 0 broadcasts a one-image residual over the batch).
 extern "C" int sbgm_conv2d_tc_ex(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
-                                 const void* residual, size_t res_plane, void* out, size_t out_plane, int fmt, int n, int h,
+                                 const void* residual, size_t res_plane, int res_pix_mod, const float* tproj, int tproj_stride,
+                                 void* out, size_t out_plane, int fmt, int n, int h,
                                  int w, int cin, int cout, int kh, int kw, int stride, int pad_h, int pad_w, int ho, int wo,
                                  int out_h, int out_w, int out_step, int out_oy, int out_ox, int act, void* workspace,
                                  size_t workspace_bytes, void* stream) {
-  ConvTcEx ex = {pad_h, pad_w, ho, wo, out_h, out_w, out_step, out_oy, out_ox, true};
-  return conv2d_tc_impl(in, in_plane, weight, w_plane, bias, residual, res_plane, nullptr, 0, out, out_plane, fmt, n, h, w, cin, cout,
-                        kh, kw, stride, pad_h, act, nullptr, 0, nullptr, workspace, workspace_bytes, nullptr, ex, stream);
+  ConvTcEx ex = {pad_h, pad_w, ho, wo, out_h, out_w, out_step, out_oy, out_ox, res_pix_mod, true};
+  return conv2d_tc_impl(in, in_plane, weight, w_plane, bias, residual, res_plane, tproj, tproj_stride, out, out_plane, fmt, n, h, w, cin,
+                        cout, kh, kw, stride, pad_h, act, nullptr, 0, nullptr, workspace, workspace_bytes, nullptr, ex, stream);
 }

@@ -45,6 +45,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_mn(int n) { return make
 template <int FMT, int BN, int kStages>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const WgradParams p) {
+  pdl_grid_sync();
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   using Cfg = WgradCfg<kSplit, BN, kStages>;
   extern __shared__ uint8_t smem_raw[];
@@ -200,7 +201,7 @@ static int launch_wgrad_tc(const CUtensorMap& tx, const CUtensorMap& td, const W
     configured = true;
   }
   dim3 grid((p.units + 1) / 2, p.cout / BN, splits);
-  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tx, td, p);
+  launch_k((kern), grid, 192, Cfg::kSmemBytes, st, tx, td, p);
   return check_launch("conv2d_wgrad_tc");
 }
 

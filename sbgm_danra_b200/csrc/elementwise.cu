@@ -15,8 +15,20 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static thread_local cudaError_t g_launch_err = cudaSuccess;
+void note_launch_error(cudaError_t e) { g_launch_err = e; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SBGM_B200_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && g_launch_err != cudaSuccess) e = g_launch_err;
+  g_launch_err = cudaSuccess;
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return 2;
@@ -28,6 +40,7 @@ int check_launch(const char* what) {
 // NCHW fp32 -> NHWC fmt via a 32(pixels) x 8k(channels) smem transpose.
 template <int FMT>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, size_t plane, int c, int hw) {
+  pdl_grid_sync();
   // block: 32 pixels x 64 channels tile; grid (hw/32, c/64 (ceil), n)
   __shared__ float tile[64][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
@@ -50,6 +63,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restr
 
 template <int FMT>
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ src, size_t plane, float* __restrict__ dst, int c, int hw) {
+  pdl_grid_sync();
   __shared__ float tile[64][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
   const int pix = threadIdx.x >> 3, vec = threadIdx.x & 7;
@@ -70,6 +84,7 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ src, size_t plane, 
 
 template <int SRC, int DST>
 __global__ void convert_kernel(const void* __restrict__ src, size_t sp, void* __restrict__ dst, size_t dp, size_t nvec) {
+  pdl_grid_sync();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float v[8];
@@ -89,6 +104,7 @@ __global__ void time_embed_project_kernel(const float* __restrict__ t, int t_row
                                           const float* __restrict__ label_emb, const float* __restrict__ pw,
                                           const float* __restrict__ pb, const int32_t* __restrict__ pset,
                                           int c_total, float* __restrict__ out) {
+  pdl_grid_sync();
   extern __shared__ float emb[];  // [n_sets][te], SiLU already applied
   const int row = blockIdx.x, half = te / 2;
   const int step = step_counter ? *step_counter : 0;
@@ -122,6 +138,7 @@ __global__ void time_embed_project_kernel(const float* __restrict__ t, int t_row
 
 __global__ void fourier_embed_kernel(const float* __restrict__ t, const float* __restrict__ fw, int half,
                                      float* __restrict__ out, int rows) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * half) return;
   const int row = i / half, j = i - row * half;
@@ -133,6 +150,7 @@ __global__ void fourier_embed_kernel(const float* __restrict__ t, const float* _
 
 __global__ void cfg_combine_kernel(const float* __restrict__ sc, const float* __restrict__ su, float scale,
                                    float* __restrict__ out, size_t count) {
+  pdl_grid_sync();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     out[i] = (1.0f + scale) * sc[i] - scale * su[i];
@@ -140,6 +158,7 @@ __global__ void cfg_combine_kernel(const float* __restrict__ sc, const float* __
 
 __global__ void select_step_row_kernel(const float* __restrict__ table, int cols, const int32_t* __restrict__ step,
                                        float* __restrict__ out) {
+  pdl_grid_sync();
   const float* row = table + static_cast<size_t>(*step) * cols;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += gridDim.x * blockDim.x) out[i] = row[i];
 }
@@ -152,6 +171,7 @@ constexpr int kGnChunks = 32;
 template <int FMT>
 __global__ void gn_partial_kernel(const void* __restrict__ x, size_t plane, int hw, int c, int groups,
                                   float* __restrict__ partials) {
+  pdl_grid_sync();
   extern __shared__ float red[];  // [lanes][c][2] then [c][2]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int vecs = c >> 3, lanes = blockDim.x / vecs;
@@ -206,6 +226,7 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, size_t x_plane, cons
                                 int chunks, int pgroups, const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                                 const void* __restrict__ skip, size_t skip_plane, const float* __restrict__ tproj,
                                 int tproj_stride, int act, void* __restrict__ y, size_t y_plane, int hw, int c) {
+  pdl_grid_sync();
   extern __shared__ float coef[];  // [c][2]: scale, shift per channel (norm + affine + tproj folded), then [groups][2]
   float* gstat = coef + 2 * c;
   const int n = blockIdx.y;
@@ -275,6 +296,7 @@ template <int FMT>
 __global__ void layernorm_kernel(const void* __restrict__ x, size_t x_plane, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, void* __restrict__ y, size_t y_plane,
                                  int rows, int c) {
+  pdl_grid_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int vecs = c >> 3;  // <= 64 -> at most 2 vectors per lane
@@ -321,6 +343,7 @@ __global__ void layernorm_kernel(const void* __restrict__ x, size_t x_plane, con
 template <int FMT>
 __global__ void upsample2x_kernel(const void* __restrict__ x, size_t x_plane, void* __restrict__ y, size_t y_plane,
                                   int n, int h, int w, int c) {
+  pdl_grid_sync();
   const int vecs = c >> 3;
   const size_t total = static_cast<size_t>(n) * h * w * vecs;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -362,6 +385,32 @@ __global__ void upsample2x_kernel(const void* __restrict__ x, size_t x_plane, vo
   }
 }
 
+// ---- stem im2col: one thread per (pixel, channel, window row) writes the row's 8 taps as one vector ----------
+template <int FMT>
+__global__ void stem_im2col_kernel(const float* __restrict__ x, const float* __restrict__ planes, int np, int cc, int c_begin, int nch,
+                                   void* __restrict__ out, size_t out_plane, int n, int h, int w) {
+  pdl_grid_sync();
+  const int ho = h / 2, wo = w / 2;
+  const size_t total = static_cast<size_t>(n) * ho * wo * nch * 8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i & 7);
+    const int cl = static_cast<int>((i >> 3) % nch);
+    const size_t pix = i / (static_cast<size_t>(nch) * 8);
+    const int ox = static_cast<int>(pix % wo), oy = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<size_t>(wo) * ho));
+    const int c = c_begin + cl;
+    const float* src = (c == 0) ? x + static_cast<size_t>(b) * h * w
+                                : planes + (static_cast<size_t>(np == 1 ? 0 : b) * cc + (c - 1)) * h * w;
+    const int iy = 2 * oy + r - 3;
+    float v[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int ix = 2 * ox + s - 3;
+      v[s] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(src + static_cast<size_t>(iy) * w + ix) : 0.0f;
+    }
+    Act<FMT>::store8(out, out_plane, i * 8, v);
+  }
+}
+
 // ---- final convolution: 3x3, cout <= 4, fused 1/std ---------------------------------------------
 // One warp per output pixel: lanes split the 9*cin products (8 channels per lane per tap),
 // warp-reduce, lane 0 writes.  Pure bandwidth: reads each input vector 9 times through L1/L2.
@@ -370,6 +419,7 @@ __global__ void final_conv_kernel(const void* __restrict__ in, size_t plane, con
                                   const float* __restrict__ bias, const float* __restrict__ inv_std, int inv_stride,
                                   int inv_step_stride, const int32_t* __restrict__ step_counter,
                                   float* __restrict__ out, int n, int h, int w, int cin) {
+  pdl_grid_sync();
   extern __shared__ float ws[];  // [COUT][9][cin]
   for (int i = threadIdx.x; i < COUT * 9 * cin; i += blockDim.x) ws[i] = wgt[i];
   __syncthreads();
@@ -413,6 +463,7 @@ __global__ void final_conv_kernel(const void* __restrict__ in, size_t plane, con
 __global__ void final_gather_kernel(const float* __restrict__ proj, const float* __restrict__ bias,
                                     const float* __restrict__ inv_std, int inv_stride, int inv_step_stride,
                                     const int32_t* __restrict__ step_counter, float* __restrict__ out, int n, int h, int w) {
+  pdl_grid_sync();
   const size_t total = static_cast<size_t>(n) * h * w;
   const int step = step_counter ? *step_counter : 0;
   const float b0 = bias[0];
@@ -463,13 +514,13 @@ int sbgm_device_is_sm100(void) {
 int sbgm_nchw_to_nhwc(const float* src, void* dst, size_t dst_plane, int fmt, int n, int c, int h, int w, void* stream) {
   SBGM_REQUIRE(c % 8 == 0, "nchw_to_nhwc: c=%d must be a multiple of 8", c);
   dim3 grid(ceil_div(h * w, 32), ceil_div(c, 64), n);
-  SBGM_DISPATCH_FMT(fmt, (nchw_to_nhwc_kernel<FMT><<<grid, 256, 0, as_stream(stream)>>>(src, dst, dst_plane, c, h * w)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((nchw_to_nhwc_kernel<FMT>), grid, 256, 0, as_stream(stream), src, dst, dst_plane, c, h * w)));
   return check_launch("nchw_to_nhwc");
 }
 int sbgm_nhwc_to_nchw(const void* src, size_t src_plane, int fmt, float* dst, int n, int c, int h, int w, void* stream) {
   SBGM_REQUIRE(c % 8 == 0, "nhwc_to_nchw: c=%d must be a multiple of 8", c);
   dim3 grid(ceil_div(h * w, 32), ceil_div(c, 64), n);
-  SBGM_DISPATCH_FMT(fmt, (nhwc_to_nchw_kernel<FMT><<<grid, 256, 0, as_stream(stream)>>>(src, src_plane, dst, c, h * w)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((nhwc_to_nchw_kernel<FMT>), grid, 256, 0, as_stream(stream), src, src_plane, dst, c, h * w)));
   return check_launch("nhwc_to_nchw");
 }
 
@@ -478,7 +529,7 @@ int sbgm_convert(const void* src, size_t sp, int sf, void* dst, size_t dp, int d
   const size_t nvec = count / 8;
   const int grid = grid_for(nvec, 256);
   cudaStream_t st = as_stream(stream);
-#define SBGM_CVT(S, D) convert_kernel<S, D><<<grid, 256, 0, st>>>(src, sp, dst, dp, nvec)
+#define SBGM_CVT(S, D) launch_k((convert_kernel<S, D>), grid, 256, 0, st, src, sp, dst, dp, nvec)
   if (sf == SBGM_FMT_F32 && df == SBGM_FMT_F32) SBGM_CVT(SBGM_FMT_F32, SBGM_FMT_F32);
   else if (sf == SBGM_FMT_F32 && df == SBGM_FMT_BF16) SBGM_CVT(SBGM_FMT_F32, SBGM_FMT_BF16);
   else if (sf == SBGM_FMT_F32 && df == SBGM_FMT_BF16X2) SBGM_CVT(SBGM_FMT_F32, SBGM_FMT_BF16X2);
@@ -496,24 +547,24 @@ int sbgm_time_embed_project(const float* t, int t_row_stride, int t_step_stride,
   SBGM_REQUIRE(te % 2 == 0 && n_sets >= 1 && rows >= 1, "time_embed_project: bad sizes te=%d sets=%d rows=%d", te, n_sets, rows);
   const size_t smem = static_cast<size_t>(n_sets) * te * sizeof(float);
   SBGM_REQUIRE(smem <= 48 * 1024, "time_embed_project: n_sets*te too large");
-  time_embed_project_kernel<<<dim3(rows, ceil_div(c_total, kTimeProjCols)), 256, smem, as_stream(stream)>>>(t, t_row_stride, t_step_stride, step_counter, y,
+  launch_k((time_embed_project_kernel), dim3(rows, ceil_div(c_total, kTimeProjCols)), 256, smem, as_stream(stream), t, t_row_stride, t_step_stride, step_counter, y,
                                                                     fourier_w, n_sets, te, label_emb, proj_w, proj_b,
                                                                     proj_set, c_total, out);
   return check_launch("time_embed_project");
 }
 
 int sbgm_fourier_embed(const float* t, const float* fourier_w, int half, float* out, int rows, void* stream) {
-  fourier_embed_kernel<<<ceil_div(static_cast<long long>(rows) * half, 256), 256, 0, as_stream(stream)>>>(t, fourier_w, half, out, rows);
+  launch_k((fourier_embed_kernel), ceil_div(static_cast<long long>(rows) * half, 256), 256, 0, as_stream(stream), t, fourier_w, half, out, rows);
   return check_launch("fourier_embed");
 }
 
 int sbgm_cfg_combine(const float* s_cond, const float* s_uncond, float scale, float* out, size_t count, void* stream) {
-  cfg_combine_kernel<<<grid_for(count, 256), 256, 0, as_stream(stream)>>>(s_cond, s_uncond, scale, out, count);
+  launch_k((cfg_combine_kernel), grid_for(count, 256), 256, 0, as_stream(stream), s_cond, s_uncond, scale, out, count);
   return check_launch("cfg_combine");
 }
 
 int sbgm_select_step_row(const float* table, int cols, const int32_t* step_counter, float* out, void* stream) {
-  select_step_row_kernel<<<ceil_div(cols, 256), 256, 0, as_stream(stream)>>>(table, cols, step_counter, out);
+  launch_k((select_step_row_kernel), ceil_div(cols, 256), 256, 0, as_stream(stream), table, cols, step_counter, out);
   return check_launch("select_step_row");
 }
 
@@ -533,8 +584,8 @@ int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const floa
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
   dim3 g2(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
-    gn_partial_kernel<FMT><<<g1, 256, smem1, st>>>(x, x_plane, hw, c, groups, partials);
-    gn_apply_kernel<FMT><<<g2, 256, smem2, st>>>(x, x_plane, partials, kGnChunks, groups, gamma, beta, groups, eps, skip,
+    launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, st, x, x_plane, hw, c, groups, partials);
+    launch_k((gn_apply_kernel<FMT>), g2, 256, smem2, st, x, x_plane, partials, kGnChunks, groups, gamma, beta, groups, eps, skip,
                                                   skip_plane, tproj, tproj_stride, act, y, y_plane, hw, c);
   });
   return check_launch("groupnorm");
@@ -549,7 +600,7 @@ int sbgm_norm_partials(const void* x, size_t x_plane, int fmt, int n, int hw, in
   const int lanes = 256 / vecs;
   const size_t smem1 = (static_cast<size_t>(lanes) + 1) * c * 2 * sizeof(float);
   dim3 g1(kGnChunks, n);
-  SBGM_DISPATCH_FMT(fmt, (gn_partial_kernel<FMT><<<g1, 256, smem1, as_stream(stream)>>>(x, x_plane, hw, c, groups, partials)));
+  SBGM_DISPATCH_FMT(fmt, (launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, as_stream(stream), x, x_plane, hw, c, groups, partials)));
   return check_launch("norm_partials");
 }
 
@@ -563,7 +614,7 @@ int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, i
   const size_t smem2 = (static_cast<size_t>(c) + groups) * 2 * sizeof(float);
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
   dim3 g2(per_n_blocks, n);
-  SBGM_DISPATCH_FMT(fmt, (gn_apply_kernel<FMT><<<g2, 256, smem2, as_stream(stream)>>>(
+  SBGM_DISPATCH_FMT(fmt, (launch_k((gn_apply_kernel<FMT>), g2, 256, smem2, as_stream(stream), 
                              x, x_plane, partials, chunks, pgroups, gamma, beta, groups, eps, skip, skip_plane, tproj,
                              tproj_stride, act, y, y_plane, hw, c)));
   return check_launch("groupnorm_apply");
@@ -572,7 +623,7 @@ int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, i
 int sbgm_layernorm(const void* x, size_t x_plane, const float* gamma, const float* beta, float eps,
                    void* y, size_t y_plane, int fmt, int rows, int c, void* stream) {
   SBGM_REQUIRE(c % 8 == 0 && c <= 512, "layernorm: c=%d must be a multiple of 8 and <= 512", c);
-  SBGM_DISPATCH_FMT(fmt, (layernorm_kernel<FMT><<<ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(
+  SBGM_DISPATCH_FMT(fmt, (launch_k((layernorm_kernel<FMT>), ceil_div(rows, 8), 256, 0, as_stream(stream), 
                              x, x_plane, gamma, beta, eps, y, y_plane, rows, c)));
   return check_launch("layernorm");
 }
@@ -581,9 +632,21 @@ int sbgm_upsample2x(const void* x, size_t x_plane, void* y, size_t y_plane, int 
                     void* stream) {
   SBGM_REQUIRE(c % 8 == 0, "upsample2x: c=%d must be a multiple of 8", c);
   const size_t total = static_cast<size_t>(n) * h * w * (c / 8);
-  SBGM_DISPATCH_FMT(fmt, (upsample2x_kernel<FMT><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+  SBGM_DISPATCH_FMT(fmt, (launch_k((upsample2x_kernel<FMT>), grid_for(total, 256), 256, 0, as_stream(stream), 
                              x, x_plane, y, y_plane, n, h, w, c)));
   return check_launch("upsample2x");
+}
+
+int sbgm_stem_im2col(const float* x, const float* planes, int np, int cc, int c_begin, int c_end, void* out, size_t out_plane,
+                     int fmt, int n, int h, int w, void* stream) {
+  SBGM_REQUIRE(h % 2 == 0 && w % 2 == 0, "stem_im2col: h=%d and w=%d must be even", h, w);
+  SBGM_REQUIRE(c_begin >= 0 && c_end > c_begin && c_end <= cc + 1, "stem_im2col: bad channel range [%d, %d) of %d", c_begin, c_end, cc + 1);
+  SBGM_REQUIRE(c_end <= 1 || (planes != nullptr && (np == 1 || np == n)), "stem_im2col: conditioning planes missing or batch %d != 1, %d", np, n);
+  const int nch = c_end - c_begin;
+  const size_t total = static_cast<size_t>(n) * (h / 2) * (w / 2) * nch * 8;
+  SBGM_DISPATCH_FMT(fmt, (launch_k((stem_im2col_kernel<FMT>), grid_for(total, 256), 256, 0, as_stream(stream), x, planes, np, cc, c_begin, nch, out,
+                                                                                                out_plane, n, h, w)));
+  return check_launch("stem_im2col");
 }
 
 int sbgm_final_conv(const void* in, size_t in_plane, int fmt, const float* weight, const float* bias,
@@ -596,7 +659,7 @@ int sbgm_final_conv(const void* in, size_t in_plane, int fmt, const float* weigh
   const int grid = grid_for(npix * 32, 256, 148 * 8);
   cudaStream_t st = as_stream(stream);
 #define SBGM_FC(CO) \
-  SBGM_DISPATCH_FMT(fmt, (final_conv_kernel<FMT, CO><<<grid, 256, smem, st>>>(in, in_plane, weight, bias, inv_std, inv_std_stride, inv_std_step_stride, step_counter, out, n, h, w, cin)))
+  SBGM_DISPATCH_FMT(fmt, (launch_k((final_conv_kernel<FMT, CO>), grid, 256, smem, st, in, in_plane, weight, bias, inv_std, inv_std_stride, inv_std_step_stride, step_counter, out, n, h, w, cin)))
   switch (cout) {
     case 1: SBGM_FC(1); break;
     case 2: SBGM_FC(2); break;
@@ -611,7 +674,7 @@ int sbgm_final_gather(const float* proj, const float* bias, const float* inv_std
                       int inv_std_step_stride, const int32_t* step_counter, float* out, int n, int h, int w,
                       void* stream) {
   const size_t total = static_cast<size_t>(n) * h * w;
-  final_gather_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(proj, bias, inv_std, inv_std_stride,
+  launch_k((final_gather_kernel), grid_for(total, 256), 256, 0, as_stream(stream), proj, bias, inv_std, inv_std_stride,
                                                                            inv_std_step_stride, step_counter, out, n, h, w);
   return check_launch("final_gather");
 }

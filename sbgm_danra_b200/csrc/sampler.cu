@@ -20,6 +20,7 @@ static int grid_for(size_t items) {
 
 template <bool NORMAL>
 __global__ void philox_fill_kernel(float* __restrict__ out, size_t count, uint64_t seed, uint32_t draw, uint64_t first_q) {
+  pdl_grid_sync();
   const size_t nq = (count + 3) / 4;
   for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq;
        q += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -39,6 +40,7 @@ __device__ __forceinline__ uint64_t state_seed(const int32_t* state) {
 }
 
 __global__ void sampler_init_kernel(float* __restrict__ x, size_t nq, float std1, uint64_t seed, uint64_t first_q) {
+  pdl_grid_sync();
   for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq;
        q += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float4 z = Philox::normal4(first_q + q, 0u, seed);
@@ -51,6 +53,7 @@ __global__ void sampler_init_kernel(float* __restrict__ x, size_t nq, float std1
 __global__ void predictor_kernel(float* __restrict__ x, const float* __restrict__ score, float* __restrict__ mean_out,
                                  size_t nq, const float* __restrict__ table, int32_t* __restrict__ step_counter,
                                  uint32_t draw_base, uint32_t draw_stride, uint64_t first_q) {
+  pdl_grid_sync();
   const int step = *step_counter;
   const uint64_t seed = state_seed(step_counter);
   const float* row = table + static_cast<size_t>(step) * SBGM_STEP_COLS;
@@ -86,6 +89,7 @@ __global__ void predictor_kernel(float* __restrict__ x, const float* __restrict_
 
 // per-member sum of squares: one 1024-thread block per member, fixed reduction order (deterministic)
 __global__ void sumsq_kernel(const float* __restrict__ score, float* __restrict__ sumsq, int per_member) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const int member = blockIdx.x;
   const size_t nq = per_member / 4;
@@ -109,6 +113,7 @@ __global__ void corrector_kernel(float* __restrict__ x, const float* __restrict_
                                  int members_total, float noise_norm, float snr, size_t nq,
                                  const int32_t* __restrict__ step_counter, uint32_t draw_base,
                                  uint32_t draw_stride, uint64_t first_q) {
+  pdl_grid_sync();
   const uint64_t seed = state_seed(step_counter);
   __shared__ float s_eps;
   if (threadIdx.x == 0) {
@@ -136,6 +141,7 @@ __global__ void corrector_kernel(float* __restrict__ x, const float* __restrict_
 __global__ void dsm_perturb_kernel(const float* __restrict__ x, const float* __restrict__ std, float* __restrict__ xt,
                                    float* __restrict__ zout, size_t nq, int per_member_q, uint64_t seed, uint32_t draw,
                                    uint64_t first_q) {
+  pdl_grid_sync();
   for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq;
        q += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float sd = std[q / per_member_q];
@@ -150,6 +156,7 @@ constexpr int kLossBlocks = 592;  // 148 SMs x 4
 __global__ void dsm_loss_partial_kernel(const float* __restrict__ score, const float* __restrict__ std,
                                         const float* __restrict__ z, const float* __restrict__ sdf, size_t nq,
                                         int per_member_q, float* __restrict__ partials) {
+  pdl_grid_sync();
   __shared__ float red[kBlock / 32];
   float acc = 0.0f;
   for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq;
@@ -176,6 +183,7 @@ __global__ void dsm_loss_partial_kernel(const float* __restrict__ score, const f
   }
 }
 __global__ void dsm_loss_finish_kernel(const float* __restrict__ partials, int nblocks, float inv_n, float* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ double red[32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc += partials[i];
@@ -197,18 +205,18 @@ extern "C" {
 
 int sbgm_philox_normal(float* out, size_t count, uint64_t seed, uint32_t draw, uint64_t first_elem, void* stream) {
   SBGM_REQUIRE(first_elem % 4 == 0, "philox_normal: first_elem must be a multiple of 4");
-  philox_fill_kernel<true><<<grid_for((count + 3) / 4), kBlock, 0, as_stream(stream)>>>(out, count, seed, draw, first_elem / 4);
+  launch_k((philox_fill_kernel<true>), grid_for((count + 3) / 4), kBlock, 0, as_stream(stream), out, count, seed, draw, first_elem / 4);
   return check_launch("philox_normal");
 }
 int sbgm_philox_uniform(float* out, size_t count, uint64_t seed, uint32_t draw, uint64_t first_elem, void* stream) {
   SBGM_REQUIRE(first_elem % 4 == 0, "philox_uniform: first_elem must be a multiple of 4");
-  philox_fill_kernel<false><<<grid_for((count + 3) / 4), kBlock, 0, as_stream(stream)>>>(out, count, seed, draw, first_elem / 4);
+  launch_k((philox_fill_kernel<false>), grid_for((count + 3) / 4), kBlock, 0, as_stream(stream), out, count, seed, draw, first_elem / 4);
   return check_launch("philox_uniform");
 }
 
 int sbgm_sampler_init(float* x, size_t count, float std1, uint64_t seed, uint64_t first_elem, void* stream) {
   SBGM_REQUIRE(count % 4 == 0 && first_elem % 4 == 0, "sampler_init: count and first_elem must be multiples of 4");
-  sampler_init_kernel<<<grid_for(count / 4), kBlock, 0, as_stream(stream)>>>(x, count / 4, std1, seed, first_elem / 4);
+  launch_k((sampler_init_kernel), grid_for(count / 4), kBlock, 0, as_stream(stream), x, count / 4, std1, seed, first_elem / 4);
   return check_launch("sampler_init");
 }
 
@@ -216,7 +224,7 @@ int sbgm_sampler_predictor(float* x, const float* score, float* mean_out, size_t
                            int32_t* step_counter, uint32_t draw_base, uint32_t draw_stride,
                            uint64_t first_elem, void* stream) {
   SBGM_REQUIRE(count % 4 == 0 && first_elem % 4 == 0, "sampler_predictor: count and first_elem must be multiples of 4");
-  predictor_kernel<<<grid_for(count / 4), kBlock, 0, as_stream(stream)>>>(x, score, mean_out, count / 4, step_table,
+  launch_k((predictor_kernel), grid_for(count / 4), kBlock, 0, as_stream(stream), x, score, mean_out, count / 4, step_table,
                                                                           step_counter, draw_base, draw_stride,
                                                                           first_elem / 4);
   return check_launch("sampler_predictor");
@@ -224,7 +232,7 @@ int sbgm_sampler_predictor(float* x, const float* score, float* mean_out, size_t
 
 int sbgm_sampler_sumsq(const float* score, float* sumsq, int members, int per_member, void* stream) {
   SBGM_REQUIRE(per_member % 4 == 0, "sampler_sumsq: per_member must be a multiple of 4");
-  sumsq_kernel<<<members, 1024, 0, as_stream(stream)>>>(score, sumsq, per_member);
+  launch_k((sumsq_kernel), members, 1024, 0, as_stream(stream), score, sumsq, per_member);
   return check_launch("sampler_sumsq");
 }
 
@@ -232,7 +240,7 @@ int sbgm_sampler_corrector(float* x, const float* score, const float* sumsq, int
                            float snr, size_t count, const int32_t* step_counter,
                            uint32_t draw_base, uint32_t draw_stride, uint64_t first_elem, void* stream) {
   SBGM_REQUIRE(count % 4 == 0 && first_elem % 4 == 0, "sampler_corrector: count and first_elem must be multiples of 4");
-  corrector_kernel<<<grid_for(count / 4), kBlock, 0, as_stream(stream)>>>(
+  launch_k((corrector_kernel), grid_for(count / 4), kBlock, 0, as_stream(stream), 
       x, score, sumsq, members_total, sqrtf(static_cast<float>(per_member)), snr, count / 4, step_counter,
       draw_base, draw_stride, first_elem / 4);
   return check_launch("sampler_corrector");
@@ -242,7 +250,7 @@ int sbgm_dsm_perturb(const float* x, const float* std, float* xt, float* z, int 
                      uint32_t draw, uint64_t first_elem, void* stream) {
   SBGM_REQUIRE(per_member % 4 == 0 && first_elem % 4 == 0, "dsm_perturb: per_member and first_elem must be multiples of 4");
   const size_t nq = static_cast<size_t>(n) * per_member / 4;
-  dsm_perturb_kernel<<<grid_for(nq), kBlock, 0, as_stream(stream)>>>(x, std, xt, z, nq, per_member / 4, seed, draw, first_elem / 4);
+  launch_k((dsm_perturb_kernel), grid_for(nq), kBlock, 0, as_stream(stream), x, std, xt, z, nq, per_member / 4, seed, draw, first_elem / 4);
   return check_launch("dsm_perturb");
 }
 
@@ -253,8 +261,8 @@ int sbgm_dsm_loss(const float* score, const float* std, const float* z, const fl
   SBGM_REQUIRE(per_member % 4 == 0, "dsm_loss: per_member must be a multiple of 4");
   const size_t nq = static_cast<size_t>(n) * per_member / 4;
   const int blocks = static_cast<int>(nq < static_cast<size_t>(kLossBlocks) * kBlock ? (nq + kBlock - 1) / kBlock : kLossBlocks);
-  dsm_loss_partial_kernel<<<blocks, kBlock, 0, as_stream(stream)>>>(score, std, z, sdf, nq, per_member / 4, partials);
-  dsm_loss_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, blocks, 1.0f / n, loss_out);
+  launch_k((dsm_loss_partial_kernel), blocks, kBlock, 0, as_stream(stream), score, std, z, sdf, nq, per_member / 4, partials);
+  launch_k((dsm_loss_finish_kernel), 1, 256, 0, as_stream(stream), partials, blocks, 1.0f / n, loss_out);
   return check_launch("dsm_loss");
 }
 

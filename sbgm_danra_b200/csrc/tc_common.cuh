@@ -131,6 +131,7 @@ struct EpilogueParams {
   const float* bias;
   const void* residual;
   size_t res_plane;
+  int res_pix_mod;       // > 0: the residual is broadcast over the batch, indexed by pix % res_pix_mod
   const float* tproj;
   int tproj_stride;
   int act;
@@ -232,8 +233,9 @@ __device__ __forceinline__ void gn_block64_stats(const uint32_t (&ra)[32], const
   }
 }
 
-// 64 accumulator columns (two 32-column TMEM loads) of one row.  ACT and PROJ are compile-time.
-template <int FMT, int ACT, bool PROJ>
+// 64 accumulator columns (two 32-column TMEM loads) of one row.  ACT and PROJ are compile-time
+// (PROJ: 0 = store, 1 = projection only, 2 = projection AND store -- the training forward keeps the tensor).
+template <int FMT, int ACT, int PROJ>
 __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const uint32_t (&ra)[32], const uint32_t (&rb)[32],
                                                  int co_base, int n, size_t pix, bool valid, int lane,
                                                  float (&proj_acc)[kProjMax]) {
@@ -254,7 +256,7 @@ __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       float rv[8];
-      Act<FMT>::load8(ep.residual, ep.res_plane, pix * ep.cout + co_base + g * 8, rv);
+      Act<FMT>::load8(ep.residual, ep.res_plane, (ep.res_pix_mod ? pix % ep.res_pix_mod : pix) * ep.cout + co_base + g * 8, rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[g * 8 + j] += rv[j];
     }
@@ -274,9 +276,8 @@ __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const
     for (int j = 0; j < 64; ++j)
 #pragma unroll
       for (int q = 0; q < kProjN; ++q) proj_acc[q] = fmaf(v[j], c_proj_w[q * 64 + j], proj_acc[q]);
-  } else {
-    store_block64<FMT>(ep.out, ep.out_plane, ep.cout, v, pix, valid, co_base, lane);
   }
+  if (PROJ != 1) store_block64<FMT>(ep.out, ep.out_plane, ep.cout, v, pix, valid, co_base, lane);   // PROJ == 2: both (training)
 }
 
 __device__ __forceinline__ void epilogue_store_proj(const EpilogueParams& ep, size_t pix, const float (&proj_acc)[kProjMax]) {

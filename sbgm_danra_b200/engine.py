@@ -148,7 +148,7 @@ class Kernels:
 
     def conv(self, x: Act, cw: ConvW, stride: int = 1, pad: int = 0, act: int = ACT_NONE,
              residual: Optional[Act] = None, tproj: Optional[torch.Tensor] = None,
-             proj: Optional[torch.Tensor] = None, gn_stats: bool = False):
+             proj: Optional[torch.Tensor] = None, gn_stats: bool = False, proj_keep: bool = False):
         """Convolution + fused epilogue.  Returns the output `Act`; with `proj` ([n_proj, 64] fp32) returns the
         projected fp32 tensor [n, h, w, PROJ_STRIDE] instead; with `gn_stats=True` returns (Act, stats) where
         stats = (partials, chunks) if the producing kernel could fuse the GroupNorm statistics, else None."""
@@ -162,6 +162,10 @@ class Kernels:
         if proj is not None:
             assert self.fmt != FMT_F32 and cw.cout == 64
             out, out_ptr, out_plane = None, None, 0
+            if proj_keep:           # training: the projected tensor AND the convolution output (64 -> 64 kernel only)
+                assert self._c64_ok(x, cw, stride, pad)
+                out = Act(self.fmt, x.n, ho, wo, cw.cout, self.device)
+                out_ptr, out_plane = out.ptr, out.plane
             pout = torch.empty((x.n, ho, wo, _lib.PROJ_STRIDE), dtype=torch.float32, device=self.device)
             pargs = (proj.data_ptr(), proj.shape[0], pout.data_ptr())
         else:
@@ -197,8 +201,25 @@ class Kernels:
                  tp_ptr, tp_stride, out_ptr, out_plane, self.fmt, x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw,
                  stride, pad, act, *pargs, ws, ws_bytes, _ptr(part), _stream())
         if proj is not None:
-            return pout
+            return (out, pout) if proj_keep else pout
         return (out, stats) if gn_stats else out
+
+    def stem_im2col(self, x: torch.Tensor, planes: Optional[torch.Tensor], c_begin: int, c_end: int, cc: int) -> Act:
+        """8x8 stride-2 window of channels [c_begin, c_end) of x || planes as an NHWC tensor with 64 channels per input channel."""
+        n, _, h, w = x.shape
+        out = Act(self.fmt, n, h // 2, w // 2, (c_end - c_begin) * 64, self.device)
+        call("sbgm_stem_im2col", x.data_ptr(), _ptr(planes), 1 if planes is None else planes.shape[0], cc, c_begin, c_end,
+             out.ptr, out.plane, self.fmt, n, h, w, _stream())
+        return out
+
+    def conv1x1_bcast(self, x: Act, cw: ConvW, residual: Act, tproj: Optional[torch.Tensor]) -> Act:
+        """1x1 tensor-core convolution whose residual may be a single image broadcast over the batch."""
+        out = Act(self.fmt, x.n, x.h, x.w, cw.cout, self.device)
+        mod = x.h * x.w if (residual.n == 1 and x.n > 1) else 0
+        call("sbgm_conv2d_tc_ex", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias), residual.ptr, residual.plane, mod,
+             _ptr(tproj), tproj.stride(0) if tproj is not None else 0, out.ptr, out.plane, self.fmt, x.n, x.h, x.w, cw.cin, cw.cout,
+             1, 1, 1, 0, 0, x.h, x.w, x.h, x.w, 1, 0, 0, ACT_NONE, None, 0, _stream())
+        return out
 
     def linear(self, x: Act, cw: ConvW, act: int = ACT_NONE, residual: Optional[Act] = None) -> Act:
         return self.conv(x, cw, 1, 0, act, residual)
@@ -335,6 +356,13 @@ class EncoderEngine:
         w1 = pk.get(f"{p}conv1.weight")                                  # [64, cin, 8, 8]
         self.cin = w1.shape[1]
         self.stem_w = w1.permute(1, 2, 3, 0).reshape(self.cin, 64, 64).contiguous()   # [cin][tap][co]
+        if fmt != FMT_F32:
+            # tensor-core stem: conv1 as a 1x1 convolution over the im2col tensor (K index = ci * 64 + r * 8 + s = OIHW order)
+            def km(wsub):
+                m = wsub.reshape(64, -1).contiguous()
+                return m.to(torch.bfloat16) if fmt == FMT_BF16 else _split_bf16(m)
+            self.stem_cw_all = ConvW(km(w1), None, self.cin * 64, 64, 1, 1)
+            self.stem_cw_x = ConvW(km(w1[:, :1]), None, 64, 64, 1, 1)
         self.conv2 = pk.conv(f"{p}conv2.weight", bn=f"{p}bn1")
         self.layers = []
         for li, nblk in enumerate(block_layers, start=1):
@@ -353,14 +381,25 @@ class EncoderEngine:
             tp.label_emb = pk.get(f"{p}label_emb.weight").contiguous()
         self.tp = tp
 
-    def stem_partial(self, planes: torch.Tensor, h: int, w: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """conv1 restricted to the conditioning channels (step-invariant in a sampler): fp32 NHWC."""
+    def alloc_partial(self, npl: int, h: int, w: int):
+        """Buffer for `stem_partial`: fp32 NHWC tensor (fp32 mode) or an `Act` in the engine's format (tensor-core modes,
+        where it enters the stem convolution's epilogue as a residual)."""
+        if self.fmt == FMT_F32:
+            return torch.empty((npl, h // 2, w // 2, 64), dtype=torch.float32, device=self.device)
+        return Act(self.fmt, npl, h // 2, w // 2, 64, self.device)
+
+    def stem_partial(self, planes: torch.Tensor, h: int, w: int, out=None):
+        """conv1 restricted to the conditioning channels (step-invariant in a sampler)."""
         npl, cc = planes.shape[0], planes.shape[1]
         if out is None:
-            out = torch.empty((npl, h // 2, w // 2, 64), dtype=torch.float32, device=self.device)
-        assert tuple(out.shape) == (npl, h // 2, w // 2, 64) and out.is_contiguous()
+            out = self.alloc_partial(npl, h, w)
+        f32 = out if self.fmt == FMT_F32 else torch.empty((npl, h // 2, w // 2, 64), dtype=torch.float32, device=self.device)
+        assert tuple(f32.shape) == (npl, h // 2, w // 2, 64) and f32.is_contiguous()
         call("sbgm_stem_conv", None, planes.data_ptr(), npl, cc, 1, cc + 1, self.stem_w.data_ptr(), None, 0, None, 0,
-             out.data_ptr(), out.numel(), FMT_F32, npl, h, w, _stream())
+             f32.data_ptr(), f32.numel(), FMT_F32, npl, h, w, _stream())
+        if self.fmt != FMT_F32:
+            assert (out.n, out.h, out.w, out.c) == (npl, h // 2, w // 2, 64)
+            call("sbgm_convert", f32.data_ptr(), 0, FMT_F32, out.ptr, out.plane, self.fmt, f32.numel(), _stream())
         return out
 
     def forward(self, x: torch.Tensor, planes: Optional[torch.Tensor], tproj: torch.Tensor,
@@ -370,8 +409,17 @@ class EncoderEngine:
         k, tp = self.k, self.tp
         n, _, h, w = x.shape
         cc = self.cin - 1
-        f1 = Act(self.fmt, n, h // 2, w // 2, 64, self.device)
         t0 = tp.cols(tproj, "enc0")
+        if self.fmt != FMT_F32:
+            # conv1 on the tensor cores: im2col of the 8x8 stride-2 window, then a 1x1 implicit GEMM (K = 64 per channel)
+            if partial is not None:
+                f1 = k.conv1x1_bcast(k.stem_im2col(x, None, 0, 1, cc), self.stem_cw_x, partial, t0)
+            else:
+                if cc > 0:
+                    assert planes is not None and planes.shape[1] == cc, f"encoder expects {cc} conditioning channels"
+                f1 = k.conv(k.stem_im2col(x, planes, 0, self.cin, cc), self.stem_cw_all, tproj=t0)
+            return self._after_stem(f1, tproj)
+        f1 = Act(self.fmt, n, h // 2, w // 2, 64, self.device)
         if partial is not None:
             call("sbgm_stem_conv", x.data_ptr(), None, 1, cc, 0, 1, self.stem_w.data_ptr(), partial.data_ptr(),
                  partial.shape[0], t0.data_ptr(), t0.stride(0), f1.ptr, f1.plane, self.fmt, n, h, w, _stream())
@@ -380,6 +428,10 @@ class EncoderEngine:
                 assert planes is not None and planes.shape[1] == cc, f"encoder expects {cc} conditioning channels"
             call("sbgm_stem_conv", x.data_ptr(), _ptr(planes), 1 if planes is None else planes.shape[0], cc, 0, self.cin,
                  self.stem_w.data_ptr(), None, 0, t0.data_ptr(), t0.stride(0), f1.ptr, f1.plane, self.fmt, n, h, w, _stream())
+        return self._after_stem(f1, tproj)
+
+    def _after_stem(self, f1: Act, tproj: torch.Tensor) -> List[Act]:
+        k, tp = self.k, self.tp
         fmaps = [f1]
         hcur = k.conv(f1, self.conv2, stride=2, pad=3, act=ACT_RELU)
         for li, blocks in enumerate(self.layers, start=1):
@@ -399,9 +451,8 @@ class DecoderEngine:
     def __init__(self, sd, prefix: str, *, plan: Sequence[Tuple[int, int, bool]], n_heads: int, norm: str,
                  gn_groups: int, activation: str, use_resize_conv: bool, out_channels: int, fmt: int, device,
                  tp: TimeProjector) -> None:
-        if not use_resize_conv:
-            raise NotImplementedError("use_resize_conv=False (ConvTranspose2d decoder) is not on the CUDA path yet")
         pk = _Packer(sd, fmt, device)
+        self.use_resize_conv = use_resize_conv
         self.k = Kernels(fmt, device)
         self.fmt, self.device = fmt, device
         self.act = ACTS[activation]
@@ -411,7 +462,7 @@ class DecoderEngine:
             bp = f"{prefix}residual_layers.{i}"
             affine = norm == "group"
             blk = dict(
-                conv_up=pk.conv(f"{bp}.conv_up.weight", f"{bp}.conv_up.bias"),
+                conv_up=pk.conv(f"{bp}.conv_up.weight", f"{bp}.conv_up.bias") if use_resize_conv else self._pack_transpose(pk, f"{bp}.transpose"),
                 conv=pk.conv(f"{bp}.conv.weight", f"{bp}.conv.bias"),
                 n1=(pk.vec(f"{bp}.norm1.weight"), pk.vec(f"{bp}.norm1.bias")) if affine else (None, None),
                 n2=(pk.vec(f"{bp}.norm2.weight"), pk.vec(f"{bp}.norm2.bias")) if affine else (None, None),
@@ -423,12 +474,46 @@ class DecoderEngine:
             tp.add_head(f"dec{i}", s, pk.get(f"{bp}.time_projection_layer.1.weight"), pk.vec(f"{bp}.time_projection_layer.1.bias"))
             self.blocks.append(blk)
         fp = f"{prefix}final_layer"
-        self.final_up = pk.conv(f"{fp}.conv_up.weight", f"{fp}.conv_up.bias")
+        self.final_up = pk.conv(f"{fp}.conv_up.weight", f"{fp}.conv_up.bias") if use_resize_conv else self._pack_transpose(pk, f"{fp}.transpose")
         wf = pk.get(f"{fp}.conv.weight")                                   # [cout, cin, 3, 3]
         self.final_w = wf.permute(0, 2, 3, 1).reshape(wf.shape[0], 9, wf.shape[1]).contiguous()
         self.final_b = pk.vec(f"{fp}.conv.bias")
         self.out_channels = out_channels
         self.tp = tp
+
+    def _pack_transpose(self, pk: _Packer, prefix: str):
+        """nn.ConvTranspose2d(c, c, kernel 2, stride 2) (score_unet.py:466-468, the use_resize_conv=False ablation):
+        out[n, 2i+a, 2j+b, co] = bias[co] + sum_ci x[n, i, j, ci] W[ci][co][a][b] -- four 1x1 convolutions scattered to
+        the four output parities (tensor cores), or one gather over the 2x2 taps (fp32 / CUDA cores)."""
+        w = pk.get(f"{prefix}.weight")                        # [cin, cout, 2, 2]
+        bias = pk.vec(f"{prefix}.bias")
+        cin, cout = w.shape[0], w.shape[1]
+        if self.fmt == FMT_F32:
+            return dict(simt=w.permute(2, 3, 0, 1).reshape(4, cin, cout).contiguous(), bias=bias, cin=cin, cout=cout)
+        subs = []
+        for a in range(2):
+            for b in range(2):
+                km = w[:, :, a, b].t().contiguous()          # [cout][cin] K-major
+                packed = km.to(torch.bfloat16) if self.fmt == FMT_BF16 else _split_bf16(km)
+                subs.append((a, b, ConvW(packed, bias, cin, cout, 1, 1)))
+        return dict(subs=subs, bias=bias, cin=cin, cout=cout)
+
+    def _transpose_up(self, x: Act, tw: dict):
+        k = self.k
+        out = Act(self.fmt, x.n, 2 * x.h, 2 * x.w, tw["cout"], self.device)
+        if self.fmt == FMT_F32:
+            # the data gradient of a (2x2, stride 2) convolution IS the transposed convolution; bias via a unit-statistics affine
+            raw = Act(self.fmt, x.n, 2 * x.h, 2 * x.w, tw["cout"], self.device)
+            call("sbgm_conv2d_dgrad_simt", x.ptr, x.plane, tw["simt"].data_ptr(), raw.ptr, raw.plane, 0, self.fmt,
+                 x.n, 2 * x.h, 2 * x.w, tw["cout"], tw["cin"], 2, 2, 2, 0, _stream())
+            unit = torch.tensor([0.0, 1.0], dtype=torch.float32, device=self.device).repeat(tw["cout"], 1).contiguous()
+            call("sbgm_norm_apply", raw.ptr, raw.plane, unit.data_ptr(), 2, tw["cout"], None, tw["bias"].data_ptr(), None, 0, None, 0, 0,
+                 ACT_NONE, out.ptr, out.plane, self.fmt, x.n, 4 * x.h * x.w, tw["cout"], _stream())
+            return out
+        for a, b, cw in tw["subs"]:
+            call("sbgm_conv2d_tc_ex", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, cw.bias.data_ptr(), None, 0, 0, None, 0, out.ptr, out.plane,
+                 self.fmt, x.n, x.h, x.w, cw.cin, cw.cout, 1, 1, 1, 0, 0, x.h, x.w, 2 * x.h, 2 * x.w, 2, a, b, ACT_NONE, None, 0, _stream())
+        return out
 
     def forward(self, fmaps: List[Act], tproj: torch.Tensor, inv_std: Optional[torch.Tensor], *,
                 inv_std_stride: int = 1, inv_std_step_stride: int = 0, step_counter: Optional[torch.Tensor] = None,
@@ -437,8 +522,11 @@ class DecoderEngine:
         rev = list(reversed(fmaps))
         out = rev[0]
         for i, blk in enumerate(self.blocks):
-            up = k.upsample2x(out)
-            a, st1 = k.conv(up, blk["conv_up"], pad=1, gn_stats=True)
+            if self.use_resize_conv:
+                up = k.upsample2x(out)
+                a, st1 = k.conv(up, blk["conv_up"], pad=1, gn_stats=True)
+            else:
+                a, st1 = self._transpose_up(out, blk["conv_up"]), None
             a = k.groupnorm(a, *blk["n1"], groups=blk["g1"], stats=st1)
             b, st2 = k.conv(a, blk["conv"], pad=1, gn_stats=True)
             skip = rev[i + 1]
@@ -448,6 +536,13 @@ class DecoderEngine:
                               stats=st2)
             if blk["attn"] is not None:
                 out = attention_block(k, blk["attn"], out)
+        if not self.use_resize_conv:
+            a = self._transpose_up(out, self.final_up)
+            res = dst if dst is not None else torch.empty((a.n, self.out_channels, a.h, a.w), dtype=torch.float32, device=self.device)
+            call("sbgm_final_conv", a.ptr, a.plane, self.fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std),
+                 inv_std_stride, inv_std_step_stride, _ptr(step_counter), res.data_ptr(), a.n, a.h, a.w, a.c,
+                 self.out_channels, _stream())
+            return res
         up = k.upsample2x(out)
         n, h, w = up.n, up.h, up.w
         res = dst if dst is not None else torch.empty((n, self.out_channels, h, w), dtype=torch.float32, device=self.device)

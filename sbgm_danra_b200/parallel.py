@@ -104,7 +104,8 @@ class GradSync:
         if flat.is_cuda:
             if self.stream is None:
                 self.stream = torch.cuda.Stream(device=flat.device)
-            flat.record_stream(self.stream)
+            if not torch.cuda.is_current_stream_capturing():
+                flat.record_stream(self.stream)
         if self.bucketer is None or self.bucketer.total != flat.numel() or (self.bucketer.expected is None and self.expected is not None):
             self.bucketer = GradBucketer(layout, flat.numel(), self.bucket_elems, self.expected)
         self.bucketer.reset()

@@ -163,9 +163,9 @@ class _NativeStep:
         self.y = torch.zeros(batch, dtype=torch.int64, device=dev) if has_y else None
         self.cfg_scale = cfg_scale
         cc = eng.enc.cin - 1
-        self.partial = torch.empty((planes_batch, size // 2, size // 2, 64), dtype=torch.float32, device=dev) if cc > 0 else None
+        self.partial = eng.enc.alloc_partial(planes_batch, size, size) if cc > 0 else None
         if cfg_scale is not None:
-            self.partial_u = None if self.partial is None else torch.empty_like(self.partial)
+            self.partial_u = None if self.partial is None else eng.enc.alloc_partial(planes_batch, size, size)
             self.y_u = None if self.y is None else torch.zeros_like(self.y)
             self.score_c = torch.empty_like(self.x)
             self.score_u = torch.empty_like(self.x)

@@ -431,22 +431,30 @@ class _ScoreNetFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, t, y, planes, inv_std, names, *params):
-        from .train_engine import TrainEngine
-        tensors = dict(zip(names, params))
-        tensors.update({k: v for k, v in model.named_buffers()})
-        hook = getattr(model, "_grad_sync", None)
-        eng = TrainEngine(tensors, model.spec(), model.precision, x.device, bn_train=model.training)
-        eng.grad_sync = hook          # parallel.GradSync: bucketed all-reduce of the flat gradient buffer, overlapped
-        out = eng.forward(x, t, y, planes, inv_std)
-        ctx.eng, ctx.names = eng, names
+        from .train_engine import TrainEngine, TrainRunner
+        buffers = list(model.named_buffers())
+        key = (model.precision, model.training, tuple(x.shape), None if planes is None else tuple(planes.shape), y is None,
+               inv_std is None, str(x.device), tuple(p.data_ptr() for p in params), tuple(b.data_ptr() for _, b in buffers))
+        runners = model.__dict__.setdefault("_train_runners", {})
+        runner = runners.get(key)
+        if runner is None:
+            def make_engine():
+                tensors = dict(zip(names, params))
+                tensors.update(buffers)
+                return TrainEngine(tensors, model.spec(), model.precision, x.device, bn_train=model.training)
+            runners.clear()                       # one live configuration at a time (the graphs pin GBs of activations)
+            runner = runners[key] = TrainRunner(make_engine, use_graphs=os.environ.get("SBGM_B200_TRAIN_GRAPHS", "1") != "0")
+        yy = None if y is None else y.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous()
+        out, handle = runner.forward(x, t.reshape(-1).float().contiguous(), yy, planes, inv_std, getattr(model, "_grad_sync", None))
+        ctx.runner, ctx.handle, ctx.names = runner, handle, names
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        eng = ctx.eng
-        with torch.cuda.device(eng.device):
-            grads = eng.backward(dout)
-        ctx.eng = None
+        runner, handle = ctx.runner, ctx.handle
+        with torch.cuda.device(dout.device):
+            grads = runner.backward(handle, dout)
+        ctx.runner = ctx.handle = None
         return (None,) * 7 + tuple(grads.get(n) for n in ctx.names)
 
 

@@ -31,8 +31,21 @@ def _pack_oihw(w: torch.Tensor, fmt: int) -> torch.Tensor:
     cout, cin, kh, kw = w.shape
     if fmt == FMT_F32:
         return w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
-    km = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).contiguous()
-    return km.to(torch.bfloat16) if fmt == FMT_BF16 else _split_bf16(km)
+    return _pack_tc(w, fmt, list(range(kh * kw)), False)
+
+
+def _pack_tc(w: torch.Tensor, fmt: int, taps: Sequence[int], transpose: bool) -> torch.Tensor:
+    """One-launch pack (sbgm_pack_weight): out[o][t][i] = w[co][ci][taps[t]], (o, i) = (ci, co) if transpose."""
+    import ctypes
+    cout, cin, kh, kw = w.shape
+    w = w.contiguous()
+    oo, ii = (cin, cout) if transpose else (cout, cin)
+    planes = 2 if fmt == FMT_BF16X2 else 1
+    out = torch.empty((planes, oo, len(taps) * ii), dtype=torch.bfloat16, device=w.device)
+    arr = (ctypes.c_int * len(taps))(*taps)
+    call("sbgm_pack_weight", w.data_ptr(), cout, cin, kh * kw, arr, len(taps), int(transpose), out.data_ptr(), oo * len(taps) * ii,
+         fmt, _stream())
+    return out if planes == 2 else out[0]
 
 
 class ConvLayer:
@@ -71,9 +84,9 @@ class ConvLayer:
             return None
         # tap index r' of the sub-kernel reads dy at offset d = r' - pad'  ->  pad' = -d_min; taps must be contiguous in d
         assert dys == list(range(dys[0], dys[0] + len(dys))) and dxs == list(range(dxs[0], dxs[0] + len(dxs)))
-        sub = self.w4[:, :, rs, :][:, :, :, ss]                       # [co, ci, kh', kw'] in increasing-d order
-        wt = sub.permute(1, 0, 2, 3).contiguous()                     # transposed conv: OIHW with O = ci, I = co
-        cw = ConvW(_pack_oihw(wt, self.fmt), None, self.cout, self.cin, len(rs), len(ss))
+        # transposed convolution: O = ci, I = co, taps in increasing-d order
+        packed = _pack_tc(self.w4, self.fmt, [r * self.kw + s for r in rs for s in ss], True)
+        cw = ConvW(packed, None, self.cout, self.cin, len(rs), len(ss))
         self._dgrad[key] = (cw, -dys[0], -dxs[0])
         return self._dgrad[key]
 
@@ -94,7 +107,14 @@ class Tape:
         self.keep.extend(keep)
 
     def pop(self, a: Act) -> Optional[Act]:
-        return self.grads.pop(a.buf.data_ptr(), None)
+        g = self.grads.pop(a.buf.data_ptr(), None)
+        if g is not None and (g.n, g.h, g.w, g.c) != (a.n, a.h, a.w, a.c):
+            # the gradient was deposited through a view (tokens <-> image): same storage, the consumer's geometry
+            assert g.plane == a.plane
+            v = Act.__new__(Act)
+            v.buf, v.fmt, v.n, v.h, v.w, v.c = g.buf, g.fmt, a.n, a.h, a.w, a.c
+            return v
+        return g
 
     def add(self, a: Act, g: Act) -> None:
         key = a.buf.data_ptr()
@@ -131,9 +151,18 @@ class TrainKernels:
 
     # -- convolution ----------------------------------------------------------------------------
     def conv(self, x: Act, layer: ConvLayer, stride: int = 1, pad: int = 0, residual: Optional[Act] = None,
-             gn_stats: bool = False, need_dx: bool = True):
-        out = self.k.conv(x, layer.fwd, stride=stride, pad=pad, residual=residual, gn_stats=gn_stats)
-        y, stats = out if gn_stats else (out, None)
+             gn_stats: bool = False, need_dx: bool = True, proj: Optional[torch.Tensor] = None,
+             tproj: Optional[torch.Tensor] = None, dtproj: Optional[torch.Tensor] = None):
+        """`proj`: also emit the nine per-tap partial products of the final 64 -> 1 convolution (returns (y, projected)).
+        `tproj` / `dtproj`: per-sample channel offsets added in the epilogue and where their gradient goes."""
+        if tproj is not None:
+            y, stats = self.k.conv(x, layer.fwd, stride=stride, pad=pad, tproj=tproj), None
+        elif proj is not None:
+            y, pout = self.k.conv(x, layer.fwd, stride=stride, pad=pad, proj=proj, proj_keep=True)
+            stats = None
+        else:
+            out = self.k.conv(x, layer.fwd, stride=stride, pad=pad, residual=residual, gn_stats=gn_stats)
+            y, stats = out if gn_stats else (out, None)
         tape = self.tape
 
         def backward() -> None:
@@ -143,8 +172,14 @@ class TrainKernels:
             self._conv_backward(x, dy, layer, stride, pad, need_dx)
             if residual is not None:
                 tape.add(residual, dy)
+            if dtproj is not None:
+                ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, dy.c))
+                call("sbgm_channel_sums", dy.ptr, dy.plane, self.fmt, dy.n, dy.h * dy.w, dy.c, dtproj.data_ptr(), dtproj.stride(0), None,
+                     ws.data_ptr(), _stream())
 
         tape.record(backward, x, y)
+        if proj is not None:
+            return y, pout
         return (y, stats) if gn_stats else y
 
     def _conv_backward(self, x: Act, dy: Act, layer: ConvLayer, stride: int, pad: int, need_dx: bool) -> None:
@@ -190,7 +225,7 @@ class TrainKernels:
                     continue
                 cw, ph, pw = ent
                 ho, wo = (h - py + stride - 1) // stride, (w - px + stride - 1) // stride
-                call("sbgm_conv2d_tc_ex", dy.ptr, dy.plane, cw.w.data_ptr(), cw.plane, None, None, 0, dx.ptr, dx.plane, fmt,
+                call("sbgm_conv2d_tc_ex", dy.ptr, dy.plane, cw.w.data_ptr(), cw.plane, None, None, 0, 0, None, 0, dx.ptr, dx.plane, fmt,
                      dy.n, dy.h, dy.w, cout, cin, cw.kh, cw.kw, 1, ph, pw, ho, wo, h, w, stride, py, px, ACT_NONE, None, 0, st)
         tape.add(x, dx)
 
@@ -413,6 +448,9 @@ class TrainEngine:
         w1 = sd[f"{p}conv1.weight"]
         self.cin = w1.shape[1]
         self.stem_w = w1.permute(1, 2, 3, 0).reshape(self.cin, 64, 64).contiguous()
+        if fmt != FMT_F32:   # tensor-core stem: 1x1 convolution over the im2col tensor; [co][ci*64 + tap] IS conv1.weight's OIHW order
+            self.stem_layer = ConvLayer(f"{p}conv1.weight", w1.reshape(64, self.cin * 64, 1, 1), None, fmt)
+            self.stem_layer.shape = tuple(w1.shape)
         self.conv2 = self._conv(f"{p}conv2.weight")
         self.bn1 = self._bn(f"{p}bn1")
         self.layers = []
@@ -486,9 +524,14 @@ class TrainEngine:
         tape.keep += [tproj, t, yy, x, planes]
         col = lambda table, name: self.tp.cols(table, name)
 
+        self._time = (t, yy, dtproj)
         # Encoder.conv1 + time projection 0 (score_unet.py:310-314)
-        f1 = Act(fmt, n, h // 2, w // 2, 64, dev)
         t0 = col(tproj, "enc0")
+        if fmt != FMT_F32:
+            xcol = tk.k.stem_im2col(x, planes, 0, self.cin, cc)
+            f1 = tk.conv(xcol, self.stem_layer, need_dx=False, tproj=t0, dtproj=col(dtproj, "enc0"))
+            return self._forward_rest(f1, tproj, dtproj, inv_std, n)
+        f1 = Act(fmt, n, h // 2, w // 2, 64, dev)
         call("sbgm_stem_conv", x.data_ptr(), _ptr(planes), 1 if planes is None else planes.shape[0], cc, 0, self.cin,
              self.stem_w.data_ptr(), None, 0, t0.data_ptr(), t0.stride(0), f1.ptr, f1.plane, fmt, n, h, w, _stream())
 
@@ -505,6 +548,11 @@ class TrainEngine:
                  dw.data_ptr(), n, h, w, ws2.data_ptr(), _stream())
 
         tape.record(stem_backward, f1)
+        return self._forward_rest(f1, tproj, dtproj, inv_std, n)
+
+    def _forward_rest(self, f1: Act, tproj: torch.Tensor, dtproj: torch.Tensor, inv_std: Optional[torch.Tensor], n: int) -> torch.Tensor:
+        tk, fmt, dev, tape = self.tk, self.fmt, self.device, self.tape
+        col = lambda table, name: self.tp.cols(table, name)
         fmaps = [f1]
         hcur = tk.batchnorm(tk.conv(f1, self.conv2, stride=2, pad=3), self.bn1, self.bn_train, act=ACT_RELU)
         for li, blocks in enumerate(self.layers, start=1):
@@ -537,12 +585,17 @@ class TrainEngine:
             if blk["attn"] is not None:
                 out = _attention_block(tk, blk["attn"], out)
         up = tk.upsample2x(out)
-        a = tk.conv(up, self.final_up, pad=1)
         res = torch.empty((n, 1, 2 * out.h, 2 * out.w), dtype=torch.float32, device=dev)
-        call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None,
-             res.data_ptr(), a.n, a.h, a.w, a.c, 1, _stream())
+        if fmt != FMT_F32 and tk.k._c64_ok(up, self.final_up.fwd, 1, 1):
+            # the 64 -> 1 convolution rides in conv_up's epilogue (projection); conv_up's output is kept for the backward
+            a, pr = tk.conv(up, self.final_up, pad=1, proj=self.final_w[0])
+            call("sbgm_final_gather", pr.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None, res.data_ptr(), a.n, a.h, a.w,
+                 _stream())
+        else:
+            a = tk.conv(up, self.final_up, pad=1)
+            call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None,
+                 res.data_ptr(), a.n, a.h, a.w, a.c, 1, _stream())
         self._final = (a, inv_std)
-        self._time = (t, yy, dtproj)
         return res
 
     # -- backward ----------------------------------------------------------------------------------------
@@ -592,3 +645,90 @@ class TrainEngine:
         tk.tape = None
         self._final = self._time = None
         return grads
+
+
+class _InFlight:
+    """Clears the runner's busy flag when the autograd node that owns it is dropped without a backward."""
+
+    def __init__(self, runner: "TrainRunner") -> None:
+        self.runner = runner
+
+    def release(self) -> None:
+        if self.runner is not None:
+            self.runner.busy = False
+            self.runner = None
+
+    def __del__(self) -> None:
+        self.release()
+
+
+class TrainRunner:
+    """Runs `TrainEngine` eagerly for the first steps, then as two captured CUDA graphs (forward, backward).
+
+    A training step is ~1 500 kernel launches sequenced from Python; replaying it from a graph removes the host
+    from the step (the reference's torch-eager loop is launch-bound in the same way).  Everything a step reads that
+    changes between steps lives in static device buffers: the inputs are copied in, parameters are updated in place
+    by the optimizer (the graph re-packs them), BatchNorm running statistics are updated in place by the graph.
+    The runner is keyed (by the caller) on shapes, precision, mode and parameter storage; a second forward while a
+    step is in flight, or graphs disabled (SBGM_B200_TRAIN_GRAPHS=0), falls back to the eager engine."""
+
+    WARMUP = 2
+
+    def __init__(self, make_engine: Callable[[], "TrainEngine"], use_graphs: bool = True) -> None:
+        self.make_engine, self.use_graphs = make_engine, use_graphs
+        self.calls = 0
+        self.busy = False
+        self.eng: Optional[TrainEngine] = None
+        self.g_fwd = self.g_bwd = None
+        self.static: Dict[str, Optional[torch.Tensor]] = {}
+        self.out: Optional[torch.Tensor] = None
+        self.grads: Optional[Dict[str, torch.Tensor]] = None
+        self.keep: list = []
+
+    @staticmethod
+    def _copy_in(dst: Optional[torch.Tensor], src: Optional[torch.Tensor]) -> None:
+        if dst is not None:
+            dst.copy_(src)
+
+    def forward(self, x, t, y, planes, inv_std, grad_sync):
+        self.calls += 1
+        graph_ok = self.use_graphs and self.calls > self.WARMUP and not self.busy
+        if not graph_ok:
+            eng = self.make_engine()
+            eng.grad_sync = grad_sync
+            return eng.forward(x, t, y, planes, inv_std), ("eager", eng)
+        ins = dict(x=x, t=t, y=y, planes=planes, inv_std=inv_std)
+        if self.g_fwd is None:
+            self.eng = self.make_engine()
+            self.eng.grad_sync = grad_sync
+            self.static = {k: (None if v is None else v.clone()) for k, v in ins.items()}
+            torch.cuda.synchronize()
+            self.pool = torch.cuda.graph_pool_handle()
+            self.g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fwd, pool=self.pool):
+                self.eng._pack()                       # re-pack from the live parameters inside the graph
+                self.out = self.eng.forward(*(self.static[k] for k in ("x", "t", "y", "planes", "inv_std")))
+            self.keep.append(self.eng.tape)
+        else:
+            for k, v in ins.items():
+                self._copy_in(self.static[k], v)
+        self.g_fwd.replay()
+        self.busy = True
+        return self.out.clone(), ("graph", _InFlight(self))
+
+    def backward(self, handle, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+        kind, obj = handle
+        if kind == "eager":
+            return obj.backward(dout)
+        if self.g_bwd is None:
+            self.static["dout"] = dout.to(dtype=torch.float32).contiguous().clone()
+            torch.cuda.synchronize()
+            self.g_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_bwd, pool=self.pool):
+                self.grads = self.eng.backward(self.static["dout"])
+            self.keep.append(self.eng.flat)
+        else:
+            self.static["dout"].copy_(dout)
+        self.g_bwd.replay()
+        obj.release()
+        return self.grads

@@ -20,6 +20,8 @@ FORWARD_CASES = {
     "fwd_c3_64_cin7_seasons": (dict(n_lr=2, geo=True, seasons=True), dict(batch=2, size=64, n_lr=2, geo=True, seasons=True)),
     "fwd_32_instance_relu_3463": (dict(n_lr=1, norm="instance", activation="relu", block_layers=(3, 4, 6, 3)),
                                   dict(batch=2, size=32, n_lr=1)),
+    "fwd_32_transpose_gelu_h8": (dict(n_lr=1, use_resize_conv=False, activation="gelu", n_heads=8),
+                                 dict(batch=3, size=32, n_lr=1)),
     "fwd_128_cin2": (dict(n_lr=1), dict(batch=1, size=128, n_lr=1)),
 }
 SCORE_TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "bf16": 5e-2}
@@ -46,7 +48,8 @@ def test_score_matches_reference_golden(golden, name, precision):
     ck, bk = FORWARD_CASES[name]
     net, _, _ = _model(ck, precision)
     b = synth_batch(**bk)
-    out = net(*[_cuda(v) for v in b.model_args()]).cpu()
+    with torch.no_grad():      # the inference engine; with grad enabled the same call runs the training graph (test_gpu_train.py)
+        out = net(*[_cuda(v) for v in b.model_args()]).cpu()
     err = rel_l2(out, golden[f"{name}/score"])
     print(f"{name} [{precision}] rel-L2 = {err:.3e}")
     assert err < SCORE_TOL[precision], f"rel-L2 {err:.3e}"
@@ -230,7 +233,7 @@ def test_score_256x256_matches_oracle():
     b = synth_batch(batch=1, size=256, n_lr=1)
     with torch.no_grad():
         want = score_ref.score_forward(sd, cfg, *b.model_args())
-    got = net(*[_cuda(v) for v in b.model_args()]).cpu()
+        got = net(*[_cuda(v) for v in b.model_args()]).cpu()
     assert rel_l2(got, want) < 1e-3
 
 
@@ -243,5 +246,5 @@ def test_non_power_of_two_size_matches_oracle():
         b = synth_batch(batch=2, size=96, n_lr=1)
         with torch.no_grad():
             want = score_ref.score_forward(sd, cfg, *b.model_args())
-        got = net(*[_cuda(v) for v in b.model_args()]).cpu()
+            got = net(*[_cuda(v) for v in b.model_args()]).cpu()
         assert rel_l2(got, want) < tol, precision

@@ -17,6 +17,7 @@ from sbgm_danra_b200 import _lib
 from sbgm_danra_b200._smoke import build_model
 
 
+@torch.no_grad()
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--precision", default="bf16x3")
