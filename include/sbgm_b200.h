@@ -259,13 +259,17 @@ int sbgm_norm_apply(const void* x, size_t x_plane, const float* stats, int per_s
                     int tproj_pre_act, int act, void* y, size_t y_plane, int fmt, int n, int hw, int c, void* stream);
 /* backward of sbgm_norm_apply: dx, dadd (= gradient w.r.t. the pre-activation; NULL to skip), dgamma/dbeta[c]
  * (NULL for non-affine norms), dtproj[n][dtproj_stride] (NULL to skip).  `scratch`:
- * sbgm_norm_backward_scratch_floats(n, c) floats. */
+ * sbgm_norm_backward_scratch_floats(n, c) floats.
+ * Synchronised BatchNorm (data-parallel training with whole-batch statistics): call with stage = 1 (per-sample sums
+ * [n][c][3] land at scratch + sbgm_norm_backward_sums_offset(n, c)), all-gather those over the ranks, then stage = 2 with
+ * sums_all[n_all][c][3].  stage = 0 does everything locally (sums_all = NULL). */
 size_t sbgm_norm_backward_scratch_floats(int n, int c);
+size_t sbgm_norm_backward_sums_offset(int n, int c);
 int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, const float* stats, int per_sample_stats,
                        int groups, const float* gamma, const float* beta, const void* add, size_t add_plane,
                        const float* tproj, int tproj_stride, int tproj_pre_act, int act, void* dx, size_t dx_plane,
                        void* dadd, size_t dadd_plane, float* dgamma, float* dbeta, float* dtproj, int dtproj_stride,
-                       int fmt, int n, int hw, int c, float* scratch, void* stream);
+                       int fmt, int n, int hw, int c, float* scratch, int stage, const float* sums_all, int n_all, void* stream);
 /* nn.LayerNorm backward (ImageSelfAttention.ln1 / ln2, score_unet.py:136-148) */
 size_t sbgm_layernorm_backward_scratch_floats(int c);
 int sbgm_layernorm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, const float* gamma, float eps,

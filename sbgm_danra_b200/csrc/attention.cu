@@ -165,6 +165,10 @@ static int launch_attention(const void* qkv, size_t plane, void* out, size_t out
 
 }  // namespace sbgm
 
+namespace sbgm {
+int attention_mma_dispatch(const void* qkv, size_t plane, void* out, size_t out_plane, int fmt, int b, int s, int c, int heads,
+                           cudaStream_t st);
+}
 using namespace sbgm;
 
 extern "C" int sbgm_attention(const void* qkv, size_t qkv_plane, void* out, size_t out_plane, int fmt,
@@ -173,6 +177,10 @@ extern "C" int sbgm_attention(const void* qkv, size_t qkv_plane, void* out, size
   const int d = c / heads;
   SBGM_REQUIRE(d % 8 == 0 && d <= 512, "attention: head dim %d must be a multiple of 8 and <= 512", d);
   cudaStream_t st = as_stream(stream);
+  {   // tensor-core formats: warp-level MMA flash attention (attention_mma.cu) for head dims 32 / 64 / 128
+    const int rc = attention_mma_dispatch(qkv, qkv_plane, out, out_plane, fmt, b, s, c, heads, st);
+    if (rc >= 0) return rc;
+  }
   const int dpl = (d + 31) / 32;
 #define SBGM_ATTN(D) SBGM_DISPATCH_FMT(fmt, return (launch_attention<FMT, D>(qkv, qkv_plane, out, out_plane, b, s, c, heads, st)))
   if (dpl <= 1) { SBGM_ATTN(1); }

@@ -222,7 +222,8 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ partials, int c
 
 // Stage 2b: dgamma / dbeta (sum over samples) and the two projection coefficients of each statistics group:
 //   A = sum(gamma * dU) / cnt,  B = sum(gamma * dU * xhat) / cnt      (coef[stat index][2])
-__global__ void norm_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ gamma, int n, int c, int n_stride,
+__global__ void norm_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ sums_all, int n_all,
+                                     const float* __restrict__ gamma, int n, int c, int n_stride,
                                      int cpg, float inv_cnt, int fixed_stats, float* __restrict__ coef, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta) {
   pdl_grid_sync();
@@ -239,11 +240,11 @@ __global__ void norm_bwd_coef_kernel(const float* __restrict__ sums, const float
   }
   if (fixed_stats) {                // eval-mode BatchNorm: the statistics are constants, no projection terms
     if (i < c) coef[2 * i] = coef[2 * i + 1] = 0.0f;
-  } else if (n_stride == 0) {       // BatchNorm: one statistics group per channel, spanning the batch
+  } else if (n_stride == 0) {       // BatchNorm: one statistics group per channel, spanning the (global) batch
     if (i < c) {
       float a = 0.0f, b = 0.0f;
-      for (int k = 0; k < n; ++k) {
-        const float* s = sums + (static_cast<size_t>(k) * c + i) * 3;
+      for (int k = 0; k < n_all; ++k) {
+        const float* s = sums_all + (static_cast<size_t>(k) * c + i) * 3;
         a += s[1];
         b += s[2];
       }
@@ -666,6 +667,8 @@ int sbgm_norm_apply(const void* x, size_t x_plane, const float* stats, int per_s
   return check_launch("norm_apply");
 }
 
+size_t sbgm_norm_backward_sums_offset(int n, int c) { return static_cast<size_t>(n) * kNormChunks * c * 3; }
+
 size_t sbgm_norm_backward_scratch_floats(int n, int c) {
   return static_cast<size_t>(n) * kNormChunks * c * 3 + static_cast<size_t>(n) * c * 3 + static_cast<size_t>(n) * c * 2 + 64;
 }
@@ -674,8 +677,10 @@ int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_
                        int groups, const float* gamma, const float* beta, const void* add, size_t add_plane,
                        const float* tproj, int tproj_stride, int tproj_pre_act, int act, void* dx, size_t dx_plane,
                        void* dadd, size_t dadd_plane, float* dgamma, float* dbeta, float* dtproj, int dtproj_stride,
-                       int fmt, int n, int hw, int c, float* scratch, void* stream) {
+                       int fmt, int n, int hw, int c, float* scratch, int stage, const float* sums_all, int n_all, void* stream) {
   SBGM_REQUIRE(c % 8 == 0 && c <= 2048 && groups >= 1 && c % groups == 0, "norm_backward: bad c=%d groups=%d", c, groups);
+  SBGM_REQUIRE(stage >= 0 && stage <= 2, "norm_backward: stage %d", stage);
+  SBGM_REQUIRE(sums_all == nullptr || (per_sample_stats == 0 && n_all >= n), "norm_backward: gathered sums are for batch statistics only");
   const int vecs = c / 8;
   SBGM_REQUIRE(vecs <= 256, "norm_backward: c too large");
   const NormArgs a = make_norm_args(x, x_plane, stats, per_sample_stats, groups, gamma, beta, add, add_plane, tproj, tproj_stride,
@@ -687,17 +692,22 @@ int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_
   const int lanes = 256 / vecs;
   const size_t smem1 = static_cast<size_t>(lanes) * c * 3 * sizeof(float);
   const int n_groups_total = per_sample_stats == 1 ? n * groups : c;
-  const double cnt = per_sample_stats == 1 ? static_cast<double>(hw) * (c / groups) : static_cast<double>(n) * hw;
+  if (sums_all == nullptr) { sums_all = sums; n_all = n; }
+  const double cnt = per_sample_stats == 1 ? static_cast<double>(hw) * (c / groups) : static_cast<double>(n_all) * hw;
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
   // enough pixels per thread to amortise the per-block prologue: ~8 per lane
   const int chunks = max(1, min(kNormChunks, hw / (lanes * 8)));
   dim3 g1(chunks, n), g3(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
-    launch_k((norm_bwd_partial_kernel<FMT>), g1, 256, smem1, st, a, dy, dy_plane, partials, chunks);
-    launch_k((norm_bwd_reduce_kernel), n, 256, 0, st, partials, c, chunks, tproj_pre_act, sums, dtproj, dtproj_stride);
-    launch_k((norm_bwd_coef_kernel), ceil_div(max(c, n_groups_total), 256), 256, 0, st, sums, gamma, n, c, a.n_stride, a.cpg,
-                                                                                static_cast<float>(1.0 / cnt), per_sample_stats == 2, coef, dgamma, dbeta);
-    launch_k((norm_bwd_apply_kernel<FMT>), g3, 256, 0, st, a, dy, dy_plane, coef, dx, dx_plane, dadd, dadd_plane);
+    if (stage != 2) {
+      launch_k((norm_bwd_partial_kernel<FMT>), g1, 256, smem1, st, a, dy, dy_plane, partials, chunks);
+      launch_k((norm_bwd_reduce_kernel), n, 256, 0, st, partials, c, chunks, tproj_pre_act, sums, dtproj, dtproj_stride);
+    }
+    if (stage != 1) {
+      launch_k((norm_bwd_coef_kernel), ceil_div(max(c, n_groups_total), 256), 256, 0, st, sums, sums_all, n_all, gamma, n, c, a.n_stride,
+               a.cpg, static_cast<float>(1.0 / cnt), per_sample_stats == 2, coef, dgamma, dbeta);
+      launch_k((norm_bwd_apply_kernel<FMT>), g3, 256, 0, st, a, dy, dy_plane, coef, dx, dx_plane, dadd, dadd_plane);
+    }
   });
   return check_launch("norm_backward");
 }

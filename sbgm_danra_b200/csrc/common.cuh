@@ -35,7 +35,9 @@ void note_launch_error(cudaError_t e);
 bool pdl_enabled();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_grid_sync() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // wait only: the dependents are released when this grid's blocks exit (implicit trigger).  Releasing them at the top
+  // (griddepcontrol.launch_dependents before the wait) measured 3% SLOWER on the sampler step and 8% on the training step:
+  // blocks of the next kernels become resident early and take issue slots / shared memory from the running grid's tail.
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 template <typename... KArgs, typename... Args>
@@ -144,7 +146,9 @@ struct Act<SBGM_FMT_BF16X2> {
   }
 
 // ---- small math ---------------------------------------------------------------------------
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// SiLU with the hardware exp2 / reciprocal (MUFU): ~2 ulp, against a 1e-3 parity gate; the GroupNorm+SiLU pass over the
+// 64x64 maps was instruction-bound (not HBM-bound) with the IEEE expf + division sequence.
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {

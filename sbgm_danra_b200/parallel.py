@@ -13,7 +13,7 @@ the GPUs of one box.  `TrainEngine` writes every parameter gradient as a view of
   * the first step all-reduces the whole buffer at the end and records which parameters receive gradients
     (the final block's unused time projection etc. never do); later steps use that set.
 
-Usage:  parallel.attach(model, group=None)   then train as usual.  Ranks must use distinct batches; the Philox
+Usage:  parallel.attach(model, group=None, sync_bn=False)   then train as usual.  Ranks must use distinct batches; the Philox
 stream is keyed by global member index via score_sampling.set_ensemble_shard(first_member=rank * B_local).
 """
 from __future__ import annotations
@@ -87,8 +87,8 @@ class GradSync:
     """The hook `TrainEngine.backward` drives: `begin(engine)`, `progress(names)` after every tape step,
     `finish()` once all gradients are enqueued.  All-reduces on a side stream, averages, then joins."""
 
-    def __init__(self, group=None, bucket_bytes: int = BUCKET_BYTES) -> None:
-        self.group, self.bucket_elems = group, max(1, bucket_bytes // 4)
+    def __init__(self, group=None, bucket_bytes: int = BUCKET_BYTES, sync_bn: bool = False) -> None:
+        self.group, self.bucket_elems, self.sync_bn = group, max(1, bucket_bytes // 4), sync_bn
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.expected: Optional[List[str]] = None
         self.bucketer: Optional[GradBucketer] = None
@@ -144,9 +144,13 @@ class GradSync:
         self.flat = None
 
 
-def attach(model, group=None, bucket_bytes: int = BUCKET_BYTES) -> GradSync:
-    """Make `loss.backward()` through `model` (a ScoreNet of this package) average gradients over `group`."""
-    sync = GradSync(group, bucket_bytes)
+def attach(model, group=None, bucket_bytes: int = BUCKET_BYTES, sync_bn: bool = False) -> GradSync:
+    """Make `loss.backward()` through `model` (a ScoreNet of this package) average gradients over `group`.
+
+    sync_bn=True additionally synchronises the BatchNorm batch statistics (forward: all-gather of the per-chunk partial
+    sums; backward: all-gather of the per-sample gradient sums), so that N ranks with B/N samples each reproduce the
+    reference's single-process batch-B statistics exactly; the default is DDP-style rank-local statistics."""
+    sync = GradSync(group, bucket_bytes, sync_bn)
     model._grad_sync = sync
     return sync
 

@@ -133,6 +133,7 @@ class TrainKernels:
         self.k = Kernels(fmt, device)
         self.tape: Optional[Tape] = None
         self.param_grad = flat_grad
+        self.sync_bn = None          # torch.distributed process group: synchronise BatchNorm statistics over it
         self._scratch: Dict[str, torch.Tensor] = {}
 
     # -- scratch management --------------------------------------------------------------------
@@ -249,11 +250,27 @@ class TrainKernels:
             dg = self.param_grad(gamma_name, (x.c,)) if gamma_name else None
             db = self.param_grad(beta_name, (x.c,)) if beta_name else None
             ws = self.scratch("norm_bwd", _lib.query("sbgm_norm_backward_scratch_floats", x.n, x.c))
-            call("sbgm_norm_backward", dy.ptr, dy.plane, x.ptr, x.plane, stats.data_ptr(), mode, groups, _ptr(gamma), _ptr(beta),
-                 None if add is None else add.ptr, 0 if add is None else add.plane, _ptr(tproj),
-                 tproj.stride(0) if tproj is not None else 0, tproj_pre, act, dx.ptr, dx.plane,
-                 None if dadd is None else dadd.ptr, 0 if dadd is None else dadd.plane, _ptr(dg), _ptr(db),
-                 _ptr(dtproj), dtproj.stride(0) if dtproj is not None else 0, fmt, x.n, hw, x.c, ws.data_ptr(), _stream())
+
+            def run(stage: int, sums_all: Optional[torch.Tensor], n_all: int) -> None:
+                call("sbgm_norm_backward", dy.ptr, dy.plane, x.ptr, x.plane, stats.data_ptr(), mode, groups, _ptr(gamma), _ptr(beta),
+                     None if add is None else add.ptr, 0 if add is None else add.plane, _ptr(tproj),
+                     tproj.stride(0) if tproj is not None else 0, tproj_pre, act, dx.ptr, dx.plane,
+                     None if dadd is None else dadd.ptr, 0 if dadd is None else dadd.plane, _ptr(dg), _ptr(db),
+                     _ptr(dtproj), dtproj.stride(0) if dtproj is not None else 0, fmt, x.n, hw, x.c, ws.data_ptr(), stage,
+                     _ptr(sums_all), n_all, _stream())
+
+            if mode == 0 and self.sync_bn is not None:
+                # synchronised BatchNorm: the projection terms need the sums over the WHOLE batch
+                import torch.distributed as dist
+                run(1, None, 0)
+                off = _lib.query("sbgm_norm_backward_sums_offset", x.n, x.c)
+                local = ws[off:off + x.n * x.c * 3]
+                world = dist.get_world_size(self.sync_bn)
+                sums_all = torch.empty(world * local.numel(), dtype=torch.float32, device=self.device)
+                dist.all_gather_into_tensor(sums_all, local, group=self.sync_bn)
+                run(2, sums_all, world * x.n)
+            else:
+                run(0, None, 0)
             tape.add(x, dx)
             if add is not None:
                 tape.add(add, dadd)
@@ -270,7 +287,16 @@ class TrainKernels:
         if train:
             part = torch.empty((x.n, NORM_CHUNKS, c, 2), dtype=torch.float32, device=self.device)
             call("sbgm_norm_partials", x.ptr, x.plane, self.fmt, x.n, hw, c, c, part.data_ptr(), _stream())
-            call("sbgm_bn_stats_finalize", part.data_ptr(), NORM_CHUNKS, x.n, hw, c, BN_EPS, BN_MOMENTUM, stats.data_ptr(),
+            n_all = x.n
+            if self.sync_bn is not None:
+                # whole-batch statistics: gather every rank's partial sums (rank-major = the unsharded sample order, so the
+                # finalised statistics are bit-identical to a single-GPU run of the full batch)
+                import torch.distributed as dist
+                world = dist.get_world_size(self.sync_bn)
+                gathered = torch.empty((world * x.n, NORM_CHUNKS, c, 2), dtype=torch.float32, device=self.device)
+                dist.all_gather_into_tensor(gathered, part, group=self.sync_bn)
+                part, n_all = gathered, world * x.n
+            call("sbgm_bn_stats_finalize", part.data_ptr(), NORM_CHUNKS, n_all, hw, c, BN_EPS, BN_MOMENTUM, stats.data_ptr(),
                  bn["running_mean"].data_ptr(), bn["running_var"].data_ptr(), _stream())
             mode = 0
         else:
@@ -690,17 +716,23 @@ class TrainRunner:
         if dst is not None:
             dst.copy_(src)
 
+    def _engine(self, grad_sync) -> "TrainEngine":
+        eng = self.make_engine()
+        eng.grad_sync = grad_sync
+        if grad_sync is not None and getattr(grad_sync, "sync_bn", False) and grad_sync.world > 1:
+            import torch.distributed as dist
+            eng.tk.sync_bn = grad_sync.group if grad_sync.group is not None else dist.group.WORLD
+        return eng
+
     def forward(self, x, t, y, planes, inv_std, grad_sync):
         self.calls += 1
         graph_ok = self.use_graphs and self.calls > self.WARMUP and not self.busy
         if not graph_ok:
-            eng = self.make_engine()
-            eng.grad_sync = grad_sync
+            eng = self._engine(grad_sync)
             return eng.forward(x, t, y, planes, inv_std), ("eager", eng)
         ins = dict(x=x, t=t, y=y, planes=planes, inv_std=inv_std)
         if self.g_fwd is None:
-            self.eng = self.make_engine()
-            self.eng.grad_sync = grad_sync
+            self.eng = self._engine(grad_sync)
             self.static = {k: (None if v is None else v.clone()) for k, v in ins.items()}
             torch.cuda.synchronize()
             self.pool = torch.cuda.graph_pool_handle()

@@ -19,6 +19,51 @@ from sbgm_danra_b200._smoke import build_model
 from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
 
 
+def train_check(rank, world, dev, net, cfg, ck) -> bool:
+    """Data-parallel DSM step: every rank takes its slice of one global batch, gradients are averaged by the bucketed
+    all-reduce (sbgm_danra_b200.parallel); rank 0 recomputes the full batch alone.  BatchNorm in eval mode (constant
+    statistics) so that the per-sample losses do not couple and the two must agree to rounding.  Steps 3+ replay the
+    captured CUDA graphs with the NCCL all-reduces inside."""
+    from sbgm_danra_b200 import parallel
+    from sbgm_danra_b200.score_unet import loss_fn
+    per, size = 2, 32
+    total = per * world
+    b = synth_batch(batch=total, size=size, shared_cond=False, **ck)
+    cut = lambda v, s: None if v is None else v[s].to(dev)
+
+    def grads(sl, first, members):
+        ss.manual_seed(77)
+        ss.set_ensemble_shard(first, members, None)
+        net.zero_grad(set_to_none=True)
+        loss = loss_fn(net, cut(b.x, sl), marginal_prob_std_fn, y=cut(b.y, sl), cond_img=cut(b.cond_img, sl),
+                       lsm_cond=cut(b.lsm_cond, sl), topo_cond=cut(b.topo_cond, sl), sdf_cond=cut(b.sdf_cond, sl))
+        loss.backward()
+        return loss.detach(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    ok = True
+    for mode, sync_bn in (("eval-mode BatchNorm", False), ("train-mode BatchNorm, synchronised statistics", True)):
+        net.train(sync_bn)
+        sync = parallel.attach(net, bucket_bytes=4 << 20, sync_bn=sync_bn)
+        for step in range(4):
+            loss, g = grads(slice(rank * per, (rank + 1) * per), rank * per, total)
+            dist.all_reduce(loss)
+            loss /= world
+        parallel.detach(net)
+        net._train_runners.clear()
+        if rank == 0:
+            loss_full, g_full = grads(slice(None), 0, None)
+            num = sum(float((g[k] - g_full[k]).double().pow(2).sum()) for k in g_full)
+            den = sum(float(g_full[k].double().pow(2).sum()) for k in g_full)
+            err = (num / den) ** 0.5
+            print(f"[multi-gpu x{world}] DSM step ({mode}): averaged sharded gradients vs single-GPU full batch rel-L2 = {err:.3e}; "
+                  f"loss {float(loss):.6f} vs {float(loss_full):.6f}; buckets {sync.stats}")
+            ok = ok and err < 1e-4 and abs(float(loss) - float(loss_full)) / abs(float(loss_full)) < 1e-5 and sync.stats["overlapped"] > 0
+        dist.barrier()
+        net._train_runners.clear()
+    net.eval()
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -54,6 +99,7 @@ def main():
             print(f"[multi-gpu x{world}] {name}: sharded vs single-GPU rel-L2 = {err:.3e}")
             ok = ok and err < 1e-4
         dist.barrier()
+    ok = train_check(rank, world, dev, net, cfg, ck) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     good = int(flag.item()) == 1
