@@ -11,7 +11,10 @@
 //     the image.  Tap (r, s) reads slab s at byte offset r * 16 * 128 -- 1024-aligned, so the UMMA
 //     descriptor needs no base offset -- i.e. 3 x 20 KB serve nine taps;
 //   * two TMEM accumulators (2 x 64 columns) ping-pong between MMA issue and the epilogue warps.
-// Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..5 = epilogue.
+// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..5 = epilogue group 0 (even tiles,
+// accumulator 0), 6..9 = epilogue group 1 (odd tiles, accumulator 1).  ncu showed the kernel epilogue-bound: one
+// tile's epilogue (tcgen05.ld, bias, split-bf16 rounding, transpose, store) is ~1.4x its MMA time on a single warp
+// per scheduler; two groups alternating tiles give each epilogue two tile periods.
 #include "tc_common.cuh"
 
 namespace sbgm {
@@ -37,7 +40,7 @@ struct C64Cfg {
 };
 
 template <int FMT, int kStages, int ACT, int PROJ>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const C64Params p) {
   pdl_grid_sync();
   using Cfg = C64Cfg<FMT, kStages>;
@@ -139,10 +142,12 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     __syncwarp();
   } else {
     const int quarter = warp & 3;
+    const uint32_t group = (warp - 2) >> 2;          // which accumulator buffer / tile parity this warp serves
     const int row = quarter * 32 + lane;
     const int w_l = row % kTW, h_l = row / kTW;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1u) != group) continue;
       const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
       const int oy = th * kTH + h_l, ox = tw * kTW + w_l;
       const size_t pix = (static_cast<size_t>(n) * p.h + oy) * p.w + ox;
@@ -204,7 +209,7 @@ static int launch_c64_inst(const CUtensorMap& ta, const CUtensorMap& tb, const C
     return 1;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  launch_k((kern), grid, 192, Cfg::kSmemBytes, st, ta, tb, p);
+  launch_k((kern), grid, 320, Cfg::kSmemBytes, st, ta, tb, p);
   return check_launch("conv3x3_c64");
 }
 

@@ -16,8 +16,10 @@
 // * BF16X2 ("split") activations and weights carry hi|lo bf16 planes; the three products
 //   hi*hi + lo*hi + hi*lo accumulate into the same TMEM tile (fp32-class accuracy, 16-bit operands).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (warp w may only touch TMEM lanes 32*(w%4) .. +31).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (warp w may only touch
+// TMEM lanes 32*(w%4) .. +31).  Tiles with BLOCK_N >= 128 get a second epilogue group (warps 6..9, 320 threads) that
+// takes the upper half of the columns: ncu showed a tile's epilogue (thousands of dependent instructions on one warp
+// per scheduler) as long as the whole K loop of the mid-size layers, with nothing to overlap it at one CTA per SM.
 #include "tc_common.cuh"
 
 namespace sbgm {
@@ -46,8 +48,15 @@ struct ConvTcCfg {
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
+template <int BLOCK_N>
+struct ConvTcThreads {
+  static constexpr int kEpiGroups = BLOCK_N >= 128 ? 2 : 1;
+  static constexpr int kThreads = 64 + 128 * kEpiGroups;
+  static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;
+};
+
 template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(ConvTcThreads<BLOCK_N>::kThreads, ConvTcThreads<BLOCK_N>::kMinCtas)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
   pdl_grid_sync();
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
@@ -139,6 +148,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ---- epilogue: TMEM -> registers -> bias/residual/act/time -> NHWC global ----
     const int quarter = warp & 3;
+    constexpr int kColsPerGroup = BLOCK_N / ConvTcThreads<BLOCK_N>::kEpiGroups;
+    const int c_begin = ((warp - 2) >> 2) * kColsPerGroup, c_end = c_begin + kColsPerGroup;
     const int row = quarter * 32 + lane;
     const int w_l = row % p.w_tile, h_l = (row / p.w_tile) % p.h_tile, n_l = row / (p.w_tile * p.h_tile);
     const int n = n0 + n_l, oy = ho0 + h_l, ox = wo0 + w_l;
@@ -162,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (!PROJ && p.splits > 1) {                    // split-K: raw fp32 partial tile, finished by splitk_finalize_kernel
       float* dst = p.ws + (static_cast<size_t>(blockIdx.z) * p.n * p.ho * p.wo + pix) * p.ep.cout + co0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t ra[32];
         load_acc(c0, ra);
         if (valid) {
@@ -174,7 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     } else {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {      // the whole warp walks the tile in 64-channel blocks
+      for (int c0 = c_begin; c0 < c_end; c0 += 64) {  // the whole warp walks its share of the tile in 64-channel blocks
         uint32_t ra[32], rb[32];
         load_acc(c0, ra);
         load_acc(c0 + 32, rb);
@@ -324,7 +335,7 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
     return 1;
   }
   dim3 grid(m_tiles, p.ep.cout / BLOCK_N, p.splits);
-  launch_k((kern), grid, 192, Cfg::kSmemBytes, st, ta, tb, p);
+  launch_k((kern), grid, ConvTcThreads<BLOCK_N>::kThreads, Cfg::kSmemBytes, st, ta, tb, p);
   if (!PROJ && p.splits > 1) {
     const size_t pixels = static_cast<size_t>(p.n) * p.ho * p.wo;
     const size_t items = pixels * (p.ep.cout / 8);
@@ -369,6 +380,9 @@ static void conv_tc_geometry(int n, int h, int w, int cin, int cout, int kh, int
   p->cin_blocks = cin / 64;
   *m_tiles = p->tiles_w * p->tiles_h * ceil_div(n, p->n_tile);
   *block_n = (cout % 256 == 0 && planes == 1) ? 256 : (cout % 128 == 0 ? 128 : 64);
+  // under-filled grids (the attention blocks' Linear layers): narrower tiles = more CTAs and a shorter epilogue each
+  // (short K loops only: with a long K loop the narrower tile re-reads the activation tile more often than it saves)
+  while (*block_n > 64 && kh * kw * p->cin_blocks <= 8 && static_cast<long long>(*m_tiles) * (cout / *block_n) * 2 <= 148) *block_n /= 2;
   p->splits = pick_splits(*m_tiles * (cout / *block_n), kh * kw * p->cin_blocks);
 }
 

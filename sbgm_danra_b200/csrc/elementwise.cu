@@ -269,21 +269,36 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, size_t x_plane, cons
   }
   __syncthreads();
   const int vecs = c >> 3;
-  const size_t total = static_cast<size_t>(hw) * vecs;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int vec = static_cast<int>(i % vecs);
-    const size_t idx = (static_cast<size_t>(n) * hw) * c + i * 8;
+  const uint32_t total = static_cast<uint32_t>(hw) * vecs;          // < 2^32 (host-checked)
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const int vec = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) % vecs);
+  float sc8[8], sh8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc8[j] = coef[2 * (vec * 8 + j)];
+    sh8[j] = coef[2 * (vec * 8 + j) + 1];
+  }
+  const bool fixed_vec = (stride % vecs) == 0;                      // always for power-of-two channel counts
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    if (!fixed_vec) {
+      const int vv = static_cast<int>(i % vecs);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc8[j] = coef[2 * (vv * 8 + j)];
+        sh8[j] = coef[2 * (vv * 8 + j) + 1];
+      }
+    }
+    const size_t idx = (static_cast<size_t>(n) * hw) * c + static_cast<size_t>(i) * 8;
     float v[8];
     Act<FMT>::load8(x, x_plane, idx, v);
     if (skip) {
       float sk[8];
       Act<FMT>::load8(skip, skip_plane, idx, sk);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], coef[2 * (vec * 8 + j)], coef[2 * (vec * 8 + j) + 1]) + sk[j];
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc8[j], sh8[j]) + sk[j];
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], coef[2 * (vec * 8 + j)], coef[2 * (vec * 8 + j) + 1]);
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc8[j], sh8[j]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act);
@@ -344,12 +359,11 @@ template <int FMT>
 __global__ void upsample2x_kernel(const void* __restrict__ x, size_t x_plane, void* __restrict__ y, size_t y_plane,
                                   int n, int h, int w, int c) {
   pdl_grid_sync();
-  const int vecs = c >> 3;
-  const size_t total = static_cast<size_t>(n) * h * w * vecs;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t vecs = c >> 3;
+  const uint32_t total = static_cast<uint32_t>(n) * h * w * vecs;   // < 2^32 (host-checked): 32-bit divisions only
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int vec = static_cast<int>(i % vecs);
-    size_t r = i / vecs;
+    uint32_t r = i / vecs;
     const int ix = static_cast<int>(r % w);
     r /= w;
     const int iy = static_cast<int>(r % h);
@@ -391,12 +405,12 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, const float* __r
                                    void* __restrict__ out, size_t out_plane, int n, int h, int w) {
   pdl_grid_sync();
   const int ho = h / 2, wo = w / 2;
-  const size_t total = static_cast<size_t>(n) * ho * wo * nch * 8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(n) * ho * wo * nch * 8;    // < 2^32 (host-checked): 32-bit divisions only
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = static_cast<int>(i & 7);
     const int cl = static_cast<int>((i >> 3) % nch);
-    const size_t pix = i / (static_cast<size_t>(nch) * 8);
-    const int ox = static_cast<int>(pix % wo), oy = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<size_t>(wo) * ho));
+    const uint32_t pix = i / (static_cast<uint32_t>(nch) * 8);
+    const int ox = static_cast<int>(pix % wo), oy = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<uint32_t>(wo) * ho));
     const int c = c_begin + cl;
     const float* src = (c == 0) ? x + static_cast<size_t>(b) * h * w
                                 : planes + (static_cast<size_t>(np == 1 ? 0 : b) * cc + (c - 1)) * h * w;
@@ -407,7 +421,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, const float* __r
       const int ix = 2 * ox + s - 3;
       v[s] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(src + static_cast<size_t>(iy) * w + ix) : 0.0f;
     }
-    Act<FMT>::store8(out, out_plane, i * 8, v);
+    Act<FMT>::store8(out, out_plane, static_cast<size_t>(i) * 8, v);
   }
 }
 
@@ -464,14 +478,13 @@ __global__ void final_gather_kernel(const float* __restrict__ proj, const float*
                                     const float* __restrict__ inv_std, int inv_stride, int inv_step_stride,
                                     const int32_t* __restrict__ step_counter, float* __restrict__ out, int n, int h, int w) {
   pdl_grid_sync();
-  const size_t total = static_cast<size_t>(n) * h * w;
+  const uint32_t total = static_cast<uint32_t>(n) * h * w;
   const int step = step_counter ? *step_counter : 0;
   const float b0 = bias[0];
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int x = static_cast<int>(i % w);
     const int y = static_cast<int>((i / w) % h);
-    const int b = static_cast<int>(i / (static_cast<size_t>(w) * h));
+    const int b = static_cast<int>(i / (static_cast<uint32_t>(w) * h));
     float acc = b0;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -632,6 +645,7 @@ int sbgm_upsample2x(const void* x, size_t x_plane, void* y, size_t y_plane, int 
                     void* stream) {
   SBGM_REQUIRE(c % 8 == 0, "upsample2x: c=%d must be a multiple of 8", c);
   const size_t total = static_cast<size_t>(n) * h * w * (c / 8);
+  SBGM_REQUIRE(total < (1ull << 32), "upsample2x: tensor too large for 32-bit indexing");
   SBGM_DISPATCH_FMT(fmt, (launch_k((upsample2x_kernel<FMT>), grid_for(total, 256), 256, 0, as_stream(stream), 
                              x, x_plane, y, y_plane, n, h, w, c)));
   return check_launch("upsample2x");
@@ -644,6 +658,7 @@ int sbgm_stem_im2col(const float* x, const float* planes, int np, int cc, int c_
   SBGM_REQUIRE(c_end <= 1 || (planes != nullptr && (np == 1 || np == n)), "stem_im2col: conditioning planes missing or batch %d != 1, %d", np, n);
   const int nch = c_end - c_begin;
   const size_t total = static_cast<size_t>(n) * (h / 2) * (w / 2) * nch * 8;
+  SBGM_REQUIRE(total < (1ull << 32), "stem_im2col: tensor too large for 32-bit indexing");
   SBGM_DISPATCH_FMT(fmt, (launch_k((stem_im2col_kernel<FMT>), grid_for(total, 256), 256, 0, as_stream(stream), x, planes, np, cc, c_begin, nch, out,
                                                                                                 out_plane, n, h, w)));
   return check_launch("stem_im2col");

@@ -40,6 +40,12 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Timing ablations only (tools/ablate.py): SBGM_B200_SKIP=attn,attn_core,gn,ln,upsample_math drops the named operator from
+# the launch sequence so that its in-graph cost can be read off as a difference.  Results are garbage when set.
+import os as _os
+_SKIP = frozenset(x for x in _os.environ.get("SBGM_B200_SKIP", "").split(",") if x)
+
+
 class Act:
     """An NHWC activation tensor in one of the three storage formats."""
     __slots__ = ("buf", "fmt", "n", "h", "w", "c")
@@ -226,6 +232,8 @@ class Kernels:
 
     def groupnorm(self, x: Act, gamma, beta, groups: int, act: int = ACT_NONE, skip: Optional[Act] = None,
                   tproj: Optional[torch.Tensor] = None, stats=None) -> Act:
+        if "gn" in _SKIP:
+            return x
         if stats is not None and (x.c // 8) % groups == 0:
             part, chunks = stats
             out = x.like()
@@ -245,6 +253,8 @@ class Kernels:
         return out
 
     def layernorm(self, x: Act, gamma, beta) -> Act:
+        if "ln" in _SKIP:
+            return x
         out = x.like()
         rows = x.n * x.h * x.w
         call("sbgm_layernorm", x.ptr, x.plane, gamma.data_ptr(), beta.data_ptr(), LN_EPS, out.ptr, out.plane, self.fmt,
@@ -258,6 +268,8 @@ class Kernels:
 
     def attention_core(self, qkv: Act, b: int, s: int, c: int, heads: int) -> Act:
         out = Act(self.fmt, 1, 1, b * s, c, self.device)
+        if "attn_core" in _SKIP:
+            return out
         call("sbgm_attention", qkv.ptr, qkv.plane, out.ptr, out.plane, self.fmt, b, s, c, heads, _stream())
         return out
 
@@ -275,6 +287,8 @@ class AttentionW:
 
 def attention_block(k: Kernels, aw: AttentionW, x: Act) -> Act:
     """ImageSelfAttention.forward (score_unet.py:136-148) on NHWC tokens (the flatten is free)."""
+    if "attn" in _SKIP:
+        return x
     tok = x.tokens()
     b, s, c = x.n, x.h * x.w, x.c
     h1 = k.layernorm(tok, *aw.ln1)
