@@ -12,25 +12,30 @@ struct TapList {
   int idx[64];
 };
 
+// One thread per (o, 8 consecutive i): it walks the tap list, so the fp32 source of a thread (8 x khw contiguous floats in
+// the forward orientation) is pulled through L1 once and every output vector is one 16-byte store per plane.
 template <int FMT>
 __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int khw, const TapList taps, int transpose,
                                    void* __restrict__ out, size_t out_plane) {
   pdl_grid_sync();
-  const int oo = transpose ? cin : cout, ii = transpose ? cout : cin;
-  const int ivec = ii >> 3;
-  const size_t total = static_cast<size_t>(oo) * taps.n * ivec;
-  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < total; v += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int i0 = static_cast<int>(v % ivec) * 8;
-    const int t = static_cast<int>((v / ivec) % taps.n);
-    const int o = static_cast<int>(v / (static_cast<size_t>(ivec) * taps.n));
-    const int tap = taps.idx[t];
-    float val[8];
+  const uint32_t oo = transpose ? cin : cout, ii = transpose ? cout : cin;
+  const uint32_t ivec = ii >> 3;
+  const uint32_t total = oo * ivec;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
+    const uint32_t o = v / ivec, i0 = (v - o * ivec) * 8;
+    const float* src[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int co = transpose ? i0 + j : o, ci = transpose ? o : i0 + j;
-      val[j] = __ldg(w + (static_cast<size_t>(co) * cin + ci) * khw + tap);
+      const uint32_t co = transpose ? i0 + j : o, ci = transpose ? o : i0 + j;
+      src[j] = w + (static_cast<size_t>(co) * cin + ci) * khw;
     }
-    Act<FMT>::store8(out, out_plane, v * 8, val);
+    for (int t = 0; t < taps.n; ++t) {
+      const int tap = taps.idx[t];
+      float val[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) val[j] = __ldg(src[j] + tap);
+      Act<FMT>::store8(out, out_plane, (static_cast<size_t>(o) * taps.n + t) * ii + i0, val);
+    }
   }
 }
 
@@ -49,7 +54,7 @@ extern "C" int sbgm_pack_weight(const float* w_oihw, int cout, int cin, int khw,
     SBGM_REQUIRE(taps_host[i] >= 0 && taps_host[i] < khw, "pack_weight: tap %d out of range", taps_host[i]);
     tl.idx[i] = taps_host[i];
   }
-  const size_t total = static_cast<size_t>(cout) * cin * ntaps / 8;
+  const size_t total = static_cast<size_t>(cout) * cin / 8;
   size_t g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   if (g < 1) g = 1;

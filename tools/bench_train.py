@@ -96,7 +96,13 @@ def main() -> None:
                "loss": float(loss), "grad_buckets": None if sync is None else sync.stats}
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        # the captured backward graph holds NCCL all-reduces: drop it before the communicator goes away and skip the
+        # interpreter teardown (destroying a communicator that graphs still reference can block)
+        net._train_runners.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
