@@ -237,8 +237,10 @@ int sbgm_dsm_loss(const float* score, const float* std, const float* z, const fl
  * use the same NHWC storage formats as the activations; parameter gradients are fp32 in torch's
  * parameter layouts (conv: OIHW).  All reductions are two-stage with a fixed order (deterministic). */
 
-/* per (n, chunk of 32) partial (sum, sumsq) over `groups` channel groups: partials[n][32][groups][2].
- * groups == c gives the per-channel partials of train-mode BatchNorm (torchvision resnet.py:89-103). */
+/* per (n, chunk) partial (sum, sumsq) over `groups` channel groups: partials[n][chunks][groups][2] with
+ * chunks = sbgm_norm_partials_chunks(hw, c) (1..32).  groups == c gives the per-channel partials of train-mode
+ * BatchNorm (torchvision resnet.py:89-103). */
+int sbgm_norm_partials_chunks(int hw, int c);
 int sbgm_norm_partials(const void* x, size_t x_plane, int fmt, int n, int hw, int c, int groups, float* partials, void* stream);
 /* GroupNorm / InstanceNorm: stats[n][groups][2] = (mean, rstd) from partials[n][chunks][pgroups][2]
  * (the stand-alone partials above or the fused statistics of the convolution kernels). */
@@ -340,6 +342,16 @@ int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const vo
  * flat tap indices r * kw + s.  A training step re-packs every parameter after each optimizer update. */
 int sbgm_pack_weight(const float* w_oihw, int cout, int cin, int khw, const int* taps_host, int ntaps, int transpose,
                      void* out, size_t out_plane, int fmt, void* stream);
+/* batched form of sbgm_pack_weight (ntaps <= 16 per job): all jobs in ceil(njobs / 80) launches; the job table is a
+ * kernel parameter, so the call is capturable in a CUDA graph.  `jobs_host` is a HOST array. */
+typedef struct {
+  const float* w_oihw;
+  void* out;
+  size_t out_plane;
+  int cout, cin, khw, ntaps, transpose;
+  int taps[16];
+} sbgm_pack_job;
+int sbgm_pack_weights(const sbgm_pack_job* jobs_host, int njobs, int fmt, void* stream);
 /* d loss / d score of sbgm_dsm_loss, times *grad_loss (device scalar; NULL = 1) */
 int sbgm_dsm_loss_backward(const float* score, const float* std, const float* z, const float* sdf, const float* grad_loss, int n,
                            int per_member, float* dscore, void* stream);

@@ -453,13 +453,13 @@ __global__ void add_inplace_kernel(void* __restrict__ dst, size_t dp, const void
 
 // per-sample channel sums: out[n][c] = sum over the hw pixels of sample n (two-stage via [n][chunks][c] partials)
 template <int FMT>
-__global__ void chansum_partial_kernel(const void* __restrict__ x, size_t plane, int hw, int c, float* __restrict__ partials) {
+__global__ void chansum_partial_kernel(const void* __restrict__ x, size_t plane, int hw, int c, float* __restrict__ partials, int chunks) {
   pdl_grid_sync();
   extern __shared__ float red[];  // [lanes][c]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int vecs = c >> 3, lanes = blockDim.x / vecs;
   const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
-  const int per_chunk = (hw + kNormChunks - 1) / kNormChunks;
+  const int per_chunk = (hw + chunks - 1) / chunks;
   const int p_begin = chunk * per_chunk, p_end = min(hw, p_begin + per_chunk);
   if (lane < lanes) {
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -476,24 +476,24 @@ __global__ void chansum_partial_kernel(const void* __restrict__ x, size_t plane,
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
     float acc = 0.0f;
     for (int l = 0; l < lanes; ++l) acc += red[static_cast<size_t>(l) * c + i];
-    partials[(static_cast<size_t>(n) * kNormChunks + chunk) * c + i] = acc;
+    partials[(static_cast<size_t>(n) * chunks + chunk) * c + i] = acc;
   }
 }
 // out_n[n][c] (nullable) and out_total[c] (nullable).  One warp per channel: lane <-> chunk (kNormChunks == 32).
-__global__ void chansum_finish_kernel(const float* __restrict__ partials, int n, int c, float* __restrict__ out_n, int out_n_stride,
-                                      float* __restrict__ out_total) {
+__global__ void chansum_finish_kernel(const float* __restrict__ partials, int n, int c, int chunks, float* __restrict__ out_n,
+                                      int out_n_stride, float* __restrict__ out_total) {
   pdl_grid_sync();
   const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (ch >= c) return;
   float tot = 0.0f;
   if (out_n) {
     for (int k = 0; k < n; ++k) {
-      const float s = warp_sum(partials[(static_cast<size_t>(k) * kNormChunks + lane) * c + ch]);
+      const float s = warp_sum(lane < chunks ? partials[(static_cast<size_t>(k) * chunks + lane) * c + ch] : 0.0f);
       if (lane == 0) out_n[static_cast<size_t>(k) * out_n_stride + ch] = s;
       tot += s;
     }
   } else {
-    for (int k = lane; k < n * kNormChunks; k += 32) tot += partials[static_cast<size_t>(k) * c + ch];
+    for (int k = lane; k < n * chunks; k += 32) tot += partials[static_cast<size_t>(k) * c + ch];
     tot = warp_sum(tot);
   }
   if (out_total && lane == 0) out_total[ch] = tot;
@@ -751,9 +751,10 @@ int sbgm_channel_sums(const void* x, size_t x_plane, int fmt, int n, int hw, int
   SBGM_REQUIRE(c % 8 == 0 && c / 8 <= 256, "channel_sums: bad c=%d", c);
   const int vecs = c / 8, lanes = 256 / vecs;
   cudaStream_t st = as_stream(stream);
-  dim3 g1(kNormChunks, n);
-  SBGM_DISPATCH_FMT(fmt, (launch_k((chansum_partial_kernel<FMT>), g1, 256, static_cast<size_t>(lanes) * c * sizeof(float), st, x, x_plane, hw, c, scratch)));
-  launch_k((chansum_finish_kernel), ceil_div(c, 8), 256, 0, st, scratch, n, c, out_per_sample, out_stride, out_total);
+  const int chunks = max(1, min(kNormChunks, hw / (lanes * 8)));
+  dim3 g1(chunks, n);
+  SBGM_DISPATCH_FMT(fmt, (launch_k((chansum_partial_kernel<FMT>), g1, 256, static_cast<size_t>(lanes) * c * sizeof(float), st, x, x_plane, hw, c, scratch, chunks)));
+  launch_k((chansum_finish_kernel), ceil_div(c, 8), 256, 0, st, scratch, n, c, chunks, out_per_sample, out_stride, out_total);
   return check_launch("channel_sums");
 }
 

@@ -126,22 +126,18 @@ wgrad_simt_kernel(const void* __restrict__ x, size_t x_plane, const void* __rest
   }
 }
 
-// Sum the split partials in a fixed order and emit torch's OIHW layout: out[co][ci][tap].  One thread per (co, ci):
-// reads are coalesced over ci for every tap, and a thread's taps are contiguous in the output.
+// Sum the split partials in a fixed order and emit torch's OIHW layout: out[co][ci][tap].
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int taps, int cin, float* __restrict__ out) {
   pdl_grid_sync();
-  const uint32_t K = static_cast<uint32_t>(taps) * cin;
-  const uint32_t pairs = static_cast<uint32_t>(cout) * cin;
+  const size_t K = static_cast<size_t>(taps) * cin;
   const size_t total = static_cast<size_t>(cout) * K;
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < pairs; j += gridDim.x * blockDim.x) {
-    const uint32_t co = j / cin, ci = j - co * cin;
-    const float* src = ws + static_cast<size_t>(co) * K + ci;
-    float* dst = out + static_cast<size_t>(j) * taps;
-    for (int t = 0; t < taps; ++t) {
-      float acc = 0.0f;
-      for (int z = 0; z < splits; ++z) acc += __ldg(src + static_cast<size_t>(z) * total + static_cast<size_t>(t) * cin);
-      dst[t] = acc;
-    }
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cin);
+    const int tap = static_cast<int>((i / cin) % taps);
+    const size_t co = i / K;
+    float acc = 0.0f;
+    for (int z = 0; z < splits; ++z) acc += __ldg(ws + static_cast<size_t>(z) * total + i);
+    out[(co * cin + ci) * taps + tap] = acc;
   }
 }
 
@@ -377,12 +373,14 @@ int sbgm_conv2d_wgrad_simt(const void* x, size_t x_plane, const void* dy, size_t
   dim3 grid(cib * cob, kh * kw, splits);
   SBGM_DISPATCH_FMT(fmt, (launch_k((wgrad_simt_kernel<FMT>), grid, 256, 0, st, x, x_plane, dy, dy_plane, workspace, n, h, w, cin, cout, kh, kw,
                                                                         stride, pad, ho, wo, cib, per)));
-  launch_k((wgrad_reduce_kernel), cgrid_for(static_cast<size_t>(cout) * cin, 128), 128, 0, st, workspace, splits, cout, kh * kw, cin, dweight_oihw);
+  const size_t total = static_cast<size_t>(cout) * kh * kw * cin;
+  launch_k((wgrad_reduce_kernel), cgrid_for(total, 256), 256, 0, st, workspace, splits, cout, kh * kw, cin, dweight_oihw);
   return check_launch("conv2d_wgrad_simt");
 }
 
 int sbgm_wgrad_reduce(const float* workspace, int splits, int cout, int taps, int cin, float* dweight_oihw, void* stream) {
-  launch_k((wgrad_reduce_kernel), cgrid_for(static_cast<size_t>(cout) * cin, 128), 128, 0, as_stream(stream), workspace, splits, cout, taps, cin, dweight_oihw);
+  const size_t total = static_cast<size_t>(cout) * taps * cin;
+  launch_k((wgrad_reduce_kernel), cgrid_for(total, 256), 256, 0, as_stream(stream), workspace, splits, cout, taps, cin, dweight_oihw);
   return check_launch("wgrad_reduce");
 }
 

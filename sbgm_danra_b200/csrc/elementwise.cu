@@ -170,13 +170,13 @@ constexpr int kGnChunks = 32;
 
 template <int FMT>
 __global__ void gn_partial_kernel(const void* __restrict__ x, size_t plane, int hw, int c, int groups,
-                                  float* __restrict__ partials) {
+                                  float* __restrict__ partials, int chunks) {
   pdl_grid_sync();
   extern __shared__ float red[];  // [lanes][c][2] then [c][2]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int vecs = c >> 3, lanes = blockDim.x / vecs;
   const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
-  const int per_chunk = (hw + kGnChunks - 1) / kGnChunks;
+  const int per_chunk = (hw + chunks - 1) / chunks;
   const int p_begin = chunk * per_chunk, p_end = min(hw, p_begin + per_chunk);
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lane < lanes) {
@@ -214,7 +214,7 @@ __global__ void gn_partial_kernel(const void* __restrict__ x, size_t plane, int 
       ss += chan[2 * (g * cpg + j)];
       qq += chan[2 * (g * cpg + j) + 1];
     }
-    float* o = partials + ((static_cast<size_t>(n) * kGnChunks + chunk) * groups + g) * 2;
+    float* o = partials + ((static_cast<size_t>(n) * chunks + chunk) * groups + g) * 2;
     o[0] = ss;
     o[1] = qq;
   }
@@ -399,30 +399,36 @@ __global__ void upsample2x_kernel(const void* __restrict__ x, size_t x_plane, vo
   }
 }
 
-// ---- stem im2col: one thread per (pixel, channel, window row) writes the row's 8 taps as one vector ----------
+// ---- stem im2col -------------------------------------------------------------------------------------------
+// A block owns 32 output pixels of one output row and one input channel: the 8 x 70 input window goes through shared
+// memory (coalesced row reads; every input value is used by 16 taps), then thread (pixel, window row r) writes that
+// row's 8 taps as one vector -- 8 consecutive threads fill one 128-byte line.  (The direct form, 8 scalar loads per
+// thread at 32 distinct lines per warp instruction, ran at the LSU wavefront limit: 374 us for the 7-channel C4 stem.)
 template <int FMT>
-__global__ void stem_im2col_kernel(const float* __restrict__ x, const float* __restrict__ planes, int np, int cc, int c_begin, int nch,
-                                   void* __restrict__ out, size_t out_plane, int n, int h, int w) {
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ x, const float* __restrict__ planes, int np, int cc, int c_begin, int nch,
+                   void* __restrict__ out, size_t out_plane, int n, int h, int w) {
   pdl_grid_sync();
+  __shared__ float tile[8][72];
   const int ho = h / 2, wo = w / 2;
-  const uint32_t total = static_cast<uint32_t>(n) * ho * wo * nch * 8;    // < 2^32 (host-checked): 32-bit divisions only
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int r = static_cast<int>(i & 7);
-    const int cl = static_cast<int>((i >> 3) % nch);
-    const uint32_t pix = i / (static_cast<uint32_t>(nch) * 8);
-    const int ox = static_cast<int>(pix % wo), oy = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<uint32_t>(wo) * ho));
-    const int c = c_begin + cl;
-    const float* src = (c == 0) ? x + static_cast<size_t>(b) * h * w
-                                : planes + (static_cast<size_t>(np == 1 ? 0 : b) * cc + (c - 1)) * h * w;
-    const int iy = 2 * oy + r - 3;
-    float v[8];
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const int ix = 2 * ox + s - 3;
-      v[s] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(src + static_cast<size_t>(iy) * w + ix) : 0.0f;
-    }
-    Act<FMT>::store8(out, out_plane, static_cast<size_t>(i) * 8, v);
+  const int ox0 = blockIdx.x * 32, oy = blockIdx.y;
+  const int b = blockIdx.z / nch, cl = blockIdx.z - b * nch;
+  const int c = c_begin + cl;
+  const float* src = (c == 0) ? x + static_cast<size_t>(b) * h * w
+                              : planes + (static_cast<size_t>(np == 1 ? 0 : b) * cc + (c - 1)) * h * w;
+  for (int i = threadIdx.x; i < 8 * 70; i += 256) {
+    const int r = i / 70, col = i - r * 70;
+    const int iy = 2 * oy + r - 3, ix = 2 * ox0 + col - 3;
+    tile[r][col] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(src + static_cast<size_t>(iy) * w + ix) : 0.0f;
   }
+  __syncthreads();
+  const int r = threadIdx.x & 7, px = threadIdx.x >> 3;
+  if (ox0 + px >= wo) return;
+  float v[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) v[s] = tile[r][2 * px + s];
+  const size_t pix = (static_cast<size_t>(b) * ho + oy) * wo + ox0 + px;
+  Act<FMT>::store8(out, out_plane, (pix * nch + cl) * 64 + r * 8, v);
 }
 
 // ---- final convolution: 3x3, cout <= 4, fused 1/std ---------------------------------------------
@@ -597,7 +603,7 @@ int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const floa
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
   dim3 g2(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
-    launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, st, x, x_plane, hw, c, groups, partials);
+    launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, st, x, x_plane, hw, c, groups, partials, kGnChunks);
     launch_k((gn_apply_kernel<FMT>), g2, 256, smem2, st, x, x_plane, partials, kGnChunks, groups, gamma, beta, groups, eps, skip,
                                                   skip_plane, tproj, tproj_stride, act, y, y_plane, hw, c);
   });
@@ -606,14 +612,24 @@ int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const floa
 
 // Stage 1 alone: per (n, chunk) partial sums [n][32][groups][2]; groups == c gives the per-channel partials
 // of train-mode BatchNorm (finished by sbgm_bn_stats_finalize / sbgm_gn_stats_finalize, backward.cu).
+// chunk count of sbgm_norm_partials: ~8 pixels per thread, at most 32 (small maps get few chunks, so the finalize
+// kernels sum few partials)
+int sbgm_norm_partials_chunks(int hw, int c) {
+  const int vecs = c / 8 > 0 ? c / 8 : 1;
+  const int lanes = 256 / vecs > 0 ? 256 / vecs : 1;
+  const int ch = hw / (lanes * 8);
+  return ch < 1 ? 1 : (ch > kGnChunks ? kGnChunks : ch);
+}
+
 int sbgm_norm_partials(const void* x, size_t x_plane, int fmt, int n, int hw, int c, int groups, float* partials, void* stream) {
   SBGM_REQUIRE(c % 8 == 0 && c <= 2048 && groups >= 1 && c % groups == 0, "norm_partials: bad c=%d groups=%d", c, groups);
   const int vecs = c / 8;
   SBGM_REQUIRE(vecs <= 256, "norm_partials: c too large");
   const int lanes = 256 / vecs;
   const size_t smem1 = (static_cast<size_t>(lanes) + 1) * c * 2 * sizeof(float);
-  dim3 g1(kGnChunks, n);
-  SBGM_DISPATCH_FMT(fmt, (launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, as_stream(stream), x, x_plane, hw, c, groups, partials)));
+  const int chunks = sbgm_norm_partials_chunks(hw, c);
+  dim3 g1(chunks, n);
+  SBGM_DISPATCH_FMT(fmt, (launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, as_stream(stream), x, x_plane, hw, c, groups, partials, chunks)));
   return check_launch("norm_partials");
 }
 
@@ -657,10 +673,10 @@ int sbgm_stem_im2col(const float* x, const float* planes, int np, int cc, int c_
   SBGM_REQUIRE(c_begin >= 0 && c_end > c_begin && c_end <= cc + 1, "stem_im2col: bad channel range [%d, %d) of %d", c_begin, c_end, cc + 1);
   SBGM_REQUIRE(c_end <= 1 || (planes != nullptr && (np == 1 || np == n)), "stem_im2col: conditioning planes missing or batch %d != 1, %d", np, n);
   const int nch = c_end - c_begin;
-  const size_t total = static_cast<size_t>(n) * (h / 2) * (w / 2) * nch * 8;
-  SBGM_REQUIRE(total < (1ull << 32), "stem_im2col: tensor too large for 32-bit indexing");
-  SBGM_DISPATCH_FMT(fmt, (launch_k((stem_im2col_kernel<FMT>), grid_for(total, 256), 256, 0, as_stream(stream), x, planes, np, cc, c_begin, nch, out,
-                                                                                                out_plane, n, h, w)));
+  SBGM_REQUIRE(static_cast<long long>(n) * nch <= 65535 && h / 2 <= 65535, "stem_im2col: grid too large");
+  dim3 grid(ceil_div(w / 2, 32), h / 2, n * nch);
+  SBGM_DISPATCH_FMT(fmt, (launch_k((stem_im2col_kernel<FMT>), grid, 256, 0, as_stream(stream), x, planes, np, cc, c_begin, nch, out,
+                                   out_plane, n, h, w)));
   return check_launch("stem_im2col");
 }
 

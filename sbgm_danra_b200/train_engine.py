@@ -48,16 +48,75 @@ def _pack_tc(w: torch.Tensor, fmt: int, taps: Sequence[int], transpose: bool) ->
     return out if planes == 2 else out[0]
 
 
-class ConvLayer:
-    """One convolution / linear layer of the training graph: forward pack + what its gradients need."""
+class _PackJob(__import__("ctypes").Structure):
+    import ctypes as _C
+    _fields_ = [("w", _C.c_void_p), ("out", _C.c_void_p), ("out_plane", _C.c_size_t), ("cout", _C.c_int), ("cin", _C.c_int),
+                ("khw", _C.c_int), ("ntaps", _C.c_int), ("transpose", _C.c_int), ("taps", _C.c_int * 16)]
 
-    def __init__(self, name: str, w: torch.Tensor, bias: Optional[torch.Tensor], fmt: int, bias_name: Optional[str] = None):
+
+class PackPlan:
+    """Collects every weight pack of a training step and runs them as one batched launch (sbgm_pack_weights); jobs with more
+    than 16 taps (the 8x8 convolution's forward pack) go through the single-weight entry point."""
+
+    def __init__(self, fmt: int) -> None:
+        self.fmt = fmt
+        self.jobs: List[Tuple[torch.Tensor, torch.Tensor, int, int, int, List[int], bool]] = []
+
+    def add(self, w4: torch.Tensor, taps: Sequence[int], transpose: bool) -> torch.Tensor:
+        cout, cin, kh, kw = w4.shape
+        w4 = w4.contiguous()
+        oo, ii = (cin, cout) if transpose else (cout, cin)
+        planes = 2 if self.fmt == FMT_BF16X2 else 1
+        out = torch.empty((planes, oo, len(taps) * ii), dtype=torch.bfloat16, device=w4.device)
+        self.jobs.append((w4, out, cout, cin, kh * kw, list(taps), transpose))
+        return out if planes == 2 else out[0]
+
+    def run(self) -> None:
+        import ctypes
+        small = [j for j in self.jobs if len(j[5]) <= 16]
+        for w4, out, cout, cin, khw, taps, tr in (j for j in self.jobs if len(j[5]) > 16):
+            arr = (ctypes.c_int * len(taps))(*taps)
+            call("sbgm_pack_weight", w4.data_ptr(), cout, cin, khw, arr, len(taps), int(tr), out.data_ptr(), out[0].numel(), self.fmt,
+                 _stream())
+        if small:
+            table = (_PackJob * len(small))()
+            for k, (w4, out, cout, cin, khw, taps, tr) in enumerate(small):
+                e = table[k]
+                e.w, e.out, e.out_plane = w4.data_ptr(), out.data_ptr(), out[0].numel()
+                e.cout, e.cin, e.khw, e.ntaps, e.transpose = cout, cin, khw, len(taps), int(tr)
+                for t, v in enumerate(taps):
+                    e.taps[t] = v
+            call("sbgm_pack_weights", table, len(small), self.fmt, _stream())
+        self.jobs = []
+
+
+def _dgrad_taps(k: int, stride: int, pad: int, par: int):
+    """Taps of a length-k filter that reach input positions of parity `par` in the data gradient, ordered by increasing
+    offset d into dy: input index i = stride * j + par receives dy[j + d] * w[r] with r = par + pad - stride * d."""
+    ds = sorted(d for d in range(-k, k + 1) if 0 <= par + pad - stride * d < k)
+    return ds, [par + pad - stride * d for d in ds]
+
+
+class ConvLayer:
+    """One convolution / linear layer of the training graph: forward pack + what its gradients need.
+
+    With a `plan` (and the layer's stride / pad), the forward and data-gradient packs are registered for the batched
+    launch instead of being packed one by one."""
+
+    def __init__(self, name: str, w: torch.Tensor, bias: Optional[torch.Tensor], fmt: int, bias_name: Optional[str] = None,
+                 plan: Optional[PackPlan] = None, stride: int = 1, pad: int = 0, need_dx: bool = True):
         self.name, self.bias_name, self.fmt = name, bias_name, fmt
         w4 = w if w.dim() == 4 else w[:, :, None, None]
         self.w4, self.shape = w4, tuple(w.shape)
         self.cout, self.cin, self.kh, self.kw = w4.shape
-        self.fwd = ConvW(_pack_oihw(w4, fmt), None if bias is None else bias.contiguous(), self.cin, self.cout, self.kh, self.kw)
+        self.plan = plan if fmt != FMT_F32 else None
+        packed = self.plan.add(w4, list(range(self.kh * self.kw)), False) if self.plan is not None else _pack_oihw(w4, fmt)
+        self.fwd = ConvW(packed, None if bias is None else bias.contiguous(), self.cin, self.cout, self.kh, self.kw)
         self._dgrad: Dict[Tuple, object] = {}
+        if self.plan is not None and need_dx and self.cin % 64 == 0 and self.cout % 64 == 0:
+            for py in range(stride):
+                for px in range(stride):
+                    self.dgrad_tc_weight(stride, pad, py, px)
 
     def dgrad_simt_weight(self) -> torch.Tensor:
         key = ("simt",)
@@ -72,20 +131,16 @@ class ConvLayer:
         if key in self._dgrad:
             return self._dgrad[key]
 
-        def taps(k: int, par: int):
-            # input index i = stride * j + par receives dy[j + d] * w[r] with r = par + pad - stride * d
-            ds = sorted(d for d in range(-k, k + 1) if 0 <= par + pad - stride * d < k)
-            return ds, [par + pad - stride * d for d in ds]
-
-        dys, rs = taps(self.kh, py)
-        dxs, ss = taps(self.kw, px)
+        dys, rs = _dgrad_taps(self.kh, stride, pad, py)
+        dxs, ss = _dgrad_taps(self.kw, stride, pad, px)
         if not rs or not ss:
             self._dgrad[key] = None
             return None
         # tap index r' of the sub-kernel reads dy at offset d = r' - pad'  ->  pad' = -d_min; taps must be contiguous in d
         assert dys == list(range(dys[0], dys[0] + len(dys))) and dxs == list(range(dxs[0], dxs[0] + len(dxs)))
         # transposed convolution: O = ci, I = co, taps in increasing-d order
-        packed = _pack_tc(self.w4, self.fmt, [r * self.kw + s for r in rs for s in ss], True)
+        tap_list = [r * self.kw + s for r in rs for s in ss]
+        packed = self.plan.add(self.w4, tap_list, True) if self.plan is not None else _pack_tc(self.w4, self.fmt, tap_list, True)
         cw = ConvW(packed, None, self.cout, self.cin, len(rs), len(ss))
         self._dgrad[key] = (cw, -dys[0], -dxs[0])
         return self._dgrad[key]
@@ -285,7 +340,8 @@ class TrainKernels:
         c, hw = x.c, x.h * x.w
         stats = torch.empty((c, 2), dtype=torch.float32, device=self.device)
         if train:
-            part = torch.empty((x.n, NORM_CHUNKS, c, 2), dtype=torch.float32, device=self.device)
+            chunks = _lib.query("sbgm_norm_partials_chunks", hw, c)
+            part = torch.empty((x.n, chunks, c, 2), dtype=torch.float32, device=self.device)
             call("sbgm_norm_partials", x.ptr, x.plane, self.fmt, x.n, hw, c, c, part.data_ptr(), _stream())
             n_all = x.n
             if self.sync_bn is not None:
@@ -293,10 +349,10 @@ class TrainKernels:
                 # finalised statistics are bit-identical to a single-GPU run of the full batch)
                 import torch.distributed as dist
                 world = dist.get_world_size(self.sync_bn)
-                gathered = torch.empty((world * x.n, NORM_CHUNKS, c, 2), dtype=torch.float32, device=self.device)
+                gathered = torch.empty((world * x.n, chunks, c, 2), dtype=torch.float32, device=self.device)
                 dist.all_gather_into_tensor(gathered, part, group=self.sync_bn)
                 part, n_all = gathered, world * x.n
-            call("sbgm_bn_stats_finalize", part.data_ptr(), NORM_CHUNKS, n_all, hw, c, BN_EPS, BN_MOMENTUM, stats.data_ptr(),
+            call("sbgm_bn_stats_finalize", part.data_ptr(), chunks, n_all, hw, c, BN_EPS, BN_MOMENTUM, stats.data_ptr(),
                  bn["running_mean"].data_ptr(), bn["running_var"].data_ptr(), _stream())
             mode = 0
         else:
@@ -313,9 +369,9 @@ class TrainKernels:
             part, chunks = fused
             pgroups = x.c // 8
         else:
-            part = torch.empty((x.n, NORM_CHUNKS, groups, 2), dtype=torch.float32, device=self.device)
+            chunks, pgroups = _lib.query("sbgm_norm_partials_chunks", hw, x.c), groups
+            part = torch.empty((x.n, chunks, groups, 2), dtype=torch.float32, device=self.device)
             call("sbgm_norm_partials", x.ptr, x.plane, self.fmt, x.n, hw, x.c, groups, part.data_ptr(), _stream())
-            chunks, pgroups = NORM_CHUNKS, groups
         call("sbgm_gn_stats_finalize", part.data_ptr(), chunks, pgroups, groups, x.n, hw, x.c, GN_EPS, stats.data_ptr(), _stream())
         return self._norm(x, stats, 1, groups, gamma, beta, gamma_name, beta_name, skip, tproj, dtproj, 1, act)
 
@@ -388,15 +444,16 @@ class TrainKernels:
 
 
 class _AttnLayers:
-    def __init__(self, sd, prefix: str, heads: int, fmt: int) -> None:
+    def __init__(self, sd, prefix: str, heads: int, fmt: int, plan: Optional[PackPlan] = None) -> None:
         g = lambda k: sd[f"{prefix}.{k}"]
+        lin = lambda w, b_: ConvLayer(f"{prefix}.{w}", g(w), g(b_), fmt, f"{prefix}.{b_}", plan=plan)
         self.heads, self.prefix = heads, prefix
         self.ln1 = (g("ln1.weight"), g("ln1.bias"))
         self.ln2 = (g("ln2.weight"), g("ln2.bias"))
-        self.in_proj = ConvLayer(f"{prefix}.mha.in_proj_weight", g("mha.in_proj_weight"), g("mha.in_proj_bias"), fmt, f"{prefix}.mha.in_proj_bias")
-        self.out_proj = ConvLayer(f"{prefix}.mha.out_proj.weight", g("mha.out_proj.weight"), g("mha.out_proj.bias"), fmt, f"{prefix}.mha.out_proj.bias")
-        self.ff0 = ConvLayer(f"{prefix}.ff.0.weight", g("ff.0.weight"), g("ff.0.bias"), fmt, f"{prefix}.ff.0.bias")
-        self.ff2 = ConvLayer(f"{prefix}.ff.2.weight", g("ff.2.weight"), g("ff.2.bias"), fmt, f"{prefix}.ff.2.bias")
+        self.in_proj = lin("mha.in_proj_weight", "mha.in_proj_bias")
+        self.out_proj = lin("mha.out_proj.weight", "mha.out_proj.bias")
+        self.ff0 = lin("ff.0.weight", "ff.0.bias")
+        self.ff2 = lin("ff.2.weight", "ff.2.bias")
 
 
 def _attention_block(tk: TrainKernels, aw: _AttnLayers, x: Act) -> Act:
@@ -465,19 +522,21 @@ class TrainEngine:
         return dict(weight=self.sd[f"{prefix}.weight"], bias=self.sd[f"{prefix}.bias"], running_mean=self.sd[f"{prefix}.running_mean"],
                     running_var=self.sd[f"{prefix}.running_var"], weight_name=f"{prefix}.weight", bias_name=f"{prefix}.bias")
 
-    def _conv(self, wname: str, bname: Optional[str] = None) -> ConvLayer:
-        return ConvLayer(wname, self.sd[wname], None if bname is None else self.sd[bname], self.fmt, bname)
+    def _conv(self, wname: str, bname: Optional[str] = None, stride: int = 1, pad: int = 0) -> ConvLayer:
+        return ConvLayer(wname, self.sd[wname], None if bname is None else self.sd[bname], self.fmt, bname, plan=self.plan,
+                         stride=stride, pad=pad)
 
     def _pack(self) -> None:
         sd, spec, fmt = self.sd, self.spec, self.fmt
+        self.plan = PackPlan(fmt)
         p = "encoder."
         w1 = sd[f"{p}conv1.weight"]
         self.cin = w1.shape[1]
         self.stem_w = w1.permute(1, 2, 3, 0).reshape(self.cin, 64, 64).contiguous()
         if fmt != FMT_F32:   # tensor-core stem: 1x1 convolution over the im2col tensor; [co][ci*64 + tap] IS conv1.weight's OIHW order
-            self.stem_layer = ConvLayer(f"{p}conv1.weight", w1.reshape(64, self.cin * 64, 1, 1), None, fmt)
+            self.stem_layer = ConvLayer(f"{p}conv1.weight", w1.reshape(64, self.cin * 64, 1, 1), None, fmt, plan=self.plan, need_dx=False)
             self.stem_layer.shape = tuple(w1.shape)
-        self.conv2 = self._conv(f"{p}conv2.weight")
+        self.conv2 = self._conv(f"{p}conv2.weight", stride=2, pad=3)
         self.bn1 = self._bn(f"{p}bn1")
         self.layers = []
         for li, nblk in enumerate(spec.block_layers, start=1):
@@ -487,11 +546,12 @@ class TrainEngine:
                 stride = 2 if (b == 0 and li > 1) else 1
                 down = None
                 if f"{bp}.downsample.0.weight" in sd:
-                    down = (self._conv(f"{bp}.downsample.0.weight"), self._bn(f"{bp}.downsample.1"))
-                blocks.append(dict(c1=self._conv(f"{bp}.conv1.weight"), b1=self._bn(f"{bp}.bn1"), c2=self._conv(f"{bp}.conv2.weight"),
+                    down = (self._conv(f"{bp}.downsample.0.weight", stride=stride, pad=0), self._bn(f"{bp}.downsample.1"))
+                blocks.append(dict(c1=self._conv(f"{bp}.conv1.weight", stride=stride, pad=1), b1=self._bn(f"{bp}.bn1"),
+                                   c2=self._conv(f"{bp}.conv2.weight", stride=1, pad=1),
                                    b2=self._bn(f"{bp}.bn2"), down=down, stride=stride))
             self.layers.append(blocks)
-        self.enc_attn = {i: _AttnLayers(sd, f"{p}attention_layers.{i}", spec.n_heads, fmt) for i in (3, 4)}
+        self.enc_attn = {i: _AttnLayers(sd, f"{p}attention_layers.{i}", spec.n_heads, fmt, self.plan) for i in (3, 4)}
         # time projector: same packing as inference (engine.TimeProjector) plus the names for the gradients
         from .engine import TimeProjector
         self.tp = TimeProjector(self.device, spec.time_embedding)
@@ -509,11 +569,11 @@ class TrainEngine:
         self.dec_blocks = []
         for i, (cin, cout, attn) in enumerate(spec.plan):
             bp = f"{d}residual_layers.{i}"
-            blk = dict(conv_up=self._conv(f"{bp}.conv_up.weight", f"{bp}.conv_up.bias"), conv=self._conv(f"{bp}.conv.weight", f"{bp}.conv.bias"),
+            blk = dict(conv_up=self._conv(f"{bp}.conv_up.weight", f"{bp}.conv_up.bias", 1, 1), conv=self._conv(f"{bp}.conv.weight", f"{bp}.conv.bias", 1, 1),
                        n1=(sd[f"{bp}.norm1.weight"], sd[f"{bp}.norm1.bias"], f"{bp}.norm1.weight", f"{bp}.norm1.bias") if affine else (None, None, None, None),
                        n2=(sd[f"{bp}.norm2.weight"], sd[f"{bp}.norm2.bias"], f"{bp}.norm2.weight", f"{bp}.norm2.bias") if affine else (None, None, None, None),
                        g1=max(1, min(spec.gn_groups, cin)) if affine else cin, g2=max(1, min(spec.gn_groups, cout)) if affine else cout,
-                       attn=_AttnLayers(sd, f"{bp}.attention", spec.n_heads, fmt) if attn else None, name=f"dec{i}")
+                       attn=_AttnLayers(sd, f"{bp}.attention", spec.n_heads, fmt, self.plan) if attn else None, name=f"dec{i}")
             s = self.tp.add_set(sd[f"{bp}.sinusoidal_embedding.W"])
             wn, bn = f"{bp}.time_projection_layer.1.weight", f"{bp}.time_projection_layer.1.bias"
             self.tp.add_head(f"dec{i}", s, sd[wn], sd[bn])
@@ -521,7 +581,7 @@ class TrainEngine:
             self.dec_blocks.append(blk)
         self.tp.finalize()
         fp = f"{d}final_layer"
-        self.final_up = self._conv(f"{fp}.conv_up.weight", f"{fp}.conv_up.bias")
+        self.final_up = self._conv(f"{fp}.conv_up.weight", f"{fp}.conv_up.bias", 1, 1)
         wf = sd[f"{fp}.conv.weight"]
         if wf.shape[0] != 1:
             raise NotImplementedError("the training path supports output_channels == 1 (the reference's only configuration)")
@@ -529,6 +589,7 @@ class TrainEngine:
         self.final_b = sd[f"{fp}.conv.bias"].contiguous()
         self.final_names = (f"{fp}.conv.weight", f"{fp}.conv.bias")
         self.act = ACTS[spec.activation]
+        self.plan.run()            # every forward / data-gradient pack of the step: one batched launch
 
     # -- forward ----------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor], planes: Optional[torch.Tensor],
