@@ -578,15 +578,22 @@ __global__ void time_embed_bwd_weight_kernel(const float* __restrict__ dout, int
   }
 }
 // de0[row][k] = silu'(e0[row][k]) * sum_{col in set 0} dout[row][col] * W[col][k]
+// block = (te threads over k) x 4 column groups; the groups' partial sums meet in shared memory
 __global__ void time_embed_bwd_input_kernel(const float* __restrict__ dout, int c_total, const float* __restrict__ e_ws, int te,
                                             const int32_t* __restrict__ pset, const float* __restrict__ pw, float* __restrict__ de0) {
   pdl_grid_sync();
-  const int row = blockIdx.x;
-  for (int k = threadIdx.x; k < te; k += blockDim.x) {
-    float acc = 0.0f;
-    for (int col = 0; col < c_total; ++col)
+  extern __shared__ float part[];     // [4][te]
+  const int row = blockIdx.x, k = threadIdx.x, grp = threadIdx.y;
+  float acc = 0.0f;
+  if (k < te) {
+    for (int col = grp; col < c_total; col += 4)
       if (pset[col] == 0) acc = fmaf(dout[static_cast<size_t>(row) * c_total + col], __ldg(pw + static_cast<size_t>(col) * te + k), acc);
-    de0[static_cast<size_t>(row) * te + k] = acc * act_grad(e_ws[static_cast<size_t>(row) * te + k], SBGM_ACT_SILU);
+    part[grp * te + k] = acc;
+  }
+  __syncthreads();
+  if (grp == 0 && k < te) {
+    const float s = (part[k] + part[te + k]) + (part[2 * te + k] + part[3 * te + k]);
+    de0[static_cast<size_t>(row) * te + k] = s * act_grad(e_ws[static_cast<size_t>(row) * te + k], SBGM_ACT_SILU);
   }
 }
 __global__ void label_emb_bwd_kernel(const float* __restrict__ de0, const int64_t* __restrict__ y, int rows, int te,
@@ -780,7 +787,8 @@ int sbgm_time_embed_backward(const float* dout, const float* t, const int64_t* y
   launch_k((time_embed_bwd_embed_kernel), rows, 256, 0, st, t, y, fourier_w, n_sets, te, label_emb, e_ws);
   launch_k((time_embed_bwd_weight_kernel), c_total, 256, 0, st, dout, c_total, e_ws, rows, te, proj_set, d_proj_w, d_proj_b);
   if (d_label_emb != nullptr && y != nullptr) {
-    launch_k((time_embed_bwd_input_kernel), rows, 256, 0, st, dout, c_total, e_ws, te, proj_set, proj_w, de0);
+    SBGM_REQUIRE(te <= 256, "time_embed_backward: te=%d > 256", te);
+    launch_k((time_embed_bwd_input_kernel), rows, dim3(te, 4), static_cast<size_t>(4) * te * sizeof(float), st, dout, c_total, e_ws, te, proj_set, proj_w, de0);
     launch_k((label_emb_bwd_kernel), n_classes, 256, 0, st, de0, y, rows, te, d_label_emb);
   }
   return check_launch("time_embed_backward");

@@ -243,7 +243,7 @@ extern "C" int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* wei
   C64Params p;
   p.n = n; p.h = h; p.w = w;
   p.tiles_w = w / kTW; p.tiles_h = h / kTH; p.total_tiles = p.tiles_w * p.tiles_h * n;
-  p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.res_pix_mod = 0; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
+  p.ep.bias = bias; p.ep.residual = residual; p.ep.res_plane = res_plane; p.ep.res_pix_mod = 0; p.ep.staged = 0; p.ep.tproj = tproj; p.ep.tproj_stride = tproj_stride;
   p.ep.act = act; p.ep.cout = 64; p.ep.out = out; p.ep.out_plane = out_plane;
   p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
   p.gn_partials = gn_partials;

@@ -224,11 +224,11 @@ __global__ void final_conv_bwd_input_kernel(const float* __restrict__ dscore, co
   extern __shared__ float wsm[];  // [9][cin]
   for (int i = threadIdx.x; i < 9 * cin; i += blockDim.x) wsm[i] = wgt[i];
   __syncthreads();
-  const int vecs = cin >> 3;
-  const size_t total = static_cast<size_t>(n) * h * w * vecs;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t vecs = cin >> 3;
+  const uint32_t total = static_cast<uint32_t>(n) * h * w * vecs;      // < 2^32 (host-checked): 32-bit divisions only
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int vec = static_cast<int>(i % vecs);
-    size_t r0 = i / vecs;
+    uint32_t r0 = i / vecs;
     const int x = static_cast<int>(r0 % w);
     r0 /= w;
     const int y = static_cast<int>(r0 % h);
@@ -249,11 +249,11 @@ __global__ void final_conv_bwd_input_kernel(const float* __restrict__ dscore, co
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, wp[j], acc[j]);
       }
     }
-    Act<FMT>::store8(da, da_plane, i * 8, acc);
+    Act<FMT>::store8(da, da_plane, static_cast<size_t>(i) * 8, acc);
   }
 }
 
-constexpr int kFinalBwdBlocks = 296;
+constexpr int kFinalBwdBlocks = 1184;   // 148 SMs x 8: the kernel is latency-bound at low occupancy (72 accumulators / thread)
 template <int FMT>
 __global__ void __launch_bounds__(256)
 final_conv_bwd_weight_kernel(const float* __restrict__ dscore, const float* __restrict__ inv_std, const void* __restrict__ a, size_t a_plane,
@@ -307,10 +307,12 @@ final_conv_bwd_weight_kernel(const float* __restrict__ dscore, const float* __re
 }
 __global__ void final_conv_bwd_finish_kernel(const float* __restrict__ partials, int blocks, int cin, float* __restrict__ dW, float* __restrict__ db) {
   pdl_grid_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;    // one warp per output
   if (i > 9 * cin) return;
   float s = 0.0f;
-  for (int k = 0; k < blocks; ++k) s += partials[static_cast<size_t>(k) * (9 * cin + 1) + i];
+  for (int k = lane; k < blocks; k += 32) s += partials[static_cast<size_t>(k) * (9 * cin + 1) + i];
+  s = warp_sum(s);
+  if (lane != 0) return;
   if (i == 9 * cin) { db[0] = s; return; }
   const int tap = i / cin, ci = i - tap * cin;
   dW[ci * 9 + tap] = s;     // OIHW with O = 1
@@ -408,6 +410,7 @@ int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const vo
   cudaStream_t st = as_stream(stream);
   const int vecs = cin / 8, lanes = 256 / vecs;
   const size_t total = static_cast<size_t>(n) * h * w * vecs;
+  SBGM_REQUIRE(total < (1ull << 32), "final_conv_backward: tensor too large for 32-bit indexing");
   const size_t smem_w = static_cast<size_t>(lanes) * (9 * cin + 1) * sizeof(float);
   SBGM_DISPATCH_FMT(fmt, {
     auto kw_ = final_conv_bwd_weight_kernel<FMT>;
@@ -418,7 +421,7 @@ int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const vo
     launch_k((final_conv_bwd_input_kernel<FMT>), cgrid_for(total, 256), 256, 9 * cin * sizeof(float), st, dscore, inv_std, weight_tap_ci, da, da_plane, n, h, w, cin);
     launch_k((kw_), kFinalBwdBlocks, 256, smem_w, st, dscore, inv_std, a, a_plane, scratch, n, h, w, cin);
   });
-  launch_k((final_conv_bwd_finish_kernel), ceil_div(9 * cin + 1, 128), 128, 0, st, scratch, kFinalBwdBlocks, cin, dweight_oihw, dbias);
+  launch_k((final_conv_bwd_finish_kernel), ceil_div((9 * cin + 1) * 32, 256), 256, 0, st, scratch, kFinalBwdBlocks, cin, dweight_oihw, dbias);
   return check_launch("final_conv_backward");
 }
 

@@ -55,9 +55,10 @@ struct ConvTcThreads {
   static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;
 };
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED>
 __global__ void __launch_bounds__(ConvTcThreads<BLOCK_N>::kThreads, ConvTcThreads<BLOCK_N>::kMinCtas)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_o, const ConvTcParams p) {
   pdl_grid_sync();
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   using Cfg = ConvTcCfg<kSplit, BLOCK_N, kStages>;
@@ -204,8 +205,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             gn_block64_stats<FMT>(ra, rb, p.ep.bias, co0 + c0, valid, lane,
                                   p.gn_partials + ((static_cast<size_t>(img) * p.gn_chunks + chunk) * (p.ep.cout >> 3) + ((co0 + c0) >> 3)) * 2);
         }
-        epilogue_block64<FMT, ACT, PROJ>(p.ep, ra, rb, co0 + c0, n, pix, valid, lane, proj_acc);
+        StageArgs sa;
+        if (STAGED) {
+          // the pipeline stages are free once tmem_full has fired (every MMA, hence every operand read, has retired):
+          // warp e stages its 64-column blocks (x planes) back to back from smem_base + e * kWarpStride
+          const int r0 = quarter * 32;
+          sa.tmap_o = &tmap_o;
+          constexpr uint32_t kBlockStride = kSplit * kStageBlockBytes, kWarpStride = (kColsPerGroup / 64) * kBlockStride;
+          sa.stage = smem_base + static_cast<uint32_t>(warp - 2) * kWarpStride + static_cast<uint32_t>((c0 - c_begin) >> 6) * kBlockStride;
+          sa.x0 = wo0 + r0 % p.w_tile;
+          sa.y0 = ho0 + (r0 / p.w_tile) % p.h_tile;
+          sa.n0 = n0 + r0 / (p.w_tile * p.h_tile);
+        }
+        epilogue_block64<FMT, ACT, PROJ, STAGED>(p.ep, ra, rb, co0 + c0, n, pix, valid, lane, proj_acc, sa);
       }
+      if (STAGED && lane == 0) tma_store_wait_read();      // the staged tiles must be read out before the CTA retires
     }
     if (PROJ && valid) epilogue_store_proj(p.ep, pix, proj_acc);
   }
@@ -279,6 +293,27 @@ int encode_act_map(CUtensorMap* map, const void* base, int planes, size_t plane_
   return 0;
 }
 
+int encode_out_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int n, int h, int w, int c,
+                   int tile_w, int tile_h, int tile_n) {
+  EncodeTiledFn encode = get_encode_fn();
+  SBGM_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  // 32 consecutive tile rows (w fastest, then h, then n) form a rectangular sub-box because every tile extent is a power of two
+  const int bw = tile_w >= 32 ? 32 : tile_w;
+  const int bh = tile_w >= 32 ? 1 : (tile_w * tile_h >= 32 ? 32 / tile_w : tile_h);
+  const int bn = 32 / (bw * bh);
+  (void)tile_n;
+  const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, (cuuint64_t)planes};
+  const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
+                                 planes == 2 ? (cuuint64_t)plane_elems * 2 : (cuuint64_t)n * h * w * c * 2};
+  const cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SBGM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(output) failed with %d", (int)r);
+  return 0;
+}
+
 int encode_weight_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int cout, int K, int box_rows) {
   EncodeTiledFn encode = get_encode_fn();
   SBGM_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
@@ -317,11 +352,13 @@ void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
   (void)pow2_floor;
 }
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ>
-static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTcParams& p, int m_tiles, cudaStream_t st) {
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED>
+static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
+                               cudaStream_t st) {
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   using Cfg = ConvTcCfg<kSplit, BLOCK_N, kStages>;
-  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ>;
+  static_assert(!STAGED || Cfg::kBarOffset >= 4u * (BLOCK_N / 64) * kSplit * kStageBlockBytes, "the staging area must fit in the pipeline stages");
+  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -335,7 +372,7 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
     return 1;
   }
   dim3 grid(m_tiles, p.ep.cout / BLOCK_N, p.splits);
-  launch_k((kern), grid, ConvTcThreads<BLOCK_N>::kThreads, Cfg::kSmemBytes, st, ta, tb, p);
+  launch_k((kern), grid, ConvTcThreads<BLOCK_N>::kThreads, Cfg::kSmemBytes, st, ta, tb, to, p);
   if (!PROJ && p.splits > 1) {
     const size_t pixels = static_cast<size_t>(p.n) * p.ho * p.wo;
     const size_t items = pixels * (p.ep.cout / 8);
@@ -346,12 +383,16 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
 }
 
 template <int FMT, int BLOCK_N, int kStages>
-static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTcParams& p, int m_tiles, cudaStream_t st) {
+static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
+                          cudaStream_t st) {
   if (p.ep.proj_w) {
     if (BLOCK_N != 64) { set_error("conv2d_tc: projection epilogue needs a 64-wide tile"); return 1; }
-    return launch_conv_tc_inst<FMT, 64, (FMT == SBGM_FMT_BF16X2 ? 2 : 4), SBGM_ACT_NONE, true>(ta, tb, p, m_tiles, st);
+    return launch_conv_tc_inst<FMT, 64, (FMT == SBGM_FMT_BF16X2 ? 2 : 4), SBGM_ACT_NONE, 1, false>(ta, tb, to, p, m_tiles, st);
   }
-  SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kStages, ACT, false>(ta, tb, p, m_tiles, st)));
+  if (p.ep.staged) {
+    SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kStages, ACT, 0, true>(ta, tb, to, p, m_tiles, st)));
+  }
+  SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kStages, ACT, 0, false>(ta, tb, to, p, m_tiles, st)));
   return 0;
 }
 
@@ -460,18 +501,26 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
   p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
   SBGM_REQUIRE(p.w_tile * stride <= 256 && p.h_tile * stride <= 256, "conv2d_tc: TMA box too large for stride %d", stride);
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
   if (encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
   const int K = kh * kw * cin;
   if (encode_weight_map(&tb, weight, planes, w_plane, cout, K, block_n)) return 1;
+  // dense output addressing, full epilogue: the tile leaves through shared memory and TMA stores (SBGM_B200_TMA_STORE=0: off)
+  static const bool tma_store_on = [] { const char* e = getenv("SBGM_B200_TMA_STORE"); return !(e != nullptr && e[0] == '0'); }();
+  p.ep.staged = (tma_store_on && !scatter && proj_w == nullptr && p.splits == 1 && out != nullptr) ? 1 : 0;
+  if (p.ep.staged) {
+    if (encode_out_map(&to, out, planes, out_plane, n, ho, wo, cout, p.w_tile, p.h_tile, p.n_tile)) return 1;
+  } else {
+    to = ta;
+  }
   cudaStream_t st = as_stream(stream);
   if (fmt == SBGM_FMT_BF16) {
-    if (block_n == 256) return launch_conv_tc<SBGM_FMT_BF16, 256, 4>(ta, tb, p, m_tiles, st);
-    if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16, 128, 3>(ta, tb, p, m_tiles, st);
-    return launch_conv_tc<SBGM_FMT_BF16, 64, 4>(ta, tb, p, m_tiles, st);
+    if (block_n == 256) return launch_conv_tc<SBGM_FMT_BF16, 256, 4>(ta, tb, to, p, m_tiles, st);
+    if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16, 128, 3>(ta, tb, to, p, m_tiles, st);
+    return launch_conv_tc<SBGM_FMT_BF16, 64, 4>(ta, tb, to, p, m_tiles, st);
   }
-  if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16X2, 128, 3>(ta, tb, p, m_tiles, st);
-  return launch_conv_tc<SBGM_FMT_BF16X2, 64, 2>(ta, tb, p, m_tiles, st);
+  if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16X2, 128, 3>(ta, tb, to, p, m_tiles, st);
+  return launch_conv_tc<SBGM_FMT_BF16X2, 64, 2>(ta, tb, to, p, m_tiles, st);
 }
 
 extern "C" int sbgm_conv2d_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,

@@ -49,6 +49,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// bulk tensor store shared -> global (the epilogue's staged tile), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -138,6 +148,7 @@ struct EpilogueParams {
   int cout;
   void* out;
   size_t out_plane;
+  int staged;            // 1: outputs leave through shared memory + TMA store (conv_tc.cu, dense output addressing)
   const float* proj_w;   // [kProjN][64] fp32 (device) or nullptr; copied to c_proj_w before the launch
   float* proj_out;       // [pix][SBGM_PROJ_STRIDE] fp32
   int n_proj;
@@ -206,6 +217,40 @@ __device__ __forceinline__ void store_block64(void* out, size_t out_plane, int c
   }
 }
 
+// Staged variant: the lane's pixel row (64 channels = 128 bytes per plane) goes to shared memory in the 128-byte-swizzle
+// layout of a TMA box (chunk j of row r at r * 128 + ((j ^ (r & 7)) << 4): conflict-free 16-byte stores), and one lane
+// hands the warp's 32 x 64 sub-box to the TMA unit.  Replaces the shuffle transpose + 8 predicated stores per plane --
+// ~220 of the ~270 instructions per plane in an epilogue that ncu showed to be the kernels' critical path; bounds clipping
+// comes from the tensor map.  `stage` = this warp's staging area for this block (planes kStageBlockBytes apart).
+constexpr uint32_t kStageBlockBytes = 32 * 128;
+template <int FMT>
+__device__ __forceinline__ void store_block64_staged(const CUtensorMap* tmap_o, uint32_t stage, const float (&v)[64], int co_base,
+                                                     int x0, int y0, int n0, int lane) {
+  constexpr int kPlanes = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
+#pragma unroll
+  for (int pl = 0; pl < kPlanes; ++pl) {
+    const uint32_t row = stage + pl * kStageBlockBytes + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = v[j * 8 + e];
+        t[e] = (pl == 0) ? x : x - bf16_round(x);
+      }
+      const uint4 c = pack_bf16x8(t);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ (lane & 7)) << 4)), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
+    }
+  }
+  fence_async_shared();
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int pl = 0; pl < kPlanes; ++pl) tma_store_5d(tmap_o, stage + pl * kStageBlockBytes, co_base, x0, y0, n0, pl);
+    tma_store_commit();
+  }
+}
+
 // GroupNorm partial statistics of one 64-channel block, at 8-channel granularity, reduced over the warp's 32
 // rows: dst[sub][2] (sum, sum of squares) for sub = 0..7.  Values are taken as stored (bias added, bf16-rounded
 // in BF16 mode).  Must be called by the whole warp; rows with !valid contribute nothing.
@@ -235,10 +280,16 @@ __device__ __forceinline__ void gn_block64_stats(const uint32_t (&ra)[32], const
 
 // 64 accumulator columns (two 32-column TMEM loads) of one row.  ACT and PROJ are compile-time
 // (PROJ: 0 = store, 1 = projection only, 2 = projection AND store -- the training forward keeps the tensor).
-template <int FMT, int ACT, int PROJ>
+struct StageArgs {          // where a staged block goes (unused when !STAGED)
+  const CUtensorMap* tmap_o;
+  uint32_t stage;
+  int x0, y0, n0;
+};
+
+template <int FMT, int ACT, int PROJ, bool STAGED = false>
 __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const uint32_t (&ra)[32], const uint32_t (&rb)[32],
                                                  int co_base, int n, size_t pix, bool valid, int lane,
-                                                 float (&proj_acc)[kProjMax]) {
+                                                 float (&proj_acc)[kProjMax], const StageArgs& sa = StageArgs{}) {
   float v[64];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -277,7 +328,10 @@ __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const
 #pragma unroll
       for (int q = 0; q < kProjN; ++q) proj_acc[q] = fmaf(v[j], c_proj_w[q * 64 + j], proj_acc[q]);
   }
-  if (PROJ != 1) store_block64<FMT>(ep.out, ep.out_plane, ep.cout, v, pix, valid, co_base, lane);   // PROJ == 2: both (training)
+  if (PROJ != 1) {          // PROJ == 2: both (training)
+    if (STAGED) store_block64_staged<FMT>(sa.tmap_o, sa.stage, v, co_base, sa.x0, sa.y0, sa.n0, lane);
+    else store_block64<FMT>(ep.out, ep.out_plane, ep.cout, v, pix, valid, co_base, lane);
+  }
 }
 
 __device__ __forceinline__ void epilogue_store_proj(const EpilogueParams& ep, size_t pix, const float (&proj_acc)[kProjMax]) {
@@ -305,6 +359,9 @@ EncodeTiledFn get_encode_fn();
 // NHWC activation [planes][n][h][w][c] bf16 as a 5-D map, box = (64, bw, bh, bn, 1), element strides (1, s, s, 1, 1)
 int encode_act_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int n, int h, int w, int c,
                    int box_w, int box_h, int box_n, int stride);
+// NHWC output [planes][n][h][w][c] bf16 as a 5-D map whose box is a warp's 32-row share of a (box_w, box_h, box_n) tile
+int encode_out_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int n, int h, int w, int c,
+                   int tile_w, int tile_h, int tile_n);
 // packed weights [planes][cout][K] bf16 as a 3-D map, box = (64, box_rows, 1)
 int encode_weight_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int cout, int K, int box_rows);
 // (w_tile, h_tile, n_tile), product 128, powers of two, covering an [n][ho][wo] pixel grid with the least padding
