@@ -221,6 +221,12 @@ int sbgm_cfg_combine(const float* s_cond, const float* s_uncond, float scale, fl
 /* copy row *step_counter of table[steps][cols] to out[cols] (time projections of the step) */
 int sbgm_select_step_row(const float* table, int cols, const int32_t* step_counter, float* out, void* stream);
 
+/* ---- ensemble statistics (BASELINE.json parity criterion; evaluation itself is sbgm/evaluate_sbgm/, out of scope) ----
+ * members[m][pixels] fp32 -> per-pixel mean, std (Bessel-corrected), and, given truth[pixels], the ensemble CRPS
+ * E|X - y| - 1/2 E|X - X'| (crps may be NULL).  Lets a sampled ensemble be scored on the device before any D2H copy. */
+int sbgm_ensemble_stats(const float* members, const float* truth, int m, size_t pixels, float* mean, float* stdev, float* crps,
+                        void* stream);
+
 /* ---- DSM loss (loss_fn, score_unet.py:936-985) -------------------------------------------
  * perturb: x_t = x + std[n] * z, z from the Philox stream (draw id `draw`), also stores z.
  * loss:    loss = 1/n * sum_{n,pix} w * (score * std[n] + z)^2, w = 0.5 sigmoid(sdf) + 0.5 or 1;

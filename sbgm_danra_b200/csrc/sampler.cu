@@ -197,6 +197,32 @@ __global__ void dsm_loss_finish_kernel(const float* __restrict__ partials, int n
   }
 }
 
+// ---- ensemble statistics: per-pixel mean, std (Bessel), CRPS = E|X - y| - 1/2 E|X - X'| over the M members ------------
+// One thread per pixel; member m of pixel p is members[m * pixels + p], so every load is coalesced across the warp.
+// The pair term is the O(M^2) double loop (M = 64: 2 016 pairs) -- the members of a pixel stay in L1.
+__global__ void ensemble_stats_kernel(const float* __restrict__ members, const float* __restrict__ truth, int m, size_t pixels,
+                                      float* __restrict__ mean, float* __restrict__ stdev, float* __restrict__ crps) {
+  pdl_grid_sync();
+  for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < pixels; p += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float s = 0.0f;
+    for (int i = 0; i < m; ++i) s += members[static_cast<size_t>(i) * pixels + p];
+    const float mu = s / m;
+    float q = 0.0f, a = 0.0f, pair = 0.0f;
+    const float y = truth ? truth[p] : 0.0f;
+    for (int i = 0; i < m; ++i) {
+      const float xi = members[static_cast<size_t>(i) * pixels + p];
+      q = fmaf(xi - mu, xi - mu, q);
+      if (crps) {
+        a += fabsf(xi - y);
+        for (int j = i + 1; j < m; ++j) pair += fabsf(xi - members[static_cast<size_t>(j) * pixels + p]);
+      }
+    }
+    mean[p] = mu;
+    stdev[p] = m > 1 ? sqrtf(q / (m - 1)) : 0.0f;
+    if (crps) crps[p] = a / m - pair / (static_cast<float>(m) * m);
+  }
+}
+
 }  // namespace sbgm
 
 using namespace sbgm;
@@ -264,6 +290,14 @@ int sbgm_dsm_loss(const float* score, const float* std, const float* z, const fl
   launch_k((dsm_loss_partial_kernel), blocks, kBlock, 0, as_stream(stream), score, std, z, sdf, nq, per_member / 4, partials);
   launch_k((dsm_loss_finish_kernel), 1, 256, 0, as_stream(stream), partials, blocks, 1.0f / n, loss_out);
   return check_launch("dsm_loss");
+}
+
+int sbgm_ensemble_stats(const float* members, const float* truth, int m, size_t pixels, float* mean, float* stdev, float* crps,
+                        void* stream) {
+  SBGM_REQUIRE(m >= 1 && pixels >= 1, "ensemble_stats: empty ensemble");
+  SBGM_REQUIRE(crps == nullptr || truth != nullptr, "ensemble_stats: CRPS needs the verifying field");
+  launch_k((ensemble_stats_kernel), grid_for(pixels), kBlock, 0, as_stream(stream), members, truth, m, pixels, mean, stdev, crps);
+  return check_launch("ensemble_stats");
 }
 
 }  // extern "C"

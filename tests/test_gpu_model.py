@@ -248,3 +248,56 @@ def test_non_power_of_two_size_matches_oracle():
             want = score_ref.score_forward(sd, cfg, *b.model_args())
             got = net(*[_cuda(v) for v in b.model_args()]).cpu()
         assert rel_l2(got, want) < tol, precision
+
+
+@pytest.mark.parametrize("m,shape", [(1, (8, 8)), (7, (5, 9)), (64, (32, 32))])
+def test_ensemble_statistics_kernel_matches_oracle(m, shape):
+    from oracle.ensemble_ref import ensemble_statistics as ref_stats
+    from sbgm_danra_b200.ensemble import ensemble_statistics
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(m, 1, *shape, generator=g) * 2.0 + 0.5
+    y = torch.randn(1, *shape, generator=g)
+    got = ensemble_statistics(x.to(DEV), y.to(DEV))
+    want = ref_stats(x[:, 0].numpy(), y[0].numpy())
+    for k in ("mean", "std", "crps"):
+        assert np.allclose(got[k].cpu().numpy(), want[k], rtol=2e-5, atol=2e-6), k
+
+
+@pytest.mark.parametrize("precision,kind", [("bf16x3", "em"), ("bf16x3", "pc"), ("bf16", "em")])
+def test_sampled_ensemble_statistics_match_oracle_within_one_percent(precision, kind):
+    """BASELINE.json parity criterion: the sampled ensemble's pixel-wise mean / std and CRPS agree with the reference
+    path (the CPU oracle's sampler on the same Philox noise) to within 1%.  16 members, 32x32, 40 steps."""
+    from oracle import samplers_ref, score_ref
+    from oracle.ensemble_ref import ensemble_statistics as ref_stats
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.ensemble import ensemble_statistics
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    members, size, steps, seed = 16, 32, 40, 99
+    cfg = config_for(n_lr=1)
+    sd = synth_state_dict(cfg)
+    net = build_model(cfg, sd, precision, DEV)
+    b = synth_batch(batch=members, size=size, n_lr=1, shared_cond=True)
+    truth = synth_batch(batch=1, size=size, n_lr=1, seed=77).x[0]
+    ss.manual_seed(seed)
+    fn = ss.Euler_Maruyama_sampler if kind == "em" else ss.pc_sampler
+    ours = fn(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=members, num_steps=steps, device=DEV, img_size=size,
+              cond_img=b.cond_img.to(DEV))
+    score = lambda x, t: score_ref.score_forward(sd, cfg, x, t, None, b.cond_img)
+    with torch.no_grad():
+        if kind == "em":
+            ref = samplers_ref.euler_maruyama(score, score_ref.marginal_prob_std, score_ref.diffusion_coeff, members, steps,
+                                              img_size=size, noise=samplers_ref.philox_noise(seed))
+        else:
+            ref = samplers_ref.predictor_corrector(score, score_ref.marginal_prob_std, score_ref.diffusion_coeff, members, steps,
+                                                   img_size=size, noise=samplers_ref.philox_noise(seed))
+    got = ensemble_statistics(ours, truth.to(DEV))
+    want = ref_stats(ref[:, 0].numpy(), truth[0].numpy())
+    for k in ("mean", "std", "crps"):
+        g_, w_ = got[k].cpu().numpy().astype(np.float64), want[k]
+        rel = np.linalg.norm(g_ - w_) / np.linalg.norm(w_)
+        dom = abs(g_.mean() - w_.mean()) / abs(w_.mean()) if k != "mean" else 0.0
+        print(f"{kind} [{precision}] {k}: field rel-L2 {rel:.2e}, domain-mean rel {dom:.2e}")
+        tol = 1e-2 if precision == "bf16x3" else 5e-2          # the 1% gate is for the fp32-class mode; bf16 is reported at 5%
+        assert rel < tol and dom < tol, (k, rel, dom)
