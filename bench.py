@@ -46,6 +46,17 @@ def _config(args, world):
             "l2": "256 MiB L2 flush between timed steps; per-network-evaluation activation footprint (~1.5 GB) exceeds the 126 MB L2"}
 
 
+def load_traffic():
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_dominant_kernel_ncu.json, written by tools/ncu_traffic.py), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_dominant_kernel_ncu.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return d["dram_bytes_read"] + d["dram_bytes_write"]
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -257,7 +268,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                     "frac": achieved / peaks["bf16_tflops"], "traffic": load_traffic(),
                      "kernel": "conv_tc_kernel (tcgen05 implicit GEMM) on decoder.final_layer.conv_up 64->64 3x3 @128x128 x64",
                      "kernel_ms": kms, "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", burst bf16",
                      "tensor_pipe_frac": (3.0 if args.precision == "bf16x3" else 1.0) * achieved / peaks["bf16_tflops"],

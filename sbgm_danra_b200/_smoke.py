@@ -51,4 +51,23 @@ def run() -> None:
     err = float((got - want).norm() / want.norm())
     print(f"smoke EM 2 steps rel-L2 vs oracle = {err:.3e}")
     assert err < 2e-3, f"sampler parity failed: {err}"
+    # one DSM training step (loss + backward kernels) against the oracle's autograd on the same Philox draws
+    from oracle import philox_ref
+    from .score_unet import loss_fn
+    cfg_t = config_for(n_lr=1)
+    bt = synth_batch(batch=2, size=32, n_lr=1)
+    net_t = build_model(cfg_t, sd, "bf16x3", dev).train()
+    score_sampling.manual_seed(11)
+    loss = loss_fn(net_t, bt.x.to(dev), marginal_prob_std_fn, cond_img=bt.cond_img.to(dev), sdf_cond=bt.sdf_cond.to(dev))
+    loss.backward()
+    sdo = {k: (v.clone().requires_grad_() if k == "decoder.final_layer.conv.weight" else v.clone()) for k, v in sd.items()}
+    u = torch.from_numpy(philox_ref.uniform(2, 11, philox_ref.DRAW_DSM_T))
+    z = torch.from_numpy(philox_ref.normal(bt.x.numel(), 11, philox_ref.DRAW_DSM_Z)).reshape(bt.x.shape)
+    lo = score_ref.dsm_loss(sdo, cfg_t, bt.x, u * (1.0 - 1e-3) + 1e-3, z, None, bt.cond_img, None, None, bt.sdf_cond, bn_train=True)
+    lo.backward()
+    g, go = net_t.decoder.final_layer.conv.weight.grad.cpu(), sdo["decoder.final_layer.conv.weight"].grad
+    e_loss = abs(loss.item() - lo.item()) / abs(lo.item())
+    e_grad = float((g - go).norm() / go.norm())
+    print(f"smoke DSM step: loss {loss.item():.5f} vs oracle {lo.item():.5f} (rel {e_loss:.2e}); d(final conv) rel-L2 = {e_grad:.2e}")
+    assert e_loss < 1e-3 and e_grad < 2e-3, "training-step parity failed"
     print("smoke OK")
