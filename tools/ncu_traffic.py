@@ -25,7 +25,7 @@ def main():
         val = lambda k: float(d[k].replace(",", "")) * UNIT.get(units[h.index(k)], 1.0)
         rec = {"kernel": d["Kernel Name"], "duration_us": float(d["gpu__time_duration.sum"].replace(",", "")),
                "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
-               "tensor_pipe_pct_of_peak_active": float(d.get("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "nan") or "nan"),
+               "sm__pipe_tensor_cycles_active_pct_of_peak_elapsed": float(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "nan") or "nan"),
                "source": os.path.basename(rep) + " (ncu --set full --clock-control none)"}
         if best is None or rec["duration_us"] > best["duration_us"]:
             best = rec
