@@ -13,6 +13,7 @@ torch supplies memory, streams and the autograd hook; every FLOP runs in this re
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -36,7 +37,6 @@ def _pack_oihw(w: torch.Tensor, fmt: int) -> torch.Tensor:
 
 def _pack_tc(w: torch.Tensor, fmt: int, taps: Sequence[int], transpose: bool) -> torch.Tensor:
     """One-launch pack (sbgm_pack_weight): out[o][t][i] = w[co][ci][taps[t]], (o, i) = (ci, co) if transpose."""
-    import ctypes
     cout, cin, kh, kw = w.shape
     w = w.contiguous()
     oo, ii = (cin, cout) if transpose else (cout, cin)
@@ -48,10 +48,10 @@ def _pack_tc(w: torch.Tensor, fmt: int, taps: Sequence[int], transpose: bool) ->
     return out if planes == 2 else out[0]
 
 
-class _PackJob(__import__("ctypes").Structure):
-    import ctypes as _C
-    _fields_ = [("w", _C.c_void_p), ("out", _C.c_void_p), ("out_plane", _C.c_size_t), ("cout", _C.c_int), ("cin", _C.c_int),
-                ("khw", _C.c_int), ("ntaps", _C.c_int), ("transpose", _C.c_int), ("taps", _C.c_int * 16)]
+class _PackJob(ctypes.Structure):        # mirrors sbgm_pack_job (include/sbgm_b200.h)
+    _fields_ = [("w", ctypes.c_void_p), ("out", ctypes.c_void_p), ("out_plane", ctypes.c_size_t), ("cout", ctypes.c_int),
+                ("cin", ctypes.c_int), ("khw", ctypes.c_int), ("ntaps", ctypes.c_int), ("transpose", ctypes.c_int),
+                ("taps", ctypes.c_int * 16)]
 
 
 class PackPlan:
@@ -72,7 +72,6 @@ class PackPlan:
         return out if planes == 2 else out[0]
 
     def run(self) -> None:
-        import ctypes
         small = [j for j in self.jobs if len(j[5]) <= 16]
         for w4, out, cout, cin, khw, taps, tr in (j for j in self.jobs if len(j[5]) > 16):
             arr = (ctypes.c_int * len(taps))(*taps)
@@ -144,6 +143,25 @@ class ConvLayer:
         cw = ConvW(packed, None, self.cout, self.cin, len(rs), len(ss))
         self._dgrad[key] = (cw, -dys[0], -dxs[0])
         return self._dgrad[key]
+
+
+class ConvTLayer:
+    """nn.ConvTranspose2d(c_in, c_out, kernel 2, stride 2) of the `use_resize_conv=False` decoder (score_unet.py:466-468).
+    Its weight [c_in][c_out][2][2] is, read as OIHW, the weight of the stride-2 2x2 convolution C: y-grid -> x-grid whose
+    transpose it is: the input gradient is C applied to dy, the weight gradient is C's weight gradient with the roles of
+    the tensors swapped."""
+
+    def __init__(self, name: str, w: torch.Tensor, bias: torch.Tensor, fmt: int, bias_name: str):
+        self.name, self.bias_name, self.fmt = name, bias_name, fmt
+        self.w, self.shape = w.contiguous(), tuple(w.shape)
+        self.cin, self.cout = w.shape[0], w.shape[1]
+        self.bias = bias.contiguous()
+        self.back = ConvW(_pack_oihw(self.w, fmt), None, self.cout, self.cin, 2, 2)          # C: cout channels in, cin out
+        if fmt == FMT_F32:
+            self.fwd_simt = self.w.permute(2, 3, 0, 1).reshape(4, self.cin, self.cout).contiguous()
+        else:
+            self.fwd_subs = [(a, b, ConvW(_pack_tc(self.w, fmt, [a * 2 + b], True), self.bias, self.cin, self.cout, 1, 1))
+                             for a in range(2) for b in range(2)]
 
 
 class Tape:
@@ -410,6 +428,43 @@ class TrainKernels:
         tape.record(backward, x, y)
         return y
 
+    def conv_transpose2x(self, x: Act, layer: ConvTLayer) -> Act:
+        fmt, st = self.fmt, _stream()
+        y = Act(fmt, x.n, 2 * x.h, 2 * x.w, layer.cout, self.device)
+        if fmt == FMT_F32:
+            raw = Act(fmt, x.n, 2 * x.h, 2 * x.w, layer.cout, self.device)
+            call("sbgm_conv2d_dgrad_simt", x.ptr, x.plane, layer.fwd_simt.data_ptr(), raw.ptr, raw.plane, 0, fmt,
+                 x.n, 2 * x.h, 2 * x.w, layer.cout, layer.cin, 2, 2, 2, 0, st)
+            unit = torch.tensor([0.0, 1.0], dtype=torch.float32, device=self.device).repeat(layer.cout, 1).contiguous()
+            call("sbgm_norm_apply", raw.ptr, raw.plane, unit.data_ptr(), 2, layer.cout, None, layer.bias.data_ptr(), None, 0, None, 0, 0,
+                 ACT_NONE, y.ptr, y.plane, fmt, x.n, 4 * x.h * x.w, layer.cout, st)
+        else:
+            for a, b, cw in layer.fwd_subs:
+                call("sbgm_conv2d_tc_ex", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, cw.bias.data_ptr(), None, 0, 0, None, 0, y.ptr, y.plane,
+                     fmt, x.n, x.h, x.w, cw.cin, cw.cout, 1, 1, 1, 0, 0, x.h, x.w, 2 * x.h, 2 * x.w, 2, a, b, ACT_NONE, None, 0, st)
+        tape = self.tape
+
+        def backward() -> None:
+            dy = tape.pop(y)
+            if dy is None:
+                return
+            s2 = _stream()
+            db = self.param_grad(layer.bias_name, (layer.cout,))
+            ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, layer.cout))
+            call("sbgm_channel_sums", dy.ptr, dy.plane, fmt, dy.n, dy.h * dy.w, layer.cout, None, 0, db.data_ptr(), ws.data_ptr(), s2)
+            dw = self.param_grad(layer.name, layer.shape)
+            args = (dy.n, dy.h, dy.w, layer.cout, layer.cin, 2, 2, 2, 0)      # C: input dy-grid (cout channels), output x-grid
+            if fmt != FMT_F32 and layer.cin % 64 == 0 and layer.cout % 64 == 0:
+                wsw = self.scratch("wgrad", _lib.query("sbgm_conv2d_wgrad_tc_workspace_floats", fmt, *args))
+                call("sbgm_conv2d_wgrad_tc", dy.ptr, dy.plane, x.ptr, x.plane, dw.data_ptr(), fmt, *args, wsw.data_ptr(), s2)
+            else:
+                wsw = self.scratch("wgrad", _lib.query("sbgm_conv2d_wgrad_simt_workspace_floats", *args))
+                call("sbgm_conv2d_wgrad_simt", dy.ptr, dy.plane, x.ptr, x.plane, dw.data_ptr(), fmt, *args, wsw.data_ptr(), s2)
+            tape.add(x, self.k.conv(dy, layer.back, stride=2, pad=0))
+
+        tape.record(backward, x, y)
+        return y
+
     def upsample2x(self, x: Act) -> Act:
         y = self.k.upsample2x(x)
         tape = self.tape
@@ -486,8 +541,6 @@ class TrainEngine:
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("sbgm_danra_b200 runs on CUDA devices only (no CPU fallback); got device " + str(device))
-        if not spec.use_resize_conv:
-            raise NotImplementedError("use_resize_conv=False (ConvTranspose2d decoder) has no training path yet")
         _lib.load_library()
         self.spec, self.device, self.fmt, self.bn_train = spec, device, PRECISIONS[precision], bn_train
         self.sd = {k: v.detach() for k, v in params.items()}
@@ -569,7 +622,9 @@ class TrainEngine:
         self.dec_blocks = []
         for i, (cin, cout, attn) in enumerate(spec.plan):
             bp = f"{d}residual_layers.{i}"
-            blk = dict(conv_up=self._conv(f"{bp}.conv_up.weight", f"{bp}.conv_up.bias", 1, 1), conv=self._conv(f"{bp}.conv.weight", f"{bp}.conv.bias", 1, 1),
+            up_layer = (self._conv(f"{bp}.conv_up.weight", f"{bp}.conv_up.bias", 1, 1) if spec.use_resize_conv else
+                        ConvTLayer(f"{bp}.transpose.weight", sd[f"{bp}.transpose.weight"], sd[f"{bp}.transpose.bias"], fmt, f"{bp}.transpose.bias"))
+            blk = dict(conv_up=up_layer, conv=self._conv(f"{bp}.conv.weight", f"{bp}.conv.bias", 1, 1),
                        n1=(sd[f"{bp}.norm1.weight"], sd[f"{bp}.norm1.bias"], f"{bp}.norm1.weight", f"{bp}.norm1.bias") if affine else (None, None, None, None),
                        n2=(sd[f"{bp}.norm2.weight"], sd[f"{bp}.norm2.bias"], f"{bp}.norm2.weight", f"{bp}.norm2.bias") if affine else (None, None, None, None),
                        g1=max(1, min(spec.gn_groups, cin)) if affine else cin, g2=max(1, min(spec.gn_groups, cout)) if affine else cout,
@@ -581,7 +636,8 @@ class TrainEngine:
             self.dec_blocks.append(blk)
         self.tp.finalize()
         fp = f"{d}final_layer"
-        self.final_up = self._conv(f"{fp}.conv_up.weight", f"{fp}.conv_up.bias", 1, 1)
+        self.final_up = (self._conv(f"{fp}.conv_up.weight", f"{fp}.conv_up.bias", 1, 1) if spec.use_resize_conv else
+                         ConvTLayer(f"{fp}.transpose.weight", sd[f"{fp}.transpose.weight"], sd[f"{fp}.transpose.bias"], fmt, f"{fp}.transpose.bias"))
         wf = sd[f"{fp}.conv.weight"]
         if wf.shape[0] != 1:
             raise NotImplementedError("the training path supports output_channels == 1 (the reference's only configuration)")
@@ -660,8 +716,10 @@ class TrainEngine:
         rev = list(reversed(fmaps))
         out = rev[0]
         for i, blk in enumerate(self.dec_blocks):
-            up = tk.upsample2x(out)
-            a, st1 = tk.conv(up, blk["conv_up"], pad=1, gn_stats=True)
+            if self.spec.use_resize_conv:
+                a, st1 = tk.conv(tk.upsample2x(out), blk["conv_up"], pad=1, gn_stats=True)
+            else:
+                a, st1 = tk.conv_transpose2x(out, blk["conv_up"]), None
             a = tk.groupnorm(a, *blk["n1"], groups=blk["g1"], fused=st1)
             b, st2 = tk.conv(a, blk["conv"], pad=1, gn_stats=True)
             skip = rev[i + 1]
@@ -671,9 +729,13 @@ class TrainEngine:
                                dtproj=col(dtproj, blk["name"]), fused=st2)
             if blk["attn"] is not None:
                 out = _attention_block(tk, blk["attn"], out)
-        up = tk.upsample2x(out)
         res = torch.empty((n, 1, 2 * out.h, 2 * out.w), dtype=torch.float32, device=dev)
-        if fmt != FMT_F32 and tk.k._c64_ok(up, self.final_up.fwd, 1, 1):
+        up = tk.upsample2x(out) if self.spec.use_resize_conv else None
+        if up is None:
+            a = tk.conv_transpose2x(out, self.final_up)
+            call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None,
+                 res.data_ptr(), a.n, a.h, a.w, a.c, 1, _stream())
+        elif fmt != FMT_F32 and tk.k._c64_ok(up, self.final_up.fwd, 1, 1):
             # the 64 -> 1 convolution rides in conv_up's epilogue (projection); conv_up's output is kept for the backward
             a, pr = tk.conv(up, self.final_up, pad=1, proj=self.final_w[0])
             call("sbgm_final_gather", pr.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None, res.data_ptr(), a.n, a.h, a.w,

@@ -464,3 +464,38 @@ def test_train_mode_batchnorm_forward_matches_reference_golden(golden, precision
     err = rel_l2(out, golden["fwd_c3_64_cin7_seasons/score_bn_train"])
     print(f"train-mode BN forward [{precision}] rel-L2 = {err:.3e}")
     assert err < {"fp32": 1e-4, "bf16x3": 1e-3}[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_transpose_decoder_trains(precision):
+    """`use_resize_conv=False` (ConvTranspose2d decoder, the reference's ablation switch): loss and all gradients against
+    the oracle's autograd."""
+    from oracle import philox_ref, score_ref
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1, use_resize_conv=False, activation="gelu", n_heads=8)
+    sd = synth_state_dict(cfg)
+    b = synth_batch(batch=4, size=32, n_lr=1)
+    net = build_model(cfg, sd, precision, DEV).train()
+    score_sampling.manual_seed(5)
+    loss = loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, cond_img=b.cond_img.to(DEV))
+    loss.backward()
+    sdo = {k: (v.clone().requires_grad_() if v.is_floating_point() and not k.endswith(("running_mean", "running_var", ".W")) else v.clone())
+           for k, v in sd.items()}
+    u = torch.from_numpy(philox_ref.uniform(4, 5, philox_ref.DRAW_DSM_T))
+    z = torch.from_numpy(philox_ref.normal(b.x.numel(), 5, philox_ref.DRAW_DSM_Z)).reshape(b.x.shape)
+    lo = score_ref.dsm_loss(sdo, cfg, b.x, u * (1.0 - 1e-3) + 1e-3, z, None, b.cond_img, None, None, None, bn_train=True)
+    lo.backward()
+    assert abs(loss.item() - lo.item()) / abs(lo.item()) < {"fp32": 1e-4, "bf16x3": 1e-3}[precision]
+    params = dict(net.named_parameters())
+    used = [k for k, v in sdo.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None]
+    assert any("transpose.weight" in k for k in used)
+    for k in used:
+        assert params[k].grad is not None, k
+        if "transpose" in k:
+            assert rel_l2(params[k].grad.cpu(), sdo[k].grad) < {"fp32": 1e-3, "bf16x3": 2e-3}[precision], k
+    whole = rel_l2(torch.cat([params[k].grad.cpu().reshape(-1) for k in used]), torch.cat([sdo[k].grad.reshape(-1) for k in used]))
+    print(f"transpose decoder [{precision}]: loss {loss.item():.5f} vs {lo.item():.5f}, whole-gradient rel-L2 {whole:.2e}")
+    assert whole < {"fp32": 1e-4, "bf16x3": 1e-3}[precision]
