@@ -70,8 +70,12 @@ def _next_seed() -> int:
 
 
 def _is_native(score_model) -> bool:
+    """The fused, graph-captured step serves a ScoreNet of this package in eval mode.  In `.train()` (the reference's
+    generation quirk: BatchNorm with batch statistics while sampling, evaluate_sbgm/generation.py:47) every step goes
+    through `ScoreNet.forward`, i.e. the training-graph forward with batch statistics and running-stat updates
+    (itself replayed from a CUDA graph after two steps)."""
     from .score_unet import ScoreNet
-    return isinstance(score_model, ScoreNet)
+    return isinstance(score_model, ScoreNet) and not score_model.training
 
 
 def _cfg_scale(cfg, clamp: bool) -> Optional[float]:

@@ -363,3 +363,59 @@ def test_conv_fused_groupnorm_statistics(E, prec, shape):
     got = kern.groupnorm(y, gamma.cuda(), beta.cuda(), 8, stats=stats).to_nchw().cpu()
     want = F.group_norm(y.to_nchw().cpu(), 8, gamma, beta, 1e-5)
     assert rel_l2(got, want) < {"bf16": 8e-3, "bf16x3": 3e-5}[prec]
+
+
+# ---- entry points added for the training step / tensor-core stem -------------------------------------------------
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_pack_weights_batched_matches_torch(prec):
+    """sbgm_pack_weights (one launch, job table as kernel parameter) and sbgm_pack_weight against a torch restatement:
+    forward orientation, transposed / tap-sliced orientation (the data-gradient weights)."""
+    from sbgm_danra_b200 import train_engine as T
+    fmt = FMTS[prec]
+    plan = T.PackPlan(fmt)
+    cases = [(gen(64, 128, 3, 3, seed=1).cuda(), list(range(9)), False), (gen(128, 64, 3, 3, seed=2).cuda(), [8, 6, 2, 0], True),
+             (gen(256, 64, 1, 1, seed=3).cuda(), [0], True), (gen(64, 64, 8, 8, seed=4).cuda(), list(range(64)), False)]
+    outs = [plan.add(w, taps, tr) for w, taps, tr in cases]
+    plan.run()
+    for (w, taps, tr), out in zip(cases, outs):
+        cout, cin = w.shape[:2]
+        sel = w.reshape(cout, cin, -1)[:, :, taps]                                  # [co][ci][t]
+        want = (sel.permute(1, 2, 0) if tr else sel.permute(0, 2, 1)).reshape(cin if tr else cout, -1)
+        single = T._pack_tc(w, fmt, taps, tr)
+        assert torch.equal(out, single)
+        got = (out[0].float() + out[1].float()) if fmt == 2 else out.float()
+        assert rel_l2(got.cpu(), want.cpu()) < ELEM_TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("cc,bcast,size", [(1, True, 64), (6, False, 32), (0, False, 96)])
+def test_stem_im2col_matches_unfold(E, prec, cc, bcast, size):
+    fmt = FMTS[prec]
+    n = 3
+    x = gen(n, 1, size, size, seed=1)
+    planes = gen(1 if bcast else n, cc, size, size, seed=2) if cc else None
+    k = E.Kernels(fmt, torch.device("cuda"))
+    col = k.stem_im2col(x.cuda(), None if planes is None else planes.cuda(), 0, cc + 1, cc).to_nchw().cpu()
+    full = x if planes is None else torch.cat([x, planes.expand(n, -1, -1, -1)], 1)
+    want = F.unfold(full, kernel_size=8, padding=3, stride=2).reshape(n, (cc + 1) * 64, size // 2, size // 2)
+    assert rel_l2(col, want) < ELEM_TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_conv2d_tc_ex_scatter_is_conv_transpose(E, prec):
+    """Four scattered 1x1 convolutions (out_step 2, offsets (a, b)) = ConvTranspose2d(kernel 2, stride 2) with bias."""
+    from sbgm_danra_b200._lib import call
+    fmt = FMTS[prec]
+    n, c_in, c_out, h, w = 2, 128, 64, 6, 10
+    x, wt, bias = gen(n, c_in, h, w, seed=1), gen(c_in, c_out, 2, 2, seed=2, scale=c_in ** -0.5), gen(c_out, seed=3, scale=0.1)
+    xa = act_of(E, x, fmt)
+    out = E.Act(fmt, n, 2 * h, 2 * w, c_out, torch.device("cuda"))
+    bd = bias.cuda()
+    for a in range(2):
+        for b in range(2):
+            km = wt[:, :, a, b].t().contiguous().cuda()
+            packed = km.to(torch.bfloat16) if fmt == 1 else E._split_bf16(km)
+            call("sbgm_conv2d_tc_ex", xa.ptr, xa.plane, packed.data_ptr(), c_out * c_in, bd.data_ptr(), None, 0, 0, None, 0, out.ptr, out.plane,
+                 fmt, n, h, w, c_in, c_out, 1, 1, 1, 0, 0, h, w, 2 * h, 2 * w, 2, a, b, 0, None, 0, torch.cuda.current_stream().cuda_stream)
+    want = F.conv_transpose2d(xa.to_nchw().cpu(), wt, bias, stride=2)
+    assert rel_l2(out.to_nchw().cpu(), want) < TOL[prec]

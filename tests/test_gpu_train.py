@@ -499,3 +499,29 @@ def test_transpose_decoder_trains(precision):
     whole = rel_l2(torch.cat([params[k].grad.cpu().reshape(-1) for k in used]), torch.cat([sdo[k].grad.reshape(-1) for k in used]))
     print(f"transpose decoder [{precision}]: loss {loss.item():.5f} vs {lo.item():.5f}, whole-gradient rel-L2 {whole:.2e}")
     assert whole < {"fp32": 1e-4, "bf16x3": 1e-3}[precision]
+
+
+def test_sampling_in_train_mode_uses_batch_statistics():
+    """`model.train()` while sampling (generation.py:47 quirk): EM trajectory against the oracle sampler whose score uses
+    BatchNorm batch statistics; the running statistics move, as they do in the reference."""
+    from oracle import samplers_ref, score_ref
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    sd = synth_state_dict(cfg)
+    net = build_model(cfg, sd, "bf16x3", DEV).train()
+    b = synth_batch(batch=4, size=32, n_lr=1, shared_cond=True)
+    rm0 = net.encoder.bn1.running_mean.clone()
+    ss.manual_seed(21)
+    got = ss.Euler_Maruyama_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=4, num_steps=5, device=DEV,
+                                    img_size=32, cond_img=b.cond_img.to(DEV)).cpu()
+    with torch.no_grad():
+        want = samplers_ref.euler_maruyama(lambda x, t: score_ref.score_forward(sd, cfg, x, t, None, b.cond_img, bn_train=True),
+                                           score_ref.marginal_prob_std, score_ref.diffusion_coeff, 4, 5, img_size=32,
+                                           noise=samplers_ref.philox_noise(21))
+    err = rel_l2(got, want)
+    print(f"train-mode EM (5 steps) rel-L2 vs oracle = {err:.3e}")
+    assert err < 2e-3
+    assert not torch.equal(net.encoder.bn1.running_mean, rm0)
