@@ -376,10 +376,12 @@ class ScoreNet(nn.Module):
                              out_channels=d.output_channels, use_resize_conv=d.use_resize_conv, norm=d.norm,
                              gn_groups=d.gn_groups, activation=_act_name(d.activation))
 
-    def engine(self) -> _eng.UNetEngine:
-        """Packed-weight engine for the current parameters (cached; rebuilt after parameter updates)."""
+    def engine(self, lane: int = 0) -> _eng.UNetEngine:
+        """Packed-weight engine for the current parameters (cached; rebuilt after parameter updates).  `lane` > 0 gives an
+        independent engine (own packed weights and scratch buffers) for a second concurrent stream of the samplers."""
         _require_cuda(self.encoder.conv1.weight, "ScoreNet")
-        return self._cache.get(self, self.precision, lambda dev: _eng.UNetEngine(self.state_dict(), self.spec(), self.precision, dev))
+        cache = self._cache if lane == 0 else self.__dict__.setdefault("_lane_caches", {}).setdefault(lane, _EngineCache())
+        return cache.get(self, self.precision, lambda dev: _eng.UNetEngine(self.state_dict(), self.spec(), self.precision, dev))
 
     def _bn_modules(self):
         return [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]

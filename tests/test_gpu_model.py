@@ -325,3 +325,26 @@ def test_ode_sampler_matches_oracle():
     err = rel_l2(got, want.float())
     print(f"ODE sampler ({nfev} RHS evaluations) rel-L2 vs oracle = {err:.3e}")
     assert err < 1e-3
+
+
+def test_two_lane_em_reproduces_one_lane_bitwise(monkeypatch):
+    """SBGM_B200_LANES=2: two half-batches on two streams inside one captured graph; members are independent and the
+    Philox stream is keyed by the global element index, so the ensemble must equal the one-lane result bit for bit."""
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    ck = dict(n_lr=2, geo=True, seasons=True)
+    cfg = config_for(**ck)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16x3", DEV)
+    for shared in (True, False):
+        b = synth_batch(batch=16, size=32, shared_cond=shared, **ck)
+        kw = dict(batch_size=16, num_steps=4, device=DEV, img_size=32, y=_cuda(b.y), cond_img=_cuda(b.cond_img),
+                  lsm_cond=_cuda(b.lsm_cond), topo_cond=_cuda(b.topo_cond))
+        out = []
+        for lanes in ("1", "2", "2"):
+            monkeypatch.setenv("SBGM_B200_LANES", lanes)
+            ss.manual_seed(42)
+            out.append(ss.Euler_Maruyama_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, **kw).cpu())
+        assert torch.equal(out[0], out[1]) and torch.equal(out[1], out[2]), f"shared_cond={shared}"
+    ss.clear_sampler_cache()
