@@ -40,7 +40,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-# Timing ablations only (tools/ablate.py): SBGM_B200_SKIP=attn,attn_core,gn,ln,upsample_math drops the named operator from
+# Timing ablations only (tools/ablate.py): SBGM_B200_SKIP=attn,attn_core,gn,ln,upsample,c64,conv_tc drops the named operator from
 # the launch sequence so that its in-graph cost can be read off as a difference.  Results are garbage when set.
 import os as _os
 _SKIP = frozenset(x for x in _os.environ.get("SBGM_B200_SKIP", "").split(",") if x)
@@ -178,6 +178,11 @@ class Kernels:
             out = Act(self.fmt, x.n, ho, wo, cw.cout, self.device)
             out_ptr, out_plane, pout, pargs = out.ptr, out.plane, None, (None, 0, None)
         stats = None
+        skip_this = ("c64" in _SKIP and self._c64_ok(x, cw, stride, pad)) or ("conv_tc" in _SKIP and not self._c64_ok(x, cw, stride, pad))
+        if skip_this:                      # timing ablation: leave the output uninitialised
+            if proj is not None:
+                return (out, pout) if proj_keep else pout
+            return (out, None) if gn_stats else out
         if self.fmt == FMT_F32:
             call("sbgm_conv2d_simt", x.ptr, cw.w.data_ptr(), _ptr(cw.bias), res_ptr, tp_ptr, tp_stride, out.ptr,
                  x.n, x.h, x.w, cw.cin, cw.cout, cw.kh, cw.kw, stride, pad, act, _stream())
@@ -263,6 +268,8 @@ class Kernels:
 
     def upsample2x(self, x: Act) -> Act:
         out = x.like(h=2 * x.h, w=2 * x.w)
+        if "upsample" in _SKIP:
+            return out
         call("sbgm_upsample2x", x.ptr, x.plane, out.ptr, out.plane, self.fmt, x.n, x.h, x.w, x.c, _stream())
         return out
 

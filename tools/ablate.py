@@ -35,7 +35,7 @@ print("MS_PER_NFE", e0.elapsed_time(e1) / 300)
 def main():
     precision = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
     base = None
-    for skip in ["", "attn", "attn_core", "ln", "gn"]:
+    for skip in ["", "attn", "attn_core", "ln", "gn", "upsample", "c64", "conv_tc", "c64,conv_tc,attn,gn,upsample"]:
         env = dict(os.environ, SBGM_B200_SKIP=skip)
         r = subprocess.run([sys.executable, "-c", CHILD, precision], env=env, capture_output=True, text=True)
         line = [l for l in r.stdout.splitlines() if l.startswith("MS_PER_NFE")]
