@@ -559,3 +559,38 @@ def test_conv_transpose_layer_forward_backward(E, T, prec, shape):
     e_dw, e_db = rel_l2(grads["w"].cpu(), wr.grad), rel_l2(grads["b"].cpu(), br.grad)
     print(f"convT {shape} [{prec}] dx {e_dx:.2e} dW {e_dw:.2e} db {e_db:.2e}")
     assert e_dx < tol and e_dw < tol and e_db < tol
+
+
+def test_gradient_accumulation_and_loss_scaling_in_graph_mode():
+    """Two backward passes without zero_grad accumulate (the captured backward writes into a static flat buffer: param.grad
+    must never alias it), and d(k * loss) = k * d(loss) (the grad_loss scalar reaches the loss-backward kernel)."""
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16x3", DEV).eval()
+    b = synth_batch(batch=2, size=32, n_lr=1)
+
+    def step(scale=1.0):
+        score_sampling.manual_seed(9)
+        loss = loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, cond_img=b.cond_img.to(DEV))
+        (loss * scale).backward()
+
+    for _ in range(3):                      # eager, eager, capture + replay
+        net.zero_grad(set_to_none=True)
+        step()
+    runner = next(iter(net._train_runners.values()))
+    assert runner.g_bwd is not None
+    net.zero_grad(set_to_none=True)
+    step()
+    single = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    step()                                   # accumulates
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            assert torch.allclose(p.grad, 2.0 * single[k], rtol=1e-6, atol=0.0), k
+    net.zero_grad(set_to_none=True)
+    step(scale=4.0)                          # a power of two commutes with every rounding on the path: exact
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, 4.0 * single[k]), k
