@@ -16,24 +16,24 @@ __global__ void attn_unpack_kernel(const void* __restrict__ qkv, size_t qkv_plan
                                    int b, int s, int c, int heads) {
   pdl_grid_sync();
   const int d = c / heads, dvec = d >> 3, cvec = c >> 3;
-  const size_t total = static_cast<size_t>(b) * s * cvec;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(b) * s * cvec;          // 32-bit divisions only
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int vec = static_cast<int>(i % cvec);
-    const size_t tok = i / cvec;
+    const uint32_t tok = i / cvec;
     const int head = vec / dvec, dv = vec - head * dvec;
-    const size_t bi = tok / s, si = tok - bi * s;
+    const size_t bi = tok / static_cast<uint32_t>(s), si = tok - bi * s;
     const size_t dst = ((bi * heads + head) * s + si) * d + dv * 8;
     float t[8];
-    Act<FMT>::load8(qkv, qkv_plane, tok * 3 * c + vec * 8, t);
+    Act<FMT>::load8(qkv, qkv_plane, static_cast<size_t>(tok) * 3 * c + vec * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) q[dst + j] = t[j];
-    Act<FMT>::load8(qkv, qkv_plane, tok * 3 * c + c + vec * 8, t);
+    Act<FMT>::load8(qkv, qkv_plane, static_cast<size_t>(tok) * 3 * c + c + vec * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) k[dst + j] = t[j];
-    Act<FMT>::load8(qkv, qkv_plane, tok * 3 * c + 2 * c + vec * 8, t);
+    Act<FMT>::load8(qkv, qkv_plane, static_cast<size_t>(tok) * 3 * c + 2 * c + vec * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[dst + j] = t[j];
-    Act<FMT>::load8(dout, dout_plane, tok * c + vec * 8, t);
+    Act<FMT>::load8(dout, dout_plane, static_cast<size_t>(tok) * c + vec * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) go[dst + j] = t[j];
   }
@@ -44,23 +44,23 @@ __global__ void attn_pack_kernel(const float* __restrict__ dq, const float* __re
                                  void* __restrict__ dqkv, size_t plane, int b, int s, int c, int heads) {
   pdl_grid_sync();
   const int d = c / heads, dvec = d >> 3, cvec = c >> 3;
-  const size_t total = static_cast<size_t>(b) * s * cvec;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(b) * s * cvec;          // 32-bit divisions only
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int vec = static_cast<int>(i % cvec);
-    const size_t tok = i / cvec;
+    const uint32_t tok = i / cvec;
     const int head = vec / dvec, dvi = vec - head * dvec;
-    const size_t bi = tok / s, si = tok - bi * s;
+    const size_t bi = tok / static_cast<uint32_t>(s), si = tok - bi * s;
     const size_t src = ((bi * heads + head) * s + si) * d + dvi * 8;
     float t[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = dq[src + j];
-    Act<FMT>::store8(dqkv, plane, tok * 3 * c + vec * 8, t);
+    Act<FMT>::store8(dqkv, plane, static_cast<size_t>(tok) * 3 * c + vec * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = dk[src + j];
-    Act<FMT>::store8(dqkv, plane, tok * 3 * c + c + vec * 8, t);
+    Act<FMT>::store8(dqkv, plane, static_cast<size_t>(tok) * 3 * c + c + vec * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = dv[src + j];
-    Act<FMT>::store8(dqkv, plane, tok * 3 * c + 2 * c + vec * 8, t);
+    Act<FMT>::store8(dqkv, plane, static_cast<size_t>(tok) * 3 * c + 2 * c + vec * 8, t);
   }
 }
 

@@ -506,11 +506,11 @@ template <int FMT>
 __global__ void upsample2x_bwd_kernel(const void* __restrict__ dy, size_t dy_plane, void* __restrict__ dx, size_t dx_plane,
                                       int n, int h, int w, int c) {
   pdl_grid_sync();
-  const int vecs = c >> 3;
-  const size_t total = static_cast<size_t>(n) * h * w * vecs;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t vecs = c >> 3;
+  const uint32_t total = static_cast<uint32_t>(n) * h * w * vecs;     // < 2^32 (host-checked): 32-bit divisions only
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int vec = static_cast<int>(i % vecs);
-    size_t r = i / vecs;
+    uint32_t r = i / vecs;
     const int ix = static_cast<int>(r % w);
     r /= w;
     const int iy = static_cast<int>(r % h);
@@ -533,7 +533,7 @@ __global__ void upsample2x_bwd_kernel(const void* __restrict__ dy, size_t dy_pla
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
       }
     }
-    Act<FMT>::store8(dx, dx_plane, i * 8, acc);
+    Act<FMT>::store8(dx, dx_plane, static_cast<size_t>(i) * 8, acc);
   }
 }
 
@@ -769,6 +769,7 @@ int sbgm_upsample2x_backward(const void* dy, size_t dy_plane, void* dx, size_t d
                              void* stream) {
   SBGM_REQUIRE(c % 8 == 0, "upsample2x_backward: c=%d must be a multiple of 8", c);
   const size_t total = static_cast<size_t>(n) * h * w * (c / 8);
+  SBGM_REQUIRE(total < (1ull << 32), "upsample2x_backward: tensor too large for 32-bit indexing");
   SBGM_DISPATCH_FMT(fmt, (launch_k((upsample2x_bwd_kernel<FMT>), bgrid_for(total, 256), 256, 0, as_stream(stream), dy, dy_plane, dx, dx_plane, n, h, w, c)));
   return check_launch("upsample2x_backward");
 }

@@ -270,11 +270,11 @@ final_conv_bwd_weight_kernel(const float* __restrict__ dscore, const float* __re
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.0f;
   float bsum = 0.0f;
   if (lane < lanes) {
-    for (size_t p = static_cast<size_t>(blockIdx.x) * lanes + lane; p < npix; p += static_cast<size_t>(gridDim.x) * lanes) {
-      const int x = static_cast<int>(p % w), y = static_cast<int>((p / w) % h), b = static_cast<int>(p / (static_cast<size_t>(w) * h));
+    for (uint32_t p = blockIdx.x * lanes + lane; p < static_cast<uint32_t>(npix); p += gridDim.x * lanes) {    // 32-bit divisions
+      const int x = static_cast<int>(p % w), y = static_cast<int>((p / w) % h), b = static_cast<int>(p / (static_cast<uint32_t>(w) * h));
       const float sc = inv_std ? inv_std[b] : 1.0f;
       float v[8];
-      Act<FMT>::load8(a, a_plane, p * cin + vec * 8, v);
+      Act<FMT>::load8(a, a_plane, static_cast<size_t>(p) * cin + vec * 8, v);
       // a[p] is the input of output pixel (y - r + 1, x - s + 1) under tap (r, s)
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
