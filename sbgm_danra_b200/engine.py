@@ -15,7 +15,6 @@ Precisions
 """
 from __future__ import annotations
 
-import ctypes
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 

@@ -19,12 +19,10 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, FMT_BF16, FMT_BF16X2, FMT_F32, call
-from .engine import (ACTS, BN_EPS, GN_EPS, LN_EPS, PRECISIONS, Act, ConvW, Kernels, UNetSpec, _Packer, _ptr, _split_bf16,
-                     _stream)
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, FMT_BF16X2, FMT_F32, call
+from .engine import ACTS, BN_EPS, GN_EPS, LN_EPS, PRECISIONS, Act, ConvW, Kernels, UNetSpec, _ptr, _stream
 
 BN_MOMENTUM = 0.1
-NORM_CHUNKS = 32
 
 
 def _pack_oihw(w: torch.Tensor, fmt: int) -> torch.Tensor:
@@ -173,7 +171,6 @@ class Tape:
         self.steps: List[Callable[[], None]] = []
         self.grads: Dict[int, Act] = {}
         self.keep: List[object] = []
-        self.pgrads: Dict[str, torch.Tensor] = {}
 
     def record(self, fn: Callable[[], None], *keep) -> None:
         self.steps.append(fn)
