@@ -223,6 +223,18 @@ __global__ void ensemble_stats_kernel(const float* __restrict__ members, const f
   }
 }
 
+// ---- back-transforms of sampled fields: y = a * x + b, optionally clamp to [lo, hi], optionally exp ----------------
+// (ZScoreBackTransform / ScaleBackTransform / PrcpLogBackTransform of sbgm/special_transforms.py:103-138, 187-237, 360-462)
+__global__ void back_transform_kernel(const float* __restrict__ x, float* __restrict__ y, size_t count, float a, float b, float lo,
+                                      float hi, int do_clamp, int do_exp) {
+  pdl_grid_sync();
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float v = __fadd_rn(__fmul_rn(x[i], a), b);     // unfused: the reference (torch) rounds the product before the sum
+    if (do_clamp) v = fminf(fmaxf(v, lo), hi);
+    y[i] = do_exp ? expf(v) : v;
+  }
+}
+
 }  // namespace sbgm
 
 using namespace sbgm;
@@ -298,6 +310,12 @@ int sbgm_ensemble_stats(const float* members, const float* truth, int m, size_t 
   SBGM_REQUIRE(crps == nullptr || truth != nullptr, "ensemble_stats: CRPS needs the verifying field");
   launch_k((ensemble_stats_kernel), grid_for(pixels), kBlock, 0, as_stream(stream), members, truth, m, pixels, mean, stdev, crps);
   return check_launch("ensemble_stats");
+}
+
+int sbgm_back_transform(const float* x, float* y, size_t count, float scale, float shift, float lo, float hi, int do_clamp,
+                        int do_exp, void* stream) {
+  launch_k((back_transform_kernel), grid_for(count), kBlock, 0, as_stream(stream), x, y, count, scale, shift, lo, hi, do_clamp, do_exp);
+  return check_launch("back_transform");
 }
 
 }  // extern "C"

@@ -380,3 +380,30 @@ def test_full_size_ensemble_properties():
     ss.manual_seed(2)
     assert not torch.equal(run(64, _cuda(b.cond_img)), full)
     ss.clear_sampler_cache()
+
+
+def test_back_transforms_match_reference_golden():
+    """special_transforms mirror classes (one fused affine/clamp/exp kernel) against the reference's own outputs."""
+    from oracle import transforms_ref as tr
+    from sbgm_danra_b200 import special_transforms as st
+    gold = np.load(os.path.join(GOLDEN_DIR, "transforms_golden.npz"))
+    x = torch.from_numpy(gold["x"]).to(DEV)
+    for name, (kind, kw) in tr.CASES.items():
+        if kind == "zscore":
+            t = st.ZScoreBackTransform(kw["mean"], kw["std"])
+        elif kind == "scale":
+            t = st.ScaleBackTransform(kw["in_low"], kw["in_high"], kw["data_min"], kw["data_max"])
+        else:
+            t = st.PrcpLogBackTransform(**kw)
+        got = t(x).cpu().numpy()
+        want = gold[name]
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isinf(want), np.isinf(got)), name
+        assert np.allclose(got[fin], want[fin], rtol=2e-5, atol=1e-6), name
+    with pytest.raises(ValueError):
+        st.PrcpLogBackTransform(scale_type="log_zscore")
+    with pytest.raises(RuntimeError):
+        st.ZScoreBackTransform(0.0, 1.0)(torch.zeros(4))          # CPU tensor: no CPU path
+    bt = st.build_back_transforms("temp", "zscore", dict(glob_mean=8.69, glob_std=6.19), ["prcp"], ["log_zscore"],
+                                  [dict(glob_mean_log=-3.0, glob_std_log=3.6, glob_min_log=None, glob_max_log=None, buffer_frac=0.5)])
+    assert set(bt) == {"temp_hr", "generated", "prcp_lr"}
