@@ -222,10 +222,10 @@ int sbgm_cfg_combine(const float* s_cond, const float* s_uncond, float scale, fl
 int sbgm_select_step_row(const float* table, int cols, const int32_t* step_counter, float* out, void* stream);
 
 /* ---- back-transforms of sampled fields to physical units (the step after the sampler) ------------
- * y = exp?(clamp?(scale * x + shift, lo, hi)): ZScoreBackTransform (sbgm/special_transforms.py:187-237), ScaleBackTransform
- * (:103-138) and every mode of PrcpLogBackTransform (:360-462) are instances. x and y may alias. */
-int sbgm_back_transform(const float* x, float* y, size_t count, float scale, float shift, float lo, float hi, int do_clamp,
-                        int do_exp, void* stream);
+ * y = exp?(clamp?(scale * (x + pre_shift) + shift, lo, hi)): ZScoreBackTransform (sbgm/special_transforms.py:187-237),
+ * ScaleBackTransform (:103-138) and every mode of PrcpLogBackTransform (:360-462) are instances. x and y may alias. */
+int sbgm_back_transform(const float* x, float* y, size_t count, float pre_shift, float scale, float shift, float lo, float hi,
+                        int do_clamp, int do_exp, void* stream);
 
 /* ---- ensemble statistics (BASELINE.json parity criterion; evaluation itself is sbgm/evaluate_sbgm/, out of scope) ----
  * members[m][pixels] fp32 -> per-pixel mean, std (Bessel-corrected), and, given truth[pixels], the ensemble CRPS

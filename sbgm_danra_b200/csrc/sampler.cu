@@ -223,13 +223,13 @@ __global__ void ensemble_stats_kernel(const float* __restrict__ members, const f
   }
 }
 
-// ---- back-transforms of sampled fields: y = a * x + b, optionally clamp to [lo, hi], optionally exp ----------------
+// ---- back-transforms of sampled fields: y = a * (x + pre) + b, optionally clamp to [lo, hi], optionally exp --------
 // (ZScoreBackTransform / ScaleBackTransform / PrcpLogBackTransform of sbgm/special_transforms.py:103-138, 187-237, 360-462)
-__global__ void back_transform_kernel(const float* __restrict__ x, float* __restrict__ y, size_t count, float a, float b, float lo,
+__global__ void back_transform_kernel(const float* __restrict__ x, float* __restrict__ y, size_t count, float pre, float a, float b, float lo,
                                       float hi, int do_clamp, int do_exp) {
   pdl_grid_sync();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float v = __fadd_rn(__fmul_rn(x[i], a), b);     // unfused: the reference (torch) rounds the product before the sum
+    float v = __fadd_rn(__fmul_rn(__fadd_rn(x[i], pre), a), b);     // unfused: the reference (torch) rounds the product before the sum
     if (do_clamp) v = fminf(fmaxf(v, lo), hi);
     y[i] = do_exp ? expf(v) : v;
   }
@@ -312,9 +312,9 @@ int sbgm_ensemble_stats(const float* members, const float* truth, int m, size_t 
   return check_launch("ensemble_stats");
 }
 
-int sbgm_back_transform(const float* x, float* y, size_t count, float scale, float shift, float lo, float hi, int do_clamp,
-                        int do_exp, void* stream) {
-  launch_k((back_transform_kernel), grid_for(count), kBlock, 0, as_stream(stream), x, y, count, scale, shift, lo, hi, do_clamp, do_exp);
+int sbgm_back_transform(const float* x, float* y, size_t count, float pre_shift, float scale, float shift, float lo, float hi,
+                        int do_clamp, int do_exp, void* stream) {
+  launch_k((back_transform_kernel), grid_for(count), kBlock, 0, as_stream(stream), x, y, count, pre_shift, scale, shift, lo, hi, do_clamp, do_exp);
   return check_launch("back_transform");
 }
 

@@ -18,7 +18,7 @@ logger = logging.getLogger(__name__)
 _INF = float("inf")
 
 
-def _apply(sample, scale: float, shift: float, lo: float = -_INF, hi: float = _INF, exp: bool = False) -> torch.Tensor:
+def _apply(sample, scale: float, shift: float, lo: float = -_INF, hi: float = _INF, exp: bool = False, pre: float = 0.0) -> torch.Tensor:
     if not isinstance(sample, torch.Tensor):
         raise RuntimeError("back-transforms take CUDA tensors (the sampler's output); there is no CPU path")
     if not sample.is_cuda:
@@ -28,8 +28,8 @@ def _apply(sample, scale: float, shift: float, lo: float = -_INF, hi: float = _I
     clamp = not (lo == -_INF and hi == _INF)
     f32 = lambda v: max(min(float(v), 3.4028234663852886e38), -3.4028234663852886e38)
     with torch.cuda.device(x.device):
-        call("sbgm_back_transform", x.data_ptr(), out.data_ptr(), x.numel(), float(scale), float(shift), f32(lo), f32(hi), int(clamp),
-             int(exp), _stream())
+        call("sbgm_back_transform", x.data_ptr(), out.data_ptr(), x.numel(), float(pre), float(scale), float(shift), f32(lo), f32(hi),
+             int(clamp), int(exp), _stream())
     return out
 
 
@@ -61,9 +61,7 @@ class ScaleBackTransform(object):
 
     def __call__(self, sample):
         old, new = self.in_high - self.in_low, self.data_max_in - self.data_min_in
-        if self.in_low == 0:
-            return _apply(sample, new / old, self.data_min_in)
-        return _apply(sample, new / old, self.data_min_in - self.in_low * new / old)
+        return _apply(sample, new / old, self.data_min_in, pre=-self.in_low)
 
 
 class PrcpLogBackTransform(object):
@@ -97,8 +95,7 @@ class PrcpLogBackTransform(object):
             return _apply(sample, _scalar(self.glob_std_log, "glob_std_log") + 1e-8, _scalar(self.glob_mean_log, "glob_mean_log"),
                           self.lo, self.hi, exp=True)
         if self.scale_type == "log_minus1_1":
-            half = 0.5 * (self.glob_max_log - self.glob_min_log)
-            return _apply(sample, half, half + self.glob_min_log, self.lo, self.hi, exp=True)
+            return _apply(sample, 0.5 * (self.glob_max_log - self.glob_min_log), self.glob_min_log, self.lo, self.hi, exp=True, pre=1.0)
         return _apply(sample, 1.0, 0.0, self.lo, self.hi, exp=True)
 
 
