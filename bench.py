@@ -169,14 +169,16 @@ def time_dominant_kernel(net, precision: str, iters: int = 20):
     x = E.Act(eng.fmt, MEMBERS, SIZE, SIZE, 64, eng.device)
     x.buf.normal_()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+    # exactly the launch the sampler step makes: the persistent 64->64 kernel with the projection epilogue (tensor-core formats)
+    proj = eng.dec.final_w[0] if (precision != "fp32" and eng.dec.out_channels == 1) else None
     for _ in range(3):
-        k.conv(x, cw, pad=1)
+        k.conv(x, cw, pad=1, proj=proj)
     times = []
     for _ in range(iters):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        k.conv(x, cw, pad=1)
+        k.conv(x, cw, pad=1, proj=proj)
         b.record()
         b.synchronize()
         times.append(a.elapsed_time(b))
@@ -269,7 +271,7 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops"], "traffic": load_traffic(),
-                     "kernel": "conv_tc_kernel (tcgen05 implicit GEMM) on decoder.final_layer.conv_up 64->64 3x3 @128x128 x64",
+                     "kernel": "conv3x3_c64_kernel (persistent tcgen05 implicit GEMM, projection epilogue) on decoder.final_layer.conv_up 64->64 3x3 @128x128 x64",
                      "kernel_ms": kms, "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", burst bf16",
                      "tensor_pipe_frac": (3.0 if args.precision == "bf16x3" else 1.0) * achieved / peaks["bf16_tflops"],
                      "note": "achieved/frac count ALGORITHMIC FLOPs; bf16x3 issues 3 bf16 tensor-core products per algorithmic "
