@@ -594,3 +594,34 @@ def test_gradient_accumulation_and_loss_scaling_in_graph_mode():
     for k, p in net.named_parameters():
         if p.grad is not None:
             assert torch.equal(p.grad, 4.0 * single[k]), k
+
+
+def test_training_step_on_ragged_maps_96x96():
+    """96x96 input: feature maps 48 / 24 / 12 / 6 / 3 -- pixel tiles with tails in the tensor-core weight gradient, odd sizes in
+    the parity-sliced data gradients of the strided convolutions, attention over 36 and 9 tokens.  Eval-mode BatchNorm keeps the
+    comparison well conditioned (see test_transpose_decoder_trains)."""
+    from oracle import philox_ref, score_ref
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    sd = synth_state_dict(cfg)
+    b = synth_batch(batch=2, size=96, n_lr=1)
+    net = build_model(cfg, sd, "bf16x3", DEV).eval()
+    score_sampling.manual_seed(17)
+    loss = loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, cond_img=b.cond_img.to(DEV), sdf_cond=b.sdf_cond.to(DEV))
+    loss.backward()
+    sdo = {k: (v.clone().requires_grad_() if v.is_floating_point() and not k.endswith(("running_mean", "running_var", ".W")) else v.clone())
+           for k, v in sd.items()}
+    u = torch.from_numpy(philox_ref.uniform(2, 17, philox_ref.DRAW_DSM_T))
+    z = torch.from_numpy(philox_ref.normal(b.x.numel(), 17, philox_ref.DRAW_DSM_Z)).reshape(b.x.shape)
+    lo = score_ref.dsm_loss(sdo, cfg, b.x, u * (1.0 - 1e-3) + 1e-3, z, None, b.cond_img, None, None, b.sdf_cond, bn_train=False)
+    lo.backward()
+    params = dict(net.named_parameters())
+    used = [k for k, v in sdo.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None]
+    whole = rel_l2(torch.cat([params[k].grad.cpu().reshape(-1) for k in used]), torch.cat([sdo[k].grad.reshape(-1) for k in used]))
+    worst = max((rel_l2(params[k].grad.cpu(), sdo[k].grad), k) for k in used)
+    print(f"96x96 training step: loss {loss.item():.4f} vs {lo.item():.4f}; whole-gradient rel-L2 {whole:.2e}; worst {worst}")
+    assert abs(loss.item() - lo.item()) / abs(lo.item()) < 1e-3
+    assert whole < 1e-3 and worst[0] < 5e-3
