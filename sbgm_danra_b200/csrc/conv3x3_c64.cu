@@ -6,10 +6,15 @@
 // tap: 24 KB per 128 MMA-cycles, 4x more than the L2->SM path sustains.  Here
 //   * one CTA per SM stays resident and walks tiles blockIdx.x, +gridDim.x, ...;
 //   * the 9 x 64 x 64 weights (72 KB bf16, 144 KB split-bf16) are loaded ONCE per CTA and stay in smem;
-//   * a tile is 8 rows x 16 columns of one image; its input arrives as three halo slabs
-//     (one per horizontal tap offset s): box = 64 ch x 16 w x 10 h at (w0+s-1, h0-1), zero-filled outside
-//     the image.  Tap (r, s) reads slab s at byte offset r * 16 * 128 -- 1024-aligned, so the UMMA
-//     descriptor needs no base offset -- i.e. 3 x 20 KB serve nine taps;
+//   * a tile is 16 rows x 8 columns of one image and its input arrives ONCE, as a halo slab of 18 x 10 pixels
+//     (zero-filled outside the image) in two 32-channel halves: box = 32 ch x 10 w x 18 h at (w0-1, h0-1), 64-byte
+//     pixel rows with the 64-byte swizzle.  Tap (r, s) is the same slab read from pixel (r, s) on: the K-major A
+//     descriptor starts at byte (r * 10 + s) * 64 and steps one slab row (640 B) per 8-row group (= one output
+//     row).  Neither is a multiple of the 512-byte swizzle atom; the tensor core applies the swizzle to absolute
+//     shared-memory address bits (probed on B200: odd 64-byte starts give bit-identical results, the descriptor's
+//     base-offset field is ignored), so any 16-byte-aligned start / stride addresses what TMA wrote.
+//     11.25 KB per plane and half, 46 KB per tile in split-bf16 instead of 120 KB for three column-shifted slabs:
+//     the earlier three-slab version was bound by the L2->SM path (ncu: MMA warp on the "full" barrier 40 %);
 //   * two TMEM accumulators (2 x 64 columns) ping-pong between MMA issue and the epilogue warps.
 // Warp roles (320 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..5 = epilogue group 0 (even tiles,
 // accumulator 0), 6..9 = epilogue group 1 (odd tiles, accumulator 1).  ncu showed the kernel epilogue-bound: one
@@ -19,8 +24,12 @@
 
 namespace sbgm {
 
-constexpr int kTH = 8, kTW = 16;                       // output tile (rows x cols) = 128 pixels
-constexpr uint32_t kSlabBytes = (kTH + 2) * kTW * 128;  // 20480 per plane
+constexpr int kTH = 16, kTW = 8;                        // output tile (rows x cols) = 128 pixels
+constexpr int kSlabW = kTW + 2, kSlabH = kTH + 2;       // halo slab: 10 x 18 pixels
+constexpr uint32_t kSlabTxBytes = kSlabH * kSlabW * 64; // 11520 per plane: one 32-channel half of the halo slab
+constexpr uint32_t kSlabBytes = 12288;                  // plane pitch in smem (1024-aligned)
+// K-major SWIZZLE_64B A operand whose 8-row groups are one slab row (10 pixels x 64 B) apart
+constexpr uint32_t kDescHiSlab = ((kSlabW * 64u) >> 4) | (1u << 14) | (4u << 29);
 constexpr uint32_t kWTapBytes = 64 * 128;               // 8192 per (tap, plane)
 
 struct C64Params {
@@ -36,7 +45,7 @@ struct C64Cfg {
   static constexpr uint32_t kWeightBytes = 9 * kSplit * kWTapBytes;
   static constexpr uint32_t kStageBytes = kSplit * kSlabBytes;
   static constexpr uint32_t kBarOffset = kWeightBytes + kStages * kStageBytes;
-  static constexpr uint32_t kSmemBytes = kBarOffset + 128 + 1024;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;
 };
 
 template <int FMT, int kStages, int ACT, int PROJ>
@@ -90,14 +99,14 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       uint32_t sidx = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
-        for (int s = 0; s < 3; ++s, ++sidx) {
+        for (int half = 0; half < 2; ++half, ++sidx) {   // unit = one 32-channel half of the tile's halo slab
           const int stage = sidx % kStages;
           const uint32_t phase = (sidx / kStages) & 1u;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          mbar_expect_tx(full_bar(stage), kSplit * kSlabTxBytes);
           for (int pl = 0; pl < kSplit; ++pl)
-            tma_load_5d(slab_base + stage * Cfg::kStageBytes + pl * kSlabBytes, &tmap_a, full_bar(stage), 0,
-                        tw * kTW + s - 1, th * kTH - 1, n, pl);
+            tma_load_5d(slab_base + stage * Cfg::kStageBytes + pl * kSlabBytes, &tmap_a, full_bar(stage), half * 32,
+                        tw * kTW - 1, th * kTH - 1, n, pl);
         }
       }
     }
@@ -113,7 +122,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * kAccCols;
 #pragma unroll
-      for (int s = 0; s < 3; ++s, ++sidx) {
+      for (int half = 0; half < 2; ++half, ++sidx) {
         const uint32_t stage = sidx % kStages;
         const uint32_t phase = (sidx / kStages) & 1u;
         mbar_wait(full_bar(stage), phase);
@@ -122,16 +131,21 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t a_hi = a_slab + ((r * (kTW * 128) + k * 32) >> 4);
-            const uint32_t b_hi = w_lo + ((((r * 3 + s) * kSplit) * kWTapBytes + k * 32) >> 4);
-            if (kSplit == 2) {
-              // hi|lo weight planes of a tap are adjacent in smem: one N = 128 MMA gives x_hi*w_hi (cols 0..63)
-              // and x_hi*w_lo (cols 64..127); x_lo*w_hi accumulates into cols 0..63.  The epilogue adds the halves.
-              umma_bf16_elect(tmem_d, a_hi, b_hi, idesc2, (s | r | k) != 0);
-              umma_bf16_elect(tmem_d, a_hi + (kSlabBytes >> 4), b_hi, idesc, 1u);
-            } else {
-              umma_bf16_elect(tmem_d, a_hi, b_hi, idesc, (s | r | k) != 0);
+          for (int s = 0; s < 3; ++s) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {            // two K = 16 steps per 32-channel half
+              // tap (r, s): the 128 A rows start at slab pixel (r, s); row groups (output rows) are one slab row apart
+              const uint32_t a_hi = a_slab + (((r * kSlabW + s) * 64 + k * 32) >> 4);
+              const uint32_t b_hi = w_lo + ((((r * 3 + s) * kSplit) * kWTapBytes + (half * 2 + k) * 32) >> 4);
+              const uint32_t acc_flag = (half | r | s | k) != 0;
+              if (kSplit == 2) {
+                // hi|lo weight planes of a tap are adjacent in smem: one N = 128 MMA gives x_hi*w_hi (cols 0..63)
+                // and x_hi*w_lo (cols 64..127); x_lo*w_hi accumulates into cols 0..63.  The epilogue adds the halves.
+                umma_bf16_elect_hi(tmem_d, a_hi, kDescHiSlab, b_hi, idesc2, acc_flag);
+                umma_bf16_elect_hi(tmem_d, a_hi + (kSlabBytes >> 4), kDescHiSlab, b_hi, idesc, 1u);
+              } else {
+                umma_bf16_elect_hi(tmem_d, a_hi, kDescHiSlab, b_hi, idesc, acc_flag);
+              }
             }
           }
         }
@@ -248,9 +262,9 @@ extern "C" int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* wei
   p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
   p.gn_partials = gn_partials;
   CUtensorMap ta, tb;
-  if (encode_act_map(&ta, in, planes, in_plane, n, h, w, 64, kTW, kTH + 2, 1, 1)) return 1;
+  if (encode_act_map(&ta, in, planes, in_plane, n, h, w, 64, kSlabW, kSlabH, 1, 1, /*box_c=*/32)) return 1;
   if (encode_weight_map(&tb, weight, planes, w_plane, 64, 9 * 64, 64)) return 1;
   cudaStream_t st = as_stream(stream);
-  if (fmt == SBGM_FMT_BF16) return launch_c64<SBGM_FMT_BF16, 4>(ta, tb, p, st);
-  return launch_c64<SBGM_FMT_BF16X2, 2>(ta, tb, p, st);
+  if (fmt == SBGM_FMT_BF16) return launch_c64<SBGM_FMT_BF16, 8>(ta, tb, p, st);
+  return launch_c64<SBGM_FMT_BF16X2, 3>(ta, tb, p, st);
 }

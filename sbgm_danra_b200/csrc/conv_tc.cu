@@ -278,17 +278,18 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int encode_act_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int n, int h, int w, int c,
-                   int box_w, int box_h, int box_n, int stride) {
+                   int box_w, int box_h, int box_n, int stride, int box_c) {
   EncodeTiledFn encode = get_encode_fn();
   SBGM_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
   const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, (cuuint64_t)planes};
   const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
                                  planes == 2 ? (cuuint64_t)plane_elems * 2 : (cuuint64_t)n * h * w * c * 2};
-  const cuuint32_t box[5] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), (cuuint32_t)box_n, 1};
+  SBGM_REQUIRE(box_c == 64 || box_c == 32, "encode_act_map: box_c must be 64 or 32");
+  const cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), (cuuint32_t)box_n, 1};
   const cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SBGM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
   return 0;
 }

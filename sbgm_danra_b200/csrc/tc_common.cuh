@@ -87,6 +87,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // SWIZZLE_128B).  Advancing an operand by `bytes` is a plain add of bytes >> 4 to the low word.
 constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+// Same issue path with an explicit high word for A: K-major SWIZZLE_64B tiles (64-byte rows, 8-row atom = 512 B:
+// SBO = 512 >> 4 = 32, version 1, layout type 4) next to a SWIZZLE_128B B operand.
+constexpr uint32_t kDescHiSw64 = 32u | (1u << 14) | (4u << 29);
+__device__ __forceinline__ void umma_bf16_elect_hi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi), "r"(a_hi)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
@@ -358,7 +373,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_fn();
 // NHWC activation [planes][n][h][w][c] bf16 as a 5-D map, box = (64, bw, bh, bn, 1), element strides (1, s, s, 1, 1)
 int encode_act_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int n, int h, int w, int c,
-                   int box_w, int box_h, int box_n, int stride);
+                   int box_w, int box_h, int box_n, int stride, int box_c = 64);   // box_c = 32: 64-byte rows, SWIZZLE_64B
 // NHWC output [planes][n][h][w][c] bf16 as a 5-D map whose box is a warp's 32-row share of a (box_w, box_h, box_n) tile
 int encode_out_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int n, int h, int w, int c,
                    int tile_w, int tile_h, int tile_n);

@@ -149,7 +149,7 @@ class Kernels:
 
     def _c64_ok(self, x: Act, cw: ConvW, stride: int, pad: int) -> bool:
         return (self.fmt != FMT_F32 and cw.cin == 64 and cw.cout == 64 and cw.kh == 3 and cw.kw == 3 and stride == 1
-                and pad == 1 and x.h % 8 == 0 and x.w % 16 == 0)
+                and pad == 1 and x.h % 16 == 0 and x.w % 8 == 0)
 
     def conv(self, x: Act, cw: ConvW, stride: int = 1, pad: int = 0, act: int = ACT_NONE,
              residual: Optional[Act] = None, tproj: Optional[torch.Tensor] = None,
@@ -188,7 +188,7 @@ class Kernels:
         elif self._c64_ok(x, cw, stride, pad):
             part = None
             if gn_stats and residual is None and tproj is None and act == ACT_NONE and proj is None:
-                chunks = (x.h // 8) * (x.w // 16) * 4
+                chunks = (x.h // 16) * (x.w // 8) * 4
                 part = torch.empty((x.n, chunks, 8, 2), dtype=torch.float32, device=self.device)
                 stats = (part, chunks)
             call("sbgm_conv3x3_c64", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias), res_ptr, res_plane,
