@@ -111,47 +111,50 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // whole warp, uniform control flow; one elected lane issues each tcgen05 instruction
-    constexpr uint32_t idesc = make_idesc(64), idesc2 = make_idesc(128);
-    mbar_wait(w_bar, 0);
-    const uint32_t w_lo = desc_lo(w_base), slab_lo0 = desc_lo(slab_base);
-    uint32_t sidx = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1u, use = it >> 1;
-      mbar_wait(acc_empty(acc), (use & 1u) ^ 1u);
-      tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * kAccCols;
-#pragma unroll
-      for (int half = 0; half < 2; ++half, ++sidx) {
-        const uint32_t stage = sidx % kStages;
-        const uint32_t phase = (sidx / kStages) & 1u;
-        mbar_wait(full_bar(stage), phase);
+    // one elected lane runs the whole issue loop: ncu showed the warp-uniform variant (election + predicate vote +
+    // descriptor moves to uniform registers for every MMA, ~13.5 instructions each) issue-bound, not data-bound
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(64), idesc2 = make_idesc(128);
+      mbar_wait(w_bar, 0);
+      const uint64_t w_desc = (static_cast<uint64_t>(kDescHi) << 32) | desc_lo(w_base);
+      const uint64_t a_desc0 = (static_cast<uint64_t>(kDescHiSlab) << 32) | desc_lo(slab_base);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, use = it >> 1;
+        mbar_wait(acc_empty(acc), (use & 1u) ^ 1u);
         tcgen05_fence_after();
-        const uint32_t a_slab = slab_lo0 + stage * (Cfg::kStageBytes >> 4);
+        const uint32_t tmem_d = tmem_base + acc * kAccCols;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t a_unit = a_desc0 + stage * (Cfg::kStageBytes >> 4);
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
+          for (int r = 0; r < 3; ++r) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {            // two K = 16 steps per 32-channel half
-              // tap (r, s): the 128 A rows start at slab pixel (r, s); row groups (output rows) are one slab row apart
-              const uint32_t a_hi = a_slab + (((r * kSlabW + s) * 64 + k * 32) >> 4);
-              const uint32_t b_hi = w_lo + ((((r * 3 + s) * kSplit) * kWTapBytes + (half * 2 + k) * 32) >> 4);
-              const uint32_t acc_flag = (half | r | s | k) != 0;
-              if (kSplit == 2) {
-                // hi|lo weight planes of a tap are adjacent in smem: one N = 128 MMA gives x_hi*w_hi (cols 0..63)
-                // and x_hi*w_lo (cols 64..127); x_lo*w_hi accumulates into cols 0..63.  The epilogue adds the halves.
-                umma_bf16_elect_hi(tmem_d, a_hi, kDescHiSlab, b_hi, idesc2, acc_flag);
-                umma_bf16_elect_hi(tmem_d, a_hi + (kSlabBytes >> 4), kDescHiSlab, b_hi, idesc, 1u);
-              } else {
-                umma_bf16_elect_hi(tmem_d, a_hi, kDescHiSlab, b_hi, idesc, acc_flag);
+            for (int s = 0; s < 3; ++s) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {            // two K = 16 steps per 32-channel half
+                // tap (r, s): the 128 A rows start at slab pixel (r, s); row groups (output rows) are one slab row apart
+                const uint64_t a_d = a_unit + (((r * kSlabW + s) * 64 + k * 32) >> 4);
+                const uint64_t b_d = w_desc + ((((r * 3 + s) * kSplit) * kWTapBytes + (half * 2 + k) * 32) >> 4);
+                const bool first = (half | r | s | k) == 0;
+                if (kSplit == 2) {
+                  // hi|lo weight planes of a tap are adjacent in smem: one N = 128 MMA gives x_hi*w_hi (cols 0..63)
+                  // and x_hi*w_lo (cols 64..127); x_lo*w_hi accumulates into cols 0..63.  The epilogue adds the halves.
+                  if (first) umma_bf16_first(tmem_d, a_d, b_d, idesc2); else umma_bf16_acc(tmem_d, a_d, b_d, idesc2);
+                  umma_bf16_acc(tmem_d, a_d + (kSlabBytes >> 4), b_d, idesc);
+                } else {
+                  if (first) umma_bf16_first(tmem_d, a_d, b_d, idesc); else umma_bf16_acc(tmem_d, a_d, b_d, idesc);
+                }
               }
             }
           }
+          umma_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_elect(empty_bar(stage));
+        umma_commit(acc_full(acc));
       }
-      umma_commit_elect(acc_full(acc));
     }
     __syncwarp();
   } else {
