@@ -121,29 +121,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // whole warp, uniform control flow; one elected lane issues each tcgen05 instruction
-    constexpr uint32_t idesc = make_idesc(BLOCK_N), idesc2 = make_idesc(kSplit * BLOCK_N);
-    const uint32_t base_lo = desc_lo(smem_base);
-    uint32_t stage = 0, phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(full_bar(stage), phase);
-      tcgen05_fence_after();
-      const uint32_t a0 = base_lo + stage * (Cfg::kStageBytes >> 4);
-      const uint32_t b0 = a0 + ((kSplit * Cfg::kABytes) >> 4);
+    // one elected lane runs the whole issue loop (64-bit descriptors, ~3 instructions per MMA; the earlier
+    // warp-uniform variant paid an election, a predicate vote and four register->uniform moves per MMA)
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N), idesc2 = make_idesc(kSplit * BLOCK_N);
+      const uint64_t base = (static_cast<uint64_t>(kDescHi) << 32) | desc_lo(smem_base);
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        const uint64_t a0 = base + stage * (Cfg::kStageBytes >> 4);
+        const uint64_t b0 = a0 + ((kSplit * Cfg::kABytes) >> 4);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) per 64-element block
-        if (kSplit == 2) {
-          // the hi|lo weight planes of a stage are adjacent: one N = 2*BLOCK_N MMA yields x_hi*w_hi (first half
-          // of the columns) and x_hi*w_lo (second half); x_lo*w_hi accumulates into the first half.
-          umma_bf16_elect(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2, (kb | k) != 0);
-          umma_bf16_elect(tmem_base, a0 + (Cfg::kABytes >> 4) + 2 * k, b0 + 2 * k, idesc, 1u);
-        } else {
-          umma_bf16_elect(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) per 64-element block
+          if (kSplit == 2) {
+            // the hi|lo weight planes of a stage are adjacent: one N = 2*BLOCK_N MMA yields x_hi*w_hi (first half
+            // of the columns) and x_hi*w_lo (second half); x_lo*w_hi accumulates into the first half.
+            if (k == 0) umma_bf16(tmem_base, a0, b0, idesc2, kb != 0);
+            else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
+            umma_bf16_acc(tmem_base, a0 + (Cfg::kABytes >> 4) + 2 * k, b0 + 2 * k, idesc);
+          } else {
+            if (k == 0) umma_bf16(tmem_base, a0, b0, idesc, kb != 0);
+            else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc);
+          }
         }
+        umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit_elect(empty_bar(stage));          // frees the smem slot once these MMAs retire
-      if (kb == num_kb - 1) umma_commit_elect(tmem_full_bar);
-      if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
     __syncwarp();
   } else {

@@ -114,27 +114,30 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_mn(BN), idesc2 = make_idesc_mn(kSplit * BN);
-    const uint32_t base_lo = desc_lo_mn(smem_base);
-    uint32_t stage = 0, phase = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      mbar_wait(full_bar(stage), phase);
-      tcgen05_fence_after();
-      const uint32_t a0 = base_lo + stage * (Cfg::kStageBytes >> 4);
-      const uint32_t b0 = a0 + (Cfg::kABytes >> 4);
+    if (elect_one()) {     // one lane runs the issue loop (see conv_tc.cu)
+      constexpr uint32_t idesc = make_idesc_mn(BN), idesc2 = make_idesc_mn(kSplit * BN);
+      const uint64_t base = (static_cast<uint64_t>(kDescHi) << 32) | desc_lo_mn(smem_base);
+      uint32_t stage = 0, phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        const uint64_t a0 = base + stage * (Cfg::kStageBytes >> 4);
+        const uint64_t b0 = a0 + (Cfg::kABytes >> 4);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {        // 8 x 16 pixels; 16 rows x 128 B = 2048 B per step
-        const uint32_t acc = (tile != tile_begin || j != 0) ? 1u : 0u;
-        if (kSplit == 2) {
-          umma_bf16_elect(tmem_base, a0 + j * 128, b0 + j * 128, idesc2, acc);
-          umma_bf16_elect(tmem_base, a0 + ((2 * kBoxBytes) >> 4) + j * 128, b0 + j * 128, idesc, 1u);
-        } else {
-          umma_bf16_elect(tmem_base, a0 + j * 128, b0 + j * 128, idesc, acc);
+        for (int j = 0; j < 8; ++j) {        // 8 x 16 pixels; 16 rows x 128 B = 2048 B per step
+          if (kSplit == 2) {
+            if (j == 0) umma_bf16(tmem_base, a0, b0, idesc2, tile != tile_begin);
+            else umma_bf16_acc(tmem_base, a0 + j * 128, b0 + j * 128, idesc2);
+            umma_bf16_acc(tmem_base, a0 + ((2 * kBoxBytes) >> 4) + j * 128, b0 + j * 128, idesc);
+          } else {
+            if (j == 0) umma_bf16(tmem_base, a0, b0, idesc, tile != tile_begin);
+            else umma_bf16_acc(tmem_base, a0 + j * 128, b0 + j * 128, idesc);
+          }
         }
+        umma_commit(empty_bar(stage));
+        if (tile == tile_end - 1) umma_commit(tmem_full_bar);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit_elect(empty_bar(stage));
-      if (tile == tile_end - 1) umma_commit_elect(tmem_full_bar);
-      if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
     __syncwarp();
   } else {
