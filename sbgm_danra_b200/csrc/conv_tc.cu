@@ -48,6 +48,23 @@ struct ConvTcCfg {
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
+// Slab mode (3x3, stride 1, pad 1, maps tileable by 16 rows x 8 columns): the activation operand of a 64-channel block
+// arrives ONCE as an 18 x 10-pixel halo slab and the nine taps are descriptor starts inside it (see conv3x3_c64.cu);
+// only the weight boxes stream per tap.  Operand ingest per k-block drops from 16 KB + B to 2.5 KB + B (per plane).
+constexpr int kSlabTileW = 8, kSlabTileH = 16, kSlabW = kSlabTileW + 2, kSlabH = kSlabTileH + 2, kSlabAStages = 2;
+constexpr uint32_t kSlabTxBytes = kSlabW * kSlabH * 128;       // 23040 per plane
+constexpr uint32_t kSlabPlaneBytes = 23552;                    // plane pitch in smem (1024-aligned)
+constexpr uint32_t kDescHiSlab128 = ((kSlabW * 128u) >> 4) | (1u << 14) | (2u << 29);   // SBO = one slab row
+template <int kSplit, int BLOCK_N, int kStages>
+struct ConvTcSlabCfg {
+  static constexpr uint32_t kBBytes = BLOCK_N * 128;
+  static constexpr uint32_t kAStageBytes = kSplit * kSlabPlaneBytes;
+  static constexpr uint32_t kBStageBytes = kSplit * kBBytes;
+  static constexpr uint32_t kBOffset = kSlabAStages * kAStageBytes;
+  static constexpr uint32_t kBarOffset = kBOffset + kStages * kBStageBytes;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;
+};
+
 template <int BLOCK_N>
 struct ConvTcThreads {
   static constexpr int kEpiGroups = BLOCK_N >= 128 ? 2 : 1;
@@ -55,20 +72,23 @@ struct ConvTcThreads {
   static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;
 };
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false>
 __global__ void __launch_bounds__(ConvTcThreads<BLOCK_N>::kThreads, ConvTcThreads<BLOCK_N>::kMinCtas)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const ConvTcParams p) {
   pdl_grid_sync();
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   using Cfg = ConvTcCfg<kSplit, BLOCK_N, kStages>;
+  using SCfg = ConvTcSlabCfg<kSplit, BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_base = smem_base + (SLAB ? SCfg::kBarOffset : Cfg::kBarOffset);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+  auto slab_full = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };                   // slab mode only
+  auto slab_empty = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + kSlabAStages + s); };
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,6 +101,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
+    if (SLAB) {
+      for (int s = 0; s < kSlabAStages; ++s) {
+        mbar_init(slab_full(s), 1);
+        mbar_init(slab_empty(s), 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kSplit * BLOCK_N);
@@ -99,7 +125,67 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int kb_begin = blockIdx.z * kb_per;
   const int num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;     // >= 1 by construction of `splits`
 
-  if (warp == 0) {
+  if (SLAB && warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        const int as = cb & 1;
+        mbar_wait(slab_empty(as), ((cb >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(slab_full(as), kSplit * kSlabTxBytes);
+#pragma unroll
+        for (int pl = 0; pl < kSplit; ++pl)
+          tma_load_5d(smem_base + as * SCfg::kAStageBytes + pl * kSlabPlaneBytes, &tmap_a, slab_full(as), cb * 64, wo0 - 1, ho0 - 1,
+                      n0, pl);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), SCfg::kBStageBytes);
+          const uint32_t b_dst = smem_base + SCfg::kBOffset + stage * SCfg::kBStageBytes;
+#pragma unroll
+          for (int pl = 0; pl < kSplit; ++pl)
+            tma_load_3d(b_dst + pl * SCfg::kBBytes, &tmap_b, full_bar(stage), (tap * p.cin_blocks + cb) * 64, co0, pl);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (SLAB && warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N), idesc2 = make_idesc(kSplit * BLOCK_N);
+      const uint64_t a_base = (static_cast<uint64_t>(kDescHiSlab128) << 32) | desc_lo(smem_base);
+      const uint64_t b_base = (static_cast<uint64_t>(kDescHi) << 32) | desc_lo(smem_base + SCfg::kBOffset);
+      uint32_t stage = 0, phase = 0;
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        const int as = cb & 1;
+        mbar_wait(slab_full(as), (cb >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint64_t a_slab = a_base + as * (SCfg::kAStageBytes >> 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          // tap (r, s): the 128 A rows start at slab pixel (r, s); 8-row groups (output rows) are one slab row apart
+          const uint64_t a0 = a_slab + ((((tap / 3) * kSlabW + (tap % 3)) * 128) >> 4);
+          const uint64_t b0 = b_base + stage * (SCfg::kBStageBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (kSplit == 2) {
+              if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc2, cb != 0);
+              else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
+              umma_bf16_acc(tmem_base, a0 + (kSlabPlaneBytes >> 4) + 2 * k, b0 + 2 * k, idesc);
+            } else {
+              if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc, cb != 0);
+              else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc);
+            }
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(slab_empty(as));
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -358,13 +444,14 @@ void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
   (void)pow2_floor;
 }
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false>
 static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
                                cudaStream_t st) {
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
-  using Cfg = ConvTcCfg<kSplit, BLOCK_N, kStages>;
+  using Cfg = std::conditional_t<SLAB, ConvTcSlabCfg<kSplit, BLOCK_N, kStages>, ConvTcCfg<kSplit, BLOCK_N, kStages>>;
   static_assert(!STAGED || Cfg::kBarOffset >= 4u * (BLOCK_N / 64) * kSplit * kStageBlockBytes, "the staging area must fit in the pipeline stages");
-  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED>;
+  static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
+  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED, SLAB>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -399,6 +486,14 @@ static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kStages, ACT, 0, true>(ta, tb, to, p, m_tiles, st)));
   }
   SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kStages, ACT, 0, false>(ta, tb, to, p, m_tiles, st)));
+  return 0;
+}
+
+// slab mode: staged TMA-store epilogue only, four weight stages
+template <int FMT, int BLOCK_N>
+static int launch_conv_tc_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
+                               cudaStream_t st) {
+  SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, 4, ACT, 0, true, true>(ta, tb, to, p, m_tiles, st)));
   return 0;
 }
 
@@ -507,19 +602,39 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
   p.ep.proj_w = proj_w; p.ep.proj_out = proj_out; p.ep.n_proj = n_proj;
   SBGM_REQUIRE(p.w_tile * stride <= 256 && p.h_tile * stride <= 256, "conv2d_tc: TMA box too large for stride %d", stride);
 
-  CUtensorMap ta, tb, to;
-  if (encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
-  const int K = kh * kw * cin;
-  if (encode_weight_map(&tb, weight, planes, w_plane, cout, K, block_n)) return 1;
   // dense output addressing, full epilogue: the tile leaves through shared memory and TMA stores (SBGM_B200_TMA_STORE=0: off)
   static const bool tma_store_on = [] { const char* e = getenv("SBGM_B200_TMA_STORE"); return !(e != nullptr && e[0] == '0'); }();
   p.ep.staged = (tma_store_on && !scatter && proj_w == nullptr && p.splits == 1 && out != nullptr) ? 1 : 0;
+  // 3x3 / stride 1 / pad 1 on maps tileable by 16 x 8: one halo slab per 64-channel block (SBGM_B200_SLAB=0: off)
+  static const bool slab_on = [] { const char* e = getenv("SBGM_B200_SLAB"); return !(e != nullptr && e[0] == '0'); }();
+  const bool slab = slab_on && p.ep.staged && kh == 3 && kw == 3 && stride == 1 && p.pad_h == 1 && p.pad_w == 1 && ho == h && wo == w &&
+                    ho % kSlabTileH == 0 && wo % kSlabTileW == 0;
+  if (slab) {
+    p.w_tile = kSlabTileW; p.h_tile = kSlabTileH; p.n_tile = 1;
+    p.tiles_w = wo / kSlabTileW; p.tiles_h = ho / kSlabTileH;
+    m_tiles = p.tiles_w * p.tiles_h * n;
+    p.gn_chunks = gn_chunks_for(p);
+  }
+  CUtensorMap ta, tb, to;
+  if (slab ? encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, kSlabH, 1, 1)
+           : encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
+  const int K = kh * kw * cin;
+  if (encode_weight_map(&tb, weight, planes, w_plane, cout, K, block_n)) return 1;
   if (p.ep.staged) {
     if (encode_out_map(&to, out, planes, out_plane, n, ho, wo, cout, p.w_tile, p.h_tile, p.n_tile)) return 1;
   } else {
     to = ta;
   }
   cudaStream_t st = as_stream(stream);
+  if (slab) {
+    if (fmt == SBGM_FMT_BF16) {
+      if (block_n == 256) return launch_conv_tc_slab<SBGM_FMT_BF16, 256>(ta, tb, to, p, m_tiles, st);
+      if (block_n == 128) return launch_conv_tc_slab<SBGM_FMT_BF16, 128>(ta, tb, to, p, m_tiles, st);
+      return launch_conv_tc_slab<SBGM_FMT_BF16, 64>(ta, tb, to, p, m_tiles, st);
+    }
+    if (block_n == 128) return launch_conv_tc_slab<SBGM_FMT_BF16X2, 128>(ta, tb, to, p, m_tiles, st);
+    return launch_conv_tc_slab<SBGM_FMT_BF16X2, 64>(ta, tb, to, p, m_tiles, st);
+  }
   if (fmt == SBGM_FMT_BF16) {
     if (block_n == 256) return launch_conv_tc<SBGM_FMT_BF16, 256, 4>(ta, tb, to, p, m_tiles, st);
     if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16, 128, 3>(ta, tb, to, p, m_tiles, st);

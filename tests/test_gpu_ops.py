@@ -116,6 +116,12 @@ CONV_CASES = [
     (3, 8, 16, 64, 64, 3, 1, 1, "full"),          # single tile per image of the persistent 64->64 kernel
     (70, 16, 32, 64, 64, 3, 1, 1, "relu"),        # 280 tiles: more than one wave of the persistent kernel
     (2, 12, 24, 64, 192, 3, 1, 1, "full"),        # non power-of-two spatial, cout = 3 x 64
+    # halo-slab mode of the generic kernel (3x3, stride 1, maps tileable by 16 rows x 8 columns)
+    (3, 32, 32, 128, 128, 3, 1, 1, "full"),
+    (2, 16, 16, 256, 256, 3, 1, 1, "relu"),
+    (2, 16, 24, 128, 64, 3, 1, 1, "plain"),       # 64-wide tile, three tiles per row
+    (2, 32, 8, 192, 320, 3, 1, 1, "full"),        # odd number of channel blocks (slab ring parity), cout = 5 x 64
+    (40, 16, 16, 128, 256, 3, 1, 1, "gelu"),      # several waves
 ]
 
 
