@@ -31,6 +31,9 @@ struct ConvTcParams {
   int w_tile, h_tile, n_tile;
   int tiles_w, tiles_h;
   int cin_blocks;
+  int slab_perm;       // slab mode on 8 x 8 x 2-image tiles: tile rows ordered [h][n][w], tensor maps with (c, w, n, h) dims
+  int slab_row;        // slab mode: descriptor units (16 B) per slab row step = pixels per slab row * 8
+  uint32_t slab_tx;    // slab mode: bytes per slab plane
   int splits;          // split-K factor (gridDim.z); > 1 => raw fp32 partial tiles go to `ws`
   float* ws;           // [splits][pixels][cout] fp32
   float* gn_partials;  // [n][gn_chunks][cout/8][2] or nullptr: fused GroupNorm statistics (8-channel granularity)
@@ -52,8 +55,7 @@ struct ConvTcCfg {
 // arrives ONCE as an 18 x 10-pixel halo slab and the nine taps are descriptor starts inside it (see conv3x3_c64.cu);
 // only the weight boxes stream per tap.  Operand ingest per k-block drops from 16 KB + B to 2.5 KB + B (per plane).
 constexpr int kSlabTileW = 8, kSlabTileH = 16, kSlabW = kSlabTileW + 2, kSlabH = kSlabTileH + 2, kSlabAStages = 2;
-constexpr uint32_t kSlabTxBytes = kSlabW * kSlabH * 128;       // 23040 per plane
-constexpr uint32_t kSlabPlaneBytes = 23552;                    // plane pitch in smem (1024-aligned)
+constexpr uint32_t kSlabPlaneBytes = 25600;                    // plane pitch in smem (1024-aligned): 18 x 10 or 10 x 2 x 10 pixels
 constexpr uint32_t kDescHiSlab128 = ((kSlabW * 128u) >> 4) | (1u << 14) | (2u << 29);   // SBO = one slab row
 template <int kSplit, int BLOCK_N, int kStages>
 struct ConvTcSlabCfg {
@@ -124,19 +126,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int kb_per = (total_kb + p.splits - 1) / p.splits;
   const int kb_begin = blockIdx.z * kb_per;
   const int num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;     // >= 1 by construction of `splits`
+  // slab mode splits K by 64-channel blocks (each block = nine taps of one slab)
+  const int cb_per = (p.cin_blocks + p.splits - 1) / p.splits;
+  const int cb_begin = blockIdx.z * cb_per;
+  const int cb_cnt = min(p.cin_blocks, cb_begin + cb_per) - cb_begin;  // >= 1: checked by the host
 
   if (SLAB && warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int cb = 0; cb < p.cin_blocks; ++cb) {
-        const int as = cb & 1;
-        mbar_wait(slab_empty(as), ((cb >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(slab_full(as), kSplit * kSlabTxBytes);
+      for (int i = 0; i < cb_cnt; ++i) {
+        const int cb = cb_begin + i, as = i & 1;
+        mbar_wait(slab_empty(as), ((i >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(slab_full(as), kSplit * p.slab_tx);
 #pragma unroll
         for (int pl = 0; pl < kSplit; ++pl)
-          tma_load_5d(smem_base + as * SCfg::kAStageBytes + pl * kSlabPlaneBytes, &tmap_a, slab_full(as), cb * 64, wo0 - 1, ho0 - 1,
-                      n0, pl);
+          tma_load_5d(smem_base + as * SCfg::kAStageBytes + pl * kSlabPlaneBytes, &tmap_a, slab_full(as), cb * 64, wo0 - 1,
+                      p.slab_perm ? n0 : ho0 - 1, p.slab_perm ? ho0 - 1 : n0, pl);
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), SCfg::kBStageBytes);
@@ -154,9 +160,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint64_t a_base = (static_cast<uint64_t>(kDescHiSlab128) << 32) | desc_lo(smem_base);
       const uint64_t b_base = (static_cast<uint64_t>(kDescHi) << 32) | desc_lo(smem_base + SCfg::kBOffset);
       uint32_t stage = 0, phase = 0;
-      for (int cb = 0; cb < p.cin_blocks; ++cb) {
-        const int as = cb & 1;
-        mbar_wait(slab_full(as), (cb >> 1) & 1u);
+      for (int i = 0; i < cb_cnt; ++i) {
+        const int as = i & 1;
+        mbar_wait(slab_full(as), (i >> 1) & 1u);
         tcgen05_fence_after();
         const uint64_t a_slab = a_base + as * (SCfg::kAStageBytes >> 4);
 #pragma unroll
@@ -164,16 +170,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           // tap (r, s): the 128 A rows start at slab pixel (r, s); 8-row groups (output rows) are one slab row apart
-          const uint64_t a0 = a_slab + ((((tap / 3) * kSlabW + (tap % 3)) * 128) >> 4);
+          const uint64_t a0 = a_slab + static_cast<uint32_t>((tap / 3) * p.slab_row + (tap % 3) * 8);
           const uint64_t b0 = b_base + stage * (SCfg::kBStageBytes >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (kSplit == 2) {
-              if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc2, cb != 0);
+              if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc2, i != 0);
               else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
               umma_bf16_acc(tmem_base, a0 + (kSlabPlaneBytes >> 4) + 2 * k, b0 + 2 * k, idesc);
             } else {
-              if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc, cb != 0);
+              if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc, i != 0);
               else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc);
             }
           }
@@ -243,7 +249,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int kColsPerGroup = BLOCK_N / ConvTcThreads<BLOCK_N>::kEpiGroups;
     const int c_begin = ((warp - 2) >> 2) * kColsPerGroup, c_end = c_begin + kColsPerGroup;
     const int row = quarter * 32 + lane;
-    const int w_l = row % p.w_tile, h_l = (row / p.w_tile) % p.h_tile, n_l = row / (p.w_tile * p.h_tile);
+    int w_l = row % p.w_tile, h_l = (row / p.w_tile) % p.h_tile, n_l = row / (p.w_tile * p.h_tile);
+    if (SLAB && p.slab_perm) {          // tile rows ordered [h][n][w]
+      n_l = (row / p.w_tile) % p.n_tile;
+      h_l = row / (p.w_tile * p.n_tile);
+    }
     const int n = n0 + n_l, oy = ho0 + h_l, ox = wo0 + w_l;
     const bool valid = (n < p.n) && (oy < p.ho) && (ox < p.wo);
     const size_t pix = (static_cast<size_t>(n) * p.out_h + oy * p.out_step + p.out_oy) * p.out_w + ox * p.out_step + p.out_ox;
@@ -307,6 +317,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           sa.x0 = wo0 + r0 % p.w_tile;
           sa.y0 = ho0 + (r0 / p.w_tile) % p.h_tile;
           sa.n0 = n0 + r0 / (p.w_tile * p.h_tile);
+          if (SLAB && p.slab_perm) {    // output map dims (c, w, n, h): the warp's 32 rows are [2 h][2 n][8 w]
+            sa.y0 = n0;
+            sa.n0 = ho0 + r0 / (p.w_tile * p.n_tile);
+          }
         }
         epilogue_block64<FMT, ACT, PROJ, STAGED>(p.ep, ra, rb, co0 + c0, n, pix, valid, lane, proj_acc, sa);
       }
@@ -406,6 +420,25 @@ int encode_out_map(CUtensorMap* map, const void* base, int planes, size_t plane_
   return 0;
 }
 
+// NHWC tensor seen with dims (c, w, n, h, plane): a box (64, box_w, box_n, box_h) lands in shared memory ordered [h][n][w], so
+// that row groups of a tile spanning several images stay one slab row apart (slab mode on 8 x 8 maps).  Used for the halo slab
+// (box 10 x 2 x 10) and for the staged output store (box 8 x 2 x 2 = one warp's 32 rows).
+static int encode_perm_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int n, int h, int w, int c,
+                           int box_w, int box_n, int box_h) {
+  EncodeTiledFn encode = get_encode_fn();
+  SBGM_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)n, (cuuint64_t)h, (cuuint64_t)planes};
+  const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)h * w * c * 2, (cuuint64_t)w * c * 2,
+                                 planes == 2 ? (cuuint64_t)plane_elems * 2 : (cuuint64_t)n * h * w * c * 2};
+  const cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_n, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SBGM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(permuted) failed with %d", (int)r);
+  return 0;
+}
+
 int encode_weight_map(CUtensorMap* map, const void* base, int planes, size_t plane_elems, int cout, int K, int box_rows) {
   EncodeTiledFn encode = get_encode_fn();
   SBGM_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
@@ -493,7 +526,11 @@ static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
 template <int FMT, int BLOCK_N>
 static int launch_conv_tc_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
                                cudaStream_t st) {
-  SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, 4, ACT, 0, true, true>(ta, tb, to, p, m_tiles, st)));
+  constexpr int kBStages = (FMT == SBGM_FMT_BF16X2 && BLOCK_N == 128) ? 3 : 4;     // 2 x 50 KB of slabs + 3 x 32 KB of weights
+  if (p.ep.staged) {
+    SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kBStages, ACT, 0, true, true>(ta, tb, to, p, m_tiles, st)));
+  }
+  SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kBStages, ACT, 0, false, true>(ta, tb, to, p, m_tiles, st)));
   return 0;
 }
 
@@ -520,6 +557,7 @@ static void conv_tc_geometry(int n, int h, int w, int cin, int cout, int kh, int
   p->tiles_w = ceil_div(p->wo, p->w_tile);
   p->tiles_h = ceil_div(p->ho, p->h_tile);
   p->cin_blocks = cin / 64;
+  p->slab_perm = 0; p->slab_row = 0; p->slab_tx = 0;
   *m_tiles = p->tiles_w * p->tiles_h * ceil_div(n, p->n_tile);
   *block_n = (cout % 256 == 0 && planes == 1) ? 256 : (cout % 128 == 0 ? 128 : 64);
   // under-filled grids (the attention blocks' Linear layers): narrower tiles = more CTAs and a shorter epilogue each
@@ -605,23 +643,33 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
   // dense output addressing, full epilogue: the tile leaves through shared memory and TMA stores (SBGM_B200_TMA_STORE=0: off)
   static const bool tma_store_on = [] { const char* e = getenv("SBGM_B200_TMA_STORE"); return !(e != nullptr && e[0] == '0'); }();
   p.ep.staged = (tma_store_on && !scatter && proj_w == nullptr && p.splits == 1 && out != nullptr) ? 1 : 0;
-  // 3x3 / stride 1 / pad 1 on maps tileable by 16 x 8: one halo slab per 64-channel block (SBGM_B200_SLAB=0: off)
+  // 3x3 / stride 1 / pad 1: one halo slab per 64-channel block (SBGM_B200_SLAB=0: off).  Maps tileable by 16 rows x 8 columns
+  // use 16 x 8 tiles of one image; other maps tileable by 8 x 8 use 8 x 8 tiles of two images with permuted tensor maps
+  // (no fused GroupNorm statistics there: a warp's 32 rows span two images).  Split-K slices the 64-channel blocks.
   static const bool slab_on = [] { const char* e = getenv("SBGM_B200_SLAB"); return !(e != nullptr && e[0] == '0'); }();
-  const bool slab = slab_on && p.ep.staged && kh == 3 && kw == 3 && stride == 1 && p.pad_h == 1 && p.pad_w == 1 && ho == h && wo == w &&
-                    ho % kSlabTileH == 0 && wo % kSlabTileW == 0;
+  bool slab = slab_on && (p.ep.staged || (p.splits > 1 && proj_w == nullptr && !scatter)) && kh == 3 && kw == 3 && stride == 1 &&
+              p.pad_h == 1 && p.pad_w == 1 && ho == h && wo == w && wo % 8 == 0 && ho % 8 == 0;
+  const bool slab_perm = slab && ho % kSlabTileH != 0;
+  if (slab_perm && gn_partials != nullptr) slab = false;
+  if (slab && p.splits > 1 && (p.splits - 1) * ceil_div(p.cin_blocks, p.splits) >= p.cin_blocks) slab = false;
   if (slab) {
-    p.w_tile = kSlabTileW; p.h_tile = kSlabTileH; p.n_tile = 1;
-    p.tiles_w = wo / kSlabTileW; p.tiles_h = ho / kSlabTileH;
-    m_tiles = p.tiles_w * p.tiles_h * n;
-    p.gn_chunks = gn_chunks_for(p);
+    p.slab_perm = slab_perm ? 1 : 0;
+    p.w_tile = 8; p.h_tile = slab_perm ? 8 : 16; p.n_tile = slab_perm ? 2 : 1;
+    p.tiles_w = wo / 8; p.tiles_h = ho / p.h_tile;
+    m_tiles = p.tiles_w * p.tiles_h * ceil_div(n, p.n_tile);
+    p.slab_row = (slab_perm ? 2 : 1) * kSlabW * 8;
+    p.slab_tx = (slab_perm ? 10 * 2 * 10 : kSlabW * kSlabH) * 128;
+    if (!slab_perm) p.gn_chunks = gn_chunks_for(p);
   }
   CUtensorMap ta, tb, to;
-  if (slab ? encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, kSlabH, 1, 1)
+  if (slab ? (slab_perm ? encode_perm_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, 2, 10)
+                        : encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, kSlabH, 1, 1))
            : encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
   const int K = kh * kw * cin;
   if (encode_weight_map(&tb, weight, planes, w_plane, cout, K, block_n)) return 1;
   if (p.ep.staged) {
-    if (encode_out_map(&to, out, planes, out_plane, n, ho, wo, cout, p.w_tile, p.h_tile, p.n_tile)) return 1;
+    if (slab && slab_perm ? encode_perm_map(&to, out, planes, out_plane, n, ho, wo, cout, 8, 2, 2)
+                          : encode_out_map(&to, out, planes, out_plane, n, ho, wo, cout, p.w_tile, p.h_tile, p.n_tile)) return 1;
   } else {
     to = ta;
   }

@@ -122,6 +122,10 @@ CONV_CASES = [
     (2, 16, 24, 128, 64, 3, 1, 1, "plain"),       # 64-wide tile, three tiles per row
     (2, 32, 8, 192, 320, 3, 1, 1, "full"),        # odd number of channel blocks (slab ring parity), cout = 5 x 64
     (40, 16, 16, 128, 256, 3, 1, 1, "gelu"),      # several waves
+    (64, 8, 8, 256, 256, 3, 1, 1, "full"),        # 8 x 8 maps: tiles of two images, permuted tensor maps
+    (5, 8, 8, 512, 512, 3, 1, 1, "full"),         # same with an odd image count and split-K over channel blocks
+    (3, 24, 8, 128, 128, 3, 1, 1, "relu"),        # 24 rows: 8-row tiles
+    (33, 8, 16, 192, 64, 3, 1, 1, "plain"),
 ]
 
 
