@@ -178,6 +178,9 @@ class Kernels:
             out_ptr, out_plane, pout, pargs = out.ptr, out.plane, None, (None, 0, None)
         stats = None
         skip_this = ("c64" in _SKIP and self._c64_ok(x, cw, stride, pad)) or ("conv_tc" in _SKIP and not self._c64_ok(x, cw, stride, pad))
+        if _SKIP and not self._c64_ok(x, cw, stride, pad):      # finer classes of the generic kernel
+            cls = "tc_1x1" if cw.kh == 1 else "tc_s2" if stride != 1 else "tc_big" if x.h >= 16 else "tc_8" if x.h == 8 else "tc_4"
+            skip_this = skip_this or cls in _SKIP
         if skip_this:                      # timing ablation: leave the output uninitialised
             if proj is not None:
                 return (out, pout) if proj_keep else pout

@@ -35,7 +35,10 @@ print("MS_PER_NFE", e0.elapsed_time(e1) / 300)
 def main():
     precision = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
     base = None
-    for skip in ["", "attn", "attn_core", "ln", "gn", "upsample", "c64", "conv_tc", "c64,conv_tc,attn,gn,upsample"]:
+    variants = ["", "attn", "attn_core", "ln", "gn", "upsample", "c64", "conv_tc", "c64,conv_tc,attn,gn,upsample"]
+    if len(sys.argv) > 2:       # e.g. tools/ablate.py bf16x3 tc_1x1 tc_s2 tc_big tc_8 tc_4  (classes of the generic conv kernel)
+        variants = [""] + sys.argv[2:]
+    for skip in variants:
         env = dict(os.environ, SBGM_B200_SKIP=skip)
         r = subprocess.run([sys.executable, "-c", CHILD, precision], env=env, capture_output=True, text=True)
         line = [l for l in r.stdout.splitlines() if l.startswith("MS_PER_NFE")]
