@@ -2,7 +2,7 @@
 // (encoder layer1, decoder block 3 and the final conv_up: 45% of the network's FLOPs, all with a
 // K loop of only nine 64-wide blocks, SURVEY.md section 7 "hard parts").
 //
-// The generic kernel (conv_tc.cu) re-fetches a 16 KB activation box and an 8 KB weight box for every
+// The generic kernel's plain mode (conv_tc.cu) re-fetches a 16 KB activation box and an 8 KB weight box for every
 // tap: 24 KB per 128 MMA-cycles, 4x more than the L2->SM path sustains.  Here
 //   * one CTA per SM stays resident and walks tiles blockIdx.x, +gridDim.x, ...;
 //   * the 9 x 64 x 64 weights (72 KB bf16, 144 KB split-bf16) are loaded ONCE per CTA and stay in smem;

@@ -81,38 +81,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Warp-uniform issue path: the WHOLE warp runs the MMA loop (uniform control flow, so descriptor arithmetic
-// stays on the uniform datapath) and one elected lane issues.  `a_lo` / `b_lo` are the low descriptor words
-// ((smem_addr & 0x3FFFF) >> 4 | 1 << 16); the high word is the constant kDescHi (SBO = 1024 B, version 1,
-// SWIZZLE_128B).  Advancing an operand by `bytes` is a plain add of bytes >> 4 to the low word.
+// `desc_lo` is the low descriptor word ((smem_addr & 0x3FFFF) >> 4 | LBO 1 << 16); the high word for K-major
+// SWIZZLE_128B tiles is the constant kDescHi (SBO = 1024 B, version 1).  Advancing an operand by `bytes` is a plain
+// add of bytes >> 4 to the descriptor.
 constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
-// Same issue path with an explicit high word for A: K-major SWIZZLE_64B tiles (64-byte rows, 8-row atom = 512 B:
-// SBO = 512 >> 4 = 32, version 1, layout type 4) next to a SWIZZLE_128B B operand.
-constexpr uint32_t kDescHiSw64 = 32u | (1u << 14) | (4u << 29);
-__device__ __forceinline__ void umma_bf16_elect_hi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc,
-                                                   uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %6};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi), "r"(a_hi)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
-      : "memory");
-}
 // Single-thread issue path: the caller has already narrowed the warp to one elected lane (elect_one()), so the
 // MMA needs no per-instruction election or predicate vote.  Descriptors are whole 64-bit values; advancing an
 // operand is one 64-bit add of bytes >> 4 (the address field never carries out of its 14 bits inside one CTA's
@@ -134,14 +107,6 @@ __device__ __forceinline__ void umma_bf16_first(uint32_t tmem_d, uint64_t adesc,
       "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 0, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
