@@ -427,6 +427,19 @@ class ScoreNet(nn.Module):
             return eng.forward(x, t, y, planes, inv_std)
 
 
+def _detach_grads_aliasing(params, flat) -> None:
+    """Give every `.grad` that is still a view of the engine's flat gradient buffer its own storage (the engine is about to
+    overwrite the buffer: the captured forward re-zeroes it, backward refills it)."""
+    if flat is None:
+        return
+    ptr = flat.untyped_storage().data_ptr()
+    with torch.no_grad():
+        for p in params:
+            g = p.grad
+            if g is not None and g.untyped_storage().data_ptr() == ptr:
+                p.grad = g.clone()
+
+
 class _ScoreNetFn(torch.autograd.Function):
     """The whole score-UNet as one autograd node: forward and backward both run this repo's kernels
     (train_engine.TrainEngine); replaces torch autograd over sbgm/score_unet.py:829-879."""
@@ -446,18 +459,33 @@ class _ScoreNetFn(torch.autograd.Function):
                 return TrainEngine(tensors, model.spec(), model.precision, x.device, bn_train=model.training)
             runners.clear()                       # one live configuration at a time (the graphs pin GBs of activations)
             runner = runners[key] = TrainRunner(make_engine, use_graphs=os.environ.get("SBGM_B200_TRAIN_GRAPHS", "1") != "0")
+        if runner.eng is not None:                # captured step: its forward graph re-zeroes the flat gradient buffer
+            _detach_grads_aliasing(params, runner.eng.flat)
         yy = None if y is None else y.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous()
         out, handle = runner.forward(x, t.reshape(-1).float().contiguous(), yy, planes, inv_std, getattr(model, "_grad_sync", None))
-        ctx.runner, ctx.handle, ctx.names = runner, handle, names
+        ctx.runner, ctx.handle, ctx.names, ctx.params = runner, handle, names, params
         return out
 
     @staticmethod
     def backward(ctx, dout):
         runner, handle = ctx.runner, ctx.handle
+        # Every parameter gradient is a view of the engine's flat buffer.  Returned as FRESH view objects (nothing else holds
+        # them), autograd's AccumulateGrad adopts them as `.grad` instead of cloning 164 tensors per step (DDP's
+        # gradient_as_bucket_view).  A `.grad` that still aliases the buffer from an earlier step (gradient accumulation,
+        # zero_grad(set_to_none=False)) is detached into its own storage before the buffer is overwritten (here and in forward).
+        # SBGM_B200_GRAD_VIEWS=0 restores independent `.grad` tensors (a held reference to an old `.grad` then survives the
+        # next backward, at the price of the copies).
+        views = os.environ.get("SBGM_B200_GRAD_VIEWS", "1") != "0"
+        _detach_grads_aliasing(ctx.params, runner.flat_of(handle))
         with torch.cuda.device(dout.device):
             grads = runner.backward(handle, dout)
-        ctx.runner = ctx.handle = None
-        return (None,) * 7 + tuple(grads.get(n) for n in ctx.names)
+        names = ctx.names
+        ctx.runner = ctx.handle = ctx.params = None
+        out = []
+        for n in names:
+            g = grads.get(n)
+            out.append(None if g is None else (g.view(g.shape) if views else g))
+        return (None,) * 7 + tuple(out)
 
 
 class _DSMLossFn(torch.autograd.Function):

@@ -868,6 +868,11 @@ class TrainRunner:
         self.busy = True
         return self.out.clone(), ("graph", _InFlight(self))
 
+    def flat_of(self, handle) -> torch.Tensor:
+        """The flat gradient buffer the backward of `handle` is going to write."""
+        kind, obj = handle
+        return (obj if kind == "eager" else self.eng).flat
+
     def backward(self, handle, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
         kind, obj = handle
         if kind == "eager":

@@ -451,6 +451,36 @@ def test_graph_replay_reproduces_eager_step_bitwise():
             assert torch.equal(grads_k[k], snaps[0][1][k]), k
 
 
+def test_parameter_gradients_are_adopted_views_of_the_flat_buffer():
+    """`.grad` tensors are views of the engine's flat gradient buffer (no per-parameter clone in AccumulateGrad); a `.grad`
+    kept across a second backward (gradient accumulation) is detached first, so accumulation still adds."""
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16x3", DEV).eval()
+    b = synth_batch(batch=2, size=32, n_lr=1)
+    c = lambda v: None if v is None else v.to(DEV)
+
+    def backward():
+        score_sampling.manual_seed(3)
+        loss_fn(net, c(b.x), marginal_prob_std_fn, cond_img=c(b.cond_img), sdf_cond=c(b.sdf_cond)).backward()
+
+    for _ in range(4):                                  # eager steps, then the captured graphs
+        net.zero_grad(set_to_none=True)
+        backward()
+        flat = next(iter(net._train_runners.values()))
+        storages = {p.grad.untyped_storage().data_ptr() for p in net.parameters() if p.grad is not None}
+        assert len(storages) == 1, "every gradient should live in one flat buffer"
+    single = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    backward()                                          # no zero_grad: accumulate on top of the adopted views
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, 2 * single[k]), k
+    del flat
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_train_mode_batchnorm_forward_matches_reference_golden(golden, precision):
     """`.train()` forward under no_grad (the generation.py:47 quirk: sampling with batch statistics)."""
