@@ -689,6 +689,11 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
     return launch_conv_tc<SBGM_FMT_BF16, 64, 4>(ta, tb, to, p, m_tiles, st);
   }
   if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16X2, 128, 3>(ta, tb, to, p, m_tiles, st);
+  // short K loop on a grid of at most one CTA per SM (the attention blocks' Linear layers): four stages put the whole K loop
+  // in flight at once -- one TMA round trip instead of two
+  static const bool deep_on = [] { const char* e = getenv("SBGM_B200_DEEP_SHORTK"); return !(e != nullptr && e[0] == '0'); }();
+  if (deep_on && proj_w == nullptr && kh * kw * p.cin_blocks <= 8 && static_cast<long long>(m_tiles) * (cout / 64) * p.splits <= 148)
+    return launch_conv_tc<SBGM_FMT_BF16X2, 64, 4>(ta, tb, to, p, m_tiles, st);
   return launch_conv_tc<SBGM_FMT_BF16X2, 64, 2>(ta, tb, to, p, m_tiles, st);
 }
 
