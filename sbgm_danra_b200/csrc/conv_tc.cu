@@ -652,6 +652,14 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
   const bool slab_perm = slab && ho % kSlabTileH != 0;
   if (slab_perm && gn_partials != nullptr) slab = false;
   if (slab && p.splits > 1 && (p.splits - 1) * ceil_div(p.cin_blocks, p.splits) >= p.cin_blocks) slab = false;
+  // slab mode makes the activation operand cheap to re-read: a two-way split-K 128-wide layer (the 8 x 8 maps) runs instead as
+  // twice as many 64-wide tiles over the whole K loop -- same CTA count, no partial tiles, no finalize kernel
+  static const bool nosplit_on = [] { const char* e = getenv("SBGM_B200_SLAB_NOSPLIT"); return !(e != nullptr && e[0] == '0'); }();
+  if (slab && nosplit_on && p.splits == 2 && block_n == 128 && tma_store_on && out != nullptr) {
+    block_n = 64;
+    p.splits = 1;
+    p.ep.staged = 1;
+  }
   if (slab) {
     p.slab_perm = slab_perm ? 1 : 0;
     p.w_tile = 8; p.h_tile = slab_perm ? 8 : 16; p.n_tile = slab_perm ? 2 : 1;
