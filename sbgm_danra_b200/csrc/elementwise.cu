@@ -5,6 +5,8 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include <mutex>
+#include <unordered_map>
 
 namespace sbgm {
 
@@ -508,6 +510,25 @@ __global__ void final_gather_kernel(const float* __restrict__ proj, const float*
   }
 }
 
+// Blocks of `kern` that are resident at once on the whole GPU.  The GroupNorm apply pass (grid-stride, 48 registers: five
+// blocks per SM) gets at most that many blocks: the fixed cap of 148 x 8 was 1.6 waves, i.e. it paid for two.
+// (The same change left the bilinear upsample, 72 registers, unchanged to slightly slower: not applied there.)
+static int resident_blocks(const void* kern, int block, size_t smem) {
+  static std::unordered_map<const void*, int> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(kern);
+  if (it != cache.end()) return it->second;
+  int per_sm = 0, dev = 0, sms = 148;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static const bool on = [] { const char* e = getenv("SBGM_B200_WAVE_GRID"); return !(e != nullptr && e[0] == '0'); }();
+  const int v = on ? per_sm * sms : 148 * 8;
+  cache[kern] = v;
+  return v;
+}
+
 static int grid_for(size_t items, int block, int max_blocks = 148 * 16) {
   size_t g = (items + block - 1) / block;
   if (g < 1) g = 1;
@@ -600,7 +621,9 @@ int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const floa
   const size_t smem1 = (static_cast<size_t>(lanes) + 1) * c * 2 * sizeof(float);
   const size_t smem2 = (static_cast<size_t>(c) + groups) * 2 * sizeof(float);
   dim3 g1(kGnChunks, n);
-  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
+  int slots = 148 * 8;
+  SBGM_DISPATCH_FMT(fmt, (slots = resident_blocks(reinterpret_cast<const void*>(gn_apply_kernel<FMT>), 256, smem2)));
+  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), slots / max(n, 1)));
   dim3 g2(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
     launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, st, x, x_plane, hw, c, groups, partials, kGnChunks);
@@ -641,7 +664,9 @@ int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, i
                "groupnorm_apply: bad c=%d groups=%d pgroups=%d chunks=%d", c, groups, pgroups, chunks);
   const int vecs = c / 8;
   const size_t smem2 = (static_cast<size_t>(c) + groups) * 2 * sizeof(float);
-  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
+  int slots = 148 * 8;
+  SBGM_DISPATCH_FMT(fmt, (slots = resident_blocks(reinterpret_cast<const void*>(gn_apply_kernel<FMT>), 256, smem2)));
+  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), slots / max(n, 1)));
   dim3 g2(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, (launch_k((gn_apply_kernel<FMT>), g2, 256, smem2, as_stream(stream), 
                              x, x_plane, partials, chunks, pgroups, gamma, beta, groups, eps, skip, skip_plane, tproj,
