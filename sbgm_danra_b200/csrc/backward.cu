@@ -667,7 +667,9 @@ int sbgm_norm_apply(const void* x, size_t x_plane, const float* stats, int per_s
   const NormArgs a = make_norm_args(x, x_plane, stats, per_sample_stats, groups, gamma, beta, add, add_plane, tproj, tproj_stride,
                                     tproj_pre_act, act, hw, c);
   const int vecs = c / 8;
-  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
+  int slots = 148 * 8;     // one wave of resident blocks (see resident_blocks)
+  SBGM_DISPATCH_FMT(fmt, (slots = resident_blocks(reinterpret_cast<const void*>(norm_apply_kernel<FMT>), 256, 0)));
+  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), slots / max(n, 1)));
   SBGM_REQUIRE(vecs <= 256, "norm_apply: c too large");
   dim3 grid(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, (launch_k((norm_apply_kernel<FMT>), grid, 256, 0, as_stream(stream), a, y, y_plane)));
@@ -701,7 +703,9 @@ int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_
   const int n_groups_total = per_sample_stats == 1 ? n * groups : c;
   if (sums_all == nullptr) { sums_all = sums; n_all = n; }
   const double cnt = per_sample_stats == 1 ? static_cast<double>(hw) * (c / groups) : static_cast<double>(n_all) * hw;
-  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), 148 * 8 / max(n, 1) + 1));
+  int slots = 148 * 8;
+  SBGM_DISPATCH_FMT(fmt, (slots = resident_blocks(reinterpret_cast<const void*>(norm_bwd_apply_kernel<FMT>), 256, 0)));
+  const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), slots / max(n, 1)));
   // enough pixels per thread to amortise the per-block prologue: ~8 per lane
   const int chunks = max(1, min(kNormChunks, hw / (lanes * 8)));
   dim3 g1(chunks, n), g3(per_n_blocks, n);

@@ -33,6 +33,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // SBGM_B200_PDL=0 disables the attribute (the device-side instructions are then no-ops).
 void note_launch_error(cudaError_t e);
 bool pdl_enabled();
+int resident_blocks(const void* kern, int block, size_t smem);   // blocks of `kern` resident at once on the GPU (elementwise.cu)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_grid_sync() {
   // wait only: the dependents are released when this grid's blocks exit (implicit trigger).  Releasing them at the top

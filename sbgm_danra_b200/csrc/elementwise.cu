@@ -513,7 +513,7 @@ __global__ void final_gather_kernel(const float* __restrict__ proj, const float*
 // Blocks of `kern` that are resident at once on the whole GPU.  The GroupNorm apply pass (grid-stride, 48 registers: five
 // blocks per SM) gets at most that many blocks: the fixed cap of 148 x 8 was 1.6 waves, i.e. it paid for two.
 // (The same change left the bilinear upsample, 72 registers, unchanged to slightly slower: not applied there.)
-static int resident_blocks(const void* kern, int block, size_t smem) {
+int resident_blocks(const void* kern, int block, size_t smem) {
   static std::unordered_map<const void*, int> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
