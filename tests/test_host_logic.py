@@ -138,3 +138,20 @@ def test_bn_fold_algebra_on_cpu():
     assert torch.allclose(got, want, atol=1e-5)
     hi_lo = engine._split_bf16(x)
     assert (hi_lo[0].float() + hi_lo[1].float() - x).abs().max() < 2e-5 * x.abs().max()
+
+
+def test_gradients_aliasing_the_flat_buffer_are_detached_before_it_is_rewritten():
+    """score_unet._detach_grads_aliasing: a `.grad` that is a view of the engine's flat gradient buffer gets its own storage
+    (values kept) before the buffer is overwritten; independent gradients and missing gradients are left alone."""
+    from sbgm_danra_b200.score_unet import _detach_grads_aliasing
+    flat = torch.arange(12, dtype=torch.float32)
+    a, b, c = (nn.Parameter(torch.zeros(2, 3)), nn.Parameter(torch.zeros(6)), nn.Parameter(torch.zeros(4)))
+    a.grad = flat[0:6].view(2, 3)
+    own = torch.full((6,), 7.0)
+    b.grad = own
+    _detach_grads_aliasing((a, b, c), flat)
+    flat.zero_()                                   # what the next captured forward does
+    assert torch.equal(a.grad, torch.arange(6, dtype=torch.float32).view(2, 3))
+    assert a.grad.untyped_storage().data_ptr() != flat.untyped_storage().data_ptr()
+    assert b.grad is own and c.grad is None
+    _detach_grads_aliasing((a, b, c), None)        # no captured engine yet: nothing to do
