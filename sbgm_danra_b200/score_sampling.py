@@ -165,8 +165,16 @@ class _NativeStep:
         self.x = torch.zeros((batch, 1, size, size), dtype=torch.float32, device=dev)
         self.score = torch.empty_like(self.x)
         self.mean = torch.empty_like(self.x)
-        self.tproj = torch.empty((batch, eng.tp.c_total), dtype=torch.float32, device=dev)
         self.y = torch.zeros(batch, dtype=torch.int64, device=dev) if has_y else None
+        if has_y:
+            self.tproj_all = None
+            self.tproj = torch.empty((batch, eng.tp.c_total), dtype=torch.float32, device=dev)
+        else:
+            # without labels every member shares the step's time: the projections of ALL steps are computed once per call
+            # (load) and a step only selects its row, broadcast over the batch with a zero row stride
+            self.tproj_all = torch.empty((n_steps, eng.tp.c_total), dtype=torch.float32, device=dev)
+            self.tproj_row = torch.empty((1, eng.tp.c_total), dtype=torch.float32, device=dev)
+            self.tproj = self.tproj_row.expand(batch, eng.tp.c_total)
         self.cfg_scale = cfg_scale
         cc = eng.enc.cin - 1
         self.partial = eng.enc.alloc_partial(planes_batch, size, size) if cc > 0 else None
@@ -175,7 +183,7 @@ class _NativeStep:
             self.y_u = None if self.y is None else torch.zeros_like(self.y)
             self.score_c = torch.empty_like(self.x)
             self.score_u = torch.empty_like(self.x)
-            self.tproj_u = torch.empty_like(self.tproj)
+            self.tproj_u = torch.empty((batch, eng.tp.c_total), dtype=torch.float32, device=dev) if has_y else self.tproj
         self.graph = None
         self.per_replay = 0
 
@@ -199,6 +207,8 @@ class _NativeStep:
         """Rewrite the call-specific contents (step table, seed, labels, conditioning partial sums) in place."""
         self.table.copy_(table)
         self.counter.copy_(torch.tensor(_seed_words(seed), dtype=torch.int32))
+        if self.tproj_all is not None:
+            self.eng.tp(self.table, None, rows=self.table.shape[0], t_row_stride=STEP_COLS, t_step_stride=0, out=self.tproj_all)
         if self.y is not None:
             self.y.copy_(y.to(device=self.dev, dtype=torch.int64).reshape(-1))
         if self.partial is not None:
@@ -208,7 +218,11 @@ class _NativeStep:
 
     def _forward(self, partial, y, tproj, out) -> None:
         eng = self.eng
-        eng.tp(self.table, y, rows=self.b, t_row_stride=0, t_step_stride=STEP_COLS, step_counter=self.counter, out=tproj)
+        if self.tproj_all is not None:
+            call("sbgm_select_step_row", self.tproj_all.data_ptr(), self.tproj_all.shape[1], self.counter.data_ptr(),
+                 self.tproj_row.data_ptr(), _eng._stream())
+        else:
+            eng.tp(self.table, y, rows=self.b, t_row_stride=0, t_step_stride=STEP_COLS, step_counter=self.counter, out=tproj)
         if partial is None:
             fmaps = eng.enc.forward(self.x, None, tproj)
         else:
