@@ -655,3 +655,55 @@ def test_training_step_on_ragged_maps_96x96():
     print(f"96x96 training step: loss {loss.item():.4f} vs {lo.item():.4f}; whole-gradient rel-L2 {whole:.2e}; worst {worst}")
     assert abs(loss.item() - lo.item()) / abs(lo.item()) < 1e-3
     assert whole < 1e-3 and worst[0] < 5e-3
+
+
+def test_reference_epoch_flow_train_validate_generate():
+    """One epoch as the reference's L2 drives it (sbgm/training.py), twice over:
+    `train_batches` (:246-422 -- dataset dict -> extract_samples -> zero_grad -> loss_fn -> backward INSIDE
+    `torch.autograd.detect_anomaly(True)` -> optimizer.step -> .item()), `validate_batches` (:510-580 -- .eval(), loss_fn
+    under `torch.inference_mode()`), then the sampler call of `generate_and_plot_samples` (:683-695 -- keyword arguments,
+    `.squeeze().detach().cpu()`).  The second epoch re-uses whatever the first one cached (engines first built under
+    inference mode are then used outside it)."""
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=2, geo=True, seasons=True)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16x3", DEV)
+    b = synth_batch(batch=4, size=32, n_lr=2, geo=True, seasons=True)
+    samples = {"temp_hr": b.x, "classifier": b.y, "prcp_lr": b.cond_img[:, :1], "temp_lr": b.cond_img[:, 1:],
+               "lsm": b.lsm_cond, "topo": b.topo_cond, "sdf": b.sdf_cond}
+
+    def extract(s):       # utils.extract_samples :405-480 (LR keys sorted and concatenated, everything .to(device).float())
+        f = lambda v: v.to(DEV, non_blocking=True).float()
+        lr = torch.cat([f(s[k]) for k in sorted(k for k in s if k.endswith("_lr"))], dim=1)
+        return f(s["temp_hr"]), s["classifier"].to(DEV, non_blocking=True), lr, f(s["lsm"]), f(s["sdf"]), f(s["topo"])
+
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    score_sampling.manual_seed(5)
+    train_losses, val_losses = [], []
+    for epoch in range(2):
+        net.train()
+        for _ in range(3):
+            x, seasons, cond, lsm, sdf, topo = extract(samples)
+            opt.zero_grad()
+            batch_loss = loss_fn(net, x, marginal_prob_std_fn, y=seasons, cond_img=cond, lsm_cond=lsm, topo_cond=topo, sdf_cond=sdf)
+            with torch.autograd.detect_anomaly(True):
+                batch_loss.backward()
+            opt.step()
+            train_losses.append(batch_loss.item())
+        net.eval()
+        with torch.inference_mode():
+            x, seasons, cond, lsm, sdf, topo = extract(samples)
+            val_losses.append(loss_fn(net, x, marginal_prob_std_fn, y=seasons, cond_img=cond, lsm_cond=lsm, topo_cond=topo,
+                                      sdf_cond=sdf).item())
+        x, seasons, cond, lsm, sdf, topo = extract(samples)
+        for sampler in (score_sampling.pc_sampler, score_sampling.Euler_Maruyama_sampler):
+            gen = sampler(score_model=net, marginal_prob_std=marginal_prob_std_fn, diffusion_coeff=diffusion_coeff_fn,
+                          batch_size=4, num_steps=3, device=DEV, img_size=32, y=seasons, cond_img=cond, lsm_cond=lsm,
+                          topo_cond=topo)
+            gen = gen.squeeze().detach().cpu()
+            assert gen.shape == (4, 32, 32) and torch.isfinite(gen).all()
+    assert all(np.isfinite(train_losses)) and all(np.isfinite(val_losses)), (train_losses, val_losses)
+    grads = [p.grad for p in net.parameters() if p.grad is not None]
+    assert len(grads) > 100 and all(torch.isfinite(g).all() for g in grads)
