@@ -9,7 +9,7 @@ CPU-only container: everything up to the first kernel launch is exercised (modul
 dict, Xavier initialisation through `model.apply`, the `.pth.tar` checkpoint round trip with weights produced by the
 REAL reference classes, `train_batches` walking its batch dict into `loss_fn`), and the launch itself must stop at
 the no-CPU-fallback RuntimeError.  The same loop with the kernels running is
-`test_gpu_train.py::test_reference_train_batches_loop_runs_under_anomaly_mode`.
+`test_gpu_train.py::test_reference_epoch_flow_train_validate_generate`.
 """
 import importlib.util
 import os
@@ -149,3 +149,25 @@ def test_training_pipeline_checkpoint_round_trip_and_loop_reaches_the_kernels(re
         pytest.skip("kernel launch itself is covered by the GPU suite")
     with pytest.raises(RuntimeError, match="CUDA"):
         pipe.train_batches([batch], epochs=1, current_epoch=1, verbose=False)
+
+
+class _Attr(dict):
+    """Attribute-style access over the nested config dict (what OmegaConf gives generation.py)."""
+    def __getattr__(self, k):
+        v = self[k]
+        return _Attr(v) if isinstance(v, dict) else v
+
+
+def test_sample_generator_calls_our_pc_sampler(ref_l2, tmp_path):
+    """generation.SampleGenerator._run_sampler (reference :56-83) reaches this package's pc_sampler with its keyword
+    arguments; on a CPU-only host the call stops at the kernel boundary."""
+    tu, _, gen = ref_l2
+    cfg = _cfg(tmp_path)
+    cfg["paths"]["sample_dir"] = str(tmp_path / "samples")
+    model, _, _ = tu.get_model(cfg)
+    sg = gen.SampleGenerator(_Attr(cfg), model, dataloader=None, back_transforms=None, device="cpu")
+    assert os.path.isdir(sg.sample_path)
+    if torch.cuda.is_available():
+        pytest.skip("kernel launch itself is covered by the GPU suite")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sg._run_sampler(2, torch.tensor([1, 2]), torch.zeros(2, 2, 32, 32), torch.ones(2, 2, 32, 32), torch.ones(2, 2, 32, 32))
