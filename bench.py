@@ -116,7 +116,7 @@ def cpu_em_fields_per_s(members: int, steps: int, threads: int, seed: int = 0):
     extrapolates linearly to the 500-step sampler.  Returns (fields/s, seconds measured)."""
     import torch
     from oracle import samplers_ref, score_ref
-    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
     torch.set_num_threads(threads)
     cfg = config_for(n_lr=N_LR)
     sd = synth_state_dict(cfg, seed)
@@ -197,7 +197,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from oracle.synth import config_for, synth_batch, synth_state_dict      # synthetic weights / inputs only
+    from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
     from sbgm_danra_b200 import _lib, score_sampling as ss
     from sbgm_danra_b200._smoke import build_model
     from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn

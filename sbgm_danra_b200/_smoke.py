@@ -6,7 +6,7 @@ import torch
 
 
 def build_model(cfg, sd, precision: str, device="cuda:0"):
-    """ScoreNet of this package for an `oracle.synth.NetConfig`, loaded with state-dict `sd`."""
+    """ScoreNet of this package for an `synth.NetConfig`, loaded with state-dict `sd`."""
     import torch.nn as nn
     from .score_unet import Decoder, Encoder, ScoreNet, marginal_prob_std_fn
     act = {"relu": nn.ReLU, "silu": nn.SiLU, "gelu": nn.GELU}[cfg.activation]
@@ -22,7 +22,7 @@ def build_model(cfg, sd, precision: str, device="cuda:0"):
 
 def run() -> None:
     from oracle import samplers_ref, score_ref
-    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from .synth import config_for, synth_batch, synth_state_dict
     from . import score_sampling
     from .score_unet import diffusion_coeff_fn, marginal_prob_std_fn
 

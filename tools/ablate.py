@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
 import sys, time, torch
 sys.path.insert(0, %r)
-from oracle.synth import config_for, synth_batch, synth_state_dict
+from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
 from sbgm_danra_b200 import score_sampling as ss
 from sbgm_danra_b200._smoke import build_model
 from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn

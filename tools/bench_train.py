@@ -35,7 +35,7 @@ def main() -> None:
     dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
     from sbgm_danra_b200 import parallel, score_sampling
     from sbgm_danra_b200._smoke import build_model
     from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn

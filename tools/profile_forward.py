@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--top", type=int, default=50)
     a = ap.parse_args()
-    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
     from sbgm_danra_b200._smoke import build_model
     cfg = config_for(n_lr=1)
     net = build_model(cfg, synth_state_dict(cfg), a.precision, "cuda:0")

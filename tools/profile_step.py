@@ -12,7 +12,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from oracle.synth import config_for, synth_batch, synth_state_dict
+from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
 from sbgm_danra_b200 import _lib
 from sbgm_danra_b200._smoke import build_model
 

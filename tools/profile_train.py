@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--top", type=int, default=45)
     a = ap.parse_args()
-    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
     from sbgm_danra_b200 import score_sampling
     from sbgm_danra_b200._smoke import build_model
     from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
