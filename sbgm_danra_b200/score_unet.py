@@ -383,6 +383,28 @@ class ScoreNet(nn.Module):
         cache = self._cache if lane == 0 else self.__dict__.setdefault("_lane_caches", {}).setdefault(lane, _EngineCache())
         return cache.get(self, self.precision, lambda dev: _eng.UNetEngine(self.state_dict(), self.spec(), self.precision, dev))
 
+    # derived device state (packed weights, captured CUDA graphs, gradient exchange): never copied or pickled with the model
+    _DERIVED = ("_cache", "_lane_caches", "_train_runners", "_grad_sync")
+
+    def __deepcopy__(self, memo):
+        """`copy.deepcopy(model)` (the reference's EMA copy, sbgm/training.py:114) copies parameters and buffers only; the copy
+        builds its own engines on first use."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k not in self._DERIVED:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__["_cache"] = _EngineCache()
+        return new
+
+    def __getstate__(self):
+        return {k: v for k, v in self.__dict__.items() if k not in self._DERIVED}
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.__dict__["_cache"] = _EngineCache()
+
     def _bn_modules(self):
         return [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
 

@@ -155,3 +155,26 @@ def test_gradients_aliasing_the_flat_buffer_are_detached_before_it_is_rewritten(
     assert a.grad.untyped_storage().data_ptr() != flat.untyped_storage().data_ptr()
     assert b.grad is own and c.grad is None
     _detach_grads_aliasing((a, b, c), None)        # no captured engine yet: nothing to do
+
+
+def test_deepcopy_and_pickle_leave_device_caches_behind():
+    """`copy.deepcopy(model)` (the reference's EMA copy, sbgm/training.py:114) and whole-model pickles carry parameters and
+    buffers, not the derived device state (packed weights, captured graphs), which is neither copyable nor shareable."""
+    import copy
+    import pickle
+    import threading
+    net = _build(config_for(n_lr=1))
+    net.precision = "bf16"
+    net._cache.key, net._cache.value = "k", threading.Lock()            # stand-ins for engines / CUDA graphs
+    net.__dict__["_train_runners"] = {"cfg": threading.Lock()}
+    net.__dict__["_lane_caches"] = {1: threading.Lock()}
+    net._grad_sync = threading.Lock()
+    for twin in (copy.deepcopy(net), pickle.loads(pickle.dumps(net))):
+        assert twin._cache is not net._cache and twin._cache.key is None and twin._cache.value is None
+        assert "_train_runners" not in twin.__dict__ and "_lane_caches" not in twin.__dict__
+        assert getattr(twin, "_grad_sync", None) is None and twin.precision == "bf16"
+        assert twin.debug_pre_sigma_div == net.debug_pre_sigma_div and twin.training == net.training
+        a, b = net.state_dict(), twin.state_dict()
+        assert list(a) == list(b)
+        assert all(torch.equal(a[k], b[k]) and a[k].data_ptr() != b[k].data_ptr() for k in a)
+    assert net.__dict__["_train_runners"] and net._cache.key == "k"      # the original keeps its own

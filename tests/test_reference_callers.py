@@ -116,12 +116,15 @@ def test_training_pipeline_checkpoint_round_trip_and_loop_reaches_the_kernels(re
     tu, tr, _ = ref_l2
     import sbgm_danra_b200.score_unet as su
     cfg = _cfg(tmp_path)
+    cfg["training"]["with_ema"] = True                       # training.py:114 deep-copies the model
     model, _, _ = tu.get_model(cfg)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     pipe = tr.TrainingPipeline_general(model, su.loss_fn, su.marginal_prob_std_fn, su.diffusion_coeff_fn, opt, "cpu", None, cfg)
     # xavier_init_weights (training.py:188-201) went through model.apply: isinstance(nn.Conv2d) must hit our containers
     assert torch.all(model.decoder.final_layer.conv.bias == 0.01)
     assert model.debug_pre_sigma_div is False
+    assert isinstance(pipe.ema_model, su.ScoreNet) and pipe.ema_model._cache is not model._cache
+    assert torch.equal(pipe.ema_model.encoder.conv1.weight, model.encoder.conv1.weight)
 
     # checkpoint ABI: weights of the REAL reference classes, saved in the reference's format, load strictly
     ref = _real_reference_score_unet()
