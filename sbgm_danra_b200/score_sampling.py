@@ -330,10 +330,13 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
                    0 if planes is None else planes.shape[0], first_elem, total, id(_state.group) if sharded else 0, use_graph)
             st = next((p for k, p in _PLAN_CACHE if k == key), None)
             if st is None:
-                st = _NativeStep(score_model, batch_size, img_size, n_steps, y is not None,
-                                 0 if planes is None else planes.shape[0], scale)
-                st.sumsq = torch.zeros(batch_size, dtype=torch.float32, device=dev)
-                st.sumsq_all = torch.zeros(total, dtype=torch.float32, device=dev) if sharded else st.sumsq
+                # cached across calls and rewritten in place: must be ordinary tensors even when the first caller is inside
+                # torch.inference_mode() (inference tensors cannot be updated in place by a later no_grad caller)
+                with torch.inference_mode(False):
+                    st = _NativeStep(score_model, batch_size, img_size, n_steps, y is not None,
+                                     0 if planes is None else planes.shape[0], scale)
+                    st.sumsq = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+                    st.sumsq_all = torch.zeros(total, dtype=torch.float32, device=dev) if sharded else st.sumsq
                 _PLAN_CACHE.insert(0, (key, st))
                 del _PLAN_CACHE[_PLAN_CACHE_SIZE:]
             st.load(table, seed, y, planes, planes_u)
@@ -401,8 +404,9 @@ def _sample_em_two_lanes(score_model, table, seed, scale, dev, batch_size, n_ste
         key = ("lanes2", id(eng0), id(score_model.engine(1)), batch_size, img_size, n_steps, scale, y is not None, pb, first_elem)
         plan = next((p for k, p in _PLAN_CACHE if k == key), None)
         if plan is None:
-            plan = [_NativeStep(score_model, half, img_size, n_steps, y is not None, min(pb, half) if pb > 1 else pb, scale, lane=l)
-                    for l in range(2)]
+            with torch.inference_mode(False):
+                plan = [_NativeStep(score_model, half, img_size, n_steps, y is not None, min(pb, half) if pb > 1 else pb, scale,
+                                    lane=l) for l in range(2)]
             plan.append({"graph": None, "per_replay": 0, "streams": [torch.cuda.Stream(device=dev) for _ in range(2)]})
             _PLAN_CACHE.insert(0, (key, plan))
             del _PLAN_CACHE[_PLAN_CACHE_SIZE:]

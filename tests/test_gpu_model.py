@@ -407,3 +407,30 @@ def test_back_transforms_match_reference_golden():
     bt = st.build_back_transforms("temp", "zscore", dict(glob_mean=8.69, glob_std=6.19), ["prcp"], ["log_zscore"],
                                   [dict(glob_mean_log=-3.0, glob_std_log=3.6, glob_min_log=None, glob_max_log=None, buffer_frac=0.5)])
     assert set(bt) == {"temp_hr", "generated", "prcp_lr"}
+
+
+@pytest.mark.parametrize("kind", ["em", "pc"])
+def test_sampler_first_called_under_inference_mode_is_reusable_outside_it(kind):
+    """The sampler plan (state buffers + CUDA graph) and the engine are cached across calls.  A first call made inside
+    `torch.inference_mode()` must leave caches that a later ordinary call can rewrite in place: same seed -> same bits."""
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=2, geo=True, seasons=True)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16x3", DEV)
+    b = synth_batch(batch=4, size=32, n_lr=2, geo=True, seasons=True)
+    fn = ss.Euler_Maruyama_sampler if kind == "em" else ss.pc_sampler
+    ss.clear_sampler_cache()
+
+    def run():
+        ss.manual_seed(21)
+        return fn(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=4, num_steps=4, device=DEV, img_size=32,
+                  y=b.y.to(DEV), cond_img=b.cond_img.to(DEV), lsm_cond=b.lsm_cond.to(DEV), topo_cond=b.topo_cond.to(DEV))
+
+    with torch.inference_mode():
+        first = run().clone()
+    second = run()
+    with torch.inference_mode():
+        third = run()
+    assert torch.isfinite(first).all() and torch.equal(first, second) and torch.equal(first, third)
