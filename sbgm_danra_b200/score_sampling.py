@@ -470,11 +470,96 @@ def pc_sampler(score_model, marginal_prob_std, diffusion_coeff, batch_size=64, n
                    img_size, y, cond_img, lsm_cond, topo_cond, cfg)
 
 
+# Dormand-Prince 5(4) tableau (scipy.integrate.RK45: C, A, B and the error weights E = B5 - B4)
+_DP_C = (0.0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0)
+_DP_A = ((), (1 / 5,), (3 / 40, 9 / 40), (44 / 45, -56 / 15, 32 / 9), (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
+         (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656))
+_DP_B = (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84)
+_DP_E = (-71 / 57600, 0.0, 71 / 16695, -71 / 1920, 17253 / 339200, -22 / 525, 1 / 40)
+
+
+def _rk45_resident(fun, t0: float, t_bound: float, y0: torch.Tensor, rtol: float, atol: float):
+    """Adaptive Dormand-Prince 5(4) with the state, the seven stages and the error estimate resident on `y0`'s device.
+
+    Restates the algorithm of the third-party integrator the reference calls (`integrate.solve_ivp(..., method='RK45')`,
+    sbgm/score_sampling.py:296; SciPy 1.18.1: `_ivp/rk.py` rk_step / RungeKutta._step_impl, `_ivp/common.py`
+    select_initial_step, norm = RMS): same initial-step rule, error norm, SAFETY 0.9 / MIN_FACTOR 0.2 / MAX_FACTOR 10 step
+    control and end-point clipping, so the accepted step sequence is SciPy's up to float64 summation order.  Only the scalar
+    error norm crosses to the host (one read per attempted step, it decides accept / reject); SciPy's host version moves
+    the whole float64 state across PCIe twice per right-hand side.  Returns (y at t_bound -- or the last accepted state if
+    the step size underflows, which is what the reference reads from `res.y[:, -1]` -- and the number of `fun` calls)."""
+    import math
+    f64 = dict(dtype=torch.float64, device=y0.device)
+    y = y0.to(torch.float64).reshape(-1).clone()
+    n = y.numel()
+    rtol = max(float(rtol), 100 * np.finfo(float).eps)              # validate_tol
+    direction = 1.0 if t_bound >= t0 else -1.0
+    A = [torch.tensor(a, **f64) for a in _DP_A]
+    B, E = torch.tensor(_DP_B, **f64), torch.tensor(_DP_E, **f64)
+    K = torch.empty((7, n), **f64)
+    nfev = 0
+
+    def rms(v: torch.Tensor) -> float:
+        return float(torch.linalg.vector_norm(v)) / math.sqrt(n)
+
+    def f_at(t: float, yy: torch.Tensor) -> torch.Tensor:
+        nonlocal nfev
+        nfev += 1
+        return fun(t, yy)
+
+    t = float(t0)
+    f = f_at(t, y)
+    # select_initial_step
+    interval = abs(t_bound - t0)
+    if n == 0 or interval == 0.0:
+        return y, nfev
+    scale = atol + y.abs() * rtol
+    d0, d1 = rms(y / scale), rms(f / scale)
+    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    h0 = min(h0, interval)
+    f1 = f_at(t + h0 * direction, y + h0 * direction * f)
+    d2 = rms((f1 - f) / scale) / h0
+    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1 / 5)
+    h_abs = min(100 * h0, h1, interval)
+
+    while direction * (t - t_bound) < 0:
+        min_step = 10 * abs(float(np.nextafter(t, direction * np.inf)) - t)
+        h_abs = max(h_abs, min_step)
+        rejected = False
+        while True:
+            if h_abs < min_step:
+                return y, nfev                                       # TOO_SMALL_STEP: the reference reads the last state
+            t_new = t + h_abs * direction
+            if direction * (t_new - t_bound) > 0:
+                t_new = t_bound
+            h = t_new - t
+            h_abs = abs(h)
+            K[0] = f                                                 # rk_step
+            for s in range(1, 6):
+                K[s] = f_at(t + _DP_C[s] * h, y + torch.mv(K[:s].T, A[s]) * h)
+            y_new = y + h * torch.mv(K[:6].T, B)
+            f_new = f_at(t + h, y_new)
+            K[6] = f_new
+            scale = atol + torch.maximum(y.abs(), y_new.abs()) * rtol
+            err = rms(torch.mv(K.T, E) * h / scale)
+            if err < 1:
+                factor = 10.0 if err == 0 else min(10.0, 0.9 * err ** -0.2)
+                h_abs *= min(1.0, factor) if rejected else factor
+                break
+            h_abs *= max(0.2, 0.9 * err ** -0.2)
+            rejected = True
+        t, y, f = t_new, y_new, f_new
+    return y, nfev
+
+
 def ode_sampler(score_model, marginal_prob_std, diffusion_coeff, num_steps=100, batch_size=64, atol=error_tolerance,
                 rtol=error_tolerance, device="cuda", z=None, eps=1e-3, img_size=64, y=None, cond_img=None,
                 lsm_cond=None, topo_cond=None, cfg=None):
     """Probability-flow ODE through scipy RK45 (score_sampling.py:239-300): the integrator runs on the host
-    in float64 exactly as in the reference; only the score evaluations run on the GPU."""
+    in float64 exactly as in the reference; only the score evaluations run on the GPU.
+
+    `SBGM_B200_ODE=resident` (opt-in) keeps the float64 state on the device and steps it with `_rk45_resident`, the same
+    Dormand-Prince controller without the per-evaluation PCIe round trip of the state."""
     from scipy import integrate
     dev = torch.device(device)
     if z is None:
@@ -495,6 +580,18 @@ def ode_sampler(score_model, marginal_prob_std, diffusion_coeff, num_steps=100, 
         g = float(diffusion_coeff(torch.tensor(t)))
         return -0.5 * (g ** 2) * s.cpu().numpy().reshape(-1).astype(np.float64)
 
+    if os.environ.get("SBGM_B200_ODE", "host") == "resident":
+        def rhs_resident(t, xflat):
+            ts = torch.full((shape[0],), float(t), device=dev, dtype=torch.float32)
+            with torch.no_grad():
+                s = score_model(xflat.to(torch.float32).reshape(shape), ts, y, cond_img, lsm_cond, topo_cond)
+            g = float(diffusion_coeff(torch.tensor(t)))
+            return (-0.5 * (g ** 2)) * s.reshape(-1).to(torch.float64)
+
+        with torch.no_grad():
+            out, nfev = _rk45_resident(rhs_resident, 1.0, eps, init.reshape(-1), rtol, atol)
+        logger.info(f"Number of function evaluations: {nfev}")
+        return out.reshape(shape)
     res = integrate.solve_ivp(rhs, (1.0, eps), init.reshape(-1).cpu().numpy(), rtol=rtol, atol=atol, method="RK45")
     logger.info(f"Number of function evaluations: {res.nfev}")
     return torch.tensor(res.y[:, -1], device=dev).reshape(shape)

@@ -327,6 +327,32 @@ def test_ode_sampler_matches_oracle():
     assert err < 1e-3
 
 
+@pytest.mark.skipif(os.environ.get("SBGM_B200_ODE") != "resident",
+                    reason="opt-in path (SBGM_B200_ODE=resident): integrator pinned to SciPy on the CPU "
+                           "(test_host_logic.py::test_resident_rk45_follows_scipy_step_for_step); device run not yet made")
+def test_ode_sampler_resident_integrator_matches_host_integrator():
+    """SBGM_B200_ODE=resident: the float64 state stays on the device; same Philox start, same score -> the SciPy-driven
+    result to integrator round-off."""
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16x3", DEV)
+    b = synth_batch(batch=2, size=32, n_lr=1, shared_cond=True)
+    outs = {}
+    for mode in ("host", "resident"):
+        os.environ["SBGM_B200_ODE"] = mode
+        try:
+            ss.manual_seed(13)
+            outs[mode] = ss.ode_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=2, atol=1e-3, rtol=1e-3,
+                                        device=DEV, img_size=32, cond_img=b.cond_img.to(DEV)).cpu()
+        finally:
+            os.environ["SBGM_B200_ODE"] = "resident"
+    assert outs["resident"].dtype == outs["host"].dtype == torch.float64
+    assert rel_l2(outs["resident"], outs["host"]) < 1e-5
+
+
 def test_two_lane_em_reproduces_one_lane_bitwise(monkeypatch):
     """SBGM_B200_LANES=2: two half-batches on two streams inside one captured graph; members are independent and the
     Philox stream is keyed by the global element index, so the ensemble must equal the one-lane result bit for bit."""

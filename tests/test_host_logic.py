@@ -178,3 +178,45 @@ def test_deepcopy_and_pickle_leave_device_caches_behind():
         assert list(a) == list(b)
         assert all(torch.equal(a[k], b[k]) and a[k].data_ptr() != b[k].data_ptr() for k in a)
     assert net.__dict__["_train_runners"] and net._cache.key == "k"      # the original keeps its own
+
+
+@pytest.mark.parametrize("tol", [1e-5, 1e-3])
+def test_resident_rk45_follows_scipy_step_for_step(tol):
+    """`score_sampling._rk45_resident` (the opt-in device-resident integrator of ode_sampler) against the integrator the
+    reference calls, `scipy.integrate.solve_ivp(method='RK45')` (sbgm/score_sampling.py:296), on the probability-flow ODE of
+    a Gaussian-mixture-like analytic score, integrated backwards from t=1 to eps as the sampler does: same number of
+    right-hand-side evaluations (= same accepted / rejected step sequence) and the same end state to float64 round-off."""
+    from scipy import integrate
+    from sbgm_danra_b200.score_sampling import _rk45_resident
+    n, sigma, eps = 4096, 25.0, 1e-3
+    g = torch.Generator().manual_seed(3)
+    mu = torch.randn(n, generator=g, dtype=torch.float64)
+    var1 = (sigma ** 2 - 1.0) / (2.0 * np.log(sigma))
+    y0 = torch.randn(n, generator=g, dtype=torch.float64) * np.sqrt(var1)
+
+    def rhs_np(t, y):
+        var = (sigma ** (2 * t) - 1.0) / (2.0 * np.log(sigma))
+        score = -(y - mu.numpy() * np.tanh(y)) / (1.0 + var)
+        return -0.5 * sigma ** (2 * t) * score
+
+    def rhs_t(t, y):
+        var = (sigma ** (2 * t) - 1.0) / (2.0 * np.log(sigma))
+        score = -(y - mu * torch.tanh(y)) / (1.0 + var)
+        return -0.5 * sigma ** (2 * t) * score
+
+    res = integrate.solve_ivp(rhs_np, (1.0, eps), y0.numpy(), rtol=tol, atol=tol, method="RK45")
+    got, nfev = _rk45_resident(rhs_t, 1.0, eps, y0, tol, tol)
+    assert res.status == 0 and nfev == res.nfev, (nfev, res.nfev)
+    want = torch.from_numpy(res.y[:, -1])
+    assert got.dtype == torch.float64 and float((got - want).abs().max() / want.abs().max()) < 1e-11
+
+
+def test_resident_rk45_edge_cases():
+    from sbgm_danra_b200.score_sampling import _rk45_resident
+    y0 = torch.ones(8, dtype=torch.float64)
+    out, nfev = _rk45_resident(lambda t, y: -y, 0.5, 0.5, y0, 1e-6, 1e-6)          # empty interval
+    assert torch.equal(out, y0) and nfev == 1
+    out, nfev = _rk45_resident(lambda t, y: torch.zeros_like(y), 1.0, 0.0, y0, 1e-6, 1e-6)   # zero field: error norm 0 path
+    assert torch.equal(out, y0)
+    out, _ = _rk45_resident(lambda t, y: -y, 0.0, 1.0, y0, 1e-8, 1e-8)            # forward direction
+    assert float((out - np.exp(-1.0)).abs().max()) < 1e-7
