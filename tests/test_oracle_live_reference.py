@@ -92,3 +92,50 @@ def test_oracle_dsm_loss_and_gradients_equal_live_reference(ref_unet):
         assert rel_l2(sd[k].grad, p.grad) < 1e-3, k
         checked += 1
     assert checked > 150
+
+
+@pytest.fixture(scope="module")
+def ref_samp():
+    spec = importlib.util.spec_from_file_location("_ref_score_sampling_live", os.path.join(REF, "sbgm", "score_sampling.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("kind", ["em", "pc"])
+def test_oracle_samplers_equal_live_reference_samplers(ref_unet, ref_samp, kind):
+    """The UNPATCHED reference samplers at 32x32 (where Euler_Maruyama_sampler's hard-coded initial shape is right,
+    score_sampling.py:94) against oracle.samplers_ref with `noise=None`: both draw from torch's global generator at the same
+    places, so the same seed gives the same trajectory."""
+    from oracle import samplers_ref
+    ck, bk = CASES["cin7_seasons_gn4_relu"]
+    cfg = config_for(**ck)
+    net = _reference(ref_unet, cfg, seed=2).eval()
+    sd = synth_state_dict(cfg, 2)
+    b = synth_batch(seed=55, **bk)
+    kw = dict(batch_size=3, num_steps=5, device="cpu", img_size=32, y=b.y, cond_img=b.cond_img, lsm_cond=b.lsm_cond,
+              topo_cond=b.topo_cond)
+    score = lambda x, t: score_ref.score_forward(sd, cfg, x, t, b.y, b.cond_img, b.lsm_cond, b.topo_cond)
+    torch.manual_seed(123)
+    if kind == "em":
+        want = ref_samp.Euler_Maruyama_sampler(net, ref_unet.marginal_prob_std_fn, ref_unet.diffusion_coeff_fn, **kw)
+    else:
+        want = ref_samp.pc_sampler(net, ref_unet.marginal_prob_std_fn, ref_unet.diffusion_coeff_fn, snr=0.16, **kw)
+    torch.manual_seed(123)
+    fn = samplers_ref.euler_maruyama if kind == "em" else samplers_ref.predictor_corrector
+    got = fn(score, score_ref.marginal_prob_std, score_ref.diffusion_coeff, 3, 5, img_size=32)
+    assert want.shape == (3, 1, 32, 32) and rel_l2(got, want) < 1e-4
+
+
+def test_oracle_guided_score_equals_live_reference(ref_unet, ref_samp):
+    from oracle import samplers_ref
+    ck, bk = CASES["cin7_seasons_gn4_relu"]
+    cfg = config_for(**ck)
+    net = _reference(ref_unet, cfg, seed=2).eval()
+    sd = synth_state_dict(cfg, 2)
+    b = synth_batch(seed=56, **bk)
+    with torch.no_grad():
+        want = ref_samp.guided_score_fn(net, b.x, b.t, b.y, b.cond_img, b.lsm_cond, b.topo_cond, scale=1.5)
+        got = samplers_ref.guided_score(lambda *a: score_ref.score_forward(sd, cfg, *a), b.x, b.t, b.y, b.cond_img, b.lsm_cond,
+                                        b.topo_cond, scale=1.5)
+    assert rel_l2(got, want) < 2e-5
