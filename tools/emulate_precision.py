@@ -7,6 +7,7 @@ layers are re-run with their operands rounded as the tensor core would see them 
 score is compared with the unrounded fp32 oracle, on the shapes of the golden cases.
 
     python tools/emulate_precision.py [--size 64] [--batch 2]
+    python tools/emulate_precision.py --sampler          # ensemble mean / std / CRPS of a 40-step EM run per format
 
 Calibration: the `bf16` and `bf16x3` rows must reproduce what the kernels measure on the GPU (6.6e-3 and 1.1e-5 in
 README.md); the other rows are predictions.  The time projections (2-D Linear inputs) and the final 64->1 convolution stay
@@ -110,5 +111,43 @@ def main():
                 print(f"  {cname:14s} {mode:52s} products {products!s:15s} rel-L2 {err:.2e}")
 
 
+def sampler_statistics(members: int = 16, size: int = 32, steps: int = 40, seed: int = 99):
+    """The second parity criterion (BASELINE.json: sampled-ensemble pixel-wise mean / std and CRPS within 1 %) for each
+    emulated format: Euler-Maruyama on the same Philox noise as tests/test_gpu_model.py's ensemble test, statistics against
+    the fp32 oracle's ensemble."""
+    import numpy as np
+    from oracle import samplers_ref, score_ref
+    from oracle.ensemble_ref import ensemble_statistics
+    from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
+    cfg = config_for(n_lr=1)
+    sd = synth_state_dict(cfg)
+    b = synth_batch(batch=members, size=size, n_lr=1, shared_cond=True)
+    truth = synth_batch(batch=1, size=size, n_lr=1, seed=77).x[0, 0].numpy()
+
+    def run():
+        score = lambda x, t: score_ref.score_forward(sd, cfg, x, t, None, b.cond_img)
+        with torch.no_grad():
+            out = samplers_ref.euler_maruyama(score, score_ref.marginal_prob_std, score_ref.diffusion_coeff, members, steps,
+                                              img_size=size, noise=samplers_ref.philox_noise(seed))
+        return ensemble_statistics(out[:, 0].numpy(), truth)
+
+    want = run()
+    print(f"EM ensemble ({members} members, {size}x{size}, {steps} steps, same noise): field rel-L2 of mean / std / CRPS vs the "
+          f"fp32 oracle (gate 1e-2)")
+    for mode in MODES:
+        saved = score_ref.F
+        score_ref.F = emulated_functional(mode)
+        try:
+            got = run()
+        finally:
+            score_ref.F = saved
+        rel = {k: np.linalg.norm(got[k] - want[k]) / np.linalg.norm(want[k]) for k in ("mean", "std", "crps")}
+        print(f"  {mode:52s} mean {rel['mean']:.2e}  std {rel['std']:.2e}  crps {rel['crps']:.2e}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--sampler" in sys.argv:
+        sys.argv.remove("--sampler")
+        sampler_statistics()
+    else:
+        main()
