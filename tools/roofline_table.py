@@ -7,7 +7,7 @@ once; weights once), and the time each bound allows at the MEASURED peaks of thi
 sustained bf16 tensor throughput, HBM copy bandwidth).  The sum is the floor the measured evaluation time is compared with
 in DESIGN.md: how far the whole path -- not just the dominant kernel -- is from the machine.
 
-    python tools/roofline_table.py [--size 128] [--cin 2] [--batch 64] [--precision bf16x3|bf16|fp16w2] [--measured-ms 1.63]
+    python tools/roofline_table.py [--size 128] [--cin 2] [--batch 64] [--precision bf16x3|bf16|fp16w2] [--measured-ms 1.63] [--train]
 """
 from __future__ import annotations
 
@@ -82,6 +82,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp16w2"])
     ap.add_argument("--measured-ms", type=float, default=None)
+    ap.add_argument("--train", action="store_true",
+                    help="DSM training step: forward + data gradient + weight gradient = 3x the contraction FLOPs; every\n"
+                         "operator's backward re-reads its input and the incoming gradient and writes one gradient: ~3x the bytes")
     args = ap.parse_args()
     peaks = {"bf16_tflops_sustained": 1399.7, "hbm_gbs": 6547.8}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -92,8 +95,8 @@ def main():
     tot = {"flops": 0.0, "t_tc": 0.0, "t_bw": 0.0, "floor": 0.0, "bytes": 0.0}
     print(f"{'operator':44s} {'GFLOP':>8s} {'MB':>8s} {'tensor us':>10s} {'HBM us':>8s}  bound")
     for name, kind, fl, rd, wr, wt in layers(args.size, args.cin, bytes_per):
-        flops = fl * args.batch
-        nbytes = (rd + wr) * args.batch * bytes_per + wt * bytes_per
+        flops = fl * args.batch * (3 if args.train else 1)
+        nbytes = ((rd + wr) * args.batch * bytes_per + wt * bytes_per) * (3 if args.train else 1)
         t_tc = (flops * products / (peaks["bf16_tflops_sustained"] * 1e12) * 1e6) if kind == "tc" else 0.0
         t_bw = nbytes / (peaks["hbm_gbs"] * 1e9) * 1e6
         bound = "tensor" if t_tc > t_bw else "hbm"
@@ -101,11 +104,11 @@ def main():
         print(f"{name:44s} {flops / 1e9:8.2f} {nbytes / 1e6:8.1f} {t_tc:10.1f} {t_bw:8.1f}  {bound}")
     print(f"{'TOTAL':44s} {tot['flops'] / 1e9:8.2f} {tot['bytes'] / 1e6:8.1f} {tot['t_tc']:10.1f} {tot['t_bw']:8.1f}")
     print(f"algorithmic FLOPs per sample: {tot['flops'] / args.batch / 1e9:.3f} G (SURVEY section 2.2: 5.146 G at 128x128, Cin 2)")
-    print(f"floor = sum over operators of max(tensor, HBM) = {tot['floor'] / 1e3:.3f} ms per evaluation "
+    print(f"floor = sum over operators of max(tensor, HBM) = {tot['floor'] / 1e3:.3f} ms per {'training step (fwd + bwd, optimizer excluded)' if args.train else 'evaluation'} "
           f"({args.precision}: {products} tensor product(s) per algorithmic product, {bytes_per} B per activation element; "
           f"peaks {peaks['bf16_tflops_sustained']:.0f} TFLOP/s sustained bf16, {peaks['hbm_gbs']:.0f} GB/s)")
     if args.measured_ms:
-        print(f"measured {args.measured_ms:.3f} ms per evaluation -> {tot['floor'] / 1e3 / args.measured_ms:.0%} of the floor's speed")
+        print(f"measured {args.measured_ms:.3f} ms per {'step' if args.train else 'evaluation'} -> {tot['floor'] / 1e3 / args.measured_ms:.0%} of the floor's speed")
 
 
 if __name__ == "__main__":
