@@ -41,3 +41,11 @@ def rel_l2(a, b):
     a = torch.as_tensor(a, dtype=torch.float64).reshape(-1)
     b = torch.as_tensor(b, dtype=torch.float64).reshape(-1)
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def free_port() -> int:
+    """A TCP port that is free right now on 127.0.0.1 (rendezvous port of the gloo multi-process tests)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:
+        sock.bind(("127.0.0.1", 0))
+        return sock.getsockname()[1]

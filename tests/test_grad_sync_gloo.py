@@ -63,7 +63,8 @@ def _worker(rank, world, port, ret):
 
 def test_two_rank_bucketed_allreduce_averages_gradients():
     world = 2
-    port = 29500 + (os.getpid() % 2000) + 7
+    from conftest import free_port
+    port = free_port()
     with mp.Manager() as m:
         ret = m.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
