@@ -37,6 +37,10 @@ METRIC = "EM-sampled 128x128 fields/sec"
 UNIT = "fields/s"
 SIZE, MEMBERS, EM_STEPS, N_LR = 128, 64, 500, 1
 FWD_FLOP = 5.146e9            # per sample per forward at 128x128, Cin = 2
+DTYPE_NAMES = {"bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate; fp32-class)",
+               "fp16x2": "fp16x2 (float16 activations x float16 hi|lo weights, fp32 accumulate; fp32-class: score rel-L2 < 1e-3)",
+               "bf16": "bf16", "fp32": "f32"}
+TENSOR_PRODUCTS = {"bf16x3": 3.0, "fp16x2": 2.0, "bf16": 1.0, "fp32": 1.0}     # tensor-core products per algorithmic product
 
 
 def _config(args, world):
@@ -263,7 +267,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate; fp32-class)", "bf16": "bf16", "fp32": "f32"}[args.precision],
+        "dtype": DTYPE_NAMES[args.precision],
         "data": "synthetic", "config": _config(args, world),
         "e2e": {"value": fields / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": cond_host.numel() * 4,
                 "d2h_bytes_per_step": out_host.numel() * 4},
@@ -273,7 +277,7 @@ def run_ours(args):
                      "frac": achieved / peaks["bf16_tflops"], "traffic": load_traffic(),
                      "kernel": "conv3x3_c64_kernel (persistent tcgen05 implicit GEMM, projection epilogue) on decoder.final_layer.conv_up 64->64 3x3 @128x128 x64",
                      "kernel_ms": kms, "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", burst bf16",
-                     "tensor_pipe_frac": (3.0 if args.precision == "bf16x3" else 1.0) * achieved / peaks["bf16_tflops"],
+                     "tensor_pipe_frac": TENSOR_PRODUCTS[args.precision] * achieved / peaks["bf16_tflops"],
                      "note": "achieved/frac count ALGORITHMIC FLOPs; bf16x3 issues 3 bf16 tensor-core products per algorithmic "
                              "product, so the tensor pipe is busy tensor_pipe_frac of the measured bf16 peak"},
         "unet_fwd_tflops": fwd_tflops, "unet_fwd_frac_of_sustained_bf16": fwd_tflops / peaks["bf16_tflops_sustained"],
@@ -296,7 +300,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16x2", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -10,13 +10,19 @@
  *   - every pointer is a DEVICE pointer unless its name ends in _host; `stream` is a cudaStream_t
  *   - all functions are asynchronous on `stream` and return 0 on success, non-zero on failure
  *     (sbgm_last_error() gives the message); nothing here falls back to the CPU
- *   - activations are NHWC ("pixels x channels"), C % 8 == 0, in one of three storage formats:
+ *   - activations are NHWC ("pixels x channels"), C % 8 == 0, in one of four storage formats:
  *       SBGM_FMT_F32     float32
  *       SBGM_FMT_BF16    bfloat16
  *       SBGM_FMT_BF16X2  two bfloat16 planes hi|lo with x ~= hi + lo (16 significant bits);
  *                        the lo plane starts `plane` elements after the hi plane.  Tensor-core
  *                        products use hi*hi + lo*hi + hi*lo, i.e. fp32-class accuracy at
  *                        bf16 tensor throughput / 3.
+ *       SBGM_FMT_F16     ONE float16 plane (11 significant bits, saturating stores).  Tensor-core layers in
+ *                        this format take their WEIGHTS as two float16 planes  w_hi | w_lo * 2^11  (22
+ *                        significant bits; `w_plane` = distance between them): the product is
+ *                        x * w_hi + 2^-11 (x * w_lo') -- two tensor-core products, one activation plane --
+ *                        so the only rounding left is the activations' (score rel-L2 2-5e-4 against the
+ *                        reference's fp32, inside the 1e-3 gate; "fp16x2" in the Python API).  Inference only.
  *   - `plane` arguments are the hi->lo plane distance in elements (ignored unless BF16X2)
  */
 #ifndef SBGM_B200_H_
@@ -29,7 +35,8 @@
 extern "C" {
 #endif
 
-enum { SBGM_FMT_F32 = 0, SBGM_FMT_BF16 = 1, SBGM_FMT_BF16X2 = 2 };
+enum { SBGM_FMT_F32 = 0, SBGM_FMT_BF16 = 1, SBGM_FMT_BF16X2 = 2, SBGM_FMT_F16 = 3 };
+#define SBGM_F16_WLO_SCALE 2048.0f   /* w_lo plane of an F16-format weight is stored times 2^11 (kept normal in float16) */
 enum { SBGM_ACT_NONE = 0, SBGM_ACT_RELU = 1, SBGM_ACT_SILU = 2, SBGM_ACT_GELU = 3 };
 
 const char* sbgm_last_error(void);

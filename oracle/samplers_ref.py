@@ -76,8 +76,10 @@ def euler_maruyama(score: ScoreFn, marginal_prob_std, diffusion_coeff, batch_siz
 
 def predictor_corrector(score: ScoreFn, marginal_prob_std, diffusion_coeff, batch_size: int, num_steps: int,
                         snr: float = 0.16, eps: float = 1e-3, img_size: int = 64, noise: NoiseFn = None,
-                        device="cpu", trajectory: Optional[list] = None) -> torch.Tensor:
-    """score_sampling.py:136-230."""
+                        device="cpu", trajectory: Optional[list] = None, score_predictor: Optional[ScoreFn] = None) -> torch.Tensor:
+    """score_sampling.py:136-230.  `score_predictor`: the score of the predictor half when it differs from the corrector's
+    (classifier-free guidance with guidance_scale_max: the corrector clamps the scale :182-186, the predictor does not
+    :209-219)."""
     t = torch.ones(batch_size, device=device)
     shape = (batch_size, 1, img_size, img_size)
     z0 = torch.randn(shape, device=device) if noise is None else noise(philox_ref.DRAW_INIT, shape).to(device)
@@ -94,7 +96,7 @@ def predictor_corrector(score: ScoreFn, marginal_prob_std, diffusion_coeff, batc
             ls = 2 * (snr * noise_norm / grad_norm) ** 2
             x = x + ls * grad + torch.sqrt(2 * ls) * _draw(noise, philox_ref.draw_pc_corrector(k), x)
             g = diffusion_coeff(bt)
-            s = score(x, bt)
+            s = (score_predictor or score)(x, bt)
             x_mean = x + (g ** 2)[:, None, None, None] * s * dt
             x = x_mean + torch.sqrt(g ** 2 * dt)[:, None, None, None] * _draw(noise, philox_ref.draw_pc_predictor(k), x)
             if trajectory is not None:

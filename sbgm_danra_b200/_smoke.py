@@ -33,7 +33,7 @@ def run() -> None:
     b = synth_batch(batch=2, size=64, n_lr=1, shared_cond=True)
     with torch.no_grad():
         ref = score_ref.score_forward(sd, cfg, *b.model_args())
-    for precision, tol in (("fp32", 1e-4), ("bf16x3", 1e-3), ("bf16", 5e-2)):
+    for precision, tol in (("fp32", 1e-4), ("bf16x3", 1e-3), ("fp16x2", 1e-3), ("bf16", 2e-2)):
         net = build_model(cfg, sd, precision, dev)
         with torch.no_grad():
             out = net(b.x.to(dev), b.t.to(dev), None, b.cond_img.to(dev)).cpu()

@@ -24,7 +24,24 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// operand element type of the format: bfloat16 (one plane or hi|lo) or float16 (one plane, 11 significant bits)
+template <int FMT>
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (FMT == SBGM_FMT_F16) mma_f16_16816(c, a, b0, b1); else mma_bf16_16816(c, a, b0, b1);
+}
+template <int FMT>
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  if (FMT == SBGM_FMT_F16) {
+    hi = pack_f16x2(x, y);
+    lo = 0u;
+    return;
+  }
   const float xh = bf16_round(x), yh = bf16_round(y);
   hi = pack_bf16x2(xh, yh);
   lo = pack_bf16x2(x - xh, y - yh);
@@ -35,7 +52,8 @@ __global__ void __launch_bounds__(128)
 attention_mma_kernel(const void* __restrict__ qkv, size_t plane, void* __restrict__ out, size_t out_plane, int s, int c, int heads,
                      float scale) {
   pdl_grid_sync();
-  constexpr bool kLo = (FMT != SBGM_FMT_BF16);      // second (lo) operand planes
+  constexpr bool kLo = (FMT == SBGM_FMT_BF16X2);    // second (lo) operand planes
+  using TF = TcFmt<FMT>;
   constexpr int kPlanes = kLo ? 2 : 1;
   constexpr int KP = D + 8;                         // row pitch of Q / K tiles (bf16 elements)
   constexpr int VP = kMmaKeys + 8;                  // row pitch of the transposed V tile
@@ -59,10 +77,10 @@ attention_mma_kernel(const void* __restrict__ qkv, size_t plane, void* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float x = v[j] * scale;
-      hi[j] = bf16_round(x);
+      hi[j] = TF::round(x);
       lo[j] = x - hi[j];
     }
-    *reinterpret_cast<uint4*>(qs + qi * KP + vec * 8) = pack_bf16x8(hi);
+    *reinterpret_cast<uint4*>(qs + qi * KP + vec * 8) = TF::pack8(hi);
     if (kLo) *reinterpret_cast<uint4*>(qs + (kMmaQ + qi) * KP + vec * 8) = pack_bf16x8(lo);
   }
   __syncthreads();
@@ -98,13 +116,17 @@ attention_mma_kernel(const void* __restrict__ qkv, size_t plane, void* __restric
       float hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        hi[j] = bf16_round(kv[j]);
+        hi[j] = TF::round(kv[j]);
         lo[j] = kv[j] - hi[j];
       }
-      *reinterpret_cast<uint4*>(ks + kj * KP + vec * 8) = pack_bf16x8(hi);
+      *reinterpret_cast<uint4*>(ks + kj * KP + vec * 8) = TF::pack8(hi);
       if (kLo) *reinterpret_cast<uint4*>(ks + (kMmaKeys + kj) * KP + vec * 8) = pack_bf16x8(lo);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        if (FMT == SBGM_FMT_F16) {      // same 16-bit slots, float16 bit patterns
+          reinterpret_cast<__half*>(vt)[(vec * 8 + j) * VP + kj] = __float2half_rn(vv[j]);
+          continue;
+        }
         const float vh = bf16_round(vv[j]);
         vt[(vec * 8 + j) * VP + kj] = __float2bfloat16_rn(vh);
         if (kLo) vt[(D + vec * 8 + j) * VP + kj] = __float2bfloat16_rn(vv[j] - vh);
@@ -122,7 +144,7 @@ attention_mma_kernel(const void* __restrict__ qkv, size_t plane, void* __restric
       for (int kk = 0; kk < D / 16; ++kk) {
         const __nv_bfloat16* kp = ks + (nt * 8 + g) * KP + kk * 16 + t4 * 2;
         const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(kp), bh1 = *reinterpret_cast<const uint32_t*>(kp + 8);
-        mma_bf16_16816(sc[nt], qa[0][kk], bh0, bh1);
+        mma_16816<FMT>(sc[nt], qa[0][kk], bh0, bh1);
         if (kLo) {
           const __nv_bfloat16* kl = kp + kMmaKeys * KP;
           mma_bf16_16816(sc[nt], qa[0][kk], *reinterpret_cast<const uint32_t*>(kl), *reinterpret_cast<const uint32_t*>(kl + 8));
@@ -161,15 +183,15 @@ attention_mma_kernel(const void* __restrict__ qkv, size_t plane, void* __restric
 #pragma unroll
     for (int kk = 0; kk < kMmaKeys / 16; ++kk) {
       uint32_t ph[4], pl[4];
-      split2(sc[2 * kk][0], sc[2 * kk][1], ph[0], pl[0]);
-      split2(sc[2 * kk][2], sc[2 * kk][3], ph[1], pl[1]);
-      split2(sc[2 * kk + 1][0], sc[2 * kk + 1][1], ph[2], pl[2]);
-      split2(sc[2 * kk + 1][2], sc[2 * kk + 1][3], ph[3], pl[3]);
+      split2<FMT>(sc[2 * kk][0], sc[2 * kk][1], ph[0], pl[0]);
+      split2<FMT>(sc[2 * kk][2], sc[2 * kk][3], ph[1], pl[1]);
+      split2<FMT>(sc[2 * kk + 1][0], sc[2 * kk + 1][1], ph[2], pl[2]);
+      split2<FMT>(sc[2 * kk + 1][2], sc[2 * kk + 1][3], ph[3], pl[3]);
 #pragma unroll
       for (int dt = 0; dt < D / 8; ++dt) {
         const __nv_bfloat16* vp = vt + (dt * 8 + g) * VP + kk * 16 + t4 * 2;
         const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(vp), bh1 = *reinterpret_cast<const uint32_t*>(vp + 8);
-        mma_bf16_16816(o[dt], ph, bh0, bh1);
+        mma_16816<FMT>(o[dt], ph, bh0, bh1);
         if (kLo) {
           const __nv_bfloat16* vl = vp + D * VP;
           mma_bf16_16816(o[dt], ph, *reinterpret_cast<const uint32_t*>(vl), *reinterpret_cast<const uint32_t*>(vl + 8));
@@ -205,7 +227,7 @@ attention_mma_kernel(const void* __restrict__ qkv, size_t plane, void* __restric
 template <int FMT, int D>
 static int launch_attention_mma(const void* qkv, size_t plane, void* out, size_t out_plane, int b, int s, int c, int heads,
                                 cudaStream_t st) {
-  constexpr int kPlanes = (FMT != SBGM_FMT_BF16) ? 2 : 1;
+  constexpr int kPlanes = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   const size_t tiles = static_cast<size_t>(kPlanes) * (2 * kMmaQ * (D + 8) + D * (kMmaKeys + 8)) * sizeof(__nv_bfloat16);
   const size_t stage = static_cast<size_t>(kMmaQ) * (D + 4) * sizeof(float);
   const size_t smem = tiles > stage ? tiles : stage;
@@ -236,6 +258,10 @@ int attention_mma_dispatch(const void* qkv, size_t plane, void* out, size_t out_
     if (d == 32) SBGM_AM(SBGM_FMT_BF16, 32);
     if (d == 64) SBGM_AM(SBGM_FMT_BF16, 64);
     if (d == 128) SBGM_AM(SBGM_FMT_BF16, 128);
+  } else if (fmt == SBGM_FMT_F16) {
+    if (d == 32) SBGM_AM(SBGM_FMT_F16, 32);
+    if (d == 64) SBGM_AM(SBGM_FMT_F16, 64);
+    if (d == 128) SBGM_AM(SBGM_FMT_F16, 128);
   }
 #undef SBGM_AM
   return -1;

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -137,12 +138,61 @@ struct Act<SBGM_FMT_BF16X2> {
   }
 };
 
+// float16 plane.  Stores saturate to +-65504 (cvt.rn.satfinite): an activation outside the float16 range clamps instead of
+// becoming inf -> NaN three layers later; everything behind a normalisation layer is O(10).
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));     // low half = a
+  return r;
+}
+__device__ __forceinline__ uint4 pack_f16x8(const float (&v)[8]) {
+  return make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack_f16x8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ float f16_round(float a) {
+  const uint32_t p = pack_f16x2(a, 0.0f);
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(p & 0xffffu)));
+}
+
+template <>
+struct Act<SBGM_FMT_F16> {
+  static constexpr int kElemBytes = 2;
+  __device__ __forceinline__ static void load8(const void* base, size_t, size_t idx, float (&v)[8]) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(base) + idx));
+    unpack_f16x8(u, v);
+  }
+  __device__ __forceinline__ static void store8(void* base, size_t, size_t idx, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(static_cast<__half*>(base) + idx) = pack_f16x8(v);
+  }
+};
+
+// Storage traits of the tensor-core formats: activation planes, weight planes, element rounding / packing.
+template <int FMT>
+struct TcFmt {
+  static constexpr int kAPlanes = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;                        // activation planes
+  static constexpr int kBPlanes = (FMT == SBGM_FMT_BF16X2 || FMT == SBGM_FMT_F16) ? 2 : 1;  // weight planes
+  static constexpr bool kHalf = (FMT == SBGM_FMT_F16);                                     // float16 (else bfloat16) elements
+  // factor of the second weight plane's product when the accumulator halves are summed
+  static constexpr float kLoScale = kHalf ? (1.0f / SBGM_F16_WLO_SCALE) : 1.0f;
+  __device__ __forceinline__ static float round(float x) { return kHalf ? f16_round(x) : bf16_round(x); }
+  __device__ __forceinline__ static uint4 pack8(const float (&v)[8]) { return kHalf ? pack_f16x8(v) : pack_bf16x8(v); }
+};
+
 // Dispatch a templated launcher on the runtime format id.
 #define SBGM_DISPATCH_FMT(fmt, ...)                                         \
   switch (fmt) {                                                             \
     case SBGM_FMT_F32: { constexpr int FMT = SBGM_FMT_F32; __VA_ARGS__; break; }       \
     case SBGM_FMT_BF16: { constexpr int FMT = SBGM_FMT_BF16; __VA_ARGS__; break; }     \
     case SBGM_FMT_BF16X2: { constexpr int FMT = SBGM_FMT_BF16X2; __VA_ARGS__; break; } \
+    case SBGM_FMT_F16: { constexpr int FMT = SBGM_FMT_F16; __VA_ARGS__; break; }       \
     default: ::sbgm::set_error("unknown activation format %d", fmt); return 1;          \
   }
 

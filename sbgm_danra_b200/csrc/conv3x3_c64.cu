@@ -41,9 +41,10 @@ struct C64Params {
 
 template <int FMT, int kStages>
 struct C64Cfg {
-  static constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
-  static constexpr uint32_t kWeightBytes = 9 * kSplit * kWTapBytes;
-  static constexpr uint32_t kStageBytes = kSplit * kSlabBytes;
+  static constexpr int kAPl = TcFmt<FMT>::kAPlanes;      // activation planes (2: split-bf16)
+  static constexpr int kBPl = TcFmt<FMT>::kBPlanes;      // weight planes (2: hi|lo, one N = 128 MMA covers both)
+  static constexpr uint32_t kWeightBytes = 9 * kBPl * kWTapBytes;
+  static constexpr uint32_t kStageBytes = kAPl * kSlabBytes;
   static constexpr uint32_t kBarOffset = kWeightBytes + kStages * kStageBytes;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;
 };
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(320, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const C64Params p) {
   pdl_grid_sync();
   using Cfg = C64Cfg<FMT, kStages>;
-  constexpr int kSplit = Cfg::kSplit;
+  constexpr int kAPl = Cfg::kAPl, kBPl = Cfg::kBPl;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base;                              // [tap][plane][64 x 128 B]
@@ -82,7 +83,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     fence_barrier_init();
   }
-  constexpr uint32_t kAccCols = 64u * kSplit;     // split mode keeps x_hi*w_lo in a second 64-column half
+  constexpr uint32_t kAccCols = 64u * kBPl;       // two weight planes keep x*w_lo in a second 64-column half
   if (warp == 1) tmem_alloc(tmem_slot, 2 * kAccCols);
   tcgen05_fence_before();
   __syncthreads();
@@ -94,8 +95,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       // weights: 9 taps x planes boxes of 64 rows x 64 k
       mbar_expect_tx(w_bar, Cfg::kWeightBytes);
       for (int tap = 0; tap < 9; ++tap)
-        for (int pl = 0; pl < kSplit; ++pl)
-          tma_load_3d(w_base + (tap * kSplit + pl) * kWTapBytes, &tmap_b, w_bar, tap * 64, 0, pl);
+        for (int pl = 0; pl < kBPl; ++pl)
+          tma_load_3d(w_base + (tap * kBPl + pl) * kWTapBytes, &tmap_b, w_bar, tap * 64, 0, pl);
       uint32_t sidx = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
@@ -103,8 +104,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int stage = sidx % kStages;
           const uint32_t phase = (sidx / kStages) & 1u;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), kSplit * kSlabTxBytes);
-          for (int pl = 0; pl < kSplit; ++pl)
+          mbar_expect_tx(full_bar(stage), kAPl * kSlabTxBytes);
+          for (int pl = 0; pl < kAPl; ++pl)
             tma_load_5d(slab_base + stage * Cfg::kStageBytes + pl * kSlabBytes, &tmap_a, full_bar(stage), half * 32,
                         tw * kTW - 1, th * kTH - 1, n, pl);
         }
@@ -114,7 +115,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // one elected lane runs the whole issue loop: ncu showed the warp-uniform variant (election + predicate vote +
     // descriptor moves to uniform registers for every MMA, ~13.5 instructions each) issue-bound, not data-bound
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(64), idesc2 = make_idesc(128);
+      constexpr uint32_t idesc = make_idesc(64, TcFmt<FMT>::kHalf), idesc2 = make_idesc(64 * kBPl, TcFmt<FMT>::kHalf);
       mbar_wait(w_bar, 0);
       const uint64_t w_desc = (static_cast<uint64_t>(kDescHi) << 32) | desc_lo(w_base);
       const uint64_t a_desc0 = (static_cast<uint64_t>(kDescHiSlab) << 32) | desc_lo(slab_base);
@@ -137,16 +138,12 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               for (int k = 0; k < 2; ++k) {            // two K = 16 steps per 32-channel half
                 // tap (r, s): the 128 A rows start at slab pixel (r, s); row groups (output rows) are one slab row apart
                 const uint64_t a_d = a_unit + (((r * kSlabW + s) * 64 + k * 32) >> 4);
-                const uint64_t b_d = w_desc + ((((r * 3 + s) * kSplit) * kWTapBytes + (half * 2 + k) * 32) >> 4);
+                const uint64_t b_d = w_desc + ((((r * 3 + s) * kBPl) * kWTapBytes + (half * 2 + k) * 32) >> 4);
                 const bool first = (half | r | s | k) == 0;
-                if (kSplit == 2) {
-                  // hi|lo weight planes of a tap are adjacent in smem: one N = 128 MMA gives x_hi*w_hi (cols 0..63)
-                  // and x_hi*w_lo (cols 64..127); x_lo*w_hi accumulates into cols 0..63.  The epilogue adds the halves.
-                  if (first) umma_bf16_first(tmem_d, a_d, b_d, idesc2); else umma_bf16_acc(tmem_d, a_d, b_d, idesc2);
-                  umma_bf16_acc(tmem_d, a_d + (kSlabBytes >> 4), b_d, idesc);
-                } else {
-                  if (first) umma_bf16_first(tmem_d, a_d, b_d, idesc); else umma_bf16_acc(tmem_d, a_d, b_d, idesc);
-                }
+                // hi|lo weight planes of a tap are adjacent in smem: one N = 128 MMA gives x*w_hi (cols 0..63) and x*w_lo
+                // (cols 64..127); split-bf16 adds x_lo*w_hi into cols 0..63.  The epilogue adds the halves.
+                if (first) umma_bf16_first(tmem_d, a_d, b_d, idesc2); else umma_bf16_acc(tmem_d, a_d, b_d, idesc2);
+                if (kAPl == 2) umma_bf16_acc(tmem_d, a_d + (kSlabBytes >> 4), b_d, idesc);
               }
             }
           }
@@ -178,14 +175,14 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       uint32_t r0[32], r1[32];
       tmem_ld32(taddr, r0);
       tmem_ld32(taddr + 32, r1);
-      if (kSplit == 2) {
+      if (kBPl == 2) {
         uint32_t t[32];
         tmem_ld32(taddr + 64, t);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(t[j]));
+        for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(fmaf(__uint_as_float(t[j]), TcFmt<FMT>::kLoScale, __uint_as_float(r0[j])));
         tmem_ld32(taddr + 96, t);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(t[j]));
+        for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(fmaf(__uint_as_float(t[j]), TcFmt<FMT>::kLoScale, __uint_as_float(r1[j])));
       }
       // the accumulator is in registers: hand the TMEM buffer back before the (long) epilogue math
       tcgen05_fence_before();
@@ -249,14 +246,14 @@ extern "C" int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* wei
                                 void* out, size_t out_plane, int fmt, int n, int h, int w, int act,
                                 const float* proj_w, int n_proj, float* proj_out, float* gn_partials, int gn_cpg,
                                 void* stream) {
-  SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv3x3_c64: format %d is not a tensor-core format", fmt);
+  SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2 || fmt == SBGM_FMT_F16, "conv3x3_c64: format %d is not a tensor-core format", fmt);
   SBGM_REQUIRE(h % kTH == 0 && w % kTW == 0, "conv3x3_c64: h=%d must be a multiple of %d and w=%d of %d", h, kTH, w, kTW);
   SBGM_REQUIRE(proj_w == nullptr || (n_proj == kProjN && proj_out != nullptr && residual == nullptr && tproj == nullptr &&
                                      act == SBGM_ACT_NONE),
                "conv3x3_c64: the projection epilogue needs n_proj == %d and a bias-only epilogue", kProjN);
   SBGM_REQUIRE(gn_partials == nullptr || (gn_cpg == 8 && residual == nullptr && tproj == nullptr && act == SBGM_ACT_NONE),
                "conv3x3_c64: fused GroupNorm statistics need 8 channels per group and a bias-only epilogue");
-  const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;
+  const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1, w_planes = (fmt == SBGM_FMT_BF16) ? 1 : 2;
   C64Params p;
   p.n = n; p.h = h; p.w = w;
   p.tiles_w = w / kTW; p.tiles_h = h / kTH; p.total_tiles = p.tiles_w * p.tiles_h * n;
@@ -266,8 +263,9 @@ extern "C" int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* wei
   p.gn_partials = gn_partials;
   CUtensorMap ta, tb;
   if (encode_act_map(&ta, in, planes, in_plane, n, h, w, 64, kSlabW, kSlabH, 1, 1, /*box_c=*/32)) return 1;
-  if (encode_weight_map(&tb, weight, planes, w_plane, 64, 9 * 64, 64)) return 1;
+  if (encode_weight_map(&tb, weight, w_planes, w_plane, 64, 9 * 64, 64)) return 1;
   cudaStream_t st = as_stream(stream);
   if (fmt == SBGM_FMT_BF16) return launch_c64<SBGM_FMT_BF16, 8>(ta, tb, p, st);
+  if (fmt == SBGM_FMT_F16) return launch_c64<SBGM_FMT_F16, 6>(ta, tb, p, st);     // 144 KB of weights + 6 x 12 KB slab halves
   return launch_c64<SBGM_FMT_BF16X2, 3>(ta, tb, p, st);
 }

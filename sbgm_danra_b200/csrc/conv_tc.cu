@@ -42,11 +42,11 @@ struct ConvTcParams {
 };
 
 // ---- kernel ---------------------------------------------------------------------------------
-template <int kSplit, int BLOCK_N, int kStages>
+template <int kAPl, int kBPl, int BLOCK_N, int kStages>
 struct ConvTcCfg {
-  static constexpr uint32_t kABytes = 128 * 128;               // 128 rows x 64 bf16
+  static constexpr uint32_t kABytes = 128 * 128;               // 128 rows x 64 16-bit elements
   static constexpr uint32_t kBBytes = BLOCK_N * 128;
-  static constexpr uint32_t kStageBytes = kSplit * (kABytes + kBBytes);
+  static constexpr uint32_t kStageBytes = kAPl * kABytes + kBPl * kBBytes;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
@@ -57,11 +57,11 @@ struct ConvTcCfg {
 constexpr int kSlabTileW = 8, kSlabTileH = 16, kSlabW = kSlabTileW + 2, kSlabH = kSlabTileH + 2, kSlabAStages = 2;
 constexpr uint32_t kSlabPlaneBytes = 25600;                    // plane pitch in smem (1024-aligned): 18 x 10 or 10 x 2 x 10 pixels
 constexpr uint32_t kDescHiSlab128 = ((kSlabW * 128u) >> 4) | (1u << 14) | (2u << 29);   // SBO = one slab row
-template <int kSplit, int BLOCK_N, int kStages>
+template <int kAPl, int kBPl, int BLOCK_N, int kStages>
 struct ConvTcSlabCfg {
   static constexpr uint32_t kBBytes = BLOCK_N * 128;
-  static constexpr uint32_t kAStageBytes = kSplit * kSlabPlaneBytes;
-  static constexpr uint32_t kBStageBytes = kSplit * kBBytes;
+  static constexpr uint32_t kAStageBytes = kAPl * kSlabPlaneBytes;
+  static constexpr uint32_t kBStageBytes = kBPl * kBBytes;
   static constexpr uint32_t kBOffset = kSlabAStages * kAStageBytes;
   static constexpr uint32_t kBarOffset = kBOffset + kStages * kBStageBytes;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;
@@ -79,9 +79,11 @@ __global__ void __launch_bounds__(ConvTcThreads<BLOCK_N>::kThreads, ConvTcThread
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const ConvTcParams p) {
   pdl_grid_sync();
-  constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
-  using Cfg = ConvTcCfg<kSplit, BLOCK_N, kStages>;
-  using SCfg = ConvTcSlabCfg<kSplit, BLOCK_N, kStages>;
+  // kAPl activation planes (2: split-bf16 hi|lo), kBPl weight planes (2: hi|lo, adjacent in a stage so that ONE MMA of width
+  // 2 * BLOCK_N multiplies an activation plane with both; F16: w_lo is stored times 2^11 and the epilogue rescales its half)
+  constexpr int kAPl = TcFmt<FMT>::kAPlanes, kBPl = TcFmt<FMT>::kBPlanes;
+  using Cfg = ConvTcCfg<kAPl, kBPl, BLOCK_N, kStages>;
+  using SCfg = ConvTcSlabCfg<kAPl, kBPl, BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + (SLAB ? SCfg::kBarOffset : Cfg::kBarOffset);
@@ -111,7 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kSplit * BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, kBPl * BLOCK_N);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -138,9 +140,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int i = 0; i < cb_cnt; ++i) {
         const int cb = cb_begin + i, as = i & 1;
         mbar_wait(slab_empty(as), ((i >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(slab_full(as), kSplit * p.slab_tx);
+        mbar_expect_tx(slab_full(as), kAPl * p.slab_tx);
 #pragma unroll
-        for (int pl = 0; pl < kSplit; ++pl)
+        for (int pl = 0; pl < kAPl; ++pl)
           tma_load_5d(smem_base + as * SCfg::kAStageBytes + pl * kSlabPlaneBytes, &tmap_a, slab_full(as), cb * 64, wo0 - 1,
                       p.slab_perm ? n0 : ho0 - 1, p.slab_perm ? ho0 - 1 : n0, pl);
         for (int tap = 0; tap < 9; ++tap) {
@@ -148,7 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_expect_tx(full_bar(stage), SCfg::kBStageBytes);
           const uint32_t b_dst = smem_base + SCfg::kBOffset + stage * SCfg::kBStageBytes;
 #pragma unroll
-          for (int pl = 0; pl < kSplit; ++pl)
+          for (int pl = 0; pl < kBPl; ++pl)
             tma_load_3d(b_dst + pl * SCfg::kBBytes, &tmap_b, full_bar(stage), (tap * p.cin_blocks + cb) * 64, co0, pl);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -156,7 +158,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (SLAB && warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N), idesc2 = make_idesc(kSplit * BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(BLOCK_N, TcFmt<FMT>::kHalf), idesc2 = make_idesc(kBPl * BLOCK_N, TcFmt<FMT>::kHalf);
       const uint64_t a_base = (static_cast<uint64_t>(kDescHiSlab128) << 32) | desc_lo(smem_base);
       const uint64_t b_base = (static_cast<uint64_t>(kDescHi) << 32) | desc_lo(smem_base + SCfg::kBOffset);
       uint32_t stage = 0, phase = 0;
@@ -174,14 +176,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t b0 = b_base + stage * (SCfg::kBStageBytes >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (kSplit == 2) {
-              if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc2, i != 0);
-              else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
-              umma_bf16_acc(tmem_base, a0 + (kSlabPlaneBytes >> 4) + 2 * k, b0 + 2 * k, idesc);
-            } else {
-              if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc, i != 0);
-              else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc);
-            }
+            if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc2, i != 0);
+            else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
+            if (kAPl == 2) umma_bf16_acc(tmem_base, a0 + (kSlabPlaneBytes >> 4) + 2 * k, b0 + 2 * k, idesc);
           }
           umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -202,13 +199,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(empty_bar(stage), phase ^ 1u);
         mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
         const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-        const uint32_t b_dst = a_dst + kSplit * Cfg::kABytes;
+        const uint32_t b_dst = a_dst + kAPl * Cfg::kABytes;
 #pragma unroll
-        for (int pl = 0; pl < kSplit; ++pl) {
+        for (int pl = 0; pl < kAPl; ++pl)
           tma_load_5d(a_dst + pl * Cfg::kABytes, &tmap_a, full_bar(stage), cb * 64, wo0 * p.stride + s - p.pad_w,
                       ho0 * p.stride + r - p.pad_h, n0, pl);
-          tma_load_3d(b_dst + pl * Cfg::kBBytes, &tmap_b, full_bar(stage), kb * 64, co0, pl);
-        }
+#pragma unroll
+        for (int pl = 0; pl < kBPl; ++pl) tma_load_3d(b_dst + pl * Cfg::kBBytes, &tmap_b, full_bar(stage), kb * 64, co0, pl);
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -216,26 +213,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // one elected lane runs the whole issue loop (64-bit descriptors, ~3 instructions per MMA; the earlier
     // warp-uniform variant paid an election, a predicate vote and four register->uniform moves per MMA)
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N), idesc2 = make_idesc(kSplit * BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(BLOCK_N, TcFmt<FMT>::kHalf), idesc2 = make_idesc(kBPl * BLOCK_N, TcFmt<FMT>::kHalf);
       const uint64_t base = (static_cast<uint64_t>(kDescHi) << 32) | desc_lo(smem_base);
       uint32_t stage = 0, phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
         const uint64_t a0 = base + stage * (Cfg::kStageBytes >> 4);
-        const uint64_t b0 = a0 + ((kSplit * Cfg::kABytes) >> 4);
+        const uint64_t b0 = a0 + ((kAPl * Cfg::kABytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) per 64-element block
-          if (kSplit == 2) {
-            // the hi|lo weight planes of a stage are adjacent: one N = 2*BLOCK_N MMA yields x_hi*w_hi (first half
-            // of the columns) and x_hi*w_lo (second half); x_lo*w_hi accumulates into the first half.
-            if (k == 0) umma_bf16(tmem_base, a0, b0, idesc2, kb != 0);
-            else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
-            umma_bf16_acc(tmem_base, a0 + (Cfg::kABytes >> 4) + 2 * k, b0 + 2 * k, idesc);
-          } else {
-            if (k == 0) umma_bf16(tmem_base, a0, b0, idesc, kb != 0);
-            else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc);
-          }
+        for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 elements = 32 B) per 64-element block
+          // two weight planes (hi|lo) of a stage are adjacent: one N = 2*BLOCK_N MMA yields x*w_hi (first half of the
+          // columns) and x*w_lo (second half); split-bf16 adds x_lo*w_hi into the first half.
+          if (k == 0) umma_bf16(tmem_base, a0, b0, idesc2, kb != 0);
+          else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
+          if (kAPl == 2) umma_bf16_acc(tmem_base, a0 + (Cfg::kABytes >> 4) + 2 * k, b0 + 2 * k, idesc);
         }
         umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
@@ -265,11 +257,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     auto load_acc = [&](int c0, uint32_t (&r)[32]) {
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
       tmem_ld32(taddr, r);
-      if (kSplit == 2) {
+      if (kBPl == 2) {
         uint32_t t[32];
         tmem_ld32(taddr + BLOCK_N, t);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(t[j]), TcFmt<FMT>::kLoScale, __uint_as_float(r[j])));
       }
     };
     if (!PROJ && p.splits > 1) {                    // split-K: raw fp32 partial tile, finished by splitk_finalize_kernel
@@ -312,7 +304,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // warp e stages its 64-column blocks (x planes) back to back from smem_base + e * kWarpStride
           const int r0 = quarter * 32;
           sa.tmap_o = &tmap_o;
-          constexpr uint32_t kBlockStride = kSplit * kStageBlockBytes, kWarpStride = (kColsPerGroup / 64) * kBlockStride;
+          constexpr uint32_t kBlockStride = kAPl * kStageBlockBytes, kWarpStride = (kColsPerGroup / 64) * kBlockStride;
           sa.stage = smem_base + static_cast<uint32_t>(warp - 2) * kWarpStride + static_cast<uint32_t>((c0 - c_begin) >> 6) * kBlockStride;
           sa.x0 = wo0 + r0 % p.w_tile;
           sa.y0 = ho0 + (r0 / p.w_tile) % p.h_tile;
@@ -330,7 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kSplit * BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_base, kBPl * BLOCK_N);
 }
 
 // Sum the split-K partial tiles in a fixed order (deterministic) and apply the fused epilogue.
@@ -480,9 +472,10 @@ void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
 template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false>
 static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
                                cudaStream_t st) {
-  constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
-  using Cfg = std::conditional_t<SLAB, ConvTcSlabCfg<kSplit, BLOCK_N, kStages>, ConvTcCfg<kSplit, BLOCK_N, kStages>>;
-  static_assert(!STAGED || Cfg::kBarOffset >= 4u * (BLOCK_N / 64) * kSplit * kStageBlockBytes, "the staging area must fit in the pipeline stages");
+  constexpr int kAPl = TcFmt<FMT>::kAPlanes, kBPl = TcFmt<FMT>::kBPlanes;
+  using Cfg = std::conditional_t<SLAB, ConvTcSlabCfg<kAPl, kBPl, BLOCK_N, kStages>, ConvTcCfg<kAPl, kBPl, BLOCK_N, kStages>>;
+  static_assert(!STAGED || Cfg::kBarOffset >= 4u * (BLOCK_N / 64) * kAPl * kStageBlockBytes, "the staging area must fit in the pipeline stages");
+  static_assert(kBPl * BLOCK_N <= 512, "accumulator exceeds the 512 TMEM columns");
   static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
   auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED, SLAB>;
   static bool configured = false;
@@ -579,7 +572,7 @@ extern "C" int sbgm_conv2d_tc_gn_chunks(int fmt, int n, int h, int w, int cin, i
   if (cin % 64 != 0 || cout % 64 != 0 || stride < 1) return 0;
   ConvTcParams p;
   int block_n = 0, m_tiles = 0;
-  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, fmt == SBGM_FMT_BF16X2 ? 2 : 1, &p, &block_n, &m_tiles);
+  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, fmt == SBGM_FMT_BF16 ? 1 : 2, &p, &block_n, &m_tiles);
   if (p.ho <= 0 || p.wo <= 0) return 0;
   return gn_chunks_for(p);
 }
@@ -589,7 +582,7 @@ extern "C" size_t sbgm_conv2d_tc_workspace_bytes(int fmt, int n, int h, int w, i
   if (cin % 64 != 0 || cout % 64 != 0 || stride < 1) return 0;
   ConvTcParams p;
   int block_n = 0, m_tiles = 0;
-  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, fmt == SBGM_FMT_BF16X2 ? 2 : 1, &p, &block_n, &m_tiles);
+  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, fmt == SBGM_FMT_BF16 ? 1 : 2, &p, &block_n, &m_tiles);
   if (p.ho <= 0 || p.wo <= 0 || p.splits <= 1) return 0;
   return static_cast<size_t>(p.splits) * n * p.ho * p.wo * cout * sizeof(float);
 }
@@ -605,7 +598,7 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
                           int kh, int kw, int stride, int pad, int act, const float* proj_w, int n_proj,
                           float* proj_out, void* workspace, size_t workspace_bytes, float* gn_partials,
                           const ConvTcEx& ex, void* stream) {
-  SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2, "conv2d_tc: format %d is not a tensor-core format", fmt);
+  SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2 || fmt == SBGM_FMT_F16, "conv2d_tc: format %d is not a tensor-core format", fmt);
   SBGM_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv2d_tc: cin=%d and cout=%d must be multiples of 64", cin, cout);
   SBGM_REQUIRE(stride >= 1 && stride <= 8, "conv2d_tc: stride %d unsupported", stride);
   SBGM_REQUIRE(proj_w == nullptr || (cout == 64 && n_proj == kProjN && proj_out != nullptr && residual == nullptr &&
@@ -613,11 +606,12 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
                "conv2d_tc: the projection epilogue needs cout == 64, n_proj == %d and a bias-only epilogue", kProjN);
   const int ho = ex.on ? ex.ho : (h + 2 * pad - kh) / stride + 1, wo = ex.on ? ex.wo : (w + 2 * pad - kw) / stride + 1;
   SBGM_REQUIRE(ho > 0 && wo > 0, "conv2d_tc: empty output");
-  const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;
+  const int planes = (fmt == SBGM_FMT_BF16X2) ? 2 : 1;        // activation planes
+  const int w_planes = (fmt == SBGM_FMT_BF16) ? 1 : 2;        // weight planes (hi | lo)
 
   ConvTcParams p;
   int block_n = 0, m_tiles = 0;
-  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, planes, &p, &block_n, &m_tiles, ex.on ? ex.ho : 0, ex.on ? ex.wo : 0);
+  conv_tc_geometry(n, h, w, cin, cout, kh, kw, stride, pad, w_planes, &p, &block_n, &m_tiles, ex.on ? ex.ho : 0, ex.on ? ex.wo : 0);
   bool scatter = false;
   if (ex.on) {
     p.pad_h = ex.pad_h; p.pad_w = ex.pad_w;
@@ -674,7 +668,7 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
                         : encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, kSlabH, 1, 1))
            : encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
   const int K = kh * kw * cin;
-  if (encode_weight_map(&tb, weight, planes, w_plane, cout, K, block_n)) return 1;
+  if (encode_weight_map(&tb, weight, w_planes, w_plane, cout, K, block_n)) return 1;
   if (p.ep.staged) {
     if (slab && slab_perm ? encode_perm_map(&to, out, planes, out_plane, n, ho, wo, cout, 8, 2, 2)
                           : encode_out_map(&to, out, planes, out_plane, n, ho, wo, cout, p.w_tile, p.h_tile, p.n_tile)) return 1;
@@ -688,6 +682,10 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
       if (block_n == 128) return launch_conv_tc_slab<SBGM_FMT_BF16, 128>(ta, tb, to, p, m_tiles, st);
       return launch_conv_tc_slab<SBGM_FMT_BF16, 64>(ta, tb, to, p, m_tiles, st);
     }
+    if (fmt == SBGM_FMT_F16) {
+      if (block_n == 128) return launch_conv_tc_slab<SBGM_FMT_F16, 128>(ta, tb, to, p, m_tiles, st);
+      return launch_conv_tc_slab<SBGM_FMT_F16, 64>(ta, tb, to, p, m_tiles, st);
+    }
     if (block_n == 128) return launch_conv_tc_slab<SBGM_FMT_BF16X2, 128>(ta, tb, to, p, m_tiles, st);
     return launch_conv_tc_slab<SBGM_FMT_BF16X2, 64>(ta, tb, to, p, m_tiles, st);
   }
@@ -695,6 +693,10 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
     if (block_n == 256) return launch_conv_tc<SBGM_FMT_BF16, 256, 4>(ta, tb, to, p, m_tiles, st);
     if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16, 128, 3>(ta, tb, to, p, m_tiles, st);
     return launch_conv_tc<SBGM_FMT_BF16, 64, 4>(ta, tb, to, p, m_tiles, st);
+  }
+  if (fmt == SBGM_FMT_F16) {      // one activation plane + two weight planes per stage: 48 KB (N = 128) / 32 KB (N = 64)
+    if (block_n == 128) return launch_conv_tc<SBGM_FMT_F16, 128, 4>(ta, tb, to, p, m_tiles, st);
+    return launch_conv_tc<SBGM_FMT_F16, 64, 4>(ta, tb, to, p, m_tiles, st);
   }
   if (block_n == 128) return launch_conv_tc<SBGM_FMT_BF16X2, 128, 3>(ta, tb, to, p, m_tiles, st);
   // short K loop on a grid of at most one CTA per SM (the attention blocks' Linear layers): four stages put the whole K loop

@@ -575,6 +575,8 @@ int sbgm_convert(const void* src, size_t sp, int sf, void* dst, size_t dp, int d
   else if (sf == SBGM_FMT_F32 && df == SBGM_FMT_BF16X2) SBGM_CVT(SBGM_FMT_F32, SBGM_FMT_BF16X2);
   else if (sf == SBGM_FMT_BF16 && df == SBGM_FMT_F32) SBGM_CVT(SBGM_FMT_BF16, SBGM_FMT_F32);
   else if (sf == SBGM_FMT_BF16X2 && df == SBGM_FMT_F32) SBGM_CVT(SBGM_FMT_BF16X2, SBGM_FMT_F32);
+  else if (sf == SBGM_FMT_F32 && df == SBGM_FMT_F16) SBGM_CVT(SBGM_FMT_F32, SBGM_FMT_F16);
+  else if (sf == SBGM_FMT_F16 && df == SBGM_FMT_F32) SBGM_CVT(SBGM_FMT_F16, SBGM_FMT_F32);
   else { set_error("convert: unsupported format pair %d -> %d", sf, df); return 1; }
 #undef SBGM_CVT
   return check_launch("convert");

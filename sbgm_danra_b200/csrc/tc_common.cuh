@@ -69,9 +69,10 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n.
-__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: 0 = float16, 1 = bfloat16), both
+// K-major, M = 128, N = n.
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n, bool half = false) {
+  return (1u << 4) | (half ? 0u : ((1u << 7) | (1u << 10))) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -195,7 +196,7 @@ template <int FMT>
 __device__ __forceinline__ void store_block64(void* out, size_t out_plane, int cout, const float (&v)[64], size_t pix,
                                               bool valid, int co_base, int lane) {
   const int l8 = lane & 7, gbase = lane & ~7;
-  constexpr int kPlanes = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
+  constexpr int kPlanes = TcFmt<FMT>::kAPlanes;
 #pragma unroll
   for (int pl = 0; pl < kPlanes; ++pl) {
     uint4 c[8];
@@ -207,7 +208,7 @@ __device__ __forceinline__ void store_block64(void* out, size_t out_plane, int c
         const float x = v[j * 8 + e];
         t[e] = (pl == 0) ? x : x - bf16_round(x);
       }
-      c[j] = pack_bf16x8(t);
+      c[j] = TcFmt<FMT>::pack8(t);
     }
     transpose8_u4(c, lane);
     __nv_bfloat16* base = static_cast<__nv_bfloat16*>(out) + pl * out_plane;
@@ -229,7 +230,7 @@ constexpr uint32_t kStageBlockBytes = 32 * 128;
 template <int FMT>
 __device__ __forceinline__ void store_block64_staged(const CUtensorMap* tmap_o, uint32_t stage, const float (&v)[64], int co_base,
                                                      int x0, int y0, int n0, int lane) {
-  constexpr int kPlanes = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
+  constexpr int kPlanes = TcFmt<FMT>::kAPlanes;
 #pragma unroll
   for (int pl = 0; pl < kPlanes; ++pl) {
     const uint32_t row = stage + pl * kStageBlockBytes + lane * 128;
@@ -241,7 +242,7 @@ __device__ __forceinline__ void store_block64_staged(const CUtensorMap* tmap_o, 
         const float x = v[j * 8 + e];
         t[e] = (pl == 0) ? x : x - bf16_round(x);
       }
-      const uint4 c = pack_bf16x8(t);
+      const uint4 c = TcFmt<FMT>::pack8(t);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ (lane & 7)) << 4)), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
     }
   }
@@ -256,7 +257,7 @@ __device__ __forceinline__ void store_block64_staged(const CUtensorMap* tmap_o, 
 
 // GroupNorm partial statistics of one 64-channel block, at 8-channel granularity, reduced over the warp's 32
 // rows: dst[sub][2] (sum, sum of squares) for sub = 0..7.  Values are taken as stored (bias added, bf16-rounded
-// in BF16 mode).  Must be called by the whole warp; rows with !valid contribute nothing.
+// in the single-plane modes).  Must be called by the whole warp; rows with !valid contribute nothing.
 template <int FMT>
 __device__ __forceinline__ void gn_block64_stats(const uint32_t (&ra)[32], const uint32_t (&rb)[32], const float* bias,
                                                  int co_base, bool valid, int lane, float* dst) {
@@ -267,7 +268,7 @@ __device__ __forceinline__ void gn_block64_stats(const uint32_t (&ra)[32], const
     for (int j = 0; j < 8; ++j) {
       float v = __uint_as_float(g < 4 ? ra[g * 8 + j] : rb[(g - 4) * 8 + j]);
       if (bias) v += __ldg(bias + co_base + g * 8 + j);
-      if (FMT == SBGM_FMT_BF16) v = bf16_round(v);
+      if (FMT == SBGM_FMT_BF16 || FMT == SBGM_FMT_F16) v = TcFmt<FMT>::round(v);
       if (!valid) v = 0.0f;
       s += v;
       q = fmaf(v, v, q);

@@ -12,6 +12,10 @@ Precisions
               fp32-class accuracy; this is the "fp32/TF32 mode" of the north star (plain TF32
               sits on the 1e-3 parity gate)
     "bf16"    tensor cores, bf16 operands, fp32 accumulate
+    "fp16x2"  tensor cores, ONE float16 activation plane, weights as float16 hi|lo planes (x*w_hi + x*w_lo: two
+              products): the weights are exact to 22 bits, only the activations are rounded (11 bits) -- score
+              rel-L2 2-5e-4 vs the reference's fp32, inside the 1e-3 gate -- at 2/3 of bf16x3's tensor work and
+              half its activation bytes.  Inference only (training with it runs the bf16x3 kernels).
 """
 from __future__ import annotations
 
@@ -21,9 +25,9 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, FMT_BF16, FMT_BF16X2, FMT_F32, call
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, F16_WLO_SCALE, FMT_BF16, FMT_BF16X2, FMT_F16, FMT_F32, call
 
-PRECISIONS = {"fp32": FMT_F32, "bf16x3": FMT_BF16X2, "bf16": FMT_BF16}
+PRECISIONS = {"fp32": FMT_F32, "bf16x3": FMT_BF16X2, "bf16": FMT_BF16, "fp16x2": FMT_F16}
 ACTS = {"relu": ACT_RELU, "silu": ACT_SILU, "gelu": ACT_GELU, "identity": ACT_NONE, None: ACT_NONE}
 FMAP_CHANNELS = (64, 64, 128, 256, 512)
 BN_EPS = 1e-5
@@ -45,8 +49,13 @@ import os as _os
 _SKIP = frozenset(x for x in _os.environ.get("SBGM_B200_SKIP", "").split(",") if x)
 
 
+# Measurement hook (bench.py `roofline.family`): when set to a list, every convolution / Linear launch of a forward appends
+# its geometry, so that the layers can afterwards be timed one by one.  None on the product path.
+CONV_TRACE: Optional[list] = None
+
+
 class Act:
-    """An NHWC activation tensor in one of the three storage formats."""
+    """An NHWC activation tensor in one of the four storage formats."""
     __slots__ = ("buf", "fmt", "n", "h", "w", "c")
 
     def __init__(self, fmt: int, n: int, h: int, w: int, c: int, device) -> None:
@@ -55,6 +64,8 @@ class Act:
             self.buf = torch.empty((n, h, w, c), dtype=torch.float32, device=device)
         elif fmt == FMT_BF16:
             self.buf = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+        elif fmt == FMT_F16:
+            self.buf = torch.empty((n, h, w, c), dtype=torch.float16, device=device)
         else:
             self.buf = torch.empty((2, n, h, w, c), dtype=torch.bfloat16, device=device)
 
@@ -110,6 +121,21 @@ def _split_bf16(x: torch.Tensor) -> torch.Tensor:
     return torch.stack([hi, lo]).contiguous()
 
 
+def _split_f16(x: torch.Tensor) -> torch.Tensor:
+    """float16 hi | lo * 2^11 planes of a weight matrix (SBGM_FMT_F16 layers): 22 significant bits.  |w| beyond the float16
+    range saturates (a BatchNorm-folded weight of 6e4 would be a broken checkpoint anyway)."""
+    hi = x.clamp(-65504.0, 65504.0).to(torch.float16)
+    lo = ((x - hi.float()) * F16_WLO_SCALE).to(torch.float16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def pack_tc_matrix(km: torch.Tensor, fmt: int) -> torch.Tensor:
+    """K-major weight matrix [cout][K] fp32 -> the tensor-core storage of `fmt`."""
+    if fmt == FMT_BF16:
+        return km.to(torch.bfloat16)
+    return _split_f16(km) if fmt == FMT_F16 else _split_bf16(km)
+
+
 class _Packer:
     def __init__(self, sd: Dict[str, torch.Tensor], fmt: int, device) -> None:
         self.sd, self.fmt, self.device = sd, fmt, device
@@ -135,7 +161,7 @@ class _Packer:
             packed = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()      # [K][cout]
         else:
             km = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).contiguous()           # [cout][K]
-            packed = km.to(torch.bfloat16) if self.fmt == FMT_BF16 else _split_bf16(km)
+            packed = pack_tc_matrix(km, self.fmt)
         return ConvW(packed, None if bias is None else bias.contiguous(), cin, cout, kh, kw)
 
 
@@ -158,6 +184,10 @@ class Kernels:
         projected fp32 tensor [n, h, w, PROJ_STRIDE] instead; with `gn_stats=True` returns (Act, stats) where
         stats = (partials, chunks) if the producing kernel could fuse the GroupNorm statistics, else None."""
         assert x.c == cw.cin, f"conv: input has {x.c} channels, weight expects {cw.cin}"
+        if CONV_TRACE is not None:
+            CONV_TRACE.append(dict(n=x.n, h=x.h, w=x.w, cw=cw, stride=stride, pad=pad, act=act, residual=residual is not None,
+                                   tproj=tproj is not None, proj=proj is not None, gn_stats=gn_stats,
+                                   c64=self._c64_ok(x, cw, stride, pad)))
         ho = (x.h + 2 * pad - cw.kh) // stride + 1
         wo = (x.w + 2 * pad - cw.kw) // stride + 1
         tp_ptr = _ptr(tproj)
@@ -382,8 +412,7 @@ class EncoderEngine:
         if fmt != FMT_F32:
             # tensor-core stem: conv1 as a 1x1 convolution over the im2col tensor (K index = ci * 64 + r * 8 + s = OIHW order)
             def km(wsub):
-                m = wsub.reshape(64, -1).contiguous()
-                return m.to(torch.bfloat16) if fmt == FMT_BF16 else _split_bf16(m)
+                return pack_tc_matrix(wsub.reshape(64, -1).contiguous(), fmt)
             self.stem_cw_all = ConvW(km(w1), None, self.cin * 64, 64, 1, 1)
             self.stem_cw_x = ConvW(km(w1[:, :1]), None, 64, 64, 1, 1)
         self.conv2 = pk.conv(f"{p}conv2.weight", bn=f"{p}bn1")
@@ -517,8 +546,7 @@ class DecoderEngine:
         for a in range(2):
             for b in range(2):
                 km = w[:, :, a, b].t().contiguous()          # [cout][cin] K-major
-                packed = km.to(torch.bfloat16) if self.fmt == FMT_BF16 else _split_bf16(km)
-                subs.append((a, b, ConvW(packed, bias, cin, cout, 1, 1)))
+                subs.append((a, b, ConvW(pack_tc_matrix(km, self.fmt), bias, cin, cout, 1, 1)))
         return dict(subs=subs, bias=bias, cin=cin, cout=cout)
 
     def _transpose_up(self, x: Act, tw: dict):

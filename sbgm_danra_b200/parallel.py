@@ -5,11 +5,14 @@ the GPUs of one box.  `TrainEngine` writes every parameter gradient as a view of
 (state-dict order, time-projection parameters last), so the exchange is an in-place bucketed
 `all_reduce` of that buffer -- no flatten / unflatten copies:
 
-  * buckets are contiguous ranges of the flat buffer; backward finishes the decoder (the END of the buffer)
-    first, so buckets complete from the high end down and each is launched on a communication stream as soon
-    as every gradient in it has been enqueued -- overlapping the remaining backward kernels;
-  * gradients are averaged (sum / world) like torch DDP, so `loss.backward(); optimizer.step()` in the reference
-    training loop needs no change;
+  * buckets are contiguous ranges of the flat buffer, which is laid out in FORWARD order (train_engine.flat_order: time
+    projections, stem, encoder stages, decoder blocks, final layer); backward produces gradients from the END of the buffer
+    down, so buckets complete from the high end and each is launched on a communication stream as soon as every gradient in it
+    has been enqueued -- overlapping the remaining backward kernels.  Only the lowest bucket (stem + time projections, a few
+    hundred KB) is exposed after the last backward kernel;
+  * gradients are averaged like torch DDP (`ReduceOp.AVG` inside NCCL; sum then scale on backends without it), so
+    `loss.backward(); optimizer.step()` in the reference training loop needs no change.  `grad_dtype="bf16"` exchanges a
+    bfloat16 copy of each bucket (half the NVLink bytes; the local fp32 buffer receives the rounded average);
   * the first step all-reduces the whole buffer at the end and records which parameters receive gradients
     (the final block's unused time projection etc. never do); later steps use that set.
 
@@ -63,6 +66,7 @@ class GradBucketer:
                 self.pending[self.bucket_of[name]] += 1
         self.seen = set()
         self.launched = [False] * len(self.bounds)
+        self.late: List[str] = []      # touched outside the expected set after their bucket had already been exchanged
 
     def touch(self, names: Sequence[str]) -> List[int]:
         """Mark gradients as enqueued; returns the buckets that just became complete (expected set known)."""
@@ -77,6 +81,8 @@ class GradBucketer:
                 if self.pending[b] == 0 and not self.launched[b]:
                     self.launched[b] = True
                     ready.append(b)
+            elif self.expected is not None and self.launched[self.bucket_of[name]]:
+                self.late.append(name)     # a gradient the first step did not produce: exchanged on its own in finish()
         return ready
 
     def remaining(self) -> List[int]:
@@ -87,9 +93,12 @@ class GradSync:
     """The hook `TrainEngine.backward` drives: `begin(engine)`, `progress(names)` after every tape step,
     `finish()` once all gradients are enqueued.  All-reduces on a side stream, averages, then joins."""
 
-    def __init__(self, group=None, bucket_bytes: int = BUCKET_BYTES, sync_bn: bool = False) -> None:
-        self.group, self.bucket_elems, self.sync_bn = group, max(1, bucket_bytes // 4), sync_bn
+    def __init__(self, group=None, bucket_bytes: int = BUCKET_BYTES, sync_bn: bool = False, grad_dtype: str = "fp32") -> None:
+        if grad_dtype not in ("fp32", "bf16"):
+            raise ValueError(f"grad_dtype must be 'fp32' or 'bf16', got {grad_dtype!r}")
+        self.group, self.bucket_elems, self.sync_bn, self.grad_dtype = group, max(1, bucket_bytes // 4), sync_bn, grad_dtype
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.native_avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
         self.expected: Optional[List[str]] = None
         self.bucketer: Optional[GradBucketer] = None
         self.stream: Optional[torch.cuda.Stream] = None
@@ -111,19 +120,30 @@ class GradSync:
         self.bucketer.reset()
         self.works = []
 
-    def _launch(self, b: int, overlapped: bool) -> None:
-        lo, hi = self.bucketer.bounds[b]
+    def _average(self, view: torch.Tensor) -> None:
+        """In-place average of `view` over the group."""
+        buf = view.to(torch.bfloat16) if self.grad_dtype == "bf16" else view
+        if self.native_avg:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)      # the division happens inside the NCCL kernel
+        else:
+            dist.all_reduce(buf, group=self.group)
+            buf.mul_(1.0 / self.world)
+        if buf is not view:
+            view.copy_(buf)
+
+    def _launch_range(self, lo: int, hi: int) -> None:
         view = self.flat[lo:hi]
-        self.stats["buckets"] += 1
-        self.stats["overlapped"] += int(overlapped)
         if self.flat.is_cuda:
             self.stream.wait_stream(torch.cuda.current_stream(self.flat.device))
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(view, group=self.group)
-                view.mul_(1.0 / self.world)
+                self._average(view)
         else:
-            dist.all_reduce(view, group=self.group)
-            view.mul_(1.0 / self.world)
+            self._average(view)
+
+    def _launch(self, b: int, overlapped: bool) -> None:
+        self.stats["buckets"] += 1
+        self.stats["overlapped"] += int(overlapped)
+        self._launch_range(*self.bucketer.bounds[b])
 
     def progress(self, names: Sequence[str]) -> None:
         if self.world == 1:
@@ -137,26 +157,42 @@ class GradSync:
         for b in self.bucketer.remaining():
             self.bucketer.launched[b] = True
             self._launch(b, False)
+        offs = {name: (off, numel) for name, off, numel in self.bucketer.layout}
+        for name in self.bucketer.late:
+            off, numel = offs[name]
+            self._launch_range(off, off + numel)
+        if self.bucketer.late and self.expected is not None:
+            self.expected = sorted(set(self.expected) | set(self.bucketer.late))
+            self.bucketer = None            # rebuilt with the enlarged set by the next begin()
         if self.flat.is_cuda:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
-        if self.expected is None:
+        if self.expected is None and self.bucketer is not None:
             self.expected = sorted(self.bucketer.seen)
         self.flat = None
 
 
-def attach(model, group=None, bucket_bytes: int = BUCKET_BYTES, sync_bn: bool = False) -> GradSync:
+def _drop_captured_steps(model) -> None:
+    """Captured training graphs have the exchange (or its absence) baked in: forget them so the next step re-captures."""
+    runners = getattr(model, "__dict__", {}).get("_train_runners")
+    if runners:
+        runners.clear()
+
+
+def attach(model, group=None, bucket_bytes: int = BUCKET_BYTES, sync_bn: bool = False, grad_dtype: str = "fp32") -> GradSync:
     """Make `loss.backward()` through `model` (a ScoreNet of this package) average gradients over `group`.
 
     sync_bn=True additionally synchronises the BatchNorm batch statistics (forward: all-gather of the per-chunk partial
     sums; backward: all-gather of the per-sample gradient sums), so that N ranks with B/N samples each reproduce the
     reference's single-process batch-B statistics exactly; the default is DDP-style rank-local statistics."""
-    sync = GradSync(group, bucket_bytes, sync_bn)
+    sync = GradSync(group, bucket_bytes, sync_bn, grad_dtype)
     model._grad_sync = sync
+    _drop_captured_steps(model)
     return sync
 
 
 def detach(model) -> None:
     model._grad_sync = None
+    _drop_captured_steps(model)
 
 
 def broadcast_parameters(model, src: int = 0, group=None) -> None:
@@ -165,4 +201,7 @@ def broadcast_parameters(model, src: int = 0, group=None) -> None:
         return
     with torch.no_grad():
         for t in list(model.parameters()) + list(model.buffers()):
-            dist.broadcast(t.data, src=src, group=group)
+            # t.detach() shares t's version counter (t.data does not): the in-place write invalidates the packed-weight
+            # caches (score_unet._EngineCache keys on data_ptr + _version) of engines built before the broadcast
+            dist.broadcast(t.detach(), src=src, group=group)
+    _drop_captured_steps(model)

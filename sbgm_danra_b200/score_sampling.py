@@ -230,13 +230,15 @@ class _NativeStep:
         eng.dec.forward(fmaps, tproj, self.inv_std, inv_std_stride=0, inv_std_step_stride=STEP_COLS,
                         step_counter=self.counter, dst=out)
 
-    def score_into(self) -> torch.Tensor:
+    def score_into(self, scale: Optional[float] = None) -> torch.Tensor:
+        """`scale`: guidance scale of THIS evaluation (the PC corrector clamps it to guidance_scale_max, the predictor does
+        not: score_sampling.py:182-186 vs :209-219); default = the plan's scale."""
         if self.cfg_scale is None:
             self._forward(self.partial, self.y, self.tproj, self.score)
         else:
             self._forward(self.partial, self.y, self.tproj, self.score_c)
             self._forward(self.partial_u, self.y_u, self.tproj_u, self.score_u)
-            call("sbgm_cfg_combine", self.score_c.data_ptr(), self.score_u.data_ptr(), self.cfg_scale,
+            call("sbgm_cfg_combine", self.score_c.data_ptr(), self.score_u.data_ptr(), self.cfg_scale if scale is None else scale,
                  self.score.data_ptr(), self.score.numel(), _eng._stream())
         return self.score
 
@@ -259,12 +261,12 @@ class _GenericStep:
         self.k = 0
         self.graph = None
 
-    def score_into(self) -> torch.Tensor:
+    def score_into(self, scale: Optional[float] = None) -> torch.Tensor:
         bt = torch.full((self.b,), float(self.table_host[self.k, 0]), dtype=torch.float32, device=self.dev)
         if self.cfg_scale is None:
             s = self.model(self.x, bt, *self.args)
         else:
-            s = guided_score_fn(self.model, self.x, bt, *self.args, scale=self.cfg_scale)
+            s = guided_score_fn(self.model, self.x, bt, *self.args, scale=self.cfg_scale if scale is None else scale)
         self.score = s.contiguous().float()
         return self.score
 
@@ -300,7 +302,10 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
         raise ValueError(f"img_size must be a multiple of 32, got {img_size}")
     seed = _next_seed()
     table = (_table_em if kind == "em" else _table_pc)(marginal_prob_std, diffusion_coeff, n_steps, eps)
-    scale = _cfg_scale(cfg, clamp=(kind == "pc"))
+    # PC: the corrector's guidance scale is clamped to guidance_scale_max, the predictor re-reads the unclamped one
+    # (score_sampling.py:182-186 vs :209-219); EM never clamps (:106-110)
+    scale = _cfg_scale(cfg, clamp=False)
+    scale_corrector = _cfg_scale(cfg, clamp=True) if kind == "pc" else scale
     native = _is_native(score_model)
     dev = score_model.engine().device if native else torch.device(device)
     if dev.type != "cuda":
@@ -326,7 +331,7 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
                                                  _strip_mask(lsm_cond), _strip_mask(topo_cond))
                 if planes_u.shape[0] != planes.shape[0]:
                     planes_u = planes_u.expand(planes.shape[0], -1, -1, -1).contiguous()
-            key = (id(eng), kind, batch_size, img_size, n_steps, scale, float(snr), y is not None,
+            key = (id(eng), kind, batch_size, img_size, n_steps, scale, scale_corrector, float(snr), y is not None,
                    0 if planes is None else planes.shape[0], first_elem, total, id(_state.group) if sharded else 0, use_graph)
             st = next((p for k, p in _PLAN_CACHE if k == key), None)
             if st is None:
@@ -348,9 +353,9 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
 
         def one_step() -> None:
             if kind == "pc":
-                st.score_into()
+                st.score_into(scale_corrector)
                 _correct(st, st.sumsq, st.sumsq_all, snr, first_elem)
-                st.score_into()
+                st.score_into(scale)
                 _predict(st, 2, 2, first_elem)
             else:
                 st.score_into()

@@ -470,8 +470,11 @@ class _ScoreNetFn(torch.autograd.Function):
     def forward(ctx, model, x, t, y, planes, inv_std, names, *params):
         from .train_engine import TrainEngine, TrainRunner
         buffers = list(model.named_buffers())
+        sync = getattr(model, "_grad_sync", None)
+        # the captured graphs bake in the gradient exchange: a runner belongs to one GradSync object (parallel.attach / detach)
+        sync_key = None if sync is None else (id(sync), bool(sync.sync_bn), sync.world)
         key = (model.precision, model.training, tuple(x.shape), None if planes is None else tuple(planes.shape), y is None,
-               inv_std is None, str(x.device), tuple(p.data_ptr() for p in params), tuple(b.data_ptr() for _, b in buffers))
+               inv_std is None, str(x.device), tuple(p.data_ptr() for p in params), tuple(b.data_ptr() for _, b in buffers), sync_key)
         runners = model.__dict__.setdefault("_train_runners", {})
         runner = runners.get(key)
         if runner is None:
@@ -484,7 +487,7 @@ class _ScoreNetFn(torch.autograd.Function):
         if runner.eng is not None:                # captured step: its forward graph re-zeroes the flat gradient buffer
             _detach_grads_aliasing(params, runner.eng.flat)
         yy = None if y is None else y.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous()
-        out, handle = runner.forward(x, t.reshape(-1).float().contiguous(), yy, planes, inv_std, getattr(model, "_grad_sync", None))
+        out, handle = runner.forward(x, t.reshape(-1).float().contiguous(), yy, planes, inv_std, sync)
         ctx.runner, ctx.handle, ctx.names, ctx.params = runner, handle, names, params
         return out
 

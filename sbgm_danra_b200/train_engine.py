@@ -23,6 +23,8 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, FMT_BF16X2, FMT_F32, call
 from .engine import ACTS, BN_EPS, GN_EPS, LN_EPS, PRECISIONS, Act, ConvW, Kernels, UNetSpec, _ptr, _stream
 
 BN_MOMENTUM = 0.1
+# "fp16x2" is an inference storage format (engine.py); a model set to it trains on the bf16x3 kernels
+TRAIN_PRECISIONS = dict(PRECISIONS, fp16x2=FMT_BF16X2)
 
 
 def _pack_oihw(w: torch.Tensor, fmt: int) -> torch.Tensor:
@@ -539,15 +541,14 @@ class TrainEngine:
         if device.type != "cuda":
             raise RuntimeError("sbgm_danra_b200 runs on CUDA devices only (no CPU fallback); got device " + str(device))
         _lib.load_library()
-        self.spec, self.device, self.fmt, self.bn_train = spec, device, PRECISIONS[precision], bn_train
+        self.spec, self.device, self.fmt, self.bn_train = spec, device, TRAIN_PRECISIONS[precision], bn_train
         self.sd = {k: v.detach() for k, v in params.items()}
         for k, v in self.sd.items():
             if v.is_floating_point() and (v.dtype != torch.float32 or not v.is_cuda):
                 raise RuntimeError(f"parameter {k} must be fp32 on CUDA for the training path, got {v.dtype} on {v.device}")
         # flat gradient buffer: parameters in state-dict order, each gradient a view (parallel.py all-reduces it in place)
         names = [k for k, v in params.items() if isinstance(v, torch.nn.Parameter) or v.requires_grad]
-        is_tail = lambda k: "time_projection_layer" in k or k.endswith("label_emb.weight")   # produced last by backward
-        self.grad_names = [k for k in names if not is_tail(k)] + [k for k in names if is_tail(k)]
+        self.grad_names = flat_order(names)
         self.offsets: Dict[str, Tuple[int, int]] = {}
         off = 0
         for k in self.grad_names:
@@ -791,6 +792,36 @@ class TrainEngine:
         tk.tape = None
         self._final = self._time = None
         return grads
+
+
+def flat_order(names: Sequence[str]) -> List[str]:
+    """Order of the parameters in the flat gradient buffer: the order in which the FORWARD pass uses them, so that backward
+    produces gradients from the END of the buffer down and the bucketed all-reduce (parallel.GradBucketer walks buckets from
+    the end) can start while backward is still running.  The time projections and the label embedding come first: their
+    gradients are the last thing backward produces (one launch for all nine heads, TrainEngine.backward).  Within a stage the
+    state-dict order is kept (stable sort)."""
+    def stage(k: str) -> int:
+        if "time_projection_layer" in k or k.endswith("label_emb.weight"):
+            return 0
+        if k.startswith("encoder."):
+            rest = k[len("encoder."):]
+            if rest.startswith("conv1."):
+                return 1
+            if rest.startswith(("conv2.", "bn1.")):
+                return 2
+            for li in range(1, 5):
+                if rest.startswith(f"layer{li}."):
+                    return 1 + 2 * li              # 3, 5, 7, 9
+            for li in range(5):
+                if rest.startswith(f"attention_layers.{li}."):
+                    return 2 + 2 * li              # after its stage: 8 (index 3), 10 (index 4)
+            return 2
+        if k.startswith("decoder.residual_layers."):
+            return 20 + int(k.split(".")[2])
+        if k.startswith("decoder.final_layer."):
+            return 40
+        return 50
+    return sorted(names, key=stage)
 
 
 class _InFlight:

@@ -14,9 +14,10 @@ from conftest import rel_l2
 
 pytestmark = pytest.mark.gpu
 
-FMTS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
-TOL = {"fp32": 2e-5, "bf16": 2e-2, "bf16x3": 1e-4}
-ELEM_TOL = {"fp32": 1e-6, "bf16": 6e-3, "bf16x3": 2e-5}   # storage round-trip only
+FMTS = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x2": 3}
+# fp16x2: float16 activations (2^-12 relative rounding on load and on store), weights exact to 22 bits
+TOL = {"fp32": 2e-5, "bf16": 2e-2, "bf16x3": 1e-4, "fp16x2": 6e-4}
+ELEM_TOL = {"fp32": 1e-6, "bf16": 6e-3, "bf16x3": 2e-5, "fp16x2": 4e-4}   # storage round-trip only
 
 
 @pytest.fixture(scope="module")
@@ -196,7 +197,7 @@ def test_groupnorm(E, prec, c, groups, hw, fused):
     out = kern.groupnorm(act_of(E, x, fmt), None if gamma is None else gamma.cuda(), None if beta is None else beta.cuda(),
                          groups, act=2 if fused else 0, skip=None if skip is None else act_of(E, skip, fmt),
                          tproj=None if tproj is None else tproj.cuda())
-    tol = {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3}[prec]
+    tol = {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3, "fp16x2": 5e-4}[prec]
     assert rel_l2(out.to_nchw().cpu(), want) < tol
 
 
@@ -210,7 +211,7 @@ def test_layernorm(E, prec, c):
     g, b = 1 + 0.2 * gen(c, seed=2), gen(c, seed=3, scale=0.2)
     want = F.layer_norm(x[0, :, 0].T, (c,), g, b, 1e-5).T[None, :, None]
     out = E.Kernels(fmt, torch.device("cuda")).layernorm(act_of(E, x, fmt), g.cuda(), b.cuda())
-    tol = {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3}[prec]
+    tol = {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3, "fp16x2": 5e-4}[prec]
     assert rel_l2(out.to_nchw().cpu(), want) < tol
 
 
@@ -238,7 +239,7 @@ def test_attention_core(E, prec, b, s, c, heads):
     want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).permute(0, 2, 1, 3).reshape(b * s, c)
     out = E.Kernels(fmt, torch.device("cuda")).attention_core(act_of(E, qkv, fmt), b, s, c, heads)
     got = out.to_nchw().cpu()[0, :, 0].T
-    assert rel_l2(got, want) < {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3}[prec]
+    assert rel_l2(got, want) < {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 8e-3, "fp16x2": 5e-4}[prec]
 
 
 @pytest.mark.parametrize("prec", list(FMTS))
@@ -330,7 +331,7 @@ def test_dsm_kernels():
         assert abs(loss.item() - want.item()) / want.item() < 1e-5
 
 
-@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3", "fp16x2"])
 @pytest.mark.parametrize("kernel", ["c64", "generic"])
 def test_projection_epilogue_and_gather(E, prec, kernel):
     """conv_up (64->64) with the projection epilogue + sbgm_final_gather == conv3x3(64->1)(conv3x3(64->64)(x))."""
@@ -353,7 +354,7 @@ def test_projection_epilogue_and_gather(E, prec, kernel):
     assert rel_l2(out.cpu(), want) < TOL[prec]
 
 
-@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3", "fp16x2"])
 @pytest.mark.parametrize("shape", [(3, 32, 32, 64, 64, True), (40, 16, 16, 128, 128, True), (160, 8, 8, 256, 512, True),
                                    (3, 16, 16, 128, 128, False),    # small grid -> split-K -> statistics not fused
                                    (2, 12, 24, 64, 128, False)],    # tile spans several partial images
@@ -372,7 +373,7 @@ def test_conv_fused_groupnorm_statistics(E, prec, shape):
     assert (stats is not None) == fused
     got = kern.groupnorm(y, gamma.cuda(), beta.cuda(), 8, stats=stats).to_nchw().cpu()
     want = F.group_norm(y.to_nchw().cpu(), 8, gamma, beta, 1e-5)
-    assert rel_l2(got, want) < {"bf16": 8e-3, "bf16x3": 3e-5}[prec]
+    assert rel_l2(got, want) < {"bf16": 8e-3, "bf16x3": 3e-5, "fp16x2": 5e-4}[prec]
 
 
 # ---- entry points added for the training step / tensor-core stem -------------------------------------------------
@@ -397,7 +398,7 @@ def test_pack_weights_batched_matches_torch(prec):
         assert rel_l2(got.cpu(), want.cpu()) < ELEM_TOL[prec]
 
 
-@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16", "fp16x2"])
 @pytest.mark.parametrize("cc,bcast,size", [(1, True, 64), (6, False, 32), (0, False, 96)])
 def test_stem_im2col_matches_unfold(E, prec, cc, bcast, size):
     fmt = FMTS[prec]
@@ -411,7 +412,7 @@ def test_stem_im2col_matches_unfold(E, prec, cc, bcast, size):
     assert rel_l2(col, want) < ELEM_TOL[prec]
 
 
-@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16", "fp16x2"])
 def test_conv2d_tc_ex_scatter_is_conv_transpose(E, prec):
     """Four scattered 1x1 convolutions (out_step 2, offsets (a, b)) = ConvTranspose2d(kernel 2, stride 2) with bias."""
     from sbgm_danra_b200._lib import call
@@ -424,8 +425,31 @@ def test_conv2d_tc_ex_scatter_is_conv_transpose(E, prec):
     for a in range(2):
         for b in range(2):
             km = wt[:, :, a, b].t().contiguous().cuda()
-            packed = km.to(torch.bfloat16) if fmt == 1 else E._split_bf16(km)
+            packed = E.pack_tc_matrix(km, fmt)
             call("sbgm_conv2d_tc_ex", xa.ptr, xa.plane, packed.data_ptr(), c_out * c_in, bd.data_ptr(), None, 0, 0, None, 0, out.ptr, out.plane,
                  fmt, n, h, w, c_in, c_out, 1, 1, 1, 0, 0, h, w, 2 * h, 2 * w, 2, a, b, 0, None, 0, torch.cuda.current_stream().cuda_stream)
     want = F.conv_transpose2d(xa.to_nchw().cpu(), wt, bias, stride=2)
     assert rel_l2(out.to_nchw().cpu(), want) < TOL[prec]
+
+
+def test_fp16x2_weight_lo_plane_carries_the_residual(E):
+    """The float16 weight planes are hi | lo * 2^11.  With weights so small that the hi plane is subnormal float16 (spacing
+    2^-24, i.e. ~1e-3 relative here) the product must still be exact to output rounding: the lo plane carries the residual.
+    Activations are chosen exactly representable so that the only other rounding is the float16 store of the result.
+    Also checks the saturating store: results beyond the float16 range clamp to +-65504 instead of becoming inf."""
+    n, c, h = 2, 64, 16
+    x = torch.round(gen(n, c, h, h, seed=1) * 2.0) * 32.0
+    tiny = gen(64, c, 1, 1, seed=2) * 2.0 ** -16
+    xa = act_of(E, x, 3)
+    assert torch.equal(xa.to_nchw().cpu(), x)
+    k = E.Kernels(3, torch.device("cuda"))
+    want = F.conv2d(x.double(), tiny.double())
+    hi_only = F.conv2d(x.double(), tiny.half().double())
+    assert rel_l2(hi_only, want) > 6e-4                                        # the case discriminates
+    got = k.conv(xa, E._Packer({"w": tiny}, 3, torch.device("cuda")).conv("w")).to_nchw().cpu().double()
+    err = rel_l2(got, want)
+    print(f"fp16x2 subnormal-hi weights: rel-L2 {err:.2e} (hi plane alone: {rel_l2(hi_only, want):.2e})")
+    assert err < 3e-4
+    big = k.conv(act_of(E, gen(n, c, h, h, seed=3), 3), E._Packer({"w": gen(64, c, 1, 1, seed=4) * 4096.0}, 3, torch.device("cuda")).conv("w"))
+    big = big.to_nchw().cpu()
+    assert torch.isfinite(big).all() and float(big.abs().max()) == 65504.0

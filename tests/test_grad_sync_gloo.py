@@ -57,6 +57,28 @@ def _worker(rank, world, port, ret):
                 want = torch.zeros(n) if name == "enc.unused" else torch.arange(n, dtype=torch.float32) * 1.5 + step
                 ok = ok and torch.allclose(flat[off:off + n], want)
         ok = ok and sync.stats["overlapped"] > 0 if bucket_bytes < (1 << 20) else ok
+    # a gradient that the first step did not produce ("enc.unused" appears from step 2 on, e.g. labels switched on): its bucket
+    # has already been exchanged when it is touched -> finish() exchanges the slice on its own and the expected set grows
+    sync = GradSync(None, 64 * 4)
+    for step in range(4):
+        flat = torch.zeros(total)
+        sync.begin(flat, layout)
+        for name in order + (["enc.unused"] if step >= 2 else []):
+            off, n = next((o, k) for nm, o, k in layout if nm == name)
+            flat[off:off + n] = torch.arange(n, dtype=torch.float32) * (rank + 1) + step
+            sync.progress([name])
+        sync.finish()
+        for name, off, n in layout:
+            want = torch.zeros(n) if (name == "enc.unused" and step < 2) else torch.arange(n, dtype=torch.float32) * 1.5 + step
+            ok = ok and torch.allclose(flat[off:off + n], want)
+    ok = ok and "enc.unused" in sync.expected
+    # bf16 exchange: the average of the bf16-rounded rank gradients
+    sync = GradSync(None, 1 << 20, grad_dtype="bf16")
+    flat = torch.full((total,), 1.0 + rank)
+    sync.begin(flat, layout)
+    sync.progress(order)
+    sync.finish()
+    ok = ok and torch.allclose(flat, torch.full((total,), 1.5))
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

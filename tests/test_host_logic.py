@@ -220,3 +220,39 @@ def test_resident_rk45_edge_cases():
     assert torch.equal(out, y0)
     out, _ = _rk45_resident(lambda t, y: -y, 0.0, 1.0, y0, 1e-8, 1e-8)            # forward direction
     assert float((out - np.exp(-1.0)).abs().max()) < 1e-7
+
+
+def test_flat_gradient_buffer_is_in_forward_order():
+    """parallel.GradBucketer launches buckets from the END of the flat buffer as backward fills them: the buffer must be in
+    forward order, with the time projections / label embedding (produced by backward's very last launch) at the start."""
+    from sbgm_danra_b200.synth import config_for, param_schema
+    from sbgm_danra_b200.train_engine import flat_order
+    cfg = config_for(n_lr=2, geo=True, seasons=True)
+    names = [k for k in param_schema(cfg) if not k.endswith(("running_mean", "running_var", "num_batches_tracked", ".W"))]
+    order = flat_order(names)
+    assert sorted(order) == sorted(names)
+    pos = {k: i for i, k in enumerate(order)}
+    first = lambda prefix: min(i for k, i in pos.items() if k.startswith(prefix) and "time_projection" not in k)
+    last = lambda prefix: max(i for k, i in pos.items() if k.startswith(prefix) and "time_projection" not in k)
+    chain = ["encoder.conv1.", "encoder.conv2.", "encoder.layer1.", "encoder.layer2.", "encoder.layer3.", "encoder.attention_layers.3.",
+             "encoder.layer4.", "encoder.attention_layers.4.", "decoder.residual_layers.0.", "decoder.residual_layers.1.",
+             "decoder.residual_layers.2.", "decoder.residual_layers.3.", "decoder.final_layer."]
+    for a, b in zip(chain, chain[1:]):
+        assert last(a) < first(b), (a, b)
+    tail = [k for k in names if "time_projection_layer" in k or k.endswith("label_emb.weight")]
+    assert tail and max(pos[k] for k in tail) < first("encoder.conv1.")
+
+
+def test_broadcast_style_write_invalidates_engine_cache_key():
+    """parallel.broadcast_parameters writes through t.detach() (shares the version counter) so that score_unet._EngineCache
+    sees the update; a write through t.data would not bump the version."""
+    import torch
+    from sbgm_danra_b200.score_unet import _versions
+    lin = torch.nn.Linear(3, 2)
+    v0 = _versions(lin)
+    with torch.no_grad():
+        lin.weight.detach().copy_(torch.ones(2, 3))
+    assert _versions(lin) != v0
+    v1 = _versions(lin)
+    lin.weight.data.copy_(torch.zeros(2, 3))          # the pattern the cache cannot see (documented in INTEGRATION.md)
+    assert _versions(lin) == v1

@@ -139,3 +139,29 @@ def test_oracle_guided_score_equals_live_reference(ref_unet, ref_samp):
         got = samplers_ref.guided_score(lambda *a: score_ref.score_forward(sd, cfg, *a), b.x, b.t, b.y, b.cond_img, b.lsm_cond,
                                         b.topo_cond, scale=1.5)
     assert rel_l2(got, want) < 2e-5
+
+
+def test_oracle_guided_pc_with_scale_clamp_equals_live_reference(ref_unet, ref_samp):
+    """Classifier-free guidance inside pc_sampler with guidance_scale_max < guidance_scale: the reference clamps the scale in
+    the corrector only (score_sampling.py:182-186) and re-reads the unclamped one in the predictor (:209-219).  The oracle
+    models that with two score callables."""
+    from oracle import samplers_ref
+    ck, bk = CASES["cin7_seasons_gn4_relu"]
+    cfg = config_for(**ck)
+    net = _reference(ref_unet, cfg, seed=2).eval()
+    sd = synth_state_dict(cfg, 2)
+    b = synth_batch(seed=57, **bk)
+    guid = {"classifier_free_guidance": {"enabled": True, "guidance_scale": 3.0, "guidance_scale_max": 1.25}}
+    torch.manual_seed(321)
+    want = ref_samp.pc_sampler(net, ref_unet.marginal_prob_std_fn, ref_unet.diffusion_coeff_fn, snr=0.16, batch_size=3, num_steps=3,
+                               device="cpu", img_size=32, y=b.y, cond_img=b.cond_img, lsm_cond=b.lsm_cond, topo_cond=b.topo_cond,
+                               cfg=guid)
+    model = lambda *a: score_ref.score_forward(sd, cfg, *a)
+    guided = lambda w: (lambda x, t: samplers_ref.guided_score(model, x, t, b.y, b.cond_img, b.lsm_cond, b.topo_cond, scale=w))
+    torch.manual_seed(321)
+    got = samplers_ref.predictor_corrector(guided(1.25), score_ref.marginal_prob_std, score_ref.diffusion_coeff, 3, 3, img_size=32,
+                                           score_predictor=guided(3.0))
+    assert rel_l2(got, want) < 1e-4
+    torch.manual_seed(321)
+    wrong = samplers_ref.predictor_corrector(guided(1.25), score_ref.marginal_prob_std, score_ref.diffusion_coeff, 3, 3, img_size=32)
+    assert rel_l2(wrong, want) > 1e-3          # one clamped scale for both halves is NOT the reference
