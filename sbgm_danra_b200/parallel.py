@@ -105,6 +105,8 @@ class GradSync:
         self.flat: Optional[torch.Tensor] = None
         self.works: list = []
         self.stats = {"buckets": 0, "overlapped": 0}
+        self.last_plan: Optional[dict] = None    # the exchange of the most recent step (what a captured graph replays)
+        self._step_overlapped: List[int] = []
 
     def begin(self, flat: torch.Tensor, layout: Sequence[Tuple[str, int, int]]) -> None:
         self.flat = flat
@@ -119,6 +121,7 @@ class GradSync:
             self.bucketer = GradBucketer(layout, flat.numel(), self.bucket_elems, self.expected)
         self.bucketer.reset()
         self.works = []
+        self._step_overlapped = []
 
     def _average(self, view: torch.Tensor) -> None:
         """In-place average of `view` over the group."""
@@ -149,14 +152,21 @@ class GradSync:
         if self.world == 1:
             return
         for b in self.bucketer.touch(names):
+            self._step_overlapped.append(b)
             self._launch(b, True)
 
     def finish(self) -> None:
         if self.world == 1:
             return
-        for b in self.bucketer.remaining():
+        tail = self.bucketer.remaining()
+        for b in tail:
             self.bucketer.launched[b] = True
             self._launch(b, False)
+        mb = lambda b: round((self.bucketer.bounds[b][1] - self.bucketer.bounds[b][0]) * 4 / 2 ** 20, 3)
+        self.last_plan = {"buckets": len(self.bucketer.bounds), "overlapped": len(self._step_overlapped),
+                          "overlapped_mb": [mb(b) for b in self._step_overlapped], "after_backward_mb": [mb(b) for b in tail],
+                          "late_gradients": len(self.bucketer.late), "dtype": self.grad_dtype,
+                          "op": "ncclAllReduce AVG" if self.native_avg else "all_reduce SUM then scale"}
         offs = {name: (off, numel) for name, off, numel in self.bucketer.layout}
         for name in self.bucketer.late:
             off, numel = offs[name]
