@@ -260,17 +260,23 @@ def run_reference(args):
 
 
 # ---- our arm ---------------------------------------------------------------------------------------------
-def _event_ms(torch, fn, iters, flush=None):
+def _event_ms(torch, fn, iters, flush=None, reps: int = 1):
+    """Median CUDA-event time of `fn` (per call when reps > 1).  A launch that precedes the first event keeps the GPU busy
+    while the host enqueues (the L2 flush when given, else a ~100 us spin kernel): without it the events would bracket
+    the HOST's launch latency of a microsecond-scale kernel, not the kernel."""
     times = []
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
+        else:
+            torch.cuda._sleep(200000)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(reps):
+            fn()
         b.record()
         b.synchronize()
-        times.append(a.elapsed_time(b))
+        times.append(a.elapsed_time(b) / reps)
     return statistics.median(times)
 
 
@@ -334,7 +340,7 @@ def time_conv_family(net, peaks, precision: str):
         for _ in range(2):
             fn()
         cold += _event_ms(torch, fn, 5, flush)
-        warm += _event_ms(torch, fn, 5)
+        warm += _event_ms(torch, fn, 5, reps=4)
         flops += 2.0 * rec["n"] * ho * wo * cw.cin * cw.cout * cw.kh * cw.kw
         launches += 1
     ach = flops / (warm * 1e-3) / 1e12
@@ -342,8 +348,9 @@ def time_conv_family(net, peaks, precision: str):
             "launches": launches, "algorithmic_flops": flops, "ms_warm": warm, "ms_cold": cold,
             "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
             "tensor_pipe_frac": TENSOR_PRODUCTS[precision] * ach / peaks["bf16_tflops"],
-            "note": "sum of per-launch CUDA-event medians; warm = the launch repeated back to back (operands L2-resident where they fit), "
-                    "cold = 256 MiB L2 flush before every launch; achieved/frac from the warm sum"}
+            "note": "sum of per-launch CUDA-event medians; warm = the same launch four times back to back behind a spin kernel "
+                    "(operands L2-resident where they fit, launch overlap as in the captured graph), cold = 256 MiB L2 flush before "
+                    "every launch; achieved/frac from the warm sum"}
 
 
 def gpu_eager_baseline(dev):
@@ -362,7 +369,7 @@ def gpu_eager_baseline(dev):
             with torch.no_grad():
                 for _ in range(3):
                     ref.forward(b_x, b_t)
-                ms = _event_ms(torch, lambda: ref.forward(b_x, b_t), 7)
+                ms = _event_ms(torch, lambda: ref.forward(b_x, b_t), 7, flush=None)
                 steps = 10
                 a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -376,6 +383,8 @@ def gpu_eager_baseline(dev):
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
     out["sample"] = "forward: median of 7 after 3 warm-ups; EM: 10 eager steps of the reference sampler, extrapolated linearly to 500"
+    out["note"] = ("TF32 moves only the contraction kernels (4.9 -> 2.4 ms of the 22 ms forward); 15 ms of it is ATen's NCHW fp32 "
+                   "upsample_bilinear2d kernel, 5 launches (profiles/r02_torch_eager_kernel_breakdown.txt)")
     return out
 
 

@@ -234,6 +234,29 @@ int sbgm_select_step_row(const float* table, int cols, const int32_t* step_count
 int sbgm_back_transform(const float* x, float* y, size_t count, float pre_shift, float scale, float shift, float lo, float hi,
                         int do_clamp, int do_exp, void* stream);
 
+/* y = back_transform(x) as above AND, per sample (n samples of `per` values), the numbers the reference's extreme-value
+ * sentinel needs (sbgm/utils.py:1642-1671 report_precip_extremes: `torch.quantile(flat, 0.999, dim=1)`, `max`; driven by
+ * sbgm/training.py:359-398 on the ground truth and :700-755 on generated fields):
+ *   out[n][4] = { quantile `quantile` with linear interpolation (ATen's rank / lerp arithmetic), max, min, 0 }.
+ * One block per sample, exact radix select in shared memory; x and y may alias. */
+int sbgm_back_transform_extremes(const float* x, float* y, int n, int per, float pre_shift, float scale, float shift, float lo,
+                                 float hi, int do_clamp, int do_exp, float quantile, float* out, void* stream);
+
+/* ---- device-resident Dormand-Prince stages of ode_sampler (sbgm/score_sampling.py:239-300: scipy RK45 on the host) ----
+ * State y[n], stages K[7][n] and results are float64 on the device; coefficient rows are HOST arrays (a row of the Butcher
+ * tableau, at most 7 entries).
+ *   combine   : out = y + h * sum_{s < n_stages} coef[s] K[s]   (out and/or its float32 copy out_f32, the network's input)
+ *   rhs       : k_out = scale * score                           (dx/dt = -1/2 g(t)^2 score, :287-291)
+ *   error_norm: *out_sumsq = sum_i ( h * sum_s coef[s] K[s][i] / (atol + max(|y_i|, |y_new_i|) * rtol) )^2, deterministic
+ *               (y_new NULL: |y_i| alone -- the norms of scipy's select_initial_step with h = 1, coef = unit vector);
+ *               scratch holds sbgm_rk45_scratch_doubles(n) doubles. */
+int sbgm_rk45_combine(const double* y, const double* k_stages, size_t n, int n_stages, const double* coef_host, double h,
+                      double* out, float* out_f32, void* stream);
+int sbgm_rk45_rhs(const float* score, double scale, double* k_out, size_t n, void* stream);
+size_t sbgm_rk45_scratch_doubles(size_t n);
+int sbgm_rk45_error_norm(const double* k_stages, size_t n, int n_stages, const double* coef_host, double h, const double* y,
+                         const double* y_new, double atol, double rtol, double* scratch, double* out_sumsq, void* stream);
+
 /* ---- ensemble statistics (BASELINE.json parity criterion; evaluation itself is sbgm/evaluate_sbgm/, out of scope) ----
  * members[m][pixels] fp32 -> per-pixel mean, std (Bessel-corrected), and, given truth[pixels], the ensemble CRPS
  * E|X - y| - 1/2 E|X - X'| (crps may be NULL).  Lets a sampled ensemble be scored on the device before any D2H copy. */
