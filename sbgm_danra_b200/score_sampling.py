@@ -29,6 +29,7 @@ from ._lib import stats as _lib_stats
 
 logger = logging.getLogger(__name__)
 
+CFG_WIDE_BELOW = 16        # classifier-free guidance as one 2B-wide evaluation below this many members
 num_steps = 800
 signal_to_noise_ratio = 0.16
 error_tolerance = 1e-5
@@ -71,12 +72,12 @@ def _next_seed() -> int:
 
 
 def _is_native(score_model) -> bool:
-    """The fused, graph-captured step serves a ScoreNet of this package in eval mode.  In `.train()` (the reference's
-    generation quirk: BatchNorm with batch statistics while sampling, evaluate_sbgm/generation.py:47) every step goes
-    through `ScoreNet.forward`, i.e. the training-graph forward with batch statistics and running-stat updates
-    (itself replayed from a CUDA graph after two steps)."""
+    """The fused, graph-captured step serves a ScoreNet of this package: in eval mode on the inference engine (`_NativeStep`),
+    in `.train()` -- the reference's generation quirk: `self.model.eval` without parentheses leaves BatchNorm on batch
+    statistics while sampling (evaluate_sbgm/generation.py:47) -- on the training engine's forward (`_TrainModeStep`), with
+    the batch statistics, the running-statistics updates and, for a sharded ensemble, their all-gather inside the captured step."""
     from .score_unet import ScoreNet
-    return isinstance(score_model, ScoreNet) and not score_model.training
+    return isinstance(score_model, ScoreNet)
 
 
 def _cfg_scale(cfg, clamp: bool) -> Optional[float]:
@@ -178,12 +179,23 @@ class _NativeStep:
         self.cfg_scale = cfg_scale
         cc = eng.enc.cin - 1
         self.partial = eng.enc.alloc_partial(planes_batch, size, size) if cc > 0 else None
+        # classifier-free guidance: the conditional and the null branch as ONE evaluation of 2B members while the GPU is not
+        # yet full (score_sampling.py:10-56 runs two B-wide forwards; below ~16 members a forward is launch/latency-bound and
+        # the 2B-wide one costs about the same as one B-wide).  SBGM_B200_CFG_WIDE=0: always two evaluations.
+        self.wide = cfg_scale is not None and batch < CFG_WIDE_BELOW and os.environ.get("SBGM_B200_CFG_WIDE", "1") != "0"
         if cfg_scale is not None:
             self.partial_u = None if self.partial is None else eng.enc.alloc_partial(planes_batch, size, size)
             self.y_u = None if self.y is None else torch.zeros_like(self.y)
             self.score_c = torch.empty_like(self.x)
             self.score_u = torch.empty_like(self.x)
             self.tproj_u = torch.empty((batch, eng.tp.c_total), dtype=torch.float32, device=dev) if has_y else self.tproj
+        if self.wide:
+            self.x2 = torch.zeros((2 * batch, 1, size, size), dtype=torch.float32, device=dev)
+            self.score2 = torch.empty_like(self.x2)
+            self.partial2 = eng.enc.alloc_partial(2 * batch, size, size) if cc > 0 else None      # per member: [cond x B ; null x B]
+            self.y2 = torch.zeros(2 * batch, dtype=torch.int64, device=dev) if has_y else None
+            self.tproj2 = (torch.empty((2 * batch, eng.tp.c_total), dtype=torch.float32, device=dev) if has_y
+                           else self.tproj_row.expand(2 * batch, eng.tp.c_total))
         self.graph = None
         self.per_replay = 0
 
@@ -215,18 +227,31 @@ class _NativeStep:
             self.eng.enc.stem_partial(planes, self.size, self.size, out=self.partial)
             if self.cfg_scale is not None:
                 self.eng.enc.stem_partial(planes_u, self.size, self.size, out=self.partial_u)
+        if self.wide:
+            if self.y2 is not None:
+                self.y2[:self.b].copy_(self.y)
+                self.y2[self.b:].zero_()                              # null token
+            if self.partial2 is not None:
+                for half, src in enumerate((self.partial, self.partial_u)):
+                    dst_t = self.partial2 if isinstance(self.partial2, torch.Tensor) else self.partial2.buf
+                    src_t = src if isinstance(src, torch.Tensor) else src.buf
+                    nd = dst_t.dim() - 4                              # leading plane dimension of the split-bf16 format
+                    dsl = (slice(None),) * nd + (slice(half * self.b, (half + 1) * self.b),)
+                    shape = tuple(dst_t.shape[:nd]) + (self.b,) + tuple(dst_t.shape[nd + 1:])
+                    dst_t[dsl].copy_(src_t.expand(shape) if src_t.shape[nd] == 1 else src_t)
 
-    def _forward(self, partial, y, tproj, out) -> None:
+    def _forward(self, partial, y, tproj, out, x=None) -> None:
         eng = self.eng
+        x = self.x if x is None else x
         if self.tproj_all is not None:
             call("sbgm_select_step_row", self.tproj_all.data_ptr(), self.tproj_all.shape[1], self.counter.data_ptr(),
                  self.tproj_row.data_ptr(), _eng._stream())
         else:
-            eng.tp(self.table, y, rows=self.b, t_row_stride=0, t_step_stride=STEP_COLS, step_counter=self.counter, out=tproj)
+            eng.tp(self.table, y, rows=x.shape[0], t_row_stride=0, t_step_stride=STEP_COLS, step_counter=self.counter, out=tproj)
         if partial is None:
-            fmaps = eng.enc.forward(self.x, None, tproj)
+            fmaps = eng.enc.forward(x, None, tproj)
         else:
-            fmaps = eng.enc.forward(self.x, None, tproj, partial=partial)
+            fmaps = eng.enc.forward(x, None, tproj, partial=partial)
         eng.dec.forward(fmaps, tproj, self.inv_std, inv_std_stride=0, inv_std_step_stride=STEP_COLS,
                         step_counter=self.counter, dst=out)
 
@@ -235,12 +260,68 @@ class _NativeStep:
         not: score_sampling.py:182-186 vs :209-219); default = the plan's scale."""
         if self.cfg_scale is None:
             self._forward(self.partial, self.y, self.tproj, self.score)
+        elif self.wide:
+            self.x2[:self.b].copy_(self.x)
+            self.x2[self.b:].copy_(self.x)
+            self._forward(self.partial2, self.y2, self.tproj2, self.score2, x=self.x2)
+            call("sbgm_cfg_combine", self.score2[:self.b].data_ptr(), self.score2[self.b:].data_ptr(),
+                 self.cfg_scale if scale is None else scale, self.score.data_ptr(), self.score.numel(), _eng._stream())
         else:
             self._forward(self.partial, self.y, self.tproj, self.score_c)
             self._forward(self.partial_u, self.y_u, self.tproj_u, self.score_u)
             call("sbgm_cfg_combine", self.score_c.data_ptr(), self.score_u.data_ptr(), self.cfg_scale if scale is None else scale,
                  self.score.data_ptr(), self.score.numel(), _eng._stream())
         return self.score
+
+
+class _TrainModeStep(_NativeStep):
+    """A sampler step of a ScoreNet left in `.train()` (evaluate_sbgm/generation.py:47): every network evaluation normalises
+    with the statistics of the CURRENT batch of members (the ensemble members are coupled) and moves the running statistics
+    (momentum 0.1, unbiased variance) and `num_batches_tracked`, exactly as torch's BatchNorm2d does under `no_grad`.  The
+    evaluation is `TrainEngine.forward` in sampler mode (step-table time projections and 1/std, no tape, no gradient buffer),
+    so the whole step still captures into ONE CUDA graph.  With `set_ensemble_shard(..., group=g)` and fewer local members than
+    the ensemble has, the per-channel partial sums are all-gathered over `g` inside the graph (synchronised BatchNorm): R ranks
+    x B/R members reproduce the single-process statistics of all B members.  Classifier-free guidance keeps the reference's
+    two separate evaluations (each with its own batch statistics): never the 2B-wide form."""
+
+    def __init__(self, model, batch: int, size: int, n_steps: int, has_y: bool, planes, planes_u, cfg_scale: Optional[float],
+                 sync_group=None):
+        super().__init__(model, batch, size, n_steps, has_y, 0, cfg_scale)
+        from .train_engine import TrainEngine
+        tensors = dict(model.named_parameters())
+        tensors.update(model.named_buffers())
+        self.train_eng = TrainEngine(tensors, model.spec(), model.precision, self.dev, bn_train=True)
+        self.train_eng.tk.sync_bn = sync_group
+        self.bn_counters = [m.num_batches_tracked for m in model._bn_modules()]
+        self.wide = False
+        # conditioning planes as static buffers (the training engine's stem reads them every evaluation)
+        self.partial = None if planes is None else torch.empty_like(planes)
+        self.partial_u = None if planes_u is None else torch.empty_like(planes_u)
+
+    def load(self, table: torch.Tensor, seed: int, y, planes, planes_u) -> None:
+        self.table.copy_(table)
+        self.counter.copy_(torch.tensor(_seed_words(seed), dtype=torch.int32))
+        if self.tproj_all is not None:
+            self.eng.tp(self.table, None, rows=self.table.shape[0], t_row_stride=STEP_COLS, t_step_stride=0, out=self.tproj_all)
+        if self.y is not None:
+            self.y.copy_(y.to(device=self.dev, dtype=torch.int64).reshape(-1))
+        if self.partial is not None:
+            self.partial.copy_(planes)
+        if self.partial_u is not None:
+            self.partial_u.copy_(planes_u)
+
+    def _forward(self, partial, y, tproj, out, x=None) -> None:
+        x = self.x if x is None else x
+        if self.tproj_all is not None:
+            call("sbgm_select_step_row", self.tproj_all.data_ptr(), self.tproj_all.shape[1], self.counter.data_ptr(),
+                 self.tproj_row.data_ptr(), _eng._stream())
+        else:
+            self.eng.tp(self.table, y, rows=x.shape[0], t_row_stride=0, t_step_stride=STEP_COLS, step_counter=self.counter, out=tproj)
+        # weights were packed when the plan was built (the plan is keyed on the parameter versions); the running statistics are
+        # read and updated live
+        self.train_eng.forward(x, None, y, partial, None,
+                               sampler=dict(tproj=tproj, inv_std=(self.inv_std, 0, STEP_COLS, self.counter), dst=out))
+        torch._foreach_add_(self.bn_counters, 1)
 
 
 class _GenericStep:
@@ -317,7 +398,8 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
     total = _state.members_total if sharded else batch_size
 
     lanes = int(os.environ.get("SBGM_B200_LANES", "1"))
-    if native and use_graph and kind == "em" and lanes == 2 and n_steps > 1 and batch_size >= 16 and batch_size % 2 == 0:
+    if (native and use_graph and kind == "em" and lanes == 2 and n_steps > 1 and batch_size >= 16 and batch_size % 2 == 0
+            and not score_model.training):
         return _sample_em_two_lanes(score_model, table, seed, scale, dev, batch_size, n_steps, img_size, std1, first_elem,
                                     y, cond_img, lsm_cond, topo_cond)
 
@@ -331,15 +413,25 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
                                                  _strip_mask(lsm_cond), _strip_mask(topo_cond))
                 if planes_u.shape[0] != planes.shape[0]:
                     planes_u = planes_u.expand(planes.shape[0], -1, -1, -1).contiguous()
-            key = (id(eng), kind, batch_size, img_size, n_steps, scale, scale_corrector, float(snr), y is not None,
-                   0 if planes is None else planes.shape[0], first_elem, total, id(_state.group) if sharded else 0, use_graph)
+            train_mode = bool(score_model.training)
+            # train-mode BatchNorm couples the members: a sharded ensemble synchronises the statistics over the shard group
+            bn_group = _state.group if (train_mode and _state.members_total not in (None, batch_size) and _state.group is not None) else None
+            # eval: keyed on the packed engine (rebuilt when a parameter changes); train mode: on the model and its parameter
+            # versions (the running statistics move every evaluation and must not invalidate the plan)
+            owner = ((id(score_model),) + tuple((p_.data_ptr(), p_._version) for p_ in score_model.parameters())) if train_mode else id(eng)
+            key = (owner, kind, batch_size, img_size, n_steps, scale, scale_corrector, float(snr), y is not None,
+                   0 if planes is None else planes.shape[0], first_elem, total, id(_state.group) if (sharded or bn_group is not None) else 0,
+                   use_graph, train_mode)
             st = next((p for k, p in _PLAN_CACHE if k == key), None)
             if st is None:
                 # cached across calls and rewritten in place: must be ordinary tensors even when the first caller is inside
                 # torch.inference_mode() (inference tensors cannot be updated in place by a later no_grad caller)
                 with torch.inference_mode(False):
-                    st = _NativeStep(score_model, batch_size, img_size, n_steps, y is not None,
-                                     0 if planes is None else planes.shape[0], scale)
+                    if train_mode:
+                        st = _TrainModeStep(score_model, batch_size, img_size, n_steps, y is not None, planes, planes_u, scale, bn_group)
+                    else:
+                        st = _NativeStep(score_model, batch_size, img_size, n_steps, y is not None,
+                                         0 if planes is None else planes.shape[0], scale)
                     st.sumsq = torch.zeros(batch_size, dtype=torch.float32, device=dev)
                     st.sumsq_all = torch.zeros(total, dtype=torch.float32, device=dev) if sharded else st.sumsq
                 _PLAN_CACHE.insert(0, (key, st))
@@ -483,6 +575,106 @@ _DP_B = (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84)
 _DP_E = (-71 / 57600, 0.0, 71 / 16695, -71 / 1920, 17253 / 339200, -22 / 525, 1 / 40)
 
 
+class _TorchStages:
+    """Stage arithmetic of `_rk45_resident` with torch float64 ops: what runs when the state is a CPU tensor, i.e. in the
+    host-logic tests that pin the CONTROLLER to scipy step for step (tests/test_host_logic.py).  `fun(t, y64) -> f64`."""
+
+    def __init__(self, y0: torch.Tensor, fun) -> None:
+        self.fun, self.n = fun, y0.numel()
+        self.y = y0.to(torch.float64).reshape(-1).clone()
+        self.K = torch.empty((7, self.n), dtype=torch.float64, device=y0.device)
+        self.y_new = None
+
+    def _comb(self, coefs, h: float) -> torch.Tensor:
+        if not coefs:
+            return self.y
+        a = torch.tensor(coefs, dtype=torch.float64, device=self.y.device)
+        return self.y + torch.mv(self.K[:len(coefs)].T, a) * h
+
+    def eval(self, slot: int, t: float, coefs, h: float) -> None:
+        self.K[slot] = self.fun(t, self._comb(coefs, h))
+
+    def propose(self, coefs, h: float, t_new: float) -> None:
+        self.y_new = self._comb(coefs, h)
+        self.K[6] = self.fun(t_new, self.y_new)
+
+    def sumsq(self, coefs, h: float, atol: float, rtol: float, with_new: bool) -> float:
+        a = torch.tensor(coefs, dtype=torch.float64, device=self.y.device)
+        v = torch.mv(self.K[:len(coefs)].T, a) * h
+        ref = torch.maximum(self.y.abs(), self.y_new.abs()) if with_new else self.y.abs()
+        return float(((v / (atol + ref * rtol)) ** 2).sum())
+
+    def sumsq_state(self, atol: float, rtol: float) -> float:
+        return float(((self.y / (atol + self.y.abs() * rtol)) ** 2).sum())
+
+    def accept(self) -> None:
+        self.y = self.y_new
+        self.K[0] = self.K[6]
+
+    def result(self) -> torch.Tensor:
+        return self.y
+
+
+class _KernelStages:
+    """The same stage arithmetic on the device (csrc/post_sampler.cu): a stage combination is one launch that also writes
+    the float32 copy the network reads, the right-hand side -1/2 g^2 score is scaled into its float64 stage slot by one launch,
+    and the scaled error norm is a deterministic two-launch reduction -- one double crosses to the host per attempted step.
+    `fun(t, x32) -> (score32, scale)` with x32 / score32 flat float32 tensors of the state's size."""
+
+    def __init__(self, y0: torch.Tensor, fun) -> None:
+        from . import _lib
+        self.fun, self.n, self.dev = fun, y0.numel(), y0.device
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.y = y0.to(torch.float64).reshape(-1).clone()
+        self.y_new = torch.empty(self.n, **f64)
+        self.K = torch.empty((7, self.n), **f64)
+        self.x32 = torch.empty(self.n, dtype=torch.float32, device=self.dev)
+        self.scratch = torch.empty(_lib.query("sbgm_rk45_scratch_doubles", self.n), **f64)
+        self.out = torch.empty(1, **f64)
+
+    @staticmethod
+    def _row(coefs):
+        import ctypes
+        return (ctypes.c_double * 7)(*coefs, *([0.0] * (7 - len(coefs))))
+
+    def _rhs(self, slot: int, t: float) -> None:
+        score, scale = self.fun(t, self.x32)
+        score = score.reshape(-1).contiguous().float()
+        call("sbgm_rk45_rhs", score.data_ptr(), float(scale), self.K[slot].data_ptr(), self.n, _eng._stream())
+
+    def eval(self, slot: int, t: float, coefs, h: float) -> None:
+        with torch.cuda.device(self.dev):
+            call("sbgm_rk45_combine", self.y.data_ptr(), self.K.data_ptr(), self.n, len(coefs), self._row(coefs), float(h), None,
+                 self.x32.data_ptr(), _eng._stream())
+            self._rhs(slot, t)
+
+    def propose(self, coefs, h: float, t_new: float) -> None:
+        with torch.cuda.device(self.dev):
+            call("sbgm_rk45_combine", self.y.data_ptr(), self.K.data_ptr(), self.n, len(coefs), self._row(coefs), float(h),
+                 self.y_new.data_ptr(), self.x32.data_ptr(), _eng._stream())
+            self._rhs(6, t_new)
+
+    def sumsq(self, coefs, h: float, atol: float, rtol: float, with_new: bool) -> float:
+        with torch.cuda.device(self.dev):
+            call("sbgm_rk45_error_norm", self.K.data_ptr(), self.n, len(coefs), self._row(coefs), float(h), self.y.data_ptr(),
+                 self.y_new.data_ptr() if with_new else None, float(atol), float(rtol), self.scratch.data_ptr(), self.out.data_ptr(),
+                 _eng._stream())
+        return float(self.out.item())
+
+    def sumsq_state(self, atol: float, rtol: float) -> float:
+        with torch.cuda.device(self.dev):      # the state itself plays the role of a one-stage "K"
+            call("sbgm_rk45_error_norm", self.y.data_ptr(), self.n, 1, self._row([1.0]), 1.0, self.y.data_ptr(), None, float(atol),
+                 float(rtol), self.scratch.data_ptr(), self.out.data_ptr(), _eng._stream())
+        return float(self.out.item())
+
+    def accept(self) -> None:
+        self.y, self.y_new = self.y_new, self.y
+        self.K[0].copy_(self.K[6])
+
+    def result(self) -> torch.Tensor:
+        return self.y
+
+
 def _rk45_resident(fun, t0: float, t_bound: float, y0: torch.Tensor, rtol: float, atol: float):
     """Adaptive Dormand-Prince 5(4) with the state, the seven stages and the error estimate resident on `y0`'s device.
 
@@ -491,39 +683,32 @@ def _rk45_resident(fun, t0: float, t_bound: float, y0: torch.Tensor, rtol: float
     select_initial_step, norm = RMS): same initial-step rule, error norm, SAFETY 0.9 / MIN_FACTOR 0.2 / MAX_FACTOR 10 step
     control and end-point clipping, so the accepted step sequence is SciPy's up to float64 summation order.  Only the scalar
     error norm crosses to the host (one read per attempted step, it decides accept / reject); SciPy's host version moves
-    the whole float64 state across PCIe twice per right-hand side.  Returns (y at t_bound -- or the last accepted state if
-    the step size underflows, which is what the reference reads from `res.y[:, -1]` -- and the number of `fun` calls)."""
+    the whole float64 state across PCIe twice per right-hand side.  On a CUDA state the stage arithmetic runs in this repo's
+    kernels (`_KernelStages`; `fun(t, x32) -> (score32, scale)`), on a CPU state in torch (`_TorchStages`; `fun(t, y64) -> f64`,
+    the controller's host-logic tests).  Returns (y at t_bound -- or the last accepted state if the step size underflows, which
+    is what the reference reads from `res.y[:, -1]` -- and the number of `fun` calls)."""
     import math
-    f64 = dict(dtype=torch.float64, device=y0.device)
-    y = y0.to(torch.float64).reshape(-1).clone()
-    n = y.numel()
+    ops = _KernelStages(y0, fun) if y0.is_cuda else _TorchStages(y0, fun)
+    n = ops.n
     rtol = max(float(rtol), 100 * np.finfo(float).eps)              # validate_tol
     direction = 1.0 if t_bound >= t0 else -1.0
-    A = [torch.tensor(a, **f64) for a in _DP_A]
-    B, E = torch.tensor(_DP_B, **f64), torch.tensor(_DP_E, **f64)
-    K = torch.empty((7, n), **f64)
     nfev = 0
-
-    def rms(v: torch.Tensor) -> float:
-        return float(torch.linalg.vector_norm(v)) / math.sqrt(n)
-
-    def f_at(t: float, yy: torch.Tensor) -> torch.Tensor:
-        nonlocal nfev
-        nfev += 1
-        return fun(t, yy)
+    rms = lambda sumsq: math.sqrt(max(sumsq, 0.0) / n)
 
     t = float(t0)
-    f = f_at(t, y)
-    # select_initial_step
     interval = abs(t_bound - t0)
+    ops.eval(0, t, (), 0.0)                                          # f = fun(t0, y0)
+    nfev += 1
     if n == 0 or interval == 0.0:
-        return y, nfev
-    scale = atol + y.abs() * rtol
-    d0, d1 = rms(y / scale), rms(f / scale)
+        return ops.result(), nfev
+    # select_initial_step (norms scaled by atol + |y| rtol)
+    d0 = rms(ops.sumsq_state(atol, rtol))
+    d1 = rms(ops.sumsq((1.0,), 1.0, atol, rtol, False))
     h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
     h0 = min(h0, interval)
-    f1 = f_at(t + h0 * direction, y + h0 * direction * f)
-    d2 = rms((f1 - f) / scale) / h0
+    ops.eval(1, t + h0 * direction, (1.0,), h0 * direction)          # f1 = fun(t0 + h0, y0 + h0 f)
+    nfev += 1
+    d2 = rms(ops.sumsq((-1.0, 1.0), 1.0, atol, rtol, False)) / h0
     h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1 / 5)
     h_abs = min(100 * h0, h1, interval)
 
@@ -533,38 +718,38 @@ def _rk45_resident(fun, t0: float, t_bound: float, y0: torch.Tensor, rtol: float
         rejected = False
         while True:
             if h_abs < min_step:
-                return y, nfev                                       # TOO_SMALL_STEP: the reference reads the last state
+                return ops.result(), nfev                            # TOO_SMALL_STEP: the reference reads the last state
             t_new = t + h_abs * direction
             if direction * (t_new - t_bound) > 0:
                 t_new = t_bound
             h = t_new - t
             h_abs = abs(h)
-            K[0] = f                                                 # rk_step
-            for s in range(1, 6):
-                K[s] = f_at(t + _DP_C[s] * h, y + torch.mv(K[:s].T, A[s]) * h)
-            y_new = y + h * torch.mv(K[:6].T, B)
-            f_new = f_at(t + h, y_new)
-            K[6] = f_new
-            scale = atol + torch.maximum(y.abs(), y_new.abs()) * rtol
-            err = rms(torch.mv(K.T, E) * h / scale)
+            for s in range(1, 6):                                    # rk_step: K[0] holds f(t, y)
+                ops.eval(s, t + _DP_C[s] * h, _DP_A[s], h)
+            ops.propose(_DP_B, h, t + h)                             # y_new and K[6] = f(t + h, y_new)
+            nfev += 6
+            err = rms(ops.sumsq(_DP_E, h, atol, rtol, True))
             if err < 1:
                 factor = 10.0 if err == 0 else min(10.0, 0.9 * err ** -0.2)
                 h_abs *= min(1.0, factor) if rejected else factor
                 break
             h_abs *= max(0.2, 0.9 * err ** -0.2)
             rejected = True
-        t, y, f = t_new, y_new, f_new
-    return y, nfev
+        t = t_new
+        ops.accept()
+    return ops.result(), nfev
 
 
 def ode_sampler(score_model, marginal_prob_std, diffusion_coeff, num_steps=100, batch_size=64, atol=error_tolerance,
                 rtol=error_tolerance, device="cuda", z=None, eps=1e-3, img_size=64, y=None, cond_img=None,
                 lsm_cond=None, topo_cond=None, cfg=None):
-    """Probability-flow ODE through scipy RK45 (score_sampling.py:239-300): the integrator runs on the host
-    in float64 exactly as in the reference; only the score evaluations run on the GPU.
+    """Probability-flow ODE with the adaptive RK45 of `scipy.integrate.solve_ivp` (score_sampling.py:239-300).
 
-    `SBGM_B200_ODE=resident` (opt-in) keeps the float64 state on the device and steps it with `_rk45_resident`, the same
-    Dormand-Prince controller without the per-evaluation PCIe round trip of the state."""
+    Default: the float64 state, the seven stages and the error estimate stay on the device (`_rk45_resident`: SciPy's
+    Dormand-Prince controller restated and pinned to it step for step, stage arithmetic in csrc/post_sampler.cu); one double
+    is read back per attempted step.  `SBGM_B200_ODE=host` runs SciPy itself on the host exactly as the reference does, with the
+    float64 state crossing PCIe twice per score evaluation (kept as the cross-check: both give the same result to integrator
+    round-off, tests/test_gpu_model.py)."""
     from scipy import integrate
     dev = torch.device(device)
     if z is None:
@@ -585,13 +770,15 @@ def ode_sampler(score_model, marginal_prob_std, diffusion_coeff, num_steps=100, 
         g = float(diffusion_coeff(torch.tensor(t)))
         return -0.5 * (g ** 2) * s.cpu().numpy().reshape(-1).astype(np.float64)
 
-    if os.environ.get("SBGM_B200_ODE", "host") == "resident":
-        def rhs_resident(t, xflat):
+    if dev.type != "cuda":
+        raise RuntimeError("samplers run on CUDA devices only (no CPU fallback); got device=" + str(device))
+    if os.environ.get("SBGM_B200_ODE", "resident") != "host":
+        def rhs_resident(t, x32):
             ts = torch.full((shape[0],), float(t), device=dev, dtype=torch.float32)
             with torch.no_grad():
-                s = score_model(xflat.to(torch.float32).reshape(shape), ts, y, cond_img, lsm_cond, topo_cond)
+                s = score_model(x32.reshape(shape), ts, y, cond_img, lsm_cond, topo_cond)
             g = float(diffusion_coeff(torch.tensor(t)))
-            return (-0.5 * (g ** 2)) * s.reshape(-1).to(torch.float64)
+            return s, -0.5 * (g ** 2)
 
         with torch.no_grad():
             out, nfev = _rk45_resident(rhs_resident, 1.0, eps, init.reshape(-1), rtol, atol)

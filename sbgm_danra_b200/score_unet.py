@@ -202,7 +202,8 @@ class Encoder(nn.Module):
                 topo_cond: Optional[torch.Tensor] = None):
         _require_cuda(self.conv1.weight, "Encoder")
         if self.training and any(isinstance(m, nn.BatchNorm2d) for m in self.modules()):
-            raise NotImplementedError("train-mode BatchNorm (batch statistics) is not on the CUDA path yet; call .eval()")
+            raise NotImplementedError("standalone Encoder.forward serves eval mode; train-mode BatchNorm (batch statistics) runs "
+                                      "through ScoreNet.forward / loss_fn / the samplers (train_engine.py) -- call .eval() here")
         dev = self.conv1.weight.device
         with torch.no_grad(), torch.cuda.device(dev):
             enc = self._engine()

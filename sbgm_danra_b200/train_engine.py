@@ -646,22 +646,31 @@ class TrainEngine:
         self.plan.run()            # every forward / data-gradient pack of the step: one batched launch
 
     # -- forward ----------------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor], planes: Optional[torch.Tensor],
-                inv_std: Optional[torch.Tensor]) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, t: Optional[torch.Tensor], y: Optional[torch.Tensor], planes: Optional[torch.Tensor],
+                inv_std: Optional[torch.Tensor], *, sampler: Optional[dict] = None) -> torch.Tensor:
+        """`sampler` (score_sampling._TrainModeStep: a sampler step with batch-statistics BatchNorm, captured in a CUDA graph):
+        dict(tproj=[n, c_total] time projections already computed for the step, inv_std=(table column, row stride, step stride,
+        device step counter), dst=output tensor); no gradient buffer is set up and the recorded tape is dropped."""
         tk, fmt, dev = self.tk, self.fmt, self.device
         tape = Tape(fmt, dev)
         tk.tape = tape
         self.tape = tape
-        self.flat = torch.zeros(self.flat_numel, dtype=torch.float32, device=dev)
+        self._sampler = sampler
         self.touched = {}
         n, _, h, w = x.shape
         cc = self.cin - 1
         if cc > 0 and (planes is None or planes.shape[1] != cc):
             raise AssertionError(f"encoder expects {cc} conditioning channels")
-        t = t.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
         yy = None if y is None else y.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
-        tproj = self.tp(t, yy)
-        dtproj = torch.zeros_like(tproj)
+        if sampler is not None:
+            self.flat = None
+            tproj = sampler["tproj"]
+            dtproj = tproj                     # never written: no backward runs on a sampler step
+        else:
+            self.flat = torch.zeros(self.flat_numel, dtype=torch.float32, device=dev)
+            t = t.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+            tproj = self.tp(t, yy)
+            dtproj = torch.zeros_like(tproj)
         tape.keep += [tproj, t, yy, x, planes]
         col = lambda table, name: self.tp.cols(table, name)
 
@@ -727,21 +736,29 @@ class TrainEngine:
                                dtproj=col(dtproj, blk["name"]), fused=st2)
             if blk["attn"] is not None:
                 out = _attention_block(tk, blk["attn"], out)
-        res = torch.empty((n, 1, 2 * out.h, 2 * out.w), dtype=torch.float32, device=dev)
+        smp = getattr(self, "_sampler", None)
+        res = smp["dst"] if smp is not None else torch.empty((n, 1, 2 * out.h, 2 * out.w), dtype=torch.float32, device=dev)
+        # 1 / std per member (training) or per sampler step (row of the step table selected by the device step counter)
+        iv = (_ptr(inv_std), 1, 0, None) if smp is None else (_ptr(smp["inv_std"][0]), smp["inv_std"][1], smp["inv_std"][2],
+                                                               _ptr(smp["inv_std"][3]))
         up = tk.upsample2x(out) if self.spec.use_resize_conv else None
         if up is None:
             a = tk.conv_transpose2x(out, self.final_up)
-            call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None,
+            call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), *iv,
                  res.data_ptr(), a.n, a.h, a.w, a.c, 1, _stream())
         elif fmt != FMT_F32 and tk.k._c64_ok(up, self.final_up.fwd, 1, 1):
             # the 64 -> 1 convolution rides in conv_up's epilogue (projection); conv_up's output is kept for the backward
             a, pr = tk.conv(up, self.final_up, pad=1, proj=self.final_w[0])
-            call("sbgm_final_gather", pr.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None, res.data_ptr(), a.n, a.h, a.w,
+            call("sbgm_final_gather", pr.data_ptr(), self.final_b.data_ptr(), *iv, res.data_ptr(), a.n, a.h, a.w,
                  _stream())
         else:
             a = tk.conv(up, self.final_up, pad=1)
-            call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), 1, 0, None,
+            call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), *iv,
                  res.data_ptr(), a.n, a.h, a.w, a.c, 1, _stream())
+        if smp is not None:                    # a sampler step: nothing will run backward -- drop the tape and its activations
+            self.tape = tk.tape = None
+            self._final = self._time = self._sampler = None
+            return res
         self._final = (a, inv_std)
         return res
 

@@ -204,6 +204,30 @@ def test_guided_pc_clamps_the_scale_in_the_corrector_only():
     assert rel_l2(got2.cpu(), want) < 2e-3
 
 
+@pytest.mark.parametrize("precision,kind,shared", [("bf16x3", "em", True), ("bf16x3", "pc", False), ("fp32", "em", False)])
+def test_guided_sampling_as_one_double_width_evaluation_equals_two_evaluations(monkeypatch, precision, kind, shared):
+    """Below 16 members classifier-free guidance runs the conditional and the null branch as ONE 2B-member evaluation
+    (conditioning partial sums, labels and time projections stacked per member); SBGM_B200_CFG_WIDE=0 runs the reference's two
+    B-member evaluations (score_sampling.py:10-56).  Same samples to rounding (the two batch sizes tile differently)."""
+    from oracle.synth import synth_batch
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    ck = dict(n_lr=2, geo=True, seasons=True)
+    net, _, _ = _model(ck, precision)
+    b = synth_batch(batch=4, size=32, shared_cond=shared, **ck)
+    guid = {"classifier_free_guidance": {"enabled": True, "guidance_scale": 1.5}}
+    fn = ss.Euler_Maruyama_sampler if kind == "em" else ss.pc_sampler
+    outs = []
+    for wide in ("1", "0"):
+        monkeypatch.setenv("SBGM_B200_CFG_WIDE", wide)
+        ss.clear_sampler_cache()
+        ss.manual_seed(SEED_NOISE)
+        outs.append(fn(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=4, num_steps=3, device=DEV, img_size=32, y=_cuda(b.y),
+                       cond_img=_cuda(b.cond_img), lsm_cond=_cuda(b.lsm_cond), topo_cond=_cuda(b.topo_cond), cfg=guid).cpu())
+    ss.clear_sampler_cache()
+    assert torch.isfinite(outs[0]).all() and rel_l2(outs[0], outs[1]) < (1e-5 if precision == "fp32" else 1e-4)
+
+
 def test_generic_callable_path_equals_graph_path():
     """A plain callable goes through the un-captured loop; it must reproduce the CUDA-graph path."""
     from sbgm_danra_b200 import score_sampling as ss
@@ -362,12 +386,10 @@ def test_ode_sampler_matches_oracle():
     assert err < 1e-3
 
 
-@pytest.mark.skipif(os.environ.get("SBGM_B200_ODE") != "resident",
-                    reason="opt-in path (SBGM_B200_ODE=resident): integrator pinned to SciPy on the CPU "
-                           "(test_host_logic.py::test_resident_rk45_follows_scipy_step_for_step); device run not yet made")
-def test_ode_sampler_resident_integrator_matches_host_integrator():
-    """SBGM_B200_ODE=resident: the float64 state stays on the device; same Philox start, same score -> the SciPy-driven
-    result to integrator round-off."""
+def test_ode_sampler_resident_integrator_matches_host_integrator(monkeypatch):
+    """The default ode_sampler keeps the float64 state on the device and steps it with this repo's Dormand-Prince stage
+    kernels; SBGM_B200_ODE=host runs scipy.integrate.solve_ivp on the host as the reference does.  Same Philox start, same
+    score -> the same adaptive step sequence and the same result to integrator round-off."""
     from oracle.synth import config_for, synth_batch, synth_state_dict
     from sbgm_danra_b200 import score_sampling as ss
     from sbgm_danra_b200._smoke import build_model
@@ -377,15 +399,49 @@ def test_ode_sampler_resident_integrator_matches_host_integrator():
     b = synth_batch(batch=2, size=32, n_lr=1, shared_cond=True)
     outs = {}
     for mode in ("host", "resident"):
-        os.environ["SBGM_B200_ODE"] = mode
-        try:
-            ss.manual_seed(13)
-            outs[mode] = ss.ode_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=2, atol=1e-3, rtol=1e-3,
-                                        device=DEV, img_size=32, cond_img=b.cond_img.to(DEV)).cpu()
-        finally:
-            os.environ["SBGM_B200_ODE"] = "resident"
+        monkeypatch.setenv("SBGM_B200_ODE", mode)
+        ss.manual_seed(13)
+        outs[mode] = ss.ode_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=2, atol=1e-3, rtol=1e-3,
+                                    device=DEV, img_size=32, cond_img=b.cond_img.to(DEV)).cpu()
     assert outs["resident"].dtype == outs["host"].dtype == torch.float64
     assert rel_l2(outs["resident"], outs["host"]) < 1e-5
+
+
+def test_rk45_stage_kernels_match_float64_torch():
+    """csrc/post_sampler.cu against the same arithmetic in torch float64: stage combination (+ its float32 copy), scaled
+    right-hand side, and the deterministic scaled error norm."""
+    import ctypes
+    from sbgm_danra_b200 import _lib
+    from sbgm_danra_b200._lib import call
+    n = 100_003
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(n, generator=g, dtype=torch.float64)
+    K = torch.randn(7, n, generator=g, dtype=torch.float64)
+    coef = [0.3, -1.25, 2.0, 0.125, -0.7]
+    h = -0.0173
+    yd, Kd = y.to(DEV), K.to(DEV)
+    out, out32 = torch.empty(n, dtype=torch.float64, device=DEV), torch.empty(n, dtype=torch.float32, device=DEV)
+    row = (ctypes.c_double * 7)(*coef, 0.0, 0.0)
+    st = torch.cuda.current_stream().cuda_stream
+    call("sbgm_rk45_combine", yd.data_ptr(), Kd.data_ptr(), n, 5, row, h, out.data_ptr(), out32.data_ptr(), st)
+    want = y + torch.mv(K[:5].T, torch.tensor(coef, dtype=torch.float64)) * h
+    assert float((out.cpu() - want).abs().max()) < 1e-14 and torch.equal(out32.cpu(), out.cpu().float())
+    score = torch.randn(n, generator=g)
+    kd = torch.empty(n, dtype=torch.float64, device=DEV)
+    call("sbgm_rk45_rhs", score.to(DEV).data_ptr(), -312.5, kd.data_ptr(), n, st)
+    assert torch.equal(kd.cpu(), score.double() * -312.5)
+    e = [-71 / 57600, 0.0, 71 / 16695, -71 / 1920, 17253 / 339200, -22 / 525, 1 / 40]
+    ynew = torch.randn(n, generator=g, dtype=torch.float64)
+    scratch = torch.empty(_lib.query("sbgm_rk45_scratch_doubles", n), dtype=torch.float64, device=DEV)
+    res = torch.empty(1, dtype=torch.float64, device=DEV)
+    call("sbgm_rk45_error_norm", Kd.data_ptr(), n, 7, (ctypes.c_double * 7)(*e), h, yd.data_ptr(), ynew.to(DEV).data_ptr(), 1e-5, 1e-5,
+         scratch.data_ptr(), res.data_ptr(), st)
+    v = torch.mv(K.T, torch.tensor(e, dtype=torch.float64)) * h / (1e-5 + torch.maximum(y.abs(), ynew.abs()) * 1e-5)
+    assert abs(float(res.item()) - float((v ** 2).sum())) / float((v ** 2).sum()) < 1e-12
+    first = float(res.item())
+    call("sbgm_rk45_error_norm", Kd.data_ptr(), n, 7, (ctypes.c_double * 7)(*e), h, yd.data_ptr(), ynew.to(DEV).data_ptr(), 1e-5, 1e-5,
+         scratch.data_ptr(), res.data_ptr(), st)
+    assert float(res.item()) == first            # fixed summation order
 
 
 def test_two_lane_em_reproduces_one_lane_bitwise(monkeypatch):
@@ -495,3 +551,57 @@ def test_sampler_first_called_under_inference_mode_is_reusable_outside_it(kind):
     with torch.inference_mode():
         third = run()
     assert torch.isfinite(first).all() and torch.equal(first, second) and torch.equal(first, third)
+
+
+def _close_dict(a, b):
+    assert set(a) == set(b), (a, b)
+    for k, v in a.items():
+        if isinstance(v, list):
+            assert len(v) == len(b[k]) and all(abs(x - y) <= 1e-5 * max(1.0, abs(y)) for x, y in zip(v, b[k])), (k, v, b[k])
+        else:
+            assert v == b[k], (k, v, b[k])
+
+
+def test_extreme_value_sentinel_matches_reference_golden():
+    """monitoring.report_precip_extremes (one kernel: per-sample 0.999 quantile by radix select + max) against the outputs of
+    the reference's own sbgm/utils.py::report_precip_extremes (tests/golden/monitoring_golden.json): same dict, same messages."""
+    from oracle import monitoring_ref
+    from sbgm_danra_b200 import monitoring
+    with open(os.path.join(GOLDEN_DIR, "monitoring_golden.json")) as f:
+        gold = json.load(f)
+    for name, x in monitoring_ref.cases().items():
+        q, mx, mn = monitoring_ref.quantile_and_max(x)
+        _, stats = monitoring.back_transform_with_extremes(x.to(DEV))
+        stats = stats.cpu()
+        assert torch.allclose(stats[:, 0], q, rtol=1e-6, atol=1e-6), name      # ATen's rank / lerp arithmetic, exact selection
+        assert torch.equal(stats[:, 1], mx) and torch.equal(stats[:, 2], mn), name
+        for cap in (500.0, 50.0):
+            msgs = []
+            got = monitoring.report_precip_extremes(x.to(DEV), name=name, cap_mm_day=cap, logger=msgs.append)
+            _close_dict(got, gold[f"{name}/cap{cap:g}"]["result"])
+            assert msgs == gold[f"{name}/cap{cap:g}"]["messages"], (name, cap)
+    with pytest.raises(RuntimeError):
+        monitoring.report_precip_extremes(torch.zeros(2, 1, 4, 4), name="cpu")     # no CPU path
+
+
+def test_generation_monitor_back_transforms_flags_and_clamps_on_device():
+    """monitoring.monitor_generated = sbgm/training.py:700-755 on the device: log-z-score back-transform fused with the
+    sentinel's statistics, then the configured clamp to [0, clamp_max_mm]; against the oracle's transform + sentinel + clamp."""
+    from oracle import monitoring_ref, transforms_ref as tr
+    from sbgm_danra_b200 import monitoring, special_transforms as st
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(6, 1, 32, 32, generator=g)
+    x[2, 0, 5, 5] = 4.2                                            # exp(4.2 * 1.9 + 0.3) ~ 4e3 mm/day: an extreme
+    kw = dict(scale_type="log_zscore", glob_mean_log=0.3, glob_std_log=1.9, glob_min_log=None, glob_max_log=None, buffer_frac=0.5)
+    want_bt = torch.from_numpy(tr.prcp_log_back(x.numpy(), **kw)).float()
+    want_chk = monitoring_ref.report_precip_extremes(want_bt, "generated_hr", 500.0, logger=lambda *_: None)
+    assert want_chk["has_extreme"]
+    msgs = []
+    got, chk = monitoring.monitor_generated(x.to(DEV), st.PrcpLogBackTransform(**kw), threshold_mm=500.0, clamp_in_generation=True,
+                                            clamp_max_mm=300.0, log=msgs.append)
+    _close_dict(chk, want_chk)
+    want = monitoring_ref.clamp_generated(want_bt, 300.0)
+    assert torch.allclose(got.cpu(), want, rtol=2e-5, atol=2e-5) and float(got.max()) == 300.0
+    assert any("Clamped generated samples to max 300.0" in m for m in msgs)
+    got2, chk2 = monitoring.monitor_generated(x.to(DEV), st.PrcpLogBackTransform(**kw), threshold_mm=1e6, clamp_in_generation=True)
+    assert chk2 == {"has_extreme": False} and torch.allclose(got2.cpu(), want_bt, rtol=2e-5, atol=2e-5)   # nothing flagged: no clamp

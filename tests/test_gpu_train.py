@@ -562,6 +562,46 @@ def test_sampling_in_train_mode_uses_batch_statistics():
     print(f"train-mode EM (5 steps) rel-L2 vs oracle = {err:.3e}")
     assert err < 2e-3
     assert not torch.equal(net.encoder.bn1.running_mean, rm0)
+    # the step is ONE captured graph on the training engine's forward (score_sampling._TrainModeStep)
+    plan = ss._PLAN_CACHE[0][1]
+    assert isinstance(plan, ss._TrainModeStep) and plan.graph is not None
+    nbt = int(net.encoder.bn1.num_batches_tracked)
+    ss.manual_seed(21)              # a second call re-uses the plan; batch statistics do not depend on the running ones
+    again = ss.Euler_Maruyama_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=4, num_steps=5, device=DEV,
+                                      img_size=32, cond_img=b.cond_img.to(DEV)).cpu()
+    assert ss._PLAN_CACHE[0][1] is plan and torch.equal(again, got)
+    assert int(net.encoder.bn1.num_batches_tracked) == nbt + 5          # one update per network evaluation, as torch counts them
+    ss.clear_sampler_cache()
+
+
+def test_train_mode_pc_sampling_with_labels_and_guidance_matches_oracle():
+    """Predictor-corrector in `.train()` with season labels and classifier-free guidance: four batch-statistics evaluations
+    per step (conditional + null branch for the corrector and for the predictor, each with its OWN batch statistics, as the
+    reference's two separate forwards have -- never the 2B-wide form)."""
+    from oracle import samplers_ref, score_ref
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling as ss
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import diffusion_coeff_fn, marginal_prob_std_fn
+    ck = dict(n_lr=2, geo=True, seasons=True)
+    cfg = config_for(**ck)
+    sd = synth_state_dict(cfg)
+    net = build_model(cfg, sd, "bf16x3", DEV).train()
+    b = synth_batch(batch=4, size=32, shared_cond=True, **ck)
+    guid = {"classifier_free_guidance": {"enabled": True, "guidance_scale": 1.5}}
+    c = lambda v: v.to(DEV)
+    ss.manual_seed(5)
+    got = ss.pc_sampler(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=4, num_steps=3, snr=0.16, device=DEV, img_size=32,
+                        y=c(b.y), cond_img=c(b.cond_img), lsm_cond=c(b.lsm_cond), topo_cond=c(b.topo_cond), cfg=guid).cpu()
+    model = lambda *a: score_ref.score_forward(sd, cfg, *a, bn_train=True)
+    score = lambda x, t: samplers_ref.guided_score(model, x, t, b.y, b.cond_img, b.lsm_cond, b.topo_cond, scale=1.5)
+    with torch.no_grad():
+        want = samplers_ref.predictor_corrector(score, score_ref.marginal_prob_std, score_ref.diffusion_coeff, 4, 3, img_size=32,
+                                                noise=samplers_ref.philox_noise(5))
+    err = rel_l2(got, want)
+    print(f"train-mode guided PC (3 steps) rel-L2 vs oracle = {err:.3e}")
+    assert err < 2e-3 and isinstance(ss._PLAN_CACHE[0][1], ss._TrainModeStep)
+    ss.clear_sampler_cache()
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16"])

@@ -99,6 +99,38 @@ def main():
             print(f"[multi-gpu x{world}] {name}: sharded vs single-GPU rel-L2 = {err:.3e}")
             ok = ok and err < 1e-4
         dist.barrier()
+    # train-mode BatchNorm while sampling (generation.py:47 quirk): the members are coupled through the batch statistics, so a
+    # sharded ensemble all-gathers the per-channel partial sums inside the captured step (synchronised BatchNorm); the gathered
+    # shards must reproduce rank 0 sampling all members alone, and the running statistics must move identically
+    net.train()
+    state0 = {k: v.clone() for k, v in net.state_dict().items()}
+    for name, fn in (("em", ss.Euler_Maruyama_sampler), ("pc", ss.pc_sampler)):
+        net.load_state_dict(state0)
+        ss.manual_seed(321)
+        ss.set_ensemble_shard(rank * per, total, dist.group.WORLD)
+        part = fn(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=per, num_steps=steps, device=dev, img_size=size,
+                  y=cut(b.y, sl), cond_img=cut(b.cond_img, sl), lsm_cond=cut(b.lsm_cond, sl), topo_cond=cut(b.topo_cond, sl))
+        rm_sharded = net.encoder.layer3[0].bn1.running_mean.clone()
+        gathered = torch.empty((total, 1, size, size), device=dev)
+        dist.all_gather_into_tensor(gathered, part.contiguous())
+        ss.clear_sampler_cache()
+        if rank == 0:
+            net.load_state_dict(state0)
+            ss.manual_seed(321)
+            ss.set_ensemble_shard(0, None, None)
+            full = fn(net, marginal_prob_std_fn, diffusion_coeff_fn, batch_size=total, num_steps=steps, device=dev,
+                      img_size=size, y=cut(b.y, slice(None)), cond_img=cut(b.cond_img, slice(None)),
+                      lsm_cond=cut(b.lsm_cond, slice(None)), topo_cond=cut(b.topo_cond, slice(None)))
+            err = float((gathered - full).norm() / full.norm())
+            rm_err = float((rm_sharded - net.encoder.layer3[0].bn1.running_mean).norm() / net.encoder.layer3[0].bn1.running_mean.norm())
+            print(f"[multi-gpu x{world}] {name}, train-mode BatchNorm with synchronised statistics: sharded vs single-GPU rel-L2 = {err:.3e}; "
+                  f"running_mean rel {rm_err:.1e}")
+            ok = ok and err < 1e-4 and rm_err < 1e-5
+            ss.clear_sampler_cache()
+        dist.barrier()
+    net.load_state_dict(state0)
+    net.eval()
+    ss.set_ensemble_shard(0, None, None)
     ok = train_check(rank, world, dev, net, cfg, ck) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
