@@ -320,6 +320,7 @@ def time_conv_family(net, peaks, precision: str):
     k = eng.dec.k
     cold = warm = flops = 0.0
     launches = 0
+    rows = []
     for rec in trace:
         if rec["c64"] or rec["proj"]:
             continue
@@ -339,11 +340,19 @@ def time_conv_family(net, peaks, precision: str):
 
         for _ in range(2):
             fn()
-        cold += _event_ms(torch, fn, 5, flush)
-        warm += _event_ms(torch, fn, 5, reps=4)
-        flops += 2.0 * rec["n"] * ho * wo * cw.cin * cw.cout * cw.kh * cw.kw
+        c_ms, w_ms = _event_ms(torch, fn, 5, flush), _event_ms(torch, fn, 5, reps=4)
+        fl = 2.0 * rec["n"] * ho * wo * cw.cin * cw.cout * cw.kh * cw.kw
+        rows.append(f"{rec['n']:3d} x {rec['h']:3d}x{rec['w']:<5d} {cw.cin:4d}->{cw.cout:<4d} k{cw.kh} s{rec['stride']}  {fl / 1e9:7.2f} GFLOP  "
+                    f"warm {w_ms * 1e3:7.1f} us ({fl / (w_ms * 1e-3) / 1e12:6.1f} TFLOP/s)  cold {c_ms * 1e3:7.1f} us")
+        cold += c_ms
+        warm += w_ms
+        flops += fl
         launches += 1
     ach = flops / (warm * 1e-3) / 1e12
+    if os.environ.get("SBGM_BENCH_FAMILY_TABLE"):             # per-layer table for profiles/
+        with open(os.environ["SBGM_BENCH_FAMILY_TABLE"], "w") as f:
+            f.write(f"conv_tc_kernel launches of one evaluation ({precision}, 64 members, 128x128), one by one; tokens x 1 = Linear layers\n")
+            f.write("\n".join(rows) + f"\ntotal: {flops / 1e9:.1f} GFLOP, warm {warm * 1e3:.1f} us, cold {cold * 1e3:.1f} us\n")
     return {"kernel": "conv_tc_kernel (generic tcgen05 implicit GEMM: every strided / 1x1 / Linear / 3x3 layer of one evaluation except the 64->64 ones)",
             "launches": launches, "algorithmic_flops": flops, "ms_warm": warm, "ms_cold": cold,
             "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],

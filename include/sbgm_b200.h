@@ -162,6 +162,16 @@ int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, i
 int sbgm_layernorm(const void* x, size_t x_plane, const float* gamma, const float* beta, float eps,
                    void* y, size_t y_plane, int fmt, int rows, int c, void* stream);
 
+/* The attention half of ImageSelfAttention.forward (score_unet.py:139-143) in one launch, single-plane tensor-core formats
+ * (SBGM_FMT_F16, SBGM_FMT_BF16):   out = x + out_proj( concat_h softmax(Q_h K_h^T / sqrt(d)) V_h ) + bias
+ *   qkv[b*s][3c]  packed in_proj output (q | k | v), x[b*s][c] the block input (residual), w_out the packed out_proj weight
+ *   ([planes][c][c] K-major; two float16 planes hi | lo * 2^11 in SBGM_FMT_F16, `w_plane` apart), bias[c] fp32, out[b*s][c].
+ * Scores, probabilities and the per-head outputs never leave the SM (tcgen05 products with TMEM accumulators).
+ * sbgm_attention_out_proj_supported: 1 for d = c / heads in {32, 64}, c in {128, 256} and s = 256 or s | 128. */
+int sbgm_attention_out_proj_supported(int fmt, int b, int s, int c, int heads);
+int sbgm_attention_out_proj(const void* qkv, const void* x, const void* w_out, size_t w_plane, const float* bias, void* out,
+                            int fmt, int b, int s, int c, int heads, void* stream);
+
 /* ---- bilinear x2 upsample (nn.Upsample(scale_factor=2, bilinear, align_corners=False),
  *      score_unet.py:467, :583) --------------------------------------------------------------- */
 int sbgm_upsample2x(const void* x, size_t x_plane, void* y, size_t y_plane, int fmt, int n, int h, int w, int c,

@@ -47,6 +47,7 @@ def _stream() -> int:
 # the launch sequence so that its in-graph cost can be read off as a difference.  Results are garbage when set.
 import os as _os
 _SKIP = frozenset(x for x in _os.environ.get("SBGM_B200_SKIP", "").split(",") if x)
+_ATTN_FUSED = _os.environ.get("SBGM_B200_ATTN_FUSED", "1") != "0"     # 0: attention core and out-projection as two launches
 
 
 # Measurement hook (bench.py `roofline.family`): when set to a list, every convolution / Linear launch of a forward appends
@@ -305,6 +306,18 @@ class Kernels:
         call("sbgm_upsample2x", x.ptr, x.plane, out.ptr, out.plane, self.fmt, x.n, x.h, x.w, x.c, _stream())
         return out
 
+    def attention_out_proj_ok(self, b: int, s: int, c: int, heads: int) -> bool:
+        """True if the attention core + out-projection + residual run as one tcgen05 kernel (csrc/attn_fused.cu)."""
+        return (_ATTN_FUSED and "attn_core" not in _SKIP and
+                bool(_lib.query("sbgm_attention_out_proj_supported", self.fmt, b, s, c, heads)))
+
+    def attention_out_proj(self, qkv: Act, x: Act, cw: ConvW, b: int, s: int, c: int, heads: int) -> Act:
+        """x + out_proj(softmax(Q K^T / sqrt(d)) V): scores, probabilities and head outputs stay on the SM."""
+        out = Act(self.fmt, 1, 1, b * s, c, self.device)
+        call("sbgm_attention_out_proj", qkv.ptr, x.ptr, cw.w.data_ptr(), cw.plane, cw.bias.data_ptr(), out.ptr, self.fmt, b, s, c, heads,
+             _stream())
+        return out
+
     def attention_core(self, qkv: Act, b: int, s: int, c: int, heads: int) -> Act:
         out = Act(self.fmt, 1, 1, b * s, c, self.device)
         if "attn_core" in _SKIP:
@@ -332,8 +345,11 @@ def attention_block(k: Kernels, aw: AttentionW, x: Act) -> Act:
     b, s, c = x.n, x.h * x.w, x.c
     h1 = k.layernorm(tok, *aw.ln1)
     qkv = k.linear(h1, aw.in_proj)
-    att = k.attention_core(qkv, b, s, c, aw.heads)
-    h = k.linear(att, aw.out_proj, residual=tok)
+    if k.attention_out_proj_ok(b, s, c, aw.heads):
+        h = k.attention_out_proj(qkv, tok, aw.out_proj, b, s, c, aw.heads)
+    else:
+        att = k.attention_core(qkv, b, s, c, aw.heads)
+        h = k.linear(att, aw.out_proj, residual=tok)
     g = k.layernorm(h, *aw.ln2)
     g = k.linear(g, aw.ff0, act=ACT_GELU)
     y = k.linear(g, aw.ff2, residual=h)

@@ -453,3 +453,32 @@ def test_fp16x2_weight_lo_plane_carries_the_residual(E):
     big = k.conv(act_of(E, gen(n, c, h, h, seed=3), 3), E._Packer({"w": gen(64, c, 1, 1, seed=4) * 4096.0}, 3, torch.device("cuda")).conv("w"))
     big = big.to_nchw().cpu()
     assert torch.isfinite(big).all() and float(big.abs().max()) == 65504.0
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "bf16"])
+@pytest.mark.parametrize("b,s,c,heads", [(2, 64, 256, 4), (4, 64, 256, 4), (3, 64, 256, 4), (8, 16, 128, 4), (5, 16, 256, 8), (2, 256, 128, 4),
+                                         (1, 256, 256, 4), (1, 128, 128, 2), (3, 32, 128, 4), (64, 4, 128, 4)])
+def test_attention_out_proj_fused_kernel(E, prec, b, s, c, heads):
+    """csrc/attn_fused.cu: x + out_proj(softmax(Q K^T / sqrt(d)) V) in one tcgen05 kernel (scores / probabilities in TMEM and
+    shared memory) against torch fp32 on the stored operands, and against the two-launch path it replaces.  Shapes: two images
+    per query tile, partial last tile (3 x 64 tokens), 8 and 32 images per tile, 16 x 16 maps (two query tiles per image),
+    one image per tile, head dims 32 and 64."""
+    fmt = FMTS[prec]
+    dev = torch.device("cuda")
+    k = E.Kernels(fmt, dev)
+    assert k.attention_out_proj_ok(b, s, c, heads)
+    qkv = gen(1, 3 * c, 1, b * s, seed=1)
+    x = gen(1, c, 1, b * s, seed=2)
+    w, bias = gen(c, c, seed=3, scale=c ** -0.5), gen(c, seed=4, scale=0.1)
+    qa, xa = act_of(E, qkv, fmt), act_of(E, x, fmt)
+    qs, xs = qa.to_nchw().cpu()[0, :, 0].T, xa.to_nchw().cpu()[0, :, 0].T            # what the kernel reads
+    d = c // heads
+    q, kk, v = (z.reshape(b, s, heads, d).permute(0, 2, 1, 3) for z in qs.reshape(b, s, 3 * c).chunk(3, dim=-1))
+    att = (torch.softmax(q @ kk.transpose(-1, -2) / math.sqrt(d), -1) @ v).permute(0, 2, 1, 3).reshape(b * s, c)
+    want = xs + att @ w.T + bias
+    cw = E._Packer({"w": w, "b": bias}, fmt, dev).conv("w", "b")
+    got = k.attention_out_proj(qa, xa, cw, b, s, c, heads).to_nchw().cpu()[0, :, 0].T
+    err = rel_l2(got, want)
+    two = k.linear(k.attention_core(qa, b, s, c, heads), cw, residual=xa).to_nchw().cpu()[0, :, 0].T
+    print(f"attention + out-proj fused [{prec}] b={b} s={s} c={c} heads={heads}: rel-L2 {err:.2e} (two-launch path {rel_l2(two, want):.2e})")
+    assert err < {"fp16x2": 8e-4, "bf16": 8e-3}[prec]
