@@ -162,6 +162,16 @@ int sbgm_groupnorm_apply(const void* x, size_t x_plane, const float* partials, i
 int sbgm_layernorm(const void* x, size_t x_plane, const float* gamma, const float* beta, float eps,
                    void* y, size_t y_plane, int fmt, int rows, int c, void* stream);
 
+/* act( LayerNorm(x; gamma, beta, eps) W^T + b ) over token rows x[rows][cin] -> y[rows][cout] with the LayerNorm folded into the
+ * tensor-core GEMM (ImageSelfAttention: ln1 -> mha.in_proj, ln2 -> ff.0 + GELU; score_unet.py:139-146).  `weight` holds
+ * W diag(gamma) packed for `fmt`, `bias` = b + W beta, `colsum[cout]` the row sums of the packed weight:
+ *     y = rstd_t (x W'^T - mean_t colsum) + b'
+ * The per-token mean / rstd are computed inside the kernel from the operand tiles as they pass through shared memory; the
+ * normalised tensor is never written.  act: SBGM_ACT_NONE or SBGM_ACT_GELU.  Tensor-core formats only. */
+int sbgm_linear_ln_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                      const float* colsum, float eps, void* out, size_t out_plane, int fmt, int rows, int cin, int cout,
+                      int act, void* stream);
+
 /* The attention half of ImageSelfAttention.forward (score_unet.py:139-143) in one launch, single-plane tensor-core formats
  * (SBGM_FMT_F16, SBGM_FMT_BF16):   out = x + out_proj( concat_h softmax(Q_h K_h^T / sqrt(d)) V_h ) + bias
  *   qkv[b*s][3c]  packed in_proj output (q | k | v), x[b*s][c] the block input (residual), w_out the packed out_proj weight

@@ -38,6 +38,10 @@ struct ConvTcParams {
   float* ws;           // [splits][pixels][cout] fp32
   float* gn_partials;  // [n][gn_chunks][cout/8][2] or nullptr: fused GroupNorm statistics (8-channel granularity)
   int gn_chunks;
+  // LayerNorm folded into a Linear layer (LNF kernels): y = LN(x) W^T + b  ==  rstd_t (x W'^T - mean_t colsum) + b'  with
+  // W' = W diag(gamma), b' = b + W beta, colsum_n = sum_c W'[n][c]; mean_t / rstd_t come from the A tiles as they pass through
+  const float* ln_colsum;
+  float ln_eps;
   EpilogueParams ep;
 };
 
@@ -74,7 +78,7 @@ struct ConvTcThreads {
   static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;
 };
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false>
 __global__ void __launch_bounds__(ConvTcThreads<BLOCK_N>::kThreads, ConvTcThreads<BLOCK_N>::kMinCtas)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const ConvTcParams p) {
@@ -102,7 +106,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      // LNF: the epilogue warps read every A tile too (row statistics) and release the stage together with the MMA
+      mbar_init(empty_bar(s), LNF ? 1 + 4 * ConvTcThreads<BLOCK_N>::kEpiGroups : 1);
     }
     mbar_init(tmem_full_bar, 1);
     if (SLAB) {
@@ -252,6 +257,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float proj_acc[kProjMax];
 #pragma unroll
     for (int q = 0; q < kProjMax; ++q) proj_acc[q] = 0.0f;
+    float ln_mean = 0.0f, ln_rstd = 1.0f;
+    if (LNF) {
+      // LayerNorm statistics of this thread's row (token) over ALL input channels, read from the A tiles while the MMA consumes
+      // them: 64 channels per k-block, 16-byte chunks at the 128-byte-swizzle positions TMA wrote them to
+      float sum = 0.0f, sq = 0.0f;
+      uint32_t stage = 0, phase = 0;
+      for (int kbi = 0; kbi < num_kb; ++kbi) {
+        mbar_wait(full_bar(stage), phase);
+        const uint32_t a_row = smem_base + stage * Cfg::kStageBytes + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int pl = 0; pl < kAPl; ++pl) {
+            uint4 u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                         : "r"(a_row + pl * Cfg::kABytes + ((j ^ (row & 7)) << 4)));
+            float t[8];
+            if (TcFmt<FMT>::kHalf) unpack_f16x8(u, t); else unpack_bf16x8(u, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += t[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            sum += v[e];
+            sq = fmaf(v[e], v[e], sq);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      const float inv_c = 1.0f / static_cast<float>(p.cin_blocks * 64);
+      ln_mean = sum * inv_c;
+      ln_rstd = rsqrtf(fmaxf(sq * inv_c - ln_mean * ln_mean, 0.0f) + p.ln_eps);
+    }
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     auto load_acc = [&](int c0, uint32_t (&r)[32]) {
@@ -283,6 +324,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t ra[32], rb[32];
         load_acc(c0, ra);
         load_acc(c0 + 32, rb);
+        if (LNF) {
+          const float* cs = p.ln_colsum + co0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            ra[j] = __float_as_uint(ln_rstd * fmaf(-ln_mean, __ldg(cs + j), __uint_as_float(ra[j])));
+            rb[j] = __float_as_uint(ln_rstd * fmaf(-ln_mean, __ldg(cs + 32 + j), __uint_as_float(rb[j])));
+          }
+        }
         if (!PROJ && p.gn_partials) {
           // this warp's 32 rows lie in one image (host-checked): chunk = which 32-row strip of that image
           int img, chunk;
@@ -469,7 +518,7 @@ void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
   (void)pow2_floor;
 }
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false>
 static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
                                cudaStream_t st) {
   constexpr int kAPl = TcFmt<FMT>::kAPlanes, kBPl = TcFmt<FMT>::kBPlanes;
@@ -477,7 +526,7 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
   static_assert(!STAGED || Cfg::kBarOffset >= 4u * (BLOCK_N / 64) * kAPl * kStageBlockBytes, "the staging area must fit in the pipeline stages");
   static_assert(kBPl * BLOCK_N <= 512, "accumulator exceeds the 512 TMEM columns");
   static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
-  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED, SLAB>;
+  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED, SLAB, LNF>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -504,6 +553,14 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
 template <int FMT, int BLOCK_N, int kStages>
 static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
                           cudaStream_t st) {
+  if (p.ln_colsum) {          // LayerNorm-folded Linear layers (in_proj: no activation; ff.0: GELU), staged store only
+    if (BLOCK_N > 128 || !p.ep.staged) { set_error("conv2d_tc: the LayerNorm-folded form needs 64/128-wide staged tiles"); return 1; }
+    constexpr int BN = BLOCK_N > 128 ? 128 : BLOCK_N;
+    if (p.ep.act == SBGM_ACT_NONE) return launch_conv_tc_inst<FMT, BN, kStages, SBGM_ACT_NONE, 0, true, false, true>(ta, tb, to, p, m_tiles, st);
+    if (p.ep.act == SBGM_ACT_GELU) return launch_conv_tc_inst<FMT, BN, kStages, SBGM_ACT_GELU, 0, true, false, true>(ta, tb, to, p, m_tiles, st);
+    set_error("conv2d_tc: LayerNorm-folded Linear supports no activation or GELU");
+    return 1;
+  }
   if (p.ep.proj_w) {
     if (BLOCK_N != 64) { set_error("conv2d_tc: projection epilogue needs a 64-wide tile"); return 1; }
     return launch_conv_tc_inst<FMT, 64, (FMT == SBGM_FMT_BF16X2 ? 2 : 4), SBGM_ACT_NONE, 1, false>(ta, tb, to, p, m_tiles, st);
@@ -597,7 +654,7 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
                           void* out, size_t out_plane, int fmt, int n, int h, int w, int cin, int cout,
                           int kh, int kw, int stride, int pad, int act, const float* proj_w, int n_proj,
                           float* proj_out, void* workspace, size_t workspace_bytes, float* gn_partials,
-                          const ConvTcEx& ex, void* stream) {
+                          const ConvTcEx& ex, void* stream, const float* ln_colsum = nullptr, float ln_eps = 0.0f) {
   SBGM_REQUIRE(fmt == SBGM_FMT_BF16 || fmt == SBGM_FMT_BF16X2 || fmt == SBGM_FMT_F16, "conv2d_tc: format %d is not a tensor-core format", fmt);
   SBGM_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv2d_tc: cin=%d and cout=%d must be multiples of 64", cin, cout);
   SBGM_REQUIRE(stride >= 1 && stride <= 8, "conv2d_tc: stride %d unsupported", stride);
@@ -623,6 +680,14 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
   }
   const size_t ws_need = static_cast<size_t>(p.splits) * n * ho * wo * cout * sizeof(float);
   if (p.splits > 1 && (scatter || proj_w != nullptr || workspace == nullptr || workspace_bytes < ws_need)) p.splits = 1;
+  if (ln_colsum != nullptr) {
+    SBGM_REQUIRE(kh == 1 && kw == 1 && stride == 1 && !ex.on && proj_w == nullptr && gn_partials == nullptr && out != nullptr,
+                 "conv2d_tc: the LayerNorm fold applies to plain Linear layers");
+    p.splits = 1;
+    if (block_n > 128) block_n = 128;
+  }
+  p.ln_colsum = ln_colsum;
+  p.ln_eps = ln_eps;
   p.ws = static_cast<float*>(workspace);
   p.gn_partials = gn_partials;
   p.gn_chunks = gn_chunks_for(p);
@@ -636,7 +701,7 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
 
   // dense output addressing, full epilogue: the tile leaves through shared memory and TMA stores (SBGM_B200_TMA_STORE=0: off)
   static const bool tma_store_on = [] { const char* e = getenv("SBGM_B200_TMA_STORE"); return !(e != nullptr && e[0] == '0'); }();
-  p.ep.staged = (tma_store_on && !scatter && proj_w == nullptr && p.splits == 1 && out != nullptr) ? 1 : 0;
+  p.ep.staged = ((tma_store_on || ln_colsum != nullptr) && !scatter && proj_w == nullptr && p.splits == 1 && out != nullptr) ? 1 : 0;
   // 3x3 / stride 1 / pad 1: one halo slab per 64-channel block (SBGM_B200_SLAB=0: off).  Maps tileable by 16 rows x 8 columns
   // use 16 x 8 tiles of one image; other maps tileable by 8 x 8 use 8 x 8 tiles of two images with permuted tensor maps
   // (no fused GroupNorm statistics there: a warp's 32 rows span two images).  Split-K slices the 64-channel blocks.
@@ -731,4 +796,17 @@ extern "C" int sbgm_conv2d_tc_ex(const void* in, size_t in_plane, const void* we
   ConvTcEx ex = {pad_h, pad_w, ho, wo, out_h, out_w, out_step, out_oy, out_ox, res_pix_mod, true};
   return conv2d_tc_impl(in, in_plane, weight, w_plane, bias, residual, res_plane, tproj, tproj_stride, out, out_plane, fmt, n, h, w, cin,
                         cout, kh, kw, stride, pad_h, act, nullptr, 0, nullptr, workspace, workspace_bytes, nullptr, ex, stream);
+}
+
+// y = act( LayerNorm(x; gamma, beta, eps) W^T + b ) over token rows x[rows][cin] -> y[rows][cout] with the LayerNorm folded into the
+// GEMM (ImageSelfAttention: ln1 -> mha.in_proj, ln2 -> ff.0 + GELU, score_unet.py:139-146): `weight` holds W diag(gamma),
+// `bias` = b + W beta, `colsum[cout]` = row sums of the folded weight; the per-token mean / rstd are computed inside the kernel
+// from the operand tiles, the normalised tensor never exists.
+extern "C" int sbgm_linear_ln_tc(const void* in, size_t in_plane, const void* weight, size_t w_plane, const float* bias,
+                                 const float* colsum, float eps, void* out, size_t out_plane, int fmt, int rows, int cin, int cout,
+                                 int act, void* stream) {
+  SBGM_REQUIRE(colsum != nullptr && bias != nullptr, "linear_ln_tc: colsum and bias are required");
+  ConvTcEx ex = {};
+  return conv2d_tc_impl(in, in_plane, weight, w_plane, bias, nullptr, 0, nullptr, 0, out, out_plane, fmt, 1, 1, rows, cin, cout, 1, 1, 1, 0,
+                        act, nullptr, 0, nullptr, nullptr, 0, nullptr, ex, stream, colsum, eps);
 }

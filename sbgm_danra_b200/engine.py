@@ -47,7 +47,8 @@ def _stream() -> int:
 # the launch sequence so that its in-graph cost can be read off as a difference.  Results are garbage when set.
 import os as _os
 _SKIP = frozenset(x for x in _os.environ.get("SBGM_B200_SKIP", "").split(",") if x)
-_ATTN_FUSED = _os.environ.get("SBGM_B200_ATTN_FUSED", "1") != "0"     # 0: attention core and out-projection as two launches
+_LN_FOLD = _os.environ.get("SBGM_B200_LN_FOLD", "1") != "0"           # 0: LayerNorm as its own kernel in front of in_proj / ff.0
+_ATTN_FUSED = _os.environ.get("SBGM_B200_ATTN_FUSED", "auto")         # 0: attention core and out-projection as two launches
 
 
 # Measurement hook (bench.py `roofline.family`): when set to a list, every convolution / Linear launch of a forward appends
@@ -110,6 +111,7 @@ class ConvW:
     cout: int
     kh: int
     kw: int
+    colsum: Optional[torch.Tensor] = None      # LayerNorm-folded Linear layers: row sums of the folded weight (fp32)
 
     @property
     def plane(self) -> int:
@@ -164,6 +166,28 @@ class _Packer:
             km = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).contiguous()           # [cout][K]
             packed = pack_tc_matrix(km, self.fmt)
         return ConvW(packed, None if bias is None else bias.contiguous(), cin, cout, kh, kw)
+
+
+def _unpack_tc_matrix(packed: torch.Tensor, fmt: int) -> torch.Tensor:
+    """The fp32 values a tensor-core layer actually multiplies with (inverse of pack_tc_matrix up to its rounding)."""
+    if fmt == FMT_BF16:
+        return packed.float()
+    if fmt == FMT_F16:
+        return packed[0].float() + packed[1].float() / F16_WLO_SCALE
+    return packed[0].float() + packed[1].float()
+
+
+def pack_linear_ln(pk: "_Packer", wkey: str, bkey: str, gkey: str, betakey: str) -> ConvW:
+    """Linear layer behind a LayerNorm, folded (sbgm_linear_ln_tc): W' = W diag(gamma), b' = b + W beta, colsum = W' 1.
+    The column sums are taken over the packed (rounded) weights, so that  x W'^T - mean colsum  cancels exactly as
+    (x - mean) W'^T would."""
+    w, b = pk.get(wkey), pk.get(bkey)
+    gamma, beta = pk.get(gkey), pk.get(betakey)
+    wf = (w * gamma[None, :]).contiguous()
+    bf = (b + w @ beta).contiguous()
+    packed = pack_tc_matrix(wf, pk.fmt)
+    colsum = _unpack_tc_matrix(packed, pk.fmt).double().sum(dim=1).float().contiguous()
+    return ConvW(packed, bf, w.shape[1], w.shape[0], 1, 1, colsum)
 
 
 class Kernels:
@@ -268,6 +292,16 @@ class Kernels:
     def linear(self, x: Act, cw: ConvW, act: int = ACT_NONE, residual: Optional[Act] = None) -> Act:
         return self.conv(x, cw, 1, 0, act, residual)
 
+    def linear_ln(self, x: Act, cw: ConvW, act: int = ACT_NONE) -> Act:
+        """act(LayerNorm(x) W^T + b) with the LayerNorm folded into the GEMM (`cw` from pack_linear_ln)."""
+        rows = x.n * x.h * x.w
+        out = Act(self.fmt, 1, 1, rows, cw.cout, self.device)
+        if "conv_tc" in _SKIP or "tc_1x1" in _SKIP:
+            return out
+        call("sbgm_linear_ln_tc", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, cw.bias.data_ptr(), cw.colsum.data_ptr(), LN_EPS, out.ptr,
+             out.plane, self.fmt, rows, cw.cin, cw.cout, act, _stream())
+        return out
+
     def groupnorm(self, x: Act, gamma, beta, groups: int, act: int = ACT_NONE, skip: Optional[Act] = None,
                   tproj: Optional[torch.Tensor] = None, stats=None) -> Act:
         if "gn" in _SKIP:
@@ -307,9 +341,14 @@ class Kernels:
         return out
 
     def attention_out_proj_ok(self, b: int, s: int, c: int, heads: int) -> bool:
-        """True if the attention core + out-projection + residual run as one tcgen05 kernel (csrc/attn_fused.cu)."""
-        return (_ATTN_FUSED and "attn_core" not in _SKIP and
-                bool(_lib.query("sbgm_attention_out_proj_supported", self.fmt, b, s, c, heads)))
+        """True if the attention core + out-projection + residual run as one tcgen05 kernel (csrc/attn_fused.cu).
+        SBGM_B200_ATTN_FUSED: 0 = never, 1 = wherever the kernel supports the shape, unset = where it measured faster than the
+        two launches it replaces: enough query tiles to fill the GPU (16 x 16 maps at the benchmark batch)."""
+        if _ATTN_FUSED == "0" or "attn_core" in _SKIP:
+            return False
+        if not _lib.query("sbgm_attention_out_proj_supported", self.fmt, b, s, c, heads):
+            return False
+        return _ATTN_FUSED == "1" or b * s >= 128 * 96
 
     def attention_out_proj(self, qkv: Act, x: Act, cw: ConvW, b: int, s: int, c: int, heads: int) -> Act:
         """x + out_proj(softmax(Q K^T / sqrt(d)) V): scores, probabilities and head outputs stay on the SM."""
@@ -335,6 +374,12 @@ class AttentionW:
         self.out_proj = pk.conv(f"{prefix}.mha.out_proj.weight", f"{prefix}.mha.out_proj.bias")
         self.ff0 = pk.conv(f"{prefix}.ff.0.weight", f"{prefix}.ff.0.bias")
         self.ff2 = pk.conv(f"{prefix}.ff.2.weight", f"{prefix}.ff.2.bias")
+        # LayerNorm folded into the Linear layer behind it (tensor-core formats): ln1 -> in_proj, ln2 -> ff.0
+        self.fold = pk.fmt != FMT_F32 and _LN_FOLD
+        if self.fold:
+            self.in_proj_ln = pack_linear_ln(pk, f"{prefix}.mha.in_proj_weight", f"{prefix}.mha.in_proj_bias", f"{prefix}.ln1.weight",
+                                             f"{prefix}.ln1.bias")
+            self.ff0_ln = pack_linear_ln(pk, f"{prefix}.ff.0.weight", f"{prefix}.ff.0.bias", f"{prefix}.ln2.weight", f"{prefix}.ln2.bias")
 
 
 def attention_block(k: Kernels, aw: AttentionW, x: Act) -> Act:
@@ -343,15 +388,14 @@ def attention_block(k: Kernels, aw: AttentionW, x: Act) -> Act:
         return x
     tok = x.tokens()
     b, s, c = x.n, x.h * x.w, x.c
-    h1 = k.layernorm(tok, *aw.ln1)
-    qkv = k.linear(h1, aw.in_proj)
+    fold = aw.fold and "ln" not in _SKIP
+    qkv = k.linear_ln(tok, aw.in_proj_ln) if fold else k.linear(k.layernorm(tok, *aw.ln1), aw.in_proj)
     if k.attention_out_proj_ok(b, s, c, aw.heads):
         h = k.attention_out_proj(qkv, tok, aw.out_proj, b, s, c, aw.heads)
     else:
         att = k.attention_core(qkv, b, s, c, aw.heads)
         h = k.linear(att, aw.out_proj, residual=tok)
-    g = k.layernorm(h, *aw.ln2)
-    g = k.linear(g, aw.ff0, act=ACT_GELU)
+    g = k.linear_ln(h, aw.ff0_ln, act=ACT_GELU) if fold else k.linear(k.layernorm(h, *aw.ln2), aw.ff0, act=ACT_GELU)
     y = k.linear(g, aw.ff2, residual=h)
     out = Act.__new__(Act)
     out.buf, out.fmt, out.n, out.h, out.w, out.c = y.buf, y.fmt, x.n, x.h, x.w, x.c

@@ -466,7 +466,8 @@ def test_attention_out_proj_fused_kernel(E, prec, b, s, c, heads):
     fmt = FMTS[prec]
     dev = torch.device("cuda")
     k = E.Kernels(fmt, dev)
-    assert k.attention_out_proj_ok(b, s, c, heads)
+    from sbgm_danra_b200 import _lib
+    assert _lib.query("sbgm_attention_out_proj_supported", fmt, b, s, c, heads)
     qkv = gen(1, 3 * c, 1, b * s, seed=1)
     x = gen(1, c, 1, b * s, seed=2)
     w, bias = gen(c, c, seed=3, scale=c ** -0.5), gen(c, seed=4, scale=0.1)
@@ -482,3 +483,28 @@ def test_attention_out_proj_fused_kernel(E, prec, b, s, c, heads):
     two = k.linear(k.attention_core(qa, b, s, c, heads), cw, residual=xa).to_nchw().cpu()[0, :, 0].T
     print(f"attention + out-proj fused [{prec}] b={b} s={s} c={c} heads={heads}: rel-L2 {err:.2e} (two-launch path {rel_l2(two, want):.2e})")
     assert err < {"fp16x2": 8e-4, "bf16": 8e-3}[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "bf16x3", "bf16"])
+@pytest.mark.parametrize("rows,cin,cout,act", [(4096, 256, 768, 0), (200, 128, 128, 3), (1024, 512, 1536, 0), (16384, 128, 384, 0),
+                                               (77, 256, 256, 3)])
+def test_linear_with_folded_layernorm(E, prec, rows, cin, cout, act):
+    """sbgm_linear_ln_tc: act(LayerNorm(x) W^T + b) with the LayerNorm folded into the GEMM (per-token statistics computed in the
+    kernel from the operand tiles, y = rstd (x W'^T - mean colsum) + b') against torch on the stored input, and against the
+    LayerNorm kernel + Linear pair it replaces.  x carries a per-token offset so that the cancellation mean * colsum matters."""
+    fmt = FMTS[prec]
+    dev = torch.device("cuda")
+    x = gen(1, cin, 1, rows, seed=1) * 1.5 + gen(1, 1, 1, rows, seed=5) * 2.0 + 0.7
+    w, b = gen(cout, cin, seed=2, scale=cin ** -0.5), gen(cout, seed=3, scale=0.1)
+    g, beta = 1 + 0.2 * gen(cin, seed=4), gen(cin, seed=6, scale=0.2)
+    xa = act_of(E, x, fmt)
+    xs = xa.to_nchw().cpu()[0, :, 0].T
+    want = F.linear(F.layer_norm(xs, (cin,), g, beta, 1e-5), w, b)
+    want = F.gelu(want) if act == 3 else want
+    pk = E._Packer({"w": w, "b": b, "g": g, "beta": beta}, fmt, dev)
+    k = E.Kernels(fmt, dev)
+    got = k.linear_ln(xa, E.pack_linear_ln(pk, "w", "b", "g", "beta"), act=act).to_nchw().cpu()[0, :, 0].T
+    two = k.linear(k.layernorm(xa, g.cuda(), beta.cuda()), pk.conv("w", "b"), act=act).to_nchw().cpu()[0, :, 0].T
+    err, err2 = rel_l2(got, want), rel_l2(two, want)
+    print(f"LayerNorm-folded Linear [{prec}] {rows}x{cin}->{cout} act={act}: rel-L2 {err:.2e} (LayerNorm kernel + Linear: {err2:.2e})")
+    assert err < {"fp16x2": 6e-4, "bf16x3": 1e-4, "bf16": 2e-2}[prec] and err < 2.0 * err2 + 1e-5
