@@ -77,6 +77,13 @@ int sbgm_fourier_embed(const float* t, const float* fourier_w, int half, float* 
  * 1x1 tensor-core convolution over this tensor (sbgm_conv2d_tc / _ex) and its weight gradient sbgm_conv2d_wgrad_tc. */
 int sbgm_stem_im2col(const float* x, const float* planes, int np, int cc, int c_begin, int c_end, void* out, size_t out_plane,
                      int fmt, int n, int h, int w, void* stream);
+/* Encoder.conv1 restricted to the noisy-field channel, on the tensor cores with the 8x8 stride-2 windows built in shared memory
+ * (no im2col tensor in HBM):  out[n][oy][ox][co] = sum_{r,s} x[n][2oy+r-3][2ox+s-3] w[co][r*8+s] + partial[..][oy][ox][co] + tproj[n][co].
+ *   x[n][h][w] fp32; w_packed [planes][64][64] K-major in the weight storage of `fmt` (planes `w_plane` apart);
+ *   partial[partial_n][h/2][w/2][64] in `fmt`: the conditioning channels' contribution (sbgm_stem_conv), partial_n == 1
+ *   broadcasts it over the batch, NULL = none; tproj[n][tproj_stride] fp32 or NULL; out NHWC `fmt`.  h % 16 == 0, w % 32 == 0. */
+int sbgm_stem_x_tc(const float* x, const void* w_packed, size_t w_plane, const void* partial, size_t partial_plane, int partial_n,
+                   const float* tproj, int tproj_stride, void* out, size_t out_plane, int fmt, int n, int h, int w, void* stream);
 /* ---- stem convolution (Encoder.conv1, score_unet.py:206-211,:312-315) ---------------------
  * 8x8 stride-2 pad-3 convolution over the virtual channel concat  x || planes  (:273-291) for
  * the input-channel range [c_begin, c_end), CUDA cores (K is tiny and the op is bandwidth bound).

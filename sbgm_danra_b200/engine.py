@@ -47,6 +47,7 @@ def _stream() -> int:
 # the launch sequence so that its in-graph cost can be read off as a difference.  Results are garbage when set.
 import os as _os
 _SKIP = frozenset(x for x in _os.environ.get("SBGM_B200_SKIP", "").split(",") if x)
+_STEM_FUSED = _os.environ.get("SBGM_B200_STEM_FUSED", "1") != "0"     # 0: stem as im2col tensor + 1x1 convolution
 _LN_FOLD = _os.environ.get("SBGM_B200_LN_FOLD", "1") != "0"           # 0: LayerNorm as its own kernel in front of in_proj / ff.0
 _ATTN_FUSED = _os.environ.get("SBGM_B200_ATTN_FUSED", "auto")         # 0: attention core and out-projection as two launches
 
@@ -524,7 +525,13 @@ class EncoderEngine:
         t0 = tp.cols(tproj, "enc0")
         if self.fmt != FMT_F32:
             # conv1 on the tensor cores: im2col of the 8x8 stride-2 window, then a 1x1 implicit GEMM (K = 64 per channel)
-            if partial is not None:
+            if (partial is not None or cc == 0) and _STEM_FUSED and h % 16 == 0 and w % 32 == 0:
+                # one kernel: windows of x built in shared memory, MMA against the resident 64 x 64 weights, + partial + time
+                f1 = Act(self.fmt, n, h // 2, w // 2, 64, self.device)
+                call("sbgm_stem_x_tc", x.data_ptr(), self.stem_cw_x.w.data_ptr(), self.stem_cw_x.plane,
+                     None if partial is None else partial.ptr, 0 if partial is None else partial.plane, 0 if partial is None else partial.n,
+                     t0.data_ptr(), t0.stride(0), f1.ptr, f1.plane, self.fmt, n, h, w, _stream())
+            elif partial is not None:
                 f1 = k.conv1x1_bcast(k.stem_im2col(x, None, 0, 1, cc), self.stem_cw_x, partial, t0)
             else:
                 if cc > 0:

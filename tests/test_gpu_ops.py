@@ -508,3 +508,31 @@ def test_linear_with_folded_layernorm(E, prec, rows, cin, cout, act):
     err, err2 = rel_l2(got, want), rel_l2(two, want)
     print(f"LayerNorm-folded Linear [{prec}] {rows}x{cin}->{cout} act={act}: rel-L2 {err:.2e} (LayerNorm kernel + Linear: {err2:.2e})")
     assert err < {"fp16x2": 6e-4, "bf16x3": 1e-4, "bf16": 2e-2}[prec] and err < 2.0 * err2 + 1e-5
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "bf16x3", "bf16"])
+@pytest.mark.parametrize("n,size,bcast,with_partial", [(3, 64, True, True), (2, 32, False, True), (5, 96, True, True), (2, 128, True, False),
+                                                       (70, 32, True, True)])
+def test_stem_fused_window_kernel(E, prec, n, size, bcast, with_partial):
+    """sbgm_stem_x_tc: conv1 on the noisy-field channel with the 8x8 stride-2 windows built in shared memory (no im2col tensor),
+    + the conditioning partial sums (broadcast or per member) + the time projection, against F.conv2d; also against the
+    im2col + 1x1 path it replaces."""
+    from sbgm_danra_b200._lib import call
+    fmt = FMTS[prec]
+    dev = torch.device("cuda")
+    x = gen(n, 1, size, size, seed=1) * 9.0
+    w = gen(64, 1, 8, 8, seed=2, scale=0.1)
+    partial = gen(1 if bcast else n, 64, size // 2, size // 2, seed=3) if with_partial else None
+    tproj = gen(n, 80, seed=4)
+    pa = None if partial is None else act_of(E, partial, fmt)
+    ps = 0.0 if partial is None else pa.to_nchw().cpu()
+    want = F.conv2d(x, w, stride=2, padding=3) + ps + tproj[:, 8:72, None, None]
+    cw = E.ConvW(E.pack_tc_matrix(w.reshape(64, 64).contiguous().cuda(), fmt), None, 64, 64, 1, 1)
+    out = E.Act(fmt, n, size // 2, size // 2, 64, dev)
+    xd, td = x.cuda(), tproj.cuda()
+    tv = td[:, 8:72]
+    call("sbgm_stem_x_tc", xd.data_ptr(), cw.w.data_ptr(), cw.plane, None if pa is None else pa.ptr, 0 if pa is None else pa.plane,
+         0 if pa is None else pa.n, tv.data_ptr(), tv.stride(0), out.ptr, out.plane, fmt, n, size, size, torch.cuda.current_stream().cuda_stream)
+    err = rel_l2(out.to_nchw().cpu(), want)
+    print(f"fused stem [{prec}] n={n} {size}x{size}: rel-L2 {err:.2e}")
+    assert err < TOL[prec]
