@@ -37,19 +37,30 @@ class GradBucketer:
     def __init__(self, layout: Sequence[Tuple[str, int, int]], total: int, bucket_elems: int, expected: Optional[Sequence[str]] = None):
         self.layout, self.total = list(layout), total
         self.bounds: List[Tuple[int, int]] = []
-        start, n = 0, 0
-        # walk from the END of the buffer (filled first by backward) so that early buckets are full-sized
+        # Walk from the END of the buffer (filled first by backward) in full-sized buckets; the START of the buffer holds what
+        # backward produces last (stem, time projections), so the lowest buckets are made SMALL (1/32 and 1/8 of a bucket): the
+        # only exchange that cannot hide behind remaining backward kernels is then ~1 MB instead of whatever the walk left over.
+        tail_sizes = [max(1, bucket_elems // 32), max(1, bucket_elems // 8)]
+        head_edges, acc, k = [0], 0, 0
+        for name, off, numel in self.layout:
+            if k >= len(tail_sizes):
+                break
+            acc += numel
+            if acc >= tail_sizes[k]:
+                head_edges.append(off + (numel + 63) // 64 * 64 if off + (numel + 63) // 64 * 64 <= total else total)
+                acc, k = 0, k + 1
+        lo_limit = head_edges[-1]
         edges = [total]
         acc = 0
         for name, off, numel in reversed(self.layout):
+            if off < lo_limit:
+                break
             acc += numel
             if acc >= bucket_elems:
                 edges.append(off)
                 acc = 0
-        if edges[-1] != 0:
-            edges.append(0)
-        edges = sorted(set(edges))
-        self.bounds = [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+        edges = sorted(set(edges) | set(e for e in head_edges if e <= total) | {0})
+        self.bounds = [(edges[i], edges[i + 1]) for i in range(len(edges) - 1) if edges[i + 1] > edges[i]]
         self.bucket_of: Dict[str, int] = {}
         for name, off, numel in self.layout:
             for b, (lo, hi) in enumerate(self.bounds):
@@ -67,6 +78,7 @@ class GradBucketer:
         self.seen = set()
         self.launched = [False] * len(self.bounds)
         self.late: List[str] = []      # touched outside the expected set after their bucket had already been exchanged
+        self.unexpected: List[str] = []   # every gradient touched outside the expected set (the set grows by these in finish())
 
     def touch(self, names: Sequence[str]) -> List[int]:
         """Mark gradients as enqueued; returns the buckets that just became complete (expected set known)."""
@@ -81,8 +93,10 @@ class GradBucketer:
                 if self.pending[b] == 0 and not self.launched[b]:
                     self.launched[b] = True
                     ready.append(b)
-            elif self.expected is not None and self.launched[self.bucket_of[name]]:
-                self.late.append(name)     # a gradient the first step did not produce: exchanged on its own in finish()
+            elif self.expected is not None:
+                self.unexpected.append(name)
+                if self.launched[self.bucket_of[name]]:
+                    self.late.append(name)     # its bucket has gone already: exchanged on its own in finish()
         return ready
 
     def remaining(self) -> List[int]:
@@ -171,8 +185,8 @@ class GradSync:
         for name in self.bucketer.late:
             off, numel = offs[name]
             self._launch_range(off, off + numel)
-        if self.bucketer.late and self.expected is not None:
-            self.expected = sorted(set(self.expected) | set(self.bucketer.late))
+        if self.bucketer.unexpected and self.expected is not None:
+            self.expected = sorted(set(self.expected) | set(self.bucketer.unexpected))
             self.bucketer = None            # rebuilt with the enlarged set by the next begin()
         if self.flat.is_cuda:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
