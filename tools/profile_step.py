@@ -25,12 +25,13 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--events", action="store_true")
+    ap.add_argument("--warmup", type=int, default=2)
     a = ap.parse_args()
     cfg = config_for(n_lr=1)
     net = build_model(cfg, synth_state_dict(cfg), a.precision, "cuda:0")
     b = synth_batch(batch=a.batch, size=a.size, n_lr=1, shared_cond=True)
     x, t, c = b.x.cuda(), b.t.cuda(), b.cond_img.cuda()
-    for _ in range(2):
+    for _ in range(a.warmup):
         net(x, t, None, c)
     torch.cuda.synchronize()
     if a.events:
