@@ -34,6 +34,7 @@ struct ConvTcParams {
   int slab_perm;       // slab mode on 8 x 8 x 2-image tiles: tile rows ordered [h][n][w], tensor maps with (c, w, n, h) dims
   int slab_row;        // slab mode: descriptor units (16 B) per slab row step = pixels per slab row * 8
   uint32_t slab_tx;    // slab mode: bytes per slab plane
+  int mt;              // pixel tiles per CTA (1 or 2; 2 = the MT = 2 kernels: two tiles share every weight box)
   int splits;          // split-K factor (gridDim.z); > 1 => raw fp32 partial tiles go to `ws`
   float* ws;           // [splits][pixels][cout] fp32
   float* gn_partials;  // [n][gn_chunks][cout/8][2] or nullptr: fused GroupNorm statistics (8-channel granularity)
@@ -78,7 +79,10 @@ struct ConvTcThreads {
   static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;
 };
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false>
+// MT = pixel tiles per CTA (1 or 2).  With MT = 2 a CTA owns two consecutive 128-pixel tiles that share every weight box: the
+// K-heavy layers are bound by the chip-wide L2 -> SM bandwidth (ncu: ~30 B/clk per SM with all SMs pulling, tensor pipe 25-48 %),
+// and two thirds to nine tenths of their operand bytes are weights that every pixel tile re-fetches.
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false, int MT = 1>
 __global__ void __launch_bounds__(ConvTcThreads<BLOCK_N>::kThreads, ConvTcThreads<BLOCK_N>::kMinCtas)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const ConvTcParams p) {
@@ -86,8 +90,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // kAPl activation planes (2: split-bf16 hi|lo), kBPl weight planes (2: hi|lo, adjacent in a stage so that ONE MMA of width
   // 2 * BLOCK_N multiplies an activation plane with both; F16: w_lo is stored times 2^11 and the epilogue rescales its half)
   constexpr int kAPl = TcFmt<FMT>::kAPlanes, kBPl = TcFmt<FMT>::kBPlanes;
-  using Cfg = ConvTcCfg<kAPl, kBPl, BLOCK_N, kStages>;
-  using SCfg = ConvTcSlabCfg<kAPl, kBPl, BLOCK_N, kStages>;
+  using Cfg = ConvTcCfg<kAPl * MT, kBPl, BLOCK_N, kStages>;          // a stage holds the A tiles of all MT pixel tiles
+  using SCfg = ConvTcSlabCfg<kAPl * MT, kBPl, BLOCK_N, kStages>;
+  constexpr uint32_t kAccCols = kBPl * BLOCK_N;                       // accumulator columns of one pixel tile
+  constexpr uint32_t kATile = kAPl * Cfg::kABytes, kSlabTile = kAPl * kSlabPlaneBytes;   // bytes of one pixel tile's A operand
+  static_assert(MT * kAccCols <= 512, "accumulators exceed the 512 TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + (SLAB ? SCfg::kBarOffset : Cfg::kBarOffset);
@@ -118,16 +125,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kBPl * BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, MT * kAccCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // tile coordinates
-  const int mt = blockIdx.x;
-  const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-  const int wo0 = tw * p.w_tile, ho0 = th * p.h_tile, n0 = tn * p.n_tile;
+  // tile coordinates (pixel tiles blockIdx.x * MT + m; a tile past the last one lies outside the tensor: TMA zero-fills its
+  // operand and clips its stores)
+  int tw_[MT], th_[MT], wo0_[MT], ho0_[MT], n0_[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    const int mt = blockIdx.x * MT + m;
+    tw_[m] = mt % p.tiles_w;
+    th_[m] = (mt / p.tiles_w) % p.tiles_h;
+    wo0_[m] = tw_[m] * p.w_tile;
+    ho0_[m] = th_[m] * p.h_tile;
+    n0_[m] = (mt / (p.tiles_w * p.tiles_h)) * p.n_tile;
+  }
   const int co0 = blockIdx.y * BLOCK_N;
   const int total_kb = p.kh * p.kw * p.cin_blocks;
   const int kb_per = (total_kb + p.splits - 1) / p.splits;
@@ -145,11 +160,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int i = 0; i < cb_cnt; ++i) {
         const int cb = cb_begin + i, as = i & 1;
         mbar_wait(slab_empty(as), ((i >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(slab_full(as), kAPl * p.slab_tx);
+        mbar_expect_tx(slab_full(as), MT * kAPl * p.slab_tx);
 #pragma unroll
-        for (int pl = 0; pl < kAPl; ++pl)
-          tma_load_5d(smem_base + as * SCfg::kAStageBytes + pl * kSlabPlaneBytes, &tmap_a, slab_full(as), cb * 64, wo0 - 1,
-                      p.slab_perm ? n0 : ho0 - 1, p.slab_perm ? ho0 - 1 : n0, pl);
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int pl = 0; pl < kAPl; ++pl)
+            tma_load_5d(smem_base + as * SCfg::kAStageBytes + m * kSlabTile + pl * kSlabPlaneBytes, &tmap_a, slab_full(as), cb * 64,
+                        wo0_[m] - 1, p.slab_perm ? n0_[m] : ho0_[m] - 1, p.slab_perm ? ho0_[m] - 1 : n0_[m], pl);
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), SCfg::kBStageBytes);
@@ -181,9 +198,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t b0 = b_base + stage * (SCfg::kBStageBytes >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (k == 0 && tap == 0) umma_bf16(tmem_base, a0, b0, idesc2, i != 0);
-            else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
-            if (kAPl == 2) umma_bf16_acc(tmem_base, a0 + (kSlabPlaneBytes >> 4) + 2 * k, b0 + 2 * k, idesc);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              const uint64_t am = a0 + m * (kSlabTile >> 4);
+              const uint32_t dm = tmem_base + m * kAccCols;
+              if (k == 0 && tap == 0) umma_bf16(dm, am, b0, idesc2, i != 0);
+              else umma_bf16_acc(dm, am + 2 * k, b0 + 2 * k, idesc2);
+              if (kAPl == 2) umma_bf16_acc(dm, am + (kSlabPlaneBytes >> 4) + 2 * k, b0 + 2 * k, idesc);
+            }
           }
           umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -204,11 +226,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(empty_bar(stage), phase ^ 1u);
         mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
         const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-        const uint32_t b_dst = a_dst + kAPl * Cfg::kABytes;
+        const uint32_t b_dst = a_dst + MT * kATile;
 #pragma unroll
-        for (int pl = 0; pl < kAPl; ++pl)
-          tma_load_5d(a_dst + pl * Cfg::kABytes, &tmap_a, full_bar(stage), cb * 64, wo0 * p.stride + s - p.pad_w,
-                      ho0 * p.stride + r - p.pad_h, n0, pl);
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int pl = 0; pl < kAPl; ++pl)
+            tma_load_5d(a_dst + m * kATile + pl * Cfg::kABytes, &tmap_a, full_bar(stage), cb * 64, wo0_[m] * p.stride + s - p.pad_w,
+                        ho0_[m] * p.stride + r - p.pad_h, n0_[m], pl);
 #pragma unroll
         for (int pl = 0; pl < kBPl; ++pl) tma_load_3d(b_dst + pl * Cfg::kBBytes, &tmap_b, full_bar(stage), kb * 64, co0, pl);
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -225,14 +249,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
         const uint64_t a0 = base + stage * (Cfg::kStageBytes >> 4);
-        const uint64_t b0 = a0 + ((kAPl * Cfg::kABytes) >> 4);
+        const uint64_t b0 = a0 + ((MT * kATile) >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 elements = 32 B) per 64-element block
           // two weight planes (hi|lo) of a stage are adjacent: one N = 2*BLOCK_N MMA yields x*w_hi (first half of the
           // columns) and x*w_lo (second half); split-bf16 adds x_lo*w_hi into the first half.
-          if (k == 0) umma_bf16(tmem_base, a0, b0, idesc2, kb != 0);
-          else umma_bf16_acc(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc2);
-          if (kAPl == 2) umma_bf16_acc(tmem_base, a0 + (Cfg::kABytes >> 4) + 2 * k, b0 + 2 * k, idesc);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint64_t am = a0 + m * (kATile >> 4);
+            const uint32_t dm = tmem_base + m * kAccCols;
+            if (k == 0) umma_bf16(dm, am, b0, idesc2, kb != 0);
+            else umma_bf16_acc(dm, am + 2 * k, b0 + 2 * k, idesc2);
+            if (kAPl == 2) umma_bf16_acc(dm, am + (Cfg::kABytes >> 4) + 2 * k, b0 + 2 * k, idesc);
+          }
         }
         umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
@@ -251,9 +280,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       n_l = (row / p.w_tile) % p.n_tile;
       h_l = row / (p.w_tile * p.n_tile);
     }
-    const int n = n0 + n_l, oy = ho0 + h_l, ox = wo0 + w_l;
-    const bool valid = (n < p.n) && (oy < p.ho) && (ox < p.wo);
-    const size_t pix = (static_cast<size_t>(n) * p.out_h + oy * p.out_step + p.out_oy) * p.out_w + ox * p.out_step + p.out_ox;
     float proj_acc[kProjMax];
 #pragma unroll
     for (int q = 0; q < kProjMax; ++q) proj_acc[q] = 0.0f;
@@ -295,8 +321,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
+#pragma unroll 1
+    for (int m = 0; m < MT; ++m) {
+    const int tw = tw_[m], th = th_[m], wo0 = wo0_[m], ho0 = ho0_[m], n0 = n0_[m];
+    const int n = n0 + n_l, oy = ho0 + h_l, ox = wo0 + w_l;
+    const bool valid = (n < p.n) && (oy < p.ho) && (ox < p.wo);
+    const size_t pix = (static_cast<size_t>(n) * p.out_h + oy * p.out_step + p.out_oy) * p.out_w + ox * p.out_step + p.out_ox;
+    if (MT > 1 && m > 0 && STAGED) {      // the warp's staging area is re-used: the previous tile's bulk stores must have read it
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
     auto load_acc = [&](int c0, uint32_t (&r)[32]) {
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + m * kAccCols + c0;
       tmem_ld32(taddr, r);
       if (kBPl == 2) {
         uint32_t t[32];
@@ -365,13 +401,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         epilogue_block64<FMT, ACT, PROJ, STAGED>(p.ep, ra, rb, co0 + c0, n, pix, valid, lane, proj_acc, sa);
       }
-      if (STAGED && lane == 0) tma_store_wait_read();      // the staged tiles must be read out before the CTA retires
     }
     if (PROJ && valid) epilogue_store_proj(p.ep, pix, proj_acc);
+    }     // pixel tiles
+    if (STAGED && !(!PROJ && p.splits > 1) && lane == 0) tma_store_wait_read();      // the staged tiles must be read out before the CTA retires
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kBPl * BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_base, MT * kAccCols);
 }
 
 // Sum the split-K partial tiles in a fixed order (deterministic) and apply the fused epilogue.
@@ -518,15 +555,15 @@ void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
   (void)pow2_floor;
 }
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false, int MT = 1>
 static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
                                cudaStream_t st) {
   constexpr int kAPl = TcFmt<FMT>::kAPlanes, kBPl = TcFmt<FMT>::kBPlanes;
-  using Cfg = std::conditional_t<SLAB, ConvTcSlabCfg<kAPl, kBPl, BLOCK_N, kStages>, ConvTcCfg<kAPl, kBPl, BLOCK_N, kStages>>;
+  using Cfg = std::conditional_t<SLAB, ConvTcSlabCfg<kAPl * MT, kBPl, BLOCK_N, kStages>, ConvTcCfg<kAPl * MT, kBPl, BLOCK_N, kStages>>;
   static_assert(!STAGED || Cfg::kBarOffset >= 4u * (BLOCK_N / 64) * kAPl * kStageBlockBytes, "the staging area must fit in the pipeline stages");
-  static_assert(kBPl * BLOCK_N <= 512, "accumulator exceeds the 512 TMEM columns");
+  static_assert(MT * kBPl * BLOCK_N <= 512, "accumulator exceeds the 512 TMEM columns");
   static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
-  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED, SLAB, LNF>;
+  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED, SLAB, LNF, MT>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -539,7 +576,7 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
     set_error("conv2d_tc: projection weight upload failed");
     return 1;
   }
-  dim3 grid(m_tiles, p.ep.cout / BLOCK_N, p.splits);
+  dim3 grid((m_tiles + MT - 1) / MT, p.ep.cout / BLOCK_N, p.splits);
   launch_k((kern), grid, ConvTcThreads<BLOCK_N>::kThreads, Cfg::kSmemBytes, st, ta, tb, to, p);
   if (!PROJ && p.splits > 1) {
     const size_t pixels = static_cast<size_t>(p.n) * p.ho * p.wo;
@@ -566,6 +603,12 @@ static int launch_conv_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     return launch_conv_tc_inst<FMT, 64, (FMT == SBGM_FMT_BF16X2 ? 2 : 4), SBGM_ACT_NONE, 1, false>(ta, tb, to, p, m_tiles, st);
   }
   if (p.ep.staged) {
+    if constexpr (TcFmt<FMT>::kAPlanes == 1 && BLOCK_N <= 128) {
+      if (p.mt == 2) {       // two pixel tiles per CTA: 2 x 16 KB of A + the weight boxes per stage
+        constexpr int kS2 = (TcFmt<FMT>::kBPlanes == 2 && BLOCK_N == 128) ? 3 : 4;
+        SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kS2, ACT, 0, true, false, false, 2>(ta, tb, to, p, m_tiles, st)));
+      }
+    }
     SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kStages, ACT, 0, true>(ta, tb, to, p, m_tiles, st)));
   }
   SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kStages, ACT, 0, false>(ta, tb, to, p, m_tiles, st)));
@@ -578,6 +621,12 @@ static int launch_conv_tc_slab(const CUtensorMap& ta, const CUtensorMap& tb, con
                                cudaStream_t st) {
   constexpr int kBStages = (FMT == SBGM_FMT_BF16X2 && BLOCK_N == 128) ? 3 : 4;     // 2 x 50 KB of slabs + 3 x 32 KB of weights
   if (p.ep.staged) {
+    if constexpr (TcFmt<FMT>::kAPlanes == 1 && BLOCK_N <= 128) {
+      if (p.mt == 2) {       // two halo slabs per A stage (2 x 2 x 25.6 KB) + the weight ring
+        constexpr int kS2 = (TcFmt<FMT>::kBPlanes == 2 && BLOCK_N == 128) ? 3 : 4;
+        SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kS2, ACT, 0, true, true, false, 2>(ta, tb, to, p, m_tiles, st)));
+      }
+    }
     SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kBStages, ACT, 0, true, true>(ta, tb, to, p, m_tiles, st)));
   }
   SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kBStages, ACT, 0, false, true>(ta, tb, to, p, m_tiles, st)));
@@ -727,6 +776,21 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
     p.slab_row = (slab_perm ? 2 : 1) * kSlabW * 8;
     p.slab_tx = (slab_perm ? 10 * 2 * 10 : kSlabW * kSlabH) * 128;
     if (!slab_perm) p.gn_chunks = gn_chunks_for(p);
+  }
+  // Two pixel tiles per CTA (MT = 2) where the grid stays full: the weight boxes -- most of a K-heavy layer's operand bytes -- are
+  // fetched once for both.  A 128-wide layer whose grid would drop below one wave keeps its CTA count by going 64-wide instead.
+  // SBGM_B200_MT: 1 = never, 2 = wherever the kernel allows it, unset = by grid size.
+  p.mt = 1;
+  {
+    static const int mt_mode = [] { const char* e = getenv("SBGM_B200_MT"); return e == nullptr ? 0 : atoi(e); }();
+    const bool allowed = planes == 1 && p.ep.staged && proj_w == nullptr && p.splits == 1 && ln_colsum == nullptr && block_n <= 128 &&
+                         m_tiles >= 2;
+    const long long ctas = static_cast<long long>(m_tiles) * (cout / block_n);
+    const int total_kb_ = kh * kw * p.cin_blocks;
+    if (allowed && mt_mode != 1) {
+      if (mt_mode == 2 || ctas >= 252) p.mt = 2;
+      else if (block_n == 128 && ctas >= 120 && total_kb_ >= 18) { block_n = 64; p.mt = 2; }
+    }
   }
   CUtensorMap ta, tb, to;
   if (slab ? (slab_perm ? encode_perm_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, 2, 10)

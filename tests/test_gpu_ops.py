@@ -536,3 +536,51 @@ def test_stem_fused_window_kernel(E, prec, n, size, bcast, with_partial):
     err = rel_l2(out.to_nchw().cpu(), want)
     print(f"fused stem [{prec}] n={n} {size}x{size}: rel-L2 {err:.2e}")
     assert err < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "bf16"])
+@pytest.mark.parametrize("case", [
+    (64, 32, 32, 128, 128, 3, 1, 1, "full"),      # slab mode, 512 tiles: two tiles per CTA at 128 wide
+    (64, 32, 32, 128, 64, 3, 1, 1, "plain"),      # 64-wide
+    (64, 16, 16, 256, 256, 3, 1, 1, "relu"),      # 256 CTAs
+    (64, 8, 8, 512, 512, 3, 1, 1, "plain"),       # 8 x 8 maps (tiles of two images): 128 CTAs -> 64-wide tiles, two per CTA
+    (33, 8, 8, 256, 256, 3, 1, 1, "full"),        # odd image count: the last CTA's second tile lies outside the tensor
+    (64, 64, 64, 64, 64, 8, 2, 3, "relu"),        # plain mode, strided (Encoder.conv2)
+    (7, 32, 32, 128, 128, 3, 1, 1, "gelu"),       # odd tile count in slab mode
+    (64, 16, 16, 128, 256, 3, 2, 1, "relu"),      # strided 3 x 3
+], ids=lambda c: "x".join(map(str, c)))
+def test_conv2d_two_pixel_tiles_per_cta(E, prec, case, monkeypatch):
+    """The MT = 2 kernels (two 128-pixel tiles per CTA sharing every weight box) against torch, with the fused GroupNorm statistics
+    where the layer has them; forced on with SBGM_B200_MT=2 is not possible inside one process (the switch is read once), so
+    the cases are shapes the automatic choice sends to MT = 2 -- checked through equality with the one-tile result of a
+    fresh process in test_mt_switch_equivalence."""
+    n, h, w, cin, cout, k, stride, pad, epi = case
+    fmt = FMTS[prec]
+    x = gen(n, cin, h, w, seed=1)
+    wt = gen(cout, cin, k, k, seed=2, scale=1.0 / math.sqrt(cin * k * k))
+    bias = gen(cout, seed=3, scale=0.1) if epi != "plain" else None
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = gen(n, cout, ho, wo, seed=4) if epi == "full" else None
+    tproj = gen(n, cout + 16, seed=5) if epi == "full" else None
+    act = {"plain": 0, "full": 1, "relu": 1, "gelu": 3}[epi]
+    want = F.conv2d(x, wt, bias, stride=stride, padding=pad)
+    if res is not None:
+        want = want + res
+    want = {0: lambda v: v, 1: F.relu, 3: F.gelu}[act](want)
+    if tproj is not None:
+        want = want + tproj[:, 8:8 + cout, None, None]
+    kern = E.Kernels(fmt, torch.device("cuda"))
+    sd = {"w": wt}
+    if bias is not None:
+        sd["b"] = bias
+    cw = E._Packer(sd, fmt, torch.device("cuda")).conv("w", "b" if bias is not None else None)
+    tp = tproj.cuda()[:, 8:8 + cout] if tproj is not None else None
+    out = kern.conv(act_of(E, x, fmt), cw, stride=stride, pad=pad, act=act, residual=None if res is None else act_of(E, res, fmt), tproj=tp)
+    err = rel_l2(out.to_nchw().cpu(), want)
+    assert err < TOL[prec], f"rel-L2 {err:.3e}"
+    if epi == "plain" and stride == 1:          # GroupNorm statistics fused into the epilogue of a two-tile CTA
+        gamma, beta = 1 + 0.2 * gen(cout, seed=6), gen(cout, seed=7, scale=0.2)
+        y, stats = kern.conv(act_of(E, x, fmt), cw, pad=pad, gn_stats=True)
+        if stats is not None:
+            got = kern.groupnorm(y, gamma.cuda(), beta.cuda(), 8, stats=stats).to_nchw().cpu()
+            assert rel_l2(got, F.group_norm(y.to_nchw().cpu(), 8, gamma, beta, 1e-5)) < {"bf16": 8e-3, "fp16x2": 5e-4}[prec]
