@@ -777,8 +777,9 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
     p.slab_tx = (slab_perm ? 10 * 2 * 10 : kSlabW * kSlabH) * 128;
     if (!slab_perm) p.gn_chunks = gn_chunks_for(p);
   }
-  // Two pixel tiles per CTA (MT = 2) where the grid stays full: the weight boxes -- most of a K-heavy layer's operand bytes -- are
-  // fetched once for both.  A 128-wide layer whose grid would drop below one wave keeps its CTA count by going 64-wide instead.
+  // Two pixel tiles per CTA (MT = 2) where the grid stays full (>= 1.7 waves of one-tile CTAs): the weight boxes -- most of a
+  // K-heavy layer's operand bytes -- are fetched once for both.  Measured per layer (profiles/r02_conv_tc_family_table_*.txt):
+  // conv2 110 -> 66 us, 128->128 at 32 x 32 47 -> 42 us; trading a 128-wide one-wave grid for 64-wide two-tile CTAs was slower.
   // SBGM_B200_MT: 1 = never, 2 = wherever the kernel allows it, unset = by grid size.
   p.mt = 1;
   {
@@ -786,11 +787,7 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
     const bool allowed = planes == 1 && p.ep.staged && proj_w == nullptr && p.splits == 1 && ln_colsum == nullptr && block_n <= 128 &&
                          m_tiles >= 2;
     const long long ctas = static_cast<long long>(m_tiles) * (cout / block_n);
-    const int total_kb_ = kh * kw * p.cin_blocks;
-    if (allowed && mt_mode != 1) {
-      if (mt_mode == 2 || ctas >= 252) p.mt = 2;
-      else if (block_n == 128 && ctas >= 120 && total_kb_ >= 18) { block_n = 64; p.mt = 2; }
-    }
+    if (allowed && mt_mode != 1 && (mt_mode == 2 || ctas >= 252)) p.mt = 2;
   }
   CUtensorMap ta, tb, to;
   if (slab ? (slab_perm ? encode_perm_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, 2, 10)
