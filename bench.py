@@ -457,13 +457,13 @@ def bench_train_c4(dev, rank, world, steps, warmup):
     64; weak: 64 per rank."""
     import torch
     import torch.distributed as dist
-    from sbgm_danra_b200 import parallel, score_sampling
+    from sbgm_danra_b200 import optim as sbgm_optim, parallel, score_sampling
     from sbgm_danra_b200._smoke import build_model
     from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
     from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
     ck = dict(n_lr=2, geo=True, seasons=True)
     cfg = config_for(**ck)
-    out = {"workload": "C4: DSM training step 128x128, Cin=7 + seasons, bf16, Adam, DDP bucketed all-reduce", "unit": "samples/s"}
+    out = {"workload": "C4: DSM training step 128x128, Cin=7 + seasons, bf16, Adam (sbgm_danra_b200.optim: torch.optim.Adam with a one-launch step), DDP bucketed all-reduce", "unit": "samples/s"}
     for mode in ("strong", "weak"):
         local = MEMBERS // world if mode == "strong" else MEMBERS
         if local < 1 or (mode == "weak" and world == 1):
@@ -472,7 +472,7 @@ def bench_train_c4(dev, rank, world, steps, warmup):
         b = synth_batch(batch=local, size=SIZE, seed=1234 + rank, **ck)
         c = lambda v: v.to(dev)
         x, y, cond, lsm, topo, sdf = c(b.x), c(b.y), c(b.cond_img), c(b.lsm_cond), c(b.topo_cond), c(b.sdf_cond)
-        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+        opt = sbgm_optim.Adam(net.parameters(), lr=1e-4)      # torch.optim.Adam with a one-launch step (csrc/optim.cu)
         sync = None
         if world > 1:
             parallel.broadcast_parameters(net)

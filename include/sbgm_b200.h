@@ -329,17 +329,22 @@ int sbgm_norm_apply(const void* x, size_t x_plane, const float* stats, int per_s
                     const float* beta, const void* add, size_t add_plane, const float* tproj, int tproj_stride,
                     int tproj_pre_act, int act, void* y, size_t y_plane, int fmt, int n, int hw, int c, void* stream);
 /* backward of sbgm_norm_apply: dx, dadd (= gradient w.r.t. the pre-activation; NULL to skip), dgamma/dbeta[c]
- * (NULL for non-affine norms), dtproj[n][dtproj_stride] (NULL to skip).  `scratch`:
- * sbgm_norm_backward_scratch_floats(n, c) floats.
+ * (NULL for non-affine norms), dtproj[n][dtproj_stride] (NULL to skip), dbias_prev[c] (NULL to skip) = dx summed over
+ * n and the pixels, i.e. the bias gradient of the convolution whose output x is (closed form from the reduction sums, no
+ * extra pass).  Two launches: the reduction tree (last-block tickets, deterministic) and the apply pass.
+ * `scratch`: sbgm_norm_backward_scratch_floats(n, c) floats, ZERO before its first use (its leading words are the
+ * tickets; every launch leaves them zero again, so one zero-initialised buffer serves all layers of a stream).
  * Synchronised BatchNorm (data-parallel training with whole-batch statistics): call with stage = 1 (per-sample sums
- * [n][c][3] land at scratch + sbgm_norm_backward_sums_offset(n, c)), all-gather those over the ranks, then stage = 2 with
- * sums_all[n_all][c][3].  stage = 0 does everything locally (sums_all = NULL). */
+ * [n][c][4] = sbgm_norm_backward_sums_floats(n, c) floats land at scratch + sbgm_norm_backward_sums_offset(n, c)),
+ * all-gather those over the ranks, then stage = 2 with sums_all[n_all][c][4].  stage = 0 does everything locally
+ * (sums_all = NULL). */
 size_t sbgm_norm_backward_scratch_floats(int n, int c);
 size_t sbgm_norm_backward_sums_offset(int n, int c);
+size_t sbgm_norm_backward_sums_floats(int n, int c);
 int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, const float* stats, int per_sample_stats,
                        int groups, const float* gamma, const float* beta, const void* add, size_t add_plane,
                        const float* tproj, int tproj_stride, int tproj_pre_act, int act, void* dx, size_t dx_plane,
-                       void* dadd, size_t dadd_plane, float* dgamma, float* dbeta, float* dtproj, int dtproj_stride,
+                       void* dadd, size_t dadd_plane, float* dgamma, float* dbeta, float* dbias_prev, float* dtproj, int dtproj_stride,
                        int fmt, int n, int hw, int c, float* scratch, int stage, const float* sums_all, int n_all, void* stream);
 /* nn.LayerNorm backward (ImageSelfAttention.ln1 / ln2, score_unet.py:136-148) */
 size_t sbgm_layernorm_backward_scratch_floats(int c);
@@ -353,17 +358,22 @@ int sbgm_act_backward(const void* dy, size_t dy_plane, const void* x, size_t x_p
 /* dst += src (gradient accumulation where a tensor has several consumers) */
 int sbgm_add_inplace(void* dst, size_t dst_plane, const void* src, size_t src_plane, int fmt, size_t count, void* stream);
 /* out_per_sample[n][out_stride] (nullable) = sum over the hw pixels; out_total[c] (nullable) = sum over everything
- * (bias gradients; time-projection gradients of the encoder stages) */
+ * (bias gradients; time-projection gradients of the encoder stages).  Total only: one launch (last-block ticket).
+ * `scratch`: sbgm_channel_sums_scratch_floats(n, c) floats, ZERO before its first use (leading ticket words; every launch
+ * leaves them zero again). */
 size_t sbgm_channel_sums_scratch_floats(int n, int c);
 int sbgm_channel_sums(const void* x, size_t x_plane, int fmt, int n, int hw, int c, float* out_per_sample, int out_stride,
                       float* out_total, float* scratch, void* stream);
 /* adjoint of sbgm_upsample2x: dy [n, 2h, 2w, c] -> dx [n, h, w, c] */
 int sbgm_upsample2x_backward(const void* dy, size_t dy_plane, void* dx, size_t dx_plane, int fmt, int n, int h, int w, int c,
                              void* stream);
-/* attention core backward: dqkv [b*s][3c] from qkv and dout [b*s][c]; scratch = ..._scratch_floats floats */
+/* attention core backward: dqkv [b*s][3c] from qkv, the forward's output `out` [b*s][c] (NULL: not available) and dout
+ * [b*s][c].  bf16 with S % 16 == 0 and head dim 32 / 64 / 128 (and `out` given): ONE warp-level tensor-core launch, a CTA
+ * per (image, head), nothing but dqkv written (attention_bwd_mma.cu; SBGM_B200_ATTN_BWD_MMA=0 disables).  Otherwise: fp32
+ * batched CUDA-core GEMMs from `scratch` (..._scratch_floats floats; unused by the tensor-core path). */
 size_t sbgm_attention_backward_scratch_floats(int b, int s, int c, int heads);
-int sbgm_attention_backward(const void* qkv, size_t qkv_plane, const void* dout, size_t dout_plane, void* dqkv, size_t dqkv_plane,
-                            int fmt, int b, int s, int c, int heads, float* scratch, void* stream);
+int sbgm_attention_backward(const void* qkv, size_t qkv_plane, const void* out, size_t out_plane, const void* dout, size_t dout_plane,
+                            void* dqkv, size_t dqkv_plane, int fmt, int b, int s, int c, int heads, float* scratch, void* stream);
 /* backward of sbgm_time_embed_project (one row per batch member): d_proj_w[c_total][te], d_proj_b[c_total],
  * d_label_emb[n_classes][te] (NULL when the model has no labels) */
 size_t sbgm_time_embed_backward_scratch_floats(int n_sets, int te, int rows);
@@ -400,11 +410,13 @@ size_t sbgm_stem_wgrad_workspace_floats(int cin);
 int sbgm_stem_wgrad(const float* x, const float* planes, int np, int cc, const void* df, size_t df_plane, int fmt, float* dweight_oihw,
                     int n, int h, int w, float* workspace, void* stream);
 /* Decoder.final_layer.conv (cin -> 1, 3x3) + the 1/std scaling, backward: g = dscore * inv_std[n];
- * da [n,h,w,cin] (fmt), dweight_oihw[1][cin][3][3], dbias[1]; weight_tap_ci = fp32 [9][cin] */
+ * da [n,h,w,cin] (fmt), dweight_oihw[1][cin][3][3], dbias[1]; weight_tap_ci = fp32 [9][cin].  dbias_up[cin] (nullable) = da
+ * summed over n,h,w: the bias gradient of the convolution that produced `a` (final_layer.conv_up), free in the same pass
+ * (needs cin / 8 to be a power of two). */
 size_t sbgm_final_conv_backward_scratch_floats(int cin);
 int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const void* a, size_t a_plane, int fmt,
-                             const float* weight_tap_ci, void* da, size_t da_plane, float* dweight_oihw, float* dbias, int n, int h,
-                             int w, int cin, float* scratch, void* stream);
+                             const float* weight_tap_ci, void* da, size_t da_plane, float* dweight_oihw, float* dbias, float* dbias_up,
+                             int n, int h, int w, int cin, float* scratch, void* stream);
 /* Pack a torch OIHW fp32 weight for the tensor-core kernels in one launch: out[o][t][i] = w[co][ci][taps_host[t]]
  * with (o, i) = (co, ci), or (ci, co) when `transpose` (the flipped / parity-sliced data-gradient weights);
  * K-major bf16 or split-bf16 (planes `out_plane` elements apart).  taps_host is a HOST array of ntaps <= 64
@@ -421,6 +433,21 @@ typedef struct {
   int taps[16];
 } sbgm_pack_job;
 int sbgm_pack_weights(const sbgm_pack_job* jobs_host, int njobs, int fmt, void* stream);
+/* torch.optim.Adam / AdamW update (sbgm/training.py:407 `self.optimizer.step()`, optimizer built by sbgm/training_utils.py:672-698)
+ * of EVERY parameter tensor in one launch.  chunks_dev: DEVICE table, one entry per block, each covering at most
+ * sbgm_adam_chunk_elems() consecutive elements of one tensor.  Arithmetic follows torch/optim/adam.py (_single_tensor_adam,
+ * amsgrad / maximize off): decoupled = 0 adds weight_decay * p to the gradient, 1 multiplies p by 1 - lr * weight_decay. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int count;
+  int pad_;
+} sbgm_adam_chunk;
+int sbgm_adam_chunk_elems(void);
+int sbgm_adam_step(const sbgm_adam_chunk* chunks_dev, int n_chunks, double lr, double beta1, double beta2, float eps, float weight_decay,
+                   int decoupled, double bias_correction1, double bias_correction2, void* stream);
 /* d loss / d score of sbgm_dsm_loss, times *grad_loss (device scalar; NULL = 1) */
 int sbgm_dsm_loss_backward(const float* score, const float* std, const float* z, const float* sdf, const float* grad_loss, int n,
                            int per_member, float* dscore, void* stream);

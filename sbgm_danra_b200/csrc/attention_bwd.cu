@@ -157,6 +157,11 @@ static void launch_bgemm(const float* A, const float* B, float* C, int M, int N,
 
 }  // namespace sbgm
 
+namespace sbgm {
+int attention_bwd_mma_dispatch(const void* qkv, const void* out, const void* dout, void* dqkv, int fmt, int b, int s, int c, int heads,
+                               cudaStream_t st);     // attention_bwd_mma.cu; -1 = shape / format not covered
+}
+
 using namespace sbgm;
 
 extern "C" {
@@ -166,10 +171,16 @@ size_t sbgm_attention_backward_scratch_floats(int b, int s, int c, int heads) {
   return static_cast<size_t>(7) * b * s * c + static_cast<size_t>(2) * b * heads * s * s;
 }
 
-int sbgm_attention_backward(const void* qkv, size_t qkv_plane, const void* dout, size_t dout_plane, void* dqkv, size_t dqkv_plane,
-                            int fmt, int b, int s, int c, int heads, float* scratch, void* stream) {
+int sbgm_attention_backward(const void* qkv, size_t qkv_plane, const void* out, size_t out_plane, const void* dout, size_t dout_plane,
+                            void* dqkv, size_t dqkv_plane, int fmt, int b, int s, int c, int heads, float* scratch, void* stream) {
   SBGM_REQUIRE(heads >= 1 && c % heads == 0 && (c / heads) % 8 == 0, "attention_backward: bad c=%d heads=%d", c, heads);
   cudaStream_t st = as_stream(stream);
+  (void)out_plane;
+  static const bool mma_on = [] { const char* e = getenv("SBGM_B200_ATTN_BWD_MMA"); return !(e != nullptr && e[0] == '0'); }();
+  if (mma_on) {      // bf16, S % 16 == 0, head dim 32 / 64 / 128: one tensor-core launch
+    const int rc = attention_bwd_mma_dispatch(qkv, out, dout, dqkv, fmt, b, s, c, heads, st);
+    if (rc >= 0) return rc;
+  }
   const int d = c / heads, bh = b * heads;
   const size_t tok = static_cast<size_t>(b) * s * c, mat = static_cast<size_t>(bh) * s * s;
   float* q = scratch;

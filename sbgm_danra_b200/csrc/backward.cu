@@ -159,112 +159,215 @@ __global__ void norm_apply_kernel(const NormArgs a, void* __restrict__ y, size_t
 }
 
 // ---- normalisation backward ---------------------------------------------------------------------
-// Stage 1: per (n, chunk) per-channel sums of  dY,  dU = dY * act'(u),  dU * xhat.
+// Two launches per layer.  Launch 1 (norm_bwd_sums_kernel) is the whole reduction tree:
+//   * every block: per (n, chunk) per-channel sums of  dY,  dU = dY * act'(u),  dU * xhat,  xhat   -> partials[n][chunk][c][4]
+//   * the LAST block of a sample to finish (integer ticket, no floating-point atomics: the order of every sum is fixed)
+//     adds the chunks -> sums[n][c][4], writes dtproj[n][c] and, for GroupNorm, the sample's projection coefficients
+//       A = sum(gamma * dU) / cnt,  B = sum(gamma * dU * xhat) / cnt      (coef[stat index][2])
+//   * the LAST sample to finish adds over the samples: dgamma / dbeta, BatchNorm's per-channel A / B, and -- closed form, no
+//     pass over dx -- the bias gradient of the convolution in front of the norm:
+//       sum_p dx = rstd * (gamma * sum dU - hw * A - B * sum xhat)
+// Launch 2 (norm_bwd_apply_kernel): dx = rstd * (gamma * dU - A - xhat * B);  dadd = dU.
+// Tickets live in the first kNormTicketWords words of the scratch buffer: zero before the first use, left zero by every launch.
+constexpr int kNormTicketWords = 4096;
+
+struct NormBwdTail {
+  unsigned int* tickets;      // [0] = samples finished, [1 + n] = chunk blocks of sample n finished
+  float* sums;                // [n][c][4]
+  const float* sums_all;      // BatchNorm over the global batch (synchronised): [n_all][c][4]; else == sums
+  float* coef;
+  float* dgamma; float* dbeta; float* dbias_prev;
+  float* dtproj; int dtproj_stride;
+  int n, n_all, fixed_stats, with_coef;
+  float inv_cnt;
+};
+
+// true in every thread of the block that takes the last of `total` tickets; the caller's global writes are published first
+__device__ __forceinline__ bool last_ticket(unsigned int* ticket, unsigned int total) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == total - 1);
+    if (is_last) *ticket = 0;          // self-cleaning: the next launch finds zero
+  }
+  __syncthreads();
+  const bool last = is_last != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// Sums over the samples, by ONE block (the tail of the reduction tree): dgamma, dbeta, BatchNorm's coefficients, the bias
+// gradient in front.  Latency-bound (n x c float4 from L2), so every thread of the block takes a slice of the samples of one
+// channel with eight loads in flight, and the slices are added in a fixed order through shared memory `sm`
+// (>= max(c, blockDim.x) * 4 floats).
+__device__ void norm_bwd_tail_global(const NormArgs& a, const NormBwdTail& t, float* sm) {
+  const int c = a.c, nt = blockDim.x;
+  const int cw = min(c, nt), parts = nt / cw;          // threads = [parts][cw]
+  const int part = threadIdx.x / cw, ch0 = threadIdx.x % cw;
+  const bool bn = a.n_stride == 0;
+  const bool gathered = bn && !t.fixed_stats && t.sums_all != t.sums;
+  const float4* sums4 = reinterpret_cast<const float4*>(t.sums);
+  for (int base = 0; base < c; base += cw) {           // (one pass unless c > blockDim.x)
+    const int ch = base + ch0;
+    float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+    if (part < parts && ch < c) {
+      const float ga = a.gamma ? a.gamma[ch] : 1.0f;
+      if (bn) {
+#pragma unroll 8
+        for (int k = part; k < t.n; k += parts) {
+          const float4 s = __ldcg(sums4 + static_cast<size_t>(k) * c + ch);
+          s1 += s.y; s2 += s.z; s3 += s.w;
+        }
+        if (gathered) {
+#pragma unroll 8
+          for (int k = part; k < t.n_all; k += parts) {
+            const float4 s = __ldcg(reinterpret_cast<const float4*>(t.sums_all) + static_cast<size_t>(k) * c + ch);
+            g1 += s.y; g2 += s.z;
+          }
+        }
+      } else {
+        // GroupNorm: s3 collects the bias gradient itself, its coefficients being per (sample, group)
+#pragma unroll 8
+        for (int k = part; k < t.n; k += parts) {
+          const float4 s = __ldcg(sums4 + static_cast<size_t>(k) * c + ch);
+          s1 += s.y; s2 += s.z;
+          if (t.dbias_prev) {
+            const size_t si = static_cast<size_t>(k) * a.n_stride + ch / a.cpg;
+            const float2 cf = __ldcg(reinterpret_cast<const float2*>(t.coef) + si);
+            s3 += a.stats[2 * si + 1] * (ga * s.y - a.hw * cf.x - s.w * cf.y);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (part < parts && ch < c) *reinterpret_cast<float4*>(sm + (static_cast<size_t>(part) * cw + ch0) * 4) = make_float4(s1, s2, s3, g1);
+    __syncthreads();
+    float g2s = g2;                                     // the gathered second moment travels through a second round
+    if (part == 0 && ch < c) {
+      for (int q = 1; q < parts; ++q) {
+        const float4 o = *reinterpret_cast<const float4*>(sm + (static_cast<size_t>(q) * cw + ch0) * 4);
+        s1 += o.x; s2 += o.y; s3 += o.z; g1 += o.w;
+      }
+    }
+    if (gathered) {
+      __syncthreads();
+      if (part < parts && ch < c) sm[static_cast<size_t>(part) * cw + ch0] = g2;
+      __syncthreads();
+      if (part == 0 && ch < c) for (int q = 1; q < parts; ++q) g2s += sm[static_cast<size_t>(q) * cw + ch0];
+    }
+    if (part == 0 && ch < c) {
+      const float ga = a.gamma ? a.gamma[ch] : 1.0f;
+      if (t.dgamma) { t.dgamma[ch] = s2; t.dbeta[ch] = s1; }
+      if (bn) {                         // one statistics group per channel, spanning the (global) batch
+        float ca = 0.0f, cb = 0.0f;
+        if (!t.fixed_stats) {           // eval mode: the statistics are constants, no projection terms
+          ca = ga * (gathered ? g1 : s1) * t.inv_cnt;
+          cb = ga * (gathered ? g2s : s2) * t.inv_cnt;
+        }
+        t.coef[2 * ch] = ca;
+        t.coef[2 * ch + 1] = cb;
+        if (t.dbias_prev) t.dbias_prev[ch] = a.stats[2 * ch + 1] * (ga * s1 - static_cast<float>(t.n) * a.hw * ca - s3 * cb);
+      } else if (t.dbias_prev) {
+        t.dbias_prev[ch] = s3;
+      }
+    }
+  }
+}
+
 template <int FMT>
-__global__ void norm_bwd_partial_kernel(const NormArgs a, const void* __restrict__ dy, size_t dy_plane, float* __restrict__ partials, int chunks) {
+__global__ void __launch_bounds__(256, 2) norm_bwd_sums_kernel(const NormArgs a, const void* __restrict__ dy, size_t dy_plane, float* __restrict__ partials, int chunks,
+                                     const NormBwdTail t) {
   pdl_grid_sync();
-  extern __shared__ float red[];  // [lanes][c][3]
+  extern __shared__ float red[];  // [lanes][c][4]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int c = a.c, vecs = c >> 3, lanes = blockDim.x / vecs;
   const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
   const int per_chunk = (a.hw + chunks - 1) / chunks;
   const int p_begin = chunk * per_chunk, p_end = min(a.hw, p_begin + per_chunk);
-  float s0[8], s1[8], s2[8];
+  float s0[8], s1[8], s2[8], s3[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = 0.0f;
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = s3[j] = 0.0f;
   if (lane < lanes) {
     float mean[8], rstd[8], ga[8], sh[8], post[8];
     norm_coefs(a, n, vec * 8, mean, rstd, ga, sh, post);
-    for (int p = p_begin + lane; p < p_end; p += lanes) {
-      const size_t idx = (static_cast<size_t>(n) * a.hw + p) * c + vec * 8;
-      float v[8], g[8], r[8];
-      Act<FMT>::load8(a.x, a.x_plane, idx, v);
-      Act<FMT>::load8(dy, dy_plane, idx, g);
-      if (a.add) Act<FMT>::load8(a.add, a.add_plane, idx, r);
+    // the layers are small (a few MB): the block is latency-bound, so the loads of kUn pixels are issued before any is used
+    // (kUn = 4 needs 254 registers: one block per SM)
+    constexpr int kUn = 2;
+    for (int p = p_begin + lane; p < p_end; p += lanes * kUn) {
+      float v[kUn][8], g[kUn][8], r[kUn][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (v[j] - mean[j]) * rstd[j];
-        float u = fmaf(xh, ga[j], sh[j]);
-        if (a.add) u += r[j];
-        const float du = g[j] * act_grad(u, a.act);
-        s0[j] += g[j];
-        s1[j] += du;
-        s2[j] = fmaf(du, xh, s2[j]);
+      for (int k = 0; k < kUn; ++k) {
+        if (p + k * lanes < p_end) {
+          const size_t idx = (static_cast<size_t>(n) * a.hw + p + k * lanes) * c + vec * 8;
+          Act<FMT>::load8(a.x, a.x_plane, idx, v[k]);
+          Act<FMT>::load8(dy, dy_plane, idx, g[k]);
+          if (a.add) Act<FMT>::load8(a.add, a.add_plane, idx, r[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kUn; ++k) {
+        if (p + k * lanes >= p_end) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (v[k][j] - mean[j]) * rstd[j];
+          float u = fmaf(xh, ga[j], sh[j]);
+          if (a.add) u += r[k][j];
+          const float du = g[k][j] * act_grad(u, a.act);
+          s0[j] += g[k][j];
+          s1[j] += du;
+          s2[j] = fmaf(du, xh, s2[j]);
+          s3[j] += xh;
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float* o = red + (static_cast<size_t>(lane) * c + vec * 8 + j) * 3;
-      o[0] = s0[j]; o[1] = s1[j]; o[2] = s2[j];
-    }
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(red + (static_cast<size_t>(lane) * c + vec * 8 + j) * 4) = make_float4(s0[j], s1[j], s2[j], s3[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < c * 3; i += blockDim.x) {
+  for (int i = threadIdx.x; i < c * 4; i += blockDim.x) {
     float acc = 0.0f;
-    for (int l = 0; l < lanes; ++l) acc += red[static_cast<size_t>(l) * c * 3 + i];
-    partials[(static_cast<size_t>(n) * chunks + chunk) * c * 3 + i] = acc;
+    for (int l = 0; l < lanes; ++l) acc += red[static_cast<size_t>(l) * c * 4 + i];
+    partials[(static_cast<size_t>(n) * chunks + chunk) * c * 4 + i] = acc;
   }
-}
-
-// Stage 2a: sums[n][c][3] over the chunks; dtproj[n][c].
-__global__ void norm_bwd_reduce_kernel(const float* __restrict__ partials, int c, int chunks, int tproj_pre, float* __restrict__ sums,
-                                       float* __restrict__ dtproj, int dtproj_stride) {
-  pdl_grid_sync();
-  const int n = blockIdx.x;
-  for (int i = threadIdx.x; i < c * 3; i += blockDim.x) {
+  // ---- last block of this sample: sums over the chunks, dtproj, GroupNorm coefficients ----
+  if (!last_ticket(t.tickets + 1 + n, chunks)) return;
+  float* sums_n = t.sums + static_cast<size_t>(n) * c * 4;
+  for (int i = threadIdx.x; i < c * 4; i += blockDim.x) {
     float s = 0.0f;
-    for (int k = 0; k < chunks; ++k) s += partials[(static_cast<size_t>(n) * chunks + k) * c * 3 + i];
-    sums[static_cast<size_t>(n) * c * 3 + i] = s;
-    const int ch = i / 3, which = i - ch * 3;
-    if (dtproj && which == (tproj_pre ? 1 : 0)) dtproj[static_cast<size_t>(n) * dtproj_stride + ch] = s;
+#pragma unroll 8
+    for (int k = 0; k < chunks; ++k) s += __ldcg(partials + (static_cast<size_t>(n) * chunks + k) * c * 4 + i);
+    sums_n[i] = s;
+    red[i] = s;
+    const int ch = i >> 2, which = i & 3;
+    if (t.dtproj && which == (a.tproj_pre ? 1 : 0)) t.dtproj[static_cast<size_t>(n) * t.dtproj_stride + ch] = s;
   }
+  __syncthreads();
+  if (t.with_coef && a.n_stride != 0) {
+    for (int g = threadIdx.x; g < a.n_stride; g += blockDim.x) {
+      float ca = 0.0f, cb = 0.0f;
+      for (int j = 0; j < a.cpg; ++j) {
+        const int ch = g * a.cpg + j;
+        const float ga = a.gamma ? a.gamma[ch] : 1.0f;
+        ca = fmaf(ga, red[ch * 4 + 1], ca);
+        cb = fmaf(ga, red[ch * 4 + 2], cb);
+      }
+      t.coef[2 * (static_cast<size_t>(n) * a.n_stride + g)] = ca * t.inv_cnt;
+      t.coef[2 * (static_cast<size_t>(n) * a.n_stride + g) + 1] = cb * t.inv_cnt;
+    }
+  }
+  // ---- last sample: sums over the samples ----
+  if (!last_ticket(t.tickets, gridDim.y)) return;
+  if (t.with_coef) norm_bwd_tail_global(a, t, red);
 }
 
-// Stage 2b: dgamma / dbeta (sum over samples) and the two projection coefficients of each statistics group:
-//   A = sum(gamma * dU) / cnt,  B = sum(gamma * dU * xhat) / cnt      (coef[stat index][2])
-__global__ void norm_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ sums_all, int n_all,
-                                     const float* __restrict__ gamma, int n, int c, int n_stride,
-                                     int cpg, float inv_cnt, int fixed_stats, float* __restrict__ coef, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
+// synchronised BatchNorm, stage 2: the per-channel tail alone (one block), over the gathered sums of every rank
+__global__ void norm_bwd_tail_kernel(const NormArgs a, const NormBwdTail t) {
   pdl_grid_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < c && dgamma) {
-    float a = 0.0f, b = 0.0f;
-    for (int k = 0; k < n; ++k) {
-      const float* s = sums + (static_cast<size_t>(k) * c + i) * 3;
-      b += s[1];
-      a += s[2];
-    }
-    dgamma[i] = a;
-    dbeta[i] = b;
-  }
-  if (fixed_stats) {                // eval-mode BatchNorm: the statistics are constants, no projection terms
-    if (i < c) coef[2 * i] = coef[2 * i + 1] = 0.0f;
-  } else if (n_stride == 0) {       // BatchNorm: one statistics group per channel, spanning the (global) batch
-    if (i < c) {
-      float a = 0.0f, b = 0.0f;
-      for (int k = 0; k < n_all; ++k) {
-        const float* s = sums_all + (static_cast<size_t>(k) * c + i) * 3;
-        a += s[1];
-        b += s[2];
-      }
-      const float g = gamma ? gamma[i] : 1.0f;
-      coef[2 * i] = g * a * inv_cnt;
-      coef[2 * i + 1] = g * b * inv_cnt;
-    }
-  } else if (i < n * n_stride) {    // GroupNorm: group (sample, g)
-    const int k = i / n_stride, g = i - k * n_stride;
-    float a = 0.0f, b = 0.0f;
-    for (int j = 0; j < cpg; ++j) {
-      const int ch = g * cpg + j;
-      const float ga = gamma ? gamma[ch] : 1.0f;
-      const float* s = sums + (static_cast<size_t>(k) * c + ch) * 3;
-      a = fmaf(ga, s[1], a);
-      b = fmaf(ga, s[2], b);
-    }
-    coef[2 * i] = a * inv_cnt;
-    coef[2 * i + 1] = b * inv_cnt;
-  }
+  extern __shared__ float red[];
+  norm_bwd_tail_global(a, t, red);
 }
 
 // Stage 3: dx = rstd * (gamma * dU - A - xhat * B);  dadd = dU.
@@ -499,6 +602,55 @@ __global__ void chansum_finish_kernel(const float* __restrict__ partials, int n,
   if (out_total && lane == 0) out_total[ch] = tot;
 }
 
+// Total only (bias gradients of the Linear layers, x = [n * hw][c]): ONE launch.  The pixels of all samples are dealt to up to
+// kChansumBlocks blocks; the last block to finish (integer ticket; summation order fixed) adds the per-block rows.
+constexpr int kChansumBlocks = 296;
+constexpr int kChansumTicketWords = 4096;     // == kNormTicketWords: one ticketed-scratch convention (train_engine.TrainKernels.scratch)
+template <int FMT>
+__global__ void chansum_total_kernel(const void* __restrict__ x, size_t plane, int pixels, int c, float* __restrict__ partials,
+                                     unsigned int* __restrict__ ticket, float* __restrict__ out_total) {
+  pdl_grid_sync();
+  extern __shared__ float red[];  // [max(lanes, parts)][c]
+  const int vecs = c >> 3, lanes = blockDim.x / vecs;
+  const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
+  if (lane < lanes) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+    for (int p = blockIdx.x * lanes + lane; p < pixels; p += gridDim.x * lanes) {
+      float v[8];
+      Act<FMT>::load8(x, plane, static_cast<size_t>(p) * c + vec * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[static_cast<size_t>(lane) * c + vec * 8 + j] = s[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    float acc = 0.0f;
+    for (int l = 0; l < lanes; ++l) acc += red[static_cast<size_t>(l) * c + i];
+    partials[static_cast<size_t>(blockIdx.x) * c + i] = acc;
+  }
+  if (!last_ticket(ticket, gridDim.x)) return;
+  const int cw = min(c, static_cast<int>(blockDim.x)), parts = blockDim.x / cw;
+  const int part = threadIdx.x / cw, ch0 = threadIdx.x % cw;
+  for (int base = 0; base < c; base += cw) {
+    const int ch = base + ch0;
+    float acc = 0.0f;
+    if (part < parts && ch < c) {
+#pragma unroll 8
+      for (int k = part; k < static_cast<int>(gridDim.x); k += parts) acc += __ldcg(partials + static_cast<size_t>(k) * c + ch);
+    }
+    __syncthreads();
+    if (part < parts && ch < c) red[static_cast<size_t>(part) * cw + ch0] = acc;
+    __syncthreads();
+    if (part == 0 && ch < c) {
+      for (int q = 1; q < parts; ++q) acc += red[static_cast<size_t>(q) * cw + ch0];
+      out_total[ch] = acc;
+    }
+  }
+}
+
 // ---- bilinear x2 upsample backward (adjoint of upsample2x_kernel) ----------------------------------
 // Input pixel i receives from output rows 2i-1, 2i, 2i+1, 2i+2 the weights
 //   0.25 (i >= 1) | 0.75 (+0.25 if i == 0) | 0.75 (+0.25 if i == h-1) | 0.25 (i <= h-2)        (same along w)
@@ -676,33 +828,40 @@ int sbgm_norm_apply(const void* x, size_t x_plane, const float* stats, int per_s
   return check_launch("norm_apply");
 }
 
-size_t sbgm_norm_backward_sums_offset(int n, int c) { return static_cast<size_t>(n) * kNormChunks * c * 3; }
+size_t sbgm_norm_backward_sums_offset(int n, int c) { return kNormTicketWords + static_cast<size_t>(n) * kNormChunks * c * 4; }
+size_t sbgm_norm_backward_sums_floats(int n, int c) { return static_cast<size_t>(n) * c * 4; }
 
 size_t sbgm_norm_backward_scratch_floats(int n, int c) {
-  return static_cast<size_t>(n) * kNormChunks * c * 3 + static_cast<size_t>(n) * c * 3 + static_cast<size_t>(n) * c * 2 + 64;
+  return kNormTicketWords + static_cast<size_t>(n) * kNormChunks * c * 4 + static_cast<size_t>(n) * c * 4 + static_cast<size_t>(n) * c * 2 + 64;
 }
 
 int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, const float* stats, int per_sample_stats,
                        int groups, const float* gamma, const float* beta, const void* add, size_t add_plane,
                        const float* tproj, int tproj_stride, int tproj_pre_act, int act, void* dx, size_t dx_plane,
-                       void* dadd, size_t dadd_plane, float* dgamma, float* dbeta, float* dtproj, int dtproj_stride,
+                       void* dadd, size_t dadd_plane, float* dgamma, float* dbeta, float* dbias_prev, float* dtproj, int dtproj_stride,
                        int fmt, int n, int hw, int c, float* scratch, int stage, const float* sums_all, int n_all, void* stream) {
   SBGM_REQUIRE(c % 8 == 0 && c <= 2048 && groups >= 1 && c % groups == 0, "norm_backward: bad c=%d groups=%d", c, groups);
   SBGM_REQUIRE(stage >= 0 && stage <= 2, "norm_backward: stage %d", stage);
-  SBGM_REQUIRE(sums_all == nullptr || (per_sample_stats == 0 && n_all >= n), "norm_backward: gathered sums are for batch statistics only");
+  SBGM_REQUIRE(stage == 0 || per_sample_stats == 0, "norm_backward: stages 1 / 2 (gathered sums) are for batch statistics only");
+  SBGM_REQUIRE(sums_all == nullptr || (stage == 2 && n_all >= n), "norm_backward: gathered sums belong to stage 2");
+  SBGM_REQUIRE(n + 1 <= kNormTicketWords, "norm_backward: batch %d too large", n);
   const int vecs = c / 8;
   SBGM_REQUIRE(vecs <= 256, "norm_backward: c too large");
   const NormArgs a = make_norm_args(x, x_plane, stats, per_sample_stats, groups, gamma, beta, add, add_plane, tproj, tproj_stride,
                                     tproj_pre_act, act, hw, c);
-  float* partials = scratch;
-  float* sums = partials + static_cast<size_t>(n) * kNormChunks * c * 3;
-  float* coef = sums + static_cast<size_t>(n) * c * 3;
+  float* partials = scratch + kNormTicketWords;
+  float* sums = partials + static_cast<size_t>(n) * kNormChunks * c * 4;
+  float* coef = sums + static_cast<size_t>(n) * c * 4;
   cudaStream_t st = as_stream(stream);
   const int lanes = 256 / vecs;
-  const size_t smem1 = static_cast<size_t>(lanes) * c * 3 * sizeof(float);
-  const int n_groups_total = per_sample_stats == 1 ? n * groups : c;
+  const size_t smem1 = static_cast<size_t>(lanes) * c * 4 * sizeof(float);
   if (sums_all == nullptr) { sums_all = sums; n_all = n; }
   const double cnt = per_sample_stats == 1 ? static_cast<double>(hw) * (c / groups) : static_cast<double>(n_all) * hw;
+  NormBwdTail t;
+  t.tickets = reinterpret_cast<unsigned int*>(scratch);
+  t.sums = sums; t.sums_all = sums_all; t.coef = coef; t.dgamma = dgamma; t.dbeta = dbeta; t.dbias_prev = dbias_prev;
+  t.dtproj = dtproj; t.dtproj_stride = dtproj_stride; t.n = n; t.n_all = n_all; t.fixed_stats = per_sample_stats == 2;
+  t.with_coef = stage == 0; t.inv_cnt = static_cast<float>(1.0 / cnt);
   int slots = 148 * 8;
   SBGM_DISPATCH_FMT(fmt, (slots = resident_blocks(reinterpret_cast<const void*>(norm_bwd_apply_kernel<FMT>), 256, 0)));
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), slots / max(n, 1)));
@@ -711,14 +870,15 @@ int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_
   dim3 g1(chunks, n), g3(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
     if (stage != 2) {
-      launch_k((norm_bwd_partial_kernel<FMT>), g1, 256, smem1, st, a, dy, dy_plane, partials, chunks);
-      launch_k((norm_bwd_reduce_kernel), n, 256, 0, st, partials, c, chunks, tproj_pre_act, sums, dtproj, dtproj_stride);
+      auto k1 = norm_bwd_sums_kernel<FMT>;
+      if (smem1 > 48 * 1024 && cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)) != cudaSuccess) {
+        set_error("norm_backward: cannot reserve %zu bytes of shared memory", smem1);
+        return 1;
+      }
+      launch_k((k1), g1, 256, smem1, st, a, dy, dy_plane, partials, chunks, t);
     }
-    if (stage != 1) {
-      launch_k((norm_bwd_coef_kernel), ceil_div(max(c, n_groups_total), 256), 256, 0, st, sums, sums_all, n_all, gamma, n, c, a.n_stride,
-               a.cpg, static_cast<float>(1.0 / cnt), per_sample_stats == 2, coef, dgamma, dbeta);
-      launch_k((norm_bwd_apply_kernel<FMT>), g3, 256, 0, st, a, dy, dy_plane, coef, dx, dx_plane, dadd, dadd_plane);
-    }
+    if (stage == 2) launch_k((norm_bwd_tail_kernel), 1, 256, static_cast<size_t>(max(c, 256)) * 4 * sizeof(float), st, a, t);
+    if (stage != 1) launch_k((norm_bwd_apply_kernel<FMT>), g3, 256, 0, st, a, dy, dy_plane, coef, dx, dx_plane, dadd, dadd_plane);
   });
   return check_launch("norm_backward");
 }
@@ -755,17 +915,34 @@ int sbgm_add_inplace(void* dst, size_t dst_plane, const void* src, size_t src_pl
   return check_launch("add_inplace");
 }
 
-size_t sbgm_channel_sums_scratch_floats(int n, int c) { return static_cast<size_t>(n) * kNormChunks * c; }
+size_t sbgm_channel_sums_scratch_floats(int n, int c) {
+  const size_t per_sample = static_cast<size_t>(n) * kNormChunks * c, total = static_cast<size_t>(kChansumBlocks) * c;
+  return kChansumTicketWords + (per_sample > total ? per_sample : total);
+}
 
 int sbgm_channel_sums(const void* x, size_t x_plane, int fmt, int n, int hw, int c, float* out_per_sample, int out_stride,
                       float* out_total, float* scratch, void* stream) {
   SBGM_REQUIRE(c % 8 == 0 && c / 8 <= 256, "channel_sums: bad c=%d", c);
   const int vecs = c / 8, lanes = 256 / vecs;
   cudaStream_t st = as_stream(stream);
+  float* partials = scratch + kChansumTicketWords;
+  if (out_per_sample == nullptr) {
+    SBGM_REQUIRE(out_total != nullptr, "channel_sums: no output");
+    const long long pixels = static_cast<long long>(n) * hw;
+    SBGM_REQUIRE(pixels < (1ll << 31), "channel_sums: tensor too large");
+    // the main pass shrinks with the block count, the last block's tail (c x blocks partials through one SM) grows with it:
+    // both are latency-bound and balance near blocks = sqrt(pixels)
+    const int blocks = max(1, min(min(kChansumBlocks, ceil_div(pixels, static_cast<long long>(lanes) * 8)),
+                                  static_cast<int>(sqrt(static_cast<double>(pixels)))));
+    const size_t smem = static_cast<size_t>(max(lanes, 256 / min(c, 256))) * c * sizeof(float);
+    SBGM_DISPATCH_FMT(fmt, (launch_k((chansum_total_kernel<FMT>), blocks, 256, smem, st, x, x_plane, static_cast<int>(pixels), c, partials,
+                                                                            reinterpret_cast<unsigned int*>(scratch), out_total)));
+    return check_launch("channel_sums");
+  }
   const int chunks = max(1, min(kNormChunks, hw / (lanes * 8)));
   dim3 g1(chunks, n);
-  SBGM_DISPATCH_FMT(fmt, (launch_k((chansum_partial_kernel<FMT>), g1, 256, static_cast<size_t>(lanes) * c * sizeof(float), st, x, x_plane, hw, c, scratch, chunks)));
-  launch_k((chansum_finish_kernel), ceil_div(c, 8), 256, 0, st, scratch, n, c, chunks, out_per_sample, out_stride, out_total);
+  SBGM_DISPATCH_FMT(fmt, (launch_k((chansum_partial_kernel<FMT>), g1, 256, static_cast<size_t>(lanes) * c * sizeof(float), st, x, x_plane, hw, c, partials, chunks)));
+  launch_k((chansum_finish_kernel), ceil_div(c, 8), 256, 0, st, partials, n, c, chunks, out_per_sample, out_stride, out_total);
   return check_launch("channel_sums");
 }
 

@@ -253,6 +253,143 @@ __global__ void final_conv_bwd_input_kernel(const float* __restrict__ dscore, co
   }
 }
 
+// Both gradients in one pass over the activation (cin / 8 a power of two <= 32): a block owns tiles of kFinalTileRows x lanes pixels
+// of one image, stages g (zero outside the image: no boundary branches) for the tile + halo in shared memory, and each thread
+// (pixel column `lane`, channel vector `vec`) walks the tile's rows: the SAME nine g values feed da[p][ci] += g * w[tap][ci] and
+// dW[tap][ci] += g * a[p][ci]; it also sums da per channel (the bias gradient of the convolution that produced `a`).  Loads of
+// `a` are issued four rows ahead.  Per block: warp-shuffle reduction over the pixel lanes, then one partial row.
+// Algorithmic traffic: read a + write da (2 x n*h*w*cin elements) -- the two separate kernels read / wrote the same bytes at
+// ~1/6 of the HBM rate (72 accumulators per thread, one load in flight, boundary branches).
+constexpr int kFinalTileRows = 8;
+template <int FMT>
+__global__ void __launch_bounds__(256, 1)
+final_conv_bwd_fused_kernel(const float* __restrict__ dscore, const float* __restrict__ inv_std, const void* __restrict__ a, size_t a_plane,
+                            const float* __restrict__ wgt, void* __restrict__ da, size_t da_plane, float* __restrict__ partials,
+                            int n, int h, int w, int cin) {
+  pdl_grid_sync();
+  extern __shared__ float sm[];
+  const int vecs = cin >> 3, lanes = 256 / vecs;
+  const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
+  const int gw = lanes + 2;
+  float* wsm = sm;                                  // [9][cin]
+  float* gs = wsm + 9 * cin;                        // [kFinalTileRows + 2][gw]
+  float* red = gs + (kFinalTileRows + 2) * gw;      // [8 warps][10 * cin + 1]
+  const int outs = 10 * cin + 1;
+  for (int i = threadIdx.x; i < 9 * cin; i += 256) wsm[i] = wgt[i];
+  float acc[9][8], bup[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bup[j] = 0.0f;
+  float bsum = 0.0f;
+  const int tiles_x = (w + lanes - 1) / lanes, tiles_y = (h + kFinalTileRows - 1) / kFinalTileRows;
+  const int ntiles = n * tiles_y * tiles_x;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const float sc = inv_std ? inv_std[b] : 1.0f;
+    const int y0 = ty * kFinalTileRows, x0 = tx * lanes;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (kFinalTileRows + 2) * gw; i += 256) {
+      const int yy = y0 - 1 + i / gw, xx = x0 - 1 + i % gw;
+      gs[i] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(dscore + (static_cast<size_t>(b) * h + yy) * w + xx) * sc : 0.0f;
+    }
+    __syncthreads();
+    const int x = x0 + lane;
+    if (x >= w) continue;            // (no barrier below this point inside the iteration)
+    const int rows = min(kFinalTileRows, h - y0);
+    const size_t base = ((static_cast<size_t>(b) * h + y0) * w + x) * cin + vec * 8;
+    const size_t row_pitch = static_cast<size_t>(w) * cin;
+    for (int ly0 = 0; ly0 < rows; ly0 += 4) {
+      float v[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ly0 + k < rows) Act<FMT>::load8(a, a_plane, base + (ly0 + k) * row_pitch, v[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ly = ly0 + k;
+        if (ly >= rows) break;
+        float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            // tap (r, s) pairs input pixel (y, x) with output pixel (y - r + 1, x - s + 1); gs origin is (y0 - 1, x0 - 1)
+            const float g = gs[(ly - r + 2) * gw + lane - s + 2];
+            const float4 w0 = *reinterpret_cast<const float4*>(wsm + (r * 3 + s) * cin + vec * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(wsm + (r * 3 + s) * cin + vec * 8 + 4);
+            o[0] = fmaf(g, w0.x, o[0]); o[1] = fmaf(g, w0.y, o[1]); o[2] = fmaf(g, w0.z, o[2]); o[3] = fmaf(g, w0.w, o[3]);
+            o[4] = fmaf(g, w1.x, o[4]); o[5] = fmaf(g, w1.y, o[5]); o[6] = fmaf(g, w1.z, o[6]); o[7] = fmaf(g, w1.w, o[7]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r * 3 + s][j] = fmaf(g, v[k][j], acc[r * 3 + s][j]);
+          }
+        Act<FMT>::store8(da, da_plane, base + ly * row_pitch, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bup[j] += o[j];
+        if (vec == 0) bsum += gs[(ly + 1) * gw + lane + 1];
+      }
+    }
+  }
+  // reduce over the pixel lanes of the warp (threads `vecs` apart share a channel vector), then over the 8 warps
+  for (int off = vecs; off < 32; off <<= 1) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] += __shfl_xor_sync(0xffffffffu, acc[t][j], off);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bup[j] += __shfl_xor_sync(0xffffffffu, bup[j], off);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  float* mine = red + static_cast<size_t>(warp) * outs;
+  if (vecs >= 32) {                      // one pixel lane per warp: every thread holds distinct channels
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine[t * cin + vec * 8 + j] = acc[t][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[9 * cin + 1 + vec * 8 + j] = bup[j];
+    if (vec == 0) mine[9 * cin] = bsum;
+  } else if (wl < vecs) {                // after the butterfly every lane holds the warp total of its vector
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine[t * cin + vec * 8 + j] = acc[t][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[9 * cin + 1 + vec * 8 + j] = bup[j];
+    if (vec == 0) mine[9 * cin] = bsum;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < outs; i += 256) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += red[static_cast<size_t>(k) * outs + i];
+    partials[static_cast<size_t>(blockIdx.x) * outs + i] = sum;
+  }
+}
+// finish of the fused kernel: dW (OIHW, O = 1), db, and the producing convolution's bias gradient dbias_up[cin] (nullable)
+__global__ void final_conv_bwd_fused_finish_kernel(const float* __restrict__ partials, int blocks, int cin, float* __restrict__ dW,
+                                                   float* __restrict__ db, float* __restrict__ dbias_up) {
+  pdl_grid_sync();
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;    // one warp per output
+  const int outs = 10 * cin + 1;
+  if (i >= outs) return;
+  float s = 0.0f;
+  for (int k = lane; k < blocks; k += 32) s += partials[static_cast<size_t>(k) * outs + i];
+  s = warp_sum(s);
+  if (lane != 0) return;
+  if (i < 9 * cin) {
+    const int tap = i / cin, ci = i - tap * cin;
+    dW[ci * 9 + tap] = s;
+  } else if (i == 9 * cin) {
+    db[0] = s;
+  } else if (dbias_up) {
+    dbias_up[i - 9 * cin - 1] = s;
+  }
+}
+
 constexpr int kFinalBwdBlocks = 1184;   // 148 SMs x 8: the kernel is latency-bound at low occupancy (72 accumulators / thread)
 template <int FMT>
 __global__ void __launch_bounds__(256)
@@ -401,16 +538,41 @@ int sbgm_stem_wgrad(const float* x, const float* planes, int np, int cc, const v
   return check_launch("stem_wgrad");
 }
 
-size_t sbgm_final_conv_backward_scratch_floats(int cin) { return static_cast<size_t>(kFinalBwdBlocks) * (9 * cin + 1); }
+static bool final_fused_ok(int cin) {
+  const int vecs = cin / 8;
+  return cin % 8 == 0 && vecs <= 32 && (vecs & (vecs - 1)) == 0;
+}
+static int final_fused_blocks() { return 148; }   // persistent: one block per SM (249 registers x 256 threads)
+
+size_t sbgm_final_conv_backward_scratch_floats(int cin) {
+  const size_t fused = static_cast<size_t>(final_fused_blocks()) * (10 * cin + 1), split = static_cast<size_t>(kFinalBwdBlocks) * (9 * cin + 1);
+  return fused > split ? fused : split;
+}
 
 int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const void* a, size_t a_plane, int fmt,
-                             const float* weight_tap_ci, void* da, size_t da_plane, float* dweight_oihw, float* dbias, int n, int h,
-                             int w, int cin, float* scratch, void* stream) {
+                             const float* weight_tap_ci, void* da, size_t da_plane, float* dweight_oihw, float* dbias, float* dbias_up,
+                             int n, int h, int w, int cin, float* scratch, void* stream) {
   SBGM_REQUIRE(cin % 8 == 0 && cin <= 256, "final_conv_backward: cin=%d unsupported", cin);
   cudaStream_t st = as_stream(stream);
   const int vecs = cin / 8, lanes = 256 / vecs;
   const size_t total = static_cast<size_t>(n) * h * w * vecs;
   SBGM_REQUIRE(total < (1ull << 32), "final_conv_backward: tensor too large for 32-bit indexing");
+  if (final_fused_ok(cin)) {
+    const size_t smem = (9 * cin + static_cast<size_t>(kFinalTileRows + 2) * (lanes + 2) + 8 * (10 * cin + 1)) * sizeof(float);
+    const int blocks = final_fused_blocks();
+    SBGM_DISPATCH_FMT(fmt, {
+      auto kf = final_conv_bwd_fused_kernel<FMT>;
+      if (smem > 48 * 1024 && cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+        set_error("final_conv_backward: cannot reserve %zu bytes of shared memory", smem);
+        return 1;
+      }
+      launch_k((kf), blocks, 256, smem, st, dscore, inv_std, a, a_plane, weight_tap_ci, da, da_plane, scratch, n, h, w, cin);
+    });
+    launch_k((final_conv_bwd_fused_finish_kernel), ceil_div((10 * cin + 1) * 32, 256), 256, 0, st, scratch, blocks, cin, dweight_oihw, dbias,
+             dbias_up);
+    return check_launch("final_conv_backward");
+  }
+  SBGM_REQUIRE(dbias_up == nullptr, "final_conv_backward: dbias_up needs cin / 8 to be a power of two (cin=%d)", cin);
   const size_t smem_w = static_cast<size_t>(lanes) * (9 * cin + 1) * sizeof(float);
   SBGM_DISPATCH_FMT(fmt, {
     auto kw_ = final_conv_bwd_weight_kernel<FMT>;

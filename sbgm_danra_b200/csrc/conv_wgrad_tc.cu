@@ -183,7 +183,10 @@ static void wgrad_tc_plan(int n, int ho, int wo, int cin, int cout, int kh, int 
   p->K = static_cast<size_t>(kh) * kw * cin;
   *bn = (fmt == SBGM_FMT_BF16 && cout % 128 == 0) ? 128 : 64;
   const int base = ((p->units + 1) / 2) * (cout / *bn);
-  int s = (148 * 3 + base - 1) / base;
+  // pixel split: `waves` x 148 CTAs per layer.  Every CTA dumps its [128 x BN] fp32 accumulator and the reduce reads it back, so
+  // the workspace traffic grows with the wave count (SBGM_B200_WGRAD_WAVES, A/B-tested on the training step)
+  static const int waves = [] { const char* e = getenv("SBGM_B200_WGRAD_WAVES"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 3; }();
+  int s = (148 * waves + base - 1) / base;
   if (s > p->total_tiles) s = p->total_tiles;
   if (s < 1) s = 1;
   p->tiles_per_split = (p->total_tiles + s - 1) / s;

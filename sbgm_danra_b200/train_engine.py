@@ -209,10 +209,16 @@ class TrainKernels:
         self._scratch: Dict[str, torch.Tensor] = {}
 
     # -- scratch management --------------------------------------------------------------------
-    def scratch(self, tag: str, floats: int) -> torch.Tensor:
+    TICKET_WORDS = 4096        # leading words of a ticketed scratch buffer (kNormTicketWords / kChansumTicketWords)
+
+    def scratch(self, tag: str, floats: int, tickets: bool = False) -> torch.Tensor:
+        """`tickets`: the buffer starts with the integer tickets of a last-block reduction (sbgm_norm_backward,
+        sbgm_channel_sums): they must be zero before the first use and every launch leaves them zero again."""
         cur = self._scratch.get(tag)
         if cur is None or cur.numel() < floats:
             cur = torch.empty(max(int(floats), 1), dtype=torch.float32, device=self.device)
+            if tickets:
+                cur[:self.TICKET_WORDS].zero_()
             self._scratch[tag] = cur
         return cur
 
@@ -225,9 +231,11 @@ class TrainKernels:
     # -- convolution ----------------------------------------------------------------------------
     def conv(self, x: Act, layer: ConvLayer, stride: int = 1, pad: int = 0, residual: Optional[Act] = None,
              gn_stats: bool = False, need_dx: bool = True, proj: Optional[torch.Tensor] = None,
-             tproj: Optional[torch.Tensor] = None, dtproj: Optional[torch.Tensor] = None):
+             tproj: Optional[torch.Tensor] = None, dtproj: Optional[torch.Tensor] = None, bias_grad: bool = True):
         """`proj`: also emit the nine per-tap partial products of the final 64 -> 1 convolution (returns (y, projected)).
-        `tproj` / `dtproj`: per-sample channel offsets added in the epilogue and where their gradient goes."""
+        `tproj` / `dtproj`: per-sample channel offsets added in the epilogue and where their gradient goes.
+        `bias_grad=False`: the consumer of y produces this layer's bias gradient as a by-product of its own backward (the
+        normalisation behind a decoder convolution, the final 64 -> 1 convolution behind conv_up)."""
         if tproj is not None:
             y, stats = self.k.conv(x, layer.fwd, stride=stride, pad=pad, tproj=tproj), None
         elif proj is not None:
@@ -242,11 +250,11 @@ class TrainKernels:
             dy = tape.pop(y)
             if dy is None:
                 return
-            self._conv_backward(x, dy, layer, stride, pad, need_dx)
+            self._conv_backward(x, dy, layer, stride, pad, need_dx, bias_grad)
             if residual is not None:
                 tape.add(residual, dy)
             if dtproj is not None:
-                ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, dy.c))
+                ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, dy.c), tickets=True)
                 call("sbgm_channel_sums", dy.ptr, dy.plane, self.fmt, dy.n, dy.h * dy.w, dy.c, dtproj.data_ptr(), dtproj.stride(0), None,
                      ws.data_ptr(), _stream())
 
@@ -255,13 +263,13 @@ class TrainKernels:
             return y, pout
         return (y, stats) if gn_stats else y
 
-    def _conv_backward(self, x: Act, dy: Act, layer: ConvLayer, stride: int, pad: int, need_dx: bool) -> None:
+    def _conv_backward(self, x: Act, dy: Act, layer: ConvLayer, stride: int, pad: int, need_dx: bool, bias_grad: bool = True) -> None:
         fmt, st = self.fmt, _stream()
         n, h, w = x.n, x.h, x.w
         cin, cout, kh, kw = layer.cin, layer.cout, layer.kh, layer.kw
-        if layer.bias_name is not None:
+        if layer.bias_name is not None and bias_grad:
             db = self.param_grad(layer.bias_name, (cout,))
-            ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, cout))
+            ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, cout), tickets=True)
             call("sbgm_channel_sums", dy.ptr, dy.plane, fmt, dy.n, dy.h * dy.w, cout, None, 0, db.data_ptr(), ws.data_ptr(), st)
         dw = self.param_grad(layer.name, layer.shape)
         tc = fmt != FMT_F32 and cin % 64 == 0 and cout % 64 == 0
@@ -304,7 +312,8 @@ class TrainKernels:
 
     # -- normalisation ------------------------------------------------------------------------------
     def _norm(self, x: Act, stats: torch.Tensor, mode: int, groups: int, gamma, beta, gamma_name, beta_name, add: Optional[Act],
-              tproj: Optional[torch.Tensor], dtproj: Optional[torch.Tensor], tproj_pre: int, act: int) -> Act:
+              tproj: Optional[torch.Tensor], dtproj: Optional[torch.Tensor], tproj_pre: int, act: int,
+              prev_bias: Optional[str] = None) -> Act:
         fmt = self.fmt
         y = x.like()
         hw = x.h * x.w
@@ -321,13 +330,14 @@ class TrainKernels:
             dadd = self.grad_like(x) if add is not None else None
             dg = self.param_grad(gamma_name, (x.c,)) if gamma_name else None
             db = self.param_grad(beta_name, (x.c,)) if beta_name else None
-            ws = self.scratch("norm_bwd", _lib.query("sbgm_norm_backward_scratch_floats", x.n, x.c))
+            dprev = self.param_grad(prev_bias, (x.c,)) if prev_bias else None      # bias gradient of the convolution that made x
+            ws = self.scratch("norm_bwd", _lib.query("sbgm_norm_backward_scratch_floats", x.n, x.c), tickets=True)
 
             def run(stage: int, sums_all: Optional[torch.Tensor], n_all: int) -> None:
                 call("sbgm_norm_backward", dy.ptr, dy.plane, x.ptr, x.plane, stats.data_ptr(), mode, groups, _ptr(gamma), _ptr(beta),
                      None if add is None else add.ptr, 0 if add is None else add.plane, _ptr(tproj),
                      tproj.stride(0) if tproj is not None else 0, tproj_pre, act, dx.ptr, dx.plane,
-                     None if dadd is None else dadd.ptr, 0 if dadd is None else dadd.plane, _ptr(dg), _ptr(db),
+                     None if dadd is None else dadd.ptr, 0 if dadd is None else dadd.plane, _ptr(dg), _ptr(db), _ptr(dprev),
                      _ptr(dtproj), dtproj.stride(0) if dtproj is not None else 0, fmt, x.n, hw, x.c, ws.data_ptr(), stage,
                      _ptr(sums_all), n_all, _stream())
 
@@ -336,7 +346,7 @@ class TrainKernels:
                 import torch.distributed as dist
                 run(1, None, 0)
                 off = _lib.query("sbgm_norm_backward_sums_offset", x.n, x.c)
-                local = ws[off:off + x.n * x.c * 3]
+                local = ws[off:off + _lib.query("sbgm_norm_backward_sums_floats", x.n, x.c)]
                 world = dist.get_world_size(self.sync_bn)
                 sums_all = torch.empty(world * local.numel(), dtype=torch.float32, device=self.device)
                 dist.all_gather_into_tensor(sums_all, local, group=self.sync_bn)
@@ -379,7 +389,8 @@ class TrainKernels:
         return self._norm(x, stats, mode, c, bn["weight"], bn["bias"], bn["weight_name"], bn["bias_name"], residual, tproj, dtproj, 0, act)
 
     def groupnorm(self, x: Act, gamma, beta, gamma_name, beta_name, groups: int, act: int = ACT_NONE, skip: Optional[Act] = None,
-                  tproj: Optional[torch.Tensor] = None, dtproj: Optional[torch.Tensor] = None, fused=None) -> Act:
+                  tproj: Optional[torch.Tensor] = None, dtproj: Optional[torch.Tensor] = None, fused=None,
+                  prev_bias: Optional[str] = None) -> Act:
         hw = x.h * x.w
         stats = torch.empty((x.n, groups, 2), dtype=torch.float32, device=self.device)
         if fused is not None and (x.c // 8) % groups == 0:
@@ -390,7 +401,7 @@ class TrainKernels:
             part = torch.empty((x.n, chunks, groups, 2), dtype=torch.float32, device=self.device)
             call("sbgm_norm_partials", x.ptr, x.plane, self.fmt, x.n, hw, x.c, groups, part.data_ptr(), _stream())
         call("sbgm_gn_stats_finalize", part.data_ptr(), chunks, pgroups, groups, x.n, hw, x.c, GN_EPS, stats.data_ptr(), _stream())
-        return self._norm(x, stats, 1, groups, gamma, beta, gamma_name, beta_name, skip, tproj, dtproj, 1, act)
+        return self._norm(x, stats, 1, groups, gamma, beta, gamma_name, beta_name, skip, tproj, dtproj, 1, act, prev_bias)
 
     def layernorm(self, x: Act, gamma, beta, gamma_name, beta_name) -> Act:
         y = self.k.layernorm(x, gamma, beta)
@@ -449,7 +460,7 @@ class TrainKernels:
                 return
             s2 = _stream()
             db = self.param_grad(layer.bias_name, (layer.cout,))
-            ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, layer.cout))
+            ws = self.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", dy.n, layer.cout), tickets=True)
             call("sbgm_channel_sums", dy.ptr, dy.plane, fmt, dy.n, dy.h * dy.w, layer.cout, None, 0, db.data_ptr(), ws.data_ptr(), s2)
             dw = self.param_grad(layer.name, layer.shape)
             args = (dy.n, dy.h, dy.w, layer.cout, layer.cin, 2, 2, 2, 0)      # C: input dy-grid (cout channels), output x-grid
@@ -489,8 +500,8 @@ class TrainKernels:
                 return
             dqkv = self.grad_like(qkv)
             ws = self.scratch("attn_bwd", _lib.query("sbgm_attention_backward_scratch_floats", b, s, c, heads))
-            call("sbgm_attention_backward", qkv.ptr, qkv.plane, dy.ptr, dy.plane, dqkv.ptr, dqkv.plane, self.fmt, b, s, c, heads,
-                 ws.data_ptr(), _stream())
+            call("sbgm_attention_backward", qkv.ptr, qkv.plane, y.ptr, y.plane, dy.ptr, dy.plane, dqkv.ptr, dqkv.plane, self.fmt, b, s, c,
+                 heads, ws.data_ptr(), _stream())
             tape.add(qkv, dqkv)
 
         tape.record(backward, qkv, y)
@@ -690,7 +701,7 @@ class TrainEngine:
             if df is None:
                 return
             d0 = col(dtproj, "enc0")
-            ws = tk.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", n, 64))
+            ws = tk.scratch("chansum", _lib.query("sbgm_channel_sums_scratch_floats", n, 64), tickets=True)
             call("sbgm_channel_sums", df.ptr, df.plane, fmt, n, f1.h * f1.w, 64, d0.data_ptr(), d0.stride(0), None, ws.data_ptr(), _stream())
             dw = self._param_grad("encoder.conv1.weight", (64, self.cin, 8, 8))
             ws2 = tk.scratch("stem", _lib.query("sbgm_stem_wgrad_workspace_floats", self.cin))
@@ -723,17 +734,18 @@ class TrainEngine:
         rev = list(reversed(fmaps))
         out = rev[0]
         for i, blk in enumerate(self.dec_blocks):
+            # the two convolutions' bias gradients come out of the normalisation backward behind them (closed form)
             if self.spec.use_resize_conv:
-                a, st1 = tk.conv(tk.upsample2x(out), blk["conv_up"], pad=1, gn_stats=True)
+                a, st1 = tk.conv(tk.upsample2x(out), blk["conv_up"], pad=1, gn_stats=True, bias_grad=False)
+                a = tk.groupnorm(a, *blk["n1"], groups=blk["g1"], fused=st1, prev_bias=blk["conv_up"].bias_name)
             else:
-                a, st1 = tk.conv_transpose2x(out, blk["conv_up"]), None
-            a = tk.groupnorm(a, *blk["n1"], groups=blk["g1"], fused=st1)
-            b, st2 = tk.conv(a, blk["conv"], pad=1, gn_stats=True)
+                a = tk.groupnorm(tk.conv_transpose2x(out, blk["conv_up"]), *blk["n1"], groups=blk["g1"])
+            b, st2 = tk.conv(a, blk["conv"], pad=1, gn_stats=True, bias_grad=False)
             skip = rev[i + 1]
             if (skip.n, skip.h, skip.w, skip.c) != (b.n, b.h, b.w, b.c):
                 raise AssertionError(f"prev_fmap shape {(skip.n, skip.c, skip.h, skip.w)} must match output shape {(b.n, b.c, b.h, b.w)}")
             out = tk.groupnorm(b, *blk["n2"], groups=blk["g2"], act=self.act, skip=skip, tproj=col(tproj, blk["name"]),
-                               dtproj=col(dtproj, blk["name"]), fused=st2)
+                               dtproj=col(dtproj, blk["name"]), fused=st2, prev_bias=blk["conv"].bias_name)
             if blk["attn"] is not None:
                 out = _attention_block(tk, blk["attn"], out)
         smp = getattr(self, "_sampler", None)
@@ -748,11 +760,11 @@ class TrainEngine:
                  res.data_ptr(), a.n, a.h, a.w, a.c, 1, _stream())
         elif fmt != FMT_F32 and tk.k._c64_ok(up, self.final_up.fwd, 1, 1):
             # the 64 -> 1 convolution rides in conv_up's epilogue (projection); conv_up's output is kept for the backward
-            a, pr = tk.conv(up, self.final_up, pad=1, proj=self.final_w[0])
+            a, pr = tk.conv(up, self.final_up, pad=1, proj=self.final_w[0], bias_grad=not self._final_bias_fused())
             call("sbgm_final_gather", pr.data_ptr(), self.final_b.data_ptr(), *iv, res.data_ptr(), a.n, a.h, a.w,
                  _stream())
         else:
-            a = tk.conv(up, self.final_up, pad=1)
+            a = tk.conv(up, self.final_up, pad=1, bias_grad=not self._final_bias_fused())
             call("sbgm_final_conv", a.ptr, a.plane, fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), *iv,
                  res.data_ptr(), a.n, a.h, a.w, a.c, 1, _stream())
         if smp is not None:                    # a sampler step: nothing will run backward -- drop the tape and its activations
@@ -761,6 +773,12 @@ class TrainEngine:
             return res
         self._final = (a, inv_std)
         return res
+
+    def _final_bias_fused(self) -> bool:
+        """final_layer.conv_up's bias gradient is a by-product of the final convolution's backward (sbgm_final_conv_backward's
+        dbias_up) when conv_up is the resize-convolution and its channel-vector count is a power of two."""
+        vecs = self.final_w.shape[2] // 8
+        return self.spec.use_resize_conv and self.final_w.shape[2] % 8 == 0 and vecs <= 32 and vecs & (vecs - 1) == 0
 
     # -- backward ----------------------------------------------------------------------------------------
     def backward(self, dscore: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -772,9 +790,10 @@ class TrainEngine:
         da = tk.grad_like(a)
         dwf = self._param_grad(self.final_names[0], (1, a.c, 3, 3))
         dbf = self._param_grad(self.final_names[1], (1,))
+        dbu = self._param_grad(self.final_up.bias_name, (a.c,)) if self._final_bias_fused() else None
         ws = tk.scratch("final", _lib.query("sbgm_final_conv_backward_scratch_floats", a.c))
         call("sbgm_final_conv_backward", dscore.data_ptr(), _ptr(inv_std), a.ptr, a.plane, fmt, self.final_w.data_ptr(), da.ptr, da.plane,
-             dwf.data_ptr(), dbf.data_ptr(), a.n, a.h, a.w, a.c, ws.data_ptr(), _stream())
+             dwf.data_ptr(), dbf.data_ptr(), _ptr(dbu), a.n, a.h, a.w, a.c, ws.data_ptr(), _stream())
         tape.add(a, da)
         sync = self.grad_sync
         if sync is not None:

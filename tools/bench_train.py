@@ -29,6 +29,8 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=64, help="global batch (strong scaling) or per-GPU batch with --weak")
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--weak", action="store_true")
+    ap.add_argument("--optimizer", default="one-launch", choices=["one-launch", "torch"],
+                    help="sbgm_danra_b200.optim.Adam (torch.optim.Adam with a single-kernel step) or torch's own foreach Adam")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -45,7 +47,8 @@ def main() -> None:
     b = synth_batch(batch=b_local, size=args.size, n_lr=2, geo=True, seasons=True, seed=1234 + rank)
     c = lambda v: None if v is None else v.to(dev)
     x, y, cond, lsm, topo, sdf = c(b.x), c(b.y), c(b.cond_img), c(b.lsm_cond), c(b.topo_cond), c(b.sdf_cond)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    from sbgm_danra_b200 import optim as sbgm_optim
+    opt = (torch.optim if args.optimizer == "torch" else sbgm_optim).Adam(net.parameters(), lr=1e-4)
     sync = None
     if world > 1:
         parallel.broadcast_parameters(net)
@@ -89,7 +92,7 @@ def main() -> None:
         gb = b_local * world
         scale = (args.size / 128) ** 2
         out = {"metric": "DSM training samples/sec", "value": gb / (ms.item() * 1e-3), "unit": "samples/s", "n_gpus": world,
-               "ms_per_step": ms.item(), "global_batch": gb, "per_gpu_batch": b_local, "img_size": args.size, "precision": args.precision,
+               "ms_per_step": ms.item(), "global_batch": gb, "per_gpu_batch": b_local, "img_size": args.size, "precision": args.precision, "optimizer": args.optimizer,
                "scaling": "weak" if args.weak else "strong",
                "algorithmic_tflops": 3 * FWD_FLOP_128_CIN7 * scale * gb / (ms.item() * 1e-3) / 1e12,
                "rank0_ms": {"loss_fn_forward": split[0] / args.steps, "backward": split[1] / args.steps, "adam": split[2] / args.steps},

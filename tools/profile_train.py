@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--list", default="", help="comma-separated kernel-name substrings: also print every matching launch of the last step, in order")
     a = ap.parse_args()
     from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
     from sbgm_danra_b200 import score_sampling
@@ -31,7 +32,8 @@ def main():
     b = synth_batch(batch=a.batch, size=a.size, n_lr=2, geo=True, seasons=True, seed=1234)
     c = lambda v: None if v is None else v.to(dev)
     x, y, cond, lsm, topo, sdf = c(b.x), c(b.y), c(b.cond_img), c(b.lsm_cond), c(b.topo_cond), c(b.sdf_cond)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    from sbgm_danra_b200 import optim as sbgm_optim
+    opt = sbgm_optim.Adam(net.parameters(), lr=1e-4)
     score_sampling.manual_seed(5)
 
     def step():
@@ -57,6 +59,14 @@ def main():
     print(f"kernel time {total / a.steps / 1e3:.3f} ms per step over {sum(v[1] for v in agg.values()) // a.steps} launches ({a.precision}, batch {a.batch})")
     for name, (us, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:a.top]:
         print(f"{us / a.steps:9.1f} us {100 * us / total:5.1f}%  x{cnt // a.steps:4d}  {name}")
+    if a.list:
+        keys = [k for k in a.list.split(",") if k]
+        evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda ev: ev.time_range.start)
+        evs = evs[len(evs) - len(evs) // a.steps:]
+        for i, ev in enumerate(evs):
+            if any(k in ev.name for k in keys):
+                dur = ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+                print(f"  #{i:4d} {dur:8.1f} us  {ev.name.split('(')[0][:70]}")
 
 
 if __name__ == "__main__":
