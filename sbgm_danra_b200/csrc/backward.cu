@@ -159,26 +159,30 @@ __global__ void norm_apply_kernel(const NormArgs a, void* __restrict__ y, size_t
 }
 
 // ---- normalisation backward ---------------------------------------------------------------------
-// Two launches per layer.  Launch 1 (norm_bwd_sums_kernel) is the whole reduction tree:
-//   * every block: per (n, chunk) per-channel sums of  dY,  dU = dY * act'(u),  dU * xhat,  xhat   -> partials[n][chunk][c][4]
-//   * the LAST block of a sample to finish (integer ticket, no floating-point atomics: the order of every sum is fixed)
-//     adds the chunks -> sums[n][c][4], writes dtproj[n][c] and, for GroupNorm, the sample's projection coefficients
-//       A = sum(gamma * dU) / cnt,  B = sum(gamma * dU * xhat) / cnt      (coef[stat index][2])
-//   * the LAST sample to finish adds over the samples: dgamma / dbeta, BatchNorm's per-channel A / B, and -- closed form, no
-//     pass over dx -- the bias gradient of the convolution in front of the norm:
-//       sum_p dx = rstd * (gamma * sum dU - hw * A - B * sum xhat)
+// Two launches per layer.  The layers are small (a few MB each, 28 of them per step), so both are built for LATENCY:
+// Launch 1 (norm_bwd_sums_kernel): a block owns ALL the pixels of one sample for a column of `vpb` channel vectors
+//   (threads = [pixel lanes][vpb]), so its block reduction already yields the finished per-sample sums
+//     sums[n][ch][4] = sum over the pixels of  dY,  dU = dY * act'(u),  dU * xhat,  xhat
+//   -- no per-chunk partials, no second pass over them.  The block also writes dtproj[n][ch] and, for GroupNorm (a column
+//   always holds whole groups), the sample's projection coefficients
+//     A = sum(gamma * dU) / cnt,  B = sum(gamma * dU * xhat) / cnt      (coef[stat index][2]).
+//   The LAST sample of a column to finish (integer ticket per column; no floating-point atomics, every sum has a fixed
+//   order) adds its channels over the samples: dgamma / dbeta, BatchNorm's per-channel A / B, and -- closed form, no pass
+//   over dx -- the bias gradient of the convolution in front of the norm:
+//     sum_p dx = rstd * (gamma * sum dU - hw * A - B * sum xhat)
 // Launch 2 (norm_bwd_apply_kernel): dx = rstd * (gamma * dU - A - xhat * B);  dadd = dU.
 // Tickets live in the first kNormTicketWords words of the scratch buffer: zero before the first use, left zero by every launch.
 constexpr int kNormTicketWords = 4096;
 
 struct NormBwdTail {
-  unsigned int* tickets;      // [0] = samples finished, [1 + n] = chunk blocks of sample n finished
+  unsigned int* tickets;      // [column]: samples of the column finished
   float* sums;                // [n][c][4]
   const float* sums_all;      // BatchNorm over the global batch (synchronised): [n_all][c][4]; else == sums
   float* coef;
   float* dgamma; float* dbeta; float* dbias_prev;
   float* dtproj; int dtproj_stride;
   int n, n_all, fixed_stats, with_coef;
+  int vpb, pl, shuffle;       // block geometry: vectors per column, pixel lanes, warp-butterfly reduction (vpb a power of two <= 32)
   float inv_cnt;
 };
 
@@ -198,21 +202,21 @@ __device__ __forceinline__ bool last_ticket(unsigned int* ticket, unsigned int t
   return last;
 }
 
-// Sums over the samples, by ONE block (the tail of the reduction tree): dgamma, dbeta, BatchNorm's coefficients, the bias
-// gradient in front.  Latency-bound (n x c float4 from L2), so every thread of the block takes a slice of the samples of one
-// channel with eight loads in flight, and the slices are added in a fixed order through shared memory `sm`
-// (>= max(c, blockDim.x) * 4 floats).
-__device__ void norm_bwd_tail_global(const NormArgs& a, const NormBwdTail& t, float* sm) {
+// Sums over the samples for the channels [ch_begin, ch_begin + ch_count), by one block: dgamma, dbeta, BatchNorm's
+// coefficients, the bias gradient in front.  Latency-bound (n x channels float4 from L2): every thread takes a slice of the
+// samples of one channel with eight loads in flight; the slices are added in a fixed order through `sm` (>= 4 * blockDim.x floats).
+__device__ void norm_bwd_tail_cols(const NormArgs& a, const NormBwdTail& t, float* sm, int ch_begin, int ch_count) {
   const int c = a.c, nt = blockDim.x;
-  const int cw = min(c, nt), parts = nt / cw;          // threads = [parts][cw]
+  const int cw = min(ch_count, nt), parts = nt / cw;          // threads = [parts][cw]
   const int part = threadIdx.x / cw, ch0 = threadIdx.x % cw;
   const bool bn = a.n_stride == 0;
   const bool gathered = bn && !t.fixed_stats && t.sums_all != t.sums;
   const float4* sums4 = reinterpret_cast<const float4*>(t.sums);
-  for (int base = 0; base < c; base += cw) {           // (one pass unless c > blockDim.x)
-    const int ch = base + ch0;
+  for (int base = 0; base < ch_count; base += cw) {           // (one pass unless the column is wider than the block)
+    const int ch = ch_begin + base + ch0;
+    const bool live = part < parts && base + ch0 < ch_count;
     float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, g1 = 0.0f, g2 = 0.0f;
-    if (part < parts && ch < c) {
+    if (live) {
       const float ga = a.gamma ? a.gamma[ch] : 1.0f;
       if (bn) {
 #pragma unroll 8
@@ -242,10 +246,10 @@ __device__ void norm_bwd_tail_global(const NormArgs& a, const NormBwdTail& t, fl
       }
     }
     __syncthreads();
-    if (part < parts && ch < c) *reinterpret_cast<float4*>(sm + (static_cast<size_t>(part) * cw + ch0) * 4) = make_float4(s1, s2, s3, g1);
+    if (live) *reinterpret_cast<float4*>(sm + (static_cast<size_t>(part) * cw + ch0) * 4) = make_float4(s1, s2, s3, g1);
     __syncthreads();
     float g2s = g2;                                     // the gathered second moment travels through a second round
-    if (part == 0 && ch < c) {
+    if (live && part == 0) {
       for (int q = 1; q < parts; ++q) {
         const float4 o = *reinterpret_cast<const float4*>(sm + (static_cast<size_t>(q) * cw + ch0) * 4);
         s1 += o.x; s2 += o.y; s3 += o.z; g1 += o.w;
@@ -253,11 +257,11 @@ __device__ void norm_bwd_tail_global(const NormArgs& a, const NormBwdTail& t, fl
     }
     if (gathered) {
       __syncthreads();
-      if (part < parts && ch < c) sm[static_cast<size_t>(part) * cw + ch0] = g2;
+      if (live) sm[static_cast<size_t>(part) * cw + ch0] = g2;
       __syncthreads();
-      if (part == 0 && ch < c) for (int q = 1; q < parts; ++q) g2s += sm[static_cast<size_t>(q) * cw + ch0];
+      if (live && part == 0) for (int q = 1; q < parts; ++q) g2s += sm[static_cast<size_t>(q) * cw + ch0];
     }
-    if (part == 0 && ch < c) {
+    if (live && part == 0) {
       const float ga = a.gamma ? a.gamma[ch] : 1.0f;
       if (t.dgamma) { t.dgamma[ch] = s2; t.dbeta[ch] = s1; }
       if (bn) {                         // one statistics group per channel, spanning the (global) batch
@@ -277,30 +281,29 @@ __device__ void norm_bwd_tail_global(const NormArgs& a, const NormBwdTail& t, fl
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 2) norm_bwd_sums_kernel(const NormArgs a, const void* __restrict__ dy, size_t dy_plane, float* __restrict__ partials, int chunks,
-                                     const NormBwdTail t) {
+__global__ void __launch_bounds__(256, 2) norm_bwd_sums_kernel(const NormArgs a, const void* __restrict__ dy, size_t dy_plane, const NormBwdTail t) {
   pdl_grid_sync();
-  extern __shared__ float red[];  // [lanes][c][4]
-  const int n = blockIdx.y, chunk = blockIdx.x;
-  const int c = a.c, vecs = c >> 3, lanes = blockDim.x / vecs;
-  const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
-  const int per_chunk = (a.hw + chunks - 1) / chunks;
-  const int p_begin = chunk * per_chunk, p_end = min(a.hw, p_begin + per_chunk);
+  extern __shared__ float red[];  // [rows][vpb * 32] block reduction, then 4 * blockDim.x floats for the column tail
+  const int n = blockIdx.y, c = a.c;
+  const int vpb = t.vpb, pl = t.pl;
+  const int vl = threadIdx.x % vpb, lane = threadIdx.x / vpb;
+  const int vec = blockIdx.x * vpb + vl;
+  const int width = vpb * 32;                        // floats per reduction row: [vpb][8 channels][4 sums]
+  const bool active = lane < pl;
   float s0[8], s1[8], s2[8], s3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = s3[j] = 0.0f;
-  if (lane < lanes) {
+  if (active) {
     float mean[8], rstd[8], ga[8], sh[8], post[8];
     norm_coefs(a, n, vec * 8, mean, rstd, ga, sh, post);
-    // the layers are small (a few MB): the block is latency-bound, so the loads of kUn pixels are issued before any is used
-    // (kUn = 4 needs 254 registers: one block per SM)
+    // latency-bound: the loads of kUn pixels are issued before any is used (kUn = 4 needs 254 registers: one block per SM)
     constexpr int kUn = 2;
-    for (int p = p_begin + lane; p < p_end; p += lanes * kUn) {
+    for (int p = lane; p < a.hw; p += pl * kUn) {
       float v[kUn][8], g[kUn][8], r[kUn][8];
 #pragma unroll
       for (int k = 0; k < kUn; ++k) {
-        if (p + k * lanes < p_end) {
-          const size_t idx = (static_cast<size_t>(n) * a.hw + p + k * lanes) * c + vec * 8;
+        if (p + k * pl < a.hw) {
+          const size_t idx = (static_cast<size_t>(n) * a.hw + p + k * pl) * c + vec * 8;
           Act<FMT>::load8(a.x, a.x_plane, idx, v[k]);
           Act<FMT>::load8(dy, dy_plane, idx, g[k]);
           if (a.add) Act<FMT>::load8(a.add, a.add_plane, idx, r[k]);
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_sums_kernel(const NormArgs a,
       }
 #pragma unroll
       for (int k = 0; k < kUn; ++k) {
-        if (p + k * lanes >= p_end) break;
+        if (p + k * pl >= a.hw) break;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (v[k][j] - mean[j]) * rstd[j];
@@ -322,52 +325,70 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_sums_kernel(const NormArgs a,
         }
       }
     }
+  }
+  // ---- block reduction over the pixel lanes -> row 0 of `red` = the sample's sums for this column ----
+  int rows;
+  if (t.shuffle) {                  // threads `vpb` apart in a warp share a channel vector: butterfly, then one row per warp
+    for (int off = vpb; off < 32; off <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(red + (static_cast<size_t>(lane) * c + vec * 8 + j) * 4) = make_float4(s0[j], s1[j], s2[j], s3[j]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < c * 4; i += blockDim.x) {
-    float acc = 0.0f;
-    for (int l = 0; l < lanes; ++l) acc += red[static_cast<size_t>(l) * c * 4 + i];
-    partials[(static_cast<size_t>(n) * chunks + chunk) * c * 4 + i] = acc;
-  }
-  // ---- last block of this sample: sums over the chunks, dtproj, GroupNorm coefficients ----
-  if (!last_ticket(t.tickets + 1 + n, chunks)) return;
-  float* sums_n = t.sums + static_cast<size_t>(n) * c * 4;
-  for (int i = threadIdx.x; i < c * 4; i += blockDim.x) {
-    float s = 0.0f;
-#pragma unroll 8
-    for (int k = 0; k < chunks; ++k) s += __ldcg(partials + (static_cast<size_t>(n) * chunks + k) * c * 4 + i);
-    sums_n[i] = s;
-    red[i] = s;
-    const int ch = i >> 2, which = i & 3;
-    if (t.dtproj && which == (a.tproj_pre ? 1 : 0)) t.dtproj[static_cast<size_t>(n) * t.dtproj_stride + ch] = s;
-  }
-  __syncthreads();
-  if (t.with_coef && a.n_stride != 0) {
-    for (int g = threadIdx.x; g < a.n_stride; g += blockDim.x) {
-      float ca = 0.0f, cb = 0.0f;
-      for (int j = 0; j < a.cpg; ++j) {
-        const int ch = g * a.cpg + j;
-        const float ga = a.gamma ? a.gamma[ch] : 1.0f;
-        ca = fmaf(ga, red[ch * 4 + 1], ca);
-        cb = fmaf(ga, red[ch * 4 + 2], cb);
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], off);
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+        s3[j] += __shfl_xor_sync(0xffffffffu, s3[j], off);
       }
-      t.coef[2 * (static_cast<size_t>(n) * a.n_stride + g)] = ca * t.inv_cnt;
-      t.coef[2 * (static_cast<size_t>(n) * a.n_stride + g) + 1] = cb * t.inv_cnt;
+    }
+    rows = blockDim.x >> 5;
+    if ((threadIdx.x & 31) < vpb) {
+      float* o = red + static_cast<size_t>(threadIdx.x >> 5) * width + vl * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(o + j * 4) = make_float4(s0[j], s1[j], s2[j], s3[j]);
+    }
+  } else {                          // one row per pixel lane
+    rows = pl;
+    if (active) {
+      float* o = red + static_cast<size_t>(lane) * width + vl * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(o + j * 4) = make_float4(s0[j], s1[j], s2[j], s3[j]);
     }
   }
-  // ---- last sample: sums over the samples ----
-  if (!last_ticket(t.tickets, gridDim.y)) return;
-  if (t.with_coef) norm_bwd_tail_global(a, t, red);
+  __syncthreads();
+  const int ch_begin = blockIdx.x * vpb * 8, ch_count = vpb * 8;
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    float s = red[i];
+    for (int r = 1; r < rows; ++r) s += red[static_cast<size_t>(r) * width + i];
+    red[i] = s;                     // (row 0, column i: read and written by this thread only)
+    const int ch = ch_begin + (i >> 2), which = i & 3;
+    t.sums[(static_cast<size_t>(n) * c + ch) * 4 + which] = s;
+    if (t.dtproj && which == (a.tproj_pre ? 1 : 0)) t.dtproj[static_cast<size_t>(n) * t.dtproj_stride + ch] = s;
+  }
+  if (!t.with_coef) return;         // synchronised BatchNorm, stage 1: the sums are gathered over the ranks first
+  __syncthreads();
+  if (a.n_stride != 0) {            // GroupNorm: the column holds whole groups (host-checked)
+    const int g_begin = ch_begin / a.cpg, g_count = ch_count / a.cpg;
+    for (int gl = threadIdx.x; gl < g_count; gl += blockDim.x) {
+      float ca = 0.0f, cb = 0.0f;
+      for (int j = 0; j < a.cpg; ++j) {
+        const int ch = (g_begin + gl) * a.cpg + j;
+        const float ga = a.gamma ? a.gamma[ch] : 1.0f;
+        ca = fmaf(ga, red[(ch - ch_begin) * 4 + 1], ca);
+        cb = fmaf(ga, red[(ch - ch_begin) * 4 + 2], cb);
+      }
+      const size_t si = static_cast<size_t>(n) * a.n_stride + g_begin + gl;
+      t.coef[2 * si] = ca * t.inv_cnt;
+      t.coef[2 * si + 1] = cb * t.inv_cnt;
+    }
+  }
+  // ---- last sample of this column: sums over the samples ----
+  if (!last_ticket(t.tickets + blockIdx.x, gridDim.y)) return;
+  norm_bwd_tail_cols(a, t, red + width, ch_begin, ch_count);
 }
 
-// synchronised BatchNorm, stage 2: the per-channel tail alone (one block), over the gathered sums of every rank
+// synchronised BatchNorm, stage 2: the per-channel tail alone (a block per column), over the gathered sums of every rank
 __global__ void norm_bwd_tail_kernel(const NormArgs a, const NormBwdTail t) {
   pdl_grid_sync();
   extern __shared__ float red[];
-  norm_bwd_tail_global(a, t, red);
+  norm_bwd_tail_cols(a, t, red, blockIdx.x * t.vpb * 8, t.vpb * 8);
 }
 
 // Stage 3: dx = rstd * (gamma * dU - A - xhat * B);  dadd = dU.
@@ -602,6 +623,37 @@ __global__ void chansum_finish_kernel(const float* __restrict__ partials, int n,
   if (out_total && lane == 0) out_total[ch] = tot;
 }
 
+// Total only, few pixels (bias gradients of the attention blocks' Linear layers, x = [tokens][c], a few MB): a block owns ONE
+// 8-channel column and all the pixels, so there is no second reduction level at all (no partials, no ticket, no tail
+// through L2): eight loads in flight per thread, warp butterfly, one shared-memory step over the warps.
+template <int FMT>
+__global__ void chansum_cols_kernel(const void* __restrict__ x, size_t plane, int pixels, int c, float* __restrict__ out_total) {
+  pdl_grid_sync();
+  __shared__ float red[32][8];
+  const int vec = blockIdx.x;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 8
+  for (int p = threadIdx.x; p < pixels; p += blockDim.x) {
+    float v[8];
+    Act<FMT>::load8(x, plane, static_cast<size_t>(p) * c + vec * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = warp_sum(s[j]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][j] = s[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float acc = 0.0f;
+    for (int w = 0; w < nwarps; ++w) acc += red[w][threadIdx.x];
+    out_total[vec * 8 + threadIdx.x] = acc;
+  }
+}
+
 // Total only (bias gradients of the Linear layers, x = [n * hw][c]): ONE launch.  The pixels of all samples are dealt to up to
 // kChansumBlocks blocks; the last block to finish (integer ticket; summation order fixed) adds the per-block rows.
 constexpr int kChansumBlocks = 296;
@@ -720,6 +772,7 @@ __global__ void time_embed_bwd_weight_kernel(const float* __restrict__ dout, int
   const float* e = e_ws + static_cast<size_t>(pset[col]) * rows * te;
   for (int k = threadIdx.x; k < te; k += blockDim.x) {
     float acc = 0.0f;
+#pragma unroll 8
     for (int r = 0; r < rows; ++r) acc = fmaf(dout[static_cast<size_t>(r) * c_total + col], silu(e[static_cast<size_t>(r) * te + k]), acc);
     dW[static_cast<size_t>(col) * te + k] = acc;
   }
@@ -730,21 +783,27 @@ __global__ void time_embed_bwd_weight_kernel(const float* __restrict__ dout, int
   }
 }
 // de0[row][k] = silu'(e0[row][k]) * sum_{col in set 0} dout[row][col] * W[col][k]
-// block = (te threads over k) x 4 column groups; the groups' partial sums meet in shared memory
-__global__ void time_embed_bwd_input_kernel(const float* __restrict__ dout, int c_total, const float* __restrict__ e_ws, int te,
-                                            const int32_t* __restrict__ pset, const float* __restrict__ pw, float* __restrict__ de0) {
+// A 64 x 1024 x 256 product (33 MFLOP) that is pure latency: block = (row, 16 values of k) x 16 column groups, so a thread's
+// chain is c_total / 16 columns with eight loads in flight; the groups' partial sums meet in shared memory in a fixed order.
+__global__ void __launch_bounds__(256) time_embed_bwd_input_kernel(const float* __restrict__ dout, int c_total, const float* __restrict__ e_ws, int te,
+                                                                  const int32_t* __restrict__ pset, const float* __restrict__ pw, float* __restrict__ de0) {
   pdl_grid_sync();
-  extern __shared__ float part[];     // [4][te]
-  const int row = blockIdx.x, k = threadIdx.x, grp = threadIdx.y;
+  __shared__ float part[16][17];
+  const int row = blockIdx.x, k = blockIdx.y * 16 + (threadIdx.x & 15), grp = threadIdx.x >> 4;
   float acc = 0.0f;
   if (k < te) {
-    for (int col = grp; col < c_total; col += 4)
-      if (pset[col] == 0) acc = fmaf(dout[static_cast<size_t>(row) * c_total + col], __ldg(pw + static_cast<size_t>(col) * te + k), acc);
-    part[grp * te + k] = acc;
+#pragma unroll 8
+    for (int col = grp; col < c_total; col += 16) {
+      const float g = pset[col] == 0 ? dout[static_cast<size_t>(row) * c_total + col] : 0.0f;
+      acc = fmaf(g, __ldg(pw + static_cast<size_t>(col) * te + k), acc);
+    }
   }
+  part[grp][threadIdx.x & 15] = acc;
   __syncthreads();
   if (grp == 0 && k < te) {
-    const float s = (part[k] + part[te + k]) + (part[2 * te + k] + part[3 * te + k]);
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += part[q][threadIdx.x];
     de0[static_cast<size_t>(row) * te + k] = s * act_grad(e_ws[static_cast<size_t>(row) * te + k], SBGM_ACT_SILU);
   }
 }
@@ -828,11 +887,33 @@ int sbgm_norm_apply(const void* x, size_t x_plane, const float* stats, int per_s
   return check_launch("norm_apply");
 }
 
-size_t sbgm_norm_backward_sums_offset(int n, int c) { return kNormTicketWords + static_cast<size_t>(n) * kNormChunks * c * 4; }
+size_t sbgm_norm_backward_sums_offset(int n, int c) { (void)n; (void)c; return kNormTicketWords; }
 size_t sbgm_norm_backward_sums_floats(int n, int c) { return static_cast<size_t>(n) * c * 4; }
 
 size_t sbgm_norm_backward_scratch_floats(int n, int c) {
-  return kNormTicketWords + static_cast<size_t>(n) * kNormChunks * c * 4 + static_cast<size_t>(n) * c * 4 + static_cast<size_t>(n) * c * 2 + 64;
+  return kNormTicketWords + static_cast<size_t>(n) * c * 4 + static_cast<size_t>(n) * c * 2 + 64;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Block geometry of norm_bwd_sums_kernel: `vpb` channel vectors per column (a divisor of c / 8) and `pl` pixel lanes.
+static void norm_bwd_geometry(int hw, int c, int per_sample_stats, int groups, int* vpb, int* pl, int* shuffle) {
+  const int vecs = c / 8, cpg = c / groups;
+  bool whole = !is_pow2(vecs);                       // odd channel counts: one column with every vector, no butterfly
+  if (per_sample_stats == 1 && !(cpg % 8 == 0 && is_pow2(cpg / 8)) && 8 % cpg != 0) whole = true;   // groups straddling vectors
+  if (whole) {
+    *vpb = vecs;
+    *pl = max(1, 256 / vecs);
+  } else {
+    int lanes = 32;                                  // enough lanes for the pixels, at most 128 (two vectors = one 32-byte sector)
+    while (lanes < 128 && lanes < hw) lanes <<= 1;
+    int v = max(256 / lanes, 1);
+    if (per_sample_stats == 1 && cpg > 8) v = max(v, cpg / 8);       // a column holds whole groups
+    v = min(v, vecs);
+    *vpb = v;
+    *pl = max(1, 256 / v);
+  }
+  *shuffle = is_pow2(*vpb) && *vpb <= 32 && is_pow2(*pl);
 }
 
 int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_plane, const float* stats, int per_sample_stats,
@@ -844,17 +925,13 @@ int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_
   SBGM_REQUIRE(stage >= 0 && stage <= 2, "norm_backward: stage %d", stage);
   SBGM_REQUIRE(stage == 0 || per_sample_stats == 0, "norm_backward: stages 1 / 2 (gathered sums) are for batch statistics only");
   SBGM_REQUIRE(sums_all == nullptr || (stage == 2 && n_all >= n), "norm_backward: gathered sums belong to stage 2");
-  SBGM_REQUIRE(n + 1 <= kNormTicketWords, "norm_backward: batch %d too large", n);
   const int vecs = c / 8;
   SBGM_REQUIRE(vecs <= 256, "norm_backward: c too large");
   const NormArgs a = make_norm_args(x, x_plane, stats, per_sample_stats, groups, gamma, beta, add, add_plane, tproj, tproj_stride,
                                     tproj_pre_act, act, hw, c);
-  float* partials = scratch + kNormTicketWords;
-  float* sums = partials + static_cast<size_t>(n) * kNormChunks * c * 4;
+  float* sums = scratch + kNormTicketWords;
   float* coef = sums + static_cast<size_t>(n) * c * 4;
   cudaStream_t st = as_stream(stream);
-  const int lanes = 256 / vecs;
-  const size_t smem1 = static_cast<size_t>(lanes) * c * 4 * sizeof(float);
   if (sums_all == nullptr) { sums_all = sums; n_all = n; }
   const double cnt = per_sample_stats == 1 ? static_cast<double>(hw) * (c / groups) : static_cast<double>(n_all) * hw;
   NormBwdTail t;
@@ -862,12 +939,16 @@ int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_
   t.sums = sums; t.sums_all = sums_all; t.coef = coef; t.dgamma = dgamma; t.dbeta = dbeta; t.dbias_prev = dbias_prev;
   t.dtproj = dtproj; t.dtproj_stride = dtproj_stride; t.n = n; t.n_all = n_all; t.fixed_stats = per_sample_stats == 2;
   t.with_coef = stage == 0; t.inv_cnt = static_cast<float>(1.0 / cnt);
+  norm_bwd_geometry(hw, c, per_sample_stats, groups, &t.vpb, &t.pl, &t.shuffle);
+  const int columns = vecs / t.vpb;
+  SBGM_REQUIRE(columns <= kNormTicketWords, "norm_backward: too many channel columns");
+  const int threads = max(32, min(256, ((t.pl * t.vpb + 31) / 32) * 32));
+  const int rows = t.shuffle ? threads / 32 : t.pl;
+  const size_t smem1 = (static_cast<size_t>(rows) * t.vpb * 32 + 4 * 256) * sizeof(float);
   int slots = 148 * 8;
   SBGM_DISPATCH_FMT(fmt, (slots = resident_blocks(reinterpret_cast<const void*>(norm_bwd_apply_kernel<FMT>), 256, 0)));
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), slots / max(n, 1)));
-  // enough pixels per thread to amortise the per-block prologue: ~8 per lane
-  const int chunks = max(1, min(kNormChunks, hw / (lanes * 8)));
-  dim3 g1(chunks, n), g3(per_n_blocks, n);
+  dim3 g1(columns, n), g3(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
     if (stage != 2) {
       auto k1 = norm_bwd_sums_kernel<FMT>;
@@ -875,9 +956,9 @@ int sbgm_norm_backward(const void* dy, size_t dy_plane, const void* x, size_t x_
         set_error("norm_backward: cannot reserve %zu bytes of shared memory", smem1);
         return 1;
       }
-      launch_k((k1), g1, 256, smem1, st, a, dy, dy_plane, partials, chunks, t);
+      launch_k((k1), g1, threads, smem1, st, a, dy, dy_plane, t);
     }
-    if (stage == 2) launch_k((norm_bwd_tail_kernel), 1, 256, static_cast<size_t>(max(c, 256)) * 4 * sizeof(float), st, a, t);
+    if (stage == 2) launch_k((norm_bwd_tail_kernel), columns, 256, static_cast<size_t>(4 * 256) * sizeof(float), st, a, t);
     if (stage != 1) launch_k((norm_bwd_apply_kernel<FMT>), g3, 256, 0, st, a, dy, dy_plane, coef, dx, dx_plane, dadd, dadd_plane);
   });
   return check_launch("norm_backward");
@@ -930,6 +1011,11 @@ int sbgm_channel_sums(const void* x, size_t x_plane, int fmt, int n, int hw, int
     SBGM_REQUIRE(out_total != nullptr, "channel_sums: no output");
     const long long pixels = static_cast<long long>(n) * hw;
     SBGM_REQUIRE(pixels < (1ll << 31), "channel_sums: tensor too large");
+    if (pixels <= 32768) {        // one block per channel vector, <= 32 pixels per thread
+      const int threads = pixels >= 8192 ? 1024 : (pixels >= 2048 ? 512 : 256);
+      SBGM_DISPATCH_FMT(fmt, (launch_k((chansum_cols_kernel<FMT>), vecs, threads, 0, st, x, x_plane, static_cast<int>(pixels), c, out_total)));
+      return check_launch("channel_sums");
+    }
     // the main pass shrinks with the block count, the last block's tail (c x blocks partials through one SM) grows with it:
     // both are latency-bound and balance near blocks = sqrt(pixels)
     const int blocks = max(1, min(min(kChansumBlocks, ceil_div(pixels, static_cast<long long>(lanes) * 8)),
@@ -969,8 +1055,7 @@ int sbgm_time_embed_backward(const float* dout, const float* t, const int64_t* y
   launch_k((time_embed_bwd_embed_kernel), rows, 256, 0, st, t, y, fourier_w, n_sets, te, label_emb, e_ws);
   launch_k((time_embed_bwd_weight_kernel), c_total, 256, 0, st, dout, c_total, e_ws, rows, te, proj_set, d_proj_w, d_proj_b);
   if (d_label_emb != nullptr && y != nullptr) {
-    SBGM_REQUIRE(te <= 256, "time_embed_backward: te=%d > 256", te);
-    launch_k((time_embed_bwd_input_kernel), rows, dim3(te, 4), static_cast<size_t>(4) * te * sizeof(float), st, dout, c_total, e_ws, te, proj_set, proj_w, de0);
+    launch_k((time_embed_bwd_input_kernel), dim3(rows, ceil_div(te, 16)), 256, 0, st, dout, c_total, e_ws, te, proj_set, proj_w, de0);
     launch_k((label_emb_bwd_kernel), n_classes, 256, 0, st, de0, y, rows, te, d_label_emb);
   }
   return check_launch("time_embed_backward");

@@ -293,9 +293,18 @@ class TrainKernels:
         if stride == 1:
             cw, ph, pw = layer.dgrad_tc_weight(1, pad)
             assert ph == pw
-            dx = self.k.conv(dy, cw, stride=1, pad=ph)
+            # x already has a gradient from another consumer (the residual branch): it rides in the convolution's epilogue as
+            # the residual instead of a separate accumulation pass
+            cur = tape.grads.get(x.buf.data_ptr())
+            if cur is not None and (cur.n, cur.h, cur.w, cur.c) != (x.n, x.h, x.w, x.c):
+                cur = None
+            dx = self.k.conv(dy, cw, stride=1, pad=ph, residual=cur)
             assert (dx.h, dx.w) == (h, w)
-            tape.add(x, dx)
+            if cur is not None:
+                tape.grads[x.buf.data_ptr()] = dx
+                tape.keep.append(cur)
+            else:
+                tape.add(x, dx)
             return
         # strided convolution: one stride-1 convolution over dy per input-parity class, scattered into dx
         dx = self.grad_like(x, zero=True)
@@ -808,18 +817,26 @@ class TrainEngine:
         # time embedding: one launch set for all nine projections (+ label embedding)
         fw, pw, pb, ps = self.tp._packed
         rows = t.numel()
-        dpw = torch.empty_like(pw)
-        dpb = torch.empty_like(pb)
+        # flat_order lays the nine projection weights, then the nine biases, out in head order: when they are contiguous (every
+        # size is a multiple of the 64-element padding) the kernel writes the flat buffer directly, no per-head copies
+        wviews = [self._param_grad(wn, (c, self.tp.te)) for wn, _, c in self.tp_names]
+        bviews = [self._param_grad(bn, (c,)) for _, bn, c in self.tp_names]
+        in_place = all(self.offsets[self.tp_names[i + 1][0]][0] == self.offsets[self.tp_names[i][0]][0] + self.tp_names[i][2] * self.tp.te and
+                       self.offsets[self.tp_names[i + 1][1]][0] == self.offsets[self.tp_names[i][1]][0] + self.tp_names[i][2]
+                       for i in range(len(self.tp_names) - 1))
+        dpw = wviews[0] if in_place else torch.empty_like(pw)
+        dpb = bviews[0] if in_place else torch.empty_like(pb)
         dlab = self._param_grad(self.label_name, tuple(self.sd[self.label_name].shape)) if (self.label_name and yy is not None) else None
         ws = tk.scratch("time", _lib.query("sbgm_time_embed_backward_scratch_floats", fw.shape[0], self.tp.te, rows))
         call("sbgm_time_embed_backward", dtproj.data_ptr(), t.data_ptr(), _ptr(yy), fw.data_ptr(), fw.shape[0], self.tp.te,
              _ptr(self.tp.label_emb) if yy is not None else None, 0 if dlab is None else dlab.shape[0], pw.data_ptr(), ps.data_ptr(),
              self.tp.c_total, rows, dpw.data_ptr(), dpb.data_ptr(), _ptr(dlab), ws.data_ptr(), _stream())
-        off = 0
-        for wn, bn, c in self.tp_names:
-            self._param_grad(wn, (c, self.tp.te)).copy_(dpw[off:off + c])
-            self._param_grad(bn, (c,)).copy_(dpb[off:off + c])
-            off += c
+        if not in_place:
+            off = 0
+            for (wn, bn, c), wv, bv in zip(self.tp_names, wviews, bviews):
+                wv.copy_(dpw[off:off + c])
+                bv.copy_(dpb[off:off + c])
+                off += c
         if sync is not None:
             sync.progress(list(self.touched)[reported:])
             sync.finish()
@@ -836,9 +853,11 @@ def flat_order(names: Sequence[str]) -> List[str]:
     the end) can start while backward is still running.  The time projections and the label embedding come first: their
     gradients are the last thing backward produces (one launch for all nine heads, TrainEngine.backward).  Within a stage the
     state-dict order is kept (stable sort)."""
-    def stage(k: str) -> int:
-        if "time_projection_layer" in k or k.endswith("label_emb.weight"):
-            return 0
+    def stage(k: str):
+        if k.endswith("label_emb.weight"):
+            return -3
+        if "time_projection_layer" in k:      # weights first, then biases, each in head order (encoder 0..4, decoder blocks):
+            return -2 if k.endswith(".weight") else -1     # one contiguous range each (TrainEngine.backward writes them in place)
         if k.startswith("encoder."):
             rest = k[len("encoder."):]
             if rest.startswith("conv1."):

@@ -810,3 +810,28 @@ def test_one_launch_adam_matches_torch(kind, wd):
     b.step()
     for p, q in zip(mine, theirs):
         assert torch.allclose(p, q, rtol=4e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("n,hw,c,per_sample", [(1, 300, 768, False),       # one block per channel vector (Linear bias gradients)
+                                               (3, 4096, 128, False),      # same, 512 threads
+                                               (4, 128 * 96, 64, False),   # > 32768 pixels: ticketed last-block reduction, twice on one scratch
+                                               (3, 1000, 64, True)])       # per-sample sums + total (time-projection gradients)
+def test_channel_sums(E, prec, n, hw, c, per_sample):
+    from sbgm_danra_b200 import _lib
+    from sbgm_danra_b200._lib import call
+    fmt = FMTS[prec]
+    x = stored(E, gen(n, c, 1, hw, seed=1), fmt)
+    xa = act_of(E, x, fmt)
+    ws = torch.zeros(_lib.query("sbgm_channel_sums_scratch_floats", n, c), device=DEV)
+    tot = torch.zeros(c, device=DEV)
+    per = torch.zeros(n, c + 5, device=DEV) if per_sample else None
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        call("sbgm_channel_sums", xa.ptr, xa.plane, fmt, n, hw, c, None if per is None else per.data_ptr(), c + 5, tot.data_ptr(),
+             ws.data_ptr(), st)
+    want = x.double().sum(dim=(2, 3))
+    assert rel_l2(tot.cpu().double(), want.sum(0)) < 1e-5
+    if per_sample:
+        assert rel_l2(per[:, :c].cpu().double(), want) < 1e-5
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
