@@ -412,7 +412,7 @@ int sbgm_stem_wgrad(const float* x, const float* planes, int np, int cc, const v
 /* Decoder.final_layer.conv (cin -> 1, 3x3) + the 1/std scaling, backward: g = dscore * inv_std[n];
  * da [n,h,w,cin] (fmt), dweight_oihw[1][cin][3][3], dbias[1]; weight_tap_ci = fp32 [9][cin].  dbias_up[cin] (nullable) = da
  * summed over n,h,w: the bias gradient of the convolution that produced `a` (final_layer.conv_up), free in the same pass
- * (needs cin / 8 to be a power of two). */
+ * (needs cin = 64, 128 or 256). */
 size_t sbgm_final_conv_backward_scratch_floats(int cin);
 int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const void* a, size_t a_plane, int fmt,
                              const float* weight_tap_ci, void* da, size_t da_plane, float* dweight_oihw, float* dbias, float* dbias_up,

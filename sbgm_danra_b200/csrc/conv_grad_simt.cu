@@ -253,7 +253,7 @@ __global__ void final_conv_bwd_input_kernel(const float* __restrict__ dscore, co
   }
 }
 
-// Both gradients in one pass over the activation (cin / 8 a power of two <= 32): a block owns tiles of kFinalTileRows x lanes pixels
+// Both gradients in one pass over the activation (cin = 64, 128 or 256): a block owns tiles of kFinalTileRows x lanes pixels
 // of one image, stages g (zero outside the image: no boundary branches) for the tile + halo in shared memory, and each thread
 // (pixel column `lane`, channel vector `vec`) walks the tile's rows: the SAME nine g values feed da[p][ci] += g * w[tap][ci] and
 // dW[tap][ci] += g * a[p][ci]; it also sums da per channel (the bias gradient of the convolution that produced `a`).  Loads of
@@ -286,16 +286,29 @@ final_conv_bwd_fused_kernel(const float* __restrict__ dscore, const float* __res
   float bsum = 0.0f;
   const int tiles_x = (w + lanes - 1) / lanes, tiles_y = (h + kFinalTileRows - 1) / kFinalTileRows;
   const int ntiles = n * tiles_y * tiles_x;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // g of a tile + halo: at most two values per thread (lanes <= 32, host-checked), fetched one tile AHEAD into registers so that
+  // the load is in flight while the current tile is computed
+  auto fetch_g = [&](int tile, float (&r)[2]) {
     const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
     const float sc = inv_std ? inv_std[b] : 1.0f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const int yy = ty * kFinalTileRows - 1 + i / gw, xx = tx * lanes - 1 + i % gw;
+      r[k] = (i < (kFinalTileRows + 2) * gw && yy >= 0 && yy < h && xx >= 0 && xx < w)
+                 ? __ldg(dscore + (static_cast<size_t>(b) * h + yy) * w + xx) * sc : 0.0f;
+    }
+  };
+  float gnext[2] = {0.0f, 0.0f};
+  if (static_cast<int>(blockIdx.x) < ntiles) fetch_g(blockIdx.x, gnext);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
     const int y0 = ty * kFinalTileRows, x0 = tx * lanes;
     __syncthreads();
-    for (int i = threadIdx.x; i < (kFinalTileRows + 2) * gw; i += 256) {
-      const int yy = y0 - 1 + i / gw, xx = x0 - 1 + i % gw;
-      gs[i] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(dscore + (static_cast<size_t>(b) * h + yy) * w + xx) * sc : 0.0f;
-    }
+    if (threadIdx.x < (kFinalTileRows + 2) * gw) gs[threadIdx.x] = gnext[0];
+    if (threadIdx.x + 256 < (kFinalTileRows + 2) * gw) gs[threadIdx.x + 256] = gnext[1];
     __syncthreads();
+    if (tile + static_cast<int>(gridDim.x) < ntiles) fetch_g(tile + gridDim.x, gnext);
     const int x = x0 + lane;
     if (x >= w) continue;            // (no barrier below this point inside the iteration)
     const int rows = min(kFinalTileRows, h - y0);
@@ -538,9 +551,9 @@ int sbgm_stem_wgrad(const float* x, const float* planes, int np, int cc, const v
   return check_launch("stem_wgrad");
 }
 
-static bool final_fused_ok(int cin) {
+static bool final_fused_ok(int cin) {       // 8, 16 or 32 channel vectors: 32, 16 or 8 pixel lanes, a g tile of <= 512 values
   const int vecs = cin / 8;
-  return cin % 8 == 0 && vecs <= 32 && (vecs & (vecs - 1)) == 0;
+  return cin % 8 == 0 && vecs >= 8 && vecs <= 32 && (vecs & (vecs - 1)) == 0;
 }
 static int final_fused_blocks() { return 148; }   // persistent: one block per SM (249 registers x 256 threads)
 
@@ -572,7 +585,7 @@ int sbgm_final_conv_backward(const float* dscore, const float* inv_std, const vo
              dbias_up);
     return check_launch("final_conv_backward");
   }
-  SBGM_REQUIRE(dbias_up == nullptr, "final_conv_backward: dbias_up needs cin / 8 to be a power of two (cin=%d)", cin);
+  SBGM_REQUIRE(dbias_up == nullptr, "final_conv_backward: dbias_up needs cin = 64, 128 or 256 (cin=%d)", cin);
   const size_t smem_w = static_cast<size_t>(lanes) * (9 * cin + 1) * sizeof(float);
   SBGM_DISPATCH_FMT(fmt, {
     auto kw_ = final_conv_bwd_weight_kernel<FMT>;

@@ -184,8 +184,12 @@ static void wgrad_tc_plan(int n, int ho, int wo, int cin, int cout, int kh, int 
   *bn = (fmt == SBGM_FMT_BF16 && cout % 128 == 0) ? 128 : 64;
   const int base = ((p->units + 1) / 2) * (cout / *bn);
   // pixel split: `waves` x 148 CTAs per layer.  Every CTA dumps its [128 x BN] fp32 accumulator and the reduce reads it back, so
-  // the workspace traffic grows with the wave count (SBGM_B200_WGRAD_WAVES, A/B-tested on the training step)
-  static const int waves = [] { const char* e = getenv("SBGM_B200_WGRAD_WAVES"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 3; }();
+  // the workspace traffic grows with the wave count.  Measured per layer on the C4 step (profiles/r02_wgrad_waves_*.txt): the
+  // 64-wide layers (few CTAs per pixel range, long pixel ranges) are faster with three waves (final conv_up 130 vs 205 us), the
+  // 128-wide ones (many (tap, channel-block) units) with one (36 launches: 362 vs 462 us, and a third of the reduce traffic).
+  // SBGM_B200_WGRAD_WAVES overrides both.
+  static const int forced = [] { const char* e = getenv("SBGM_B200_WGRAD_WAVES"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 0; }();
+  const int waves = forced ? forced : (*bn == 64 ? 3 : 1);
   int s = (148 * waves + base - 1) / base;
   if (s > p->total_tiles) s = p->total_tiles;
   if (s < 1) s = 1;

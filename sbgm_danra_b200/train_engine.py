@@ -787,7 +787,7 @@ class TrainEngine:
         """final_layer.conv_up's bias gradient is a by-product of the final convolution's backward (sbgm_final_conv_backward's
         dbias_up) when conv_up is the resize-convolution and its channel-vector count is a power of two."""
         vecs = self.final_w.shape[2] // 8
-        return self.spec.use_resize_conv and self.final_w.shape[2] % 8 == 0 and vecs <= 32 and vecs & (vecs - 1) == 0
+        return self.spec.use_resize_conv and self.final_w.shape[2] % 8 == 0 and 8 <= vecs <= 32 and vecs & (vecs - 1) == 0
 
     # -- backward ----------------------------------------------------------------------------------------
     def backward(self, dscore: torch.Tensor) -> Dict[str, torch.Tensor]:
