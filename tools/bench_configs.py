@@ -16,16 +16,19 @@ CONFIGS = {
     # name: (sampler, size, batch, steps, precision, net kwargs, flops/sample/forward, nfe)
     "C1": ("em", 64, 4, 100, "bf16x3", dict(n_lr=1), 1.279e9, 1),
     "C2": ("em", 128, 64, 500, "bf16x3", dict(n_lr=1), 5.146e9, 1),
+    "C2-fp16x2": ("em", 128, 64, 500, "fp16x2", dict(n_lr=1), 5.146e9, 1),
     "C2-bf16": ("em", 128, 64, 500, "bf16", dict(n_lr=1), 5.146e9, 1),
     "C3": ("pc", 128, 64, 500, "bf16", dict(n_lr=2, geo=True, seasons=True), 5.313e9, 2),
     "C3-bf16x3": ("pc", 128, 64, 500, "bf16x3", dict(n_lr=2, geo=True, seasons=True), 5.313e9, 2),
+    "C3-fp16x2": ("pc", 128, 64, 500, "fp16x2", dict(n_lr=2, geo=True, seasons=True), 5.313e9, 2),
     "C5": ("em", 256, 4, 1000, "bf16x3", dict(n_lr=1), 21.09e9, 1),
     "C5-b32": ("em", 256, 32, 1000, "bf16x3", dict(n_lr=1), 21.09e9, 1),
+    "C5-b32-fp16x2": ("em", 256, 32, 1000, "fp16x2", dict(n_lr=1), 21.09e9, 1),
 }
 
 
 def main():
-    names = sys.argv[1:] or ["C1", "C2", "C2-bf16", "C3", "C3-bf16x3", "C5", "C5-b32"]
+    names = sys.argv[1:] or list(CONFIGS)
     dev = torch.device("cuda:0")
     for name in names:
         kind, size, batch, steps, prec, ck, flop, nfe = CONFIGS[name]
