@@ -325,6 +325,16 @@ class Kernels:
              x.n, x.h * x.w, x.c, self._gn_scratch.data_ptr(), _stream())
         return out
 
+    def affine(self, x: Act, skip: Optional[Act] = None, tproj: Optional[torch.Tensor] = None, act: int = ACT_NONE) -> Act:
+        """act(x + skip + tproj): the epilogue of a decoder block whose norm is nn.Identity (score_unet.py:593-612), as the
+        normalisation kernel with unit statistics (mean 0, rstd 1, no affine)."""
+        unit = torch.tensor([0.0, 1.0], dtype=torch.float32, device=self.device).repeat(x.c, 1).contiguous()
+        out = x.like()
+        call("sbgm_norm_apply", x.ptr, x.plane, unit.data_ptr(), 2, x.c, None, None, None if skip is None else skip.ptr,
+             0 if skip is None else skip.plane, _ptr(tproj), tproj.stride(0) if tproj is not None else 0, 1, act, out.ptr, out.plane,
+             self.fmt, x.n, x.h * x.w, x.c, _stream())
+        return out
+
     def layernorm(self, x: Act, gamma, beta) -> Act:
         if "ln" in _SKIP:
             return x

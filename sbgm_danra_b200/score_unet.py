@@ -201,10 +201,27 @@ class Encoder(nn.Module):
                 cond_img: Optional[torch.Tensor] = None, lsm_cond: Optional[torch.Tensor] = None,
                 topo_cond: Optional[torch.Tensor] = None):
         _require_cuda(self.conv1.weight, "Encoder")
-        if self.training and any(isinstance(m, nn.BatchNorm2d) for m in self.modules()):
-            raise NotImplementedError("standalone Encoder.forward serves eval mode; train-mode BatchNorm (batch statistics) runs "
-                                      "through ScoreNet.forward / loss_fn / the samplers (train_engine.py) -- call .eval() here")
         dev = self.conv1.weight.device
+        if self.training and any(isinstance(m, nn.BatchNorm2d) for m in self.modules()):
+            # .train(): batch statistics, running statistics and num_batches_tracked updated as nn.BatchNorm2d does (the
+            # reference's Encoder.forward, score_unet.py:247-364, in training mode).  The standalone call returns detached
+            # feature maps; gradients flow through ScoreNet.forward / loss_fn, which own the backward tape.
+            from .train_engine import TrainEngine
+            with torch.no_grad(), torch.cuda.device(dev):
+                tensors = {f"encoder.{k}": v for k, v in list(self.named_parameters()) + list(self.named_buffers())}
+                spec = _eng.UNetSpec(cin_total=self.input_channels, time_embedding=self.time_embedding,
+                                     block_layers=tuple(self.block_layers), n_heads=self.n_heads,
+                                     has_labels=self.num_classes is not None)
+                eng = TrainEngine(tensors, spec, self.precision, dev, bn_train=True, encoder_only=True)
+                planes = _eng.concat_planes(x.shape[0], lsm_cond, topo_cond, cond_img, dev)
+                if planes is not None and planes.shape[0] != x.shape[0]:
+                    planes = planes.expand(x.shape[0], -1, -1, -1).contiguous()
+                fmaps = eng.forward(x.to(device=dev, dtype=torch.float32).contiguous(), t.to(dev), None if y is None else y.to(dev),
+                                    planes, None)
+                for m in self.modules():
+                    if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None:
+                        m.num_batches_tracked += 1
+                return tuple(f.to_nchw() for f in fmaps)
         with torch.no_grad(), torch.cuda.device(dev):
             enc = self._engine()
             x = x.to(device=dev, dtype=torch.float32).contiguous()
@@ -254,18 +271,20 @@ class DecoderBlock(nn.Module):
         if n1 is None or n2 is None:
             raise ValueError("Norm layers not found; possible init error.")
         _require_cuda(self.conv.weight, "DecoderBlock")
-        identity = isinstance(n1, nn.Identity) or isinstance(n2, nn.Identity)
-        if identity or prev_fmap is None or t is None or (t.dim() == 2 and t.shape[-1] == self.time_embedding):
-            raise NotImplementedError("standalone DecoderBlock.forward supports the residual-block form "
-                                      "(norms present, prev_fmap and scalar t given); use Decoder/ScoreNet otherwise")
+        id1, id2 = isinstance(n1, nn.Identity), isinstance(n2, nn.Identity)
         dev = self.conv.weight.device
 
         def build(d):
             fmt = _eng.PRECISIONS[self.precision]
             tp = _eng.TimeProjector(d, self.time_embedding)
-            sd = {f"d.residual_layers.0.{k}": v for k, v in self.state_dict().items()}
+            own = dict(self.state_dict())
+            for nm, c, ident in (("norm1", self.input_channels, id1), ("norm2", self.output_channels, id2)):
+                if ident and self.norm_kind == "group":      # an Identity norm (Decoder.final_layer): placeholders, never applied
+                    own[f"{nm}.weight"] = torch.ones(c, device=d)
+                    own[f"{nm}.bias"] = torch.zeros(c, device=d)
+            sd = {f"d.residual_layers.0.{k}": v for k, v in own.items()}
             # a one-block decoder without final layer: reuse DecoderEngine's block packing
-            sd.update({f"d.final_layer.{k}": v for k, v in self.state_dict().items() if k.startswith(("conv_up", "conv."))})
+            sd.update({f"d.final_layer.{k}": v for k, v in own.items() if k.startswith(("conv_up", "transpose", "conv."))})
             sd["d.final_layer.conv.weight"] = self.conv.weight[:1]
             sd["d.final_layer.conv.bias"] = self.conv.bias[:1]
             de = _eng.DecoderEngine(sd, "d.", plan=[(self.input_channels, self.output_channels, self.compute_attn)],
@@ -276,20 +295,49 @@ class DecoderBlock(nn.Module):
             return de, fmt
 
         with torch.no_grad(), torch.cuda.device(dev):
-            de, fmt = self._cache.get(self, self.precision, build)
-            if tuple(prev_fmap.shape) != (fmap.shape[0], self.output_channels, 2 * fmap.shape[2], 2 * fmap.shape[3]):
-                raise AssertionError(f"prev_fmap shape {tuple(prev_fmap.shape)} must match output shape "
-                                     f"{(fmap.shape[0], self.output_channels, 2 * fmap.shape[2], 2 * fmap.shape[3])}")
-            tproj = de.tp(t.to(dev), None)
+            de, fmt = self._cache.get(self, (self.precision, id1, id2), build)
+            out_shape = (fmap.shape[0], self.output_channels, 2 * fmap.shape[2], 2 * fmap.shape[3])
+            skip = None
+            if prev_fmap is not None and torch.is_tensor(prev_fmap):
+                if tuple(prev_fmap.shape) != out_shape:
+                    raise AssertionError(f"prev_fmap shape {tuple(prev_fmap.shape)} must match output shape {out_shape}")
+                skip = _eng.Act.from_nchw(prev_fmap.to(dev), fmt)
             k, blk = de.k, de.blocks[0]
+            tcols = None
+            if t is not None:
+                t = t.to(dev)
+                if t.dim() == 1 or (t.dim() == 2 and t.shape[-1] != self.time_embedding):      # raw timesteps [B]
+                    tcols = de.tp.cols(de.tp(t.reshape(-1).float(), None), "dec0")
+                else:                                   # a precomputed embedding [B, time_dim]: SiLU -> Linear on the kernels
+                    tcols = self._project_embedding(k, t.float(), fmt)
             x = _eng.Act.from_nchw(fmap.to(dev), fmt)
-            skip = _eng.Act.from_nchw(prev_fmap.to(dev), fmt)
-            a = k.groupnorm(k.conv(k.upsample2x(x), blk["conv_up"], pad=1), *blk["n1"], groups=blk["g1"])
+            a = k.conv(k.upsample2x(x), blk["conv_up"], pad=1) if self.use_resize_conv else de._transpose_up(x, blk["conv_up"])
+            if not id1:
+                a = k.groupnorm(a, *blk["n1"], groups=blk["g1"])
             b = k.conv(a, blk["conv"], pad=1)
-            out = k.groupnorm(b, *blk["n2"], groups=blk["g2"], act=de.act, skip=skip, tproj=de.tp.cols(tproj, "dec0"))
+            if id2:
+                out = k.affine(b, skip=skip, tproj=tcols, act=de.act)            # x + prev_fmap + t_proj, then the activation
+            else:
+                out = k.groupnorm(b, *blk["n2"], groups=blk["g2"], act=de.act, skip=skip, tproj=tcols)
             if blk["attn"] is not None:
                 out = _eng.attention_block(k, blk["attn"], out)
             return out.to_nchw()
+
+    def _project_embedding(self, k, t_emb: torch.Tensor, fmt: int) -> torch.Tensor:
+        """time_projection_layer (SiLU -> Linear) of a precomputed embedding [B, time_dim] -> fp32 [B, C_out]."""
+        cache = self.__dict__.setdefault("_tproj_cw", {})
+        lin = self.time_projection_layer[1]
+        key = (fmt, lin.weight._version, lin.bias._version, lin.weight.data_ptr())
+        if key not in cache:
+            cache.clear()
+            pk = _eng._Packer({"w": lin.weight.detach(), "b": lin.bias.detach()}, fmt, lin.weight.device)
+            cache[key] = pk.conv("w", "b")
+        rows = t_emb.shape[0]
+        tok = _eng.Act.from_nchw(t_emb.t().reshape(1, self.time_embedding, 1, rows).contiguous(), fmt)
+        h = tok.like()
+        _eng.call("sbgm_act_forward", tok.ptr, tok.plane, h.ptr, h.plane, fmt, tok.plane, _eng.ACTS["silu"], _eng._stream())
+        out = k.linear(h, cache[key])
+        return out.to_nchw().reshape(self.output_channels, rows).t().contiguous()
 
 
 class Decoder(nn.Module):

@@ -554,7 +554,10 @@ class TrainEngine:
     `params` maps state-dict names to the live parameter / buffer tensors (fp32, CUDA).  BatchNorm running
     statistics are updated in place when `bn_train` is set."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], spec: UNetSpec, precision: str, device, bn_train: bool) -> None:
+    def __init__(self, params: Dict[str, torch.Tensor], spec: UNetSpec, precision: str, device, bn_train: bool,
+                 encoder_only: bool = False) -> None:
+        """`encoder_only`: `params` holds the encoder alone and `forward` returns its five feature maps (the standalone
+        `Encoder.forward` in .train(): batch statistics, running statistics updated; nothing is differentiated)."""
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
         device = torch.device(device)
@@ -562,6 +565,7 @@ class TrainEngine:
             raise RuntimeError("sbgm_danra_b200 runs on CUDA devices only (no CPU fallback); got device " + str(device))
         _lib.load_library()
         self.spec, self.device, self.fmt, self.bn_train = spec, device, TRAIN_PRECISIONS[precision], bn_train
+        self.encoder_only = encoder_only
         self.sd = {k: v.detach() for k, v in params.items()}
         for k, v in self.sd.items():
             if v.is_floating_point() and (v.dtype != torch.float32 or not v.is_cuda):
@@ -635,6 +639,11 @@ class TrainEngine:
         self.label_name = f"{p}label_emb.weight" if spec.has_labels else None
         if spec.has_labels:
             self.tp.label_emb = sd[self.label_name].contiguous()
+        self.act = ACTS[spec.activation]
+        if self.encoder_only:
+            self.tp.finalize()
+            self.plan.run()
+            return
         d = "decoder."
         affine = spec.norm == "group"
         self.dec_blocks = []
@@ -662,7 +671,6 @@ class TrainEngine:
         self.final_w = wf.permute(0, 2, 3, 1).reshape(wf.shape[0], 9, wf.shape[1]).contiguous()
         self.final_b = sd[f"{fp}.conv.bias"].contiguous()
         self.final_names = (f"{fp}.conv.weight", f"{fp}.conv.bias")
-        self.act = ACTS[spec.activation]
         self.plan.run()            # every forward / data-gradient pack of the step: one batched launch
 
     # -- forward ----------------------------------------------------------------------------------------
@@ -738,6 +746,10 @@ class TrainEngine:
             if li in self.enc_attn:
                 hcur = _attention_block(tk, self.enc_attn[li], hcur)
             fmaps.append(hcur)
+        if self.encoder_only:                  # standalone Encoder.forward: the feature maps are the result, no backward follows
+            self.tape = tk.tape = None
+            self._final = self._time = self._sampler = None
+            return fmaps
 
         # Decoder (score_unet.py:733-758)
         rev = list(reversed(fmaps))

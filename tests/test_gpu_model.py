@@ -94,6 +94,68 @@ def test_encoder_decoder_standalone_api():
         net.decoder(*fm[:4], t=b.t.to(DEV))
 
 
+def test_encoder_standalone_in_train_mode_uses_batch_statistics():
+    """Encoder.forward in .train() (the reference accepts it, score_unet.py:247-364): batch-statistics BatchNorm, running
+    statistics and num_batches_tracked move as nn.BatchNorm2d's do."""
+    from oracle import score_ref
+    from oracle.synth import synth_batch
+    ck = dict(n_lr=2, geo=True, seasons=True)
+    net, cfg, sd = _model(ck, "bf16x3")
+    b = synth_batch(batch=4, size=64, n_lr=2, geo=True, seasons=True)
+    enc = net.encoder.train()
+    rm0 = enc.bn1.running_mean.clone()
+    nbt0 = int(enc.bn1.num_batches_tracked)
+    fm = enc(*[_cuda(v) for v in b.model_args()])
+    with torch.no_grad():
+        want = score_ref.encoder_forward(sd, cfg, *b.model_args(), bn_train=True)
+    for got, w in zip(fm, want):
+        assert got.shape == w.shape and rel_l2(got.cpu(), w) < 1e-3
+    assert not torch.equal(enc.bn1.running_mean, rm0) and int(enc.bn1.num_batches_tracked) == nbt0 + 1
+    enc.eval()
+
+
+@pytest.mark.parametrize("form", ["plain", "skip_only", "time_only", "embedded_time", "identity_norms", "transpose_identity"])
+def test_decoder_block_standalone_forms(form):
+    """DecoderBlock.forward in every form the reference accepts (score_unet.py:559-627): without prev_fmap, without t, with a
+    precomputed time embedding, with nn.Identity norms (Decoder.final_layer), with the ConvTranspose2d up-path."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from sbgm_danra_b200.score_unet import DecoderBlock
+    torch.manual_seed(3)
+    cin, cout, te, n, h = 128, 64, 256, 2, 8
+    resize = form != "transpose_identity"
+    blk = DecoderBlock(cin, cout, te, activation=nn.SiLU, compute_attn=False, use_resize_conv=resize, norm="group", gn_groups=8).to(DEV)
+    blk.precision = "bf16x3"
+    if form in ("identity_norms", "transpose_identity"):
+        blk.norm1, blk.norm2 = nn.Identity(), nn.Identity()
+    fmap = torch.randn(n, cin, h, h, device=DEV)
+    prev = torch.randn(n, cout, 2 * h, 2 * h, device=DEV) if form not in ("plain", "time_only") else None
+    t = None
+    if form in ("time_only", "identity_norms", "transpose_identity"):
+        t = torch.rand(n, device=DEV) * 0.9 + 0.05
+    elif form == "embedded_time":
+        t = torch.randn(n, te, device=DEV)
+    got = blk(fmap, prev, t)
+    with torch.no_grad():       # the reference's forward, restated in plain fp32 torch on the CPU with the block's own parameters
+        p = {k: v.detach().cpu() for k, v in blk.state_dict().items()}
+        gn = lambda v, key: v if f"{key}.weight" not in p else F.group_norm(v, 8, p[f"{key}.weight"], p[f"{key}.bias"], eps=1e-5)
+        if resize:
+            x = F.conv2d(F.interpolate(fmap.cpu(), scale_factor=2, mode="bilinear", align_corners=False), p["conv_up.weight"], p["conv_up.bias"], padding=1)
+        else:
+            x = F.conv_transpose2d(fmap.cpu(), p["transpose.weight"], p["transpose.bias"], stride=2)
+        x = gn(F.conv2d(gn(x, "norm1"), p["conv.weight"], p["conv.bias"], padding=1), "norm2")
+        if prev is not None:
+            x = x + prev.cpu()
+        if t is not None:
+            emb = t.cpu() if t.dim() == 2 else blk.sinusoidal_embedding(t).cpu()
+            x = x + F.linear(F.silu(emb), p["time_projection_layer.1.weight"], p["time_projection_layer.1.bias"])[:, :, None, None]
+        want = F.silu(x)
+    assert got.shape == want.shape and rel_l2(got.cpu(), want.cpu()) < 1e-3, form
+    if prev is not None:
+        with pytest.raises(AssertionError):
+            blk(fmap, prev[:, :, :-1], t)
+
+
 def test_attention_and_embedding_modules():
     from oracle import score_ref
     from sbgm_danra_b200.score_unet import ImageSelfAttention, SinusoidalEmbedding
