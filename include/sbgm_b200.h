@@ -433,6 +433,23 @@ typedef struct {
   int taps[16];
 } sbgm_pack_job;
 int sbgm_pack_weights(const sbgm_pack_job* jobs_host, int njobs, int fmt, void* stream);
+/* On-device batch assembly (sbgm/utils.py:405-480 `extract_samples`; the dataset transforms of sbgm/special_transforms.py:62-343
+ * that sbgm/data_modules.py:727-997 applies on the CPU): ONE launch writes every float32 tensor of a batch from source tensors
+ * of any dtype -- conversion, channel concatenation (a source lands at `dst_offset` inside each destination sample of
+ * `dst_stride` elements; `inner` = elements per sample in the source) and the optional forward transform
+ *     v = log ? log(x + eps) : x;   y = transform ? (((v - sub) * mul) / div) * post_mul + post_add : v.
+ * jobs_dev: DEVICE table ordered by first_block; a block covers sbgm_batch_chunk_elems() elements of one job. */
+enum { SBGM_DT_F32 = 0, SBGM_DT_F64 = 1, SBGM_DT_F16 = 2, SBGM_DT_BF16 = 3, SBGM_DT_I64 = 4, SBGM_DT_I32 = 5, SBGM_DT_I16 = 6,
+       SBGM_DT_U8 = 7, SBGM_DT_I8 = 8 };
+typedef struct {
+  const void* src;
+  float* dst;
+  long long count, inner, dst_stride, dst_offset, first_block;
+  int dtype, log, transform, pad_;
+  float eps, sub, mul, div, post_mul, post_add;
+} sbgm_batch_job;
+int sbgm_batch_chunk_elems(void);
+int sbgm_assemble_batch(const sbgm_batch_job* jobs_dev, int njobs, long long total_blocks, void* stream);
 /* torch.optim.Adam / AdamW update (sbgm/training.py:407 `self.optimizer.step()`, optimizer built by sbgm/training_utils.py:672-698)
  * of EVERY parameter tensor in one launch.  chunks_dev: DEVICE table, one entry per block, each covering at most
  * sbgm_adam_chunk_elems() consecutive elements of one tensor.  Arithmetic follows torch/optim/adam.py (_single_tensor_adam,

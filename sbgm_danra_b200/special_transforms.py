@@ -1,4 +1,4 @@
-"""Inverse transforms of `sbgm/special_transforms.py` on the device: the step after the sampler,
+"""Transforms of `sbgm/special_transforms.py` on the device: the inverse ones: the step after the sampler,
 so that a sampled ensemble reaches physical units (and can be scored, `ensemble.py`) before any device-to-host copy.
 
 Same class names, constructor arguments, validation and arithmetic as the reference (`ZScoreBackTransform` :187-237,
@@ -97,6 +97,79 @@ class PrcpLogBackTransform(object):
         if self.scale_type == "log_minus1_1":
             return _apply(sample, 0.5 * (self.glob_max_log - self.glob_min_log), self.glob_min_log, self.lo, self.hi, exp=True, pre=1.0)
         return _apply(sample, 1.0, 0.0, self.lo, self.hi, exp=True)
+
+
+# ---- forward transforms (special_transforms.py:62-343), applied by the dataset on the CPU in the reference ------------------
+# Each class describes itself as the parameters of the batch-assembly kernel (csrc/batch.cu):
+#     v = log ? log(x + eps) : x;   y = (((v - sub) * mul) / div) * post_mul + post_add        (float32, this operation order)
+# so that `batch.BatchAssembler` can apply it while the batch is written on the device; called directly on a CUDA tensor it
+# runs that kernel as a single job.
+class _ForwardTransform(object):
+    def kernel_params(self):                       # (log, eps, sub, mul, div, post_mul, post_add)
+        raise NotImplementedError
+
+    def __call__(self, sample):
+        from .batch import apply_transform
+        return apply_transform(sample, self)
+
+
+class Scale(_ForwardTransform):
+    """(((x - data_min_in) * (in_high - in_low)) / (data_max_in - data_min_in)) + in_low (special_transforms.py:62-100)."""
+
+    def __init__(self, in_low, in_high, data_min_in=0, data_max_in=1):
+        self.in_low, self.in_high, self.data_min_in, self.data_max_in = in_low, in_high, data_min_in, data_max_in
+
+    def kernel_params(self):
+        return (False, 0.0, float(self.data_min_in), float(self.in_high - self.in_low), float(self.data_max_in - self.data_min_in),
+                1.0, float(self.in_low))
+
+
+class ZScoreTransform(_ForwardTransform):
+    """(x - mean) / (std + 1e-8) with the statistics held in float32 (special_transforms.py:143-185)."""
+
+    def __init__(self, mean, std):
+        self.mean, self.std = mean, std
+
+    def kernel_params(self):
+        div = float(torch.tensor(_scalar(self.std, "std"), dtype=torch.float32) + 1e-8)
+        return (False, 0.0, float(torch.tensor(_scalar(self.mean, "mean"), dtype=torch.float32)), 1.0, div, 1.0, 0.0)
+
+
+class PrcpLogTransform(_ForwardTransform):
+    """log(x + eps), then the scaling chosen by `scale_type` (special_transforms.py:239-343; the forward class widens the
+    log range by buffer_frac on EACH side, the inverse by buffer_frac / 2 -- both as the reference has them)."""
+
+    def __init__(self, eps=0.01, scale_type="log_zscore", glob_mean_log=None, glob_std_log=None, glob_min_log=None, glob_max_log=None,
+                 buffer_frac=0.5):
+        self.eps, self.scale_type = eps, scale_type
+        self.glob_mean_log, self.glob_std_log = glob_mean_log, glob_std_log
+        self.glob_min_log, self.glob_max_log, self.buffer_frac = glob_min_log, glob_max_log, buffer_frac
+        if self.glob_min_log is not None and self.glob_max_log is not None:
+            log_range = self.glob_max_log - self.glob_min_log
+            self.glob_min_log = self.glob_min_log - self.buffer_frac * log_range
+            self.glob_max_log = self.glob_max_log + self.buffer_frac * log_range
+        if scale_type == "log_zscore":
+            if self.glob_mean_log is None or self.glob_std_log is None:
+                raise ValueError("Global mean and standard deviation not provided. Using local statistics is not recommended.")
+        elif scale_type in ("log_01", "log_minus1_1"):
+            if self.glob_min_log is None or self.glob_max_log is None:
+                raise ValueError("Min and max log values not provided. Using global statistics is recommended.")
+        elif scale_type != "log":
+            raise ValueError("Invalid scale type. Please choose '01' or 'zscore'.")
+
+    def kernel_params(self):
+        eps = float(self.eps)
+        if self.scale_type == "log_zscore":
+            return (True, eps, float(_scalar(self.glob_mean_log, "glob_mean_log")), 1.0,
+                    float(_scalar(self.glob_std_log, "glob_std_log") + 1e-8), 1.0, 0.0)
+        if self.scale_type in ("log_01", "log_minus1_1"):
+            denom = float(self.glob_max_log - self.glob_min_log)
+            if denom == 0:
+                raise ValueError("The log-range of data is zero. Cannot scale to [0, 1]. Please check the data.")
+            if self.scale_type == "log_01":
+                return (True, eps, float(self.glob_min_log), 1.0, denom, 1.0, 0.0)
+            return (True, eps, float(self.glob_min_log), 1.0, denom, 2.0, -1.0)
+        return (True, eps, 0.0, 1.0, 1.0, 1.0, 0.0)
 
 
 def build_back_transforms(hr_var, hr_scaling_method, hr_scaling_params, lr_vars, lr_scaling_methods, lr_scaling_params):

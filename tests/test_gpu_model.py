@@ -667,3 +667,66 @@ def test_generation_monitor_back_transforms_flags_and_clamps_on_device():
     assert any("Clamped generated samples to max 300.0" in m for m in msgs)
     got2, chk2 = monitoring.monitor_generated(x.to(DEV), st.PrcpLogBackTransform(**kw), threshold_mm=1e6, clamp_in_generation=True)
     assert chk2 == {"has_extreme": False} and torch.allclose(got2.cpu(), want_bt, rtol=2e-5, atol=2e-5)   # nothing flagged: no clamp
+
+
+# ---- the host->device boundary: batch assembly -------------------------------------------
+_BATCH_NAMES = ("hr", "classifier", "lr", "lsm_hr", "lsm", "sdf", "topo", "hr_point", "lr_point")
+
+
+@pytest.mark.parametrize("two_lr", [True, False])
+def test_extract_samples_matches_reference_golden(two_lr):
+    """sbgm_danra_b200.batch.extract_samples (one pinned staging buffer, one H2D copy, one kernel) against the reference's own
+    `extract_samples` (tests/golden/batch_golden.npz) and the oracle: bit-exact, mixed source dtypes, LR concatenation."""
+    from oracle import batch_ref as br
+    from sbgm_danra_b200 import batch
+    gold = np.load(os.path.join(GOLDEN_DIR, "batch_golden.npz"))
+    samples = br.sample_dict(two_lr=two_lr)
+    want = br.extract_samples_ref(samples)
+    for rep in range(3):                       # the staging buffers alternate and are reused
+        got = batch.extract_samples(samples, device=DEV)
+        for nm, g, w in zip(_BATCH_NAMES, got, want):
+            assert g.is_cuda and tuple(g.shape) == tuple(w.shape), nm
+            assert torch.equal(g.cpu(), w), nm
+            assert np.array_equal(g.cpu().numpy(), gold[f"extract{int(two_lr)}/{nm}"]), nm
+            if nm != "classifier":
+                assert g.dtype == torch.float32
+    # sources already on the device (a GPU-resident dataset) and missing optional keys
+    on_dev = {k: v.to(DEV) for k, v in samples.items() if k not in ("sdf", "lr_point")}
+    got = batch.extract_samples(on_dev, device=DEV)
+    assert got[5] is None and got[8] is None and torch.equal(got[0].cpu(), want[0]) and torch.equal(got[2].cpu(), want[2])
+    with pytest.raises(ValueError, match="No HR image found"):
+        batch.extract_samples({"temp_lr": samples["temp_lr"]}, device=DEV)
+
+
+@pytest.mark.parametrize("name", ["zscore_t2m", "scale_01", "scale_m11", "log_zscore", "log_01", "log_minus1_1", "log_plain"])
+def test_forward_transforms_match_reference_golden(name):
+    """special_transforms.Scale / ZScoreTransform / PrcpLogTransform on the device against the reference classes' outputs."""
+    from oracle import batch_ref as br
+    from sbgm_danra_b200 import special_transforms as st
+    gold = np.load(os.path.join(GOLDEN_DIR, "batch_golden.npz"))
+    kind, kw, inp = br.FWD_CASES[name]
+    x = torch.from_numpy(br.fwd_case_input(inp))
+    tf = {"zscore": lambda: st.ZScoreTransform(kw["mean"], kw["std"]), "scale": lambda: st.Scale(**kw),
+          "log": lambda: st.PrcpLogTransform(**kw)}[kind]()
+    got = tf(x.to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(got, gold[f"fwd/{name}"], rtol=1e-6, atol=3e-7)
+    np.testing.assert_allclose(got, br.apply_fwd_case(name, x.numpy()), rtol=1e-6, atol=3e-7)
+
+
+def test_batch_assembler_applies_transforms_while_assembling():
+    """Raw physical fields cross the bus; the dataset's transforms run inside the assembly kernel, per sample-dict key."""
+    from oracle import batch_ref as br
+    from sbgm_danra_b200 import batch, special_transforms as st
+    g = torch.Generator().manual_seed(1)
+    raw = {"prcp_hr": torch.rand(4, 1, 32, 32, generator=g).double() * 30, "temp_lr": torch.randn(4, 1, 32, 32, generator=g) * 9 + 8,
+           "prcp_lr": torch.rand(4, 1, 32, 32, generator=g) * 20, "topo": torch.rand(4, 1, 32, 32, generator=g) * 170}
+    kw_p = dict(eps=0.01, scale_type="log_zscore", glob_mean_log=-1.2, glob_std_log=2.0)
+    tfs = {"prcp_hr": st.PrcpLogTransform(**kw_p), "prcp_lr": st.PrcpLogTransform(**kw_p), "temp_lr": st.ZScoreTransform(8.69, 6.19),
+           "topo": st.Scale(0, 1, 0.0, 170.0)}
+    hr, cls, lr, lsm_hr, lsm, sdf, topo, hp, lp = batch.BatchAssembler(DEV, transforms=tfs)(raw)
+    assert cls is None and lsm is None and sdf is None
+    f32 = lambda v: v.float().numpy()
+    np.testing.assert_allclose(hr.cpu().numpy(), br.prcp_log_fwd(f32(raw["prcp_hr"]), **kw_p), rtol=1e-6, atol=3e-7)
+    want_lr = np.concatenate([br.prcp_log_fwd(f32(raw["prcp_lr"]), **kw_p), br.zscore_fwd(f32(raw["temp_lr"]), 8.69, 6.19)], axis=1)
+    np.testing.assert_allclose(lr.cpu().numpy(), want_lr, rtol=1e-6, atol=3e-7)
+    np.testing.assert_allclose(topo.cpu().numpy(), br.scale_fwd(f32(raw["topo"]), 0, 1, 0.0, 170.0), rtol=1e-6, atol=3e-7)

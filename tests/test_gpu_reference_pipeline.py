@@ -99,17 +99,24 @@ def _batches(n_batches, batch, size):
     return out
 
 
-def test_reference_train_batches_three_steps_match_oracle(ref_pipeline, tmp_path, monkeypatch):
+@pytest.mark.parametrize("native_boundary", [False, True])
+def test_reference_train_batches_three_steps_match_oracle(ref_pipeline, tmp_path, monkeypatch, native_boundary):
+    """native_boundary: the loop's two library calls either side of the kernels are this package's too -- `extract_samples`
+    (training.py:287, utils.py:405-480) becomes the one-copy / one-kernel batch assembler and the optimizer the one-launch Adam;
+    the reference file still drives every step."""
     from oracle import philox_ref, score_ref
-    from sbgm_danra_b200 import score_sampling as ss, score_unet as su
+    from sbgm_danra_b200 import batch as sbatch, optim as soptim, score_sampling as ss, score_unet as su
     tu, tr, _ = ref_pipeline
+    if native_boundary:
+        assert hasattr(tr, "extract_samples")
+        monkeypatch.setattr(tr, "extract_samples", sbatch.extract_samples)
     cfg = _cfg(tmp_path)
     model, _, _ = tu.get_model(cfg)                                   # the reference's factory builds THIS package's modules
     assert isinstance(model, su.ScoreNet)
     model = model.to(DEV)
     model.precision = "bf16x3"
     sd0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = (soptim if native_boundary else torch.optim).Adam(model.parameters(), lr=1e-4)
     pipe = tr.TrainingPipeline_general(model, su.loss_fn, su.marginal_prob_std_fn, su.diffusion_coeff_fn, opt, DEV, None, cfg)
     batch, size, steps = 4, 32, 3
     loader = _batches(steps, batch, size)
