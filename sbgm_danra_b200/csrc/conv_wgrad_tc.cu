@@ -230,6 +230,16 @@ extern "C" size_t sbgm_conv2d_wgrad_tc_workspace_floats(int fmt, int n, int h, i
   return static_cast<size_t>(splits) * cout * p.K;
 }
 
+extern "C" int sbgm_conv2d_wgrad_tc_splits(int fmt, int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad) {
+  if (cin % 64 != 0 || cout % 64 != 0 || stride < 1) return 0;
+  const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
+  if (ho <= 0 || wo <= 0) return 0;
+  WgradParams p;
+  int bn = 0, splits = 0;
+  wgrad_tc_plan(n, ho, wo, cin, cout, kh, kw, fmt, &p, &bn, &splits);
+  return splits;
+}
+
 extern "C" int sbgm_conv2d_wgrad_tc(const void* x, size_t x_plane, const void* dy, size_t dy_plane, float* dweight_oihw, int fmt,
                                     int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, float* workspace,
                                     void* stream) {
@@ -253,5 +263,6 @@ extern "C" int sbgm_conv2d_wgrad_tc(const void* x, size_t x_plane, const void* d
                                              : launch_wgrad_tc<SBGM_FMT_BF16, 64, 4>(tx, td, p, splits, st);
   else rc = launch_wgrad_tc<SBGM_FMT_BF16X2, 64, 2>(tx, td, p, splits, st);
   if (rc) return rc;
+  if (dweight_oihw == nullptr) return 0;      // the caller sums the slabs later (sbgm_wgrad_reduce_batch)
   return sbgm_wgrad_reduce(workspace, splits, cout, kh * kw, cin, dweight_oihw, stream);
 }

@@ -433,7 +433,7 @@ class ScoreNet(nn.Module):
         return cache.get(self, self.precision, lambda dev: _eng.UNetEngine(self.state_dict(), self.spec(), self.precision, dev))
 
     # derived device state (packed weights, captured CUDA graphs, gradient exchange): never copied or pickled with the model
-    _DERIVED = ("_cache", "_lane_caches", "_train_runners", "_grad_sync")
+    _DERIVED = ("_cache", "_lane_caches", "_train_runners", "_grad_sync", "_members")
 
     def __deepcopy__(self, memo):
         """`copy.deepcopy(model)` (the reference's EMA copy, sbgm/training.py:114) copies parameters and buffers only; the copy
@@ -455,14 +455,47 @@ class ScoreNet(nn.Module):
         self.__dict__["_cache"] = _EngineCache()
 
     def _bn_modules(self):
-        return [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+        return self._member_lists()[3]
+
+    def _member_lists(self):
+        """(parameter names, parameters, named buffers, BatchNorm modules) of the module tree, cached: four traversals of
+        ~120 modules cost ~0.5 ms of host time per training step, during which the GPU of a loop that reads `loss.item()`
+        every step (sbgm/training.py:410) sits idle.  The cache is dropped by `_apply` (.to / .cuda / .float) and checked
+        against the identity of the first and last parameter and buffer; code that swaps a parameter or a submodule in the
+        middle of the tree after the first training forward must call `model.invalidate_members()`."""
+        m = self.__dict__.get("_members")
+        if m is not None:
+            names, params, buffers, _ = m
+            first, last = names[0], names[-1]
+            if (self.get_parameter(first) is params[0] and self.get_parameter(last) is params[-1]
+                    and (not buffers or self.get_buffer(buffers[-1][0]) is buffers[-1][1])):
+                return m
+        named = list(self.named_parameters())
+        m = ([k for k, _ in named], [p for _, p in named], list(self.named_buffers()),
+             [mod for mod in self.modules() if isinstance(mod, nn.BatchNorm2d)])
+        self.__dict__["_members"] = m
+        return m
+
+    def invalidate_members(self) -> None:
+        self.__dict__.pop("_members", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_members", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__.pop("_members", None)
+        return super().load_state_dict(*args, **kwargs)
 
     def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor] = None,
                 cond_img: Optional[torch.Tensor] = None, lsm_cond: Optional[torch.Tensor] = None,
                 topo_cond: Optional[torch.Tensor] = None) -> torch.Tensor:
         _require_cuda(self.encoder.conv1.weight, "ScoreNet")
         dev = self.encoder.conv1.weight.device
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        needs_grad = False
+        if torch.is_grad_enabled() or self.training:
+            names, params, _, bn_modules = self._member_lists()
+            needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if needs_grad or self.training:
             # training graph: unfolded BatchNorm (batch statistics when .training), backward tape (train_engine.py)
             with torch.cuda.device(dev):
@@ -472,11 +505,9 @@ class ScoreNet(nn.Module):
                 std = self.marginal_prob_std(t)
                 pre = bool(getattr(self, "debug_pre_sigma_div", True))
                 inv_std = None if pre else (1.0 / std.float()).contiguous()
-                names = [k for k, _ in self.named_parameters()]
-                params = [p_ for _, p_ in self.named_parameters()]
                 out = _ScoreNetFn.apply(self, x, t, y, planes, inv_std, names, *params)
                 if self.training:
-                    torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
+                    torch._foreach_add_([m.num_batches_tracked for m in bn_modules], 1)
                 if pre:
                     with torch.no_grad():
                         logger.info(f"[pre-σ-div] mean = {float(out.mean()):.4g}, std = {float(out.std()):.4g}, "
@@ -518,7 +549,7 @@ class _ScoreNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, t, y, planes, inv_std, names, *params):
         from .train_engine import TrainEngine, TrainRunner
-        buffers = list(model.named_buffers())
+        buffers = model._member_lists()[2]
         sync = getattr(model, "_grad_sync", None)
         # the captured graphs bake in the gradient exchange: a runner belongs to one GradSync object (parallel.attach / detach)
         sync_key = None if sync is None else (id(sync), bool(sync.sync_bn), sync.world)
@@ -594,8 +625,14 @@ def marginal_prob_std(t: torch.Tensor, sigma: float, eps: float = 1e-5) -> torch
     """VE-SDE marginal std sqrt((sigma^(2t) - 1) / (2 ln sigma)), clamped at eps (score_unet.py:881-897).
     A [B]-sized scalar schedule: evaluated with torch on whatever device `t` lives on."""
     t = t.to(dtype=torch.float32)
-    log_sigma = torch.log(torch.tensor(sigma, dtype=torch.float32, device=t.device))
+    key = (float(sigma), t.device)
+    log_sigma = _LOG_SIGMA.get(key)
+    if log_sigma is None:           # torch.tensor(..., device=cuda) is a blocking host-to-device copy: made once, not every call
+        log_sigma = _LOG_SIGMA[key] = torch.log(torch.tensor(sigma, dtype=torch.float32, device=t.device))
     return torch.clamp(torch.sqrt((torch.exp((2.0 * t) * log_sigma) - 1.0) / (2.0 * log_sigma)), min=eps)
+
+
+_LOG_SIGMA: dict = {}
 
 
 def diffusion_coeff(t, sigma, device=None):

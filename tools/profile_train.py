@@ -7,7 +7,8 @@ import collections
 import os
 import sys
 
-os.environ["SBGM_B200_TRAIN_GRAPHS"] = "0"
+if "--graphs" not in sys.argv:
+    os.environ["SBGM_B200_TRAIN_GRAPHS"] = "0"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import ProfilerActivity, profile
@@ -20,6 +21,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--graphs", action="store_true", help="keep the CUDA-graph replay on and report the GPU idle gaps of a step")
     ap.add_argument("--list", default="", help="comma-separated kernel-name substrings: also print every matching launch of the last step, in order")
     a = ap.parse_args()
     from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
@@ -59,6 +61,17 @@ def main():
     print(f"kernel time {total / a.steps / 1e3:.3f} ms per step over {sum(v[1] for v in agg.values()) // a.steps} launches ({a.precision}, batch {a.batch})")
     for name, (us, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:a.top]:
         print(f"{us / a.steps:9.1f} us {100 * us / total:5.1f}%  x{cnt // a.steps:4d}  {name}")
+    if a.graphs:
+        evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda ev: ev.time_range.start)
+        evs = evs[len(evs) - len(evs) // a.steps:]
+        span = evs[-1].time_range.end - evs[0].time_range.start
+        busy = sum(ev.time_range.end - ev.time_range.start for ev in evs)
+        gaps = [(evs[i + 1].time_range.start - evs[i].time_range.end, evs[i].name.split("(")[0][:50], evs[i + 1].name.split("(")[0][:50])
+                for i in range(len(evs) - 1)]
+        print(f"last step under graph replay: span {span / 1e3:.3f} ms, kernels {busy / 1e3:.3f} ms, idle {sum(max(g[0], 0) for g in gaps) / 1e3:.3f} ms "
+              f"over {len(gaps)} boundaries (median gap {sorted(g[0] for g in gaps)[len(gaps) // 2]:.2f} us)")
+        for g in sorted(gaps, key=lambda g: -g[0])[:12]:
+            print(f"   gap {g[0]:8.1f} us  after {g[1]}  before {g[2]}")
     if a.list:
         keys = [k for k in a.list.split(",") if k]
         evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda ev: ev.time_range.start)
