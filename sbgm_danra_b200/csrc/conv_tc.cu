@@ -35,6 +35,7 @@ struct ConvTcParams {
   int slab_row;        // slab mode: descriptor units (16 B) per slab row step = pixels per slab row * 8
   uint32_t slab_tx;    // slab mode: bytes per slab plane
   int mt;              // pixel tiles per CTA (1 or 2; 2 = the MT = 2 kernels: two tiles share every weight box)
+  int cluster;         // CTAs per cluster (1 or 2; 2 = slab mode with the weight boxes multicast over a CTA pair)
   int splits;          // split-K factor (gridDim.z); > 1 => raw fp32 partial tiles go to `ws`
   float* ws;           // [splits][pixels][cout] fp32
   float* gn_partials;  // [n][gn_chunks][cout/8][2] or nullptr: fused GroupNorm statistics (8-channel granularity)
@@ -82,7 +83,12 @@ struct ConvTcThreads {
 // MT = pixel tiles per CTA (1 or 2).  With MT = 2 a CTA owns two consecutive 128-pixel tiles that share every weight box: the
 // K-heavy layers are bound by the chip-wide L2 -> SM bandwidth (ncu: ~30 B/clk per SM with all SMs pulling, tensor pipe 25-48 %),
 // and two thirds to nine tenths of their operand bytes are weights that every pixel tile re-fetches.
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false, int MT = 1>
+// CL = CTAs per cluster (1 or 2; slab mode only).  With CL = 2 the two CTAs of a cluster own different pixel tiles of the SAME
+// output-channel block and K range, so they consume the same weight stream: each loads HALF of every weight box and multicasts it
+// into both CTAs' stage (the L2 -> SM weight traffic, two thirds to nine tenths of a K-heavy layer's operand bytes, halves).
+// A weight stage may be rewritten only when BOTH consumers have released it: the MMA issuer's commit arrives on the `empty`
+// barrier of both CTAs (count 2).  The activation slabs and everything else stay per CTA.
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false, int MT = 1, int CL = 1>
 __global__ void __launch_bounds__(ConvTcThreads<BLOCK_N>::kThreads, ConvTcThreads<BLOCK_N>::kMinCtas)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const ConvTcParams p) {
@@ -107,6 +113,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  static_assert(CL == 1 || (CL == 2 && SLAB && !LNF && !PROJ), "clusters: slab mode only");
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -114,7 +122,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       // LNF: the epilogue warps read every A tile too (row statistics) and release the stage together with the MMA
-      mbar_init(empty_bar(s), LNF ? 1 + 4 * ConvTcThreads<BLOCK_N>::kEpiGroups : 1);
+      // CL = 2: the stage is shared by the cluster's two consumers
+      mbar_init(empty_bar(s), LNF ? 1 + 4 * ConvTcThreads<BLOCK_N>::kEpiGroups : CL);
     }
     mbar_init(tmem_full_bar, 1);
     if (SLAB) {
@@ -128,6 +137,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) tmem_alloc(tmem_slot, MT * kAccCols);
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // the peer's barriers exist before anything is multicast into this CTA or arrives on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -172,8 +182,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_expect_tx(full_bar(stage), SCfg::kBStageBytes);
           const uint32_t b_dst = smem_base + SCfg::kBOffset + stage * SCfg::kBStageBytes;
 #pragma unroll
-          for (int pl = 0; pl < kBPl; ++pl)
-            tma_load_3d(b_dst + pl * SCfg::kBBytes, &tmap_b, full_bar(stage), (tap * p.cin_blocks + cb) * 64, co0, pl);
+          for (int pl = 0; pl < kBPl; ++pl) {
+            if (CL > 1)      // this CTA's half of the rows, into both CTAs' stage (tmap_b's box is BLOCK_N / 2 rows)
+              tma_load_3d_multicast(b_dst + pl * SCfg::kBBytes + cta_rank * (BLOCK_N / 2) * 128u, &tmap_b, full_bar(stage),
+                                    (tap * p.cin_blocks + cb) * 64, co0 + static_cast<int>(cta_rank) * (BLOCK_N / 2), pl, 0x3);
+            else
+              tma_load_3d(b_dst + pl * SCfg::kBBytes, &tmap_b, full_bar(stage), (tap * p.cin_blocks + cb) * 64, co0, pl);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -207,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (kAPl == 2) umma_bf16_acc(dm, am + (kSlabPlaneBytes >> 4) + 2 * k, b0 + 2 * k, idesc);
             }
           }
-          umma_commit(empty_bar(stage));
+          if (CL > 1) umma_commit_multicast(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(slab_empty(as));
@@ -408,6 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // no CTA retires while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, MT * kAccCols);
 }
 
@@ -555,7 +571,7 @@ void pick_tile(int n, int ho, int wo, int* wt, int* ht, int* nt) {
   (void)pow2_floor;
 }
 
-template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false, int MT = 1>
+template <int FMT, int BLOCK_N, int kStages, int ACT, int PROJ, bool STAGED, bool SLAB = false, bool LNF = false, int MT = 1, int CL = 1>
 static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvTcParams& p, int m_tiles,
                                cudaStream_t st) {
   constexpr int kAPl = TcFmt<FMT>::kAPlanes, kBPl = TcFmt<FMT>::kBPlanes;
@@ -563,7 +579,7 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
   static_assert(!STAGED || Cfg::kBarOffset >= 4u * (BLOCK_N / 64) * kAPl * kStageBlockBytes, "the staging area must fit in the pipeline stages");
   static_assert(MT * kBPl * BLOCK_N <= 512, "accumulator exceeds the 512 TMEM columns");
   static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
-  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED, SLAB, LNF, MT>;
+  auto kern = conv_tc_kernel<FMT, BLOCK_N, kStages, ACT, PROJ, STAGED, SLAB, LNF, MT, CL>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -577,7 +593,12 @@ static int launch_conv_tc_inst(const CUtensorMap& ta, const CUtensorMap& tb, con
     return 1;
   }
   dim3 grid((m_tiles + MT - 1) / MT, p.ep.cout / BLOCK_N, p.splits);
-  launch_k((kern), grid, ConvTcThreads<BLOCK_N>::kThreads, Cfg::kSmemBytes, st, ta, tb, to, p);
+  if (CL > 1) {        // whole clusters: a CTA past the last pixel tile computes on zero-filled operands and stores nothing
+    grid.x = (grid.x + CL - 1) / CL * CL;
+    launch_k_cluster((kern), grid, ConvTcThreads<BLOCK_N>::kThreads, Cfg::kSmemBytes, st, CL, ta, tb, to, p);
+  } else {
+    launch_k((kern), grid, ConvTcThreads<BLOCK_N>::kThreads, Cfg::kSmemBytes, st, ta, tb, to, p);
+  }
   if (!PROJ && p.splits > 1) {
     const size_t pixels = static_cast<size_t>(p.n) * p.ho * p.wo;
     const size_t items = pixels * (p.ep.cout / 8);
@@ -624,8 +645,12 @@ static int launch_conv_tc_slab(const CUtensorMap& ta, const CUtensorMap& tb, con
     if constexpr (TcFmt<FMT>::kAPlanes == 1 && BLOCK_N <= 128) {
       if (p.mt == 2) {       // two halo slabs per A stage (2 x 2 x 25.6 KB) + the weight ring
         constexpr int kS2 = (TcFmt<FMT>::kBPlanes == 2 && BLOCK_N == 128) ? 3 : 4;
+        if (p.cluster == 2)
+          SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kS2, ACT, 0, true, true, false, 2, 2>(ta, tb, to, p, m_tiles, st)));
         SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kS2, ACT, 0, true, true, false, 2>(ta, tb, to, p, m_tiles, st)));
       }
+      if (p.cluster == 2)
+        SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kBStages, ACT, 0, true, true, false, 1, 2>(ta, tb, to, p, m_tiles, st)));
     }
     SBGM_DISPATCH_ACT(p.ep.act, return (launch_conv_tc_inst<FMT, BLOCK_N, kBStages, ACT, 0, true, true>(ta, tb, to, p, m_tiles, st)));
   }
@@ -789,12 +814,26 @@ static int conv2d_tc_impl(const void* in, size_t in_plane, const void* weight, s
     const long long ctas = static_cast<long long>(m_tiles) * (cout / block_n);
     if (allowed && mt_mode != 1 && (mt_mode == 2 || ctas >= 252)) p.mt = 2;
   }
+  // Weight multicast over a CTA pair (CL = 2) in slab mode: both CTAs stream the same weight boxes (same output-channel block,
+  // same K range), each loads half and multicasts it.  Single-plane activations, staged store, at least one full pair of CTAs
+  // along the pixel tiles.  Measured per layer on the C2 forward (profiles/r02_conv_tc_family_table_fp16x2_cluster.txt against
+  // ..._mt2_first.txt): the pair runs in lock step, so it pays only where the weight stream is what the layer waits for --
+  // 512 -> 512 at 8 x 8: 40.4 -> 36.6 us (478 -> 528 TFLOP/s); the 128- and 256-channel layers are within +-1.5 us either way
+  // (sum over the family 551.6 -> 555.7 us with the pair everywhere).  Default: pairs for cin, cout >= 512 only.
+  // SBGM_B200_CLUSTER: 0 = never, 2 = wherever the kernel allows it, unset = by layer size.
+  p.cluster = 1;
+  {
+    static const int cl_mode = [] { const char* e = getenv("SBGM_B200_CLUSTER"); return e == nullptr ? 1 : atoi(e); }();
+    const int ctas_x = (m_tiles + p.mt - 1) / p.mt;
+    const bool allowed = slab && planes == 1 && p.ep.staged && proj_w == nullptr && ln_colsum == nullptr && block_n <= 128 && ctas_x >= 2;
+    if (allowed && cl_mode != 0 && (cl_mode == 2 || (cin >= 512 && cout >= 512))) p.cluster = 2;
+  }
   CUtensorMap ta, tb, to;
   if (slab ? (slab_perm ? encode_perm_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, 2, 10)
                         : encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, kSlabW, kSlabH, 1, 1))
            : encode_act_map(&ta, in, planes, in_plane, n, h, w, cin, p.w_tile, p.h_tile, p.n_tile, stride)) return 1;
   const int K = kh * kw * cin;
-  if (encode_weight_map(&tb, weight, w_planes, w_plane, cout, K, block_n)) return 1;
+  if (encode_weight_map(&tb, weight, w_planes, w_plane, cout, K, block_n / p.cluster)) return 1;     // a pair's CTA loads half the rows
   if (p.ep.staged) {
     if (slab && slab_perm ? encode_perm_map(&to, out, planes, out_plane, n, ho, wo, cout, 8, 2, 2)
                           : encode_out_map(&to, out, planes, out_plane, n, ho, wo, cout, p.w_tile, p.h_tile, p.n_tile)) return 1;

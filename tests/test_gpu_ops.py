@@ -127,6 +127,10 @@ CONV_CASES = [
     (5, 8, 8, 512, 512, 3, 1, 1, "full"),         # same with an odd image count and split-K over channel blocks
     (3, 24, 8, 128, 128, 3, 1, 1, "relu"),        # 24 rows: 8-row tiles
     (33, 8, 16, 192, 64, 3, 1, 1, "plain"),
+    # weight multicast over a CTA pair (slab mode, cin / cout >= 512, single-plane formats): two-image tiles, and an ODD number
+    # of pixel tiles (the pair's second CTA of the last cluster has no tile)
+    (64, 8, 8, 512, 512, 3, 1, 1, "full"),
+    (19, 16, 8, 512, 512, 3, 1, 1, "relu"),
 ]
 
 
