@@ -42,11 +42,17 @@ struct WgradCfg {
 __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | ((kBoxBytes >> 4) << 16); }
 __device__ __forceinline__ constexpr uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
 
-template <int FMT, int BN, int kStages>
+// CL = CTAs per cluster along x (1 or 2).  The CTAs of a row of the grid (different (tap, channel-block) units, same output
+// channels, same pixel range) all consume the SAME dy tiles: with CL = 2 a pair loads one dy box each (BN = 128: two 64-channel
+// boxes per stage) and multicasts it into both CTAs' stage, halving the dy traffic out of L2.  A stage is released by both
+// consumers (count 2).  An experiment that did not pay (see the launcher): kept opt-in.
+template <int FMT, int BN, int kStages, int CL = 1>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const WgradParams p) {
   pdl_grid_sync();
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
+  static_assert(CL == 1 || (CL == 2 && kSplit * (BN / 64) == 2), "pairs split the stage's two dy boxes");
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
   using Cfg = WgradCfg<kSplit, BN, kStages>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -63,7 +69,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     tma_prefetch_desc(&tmap_dy);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -71,11 +77,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   if (warp == 1) tmem_alloc(tmem_slot, kSplit * BN);
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int u0 = blockIdx.x * 2;
-  const bool second = (u0 + 1) < p.units;
+  // a CTA past the last unit pair (the grid is padded to whole clusters) loads its share of dy, computes on unit 0 and stores nothing
+  const bool phantom = static_cast<int>(blockIdx.x) * 2 >= p.units;
+  const int u0 = phantom ? 0 : blockIdx.x * 2;
+  const bool second = !phantom && (u0 + 1) < p.units;
   const int u1 = second ? u0 + 1 : u0;
   const int co0 = blockIdx.y * BN;
   const int tile_begin = blockIdx.z * p.tiles_per_split;
@@ -107,8 +116,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             tma_load_5d(a_dst + (pl * 2 + i) * kBoxBytes, &tmap_x, full_bar(stage), cb_[i] * 64, wo0 * p.stride + s_[i] - p.pad,
                         ho0 * p.stride + r_[i] - p.pad, n0, pl);
 #pragma unroll
-          for (int ch = 0; ch < BN / 64; ++ch)
-            tma_load_5d(b_dst + (pl * (BN / 64) + ch) * kBoxBytes, &tmap_dy, full_bar(stage), co0 + ch * 64, wo0, ho0, n0, pl);
+          for (int ch = 0; ch < BN / 64; ++ch) {
+            const int box = pl * (BN / 64) + ch;
+            if (CL > 1) {
+              if (box == static_cast<int>(cta_rank))
+                tma_load_5d_multicast(b_dst + box * kBoxBytes, &tmap_dy, full_bar(stage), co0 + ch * 64, wo0, ho0, n0, pl, 0x3);
+            } else {
+              tma_load_5d(b_dst + box * kBoxBytes, &tmap_dy, full_bar(stage), co0 + ch * 64, wo0, ho0, n0, pl);
+            }
+          }
         }
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
@@ -134,7 +150,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             else umma_bf16_acc(tmem_base, a0 + j * 128, b0 + j * 128, idesc);
           }
         }
-        umma_commit(empty_bar(stage));
+        if (CL > 1) umma_commit_multicast(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
         if (tile == tile_end - 1) umma_commit(tmem_full_bar);
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
@@ -144,7 +160,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int unit = (row < 64) ? u0 : u1;
-    const bool valid = (row < 64) || second;
+    const bool valid = !phantom && ((row < 64) || second);
     const size_t kcol = static_cast<size_t>(unit) * 64 + (row & 63);
     float* dst = p.ws + (static_cast<size_t>(blockIdx.z) * p.cout + co0) * p.K + kcol;
     mbar_wait(tmem_full_bar, 0);
@@ -168,6 +184,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   if (warp == 1) tmem_dealloc(tmem_base, kSplit * BN);
 }
 
@@ -197,11 +214,11 @@ static void wgrad_tc_plan(int n, int ho, int wo, int cin, int cout, int kh, int 
   *splits = (p->total_tiles + p->tiles_per_split - 1) / p->tiles_per_split;
 }
 
-template <int FMT, int BN, int kStages>
+template <int FMT, int BN, int kStages, int CL = 1>
 static int launch_wgrad_tc(const CUtensorMap& tx, const CUtensorMap& td, const WgradParams& p, int splits, cudaStream_t st) {
   constexpr int kSplit = (FMT == SBGM_FMT_BF16X2) ? 2 : 1;
   using Cfg = WgradCfg<kSplit, BN, kStages>;
-  auto kern = conv_wgrad_tc_kernel<FMT, BN, kStages>;
+  auto kern = conv_wgrad_tc_kernel<FMT, BN, kStages, CL>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
@@ -211,7 +228,12 @@ static int launch_wgrad_tc(const CUtensorMap& tx, const CUtensorMap& td, const W
     configured = true;
   }
   dim3 grid((p.units + 1) / 2, p.cout / BN, splits);
-  launch_k((kern), grid, 192, Cfg::kSmemBytes, st, tx, td, p);
+  if (CL > 1) {
+    grid.x = (grid.x + CL - 1) / CL * CL;
+    launch_k_cluster((kern), grid, 192, Cfg::kSmemBytes, st, CL, tx, td, p);
+  } else {
+    launch_k((kern), grid, 192, Cfg::kSmemBytes, st, tx, td, p);
+  }
   return check_launch("conv2d_wgrad_tc");
 }
 
@@ -259,9 +281,15 @@ extern "C" int sbgm_conv2d_wgrad_tc(const void* x, size_t x_plane, const void* d
   if (encode_act_map(&td, dy, planes, dy_plane, n, ho, wo, cout, p.w_tile, p.h_tile, p.n_tile, 1)) return 1;
   cudaStream_t st = as_stream(stream);
   int rc;
-  if (fmt == SBGM_FMT_BF16) rc = (bn == 128) ? launch_wgrad_tc<SBGM_FMT_BF16, 128, 3>(tx, td, p, splits, st)
+  // dy multicast over CTA pairs where a stage holds two dy boxes and there are at least two unit pairs.  Measured SLOWER on the C4
+  // step (30 paired launches 407 us + 6 unpaired 34 us against 364 us for the 36 unpaired; step 5.78 vs 5.66-5.77 ms): the pair
+  // runs in lock step and the kernel is not waiting for L2 bandwidth.  Opt-in: SBGM_B200_WGRAD_CLUSTER=1.
+  static const bool pairs_on = [] { const char* e = getenv("SBGM_B200_WGRAD_CLUSTER"); return e != nullptr && e[0] == '1'; }();
+  const bool pairs = pairs_on && p.units >= 3;
+  if (fmt == SBGM_FMT_BF16) rc = (bn == 128) ? (pairs ? launch_wgrad_tc<SBGM_FMT_BF16, 128, 3, 2>(tx, td, p, splits, st)
+                                                      : launch_wgrad_tc<SBGM_FMT_BF16, 128, 3>(tx, td, p, splits, st))
                                              : launch_wgrad_tc<SBGM_FMT_BF16, 64, 4>(tx, td, p, splits, st);
-  else rc = launch_wgrad_tc<SBGM_FMT_BF16X2, 64, 2>(tx, td, p, splits, st);
+  else rc = pairs ? launch_wgrad_tc<SBGM_FMT_BF16X2, 64, 2, 2>(tx, td, p, splits, st) : launch_wgrad_tc<SBGM_FMT_BF16X2, 64, 2>(tx, td, p, splits, st);
   if (rc) return rc;
   if (dweight_oihw == nullptr) return 0;      // the caller sums the slabs later (sbgm_wgrad_reduce_batch)
   return sbgm_wgrad_reduce(workspace, splits, cout, kh * kw, cin, dweight_oihw, stream);
