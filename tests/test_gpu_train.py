@@ -242,13 +242,20 @@ def test_conv_backward(E, T, prec, case):
 
 
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
-def test_wgrad_tc_matches_simt(E, prec):
+@pytest.mark.parametrize("geom", [(4, 32, 32, 64, 64, 3, 1, 1),
+                                  # bf16: the halo-slab kernel (3x3 / stride 1, maps tileable by 16 rows x 8 columns) -- two channel
+                                  # blocks, two output blocks, one tile per image, an odd image count over several pixel splits
+                                  (3, 16, 8, 128, 128, 3, 1, 1), (5, 48, 24, 64, 192, 3, 1, 1), (2, 32, 32, 256, 64, 3, 1, 1),
+                                  (2, 24, 16, 64, 64, 3, 1, 1),          # 24 rows: not slab-tileable, the per-unit kernel
+                                  (2, 16, 16, 64, 128, 3, 2, 1)])        # strided: the per-unit kernel
+def test_wgrad_tc_matches_simt(E, prec, geom):
     """The tensor-core weight gradient against the CUDA-core one on identical stored operands."""
     from sbgm_danra_b200 import _lib
     from sbgm_danra_b200._lib import call
     fmt = FMTS[prec]
-    n, h, w, cin, cout, k, stride, pad = 4, 32, 32, 64, 64, 3, 1, 1
-    xa, da = act_of(E, gen(n, cin, h, w, seed=1), fmt), act_of(E, gen(n, cout, h, w, seed=2), fmt)
+    n, h, w, cin, cout, k, stride, pad = geom
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    xa, da = act_of(E, gen(n, cin, h, w, seed=1), fmt), act_of(E, gen(n, cout, ho, wo, seed=2), fmt)
     st = torch.cuda.current_stream().cuda_stream
     out = []
     for name in ("tc", "simt"):
