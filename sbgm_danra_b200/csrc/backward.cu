@@ -611,10 +611,16 @@ __global__ void chansum_finish_kernel(const float* __restrict__ partials, int n,
   if (ch >= c) return;
   float tot = 0.0f;
   if (out_n) {
-    for (int k = 0; k < n; ++k) {
-      const float s = warp_sum(lane < chunks ? partials[(static_cast<size_t>(k) * chunks + lane) * c + ch] : 0.0f);
-      if (lane == 0) out_n[static_cast<size_t>(k) * out_n_stride + ch] = s;
-      tot += s;
+    // per-sample sums: lanes over the samples, each adds its sample's chunks (a loop of 64 warp reductions in sequence was a
+    // 30 us kernel for 16 KB of partials); the total adds the per-sample sums in lane order
+    for (int k0 = 0; k0 < n; k0 += 32) {
+      const int k = k0 + lane;
+      float s = 0.0f;
+      if (k < n) {
+        for (int q = 0; q < chunks; ++q) s += partials[(static_cast<size_t>(k) * chunks + q) * c + ch];
+        out_n[static_cast<size_t>(k) * out_n_stride + ch] = s;
+      }
+      tot += warp_sum(s);
     }
   } else {
     for (int k = lane; k < n * chunks; k += 32) tot += partials[static_cast<size_t>(k) * c + ch];
@@ -746,7 +752,8 @@ __global__ void upsample2x_bwd_kernel(const void* __restrict__ dy, size_t dy_pla
 // h = silu(e),  out[n][col] = b[col] + sum_k h_{set(col)}[n][k] * W[col][k].
 // (1) e -> workspace;  (2) dW, db per column;  (3) d(label_emb) through set 0.
 __global__ void time_embed_bwd_embed_kernel(const float* __restrict__ t, const int64_t* __restrict__ y, const float* __restrict__ fw,
-                                            int n_sets, int te, const float* __restrict__ label_emb, float* __restrict__ e_ws) {
+                                            int n_sets, int te, const float* __restrict__ label_emb, float* __restrict__ e_ws,
+                                            float* __restrict__ h_ws) {
   pdl_grid_sync();
   const int row = blockIdx.x, half = te / 2, rows = gridDim.x;
   const float tv = t[row];
@@ -762,18 +769,21 @@ __global__ void time_embed_bwd_embed_kernel(const float* __restrict__ t, const i
     float* e = e_ws + (static_cast<size_t>(s) * rows + row) * te;
     e[j] = sv;
     e[half + j] = cv;
+    float* hh = h_ws + (static_cast<size_t>(s) * rows + row) * te;     // h = silu(e): every output column re-used it 1 700 times
+    hh[j] = silu(sv);
+    hh[half + j] = silu(cv);
   }
 }
 // one block per output column; threads over k
-__global__ void time_embed_bwd_weight_kernel(const float* __restrict__ dout, int c_total, const float* __restrict__ e_ws, int rows, int te,
+__global__ void time_embed_bwd_weight_kernel(const float* __restrict__ dout, int c_total, const float* __restrict__ h_ws, int rows, int te,
                                              const int32_t* __restrict__ pset, float* __restrict__ dW, float* __restrict__ db) {
   pdl_grid_sync();
   const int col = blockIdx.x;
-  const float* e = e_ws + static_cast<size_t>(pset[col]) * rows * te;
+  const float* hh = h_ws + static_cast<size_t>(pset[col]) * rows * te;
   for (int k = threadIdx.x; k < te; k += blockDim.x) {
     float acc = 0.0f;
 #pragma unroll 8
-    for (int r = 0; r < rows; ++r) acc = fmaf(dout[static_cast<size_t>(r) * c_total + col], silu(e[static_cast<size_t>(r) * te + k]), acc);
+    for (int r = 0; r < rows; ++r) acc = fmaf(dout[static_cast<size_t>(r) * c_total + col], hh[static_cast<size_t>(r) * te + k], acc);
     dW[static_cast<size_t>(col) * te + k] = acc;
   }
   if (threadIdx.x == 0) {
@@ -1042,7 +1052,7 @@ int sbgm_upsample2x_backward(const void* dy, size_t dy_plane, void* dx, size_t d
 }
 
 size_t sbgm_time_embed_backward_scratch_floats(int n_sets, int te, int rows) {
-  return static_cast<size_t>(n_sets) * rows * te + static_cast<size_t>(rows) * te;
+  return static_cast<size_t>(2) * n_sets * rows * te + static_cast<size_t>(rows) * te;
 }
 
 int sbgm_time_embed_backward(const float* dout, const float* t, const int64_t* y, const float* fourier_w, int n_sets, int te,
@@ -1051,9 +1061,10 @@ int sbgm_time_embed_backward(const float* dout, const float* t, const int64_t* y
   SBGM_REQUIRE(te % 2 == 0 && n_sets >= 1 && rows >= 1, "time_embed_backward: bad sizes");
   cudaStream_t st = as_stream(stream);
   float* e_ws = scratch;
-  float* de0 = scratch + static_cast<size_t>(n_sets) * rows * te;
-  launch_k((time_embed_bwd_embed_kernel), rows, 256, 0, st, t, y, fourier_w, n_sets, te, label_emb, e_ws);
-  launch_k((time_embed_bwd_weight_kernel), c_total, 256, 0, st, dout, c_total, e_ws, rows, te, proj_set, d_proj_w, d_proj_b);
+  float* h_ws = scratch + static_cast<size_t>(n_sets) * rows * te;
+  float* de0 = h_ws + static_cast<size_t>(n_sets) * rows * te;
+  launch_k((time_embed_bwd_embed_kernel), rows, 256, 0, st, t, y, fourier_w, n_sets, te, label_emb, e_ws, h_ws);
+  launch_k((time_embed_bwd_weight_kernel), c_total, 256, 0, st, dout, c_total, h_ws, rows, te, proj_set, d_proj_w, d_proj_b);
   if (d_label_emb != nullptr && y != nullptr) {
     launch_k((time_embed_bwd_input_kernel), dim3(rows, ceil_div(te, 16)), 256, 0, st, dout, c_total, e_ws, te, proj_set, proj_w, de0);
     launch_k((label_emb_bwd_kernel), n_classes, 256, 0, st, de0, y, rows, te, d_label_emb);
