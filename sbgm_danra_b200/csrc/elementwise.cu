@@ -622,14 +622,17 @@ int sbgm_groupnorm(const void* x, size_t x_plane, const float* gamma, const floa
   const int lanes = 256 / vecs;
   const size_t smem1 = (static_cast<size_t>(lanes) + 1) * c * 2 * sizeof(float);
   const size_t smem2 = (static_cast<size_t>(c) + groups) * 2 * sizeof(float);
-  dim3 g1(kGnChunks, n);
+  // ~8 pixels per thread, at most kGnChunks chunks: the 8 x 8 x 512 map of the first decoder block was 32 chunks of TWO pixels
+  // (2 048 blocks that mostly synchronise: 13.7 us for 4 MB)
+  const int chunks = sbgm_norm_partials_chunks(hw, c);
+  dim3 g1(chunks, n);
   int slots = 148 * 8;
   SBGM_DISPATCH_FMT(fmt, (slots = resident_blocks(reinterpret_cast<const void*>(gn_apply_kernel<FMT>), 256, smem2)));
   const int per_n_blocks = max(1, min(ceil_div(static_cast<long long>(hw) * vecs, 256 * 4), slots / max(n, 1)));
   dim3 g2(per_n_blocks, n);
   SBGM_DISPATCH_FMT(fmt, {
-    launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, st, x, x_plane, hw, c, groups, partials, kGnChunks);
-    launch_k((gn_apply_kernel<FMT>), g2, 256, smem2, st, x, x_plane, partials, kGnChunks, groups, gamma, beta, groups, eps, skip,
+    launch_k((gn_partial_kernel<FMT>), g1, 256, smem1, st, x, x_plane, hw, c, groups, partials, chunks);
+    launch_k((gn_apply_kernel<FMT>), g2, 256, smem2, st, x, x_plane, partials, chunks, groups, gamma, beta, groups, eps, skip,
                                                   skip_plane, tproj, tproj_stride, act, y, y_plane, hw, c);
   });
   return check_launch("groupnorm");
