@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--members", type=int, default=64)
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--list", default="", help="comma-separated kernel-name substrings: print every matching launch of the LAST step, in order")
     a = ap.parse_args()
     from sbgm_danra_b200.synth import config_for, synth_batch, synth_state_dict
     from sbgm_danra_b200 import score_sampling as ss
@@ -47,6 +48,14 @@ def main():
           f"sum of kernel durations {busy / a.steps:.1f} us per step over {len(evs) / a.steps:.1f} launches per step")
     for name, (us, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:a.top]:
         print(f"{us / a.steps:9.1f} us {100 * us / busy:5.1f}%  x{cnt / a.steps:5.1f}  {name}")
+    if a.list:
+        keys = [k for k in a.list.split(",") if k]
+        # the last step = everything after the second-to-last predictor kernel
+        pred = [i for i, ev in enumerate(evs) if "predictor_kernel" in ev.name]
+        last = evs[pred[-2] + 1:] if len(pred) >= 2 else evs
+        for i, ev in enumerate(last):
+            if any(k in ev.name for k in keys):
+                print(f"  #{i:3d} {ev.time_range.end - ev.time_range.start:8.1f} us  {ev.name.split('(')[0][:70]}")
 
 
 if __name__ == "__main__":
