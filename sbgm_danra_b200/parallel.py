@@ -29,6 +29,11 @@ import torch.distributed as dist
 BUCKET_BYTES = 32 << 20
 
 
+def _produced_last(name: str) -> bool:
+    """Parameters whose gradients come out of the final kernels of TrainEngine.backward (one launch set for all of them)."""
+    return "time_projection_layer" in name or name.endswith("label_emb.weight")
+
+
 class GradBucketer:
     """Tracks which contiguous buckets of a flat gradient buffer are complete.
 
@@ -40,11 +45,24 @@ class GradBucketer:
         # Walk from the END of the buffer (filled first by backward) in full-sized buckets; the START of the buffer holds what
         # backward produces last (stem, time projections), so the lowest buckets are made SMALL (1/32 and 1/8 of a bucket): the
         # only exchange that cannot hide behind remaining backward kernels is then ~1 MB instead of whatever the walk left over.
+        # The very first bucket is exactly the group that the LAST kernels of backward produce in one go (time projections and
+        # label embedding: train_engine.flat_order puts them first): mixed into a size-cut bucket they held back the stem /
+        # layer-1 gradients that were ready 50 us earlier, and two exchanges (4.2 MB + 1.0 MB) ran after backward instead of one.
         tail_sizes = [max(1, bucket_elems // 32), max(1, bucket_elems // 8)]
         head_edges, acc, k = [0], 0, 0
+        late_end = 0
+        for name, off, numel in self.layout:
+            if _produced_last(name):
+                late_end = min(total, off + (numel + 63) // 64 * 64)
+            else:
+                break
+        if late_end > 0:
+            head_edges.append(late_end)
         for name, off, numel in self.layout:
             if k >= len(tail_sizes):
                 break
+            if off < late_end:
+                continue
             acc += numel
             if acc >= tail_sizes[k]:
                 head_edges.append(off + (numel + 63) // 64 * 64 if off + (numel + 63) // 64 * 64 <= total else total)

@@ -29,6 +29,8 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=64, help="global batch (strong scaling) or per-GPU batch with --weak")
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--weak", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="rank 0: profile three more steps and print the NCCL kernels' durations, "
+                    "the span of a step and the largest gaps between consecutive kernels")
     ap.add_argument("--optimizer", default="one-launch", choices=["one-launch", "torch"],
                     help="sbgm_danra_b200.optim.Adam (torch.optim.Adam with a single-kernel step) or torch's own foreach Adam")
     args = ap.parse_args()
@@ -98,6 +100,31 @@ def main() -> None:
                "rank0_ms": {"loss_fn_forward": split[0] / args.steps, "backward": split[1] / args.steps, "adam": split[2] / args.steps},
                "loss": float(loss), "grad_buckets": None if sync is None else sync.stats}
         print(json.dumps(out))
+    if args.timeline and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step(False)
+            torch.cuda.synchronize()
+        evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda ev: ev.time_range.start)
+        evs = evs[len(evs) - len(evs) // 3:]
+        span = evs[-1].time_range.end - evs[0].time_range.start
+        nccl = [ev for ev in evs if "nccl" in ev.name.lower()]
+        rest = [ev for ev in evs if "nccl" not in ev.name.lower()]
+        busy = sum(ev.time_range.end - ev.time_range.start for ev in rest)
+        print(f"[timeline] last step: span {span / 1e3:.3f} ms, non-NCCL kernel time {busy / 1e3:.3f} ms over {len(rest)} launches", file=sys.stderr)
+        t0 = evs[0].time_range.start
+        for ev in nccl:
+            print(f"[timeline]   NCCL {ev.name.split('(')[0][:60]}: start {(ev.time_range.start - t0) / 1e3:.3f} ms, {(ev.time_range.end - ev.time_range.start):.1f} us",
+                  file=sys.stderr)
+        gaps = sorted(((rest[i + 1].time_range.start - rest[i].time_range.end, (rest[i].time_range.end - t0) / 1e3, rest[i].name.split("(")[0][:40],
+                        rest[i + 1].name.split("(")[0][:40]) for i in range(len(rest) - 1)), reverse=True)[:8]
+        for g, at, a_, b_ in gaps:
+            print(f"[timeline]   gap {g:7.1f} us at {at:.3f} ms after {a_} before {b_}", file=sys.stderr)
+    elif args.timeline and world > 1:
+        for _ in range(3):
+            step(False)
+        torch.cuda.synchronize()
     if world > 1:
         # the captured backward graph holds NCCL all-reduces: drop it before the communicator goes away and skip the
         # interpreter teardown (destroying a communicator that graphs still reference can block)
