@@ -241,6 +241,42 @@ def test_flat_gradient_buffer_is_in_forward_order():
         assert last(a) < first(b), (a, b)
     tail = [k for k in names if "time_projection_layer" in k or k.endswith("label_emb.weight")]
     assert tail and max(pos[k] for k in tail) < first("encoder.conv1.")
+    # the projection weights, then the biases, each one contiguous run in head order (encoder 0..4, decoder blocks, then the
+    # final layer's unused one): TrainEngine.backward lets the time-embedding kernel write the nine used ones in place
+    tw = [k for k in order if "time_projection_layer" in k and k.endswith(".weight")]
+    tb = [k for k in order if "time_projection_layer" in k and k.endswith(".bias")]
+    assert len(tw) == len(tb) == 10 and tw[-1].startswith("decoder.final_layer.")
+    assert [pos[k] for k in tw] == list(range(pos[tw[0]], pos[tw[0]] + 10)) and [pos[k] for k in tb] == list(range(pos[tb[0]], pos[tb[0]] + 10))
+    assert pos[tw[-1]] < pos[tb[0]] and [k.replace(".weight", "") for k in tw] == [k.replace(".bias", "") for k in tb]
+
+
+def test_bucketer_gives_the_last_produced_gradients_their_own_first_bucket():
+    """The gradients that backward's final kernels produce together (time projections, label embedding) must not share a bucket
+    with gradients that are ready earlier: that bucket could only be exchanged after backward (measured: 75 us exposed)."""
+    from sbgm_danra_b200.parallel import GradBucketer
+    from sbgm_danra_b200.synth import config_for, param_schema
+    from sbgm_danra_b200.train_engine import flat_order
+    cfg = config_for(n_lr=2, geo=True, seasons=True)
+    schema = param_schema(cfg)
+    names = flat_order([k for k in schema if not k.endswith(("running_mean", "running_var", "num_batches_tracked", ".W"))])
+    layout, off = [], 0
+    for k in names:
+        n = 1
+        for d in schema[k]:
+            n *= d
+        layout.append((k, off, n))
+        off += (n + 63) // 64 * 64
+    b = GradBucketer(layout, off, bucket_elems=(32 << 20) // 4, expected=names)
+    late = [k for k in names if "time_projection_layer" in k or k.endswith("label_emb.weight")]
+    first_bucket = {k for k in names if b.bucket_of[k] == 0}
+    assert first_bucket == set(late)
+    assert b.bounds[0][1] == max(o + (n + 63) // 64 * 64 for k, o, n in layout if k in first_bucket)
+    # backward order: everything else first (decoder ... stem), the late group at the very end -> only bucket 0 is left for the end
+    fired = []
+    for k in reversed([k for k in names if k not in first_bucket]):
+        fired += b.touch([k])
+    assert sorted(fired) == list(range(1, len(b.bounds)))
+    assert b.touch(late) == [0]
 
 
 def test_broadcast_style_write_invalidates_engine_cache_key():
