@@ -139,6 +139,14 @@ int sbgm_conv3x3_c64(const void* in, size_t in_plane, const void* weight, size_t
                      const void* residual, size_t res_plane, const float* tproj, int tproj_stride,
                      void* out, size_t out_plane, int fmt, int n, int h, int w, int act,
                      const float* proj_w, int n_proj, float* proj_out, float* gn_partials, int gn_cpg, void* stream);
+/* The same convolution over upsample2x(x), x = [n][h/2][w/2][64]: the bilinear F.interpolate(scale_factor=2, align_corners=False)
+ * that opens every decoder block and the final layer (score_unet.py:560-570, :652-659) is produced inside the kernel's operand
+ * stage (TMA loads the tile's low-resolution patch, producer warps interpolate the halo slab into the swizzled operand layout):
+ * the 4x larger upsampled tensor is never written.  h, w are the OUTPUT (high-resolution) size; bias-only epilogue (act = none),
+ * optionally with the projection or the GroupNorm statistics.  Single-plane formats only (SBGM_FMT_BF16, SBGM_FMT_F16). */
+int sbgm_conv3x3_c64_up(const void* x, size_t x_plane, const void* weight, size_t w_plane, const float* bias, void* out,
+                        size_t out_plane, int fmt, int n, int h, int w, int act, const float* proj_w, int n_proj,
+                        float* proj_out, float* gn_partials, int gn_cpg, void* stream);
 /* Projection epilogue (proj_w != NULL, cout == 64 only): instead of storing the 64 output channels the
  * kernel stores proj_out[pix][SBGM_PROJ_STRIDE] = sum_c v[c] * proj_w[q][c] for q < n_proj (fp32) -- the
  * nine per-tap partial products of the final 64 -> 1 convolution, so its input never touches HBM.

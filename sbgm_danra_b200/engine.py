@@ -49,6 +49,7 @@ import os as _os
 _SKIP = frozenset(x for x in _os.environ.get("SBGM_B200_SKIP", "").split(",") if x)
 _STEM_FUSED = _os.environ.get("SBGM_B200_STEM_FUSED", "1") != "0"     # 0: stem as im2col tensor + 1x1 convolution
 _LN_FOLD = _os.environ.get("SBGM_B200_LN_FOLD", "1") != "0"           # 0: LayerNorm as its own kernel in front of in_proj / ff.0
+_UP_FUSED = _os.environ.get("SBGM_B200_UP_FUSED", "1") != "0"         # 0: the bilinear upsample ahead of a 64 -> 64 conv_up as its own launch
 _ATTN_FUSED = _os.environ.get("SBGM_B200_ATTN_FUSED", "auto")         # 0: attention core and out-projection as two launches
 
 
@@ -324,6 +325,35 @@ class Kernels:
              _ptr(tproj), tproj.stride(0) if tproj is not None else 0, act, out.ptr, out.plane, self.fmt,
              x.n, x.h * x.w, x.c, self._gn_scratch.data_ptr(), _stream())
         return out
+
+    def up_fused_ok(self, x: Act, cw: ConvW) -> bool:
+        """True if conv3x3(upsample2x(x)) runs as ONE kernel (sbgm_conv3x3_c64_up): a 64 -> 64 convolution in a single-plane format."""
+        return (_UP_FUSED and self.fmt in (FMT_BF16, FMT_F16) and x.c == 64 and cw.cin == 64 and cw.cout == 64 and cw.kh == 3
+                and cw.kw == 3 and (2 * x.h) % 16 == 0 and (2 * x.w) % 8 == 0 and not _SKIP)
+
+    def conv_up_fused(self, x: Act, cw: ConvW, proj: Optional[torch.Tensor] = None, gn_stats: bool = False):
+        """conv3x3(upsample2x(x)) with the bilinear resize inside the kernel's operand stage.  Returns like `conv`: the projected
+        tensor (`proj`), (Act, stats) (`gn_stats`) or the Act."""
+        h, w = 2 * x.h, 2 * x.w
+        if CONV_TRACE is not None:
+            CONV_TRACE.append(dict(n=x.n, h=h, w=w, cw=cw, stride=1, pad=1, act=ACT_NONE, residual=False, tproj=False,
+                                   proj=proj is not None, gn_stats=gn_stats, c64=True, up_fused=True))
+        out, pout, part, stats = None, None, None, None
+        if proj is not None:
+            pout = torch.empty((x.n, h, w, _lib.PROJ_STRIDE), dtype=torch.float32, device=self.device)
+            pargs = (proj.data_ptr(), proj.shape[0], pout.data_ptr())
+        else:
+            out = Act(self.fmt, x.n, h, w, cw.cout, self.device)
+            pargs = (None, 0, None)
+            if gn_stats:
+                chunks = (h // 16) * (w // 8) * 4
+                part = torch.empty((x.n, chunks, 8, 2), dtype=torch.float32, device=self.device)
+                stats = (part, chunks)
+        call("sbgm_conv3x3_c64_up", x.ptr, x.plane, cw.w.data_ptr(), cw.plane, _ptr(cw.bias), None if out is None else out.ptr,
+             0 if out is None else out.plane, self.fmt, x.n, h, w, ACT_NONE, *pargs, _ptr(part), 8, _stream())
+        if proj is not None:
+            return pout
+        return (out, stats) if gn_stats else out
 
     def affine(self, x: Act, skip: Optional[Act] = None, tproj: Optional[torch.Tensor] = None, act: int = ACT_NONE) -> Act:
         """act(x + skip + tproj): the epilogue of a decoder block whose norm is nn.Identity (score_unet.py:593-612), as the
@@ -650,7 +680,9 @@ class DecoderEngine:
         rev = list(reversed(fmaps))
         out = rev[0]
         for i, blk in enumerate(self.blocks):
-            if self.use_resize_conv:
+            if self.use_resize_conv and k.up_fused_ok(out, blk["conv_up"]):
+                a, st1 = k.conv_up_fused(out, blk["conv_up"], gn_stats=True)       # the bilinear upsample inside the operand stage
+            elif self.use_resize_conv:
                 up = k.upsample2x(out)
                 a, st1 = k.conv(up, blk["conv_up"], pad=1, gn_stats=True)
             else:
@@ -664,6 +696,19 @@ class DecoderEngine:
                               stats=st2)
             if blk["attn"] is not None:
                 out = attention_block(k, blk["attn"], out)
+        if self.use_resize_conv and isinstance(self.final_up, ConvW) and k.up_fused_ok(out, self.final_up):
+            n, h, w = out.n, 2 * out.h, 2 * out.w
+            res = dst if dst is not None else torch.empty((n, self.out_channels, h, w), dtype=torch.float32, device=self.device)
+            if self.out_channels == 1:
+                pr = k.conv_up_fused(out, self.final_up, proj=self.final_w[0])
+                call("sbgm_final_gather", pr.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std), inv_std_stride,
+                     inv_std_step_stride, _ptr(step_counter), res.data_ptr(), n, h, w, _stream())
+                return res
+            a = k.conv_up_fused(out, self.final_up)
+            call("sbgm_final_conv", a.ptr, a.plane, self.fmt, self.final_w.data_ptr(), self.final_b.data_ptr(), _ptr(inv_std),
+                 inv_std_stride, inv_std_step_stride, _ptr(step_counter), res.data_ptr(), a.n, a.h, a.w, a.c,
+                 self.out_channels, _stream())
+            return res
         if not self.use_resize_conv:
             a = self._transpose_up(out, self.final_up)
             res = dst if dst is not None else torch.empty((a.n, self.out_channels, a.h, a.w), dtype=torch.float32, device=self.device)

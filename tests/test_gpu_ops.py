@@ -588,3 +588,40 @@ def test_conv2d_two_pixel_tiles_per_cta(E, prec, case, monkeypatch):
         if stats is not None:
             got = kern.groupnorm(y, gamma.cuda(), beta.cuda(), 8, stats=stats).to_nchw().cpu()
             assert rel_l2(got, F.group_norm(y.to_nchw().cpu(), 8, gamma, beta, 1e-5)) < {"bf16": 8e-3, "fp16x2": 5e-4}[prec]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16x2"])
+@pytest.mark.parametrize("mode", ["plain", "stats", "proj"])
+@pytest.mark.parametrize("shape", [(3, 8, 4), (2, 16, 16), (5, 16, 8), (150, 8, 4), (2, 24, 12)], ids=lambda t: "x".join(map(str, t)))
+def test_conv_with_the_upsample_in_its_operand_stage(E, prec, mode, shape):
+    """sbgm_conv3x3_c64_up == bilinear upsample -> 64 -> 64 convolution as two launches (the same fp32 interpolation expression
+    and the same single rounding of the operand, so the two agree to the odd last-bit tie), and == torch on what the kernel
+    reads.  Shapes: one tile per image (every halo row and column is padding or a
+    clamped border tap), 2 x 4 tiles, 2 x 2, more tiles than SMs (persistent loop, stage ring and patch buffers wrap around),
+    3 x 3 tiles (interior tiles on every side)."""
+    fmt = FMTS[prec]
+    n, hl, wl = shape
+    dev = torch.device("cuda")
+    kern = E.Kernels(fmt, dev)
+    x = act_of(E, gen(n, 64, hl, wl, seed=1), fmt)
+    w1, b1 = gen(64, 64, 3, 3, seed=4, scale=1.0 / 24), gen(64, seed=5, scale=0.1)
+    cw1 = E._Packer({"w1": w1, "b1": b1}, fmt, dev).conv("w1", "b1")
+    assert kern.up_fused_ok(x, cw1)
+    pw = gen(9, 64, seed=10, scale=0.1).cuda() if mode == "proj" else None
+    ref = kern.conv(kern.upsample2x(x), cw1, pad=1, proj=pw, gn_stats=(mode == "stats"))
+    got = kern.conv_up_fused(x, cw1, proj=pw, gn_stats=(mode == "stats"))
+    torch.cuda.synchronize()
+    tol2 = {"bf16": 3e-4, "fp16x2": 2e-5}[prec]           # a handful of operand values that round the other way
+    want = F.conv2d(F.interpolate(x.to_nchw().cpu(), scale_factor=2, mode="bilinear", align_corners=False), w1, b1, padding=1)
+    if mode == "proj":
+        assert rel_l2(got[..., :9].cpu(), ref[..., :9].cpu()) < tol2
+        wp = torch.einsum("nchw,qc->nhwq", want, pw.cpu())
+        assert rel_l2(got[..., :9].cpu(), wp) < {"bf16": 1.2e-2, "fp16x2": 1e-3}[prec]
+    else:
+        a, b = (got[0], ref[0]) if mode == "stats" else (got, ref)
+        assert rel_l2(a.to_nchw().cpu(), b.to_nchw().cpu()) < tol2
+        assert rel_l2(a.to_nchw().cpu(), want) < {"bf16": 1.2e-2, "fp16x2": 1e-3}[prec]
+        if mode == "stats":      # the statistics describe the tensor this kernel stored
+            gamma, beta = 1 + 0.2 * gen(64, seed=6), gen(64, seed=7, scale=0.2)
+            y = kern.groupnorm(a, gamma.cuda(), beta.cuda(), 8, stats=got[1]).to_nchw().cpu()
+            assert rel_l2(y, F.group_norm(a.to_nchw().cpu(), 8, gamma, beta, 1e-5)) < {"bf16": 8e-3, "fp16x2": 5e-4}[prec]
