@@ -235,7 +235,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       for (int i = 0; i < 4; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(f[2 * i]), "=f"(f[2 * i + 1]) : "l"(a.v[i]));
       return TcFmt<FMT>::pack8(f);
     };
-    const unsigned long long kW75 = pair(0.75f, 0.75f), kW25 = pair(0.25f, 0.25f), kW1 = pair(1.0f, 1.0f), kW0 = pair(0.0f, 0.0f);
+    const unsigned long long kW75 = pair(0.75f, 0.75f), kW25 = pair(0.25f, 0.25f);
+    const unsigned long long hx = (sx & 1) ? kW25 : kW75, lx = (sx & 1) ? kW75 : kW25;     // weights of the (left, right) taps
     // the patch is [10 x 6 pixels][128 B] with the 128-byte swizzle: 16-byte chunk c of pixel q sits at chunk c ^ (q & 7)
     const int vch = half * 4 + chunk;
     auto lds_patch = [&](uint32_t base, int q) {
@@ -243,48 +244,52 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(base + q * 128 + ((vch ^ (q & 7)) << 4)));
       return u;
     };
+    auto sts = [](uint32_t dst, const uint4& c) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
+    };
     uint32_t sidx = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, sidx += 2, ++it) {
       const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h;
       const uint32_t pb = it & 1u;
       const uint32_t patch = smem_base + Cfg::kPatchOffset + pb * kUpPatchBytes;
       const uint32_t s0 = sidx % kStages, s1 = (sidx + 1) % kStages;
-      // weights of the (left, right) taps; a tap outside the image (zero-filled by TMA) gets weight 0 and the other one 1
-      const bool left_out = tw == 0 && pc == 0, right_out = tw == p.tiles_w - 1 && pc == kUpPatchW - 2;
-      const unsigned long long hx = left_out ? kW0 : right_out ? kW1 : (sx & 1) ? kW25 : kW75;
-      const unsigned long long lx = left_out ? kW1 : right_out ? kW0 : (sx & 1) ? kW75 : kW25;
-      const bool zero_col = (sx == 0 && tw == 0) || (sx == kSlabW - 1 && tw == p.tiles_w - 1);
-      const uint32_t dst_plane = slab_base + (half ? s1 : s0) * Cfg::kStageBytes;
+      // A tap outside the image (zero-filled by TMA) is replaced by its neighbour inside: both taps of the pair then hold the
+      // edge pixel and 0.75 x + 0.25 x = x exactly -- ATen's clamped taps, without per-row weight selects.
+      const int pl = pc + ((tw == 0 && pc == 0) ? 1 : 0), pr = pc + ((tw == p.tiles_w - 1 && pc == kUpPatchW - 2) ? 0 : 1);
+      const int row_lo = (th == 0 && rh == 0) ? 1 : 0, row_hi = (th == p.tiles_h - 1 && rh == 1) ? 4 : 5;   // this half's rows inside the image
+      auto hrow = [&](int r, uint4& ul, uint4& ur) {
+        const int q = (4 * rh + min(max(r, row_lo), row_hi)) * kUpPatchW;
+        ul = lds_patch(patch, q + pl);
+        ur = lds_patch(patch, q + pr);
+      };
+      // slab address of row b of this half: pixel q = (8 rh + b) * 10 + sx, chunk ^ ((q >> 1) & 3) = chunk ^ ((b + pc) & 3)
+      const uint32_t dst0 = slab_base + (half ? s1 : s0) * Cfg::kStageBytes + (8 * rh * kSlabW + sx) * 64;
+      auto dst_of = [&](int b) { return dst0 + b * (kSlabW * 64) + ((chunk ^ ((b + pc) & 3)) << 4); };
       mbar_wait(patch_full(pb), (it >> 1) & 1u);
       mbar_wait(empty_bar(s0), ((sidx / kStages) & 1u) ^ 1u);
       mbar_wait(empty_bar(s1), (((sidx + 1) / kStages) & 1u) ^ 1u);
       // six low-resolution rows (4 * rh ..), blended horizontally; slab rows sy = 8 * rh + b, b = 0..9 (the two halves overlap
       // in rows 8, 9: the first takes 8, the second 9) use the row pair (b >> 1, b >> 1 + 1) with weights (0.75, 0.25) for even
       // b and (0.25, 0.75) for odd b.  Rolled over the five row pairs (code size), the next row's loads ahead of the stores.
-      const int q0 = 4 * rh * kUpPatchW + pc;
-      F8 prev = blend(hx, lx, widen(lds_patch(patch, q0)), widen(lds_patch(patch, q0 + 1)));
-      uint4 ul = lds_patch(patch, q0 + kUpPatchW), ur = lds_patch(patch, q0 + kUpPatchW + 1);
+      uint4 ul, ur;
+      hrow(0, ul, ur);
+      F8 prev = blend(hx, lx, widen(ul), widen(ur));
+      hrow(1, ul, ur);
 #pragma unroll 1
       for (int a = 0; a < 5; ++a) {
         const F8 next = blend(hx, lx, widen(ul), widen(ur));
-        if (a < 4) {
-          ul = lds_patch(patch, q0 + (a + 2) * kUpPatchW);
-          ur = lds_patch(patch, q0 + (a + 2) * kUpPatchW + 1);
-        }
-        const bool top_out = th == 0 && rh == 0 && a == 0, bot_out = th == p.tiles_h - 1 && rh == 1 && a == 4;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int b = 2 * a + e;
-          if (rh == 0 ? b == 9 : b == 0) continue;
-          const int sy = 8 * rh + b;
-          const unsigned long long hy = top_out ? kW0 : bot_out ? kW1 : e ? kW25 : kW75, ly = top_out ? kW1 : bot_out ? kW0 : e ? kW75 : kW25;
-          uint4 c = narrow(blend(hy, ly, prev, next));
-          if (zero_col || (sy == 0 && th == 0) || (sy == kSlabH - 1 && th == p.tiles_h - 1)) c = make_uint4(0u, 0u, 0u, 0u);
-          const int q = sy * kSlabW + sx;
-          const uint32_t dst = dst_plane + q * 64 + ((chunk ^ ((q >> 1) & 3)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
-        }
+        hrow(a + 2, ul, ur);                                 // (a = 4: a clamped re-read, unused)
+        if (!(rh == 1 && a == 0)) sts(dst_of(2 * a), narrow(blend(kW75, kW25, prev, next)));
+        if (!(rh == 0 && a == 4)) sts(dst_of(2 * a + 1), narrow(blend(kW25, kW75, prev, next)));
         prev = next;
+      }
+      // the convolution's zero padding: slab rows / columns outside the image, written over what the loop stored there
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      if (th == 0 && rh == 0) sts(dst_of(0), zero);
+      if (th == p.tiles_h - 1 && rh == 1) sts(dst_of(9), zero);
+      if ((sx == 0 && tw == 0) || (sx == kSlabW - 1 && tw == p.tiles_w - 1)) {
+#pragma unroll 1
+        for (int b = rh; b < 9 + rh; ++b) sts(dst_of(b), zero);
       }
       fence_async_shared();
       __syncwarp();
