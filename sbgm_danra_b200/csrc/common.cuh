@@ -208,6 +208,18 @@ struct TcFmt {
   // factor of the second weight plane's product when the accumulator halves are summed
   static constexpr float kLoScale = kHalf ? (1.0f / SBGM_F16_WLO_SCALE) : 1.0f;
   __device__ __forceinline__ static float round(float x) { return kHalf ? f16_round(x) : bf16_round(x); }
+  // two values through one pack instruction
+  __device__ __forceinline__ static void round2(float& a, float& b) {
+    if (kHalf) {
+      const uint32_t p = pack_f16x2(a, b);
+      a = __half2float(__ushort_as_half(static_cast<unsigned short>(p & 0xffffu)));
+      b = __half2float(__ushort_as_half(static_cast<unsigned short>(p >> 16)));
+    } else {
+      const uint32_t p = pack_bf16x2(a, b);
+      a = __uint_as_float(p << 16);
+      b = __uint_as_float(p & 0xffff0000u);
+    }
+  }
   __device__ __forceinline__ static uint4 pack8(const float (&v)[8]) { return kHalf ? pack_f16x8(v) : pack_bf16x8(v); }
 };
 

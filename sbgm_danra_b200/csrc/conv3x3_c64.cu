@@ -323,11 +323,9 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (kBPl == 2) {
         uint32_t t[32];
         tmem_ld32(taddr + 64, t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(fmaf(__uint_as_float(t[j]), TcFmt<FMT>::kLoScale, __uint_as_float(r0[j])));
+        merge_lo<FMT>(r0, t);
         tmem_ld32(taddr + 96, t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(fmaf(__uint_as_float(t[j]), TcFmt<FMT>::kLoScale, __uint_as_float(r1[j])));
+        merge_lo<FMT>(r1, t);
       }
       // the accumulator is in registers: hand the TMEM buffer back before the (long) epilogue math
       tcgen05_fence_before();

@@ -352,8 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (kBPl == 2) {
         uint32_t t[32];
         tmem_ld32(taddr + BLOCK_N, t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(t[j]), TcFmt<FMT>::kLoScale, __uint_as_float(r[j])));
+        merge_lo<FMT>(r, t);
       }
     };
     if (!PROJ && p.splits > 1) {                    // split-K: raw fp32 partial tile, finished by splitk_finalize_kernel

@@ -179,11 +179,9 @@ stem_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p)
       if (kBPl == 2) {
         uint32_t t[32];
         tmem_ld32(taddr + 64, t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(fmaf(__uint_as_float(t[j]), TcFmt<FMT>::kLoScale, __uint_as_float(r0[j])));
+        merge_lo<FMT>(r0, t);
         tmem_ld32(taddr + 96, t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(fmaf(__uint_as_float(t[j]), TcFmt<FMT>::kLoScale, __uint_as_float(r1[j])));
+        merge_lo<FMT>(r1, t);
       }
       tcgen05_fence_before();
       __syncwarp();

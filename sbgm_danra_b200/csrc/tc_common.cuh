@@ -188,7 +188,7 @@ struct EpilogueParams {
 };
 constexpr int kProjN = 9;
 constexpr int kProjMax = SBGM_PROJ_STRIDE;
-static __constant__ float c_proj_w[kProjN * 64];
+static __constant__ __align__(16) float c_proj_w[kProjN * 64];
 
 template <int ACT>
 __device__ __forceinline__ float act_ct(float x) {
@@ -287,28 +287,79 @@ __device__ __forceinline__ void store_block64_staged(const CUtensorMap* tmap_o, 
 // GroupNorm partial statistics of one 64-channel block, at 8-channel granularity, reduced over the warp's 32
 // rows: dst[sub][2] (sum, sum of squares) for sub = 0..7.  Values are taken as stored (bias added, bf16-rounded
 // in the single-plane modes).  Must be called by the whole warp; rows with !valid contribute nothing.
+// Two fp32 operations per issue slot (FADD2 / FFMA2): the epilogue warps are issue-bound next to the MMA issuer.
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+// (a0, a1) += s * (t0, t1)
+__device__ __forceinline__ void fma_scalar_f32x2(float& a0, float& a1, float t0, float t1, float s) {
+  unsigned long long a, t, ss;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(t), "l"(ss));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+
 template <int FMT>
 __device__ __forceinline__ void gn_block64_stats(const uint32_t (&ra)[32], const uint32_t (&rb)[32], const float* bias,
                                                  int co_base, bool valid, int lane, float* dst) {
+  // x[2 g] = sum, x[2 g + 1] = sum of squares of group g over this thread's row (packed fp32: two channels per instruction)
+  float x[16];
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
-    float s = 0.0f, q = 0.0f;
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = __uint_as_float(g < 4 ? ra[g * 8 + j] : rb[(g - 4) * 8 + j]);
-      if (bias) v += __ldg(bias + co_base + g * 8 + j);
-      if (FMT == SBGM_FMT_BF16 || FMT == SBGM_FMT_F16) v = TcFmt<FMT>::round(v);
-      if (!valid) v = 0.0f;
-      s += v;
-      q = fmaf(v, v, q);
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(g < 4 ? ra[g * 8 + j] : rb[(g - 4) * 8 + j]);
+    if (bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + co_base + g * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + co_base + g * 8) + 1);
+      add_f32x2(v[0], v[1], b0.x, b0.y);
+      add_f32x2(v[2], v[3], b0.z, b0.w);
+      add_f32x2(v[4], v[5], b1.x, b1.y);
+      add_f32x2(v[6], v[7], b1.z, b1.w);
     }
-    s = warp_sum(s);
-    q = warp_sum(q);
-    if (lane == 0) {
-      dst[2 * g] = s;
-      dst[2 * g + 1] = q;
+    if (FMT == SBGM_FMT_BF16 || FMT == SBGM_FMT_F16) {      // the statistics describe the values as stored
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) TcFmt<FMT>::round2(v[j], v[j + 1]);
+    }
+    if (!valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    }
+    unsigned long long p[4], sp, qp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) asm("mov.b64 %0, {%1, %2};" : "=l"(p[j]) : "f"(v[2 * j]), "f"(v[2 * j + 1]));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sp) : "l"(p[0]), "l"(p[1]));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(qp) : "l"(p[0]));
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+      if (j > 1) asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sp) : "l"(p[j]));
+      asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(qp) : "l"(p[j]));
+    }
+    float s0, s1, q0, q1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(sp));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(qp));
+    x[2 * g] = s0 + s1;
+    x[2 * g + 1] = q0 + q1;
+  }
+  // transposing butterfly over the warp's 32 rows: each step halves the values a lane carries (16 shuffles instead of 80);
+  // after the steps 16, 8, 4, 2 lane L holds value ((L >> 4) & 1) * 8 + ((L >> 3) & 1) * 4 + ((L >> 2) & 1) * 2 + ((L >> 1) & 1)
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 16 >> step, cnt = 8 >> step;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const float send = upper ? x[i] : x[i + cnt], keep = upper ? x[i + cnt] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
+  x[0] += __shfl_xor_sync(0xffffffffu, x[0], 1);
+  if ((lane & 1) == 0) dst[((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = x[0];
 }
 
 // 64 accumulator columns (two 32-column TMEM loads) of one row.  ACT and PROJ are compile-time
@@ -318,6 +369,18 @@ struct StageArgs {          // where a staged block goes (unused when !STAGED)
   uint32_t stage;
   int x0, y0, n0;
 };
+
+// acc += lo * kLoScale for the x * w_lo half of the accumulator, two columns per instruction
+template <int FMT>
+__device__ __forceinline__ void merge_lo(uint32_t (&r)[32], const uint32_t (&t)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float a0 = __uint_as_float(r[j]), a1 = __uint_as_float(r[j + 1]);
+    fma_scalar_f32x2(a0, a1, __uint_as_float(t[j]), __uint_as_float(t[j + 1]), TcFmt<FMT>::kLoScale);
+    r[j] = __float_as_uint(a0);
+    r[j + 1] = __float_as_uint(a1);
+  }
+}
 
 template <int FMT, int ACT, int PROJ, bool STAGED = false>
 __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const uint32_t (&ra)[32], const uint32_t (&rb)[32],
@@ -333,7 +396,8 @@ __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const
 #pragma unroll
     for (int g = 0; g < 16; ++g) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + co_base) + g);
-      v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+      add_f32x2(v[4 * g], v[4 * g + 1], b.x, b.y);
+      add_f32x2(v[4 * g + 2], v[4 * g + 3], b.z, b.w);
     }
   }
   if (!PROJ && ep.residual && valid) {
@@ -356,10 +420,28 @@ __device__ __forceinline__ void epilogue_block64(const EpilogueParams& ep, const
     }
   }
   if (PROJ) {
+    // two channels per instruction (FFMA2, the weight pair straight from the constant bank): 288 instead of 576 issue slots per
+    // pixel -- the epilogue warps share their schedulers with the MMA issuer and, in the fused-upsample kernel, the producers.
+    // Each tap keeps an (even channels, odd channels) pair of partial sums, added at the end.
+    unsigned long long acc2[kProjN];
 #pragma unroll
-    for (int j = 0; j < 64; ++j)
+    for (int q = 0; q < kProjN; ++q) acc2[q] = 0ull;
 #pragma unroll
-      for (int q = 0; q < kProjN; ++q) proj_acc[q] = fmaf(v[j], c_proj_w[q * 64 + j], proj_acc[q]);
+    for (int j = 0; j < 64; j += 2) {
+      unsigned long long vp;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(vp) : "f"(v[j]), "f"(v[j + 1]));
+#pragma unroll
+      for (int q = 0; q < kProjN; ++q) {
+        const unsigned long long wp = *reinterpret_cast<const unsigned long long*>(&c_proj_w[q * 64 + j]);
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[q]) : "l"(vp), "l"(wp));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kProjN; ++q) {
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc2[q]));
+      proj_acc[q] += lo + hi;
+    }
   }
   if (PROJ != 1) {          // PROJ == 2: both (training)
     if (STAGED) store_block64_staged<FMT>(sa.tmap_o, sa.stage, v, co_base, sa.x0, sa.y0, sa.n0, lane);
