@@ -1016,7 +1016,9 @@ class TrainRunner:
             torch.cuda.synchronize()
             self.pool = torch.cuda.graph_pool_handle()
             self.g_fwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_fwd, pool=self.pool):
+            # thread_local: a DataLoader's pin-memory thread (cudaHostAlloc, event queries) running next to the capture would
+            # invalidate it in the default global mode -- seen as an order-dependent failure behind the reference's own pipeline
+            with torch.cuda.graph(self.g_fwd, pool=self.pool, capture_error_mode="thread_local"):
                 self.eng._pack()                       # re-pack from the live parameters inside the graph
                 self.out = self.eng.forward(*(self.static[k] for k in ("x", "t", "y", "planes", "inv_std")))
             self.keep.append(self.eng.tape)
@@ -1040,7 +1042,7 @@ class TrainRunner:
             self.static["dout"] = dout.to(dtype=torch.float32).contiguous().clone()
             torch.cuda.synchronize()
             self.g_bwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_bwd, pool=self.pool):
+            with torch.cuda.graph(self.g_bwd, pool=self.pool, capture_error_mode="thread_local"):
                 self.grads = self.eng.backward(self.static["dout"])
             self.keep.append(self.eng.flat)
         else:

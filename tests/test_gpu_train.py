@@ -873,3 +873,39 @@ def test_deferred_weight_gradients_equal_immediate_ones(E, T):
         results.append({k: v.clone() for k, v in grads.items()})
     for k in results[0]:
         assert torch.equal(results[0][k], results[1][k]), k
+
+
+def test_graph_capture_survives_a_pinning_thread():
+    """The training graphs are captured on the third step, while a DataLoader(pin_memory=True) thread may be allocating pinned
+    memory and querying events: the capture must not be invalidated by CUDA calls of OTHER threads (capture_error_mode)."""
+    import threading
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16", DEV).eval()
+    b = synth_batch(batch=2, size=32, n_lr=1)
+    stop = threading.Event()
+
+    def pin_loop():
+        while not stop.is_set():
+            buf = torch.empty(1 << 16, dtype=torch.uint8, pin_memory=True)     # cudaHostAlloc: "unsafe" during a global-mode capture
+            ev = torch.cuda.Event()
+            ev.query()
+            del buf
+
+    th = threading.Thread(target=pin_loop, daemon=True)
+    th.start()
+    try:
+        losses = []
+        for _ in range(5):
+            score_sampling.manual_seed(5)
+            net.zero_grad(set_to_none=True)
+            loss = loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, cond_img=b.cond_img.to(DEV))
+            loss.backward()
+            losses.append(float(loss))
+    finally:
+        stop.set()
+        th.join()
+    assert all(abs(v - losses[0]) <= 1e-6 * abs(losses[0]) for v in losses), losses
