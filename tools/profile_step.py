@@ -1,6 +1,7 @@
 """One (or a few) UNet evaluations at the benchmark shape, for ncu launch lists / captures.
 
     python tools/profile_step.py [--precision bf16x3] [--batch 64] [--size 128] [--iters 2] [--events]
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file launches.csv python tools/profile_step.py ...
 
 With --events it prints a per-kernel-family time table measured with CUDA events around every C-ABI
 call (serialised; shares only)."""
@@ -64,9 +65,11 @@ def main():
         for k, (ms, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             print(f"{ms / a.iters:8.3f} ms  {100 * ms / total:5.1f}%  x{cnt // a.iters:3d}  {k}")
     else:
+        torch.cuda.profiler.start()       # `ncu --profile-from-start off`: the launch list holds these evaluations only
         for _ in range(a.iters):
             net(x, t, None, c)
         torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     print("done")
 
 
