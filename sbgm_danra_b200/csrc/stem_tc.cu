@@ -205,17 +205,23 @@ stem_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p)
           }
         }
       }
+      // the row leaves through the 8-lane transposing store of the convolution kernels: every store instruction writes four
+      // full 128-byte lines (the lane's own row in 16-byte pieces was 32 quarter-lines per instruction)
+      float v[64];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(g < 4 ? r0[g * 8 + e] : r1[(g - 4) * 8 + e]);
-        if (tp) {
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(tp + g * 8)), t1 = __ldg(reinterpret_cast<const float4*>(tp + g * 8) + 1);
-          v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-        }
-        Act<FMT>::store8(p.out, p.out_plane, pix * 64 + g * 8, v);
+      for (int j = 0; j < 32; ++j) {
+        v[j] = __uint_as_float(r0[j]);
+        v[32 + j] = __uint_as_float(r1[j]);
       }
+      if (tp) {
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(tp) + g);
+          add_f32x2(v[4 * g], v[4 * g + 1], t.x, t.y);
+          add_f32x2(v[4 * g + 2], v[4 * g + 3], t.z, t.w);
+        }
+      }
+      store_block64<FMT>(p.out, p.out_plane, 64, v, pix, true, 0, lane);
     }
   }
   tcgen05_fence_before();
