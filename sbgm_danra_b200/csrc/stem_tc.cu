@@ -86,30 +86,39 @@ stem_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p)
     }
     const int row = threadIdx.x;                       // 0..127
     const int py = row / kStTW, px = row % kStTW;
+    // A thread's patch values are requested one TILE ahead and all at once (the patch fetch is an L2 round trip that sat on the
+    // builders' critical path: ncu, long-scoreboard stalls in front of the patch stores).  Volatile asm with the bounds test as
+    // a multiplier: as plain predicated loads the compiler sinks them to their first use, which undoes the prefetch.
+    constexpr int kPerThread = (kStPH * kStPW + 127) / 128;
+    float pv[kPerThread];
+    auto fetch = [&](int tile) {
+      const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+      const int iy0 = 2 * th * kStTH - 3, ix0 = 2 * tw * kStTW - 3;
+      const float* xs = p.x + static_cast<size_t>(n) * p.h * p.w;
+#pragma unroll
+      for (int k = 0; k < kPerThread; ++k) {
+        const int i = min(static_cast<int>(threadIdx.x) + k * 128, kStPH * kStPW - 1);
+        const int r = i / kStPW, c = i - r * kStPW;
+        const int iy = iy0 + r, ix = ix0 + c;
+        const bool in = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+        const float* src = xs + static_cast<size_t>(min(max(iy, 0), p.h - 1)) * p.w + min(max(ix, 0), p.w - 1);
+        float v;
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(src));
+        pv[k] = in ? v : 0.0f;
+      }
+    };
+    fetch(min(static_cast<int>(blockIdx.x), p.total_tiles - 1));
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
       float* patch = reinterpret_cast<float*>(smem_gen + Cfg::kPatchOffset + buf * Cfg::kPatchBytes);
       // the patch buffer `buf` was last read two tiles ago by these same 128 threads: the named barrier below orders it
-      const int iy0 = 2 * th * kStTH - 3, ix0 = 2 * tw * kStTW - 3;
-      const float* xs = p.x + static_cast<size_t>(n) * p.h * p.w;
-      // all of a thread's patch values are requested before the first is stored (7 loads in flight instead of a load -> store
-      // chain: the patch fetch is an L2 round trip per tile and sits on the builders' critical path)
-      constexpr int kPerThread = (kStPH * kStPW + 127) / 128;
-      float pv[kPerThread];
-#pragma unroll
-      for (int k = 0; k < kPerThread; ++k) {
-        const int i = threadIdx.x + k * 128;
-        const int r = i / kStPW, c = i - r * kStPW;
-        const int iy = iy0 + r, ix = ix0 + c;
-        pv[k] = (i < kStPH * kStPW && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) ? __ldg(xs + static_cast<size_t>(iy) * p.w + ix) : 0.0f;
-      }
 #pragma unroll
       for (int k = 0; k < kPerThread; ++k) {
         const int i = threadIdx.x + k * 128;
         if (i < kStPH * kStPW) patch[(i / kStPW) * kStPP + (i % kStPW)] = pv[k];
       }
+      fetch(min(tile + static_cast<int>(gridDim.x), p.total_tiles - 1));      // in flight while this tile's window matrix is built
       asm volatile("bar.sync 1, 128;" ::: "memory");                    // patch complete (builder warps only)
       mbar_wait(a_empty(buf), ((it >> 1) & 1u) ^ 1u);
       const uint32_t a_row = a_base + buf * Cfg::kABytes + row * 128;
@@ -170,6 +179,17 @@ stem_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p)
       const uint32_t buf = it & 1u, use = it >> 1;
       const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
       const int oy = th * kStTH + py, ox = tw * kStTW + px;
+      const size_t pix = (static_cast<size_t>(n) * p.ho + oy) * p.wo + ox;
+      const size_t ppix = p.partial_n == 1 ? static_cast<size_t>(oy) * p.wo + ox : pix;
+      // single-plane formats: the pixel's conditioning partial sums are requested BEFORE the wait for the accumulator (they do
+      // not depend on it; ncu showed the L2 round trip behind the wait as long-scoreboard stalls)
+      uint4 pa[8];
+      if (kAPl == 1 && p.partial) {
+        const uint8_t* src = static_cast<const uint8_t*>(p.partial) + ppix * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pa[g].x), "=r"(pa[g].y), "=r"(pa[g].z), "=r"(pa[g].w) : "l"(src + g * 16));
+      }
       mbar_wait(acc_full(buf), use & 1u);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * Cfg::kAccCols;
@@ -186,8 +206,6 @@ stem_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p)
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
-      const size_t pix = (static_cast<size_t>(n) * p.ho + oy) * p.wo + ox;
-      const size_t ppix = p.partial_n == 1 ? static_cast<size_t>(oy) * p.wo + ox : pix;
       const float* tp = p.tproj ? p.tproj + static_cast<size_t>(n) * p.tproj_stride : nullptr;
       // the conditioning partial sums of the whole pixel are requested before the first store: the output pointer may alias
       // them as far as the compiler knows, so a load-inside-the-loop form serialises eight L2 round trips per tile
@@ -197,7 +215,11 @@ stem_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p)
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           float a[8];
-          Act<FMT>::load8(p.partial, p.partial_plane, ppix * 64 + g * 8, a);
+          if (kAPl == 1) {
+            if (TcFmt<FMT>::kHalf) unpack_f16x8(pa[g], a); else unpack_bf16x8(pa[g], a);
+          } else {
+            Act<FMT>::load8(p.partial, p.partial_plane, ppix * 64 + g * 8, a);
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             if (g < 4) r0[g * 8 + e] = __float_as_uint(__uint_as_float(r0[g * 8 + e]) + a[e]);
