@@ -302,7 +302,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (LNF) {
       // LayerNorm statistics of this thread's row (token) over ALL input channels, read from the A tiles while the MMA consumes
       // them: 64 channels per k-block, 16-byte chunks at the 128-byte-swizzle positions TMA wrote them to
-      float sum = 0.0f, sq = 0.0f;
+      // two channels per instruction (FADD2 / FFMA2): (even, odd) partial sums, added at the end
+      unsigned long long sum2 = 0ull, sq2 = 0ull;
       uint32_t stage = 0, phase = 0;
       for (int kbi = 0; kbi < num_kb; ++kbi) {
         mbar_wait(full_bar(stage), phase);
@@ -321,15 +322,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int e = 0; e < 8; ++e) v[e] += t[e];
           }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            sum += v[e];
-            sq = fmaf(v[e], v[e], sq);
+          for (int e = 0; e < 8; e += 2) {
+            unsigned long long vp;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(vp) : "f"(v[e]), "f"(v[e + 1]));
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum2) : "l"(vp));
+            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(sq2) : "l"(vp));
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(stage));
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
+      float s0, s1, q0, q1;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(sum2));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(sq2));
+      const float sum = s0 + s1, sq = q0 + q1;
       const float inv_c = 1.0f / static_cast<float>(p.cin_blocks * 64);
       ln_mean = sum * inv_c;
       ln_rstd = rsqrtf(fmaxf(sq * inv_c - ln_mean * ln_mean, 0.0f) + p.ln_eps);
@@ -375,11 +382,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         load_acc(c0, ra);
         load_acc(c0 + 32, rb);
         if (LNF) {
-          const float* cs = p.ln_colsum + co0 + c0;
+          // rstd * (acc - mean * colsum), four column sums per load, two columns per instruction
+          const float4* cs = reinterpret_cast<const float4*>(p.ln_colsum + co0 + c0);
+          unsigned long long nm2, rs2;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(nm2) : "f"(-ln_mean));
+          asm("mov.b64 %0, {%1, %1};" : "=l"(rs2) : "f"(ln_rstd));
+          auto fold = [&](uint32_t& x0, uint32_t& x1, float c0_, float c1_) {
+            unsigned long long a, c;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(x0), "r"(x1));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0_), "f"(c1_));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(nm2), "l"(c));
+            asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(rs2));
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(x0), "=r"(x1) : "l"(a));
+          };
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            ra[j] = __float_as_uint(ln_rstd * fmaf(-ln_mean, __ldg(cs + j), __uint_as_float(ra[j])));
-            rb[j] = __float_as_uint(ln_rstd * fmaf(-ln_mean, __ldg(cs + 32 + j), __uint_as_float(rb[j])));
+          for (int g = 0; g < 8; ++g) {
+            const float4 ca = __ldg(cs + g), cb = __ldg(cs + 8 + g);
+            fold(ra[4 * g], ra[4 * g + 1], ca.x, ca.y);
+            fold(ra[4 * g + 2], ra[4 * g + 3], ca.z, ca.w);
+            fold(rb[4 * g], rb[4 * g + 1], cb.x, cb.y);
+            fold(rb[4 * g + 2], rb[4 * g + 3], cb.z, cb.w);
           }
         }
         if (!PROJ && p.gn_partials) {
