@@ -734,3 +734,26 @@ def test_batch_assembler_applies_transforms_while_assembling():
     want_lr = np.concatenate([br.prcp_log_fwd(f32(raw["prcp_lr"]), **kw_p), br.zscore_fwd(f32(raw["temp_lr"]), 8.69, 6.19)], axis=1)
     np.testing.assert_allclose(lr.cpu().numpy(), want_lr, rtol=1e-6, atol=3e-7)
     np.testing.assert_allclose(topo.cpu().numpy(), br.scale_fwd(f32(raw["topo"]), 0, 1, 0.0, 170.0), rtol=1e-6, atol=3e-7)
+
+
+@pytest.mark.parametrize("precision", ["fp16x2", "bf16"])
+@pytest.mark.parametrize("size", [64, 96])
+def test_upsample_inside_conv_up_is_bit_identical_to_the_two_launch_path(monkeypatch, precision, size):
+    """The network with the bilinear upsample produced inside the 64 -> 64 conv_up layers' operand stage (decoder block 3 and the
+    final layer; 96x96 gives non-power-of-two tile counts, 3 x 6 and 6 x 12) returns the very bits of the network with
+    stand-alone upsample launches: same interpolation expression, same single rounding."""
+    from oracle.synth import synth_batch
+    from sbgm_danra_b200 import engine as E
+    net, cfg, sd = _model(dict(n_lr=1), precision)
+    b = synth_batch(batch=3, size=size, n_lr=1)
+    args = [_cuda(v) for v in b.model_args()]
+    trace = []
+    monkeypatch.setattr(E, "CONV_TRACE", trace)
+    with torch.no_grad():
+        fused = net(*args).clone()
+    assert any(rec.get("up_fused") for rec in trace), "the fused path did not run"
+    monkeypatch.setattr(E, "CONV_TRACE", None)
+    monkeypatch.setattr(E, "_UP_FUSED", False)
+    with torch.no_grad():
+        plain = net(*args).clone()
+    assert torch.equal(fused, plain)
