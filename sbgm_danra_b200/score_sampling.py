@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import engine as _eng
+from ._capture import graph_capture
 from ._lib import STEP_COLS, call
 from ._lib import stats as _lib_stats
 
@@ -462,7 +463,7 @@ def _sample(kind: str, score_model, marginal_prob_std, diffusion_coeff, batch_si
             torch.cuda.current_stream(dev).wait_stream(side)
             st.graph = torch.cuda.CUDAGraph()
             before = _lib_stats.launches
-            with torch.cuda.graph(st.graph, capture_error_mode="thread_local"):
+            with graph_capture(st.graph):
                 one_step()
             st.per_replay = _lib_stats.launches - before     # kernels recorded in the graph
             _lib_stats.launches = before
@@ -537,7 +538,7 @@ def _sample_em_two_lanes(score_model, table, seed, scale, dev, batch_size, n_ste
             torch.cuda.synchronize(dev)
             meta["graph"] = torch.cuda.CUDAGraph()
             before = _lib_stats.launches
-            with torch.cuda.graph(meta["graph"], capture_error_mode="thread_local"):
+            with graph_capture(meta["graph"]):
                 both(True)
             meta["per_replay"] = _lib_stats.launches - before
             _lib_stats.launches = before

@@ -558,10 +558,15 @@ class _ScoreNetFn(torch.autograd.Function):
         runners = model.__dict__.setdefault("_train_runners", {})
         runner = runners.get(key)
         if runner is None:
+            # the closure holds the model's tensors and settings, not the model: model -> runner -> closure -> model would be a
+            # reference cycle, and the runner's CUDA graphs would then die whenever the cyclic collector runs (possibly inside
+            # someone else's graph capture) instead of with the model
+            spec, precision, training, device = model.spec(), model.precision, model.training, x.device
+
             def make_engine():
                 tensors = dict(zip(names, params))
                 tensors.update(buffers)
-                return TrainEngine(tensors, model.spec(), model.precision, x.device, bn_train=model.training)
+                return TrainEngine(tensors, spec, precision, device, bn_train=training)
             runners.clear()                       # one live configuration at a time (the graphs pin GBs of activations)
             runner = runners[key] = TrainRunner(make_engine, use_graphs=os.environ.get("SBGM_B200_TRAIN_GRAPHS", "1") != "0")
         if runner.eng is not None:                # captured step: its forward graph re-zeroes the flat gradient buffer

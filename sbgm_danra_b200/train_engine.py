@@ -20,6 +20,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from ._capture import graph_capture
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, FMT_BF16X2, FMT_F32, call
 from .engine import ACTS, BN_EPS, GN_EPS, LN_EPS, PRECISIONS, Act, ConvW, Kernels, UNetSpec, _ptr, _stream
 
@@ -990,6 +991,20 @@ class TrainRunner:
         self.grads: Optional[Dict[str, torch.Tensor]] = None
         self.keep: list = []
 
+    def _capture_failed(self, exc: Exception) -> None:
+        import warnings
+        self.capture_failures = getattr(self, "capture_failures", 0) + 1
+        self.eng = self.g_fwd = self.g_bwd = self.out = self.grads = None
+        self.static = {}
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        if self.capture_failures >= 3:
+            self.use_graphs = False
+        warnings.warn(f"sbgm_danra_b200: CUDA-graph capture of the training step failed ({type(exc).__name__}: {str(exc)[:200]}); "
+                      + ("staying on the eager launch sequence" if not self.use_graphs else "this step runs eagerly, capture will be retried"))
+
     @staticmethod
     def _copy_in(dst: Optional[torch.Tensor], src: Optional[torch.Tensor]) -> None:
         if dst is not None:
@@ -1011,17 +1026,23 @@ class TrainRunner:
             return eng.forward(x, t, y, planes, inv_std), ("eager", eng)
         ins = dict(x=x, t=t, y=y, planes=planes, inv_std=inv_std)
         if self.g_fwd is None:
-            self.eng = self._engine(grad_sync)
-            self.static = {k: (None if v is None else v.clone()) for k, v in ins.items()}
-            torch.cuda.synchronize()
-            self.pool = torch.cuda.graph_pool_handle()
-            self.g_fwd = torch.cuda.CUDAGraph()
-            # thread_local: a DataLoader's pin-memory thread (cudaHostAlloc, event queries) running next to the capture would
-            # invalidate it in the default global mode -- seen as an order-dependent failure behind the reference's own pipeline
-            with torch.cuda.graph(self.g_fwd, pool=self.pool, capture_error_mode="thread_local"):
-                self.eng._pack()                       # re-pack from the live parameters inside the graph
-                self.out = self.eng.forward(*(self.static[k] for k in ("x", "t", "y", "planes", "inv_std")))
-            self.keep.append(self.eng.tape)
+            try:
+                self.eng = self._engine(grad_sync)
+                self.static = {k: (None if v is None else v.clone()) for k, v in ins.items()}
+                torch.cuda.synchronize()
+                self.pool = torch.cuda.graph_pool_handle()
+                self.g_fwd = torch.cuda.CUDAGraph()
+                with graph_capture(self.g_fwd, pool=self.pool):
+                    self.eng._pack()                       # re-pack from the live parameters inside the graph
+                    self.out = self.eng.forward(*(self.static[k] for k in ("x", "t", "y", "planes", "inv_std")))
+                self.keep.append(self.eng.tape)
+            except Exception as exc:
+                # A capture can still be invalidated by activity outside this call: nothing of it has executed, so this step runs
+                # the eager launch sequence and the capture is tried again on a later step (three attempts, then the runner
+                # stays eager).
+                self._capture_failed(exc)
+                eng = self._engine(grad_sync)
+                return eng.forward(x, t, y, planes, inv_std), ("eager", eng)
         else:
             for k, v in ins.items():
                 self._copy_in(self.static[k], v)
@@ -1042,7 +1063,7 @@ class TrainRunner:
             self.static["dout"] = dout.to(dtype=torch.float32).contiguous().clone()
             torch.cuda.synchronize()
             self.g_bwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_bwd, pool=self.pool, capture_error_mode="thread_local"):
+            with graph_capture(self.g_bwd, pool=self.pool):
                 self.grads = self.eng.backward(self.static["dout"])
             self.keep.append(self.eng.flat)
         else:

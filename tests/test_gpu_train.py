@@ -909,3 +909,78 @@ def test_graph_capture_survives_a_pinning_thread():
         stop.set()
         th.join()
     assert all(abs(v - losses[0]) <= 1e-6 * abs(losses[0]) for v in losses), losses
+
+
+def test_failed_graph_capture_falls_back_to_eager_and_is_retried(monkeypatch):
+    """A capture that is invalidated (here: a synchronize inside it, once) must cost one eager step, not the training run: the step
+    still returns the right loss and gradients, and the next step captures."""
+    import warnings
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling, train_engine
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16", DEV).eval()
+    b = synth_batch(batch=2, size=32, n_lr=1)
+    orig_pack = train_engine.TrainEngine._pack
+    fired = []
+
+    def pack_once_broken(self):
+        if torch.cuda.is_current_stream_capturing() and not fired:
+            fired.append(1)
+            torch.cuda.synchronize()            # illegal inside a capture: invalidates it and raises
+        return orig_pack(self)
+
+    monkeypatch.setattr(train_engine.TrainEngine, "_pack", pack_once_broken)
+    snaps = []
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        for _ in range(6):
+            score_sampling.manual_seed(11)
+            net.zero_grad(set_to_none=True)
+            loss = loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, cond_img=b.cond_img.to(DEV))
+            loss.backward()
+            snaps.append((float(loss), torch.cat([p.grad.flatten() for p in net.parameters() if p.grad is not None]).clone()))
+    assert fired and any("capture" in str(w.message) for w in caught)
+    for lo, g in snaps[1:]:
+        assert lo == snaps[0][0] and torch.equal(g, snaps[0][1])
+    (runner,) = net.__dict__["_train_runners"].values()
+    assert runner.g_fwd is not None and runner.capture_failures == 1 and runner.use_graphs
+
+
+def test_dead_cycle_owning_a_cuda_graph_does_not_break_the_next_capture():
+    """The root cause of the order-dependent capture failure: an unreachable reference cycle that owns a CUDA graph (an earlier
+    model and its runner) is finalised by the cyclic collector at an arbitrary allocation -- inside a capture that is "not
+    permitted" and invalidates it.  graph_capture collects before the capture and pauses the collector during it."""
+    import gc
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+
+    class Holder:
+        pass
+
+    gc.collect()
+    g = torch.cuda.CUDAGraph()
+    buf = torch.zeros(1024, device=DEV)
+    with torch.cuda.graph(g):
+        buf += 1
+    a, b_ = Holder(), Holder()
+    a.other, b_.other, a.graph = b_, a, g          # a cycle that owns the graph ...
+    for _ in range(3):
+        gc.collect()                               # ... promoted to the oldest generation while alive ...
+    del a, b_, g                                   # ... and now dead, waiting for a full collection
+    gc.set_threshold(50, 2, 2)                     # make full collections frequent for the rest of this test
+    try:
+        cfg = config_for(n_lr=1)
+        net = build_model(cfg, synth_state_dict(cfg), "bf16", DEV).eval()
+        b = synth_batch(batch=2, size=32, n_lr=1)
+        for _ in range(4):
+            score_sampling.manual_seed(2)
+            net.zero_grad(set_to_none=True)
+            loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, cond_img=b.cond_img.to(DEV)).backward()
+        (runner,) = net.__dict__["_train_runners"].values()
+        assert runner.g_fwd is not None and runner.g_bwd is not None and getattr(runner, "capture_failures", 0) == 0
+    finally:
+        gc.set_threshold(700, 10, 10)
