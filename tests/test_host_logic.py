@@ -292,3 +292,38 @@ def test_broadcast_style_write_invalidates_engine_cache_key():
     v1 = _versions(lin)
     lin.weight.data.copy_(torch.zeros(2, 3))          # the pattern the cache cannot see (documented in INTEGRATION.md)
     assert _versions(lin) == v1
+
+
+def test_graph_capture_pauses_the_cyclic_collector_and_restores_it(monkeypatch):
+    """`_capture.graph_capture` collects before the capture, keeps the cyclic collector off inside it (a dead cycle owning a CUDA
+    graph must not be finalised mid-capture), asks for thread-local error mode and restores the collector -- also when the body
+    raises, and without switching it on for a caller that had it off."""
+    import contextlib
+    import gc
+    from sbgm_danra_b200 import _capture
+    seen = {}
+
+    @contextlib.contextmanager
+    def fake_graph(graph, **kw):
+        seen.update(kw, graph=graph, gc_inside=gc.isenabled())
+        yield
+
+    monkeypatch.setattr(torch.cuda, "graph", fake_graph)
+    collected = []
+    monkeypatch.setattr(_capture.gc, "collect", lambda *a: collected.append(1) or 0)
+    assert gc.isenabled()
+    with _capture.graph_capture("g", pool="p"):
+        assert not gc.isenabled()
+    assert gc.isenabled() and collected == [1]
+    assert seen == dict(graph="g", pool="p", capture_error_mode="thread_local", gc_inside=False)
+    with pytest.raises(RuntimeError):
+        with _capture.graph_capture("g"):
+            raise RuntimeError("capture invalidated")
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with _capture.graph_capture("g"):
+            pass
+        assert not gc.isenabled()
+    finally:
+        gc.enable()
