@@ -995,7 +995,7 @@ class TrainRunner:
         import warnings
         self.capture_failures = getattr(self, "capture_failures", 0) + 1
         self.eng = self.g_fwd = self.g_bwd = self.out = self.grads = None
-        self.static = {}
+        self.static, self.keep = {}, []
         try:
             torch.cuda.synchronize()
         except Exception:
@@ -1004,6 +1004,21 @@ class TrainRunner:
             self.use_graphs = False
         warnings.warn(f"sbgm_danra_b200: CUDA-graph capture of the training step failed ({type(exc).__name__}: {str(exc)[:200]}); "
                       + ("staying on the eager launch sequence" if not self.use_graphs else "this step runs eagerly, capture will be retried"))
+
+    def _backward_capture_failed(self, exc: Exception, inflight: "_InFlight", dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """This step's forward graph has run, its backward could not be captured (and a half-walked tape cannot be resumed):
+        drop both graphs and redo the step on the eager launch sequence from the static inputs -- same gradients; with
+        train-mode BatchNorm the running statistics see this batch twice.  With a gradient exchange attached the ranks would
+        no longer issue the same collectives, so there the failure is raised."""
+        static, sync = self.static, (None if self.eng is None else self.eng.grad_sync)
+        self._capture_failed(exc)
+        inflight.release()
+        if sync is not None and sync.world > 1:
+            raise RuntimeError("sbgm_danra_b200: capturing the backward graph of a data-parallel training step failed; "
+                               "set SBGM_B200_TRAIN_GRAPHS=0 to train on the eager launch sequence") from exc
+        eng = self._engine(sync)
+        eng.forward(*(static[k] for k in ("x", "t", "y", "planes", "inv_std")))
+        return eng.backward(dout)
 
     @staticmethod
     def _copy_in(dst: Optional[torch.Tensor], src: Optional[torch.Tensor]) -> None:
@@ -1060,12 +1075,15 @@ class TrainRunner:
         if kind == "eager":
             return obj.backward(dout)
         if self.g_bwd is None:
-            self.static["dout"] = dout.to(dtype=torch.float32).contiguous().clone()
-            torch.cuda.synchronize()
-            self.g_bwd = torch.cuda.CUDAGraph()
-            with graph_capture(self.g_bwd, pool=self.pool):
-                self.grads = self.eng.backward(self.static["dout"])
-            self.keep.append(self.eng.flat)
+            try:
+                self.static["dout"] = dout.to(dtype=torch.float32).contiguous().clone()
+                torch.cuda.synchronize()
+                self.g_bwd = torch.cuda.CUDAGraph()
+                with graph_capture(self.g_bwd, pool=self.pool):
+                    self.grads = self.eng.backward(self.static["dout"])
+                self.keep.append(self.eng.flat)
+            except Exception as exc:
+                return self._backward_capture_failed(exc, obj, dout)
         else:
             self.static["dout"].copy_(dout)
         self.g_bwd.replay()

@@ -948,6 +948,43 @@ def test_failed_graph_capture_falls_back_to_eager_and_is_retried(monkeypatch):
     assert runner.g_fwd is not None and runner.capture_failures == 1 and runner.use_graphs
 
 
+def test_failed_backward_capture_redoes_the_step_eagerly(monkeypatch):
+    """The forward graph has already run when the backward capture fails: the step is redone on the eager launch sequence from the
+    static inputs (same loss, same gradients, bit for bit), both graphs are dropped and captured again on the next step."""
+    import warnings
+    from oracle.synth import config_for, synth_batch, synth_state_dict
+    from sbgm_danra_b200 import score_sampling, train_engine
+    from sbgm_danra_b200._smoke import build_model
+    from sbgm_danra_b200.score_unet import loss_fn, marginal_prob_std_fn
+    cfg = config_for(n_lr=1)
+    net = build_model(cfg, synth_state_dict(cfg), "bf16", DEV).eval()
+    b = synth_batch(batch=2, size=32, n_lr=1)
+    orig_backward = train_engine.TrainEngine.backward
+    fired = []
+
+    def backward_once_broken(self, dscore):
+        if torch.cuda.is_current_stream_capturing() and not fired:
+            fired.append(1)
+            torch.cuda.synchronize()            # illegal inside a capture: invalidates it and raises
+        return orig_backward(self, dscore)
+
+    monkeypatch.setattr(train_engine.TrainEngine, "backward", backward_once_broken)
+    snaps = []
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        for _ in range(6):
+            score_sampling.manual_seed(11)
+            net.zero_grad(set_to_none=True)
+            loss = loss_fn(net, b.x.to(DEV), marginal_prob_std_fn, cond_img=b.cond_img.to(DEV))
+            loss.backward()
+            snaps.append((float(loss), torch.cat([p.grad.flatten() for p in net.parameters() if p.grad is not None]).clone()))
+    assert fired and any("capture" in str(w.message) for w in caught)
+    for lo, g in snaps[1:]:
+        assert lo == snaps[0][0] and torch.equal(g, snaps[0][1])
+    (runner,) = net.__dict__["_train_runners"].values()
+    assert runner.g_fwd is not None and runner.g_bwd is not None and runner.capture_failures == 1 and not runner.busy
+
+
 def test_dead_cycle_owning_a_cuda_graph_does_not_break_the_next_capture():
     """The root cause of the order-dependent capture failure: an unreachable reference cycle that owns a CUDA graph (an earlier
     model and its runner) is finalised by the cyclic collector at an arbitrary allocation -- inside a capture that is "not
