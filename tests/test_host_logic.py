@@ -327,3 +327,113 @@ def test_graph_capture_pauses_the_cyclic_collector_and_restores_it(monkeypatch):
         assert not gc.isenabled()
     finally:
         gc.enable()
+
+
+class _FakeTrainEngine:
+    """Stands in for train_engine.TrainEngine in the runner's state-machine test: forward = 2x, backward = {"w": 3 dout}."""
+    made = 0
+
+    def __init__(self):
+        type(self).made += 1
+        self.grad_sync, self.tape, self.flat = None, object(), torch.zeros(4)
+        self.tk = type("TK", (), {})()
+        self.forwards = self.backwards = 0
+
+    def _pack(self):
+        pass
+
+    def forward(self, x, t, y, planes, inv_std):
+        self.forwards += 1
+        return 2 * x
+
+    def backward(self, dout):
+        self.backwards += 1
+        return {"w": 3 * dout}
+
+
+def _fake_cuda_graphs(monkeypatch, fail):
+    """CUDA-graph stand-ins on CPU: the capture context runs its body once (or raises when `fail` pops True), replay is a no-op."""
+    import contextlib
+    from sbgm_danra_b200 import train_engine
+
+    class FakeGraph:
+        def replay(self):
+            pass
+
+    @contextlib.contextmanager
+    def fake_capture(graph, **kw):
+        if fail and fail.pop(0):
+            raise RuntimeError("operation failed due to a previous error during capture")
+        yield
+
+    monkeypatch.setattr(train_engine, "graph_capture", fake_capture)
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph_pool_handle", lambda: (0, 0))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    return train_engine
+
+
+def _runner_step(runner, x, sync=None):
+    out, handle = runner.forward(x, None, None, None, None, sync)
+    grads = runner.backward(handle, torch.ones_like(x))
+    return out, grads, handle[0]
+
+
+def test_train_runner_state_machine_and_capture_failures(monkeypatch):
+    """TrainRunner on stand-in graphs: two eager warm-up steps, then capture + replay; a failed forward capture costs one eager
+    step and is retried, three failures switch the runner to eager for good; a failed backward capture redoes the step eagerly,
+    frees both graphs and leaves the runner idle -- and raises when a gradient exchange over more than one rank is attached."""
+    import warnings
+    x = torch.arange(4.0)
+    fail = [False, False]                                  # first capture pair succeeds
+    te = _fake_cuda_graphs(monkeypatch, fail)
+    runner = te.TrainRunner(_FakeTrainEngine)
+    kinds = [_runner_step(runner, x)[2] for _ in range(4)]
+    assert kinds == ["eager", "eager", "graph", "graph"] and runner.g_fwd is not None and runner.g_bwd is not None and not runner.busy
+    out, grads, _ = _runner_step(runner, x)
+    assert torch.equal(out, 2 * x) and torch.equal(grads["w"], 3 * torch.ones(4))
+    # a second forward while a captured step is in flight runs on its own eager engine
+    _, h1 = runner.forward(x, None, None, None, None, None)
+    _, h2 = runner.forward(x, None, None, None, None, None)
+    assert (h1[0], h2[0]) == ("graph", "eager") and runner.busy
+    runner.backward(h2, torch.ones(4))
+    runner.backward(h1, torch.ones(4))
+    assert not runner.busy
+
+    fail[:] = [True, False, False]                         # forward capture fails once, then the pair succeeds
+    runner = te.TrainRunner(_FakeTrainEngine)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        kinds = [_runner_step(runner, x)[2] for _ in range(5)]
+    assert kinds == ["eager", "eager", "eager", "graph", "graph"] and runner.capture_failures == 1 and runner.use_graphs
+    assert any("capture will be retried" in str(w.message) for w in caught)
+
+    fail[:] = [True, True, True]
+    runner = te.TrainRunner(_FakeTrainEngine)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        kinds = [_runner_step(runner, x)[2] for _ in range(7)]
+    assert kinds == ["eager"] * 7 and runner.capture_failures == 3 and not runner.use_graphs and fail == []
+    assert any("staying on the eager launch sequence" in str(w.message) for w in caught)
+
+    fail[:] = [False, True, False, False]                  # forward capture fine, backward capture fails, next step captures both
+    runner = te.TrainRunner(_FakeTrainEngine)
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter("always")
+        res = [_runner_step(runner, x) for _ in range(5)]
+    assert [r[2] for r in res] == ["eager", "eager", "graph", "graph", "graph"] and runner.capture_failures == 1
+    assert all(torch.equal(r[0], 2 * x) and torch.equal(r[1]["w"], 3 * torch.ones(4)) for r in res)
+    assert runner.g_fwd is not None and runner.g_bwd is not None and not runner.busy and fail == []
+
+    class Sync:
+        world, sync_bn, group = 2, False, None
+
+    fail[:] = [False, True]
+    runner = te.TrainRunner(_FakeTrainEngine)
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter("always")
+        _runner_step(runner, x, Sync())
+        _runner_step(runner, x, Sync())
+        with pytest.raises(RuntimeError, match="data-parallel"):
+            _runner_step(runner, x, Sync())
+    assert runner.g_fwd is None and runner.g_bwd is None and not runner.busy
